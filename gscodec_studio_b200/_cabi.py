@@ -1,0 +1,113 @@
+"""ctypes binding of libgsb200.so -- the only door between Python and the CUDA kernels.
+
+Plays the role of ``gsplat/cuda/_backend.py`` (reference: resolves the pybind11 module ``_C``,
+_backend.py:81-139).  There is deliberately NO fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised (the reference raises through TORCH_CHECK, bindings.h:10-16).
+Signatures are the ones declared in ``include/gsb200.h``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsb200.so")
+ABI_VERSION = 1
+
+_P = c_void_p
+_U = c_uint32
+_F = c_float
+_I = c_int
+_L = c_int64
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/gsb200.h
+SIGNATURES = {
+    "gsb200_abi_version": [],
+    "gsb200_last_error": [],
+    "gsb200_launch_count": [],
+    "gsb200_projection_fwd": [_U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _F, _F, _F, _I, _I, _P, _P, _P, _P, _P, _P],
+    "gsb200_projection_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                              _P, _P],
+    "gsb200_compact_count": [_U, _U, _P, _P, _P, _P],
+    "gsb200_compact_fill": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_scatter_rows": [_U, _U, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_sh_fwd": [_U, _U, _U, _P, _P, _P, _P, _P],
+    "gsb200_sh_bwd": [_U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_isect_prepare": [_U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
+    "gsb200_isect_fill": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _L, _P, _P, _P, _P, _P, _P],
+    "gsb200_isect_offset_encode": [_L, _P, _U, _U, _U, _P, _P],
+    "gsb200_rasterize_fwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P],
+    "gsb200_grad_record": [_U],
+    "gsb200_rasterize_bwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P,
+                             _P, _P, _P, _P, _P],
+    "gsb200_fake_quantize_fwd": [_L, _P, _F, _F, _I, _I, _I, _P, c_uint64, c_uint64, _P, _P],
+    "gsb200_fake_quantize_bwd": [_L, _P, _P, _F, _F, _I, _I, _P, _P, _P],
+    "gsb200_entropy_fwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P],
+    "gsb200_entropy_bwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P, _P, _P],
+}
+_RESTYPES = {"gsb200_last_error": c_char_p, "gsb200_launch_count": c_uint64, "gsb200_grad_record": c_uint32}
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libgsb200.so and bind every symbol of include/gsb200.h.  No compute, no GPU needed."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"gscodec_studio_b200: {LIB_PATH} is missing. Build it with "
+            "`python -m gscodec_studio_b200._build` (needs nvcc); there is no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    if lib.gsb200_abi_version() != ABI_VERSION:
+        raise RuntimeError("gscodec_studio_b200: libgsb200.so ABI version mismatch; rebuild the library")
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    return int(load_library().gsb200_launch_count())
+
+
+def stream_ptr(device=None) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    """Device pointer of a contiguous CUDA tensor (NULL for None)."""
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("gscodec_studio_b200: tensor must be a CUDA tensor (the hot path has no CPU implementation)")
+    if not t.is_contiguous():
+        raise RuntimeError("gscodec_studio_b200: tensor must be contiguous")
+    return c_void_p(t.data_ptr())
+
+
+def aligned(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Contiguous and 16-byte aligned version of `t` (a clone only when needed)."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+def call(name: str, *args) -> None:
+    lib = load_library()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.gsb200_last_error()
+        raise RuntimeError(f"{name} failed ({rc}): {msg.decode() if msg else 'unknown error'}")

@@ -1,0 +1,487 @@
+// Stage 3 / 4a: per-tile front-to-back alpha blend, forward and backward (sm_100a).
+//
+// Replaces _C.rasterize_to_pixels_fwd / _bwd (gsplat/cuda/csrc/rasterize_to_pixels_fwd.cu:16-185,
+// rasterize_to_pixels_bwd.cu:17-277).  Per-pixel arithmetic (pixel centre +0.5, sigma expression,
+// __expf, min(0.999), 1/255 cut, exclusive 1e-4 transmittance stop, last_ids, T restored by division
+// in the backward) is the reference's, so the same (pixel, Gaussian) pairs contribute.
+//
+// What is different:
+//   * a 16x16 tile is owned by 8 warps of 8x4 pixels (the reference uses 16x2 strips); each warp
+//     culls the staged Gaussians against ITS pixel rectangle 32 at a time -- lane l tests Gaussian l's
+//     1/255-alpha ellipse bounding box, one ballot, and only survivors are evaluated.  The box is a
+//     conservative superset (margin below), so per-pixel results are unchanged;
+//   * warps stop independently as soon as all of their pixels are saturated (the reference only
+//     stops when the whole tile is);
+//   * colours are staged in shared memory with the geometry (the reference re-reads them from global
+//     memory per pixel in the forward);
+//   * backward: the 9+D per-Gaussian partial gradients of a warp are reduced with a halving butterfly
+//     (8 values in 9 shuffles instead of 8x5) that leaves each total in a different lane, and those
+//     lanes issue ONE coalesced red.global to a packed per-Gaussian gradient record (a single 32-byte
+//     sector for D=3) instead of 9+D scalar atomics to four tensors; an unpack pass then writes the
+//     reference's v_means2d / v_conics / v_colors / v_opacities layout;
+//   * backward skips staging of batches that lie behind every pixel's last contributing Gaussian.
+#include <float.h>
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace gsb200 {
+
+constexpr int kBatch = 256;
+constexpr float kAlphaMax = 0.999f;
+constexpr float kAlphaMin = 1.f / 255.f;
+constexpr float kTStop = 1e-4f;  // reference compares against the double 1e-4; identical set of floats
+
+struct BlendGeom {
+    uint32_t C, W, H, ts, tw, th;
+    int64_t n_isects;
+};
+
+// pixel owned by this thread inside its tile: 8x4 warp blocks for 16x16 tiles, row-major otherwise
+__device__ __forceinline__ void pixel_in_tile(uint32_t ts, uint32_t tid, uint32_t &lx, uint32_t &ly) {
+    if (ts == 16) {
+        const uint32_t w = tid >> 5, l = tid & 31;
+        lx = (w & 1) * 8 + (l & 7);
+        ly = (w >> 1) * 4 + (l >> 3);
+    } else {
+        lx = tid % ts;
+        ly = tid / ts;  // >= ts for the padding threads of a block rounded up to a full warp
+    }
+}
+
+// half extents of the bounding box of { d : 0.5 d^T A d <= ln(255 * opac) } with safety margin;
+// +inf (always evaluate) when the conic is not positive definite, -inf when no pixel can pass.
+__device__ __forceinline__ void cull_extent(float a, float b, float c, float opac, float &hx, float &hy) {
+    const float det = a * c - b * b;
+    const float tau = __logf(255.f * opac);
+    if (!(opac > 0.f) || !(tau >= 0.f)) {
+        if (opac * 255.f >= 1.f) { hx = hy = FLT_MAX; }  // NaN / inf guard: keep
+        else { hx = hy = -FLT_MAX; }
+        return;
+    }
+    if (!(det > 0.f) || !(a > 0.f) || !(c > 0.f)) { hx = hy = FLT_MAX; return; }
+    const float k = 2.f * (tau * 1.001f + 1e-3f) / det;
+    hx = sqrtf(k * c) * 1.001f + 0.05f;
+    hy = sqrtf(k * a) * 1.001f + 0.05f;
+}
+
+template <int CDIM>
+__global__ void __launch_bounds__(kBatch)
+blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
+                 const float *__restrict__ colors, const float *__restrict__ opacities,
+                 const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
+                 const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                 float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
+    extern __shared__ float4 smem4[];
+    const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
+    const uint32_t batch = min(nthreads, (uint32_t)kBatch);
+    float4 *sA = smem4;                               // x, y, opacity, hx
+    float4 *sB = sA + batch;                          // conic a, b, c, hy
+    float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CDIM]
+
+    const uint32_t cam = blockIdx.z, tile_id = blockIdx.y * G.tw + blockIdx.x;
+    uint32_t lx, ly;
+    pixel_in_tile(G.ts, tid, lx, ly);
+    const uint32_t i = blockIdx.y * G.ts + ly, j = blockIdx.x * G.ts + lx;
+    const bool inside = ly < G.ts && i < G.H && j < G.W;
+    const size_t pix = ((size_t)cam * G.H + i) * G.W + j;
+    const float *bg = backgrounds ? backgrounds + (size_t)cam * CDIM : nullptr;
+    const size_t ct = (size_t)cam * G.tw * G.th + tile_id;
+
+    if (masks != nullptr && !masks[ct]) {  // rasterize_to_pixels_fwd.cu:70-76
+        if (inside)
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) render_colors[pix * CDIM + k] = bg ? bg[k] : 0.f;
+        return;
+    }
+    const int32_t range_start = tile_offsets[ct];
+    const int32_t range_end = (cam == G.C - 1 && tile_id == G.tw * G.th - 1) ? (int32_t)G.n_isects : tile_offsets[ct + 1];
+
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const unsigned wmask = 0xffffffffu;  // blocks are launched with whole warps
+    const uint32_t lane = tid & 31;
+    // pixel-centre rectangle of the warp (inside pixels only)
+    const int jmin = __reduce_min_sync(wmask, inside ? (int)j : INT_MAX), jmax = __reduce_max_sync(wmask, inside ? (int)j : -1);
+    const int imin = __reduce_min_sync(wmask, inside ? (int)i : INT_MAX), imax = __reduce_max_sync(wmask, inside ? (int)i : -1);
+    const float wx0 = (float)jmin + 0.5f, wx1 = (float)jmax + 0.5f, wy0 = (float)imin + 0.5f, wy1 = (float)imax + 0.5f;
+
+    float T = 1.f;
+    uint32_t cur_idx = 0;
+    float pix_out[CDIM];
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) pix_out[k] = 0.f;
+    bool done = !inside;
+    bool warp_done = jmax < 0;
+
+    for (int32_t batch_start = range_start; batch_start < range_end; batch_start += (int32_t)batch) {
+        // barrier protects the staging buffers; stop when every pixel of the tile is saturated
+        if (__syncthreads_count(done) >= (int)nthreads) break;
+        const int32_t idx = batch_start + (int32_t)tid;
+        if (tid < batch && idx < range_end) {
+            const int32_t g = flatten_ids[idx];
+            const float2 xy = __ldg(means2d + g);
+            const float opac = __ldg(opacities + g);
+            const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
+                        cc = __ldg(conics + (size_t)g * 3 + 2);
+            float hx, hy;
+            cull_extent(ca, cb, cc, opac, hx, hy);
+            sA[tid] = make_float4(xy.x, xy.y, opac, hx);
+            sB[tid] = make_float4(ca, cb, cc, hy);
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) sC[tid * CDIM + k] = __ldg(colors + (size_t)g * CDIM + k);
+        }
+        __syncthreads();
+        if (warp_done) continue;
+        const uint32_t bsize = min(batch, (uint32_t)(range_end - batch_start));
+        for (uint32_t c0 = 0; c0 < bsize; c0 += 32) {
+            const uint32_t e = c0 + lane;
+            bool hit = false;
+            if (e < bsize) {
+                const float4 A = sA[e];
+                const float hy = sB[e].w;
+                hit = (A.x + A.w >= wx0) && (A.x - A.w <= wx1) && (A.y + hy >= wy0) && (A.y - hy <= wy1);
+            }
+            unsigned m = __ballot_sync(wmask, hit);
+            while (m) {
+                const uint32_t t = c0 + (uint32_t)__ffs(m) - 1u;
+                m &= m - 1;
+                if (!done) {
+                    const float4 A = sA[t];
+                    const float4 B = sB[t];
+                    const float dx = A.x - px, dy = A.y - py;
+                    const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+                    const float alpha = fminf(kAlphaMax, A.z * __expf(-sigma));
+                    if (!(sigma < 0.f || alpha < kAlphaMin)) {
+                        const float next_T = T * (1.f - alpha);
+                        if (next_T <= kTStop) {
+                            done = true;
+                        } else {
+                            const float vis = alpha * T;
+#pragma unroll
+                            for (int k = 0; k < CDIM; ++k) pix_out[k] += sC[t * CDIM + k] * vis;
+                            cur_idx = (uint32_t)batch_start + t;
+                            T = next_T;
+                        }
+                    }
+                }
+            }
+            if (__ballot_sync(wmask, !done) == 0) { warp_done = true; break; }
+        }
+    }
+    if (inside) {
+        render_alphas[pix] = 1.f - T;
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k) render_colors[pix * CDIM + k] = bg ? (pix_out[k] + T * bg[k]) : pix_out[k];
+        last_ids[pix] = (int32_t)cur_idx;
+    }
+}
+
+// ---- warp reductions that leave each of NV totals in a distinct lane group --------------------
+// After reduce_spread<NV>(v): the total of value `slot` is held in v[0] by every lane whose
+// (lane >> shift) & (NV-1), bit-reversed over log2(NV) bits, equals slot -- see spread_slot().
+template <int NV>
+__device__ __forceinline__ void reduce_spread(float *v, uint32_t lane) {
+    // halving steps: partner distance 16, 8, ... while more than one value is alive
+    int alive = NV;
+    int dist = 16;
+#pragma unroll
+    for (; alive > 1; alive >>= 1, dist >>= 1) {
+        const bool upper = (lane & dist) != 0;
+        const int half = alive >> 1;
+#pragma unroll
+        for (int q = 0; q < half; ++q) {
+            const float keep = upper ? v[half + q] : v[q];
+            const float send = upper ? v[q] : v[half + q];
+            v[q] = keep + __shfl_xor_sync(0xffffffffu, send, dist);
+        }
+    }
+#pragma unroll
+    for (; dist > 0; dist >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], dist);
+}
+// value slot held by `lane` after reduce_spread<NV>
+template <int NV>
+__device__ __forceinline__ uint32_t spread_slot(uint32_t lane) {
+    uint32_t slot = 0, alive = NV, dist = 16;
+    for (; alive > 1; alive >>= 1, dist >>= 1) slot += (lane & dist) ? (alive >> 1) : 0;
+    return slot;
+}
+
+// packed gradient record (floats): [rgb(CDIM) | conic(3) | xy(2) | opac(1) | abs(2)] rounded up to 4
+__host__ __device__ constexpr uint32_t grad_record(uint32_t cdim) { return (cdim + 8 + 3) / 4 * 4; }
+
+template <int CDIM>
+__global__ void __launch_bounds__(kBatch)
+blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
+                 const float *__restrict__ colors, const float *__restrict__ opacities,
+                 const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
+                 const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                 const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
+                 const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas, bool absgrad,
+                 float *__restrict__ grad_rec) {
+    constexpr uint32_t REC = grad_record(CDIM);
+    constexpr int NVAL = CDIM + 8;          // rgb, conic, xy, opac, abs
+    constexpr int NGRP = (NVAL + 7) / 8;    // groups of 8 values, each reduced with reduce_spread<8>
+    extern __shared__ float4 smem4[];
+    __shared__ int s_binmax;
+    const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
+    const uint32_t batch = min(nthreads, (uint32_t)kBatch);
+    float4 *sA = smem4;                                 // x, y, opacity, hx
+    float4 *sB = sA + batch;                            // conic a, b, c, hy
+    float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CDIM]
+    int32_t *sId = reinterpret_cast<int32_t *>(sC + batch * CDIM);
+
+    const uint32_t cam = blockIdx.z, tile_id = blockIdx.y * G.tw + blockIdx.x;
+    const size_t ct = (size_t)cam * G.tw * G.th + tile_id;
+    if (masks != nullptr && !masks[ct]) return;
+    uint32_t lx, ly;
+    pixel_in_tile(G.ts, tid, lx, ly);
+    const uint32_t i = blockIdx.y * G.ts + ly, j = blockIdx.x * G.ts + lx;
+    const bool inside = ly < G.ts && i < G.H && j < G.W;
+    const size_t pix = inside ? ((size_t)cam * G.H + i) * G.W + j : 0;
+    const float *bg = backgrounds ? backgrounds + (size_t)cam * CDIM : nullptr;
+    const int32_t range_start = tile_offsets[ct];
+    int32_t range_end = (cam == G.C - 1 && tile_id == G.tw * G.th - 1) ? (int32_t)G.n_isects : tile_offsets[ct + 1];
+
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const unsigned wmask = 0xffffffffu;  // blocks are launched with whole warps
+    const uint32_t lane = tid & 31;
+    const int jmin = __reduce_min_sync(wmask, inside ? (int)j : INT_MAX), jmax = __reduce_max_sync(wmask, inside ? (int)j : -1);
+    const int imin = __reduce_min_sync(wmask, inside ? (int)i : INT_MAX), imax = __reduce_max_sync(wmask, inside ? (int)i : -1);
+    const float wx0 = (float)jmin + 0.5f, wx1 = (float)jmax + 0.5f, wy0 = (float)imin + 0.5f, wy1 = (float)imax + 0.5f;
+
+    const float T_final = inside ? 1.f - render_alphas[pix] : 1.f;
+    float T = T_final;
+    float buffer[CDIM], v_c[CDIM];
+    float bg_dot = 0.f;  // sum_k bg_k * v_render_c_k
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) {
+        buffer[k] = 0.f;
+        v_c[k] = inside ? v_render_colors[pix * CDIM + k] : 0.f;
+        if (bg) bg_dot += bg[k] * v_c[k];
+    }
+    const float v_a = inside ? v_render_alphas[pix] : 0.f;
+    const int32_t bin_final = inside ? last_ids[pix] : -1;
+    const int32_t warp_bin_final = __reduce_max_sync(wmask, bin_final);
+
+    // tile-wide last contributing index: nothing behind it needs staging
+    if (tid == 0) s_binmax = -1;
+    __syncthreads();
+    if (lane == 0) atomicMax(&s_binmax, warp_bin_final);
+    __syncthreads();
+    range_end = min(range_end, s_binmax + 1);
+
+    // lanes that publish totals: group gi, value slot -> record offset
+    const bool publisher = (lane & 3) == 0;
+    const uint32_t slot8 = spread_slot<8>(lane);
+
+    for (int32_t batch_end = range_end - 1; batch_end >= range_start; batch_end -= (int32_t)batch) {
+        __syncthreads();
+        const int32_t bsize = min((int32_t)batch, batch_end + 1 - range_start);
+        if ((int32_t)tid < bsize) {
+            const int32_t g = flatten_ids[batch_end - (int32_t)tid];
+            const float2 xy = __ldg(means2d + g);
+            const float opac = __ldg(opacities + g);
+            const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
+                        cc = __ldg(conics + (size_t)g * 3 + 2);
+            float hx, hy;
+            cull_extent(ca, cb, cc, opac, hx, hy);
+            sA[tid] = make_float4(xy.x, xy.y, opac, hx);
+            sB[tid] = make_float4(ca, cb, cc, hy);
+            sId[tid] = g;
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) sC[tid * CDIM + k] = __ldg(colors + (size_t)g * CDIM + k);
+        }
+        __syncthreads();
+        if (warp_bin_final < 0) continue;
+        // entry t <-> sorted index batch_end - t ; start at the warp's last contributing Gaussian
+        const int32_t t_first = max(0, batch_end - warp_bin_final);
+        for (int32_t c0 = t_first; c0 < bsize; c0 += 32) {
+            const int32_t e = c0 + (int32_t)lane;
+            bool hit = false;
+            if (e < bsize) {
+                const float4 A = sA[e];
+                const float hy = sB[e].w;
+                hit = (A.x + A.w >= wx0) && (A.x - A.w <= wx1) && (A.y + hy >= wy0) && (A.y - hy <= wy1);
+            }
+            unsigned m = __ballot_sync(wmask, hit);
+            while (m) {
+                const int32_t t = c0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 A = sA[t];
+                const float4 B = sB[t];
+                const float dx = A.x - px, dy = A.y - py;
+                const float opac = A.z;
+                const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
+                const float vis = __expf(-sigma);
+                const float alpha = fminf(kAlphaMax, opac * vis);
+                const bool valid = inside && (batch_end - t <= bin_final) && !(sigma < 0.f || alpha < kAlphaMin);
+                if (!__any_sync(wmask, valid)) continue;
+                float vals[NGRP * 8];
+#pragma unroll
+                for (int k = 0; k < NGRP * 8; ++k) vals[k] = 0.f;
+                if (valid) {
+                    const float ra = 1.f / (1.f - alpha);
+                    T *= ra;
+                    const float fac = alpha * T;
+                    float v_alpha = 0.f;
+#pragma unroll
+                    for (int k = 0; k < CDIM; ++k) {
+                        const float ck = sC[t * CDIM + k];
+                        vals[k] = fac * v_c[k];
+                        v_alpha += (ck * T - buffer[k] * ra) * v_c[k];
+                        buffer[k] += ck * fac;
+                    }
+                    v_alpha += T_final * ra * v_a;
+                    if (bg) v_alpha += -T_final * ra * bg_dot;
+                    if (opac * vis <= kAlphaMax) {
+                        const float v_sigma = -opac * vis * v_alpha;
+                        vals[CDIM + 0] = 0.5f * v_sigma * dx * dx;
+                        vals[CDIM + 1] = v_sigma * dx * dy;
+                        vals[CDIM + 2] = 0.5f * v_sigma * dy * dy;
+                        const float gx = v_sigma * (B.x * dx + B.y * dy);
+                        const float gy = v_sigma * (B.y * dx + B.z * dy);
+                        vals[CDIM + 3] = gx;
+                        vals[CDIM + 4] = gy;
+                        vals[CDIM + 5] = vis * v_alpha;
+                        vals[CDIM + 6] = fabsf(gx);
+                        vals[CDIM + 7] = fabsf(gy);
+                    }
+                }
+                float *rec = grad_rec + (size_t)sId[t] * REC;
+#pragma unroll
+                for (int gi = 0; gi < NGRP; ++gi) {
+                    reduce_spread<8>(vals + gi * 8, lane);
+                    const uint32_t off = gi * 8 + slot8;
+                    // skip padding slots and, unless requested, the abs-gradient slots
+                    const bool live = off < (uint32_t)NVAL && (absgrad || off < (uint32_t)(CDIM + 6));
+                    if (publisher && live) red_add(rec + off, vals[gi * 8]);
+                }
+            }
+        }
+    }
+}
+
+// packed gradient records -> the reference's tensors
+template <int CDIM>
+__global__ void __launch_bounds__(kThreads)
+unpack_grads_kernel(uint32_t M, const float *__restrict__ rec, float *__restrict__ v_abs, float *__restrict__ v_means2d,
+                    float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opac) {
+    constexpr uint32_t REC = grad_record(CDIM);
+    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
+    if (g >= M) return;
+    float r[REC];
+#pragma unroll
+    for (uint32_t k = 0; k < REC; k += 4) {
+        const float4 v = ldg4(rec + (size_t)g * REC + k);
+        r[k] = v.x; r[k + 1] = v.y; r[k + 2] = v.z; r[k + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) v_colors[(size_t)g * CDIM + k] = r[k];
+    v_conics[(size_t)g * 3] = r[CDIM]; v_conics[(size_t)g * 3 + 1] = r[CDIM + 1]; v_conics[(size_t)g * 3 + 2] = r[CDIM + 2];
+    *reinterpret_cast<float2 *>(v_means2d + (size_t)g * 2) = make_float2(r[CDIM + 3], r[CDIM + 4]);
+    v_opac[g] = r[CDIM + 5];
+    if (v_abs != nullptr) *reinterpret_cast<float2 *>(v_abs + (size_t)g * 2) = make_float2(r[CDIM + 6], r[CDIM + 7]);
+}
+
+template <int CDIM>
+static int launch_fwd(const BlendGeom &G, const float *means2d, const float *conics, const float *colors,
+                      const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
+                      const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
+                      cudaStream_t s) {
+    const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
+    const uint32_t batch = nthreads;
+    const size_t smem = (size_t)batch * (32 + 4 * CDIM);
+    if (smem > 48 * 1024)
+        GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(G.tw, G.th, G.C);
+    blend_fwd_kernel<CDIM><<<grid, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
+                                                         opacities, backgrounds, masks, tile_offsets, flatten_ids,
+                                                         render_colors, render_alphas, last_ids);
+    return check_launch("blend_fwd");
+}
+
+template <int CDIM>
+static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, const float *conics, const float *colors,
+                      const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
+                      const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
+                      const float *v_render_colors, const float *v_render_alphas, float *grad_scratch, float *v_abs,
+                      float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t s) {
+    const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
+    const uint32_t batch = nthreads;
+    const size_t smem = (size_t)batch * (32 + 4 * CDIM + 4);
+    if (smem > 48 * 1024)
+        GSB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_CUDA_OK(cudaMemsetAsync(grad_scratch, 0, sizeof(float) * (size_t)M * grad_record(CDIM), s));
+    if (G.n_isects > 0) {
+        dim3 grid(G.tw, G.th, G.C);
+        blend_bwd_kernel<CDIM><<<grid, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
+                                                             opacities, backgrounds, masks, tile_offsets, flatten_ids,
+                                                             render_alphas, last_ids, v_render_colors, v_render_alphas,
+                                                             v_abs != nullptr, grad_scratch);
+        if (int e = check_launch("blend_bwd")) return e;
+    }
+    unpack_grads_kernel<CDIM><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors,
+                                                                      v_opacities);
+    return check_launch("unpack_grads");
+}
+
+}  // namespace gsb200
+
+using namespace gsb200;
+
+#define GSB_DISPATCH_CDIM(D, CALL)                                                                 \
+    switch (D) {                                                                                   \
+        case 1: { constexpr int CD = 1; return CALL; }                                             \
+        case 2: { constexpr int CD = 2; return CALL; }                                             \
+        case 3: { constexpr int CD = 3; return CALL; }                                             \
+        case 4: { constexpr int CD = 4; return CALL; }                                             \
+        case 5: { constexpr int CD = 5; return CALL; }                                             \
+        case 8: { constexpr int CD = 8; return CALL; }                                             \
+        case 9: { constexpr int CD = 9; return CALL; }                                             \
+        case 16: { constexpr int CD = 16; return CALL; }                                           \
+        case 17: { constexpr int CD = 17; return CALL; }                                           \
+        case 32: { constexpr int CD = 32; return CALL; }                                           \
+        case 33: { constexpr int CD = 33; return CALL; }                                           \
+        default: return fail(2, "gsb200_rasterize: unsupported number of channels");               \
+    }
+
+extern "C" uint32_t gsb200_grad_record(uint32_t D) { return grad_record(D); }
+
+static int check_geom(uint32_t tile_size, uint32_t W, uint32_t H, uint32_t tw, uint32_t th) {
+    if (tile_size == 0 || tile_size > 16) return fail(2, "gsb200_rasterize: tile_size must be in [1, 16]");
+    if (tw * tile_size < W || th * tile_size < H)
+        return fail(2, "gsb200_rasterize: tile grid does not cover the image (Assert Failed: tile_height * tile_size >= image_height)");
+    return 0;
+}
+
+extern "C" int gsb200_rasterize_fwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
+                                    const float *conics, const float *colors, const float *opacities,
+                                    const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_size,
+                                    uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
+                                    const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
+                                    gsb200_stream_t stream) {
+    (void)M;
+    if (int e = check_geom(tile_size, W, H, tile_width, tile_height)) return e;
+    if (C == 0 || W == 0 || H == 0) return 0;
+    BlendGeom G{C, W, H, tile_size, tile_width, tile_height, n_isects};
+    cudaStream_t s = (cudaStream_t)stream;
+    GSB_DISPATCH_CDIM(D, (launch_fwd<CD>(G, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
+                                         render_colors, render_alphas, last_ids, s)));
+}
+
+extern "C" int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
+                                    const float *conics, const float *colors, const float *opacities,
+                                    const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_size,
+                                    uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
+                                    const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
+                                    const float *v_render_colors, const float *v_render_alphas, float *grad_scratch,
+                                    float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                                    gsb200_stream_t stream) {
+    if (int e = check_geom(tile_size, W, H, tile_width, tile_height)) return e;
+    if (M == 0) return 0;
+    BlendGeom G{C, W, H, tile_size, tile_width, tile_height, n_isects};
+    cudaStream_t s = (cudaStream_t)stream;
+    GSB_DISPATCH_CDIM(D, (launch_bwd<CD>(G, M, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets,
+                                         flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch,
+                                         v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s)));
+}

@@ -1,0 +1,603 @@
+// Stage 1 / 4b: fused 3D->2D projection of Gaussians, forward and backward (sm_100a).
+//
+// Behaviour follows the reference ops _C.fully_fused_projection_{fwd,bwd}
+// (gsplat/cuda/csrc/fully_fused_projection_fwd.cu:22-196, fully_fused_projection_bwd.cu:24-263 and the
+// device math in gsplat/cuda/include/{quat,transform,proj,utils,quat_scale_to_covar_preci}.cuh).
+//
+// Design differences (B200-first, not a translation):
+//   * one thread owns one Gaussian and loops over the C cameras: the 40 B of Gaussian parameters
+//     and the quaternion -> covariance work are read / done once instead of C times, and the
+//     backward needs NO atomics and no warp-group partitions -- the sum over cameras is a register
+//     accumulation followed by one plain store (deterministic);
+//   * camera matrices live in shared memory (the reference re-reads them from global per thread);
+//   * [N,3] arrays are moved with 128-bit loads through a shared-memory transpose;
+//   * culled entries are zero-filled, so downstream consumers never see uninitialised memory;
+//   * v_viewmats is block-reduced in shared memory, one atomic set per block and camera.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace gsb200 {
+
+struct Sym3 { float xx, xy, xz, yy, yz, zz; };
+struct Mat3 { float m[3][3]; };  // row-major
+
+__device__ __forceinline__ Mat3 quat_to_rot(float w, float x, float y, float z, float *inv_norm_out) {
+    float inv_norm = rsqrtf(x * x + y * y + z * z + w * w);
+    x *= inv_norm; y *= inv_norm; z *= inv_norm; w *= inv_norm;
+    if (inv_norm_out) *inv_norm_out = inv_norm;
+    float x2 = x * x, y2 = y * y, z2 = z * z;
+    float xy = x * y, xz = x * z, yz = y * z;
+    float wx = w * x, wy = w * y, wz = w * z;
+    Mat3 R;
+    R.m[0][0] = 1.f - 2.f * (y2 + z2); R.m[0][1] = 2.f * (xy - wz); R.m[0][2] = 2.f * (xz + wy);
+    R.m[1][0] = 2.f * (xy + wz); R.m[1][1] = 1.f - 2.f * (x2 + z2); R.m[1][2] = 2.f * (yz - wx);
+    R.m[2][0] = 2.f * (xz - wy); R.m[2][1] = 2.f * (yz + wx); R.m[2][2] = 1.f - 2.f * (x2 + y2);
+    return R;
+}
+
+// Sigma = (Rq diag(s)) (Rq diag(s))^T
+__device__ __forceinline__ Sym3 covar_from_quat_scale(const Mat3 &Rq, float sx, float sy, float sz) {
+    float M[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { M[i][0] = Rq.m[i][0] * sx; M[i][1] = Rq.m[i][1] * sy; M[i][2] = Rq.m[i][2] * sz; }
+    Sym3 S;
+    S.xx = M[0][0] * M[0][0] + M[0][1] * M[0][1] + M[0][2] * M[0][2];
+    S.xy = M[0][0] * M[1][0] + M[0][1] * M[1][1] + M[0][2] * M[1][2];
+    S.xz = M[0][0] * M[2][0] + M[0][1] * M[2][1] + M[0][2] * M[2][2];
+    S.yy = M[1][0] * M[1][0] + M[1][1] * M[1][1] + M[1][2] * M[1][2];
+    S.yz = M[1][0] * M[2][0] + M[1][1] * M[2][1] + M[1][2] * M[2][2];
+    S.zz = M[2][0] * M[2][0] + M[2][1] * M[2][1] + M[2][2] * M[2][2];
+    return S;
+}
+
+// Sigma_c = R Sigma R^T, association (R Sigma) R^T as in transform.cuh:40-49
+__device__ __forceinline__ Sym3 covar_to_cam(const float *R /*3x4 rows*/, const Sym3 &S) {
+    float A[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float r0 = R[i * 4 + 0], r1 = R[i * 4 + 1], r2 = R[i * 4 + 2];
+        A[i][0] = r0 * S.xx + r1 * S.xy + r2 * S.xz;
+        A[i][1] = r0 * S.xy + r1 * S.yy + r2 * S.yz;
+        A[i][2] = r0 * S.xz + r1 * S.yz + r2 * S.zz;
+    }
+    Sym3 O;
+    O.xx = A[0][0] * R[0] + A[0][1] * R[1] + A[0][2] * R[2];
+    O.xy = A[0][0] * R[4] + A[0][1] * R[5] + A[0][2] * R[6];
+    O.xz = A[0][0] * R[8] + A[0][1] * R[9] + A[0][2] * R[10];
+    O.yy = A[1][0] * R[4] + A[1][1] * R[5] + A[1][2] * R[6];
+    O.yz = A[1][0] * R[8] + A[1][1] * R[9] + A[1][2] * R[10];
+    O.zz = A[2][0] * R[8] + A[2][1] * R[9] + A[2][2] * R[10];
+    return O;
+}
+
+struct CamProj {
+    float J[2][3];
+    float mx, my;
+    float tx, ty, rz;     // pinhole only
+    bool clip_x, clip_y;  // pinhole only: x/z (y/z) was clamped to the fov limits
+};
+
+// Jacobian of the camera projection and projected mean (proj.cuh:9-36, 80-119)
+__device__ __forceinline__ CamProj project_point(int model, float x, float y, float z, float fx, float fy,
+                                                 float cx, float cy, float W, float H) {
+    CamProj P;
+    P.clip_x = P.clip_y = false;
+    P.tx = P.ty = 0.f; P.rz = 0.f;
+    if (model == GSB200_CAMERA_PINHOLE) {
+        float tan_fovx = 0.5f * W / fx, tan_fovy = 0.5f * H / fy;
+        float lim_x_pos = (W - cx) / fx + 0.3f * tan_fovx, lim_x_neg = cx / fx + 0.3f * tan_fovx;
+        float lim_y_pos = (H - cy) / fy + 0.3f * tan_fovy, lim_y_neg = cy / fy + 0.3f * tan_fovy;
+        float rz = 1.f / z, rz2 = rz * rz;
+        float xz = x * rz, yz = y * rz;
+        float tx = z * fminf(lim_x_pos, fmaxf(-lim_x_neg, xz));
+        float ty = z * fminf(lim_y_pos, fmaxf(-lim_y_neg, yz));
+        P.clip_x = !(xz <= lim_x_pos && xz >= -lim_x_neg);
+        P.clip_y = !(yz <= lim_y_pos && yz >= -lim_y_neg);
+        P.J[0][0] = fx * rz; P.J[0][1] = 0.f; P.J[0][2] = -fx * tx * rz2;
+        P.J[1][0] = 0.f; P.J[1][1] = fy * rz; P.J[1][2] = -fy * ty * rz2;
+        P.mx = fx * x * rz + cx; P.my = fy * y * rz + cy;
+        P.tx = tx; P.ty = ty; P.rz = rz;
+    } else {  // ORTHO
+        P.J[0][0] = fx; P.J[0][1] = 0.f; P.J[0][2] = 0.f;
+        P.J[1][0] = 0.f; P.J[1][1] = fy; P.J[1][2] = 0.f;
+        P.mx = fx * x + cx; P.my = fy * y + cy;
+    }
+    return P;
+}
+
+// cov2d = (J Sigma_c) J^T -> (c00, c01, c11)
+__device__ __forceinline__ void project_covar(const CamProj &P, const Sym3 &S, float &c00, float &c01, float &c11) {
+    float B00 = P.J[0][0] * S.xx + P.J[0][1] * S.xy + P.J[0][2] * S.xz;
+    float B01 = P.J[0][0] * S.xy + P.J[0][1] * S.yy + P.J[0][2] * S.yz;
+    float B02 = P.J[0][0] * S.xz + P.J[0][1] * S.yz + P.J[0][2] * S.zz;
+    float B10 = P.J[1][0] * S.xx + P.J[1][1] * S.xy + P.J[1][2] * S.xz;
+    float B11 = P.J[1][0] * S.xy + P.J[1][1] * S.yy + P.J[1][2] * S.yz;
+    float B12 = P.J[1][0] * S.xz + P.J[1][1] * S.yz + P.J[1][2] * S.zz;
+    c00 = B00 * P.J[0][0] + B01 * P.J[0][1] + B02 * P.J[0][2];
+    c01 = B00 * P.J[1][0] + B01 * P.J[1][1] + B02 * P.J[1][2];
+    c11 = B10 * P.J[1][0] + B11 * P.J[1][1] + B12 * P.J[1][2];
+}
+
+// cooperative 128-bit load of a block's [kThreads,3] slice into shared memory
+__device__ __forceinline__ void load_vec3_block(const float *__restrict__ src, uint32_t first, uint32_t n_total,
+                                                float *smem /*kThreads*3*/) {
+    const uint32_t base = first * 3;
+    const uint32_t total = n_total * 3;
+    // base is a multiple of 3*kThreads floats = 3072 B, so 16-byte aligned
+    for (uint32_t i = threadIdx.x * 4; i < kThreads * 3; i += blockDim.x * 4) {
+        if (base + i + 3 < total) {
+            float4 v = ldg4(src + base + i);
+            smem[i] = v.x; smem[i + 1] = v.y; smem[i + 2] = v.z; smem[i + 3] = v.w;
+        } else {
+            for (uint32_t k = 0; k < 4; ++k)
+                if (base + i + k < total) smem[i + k] = __ldg(src + base + i + k);
+        }
+    }
+}
+
+constexpr int kMaxSmemCams = 64;  // cameras cached in shared memory per pass
+
+__global__ void __launch_bounds__(kThreads)
+projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
+                      const float *__restrict__ quats, const float *__restrict__ scales,
+                      const float *__restrict__ viewmats, const float *__restrict__ Ks, float W, float H,
+                      float eps2d, float near_plane, float far_plane, float radius_clip, int model,
+                      int packed_rule, int32_t *__restrict__ radii, float *__restrict__ means2d,
+                      float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ comps) {
+    __shared__ float s_vm[kMaxSmemCams][12];
+    __shared__ float s_k[kMaxSmemCams][4];
+    __shared__ float s_a[kThreads * 3];
+    __shared__ float s_b[kThreads * 3];
+    const uint32_t first = blockIdx.x * kThreads;
+    const uint32_t g = first + threadIdx.x;
+    load_vec3_block(means, first, N, s_a);
+    if (covars == nullptr) load_vec3_block(scales, first, N, s_b);
+    __syncthreads();
+    float px = 0.f, py = 0.f, pz = 0.f;
+    Sym3 S = {0, 0, 0, 0, 0, 0};
+    if (g < N) {
+        px = s_a[threadIdx.x * 3]; py = s_a[threadIdx.x * 3 + 1]; pz = s_a[threadIdx.x * 3 + 2];
+        if (covars != nullptr) {
+            const float *c = covars + (size_t)g * 6;
+            S.xx = c[0]; S.xy = c[1]; S.xz = c[2]; S.yy = c[3]; S.yz = c[4]; S.zz = c[5];
+        } else {
+            float4 q = ldg4(quats + (size_t)g * 4);
+            Mat3 Rq = quat_to_rot(q.x, q.y, q.z, q.w, nullptr);
+            S = covar_from_quat_scale(Rq, s_b[threadIdx.x * 3], s_b[threadIdx.x * 3 + 1], s_b[threadIdx.x * 3 + 2]);
+        }
+    }
+    for (uint32_t c0 = 0; c0 < C; c0 += kMaxSmemCams) {
+        const uint32_t nc = min((uint32_t)kMaxSmemCams, C - c0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nc * 12; i += blockDim.x) s_vm[i / 12][i % 12] = viewmats[(size_t)(c0 + i / 12) * 16 + i % 12];
+        for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+            const float *K = Ks + (size_t)(c0 + i) * 9;
+            s_k[i][0] = K[0]; s_k[i][1] = K[4]; s_k[i][2] = K[2]; s_k[i][3] = K[5];
+        }
+        __syncthreads();
+        if (g >= N) continue;
+        for (uint32_t ci = 0; ci < nc; ++ci) {
+            const float *R = s_vm[ci];
+            const size_t idx = (size_t)(c0 + ci) * N + g;
+            float mx = R[0] * px + R[1] * py + R[2] * pz + R[3];
+            float my = R[4] * px + R[5] * py + R[6] * pz + R[7];
+            float mz = R[8] * px + R[9] * py + R[10] * pz + R[11];
+            int32_t rad = 0;
+            float o_mx = 0.f, o_my = 0.f, o_d = 0.f, o_a = 0.f, o_b = 0.f, o_c = 0.f, o_comp = 0.f;
+            if (!(mz < near_plane || mz > far_plane)) {
+                Sym3 Sc = covar_to_cam(R, S);
+                CamProj P = project_point(model, mx, my, mz, s_k[ci][0], s_k[ci][1], s_k[ci][2], s_k[ci][3], W, H);
+                float c00, c01, c11;
+                project_covar(P, Sc, c00, c01, c11);
+                float det_orig = c00 * c11 - c01 * c01;
+                c00 += eps2d; c11 += eps2d;
+                float det = c00 * c11 - c01 * c01;
+                float compensation = sqrtf(fmaxf(0.f, det_orig / det));
+                if (det > 0.f) {
+                    float inv_det = 1.f / det;
+                    float b = 0.5f * (c00 + c11);
+                    float radius;
+                    if (packed_rule) {
+                        float s = sqrtf(fmaxf(0.1f, b * b - det));
+                        radius = ceilf(3.f * sqrtf(fmaxf(b + s, b - s)));
+                    } else {
+                        float v1 = b + sqrtf(fmaxf(0.01f, b * b - det));
+                        radius = ceilf(3.f * sqrtf(v1));
+                    }
+                    bool ok = !(radius <= radius_clip);
+                    ok = ok && !(P.mx + radius <= 0 || P.mx - radius >= W || P.my + radius <= 0 || P.my - radius >= H);
+                    if (ok) {
+                        rad = (int32_t)radius;
+                        o_mx = P.mx; o_my = P.my; o_d = mz;
+                        o_a = c11 * inv_det; o_b = -c01 * inv_det; o_c = c00 * inv_det;
+                        o_comp = compensation;
+                    }
+                }
+            }
+            radii[idx] = rad;
+            *reinterpret_cast<float2 *>(means2d + idx * 2) = make_float2(o_mx, o_my);
+            depths[idx] = o_d;
+            conics[idx * 3] = o_a; conics[idx * 3 + 1] = o_b; conics[idx * 3 + 2] = o_c;
+            if (comps != nullptr) comps[idx] = o_comp;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
+                      const float *__restrict__ quats, const float *__restrict__ scales,
+                      const float *__restrict__ viewmats, const float *__restrict__ Ks, float W, float H,
+                      float eps2d, int model, const int32_t *__restrict__ radii, const float *__restrict__ conics,
+                      const float *__restrict__ comps, const float *__restrict__ v_means2d,
+                      const float *__restrict__ v_depths, const float *__restrict__ v_conics,
+                      const float *__restrict__ v_comps, float *__restrict__ v_means, float *__restrict__ v_covars,
+                      float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_viewmats) {
+    __shared__ float s_vm[kMaxSmemCams][12];
+    __shared__ float s_k[kMaxSmemCams][4];
+    __shared__ float s_a[kThreads * 3];
+    __shared__ float s_b[kThreads * 3];
+    __shared__ float s_red[kThreads / 32][12];
+    const uint32_t first = blockIdx.x * kThreads;
+    const uint32_t g = first + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    load_vec3_block(means, first, N, s_a);
+    if (covars == nullptr) load_vec3_block(scales, first, N, s_b);
+    __syncthreads();
+    float px = 0.f, py = 0.f, pz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    Sym3 S = {0, 0, 0, 0, 0, 0};
+    Mat3 Rq;
+    float inv_norm = 1.f;
+    if (g < N) {
+        px = s_a[threadIdx.x * 3]; py = s_a[threadIdx.x * 3 + 1]; pz = s_a[threadIdx.x * 3 + 2];
+        if (covars != nullptr) {
+            const float *c = covars + (size_t)g * 6;
+            S.xx = c[0]; S.xy = c[1]; S.xz = c[2]; S.yy = c[3]; S.yz = c[4]; S.zz = c[5];
+        } else {
+            q = ldg4(quats + (size_t)g * 4);
+            sx = s_b[threadIdx.x * 3]; sy = s_b[threadIdx.x * 3 + 1]; sz = s_b[threadIdx.x * 3 + 2];
+            Rq = quat_to_rot(q.x, q.y, q.z, q.w, &inv_norm);
+            S = covar_from_quat_scale(Rq, sx, sy, sz);
+        }
+    }
+    float vmean[3] = {0.f, 0.f, 0.f};
+    float vS[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};  // full (non-symmetrised) v_Sigma
+    for (uint32_t c0 = 0; c0 < C; c0 += kMaxSmemCams) {
+        const uint32_t nc = min((uint32_t)kMaxSmemCams, C - c0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nc * 12; i += blockDim.x) s_vm[i / 12][i % 12] = viewmats[(size_t)(c0 + i / 12) * 16 + i % 12];
+        for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+            const float *K = Ks + (size_t)(c0 + i) * 9;
+            s_k[i][0] = K[0]; s_k[i][1] = K[4]; s_k[i][2] = K[2]; s_k[i][3] = K[5];
+        }
+        __syncthreads();
+        for (uint32_t ci = 0; ci < nc; ++ci) {
+            const float *R = s_vm[ci];
+            const size_t idx = (size_t)(c0 + ci) * N + g;
+            float vR[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+            float vt[3] = {0.f, 0.f, 0.f};
+            const bool active = (g < N) && radii[idx] > 0;
+            if (active) {
+                const float ca = conics[idx * 3], cb = conics[idx * 3 + 1], cc = conics[idx * 3 + 2];
+                const float va = v_conics[idx * 3], vb = 0.5f * v_conics[idx * 3 + 1], vc = v_conics[idx * 3 + 2];
+                // v_cov2d = -Cn V Cn  (utils.cuh:24-29)
+                float t00 = ca * va + cb * vb, t01 = ca * vb + cb * vc;
+                float t10 = cb * va + cc * vb, t11 = cb * vb + cc * vc;
+                float G00 = -(t00 * ca + t01 * cb), G01 = -(t00 * cb + t01 * cc);
+                float G10 = -(t10 * ca + t11 * cb), G11 = -(t10 * cb + t11 * cc);
+                if (v_comps != nullptr) {  // utils.cuh:42-73
+                    const float comp = comps[idx], v_comp = v_comps[idx];
+                    float det_conic = ca * cc - cb * cb;
+                    float v_sqr = v_comp * 0.5f / (comp + 1e-6f);
+                    float omc = 1.f - comp * comp;
+                    G00 += v_sqr * (omc * ca - eps2d * det_conic);
+                    G01 += v_sqr * (omc * cb);
+                    G10 += v_sqr * (omc * cb);
+                    G11 += v_sqr * (omc * cc - eps2d * det_conic);
+                }
+                float mx = R[0] * px + R[1] * py + R[2] * pz + R[3];
+                float my = R[4] * px + R[5] * py + R[6] * pz + R[7];
+                float mz = R[8] * px + R[9] * py + R[10] * pz + R[11];
+                Sym3 Sc = covar_to_cam(R, S);
+                const float fx = s_k[ci][0], fy = s_k[ci][1];
+                CamProj P = project_point(model, mx, my, mz, fx, fy, s_k[ci][2], s_k[ci][3], W, H);
+                const float vm0 = v_means2d[idx * 2], vm1 = v_means2d[idx * 2 + 1];
+                // v_Sigma_c = J^T G J
+                float GJ[2][3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    GJ[0][j] = G00 * P.J[0][j] + G01 * P.J[1][j];
+                    GJ[1][j] = G10 * P.J[0][j] + G11 * P.J[1][j];
+                }
+                float vSc[3][3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) vSc[i][j] = P.J[0][i] * GJ[0][j] + P.J[1][i] * GJ[1][j];
+                float vmc[3];
+                if (model == GSB200_CAMERA_PINHOLE) {
+                    const float rz = P.rz, rz2 = rz * rz, rz3 = rz2 * rz;
+                    vmc[0] = fx * rz * vm0;
+                    vmc[1] = fy * rz * vm1;
+                    vmc[2] = -(fx * mx * vm0 + fy * my * vm1) * rz2;
+                    // v_J = G J Sigma_c^T + G^T J Sigma_c  (only the entries the pinhole Jacobian depends on)
+                    float ScM[3][3] = {{Sc.xx, Sc.xy, Sc.xz}, {Sc.xy, Sc.yy, Sc.yz}, {Sc.xz, Sc.yz, Sc.zz}};
+                    float GtJ[2][3];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        GtJ[0][j] = G00 * P.J[0][j] + G10 * P.J[1][j];
+                        GtJ[1][j] = G01 * P.J[0][j] + G11 * P.J[1][j];
+                    }
+                    float vJ[2][3];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            vJ[r][j] = (GJ[r][0] + GtJ[r][0]) * ScM[0][j] + (GJ[r][1] + GtJ[r][1]) * ScM[1][j] +
+                                       (GJ[r][2] + GtJ[r][2]) * ScM[2][j];
+                    if (!P.clip_x) vmc[0] += -fx * rz2 * vJ[0][2];
+                    else vmc[2] += -fx * rz3 * vJ[0][2] * P.tx;
+                    if (!P.clip_y) vmc[1] += -fy * rz2 * vJ[1][2];
+                    else vmc[2] += -fy * rz3 * vJ[1][2] * P.ty;
+                    vmc[2] += -fx * rz2 * vJ[0][0] - fy * rz2 * vJ[1][1] + 2.f * fx * P.tx * rz3 * vJ[0][2] +
+                              2.f * fy * P.ty * rz3 * vJ[1][2];
+                } else {
+                    vmc[0] = fx * vm0; vmc[1] = fy * vm1; vmc[2] = 0.f;
+                }
+                vmc[2] += v_depths[idx];
+                // world -> camera VJPs (transform.cuh:20-71)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) vmean[j] += R[j] * vmc[0] + R[4 + j] * vmc[1] + R[8 + j] * vmc[2];
+                // v_Sigma += R^T vSc R
+                float Tm[3][3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) Tm[i][j] = vSc[i][0] * R[j] + vSc[i][1] * R[4 + j] + vSc[i][2] * R[8 + j];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) vS[i][j] += R[i] * Tm[0][j] + R[4 + i] * Tm[1][j] + R[8 + i] * Tm[2][j];
+                if (v_viewmats != nullptr) {
+                    const float p[3] = {px, py, pz};
+                    const float SM[3][3] = {{S.xx, S.xy, S.xz}, {S.xy, S.yy, S.yz}, {S.xz, S.yz, S.zz}};
+                    // v_R = outer(vmc, p) + vSc R Sigma^T + vSc^T R Sigma = outer + (vSc + vSc^T) R Sigma
+                    float RS[3][3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) RS[i][j] = R[i * 4] * SM[0][j] + R[i * 4 + 1] * SM[1][j] + R[i * 4 + 2] * SM[2][j];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        vt[i] = vmc[i];
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            vR[i][j] = vmc[i] * p[j] + (vSc[i][0] + vSc[0][i]) * RS[0][j] + (vSc[i][1] + vSc[1][i]) * RS[1][j] +
+                                       (vSc[i][2] + vSc[2][i]) * RS[2][j];
+                    }
+                }
+            }
+            if (v_viewmats != nullptr) {  // block reduction over Gaussians, one atomic set per block and camera
+                float vals[12];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    vals[i * 4 + 0] = warp_sum(vR[i][0]); vals[i * 4 + 1] = warp_sum(vR[i][1]);
+                    vals[i * 4 + 2] = warp_sum(vR[i][2]); vals[i * 4 + 3] = warp_sum(vt[i]);
+                }
+                __syncthreads();
+                if (lane == 0)
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) s_red[warp][k] = vals[k];
+                __syncthreads();
+                if (threadIdx.x < 12) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kThreads / 32; ++w) s += s_red[w][threadIdx.x];
+                    if (s != 0.f) atomicAdd(v_viewmats + (size_t)(c0 + ci) * 16 + threadIdx.x, s);
+                }
+            }
+        }
+    }
+    if (g >= N) return;
+    v_means[(size_t)g * 3] = vmean[0]; v_means[(size_t)g * 3 + 1] = vmean[1]; v_means[(size_t)g * 3 + 2] = vmean[2];
+    if (covars != nullptr) {
+        float *o = v_covars + (size_t)g * 6;
+        o[0] = vS[0][0]; o[1] = vS[0][1] + vS[1][0]; o[2] = vS[0][2] + vS[2][0];
+        o[3] = vS[1][1]; o[4] = vS[1][2] + vS[2][1]; o[5] = vS[2][2];
+    } else {
+        // Sigma = M M^T, M = Rq diag(s)  (quat_scale_to_covar_preci.cuh:44-81, quat.cuh:35-57)
+        float M[3][3], vM[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { M[i][0] = Rq.m[i][0] * sx; M[i][1] = Rq.m[i][1] * sy; M[i][2] = Rq.m[i][2] * sz; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                vM[i][j] = (vS[i][0] + vS[0][i]) * M[0][j] + (vS[i][1] + vS[1][i]) * M[1][j] + (vS[i][2] + vS[2][i]) * M[2][j];
+        float vRq[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { vRq[i][0] = vM[i][0] * sx; vRq[i][1] = vM[i][1] * sy; vRq[i][2] = vM[i][2] * sz; }
+        float vsx = Rq.m[0][0] * vM[0][0] + Rq.m[1][0] * vM[1][0] + Rq.m[2][0] * vM[2][0];
+        float vsy = Rq.m[0][1] * vM[0][1] + Rq.m[1][1] * vM[1][1] + Rq.m[2][1] * vM[2][1];
+        float vsz = Rq.m[0][2] * vM[0][2] + Rq.m[1][2] * vM[1][2] + Rq.m[2][2] * vM[2][2];
+        const float w = q.x * inv_norm, x = q.y * inv_norm, y = q.z * inv_norm, z = q.w * inv_norm;
+        float vw = 2.f * (x * (vRq[2][1] - vRq[1][2]) + y * (vRq[0][2] - vRq[2][0]) + z * (vRq[1][0] - vRq[0][1]));
+        float vx = 2.f * (-2.f * x * (vRq[1][1] + vRq[2][2]) + y * (vRq[1][0] + vRq[0][1]) + z * (vRq[2][0] + vRq[0][2]) +
+                          w * (vRq[2][1] - vRq[1][2]));
+        float vy = 2.f * (x * (vRq[1][0] + vRq[0][1]) - 2.f * y * (vRq[0][0] + vRq[2][2]) + z * (vRq[2][1] + vRq[1][2]) +
+                          w * (vRq[0][2] - vRq[2][0]));
+        float vz = 2.f * (x * (vRq[2][0] + vRq[0][2]) + y * (vRq[2][1] + vRq[1][2]) - 2.f * z * (vRq[0][0] + vRq[1][1]) +
+                          w * (vRq[1][0] - vRq[0][1]));
+        float dotp = vw * w + vx * x + vy * y + vz * z;
+        stg4(v_quats + (size_t)g * 4, make_float4((vw - dotp * w) * inv_norm, (vx - dotp * x) * inv_norm,
+                                                   (vy - dotp * y) * inv_norm, (vz - dotp * z) * inv_norm));
+        v_scales[(size_t)g * 3] = vsx; v_scales[(size_t)g * 3 + 1] = vsy; v_scales[(size_t)g * 3 + 2] = vsz;
+    }
+}
+
+// ------------------------------------------------------------------ packed (COO) helpers
+constexpr int kCompactItems = 8;  // 2048 elements per block
+
+__global__ void __launch_bounds__(kThreads) compact_count_kernel(uint32_t n, const int32_t *__restrict__ radii,
+                                                                 int32_t *__restrict__ block_counts) {
+    __shared__ int s_w[kThreads / 32];
+    const uint32_t base = blockIdx.x * kThreads * kCompactItems;
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kCompactItems; ++k) {
+        uint32_t i = base + k * kThreads + threadIdx.x;
+        cnt += (i < n && radii[i] > 0) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kThreads / 32; ++w) t += s_w[w];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+compact_fill_kernel(uint32_t C, uint32_t N, const int32_t *__restrict__ radii, const float *__restrict__ means2d,
+                    const float *__restrict__ depths, const float *__restrict__ conics, const float *__restrict__ comps,
+                    const int32_t *__restrict__ block_offsets, int32_t *__restrict__ indptr,
+                    int64_t *__restrict__ camera_ids, int64_t *__restrict__ gaussian_ids, int32_t *__restrict__ p_radii,
+                    float *__restrict__ p_means2d, float *__restrict__ p_depths, float *__restrict__ p_conics,
+                    float *__restrict__ p_comps) {
+    __shared__ int s_w[kThreads / 32];
+    const uint32_t n = C * N;
+    const uint32_t base = blockIdx.x * kThreads * kCompactItems;
+    int running = block_offsets[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < kCompactItems; ++k) {
+        const uint32_t i = base + k * kThreads + threadIdx.x;
+        const bool vis = i < n && radii[i] > 0;
+        const unsigned m = __ballot_sync(0xffffffffu, vis);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+            const int c = s_w[w];
+            before += w < warp ? c : 0;
+            total += c;
+        }
+        const int row = running + before + __popc(m & ((1u << lane) - 1u));
+        if (vis) {
+            camera_ids[row] = i / N;
+            gaussian_ids[row] = i % N;
+            p_radii[row] = radii[i];
+            p_means2d[(size_t)row * 2] = means2d[(size_t)i * 2];
+            p_means2d[(size_t)row * 2 + 1] = means2d[(size_t)i * 2 + 1];
+            p_depths[row] = depths[i];
+            p_conics[(size_t)row * 3] = conics[(size_t)i * 3];
+            p_conics[(size_t)row * 3 + 1] = conics[(size_t)i * 3 + 1];
+            p_conics[(size_t)row * 3 + 2] = conics[(size_t)i * 3 + 2];
+            if (p_comps != nullptr) p_comps[row] = comps[i];
+        }
+        // indptr[c] = number of visible rows before element c*N: element i == c*N exactly starts camera c
+        if (i < n && i % N == 0) indptr[i / N] = row;
+        running += total;
+        __syncthreads();
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) indptr[C] = block_offsets[gridDim.x];
+}
+
+__global__ void __launch_bounds__(kThreads)
+scatter_rows_kernel(uint32_t N, int64_t nnz, const int64_t *__restrict__ camera_ids, const int64_t *__restrict__ gaussian_ids,
+                    const float *__restrict__ pm, const float *__restrict__ pd, const float *__restrict__ pc,
+                    const float *__restrict__ pk, float *__restrict__ vm, float *__restrict__ vd, float *__restrict__ vc,
+                    float *__restrict__ vk) {
+    const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (r >= nnz) return;
+    const size_t i = (size_t)camera_ids[r] * N + (size_t)gaussian_ids[r];
+    vm[i * 2] = pm[r * 2]; vm[i * 2 + 1] = pm[r * 2 + 1];
+    vd[i] = pd[r];
+    vc[i * 3] = pc[r * 3]; vc[i * 3 + 1] = pc[r * 3 + 1]; vc[i * 3 + 2] = pc[r * 3 + 2];
+    if (vk != nullptr) vk[i] = pk[r];
+}
+
+}  // namespace gsb200
+
+using namespace gsb200;
+
+extern "C" int gsb200_projection_fwd(uint32_t C, uint32_t N, const float *means, const float *covars, const float *quats,
+                                     const float *scales, const float *viewmats, const float *Ks, uint32_t W, uint32_t H,
+                                     float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
+                                     int packed_radius_rule, int32_t *radii, float *means2d, float *depths, float *conics,
+                                     float *compensations, gsb200_stream_t stream) {
+    if (camera_model != GSB200_CAMERA_PINHOLE && camera_model != GSB200_CAMERA_ORTHO)
+        return fail(2, "gsb200_projection_fwd: camera_model must be pinhole or ortho (fisheye not implemented)");
+    if (covars == nullptr && (quats == nullptr || scales == nullptr))
+        return fail(2, "gsb200_projection_fwd: covars or (quats, scales) should be provided");
+    if (C == 0 || N == 0) return 0;
+    projection_fwd_kernel<<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip,
+        camera_model, packed_radius_rule, radii, means2d, depths, conics, compensations);
+    return check_launch("projection_fwd");
+}
+
+extern "C" int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means, const float *covars, const float *quats,
+                                     const float *scales, const float *viewmats, const float *Ks, uint32_t W, uint32_t H,
+                                     float eps2d, int camera_model, const int32_t *radii, const float *conics,
+                                     const float *compensations, const float *v_means2d, const float *v_depths,
+                                     const float *v_conics, const float *v_compensations, float *v_means, float *v_covars,
+                                     float *v_quats, float *v_scales, float *v_viewmats, gsb200_stream_t stream) {
+    if (camera_model != GSB200_CAMERA_PINHOLE && camera_model != GSB200_CAMERA_ORTHO)
+        return fail(2, "gsb200_projection_bwd: camera_model must be pinhole or ortho (fisheye not implemented)");
+    if (C == 0 || N == 0) return 0;
+    if (v_viewmats != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_viewmats, 0, sizeof(float) * 16 * C, (cudaStream_t)stream));
+    projection_bwd_kernel<<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,
+        compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats);
+    return check_launch("projection_bwd");
+}
+
+extern "C" int gsb200_compact_count(uint32_t C, uint32_t N, const int32_t *radii, int32_t *block_offsets,
+                                    int64_t *nnz_host, gsb200_stream_t stream) {
+    const uint32_t n = C * N;
+    const uint32_t nb = cdiv(n, kThreads * kCompactItems);
+    *nnz_host = 0;
+    if (n == 0) return 0;
+    compact_count_kernel<<<nb, kThreads, 0, (cudaStream_t)stream>>>(n, radii, block_offsets);
+    if (int e = check_launch("compact_count")) return e;
+    scan_single_block_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nb, block_offsets);
+    if (int e = check_launch("scan_blocks")) return e;
+    int32_t total = 0;
+    GSB_CUDA_OK(cudaMemcpyAsync(&total, block_offsets + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GSB_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    *nnz_host = total;
+    return 0;
+}
+
+extern "C" int gsb200_compact_fill(uint32_t C, uint32_t N, const int32_t *radii, const float *means2d, const float *depths,
+                                   const float *conics, const float *compensations, const int32_t *block_offsets,
+                                   int32_t *indptr, int64_t *camera_ids, int64_t *gaussian_ids, int32_t *p_radii,
+                                   float *p_means2d, float *p_depths, float *p_conics, float *p_compensations,
+                                   gsb200_stream_t stream) {
+    const uint32_t n = C * N;
+    if (n == 0) return 0;
+    const uint32_t nb = cdiv(n, kThreads * kCompactItems);
+    compact_fill_kernel<<<nb, kThreads, 0, (cudaStream_t)stream>>>(C, N, radii, means2d, depths, conics, compensations,
+                                                                    block_offsets, indptr, camera_ids, gaussian_ids, p_radii,
+                                                                    p_means2d, p_depths, p_conics, p_compensations);
+    return check_launch("compact_fill");
+}
+
+extern "C" int gsb200_scatter_rows(uint32_t C, uint32_t N, int64_t nnz, const int64_t *camera_ids,
+                                   const int64_t *gaussian_ids, const float *p_v_means2d, const float *p_v_depths,
+                                   const float *p_v_conics, const float *p_v_compensations, float *v_means2d, float *v_depths,
+                                   float *v_conics, float *v_compensations, gsb200_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)C * N;
+    GSB_CUDA_OK(cudaMemsetAsync(v_means2d, 0, n * 2 * sizeof(float), s));
+    GSB_CUDA_OK(cudaMemsetAsync(v_depths, 0, n * sizeof(float), s));
+    GSB_CUDA_OK(cudaMemsetAsync(v_conics, 0, n * 3 * sizeof(float), s));
+    if (v_compensations != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_compensations, 0, n * sizeof(float), s));
+    if (nnz == 0) return 0;
+    scatter_rows_kernel<<<(unsigned)((nnz + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+        N, nnz, camera_ids, gaussian_ids, p_v_means2d, p_v_depths, p_v_conics, p_v_compensations, v_means2d, v_depths,
+        v_conics, v_compensations);
+    return check_launch("scatter_rows");
+}

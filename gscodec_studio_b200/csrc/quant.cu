@@ -1,0 +1,297 @@
+// In-loop compression simulation: fused fake-quantisation (+ activation) and the factorized-prior
+// entropy model, forward and backward (sm_100a).  HBM-bound elementwise kernels.
+//
+// fake quantisation replaces the torch op chain of gsplat/compression_simulation/ops.py:39-75
+// (clamp, uniform_ noise, mul, add -- 4-6 kernels per attribute, each a full read+write) with one
+// pass that can also apply the activation the trainer applies next (exp for scales, sigmoid for
+// opacities; examples/simple_trainer.py:758-776).
+//
+// The entropy model replaces Entropy_factorized_optimized_refactor.forward
+// (gsplat/compression_simulation/entropy_model.py:201-254): 3-4 bmm + ~12 elementwise kernels per
+// attribute become one kernel that evaluates the per-channel monotone MLP CDF in registers.  The
+// reference's reshape [2ch,1,Npad] -> [64ch,1,Npad/32] with weights tiled by repeat(64,1,1) means
+// element (n, c) is evaluated with parameter set p = (32*c + n / (Npad/32)) mod ch for BOTH the
+// lower and the upper logit; blocks are laid out so p is block-uniform.
+#include "common.cuh"
+
+namespace gsb200 {
+
+// ---------------------------------------------------------------- Philox4x32-10 (counter RNG)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01_centered(uint32_t r) {  // uniform in (-0.5, 0.5)
+    return ((float)(r >> 8) + 0.5f) * (1.f / 16777216.f) - 0.5f;
+}
+
+__device__ __forceinline__ float activate(int act, float v) {
+    if (act == 1) return __expf(v);
+    if (act == 2) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+fake_quantize_fwd_kernel(int64_t n, float *__restrict__ x, float lo, float hi, float q_step, float qs_norm, int mode, int act,
+                         const float *__restrict__ noise, uint64_t seed, uint64_t offset, float *__restrict__ y) {
+    // 4 consecutive elements per thread (one Philox call yields 4 uniforms)
+    const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (base >= n) return;
+    float u[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mode == 0) {
+        if (noise != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = base + k < n ? noise[base + k] : 0.f;
+        } else {
+            const uint64_t c = offset + (uint64_t)(base >> 2);
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            u[0] = u01_centered(r.x); u[1] = u01_centered(r.y); u[2] = u01_centered(r.z); u[3] = u01_centered(r.w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k >= n) break;
+        const float v = x[base + k];
+        const float cl = fminf(fmaxf(v, lo), hi);
+        float out;
+        if (mode == 0) {
+            out = __fadd_rn(cl, __fmul_rn(u[k], q_step));  // ops.py:44-47 (two roundings, like the torch ops)
+        } else {
+            x[base + k] = cl;  // in-place clamp of the parameter, ops.py:63
+            const float nrm = __fdiv_rn(cl - lo, hi - lo);
+            out = __fadd_rn(__fmul_rn(__fmul_rn(rintf(__fdiv_rn(nrm, qs_norm)), qs_norm), hi - lo), lo);  // ops.py:65-69
+        }
+        y[base + k] = activate(act, out);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fake_quantize_bwd_kernel(int64_t n, const float *__restrict__ x, const float *__restrict__ y, float lo, float hi, int mode,
+                         int act, const float *__restrict__ v_y, float *__restrict__ v_x) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    float g = v_y[i];
+    if (act == 1) g *= y[i];
+    else if (act == 2) { const float s = y[i]; g *= s * (1.f - s); }
+    if (mode == 0) { const float v = x[i]; g = (v >= lo && v <= hi) ? g : 0.f; }  // clamp gate; round mode is a pure STE
+    v_x[i] = g;
+}
+
+// ---------------------------------------------------------------- factorized entropy model
+// activated parameter set layout (floats), NH hidden layers of width 3:
+//   layer 0      : W[3] (3x1), b[3], tf[3]
+//   layer 1..NH-1: W[9] (3x3 row-major [out][in]), b[3], tf[3]
+//   last         : W[3] (1x3), b[1]
+template <int NH> struct EntropyDims { static constexpr int PS = 9 + (NH - 1) * 15 + 4; };
+
+__device__ __forceinline__ float fast_tanh(float v) {
+    const float e = __expf(2.f * v);
+    return 1.f - 2.f / (e + 1.f);  // tanh(v); saturates correctly for |v| large
+}
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+template <int NH>
+__device__ __forceinline__ float entropy_logit(const float *__restrict__ P, float u, float (*h_pre)[3], float (*h_tanh)[3]) {
+    // returns the logit; optionally records per-layer pre-activations and tanh values for the VJP
+    float h[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const float z = P[o] * u + P[3 + o];
+        const float t = fast_tanh(z);
+        if (h_pre) { h_pre[0][o] = z; h_tanh[0][o] = t; }
+        h[o] = z + P[6 + o] * t;
+    }
+#pragma unroll
+    for (int l = 1; l < NH; ++l) {
+        const float *L = P + 9 + (l - 1) * 15;
+        float hn[3];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const float z = L[o * 3] * h[0] + L[o * 3 + 1] * h[1] + L[o * 3 + 2] * h[2] + L[9 + o];
+            const float t = fast_tanh(z);
+            if (h_pre) { h_pre[l][o] = z; h_tanh[l][o] = t; }
+            hn[o] = z + L[12 + o] * t;
+        }
+        h[0] = hn[0]; h[1] = hn[1]; h[2] = hn[2];
+    }
+    const float *L = P + 9 + (NH - 1) * 15;
+    return L[0] * h[0] + L[1] * h[1] + L[2] * h[2] + L[3];
+}
+
+// VJP of entropy_logit w.r.t. u and the activated parameters; vP accumulates (+=)
+template <int NH>
+__device__ __forceinline__ float entropy_logit_vjp(const float *__restrict__ P, float u, float v_logit, float *vP) {
+    float h_pre[NH][3], h_tanh[NH][3];
+    (void)entropy_logit<NH>(P, u, h_pre, h_tanh);
+    // layer outputs h_l = z + tf * tanh(z)
+    const float *LL = P + 9 + (NH - 1) * 15;
+    float *vLL = vP + 9 + (NH - 1) * 15;
+    float vh[3];
+    {
+        float hl[3];
+        const float *tfp = NH == 1 ? P + 6 : P + 9 + (NH - 2) * 15 + 12;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) hl[o] = h_pre[NH - 1][o] + tfp[o] * h_tanh[NH - 1][o];
+#pragma unroll
+        for (int o = 0; o < 3; ++o) { vLL[o] += v_logit * hl[o]; vh[o] = v_logit * LL[o]; }
+        vLL[3] += v_logit;
+    }
+#pragma unroll
+    for (int l = NH - 1; l >= 1; --l) {
+        const float *L = P + 9 + (l - 1) * 15;
+        float *vL = vP + 9 + (l - 1) * 15;
+        // input to layer l = output of layer l-1
+        float hin[3];
+        const float *tfp = l == 1 ? P + 6 : P + 9 + (l - 2) * 15 + 12;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) hin[o] = h_pre[l - 1][o] + tfp[o] * h_tanh[l - 1][o];
+        float vin[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            const float t = h_tanh[l][o];
+            vL[12 + o] += vh[o] * t;                              // d/d tf
+            const float vz = vh[o] * (1.f + L[12 + o] * (1.f - t * t));
+            vL[9 + o] += vz;                                      // bias
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { vL[o * 3 + k] += vz * hin[k]; vin[k] += vz * L[o * 3 + k]; }
+        }
+        vh[0] = vin[0]; vh[1] = vin[1]; vh[2] = vin[2];
+    }
+    float vu = 0.f;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const float t = h_tanh[0][o];
+        vP[6 + o] += vh[o] * t;
+        const float vz = vh[o] * (1.f + P[6 + o] * (1.f - t * t));
+        vP[3 + o] += vz;
+        vP[o] += vz * u;
+        vu += vz * P[o];
+    }
+    return vu;
+}
+
+constexpr int kEntropyThreads = 128;
+
+// grid: (ceil(L / kEntropyThreads), 32 chunks, ch); element n = j*L + blockIdx.x*threads + tid
+template <int NH, bool BWD>
+__global__ void __launch_bounds__(kEntropyThreads)
+entropy_kernel(int64_t N, uint32_t ch, int64_t L, const float *__restrict__ x, float q, const float *__restrict__ params,
+               float bound, float *__restrict__ bits, const float *__restrict__ v_bits, float *__restrict__ v_x,
+               float *__restrict__ v_params) {
+    constexpr int PS = EntropyDims<NH>::PS;
+    __shared__ float sP[PS];
+    __shared__ float sV[PS];
+    const uint32_t j = blockIdx.y, c = blockIdx.z;
+    const uint32_t p = (32u * c + j) % ch;
+    for (int k = threadIdx.x; k < PS; k += blockDim.x) { sP[k] = params[(size_t)p * PS + k]; if (BWD) sV[k] = 0.f; }
+    __syncthreads();
+    const int64_t local = (int64_t)blockIdx.x * kEntropyThreads + threadIdx.x;
+    const int64_t n = (int64_t)j * L + local;
+    const bool on = local < L && n < N;
+    float vP[PS];
+    if (BWD) {
+#pragma unroll
+        for (int k = 0; k < PS; ++k) vP[k] = 0.f;
+    }
+    if (on) {
+        const float xv = x[n * ch + c];
+        const float ul = xv - 0.5f * q, uu = xv + 0.5f * q;
+        const float lower = entropy_logit<NH>(sP, ul, nullptr, nullptr);
+        const float upper = entropy_logit<NH>(sP, uu, nullptr, nullptr);
+        const float s = lower + upper;
+        const float sign = s > 0.f ? -1.f : (s < 0.f ? 1.f : 0.f);
+        const float su = sigmoidf_(sign * upper), sl = sigmoidf_(sign * lower);
+        const float diff = su - sl;
+        const float lik_raw = fabsf(diff);
+        const float lik = fmaxf(lik_raw, bound);
+        if (!BWD) {
+            bits[n * ch + c] = -__log2f(lik);
+        } else {
+            const float vb = v_bits[n * ch + c];
+            float v_lik = -vb / (lik * 0.6931471805599453f);
+            if (!(lik_raw >= bound || v_lik < 0.f)) v_lik = 0.f;  // LowerBound gradient rule, entropy_model.py:351-353
+            const float sd = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+            const float v_upper = v_lik * sd * su * (1.f - su) * sign;
+            const float v_lower = -v_lik * sd * sl * (1.f - sl) * sign;
+            float vx = entropy_logit_vjp<NH>(sP, uu, v_upper, vP);
+            vx += entropy_logit_vjp<NH>(sP, ul, v_lower, vP);
+            v_x[n * ch + c] = vx;
+        }
+    }
+    if (BWD) {
+        // block reduction of the PS parameter gradients: warp butterfly, then shared, then one atomic each
+#pragma unroll
+        for (int k = 0; k < PS; ++k) {
+            const float t = warp_sum(vP[k]);
+            if ((threadIdx.x & 31) == 0 && t != 0.f) atomicAdd(&sV[k], t);
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < PS; k += blockDim.x)
+            if (sV[k] != 0.f) atomicAdd(v_params + (size_t)p * PS + k, sV[k]);
+    }
+}
+
+}  // namespace gsb200
+
+using namespace gsb200;
+
+extern "C" int gsb200_fake_quantize_fwd(int64_t n, float *x, float lo, float hi, int bitwidth, int mode, int act,
+                                        const float *noise, uint64_t seed, uint64_t offset, float *y, gsb200_stream_t stream) {
+    if (mode != 0 && mode != 1) return fail(2, "gsb200_fake_quantize_fwd: mode must be 0 (noise) or 1 (round)");
+    if (act < 0 || act > 2) return fail(2, "gsb200_fake_quantize_fwd: act must be 0, 1 or 2");
+    if (n == 0) return 0;
+    const double levels = (double)((1ull << bitwidth) - 1ull);
+    const float q_step = (float)(((double)hi - (double)lo) / levels);
+    const float qs_norm = (float)(1.0 / levels);
+    const int64_t nthreads = (n + 3) / 4;
+    fake_quantize_fwd_kernel<<<(unsigned)((nthreads + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        n, x, lo, hi, q_step, qs_norm, mode, act, noise, seed, offset, y);
+    return check_launch("fake_quantize_fwd");
+}
+
+extern "C" int gsb200_fake_quantize_bwd(int64_t n, const float *x, const float *y, float lo, float hi, int mode, int act,
+                                        const float *v_y, float *v_x, gsb200_stream_t stream) {
+    if (n == 0) return 0;
+    fake_quantize_bwd_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        n, x, y, lo, hi, mode, act, v_y, v_x);
+    return check_launch("fake_quantize_bwd");
+}
+
+static int entropy_launch(bool bwd, int64_t N, uint32_t ch, uint32_t n_hidden, const float *x, float q, const float *params,
+                          float bound, float *bits, const float *v_bits, float *v_x, float *v_params, cudaStream_t s) {
+    if (n_hidden != 2 && n_hidden != 3) return fail(2, "gsb200_entropy: n_hidden must be 2 or 3 (filters (3,3) or (3,3,3))");
+    if (ch == 0 || ch > 65535) return fail(2, "gsb200_entropy: bad channel count");
+    if (N == 0) return 0;
+    const int64_t Npad = N + (32 - N % 32);  // entropy_model.py:223 (a full extra 32 when N % 32 == 0)
+    const int64_t L = Npad / 32;
+    dim3 grid((unsigned)((L + kEntropyThreads - 1) / kEntropyThreads), 32, ch);
+    if (!bwd) {
+        if (n_hidden == 2) entropy_kernel<2, false><<<grid, kEntropyThreads, 0, s>>>(N, ch, L, x, q, params, bound, bits, nullptr, nullptr, nullptr);
+        else entropy_kernel<3, false><<<grid, kEntropyThreads, 0, s>>>(N, ch, L, x, q, params, bound, bits, nullptr, nullptr, nullptr);
+    } else {
+        if (n_hidden == 2) entropy_kernel<2, true><<<grid, kEntropyThreads, 0, s>>>(N, ch, L, x, q, params, bound, nullptr, v_bits, v_x, v_params);
+        else entropy_kernel<3, true><<<grid, kEntropyThreads, 0, s>>>(N, ch, L, x, q, params, bound, nullptr, v_bits, v_x, v_params);
+    }
+    return check_launch(bwd ? "entropy_bwd" : "entropy_fwd");
+}
+
+extern "C" int gsb200_entropy_fwd(int64_t N, uint32_t ch, uint32_t n_hidden, const float *x, float q, const float *params,
+                                  float likelihood_bound, float *bits, gsb200_stream_t stream) {
+    return entropy_launch(false, N, ch, n_hidden, x, q, params, likelihood_bound, bits, nullptr, nullptr, nullptr,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int gsb200_entropy_bwd(int64_t N, uint32_t ch, uint32_t n_hidden, const float *x, float q, const float *params,
+                                  float likelihood_bound, const float *v_bits, float *v_x, float *v_params,
+                                  gsb200_stream_t stream) {
+    return entropy_launch(true, N, ch, n_hidden, x, q, params, likelihood_bound, nullptr, v_bits, v_x, v_params,
+                          (cudaStream_t)stream);
+}

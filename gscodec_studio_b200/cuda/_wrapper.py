@@ -1,0 +1,505 @@
+"""Operator layer of the hot path: torch.autograd Functions over the libgsb200 C-ABI.
+
+Mirrors the public op API of the reference's ``gsplat/cuda/_wrapper.py`` (same function names,
+argument order, defaults, shape asserts and error behaviour) so callers and tests written against
+``gsplat.cuda._wrapper`` run unchanged:
+
+    spherical_harmonics          _wrapper.py:47-73,   _SphericalHarmonics        :1226-1256
+    fully_fused_projection       _wrapper.py:203-339, _FullyFusedProjection      :775-898,
+                                                      _FullyFusedProjectionPacked:1031-1223
+    isect_tiles                  _wrapper.py:342-413
+    isect_offset_encode          _wrapper.py:416-433
+    rasterize_to_pixels          _wrapper.py:436-568, _RasterizeToPixels         :901-1028
+
+Python only allocates outputs (torch caching allocator), checks shapes and records the autograd
+graph; all arithmetic happens in the CUDA kernels behind ``_cabi.call``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+from typing_extensions import Literal
+
+from .. import _cabi
+from .._cabi import aligned, call, ptr, stream_ptr
+
+_CAMERA_MODELS = {"pinhole": 0, "ortho": 1, "fisheye": 2}
+_SUPPORTED_CHANNELS = (1, 2, 3, 4, 5, 8, 9, 16, 17, 32, 33)
+
+
+def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("gscodec_studio_b200: tensor must be a CUDA tensor (the hot path has no CPU implementation)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"gscodec_studio_b200: expected float32 tensor, got {t.dtype}")
+    return aligned(t)
+
+
+# --------------------------------------------------------------------------------------
+# spherical harmonics
+# --------------------------------------------------------------------------------------
+def spherical_harmonics(
+    degrees_to_use: int,
+    dirs: Tensor,  # [..., 3]
+    coeffs: Tensor,  # [..., K, 3]
+    masks: Optional[Tensor] = None,
+) -> Tensor:
+    """Computes spherical harmonics.  Returns colours [..., 3] (zero where masks is False)."""
+    assert (degrees_to_use + 1) ** 2 <= coeffs.shape[-2], coeffs.shape
+    assert dirs.shape[:-1] == coeffs.shape[:-2], (dirs.shape, coeffs.shape)
+    assert dirs.shape[-1] == 3, dirs.shape
+    assert coeffs.shape[-1] == 3, coeffs.shape
+    if masks is not None:
+        assert masks.shape == dirs.shape[:-1], masks.shape
+        masks = masks.contiguous()
+    return _SphericalHarmonics.apply(degrees_to_use, dirs.contiguous(), coeffs.contiguous(), masks)
+
+
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor]) -> Tensor:
+        dirs, coeffs = _f32(dirs), _f32(coeffs)
+        n = dirs.numel() // 3
+        K = coeffs.shape[-2]
+        masks_u8 = None if masks is None else masks.to(torch.uint8).contiguous()
+        colors = torch.empty(dirs.shape, dtype=torch.float32, device=dirs.device)
+        with torch.cuda.device(dirs.device):
+            call("gsb200_sh_fwd", n, K, sh_degree, ptr(dirs), ptr(coeffs), ptr(masks_u8), ptr(colors),
+                 stream_ptr(dirs.device))
+        ctx.save_for_backward(dirs, coeffs, masks_u8)
+        ctx.sh_degree = sh_degree
+        ctx.num_bases = K
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors: Tensor):
+        dirs, coeffs, masks_u8 = ctx.saved_tensors
+        n = dirs.numel() // 3
+        compute_v_dirs = ctx.needs_input_grad[1]
+        v_colors = _f32(v_colors.contiguous())
+        v_coeffs = torch.empty_like(coeffs)
+        v_dirs = torch.empty_like(dirs) if compute_v_dirs else None
+        with torch.cuda.device(dirs.device):
+            call("gsb200_sh_bwd", n, ctx.num_bases, ctx.sh_degree, ptr(dirs), ptr(coeffs), ptr(masks_u8),
+                 ptr(v_colors), ptr(v_coeffs), ptr(v_dirs), stream_ptr(dirs.device))
+        return None, v_dirs, v_coeffs, None
+
+
+# --------------------------------------------------------------------------------------
+# projection
+# --------------------------------------------------------------------------------------
+def fully_fused_projection(
+    means: Tensor,  # [N, 3]
+    covars: Optional[Tensor],  # [N, 6] or None
+    quats: Optional[Tensor],  # [N, 4] or None
+    scales: Optional[Tensor],  # [N, 3] or None
+    viewmats: Tensor,  # [C, 4, 4]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    eps2d: float = 0.3,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    packed: bool = False,
+    sparse_grad: bool = False,
+    calc_compensations: bool = False,
+    camera_model: Literal["pinhole", "ortho", "fisheye"] = "pinhole",
+):
+    """Projects Gaussians to 2D (dense: radii, means2d, depths, conics, compensations;
+    packed: camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations)."""
+    C = viewmats.size(0)
+    N = means.size(0)
+    assert means.size() == (N, 3), means.size()
+    assert viewmats.size() == (C, 4, 4), viewmats.size()
+    assert Ks.size() == (C, 3, 3), Ks.size()
+    means = means.contiguous()
+    if covars is not None:
+        assert covars.size() == (N, 6), covars.size()
+        covars = covars.contiguous()
+    else:
+        assert quats is not None, "covars or quats is required"
+        assert scales is not None, "covars or scales is required"
+        assert quats.size() == (N, 4), quats.size()
+        assert scales.size() == (N, 3), scales.size()
+        quats = quats.contiguous()
+        scales = scales.contiguous()
+    if sparse_grad:
+        assert packed, "sparse_grad is only supported when packed is True"
+    if camera_model not in _CAMERA_MODELS:
+        raise ValueError(f"Unsupported camera model: {camera_model}")
+    viewmats = viewmats.contiguous()
+    Ks = Ks.contiguous()
+    if packed:
+        return _FullyFusedProjectionPacked.apply(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+            radius_clip, sparse_grad, calc_compensations, camera_model)
+    return _FullyFusedProjection.apply(
+        means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+        radius_clip, calc_compensations, camera_model)
+
+
+def _projection_fwd(means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                    radius_clip, calc_compensations, camera_model, packed_rule):
+    C, N = viewmats.shape[0], means.shape[0]
+    dev = means.device
+    radii = torch.empty((C, N), dtype=torch.int32, device=dev)
+    means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
+    depths = torch.empty((C, N), dtype=torch.float32, device=dev)
+    conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+    comps = torch.empty((C, N), dtype=torch.float32, device=dev) if calc_compensations else None
+    with torch.cuda.device(dev):
+        call("gsb200_projection_fwd", C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks),
+             width, height, eps2d, near_plane, far_plane, radius_clip, _CAMERA_MODELS[camera_model], int(packed_rule),
+             ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), stream_ptr(dev))
+    return radii, means2d, depths, conics, comps
+
+
+def _projection_bwd(means, covars, quats, scales, viewmats, Ks, width, height, eps2d, camera_model, radii, conics,
+                    comps, v_means2d, v_depths, v_conics, v_comps, viewmats_requires_grad):
+    C, N = viewmats.shape[0], means.shape[0]
+    dev = means.device
+    v_means = torch.empty_like(means)
+    v_covars = torch.empty_like(covars) if covars is not None else None
+    v_quats = torch.empty_like(quats) if covars is None else None
+    v_scales = torch.empty_like(scales) if covars is None else None
+    v_viewmats = torch.empty_like(viewmats) if viewmats_requires_grad else None
+    with torch.cuda.device(dev):
+        call("gsb200_projection_bwd", C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks),
+             width, height, eps2d, _CAMERA_MODELS[camera_model], ptr(radii), ptr(conics), ptr(comps),
+             ptr(_f32(v_means2d.contiguous())), ptr(_f32(v_depths.contiguous())), ptr(_f32(v_conics.contiguous())),
+             ptr(None if v_comps is None else _f32(v_comps.contiguous())), ptr(v_means), ptr(v_covars), ptr(v_quats),
+             ptr(v_scales), ptr(v_viewmats), stream_ptr(dev))
+    return v_means, v_covars, v_quats, v_scales, v_viewmats
+
+
+class _FullyFusedProjection(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                radius_clip, calc_compensations, camera_model):
+        means, covars, quats, scales, viewmats, Ks = map(_f32, (means, covars, quats, scales, viewmats, Ks))
+        radii, means2d, depths, conics, comps = _projection_fwd(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+            calc_compensations, camera_model, False)
+        ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, radii, conics, comps)
+        ctx.dims = (width, height, eps2d, camera_model)
+        ctx.mark_non_differentiable(radii)
+        return radii, means2d, depths, conics, comps
+
+    @staticmethod
+    def backward(ctx, v_radii, v_means2d, v_depths, v_conics, v_comps):
+        means, covars, quats, scales, viewmats, Ks, radii, conics, comps = ctx.saved_tensors
+        width, height, eps2d, camera_model = ctx.dims
+        if comps is None:
+            v_comps = None
+        elif v_comps is None:
+            v_comps = torch.zeros_like(comps)
+        v_means, v_covars, v_quats, v_scales, v_viewmats = _projection_bwd(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, camera_model, radii, conics, comps,
+            v_means2d, v_depths, v_conics, v_comps, ctx.needs_input_grad[4])
+        if not ctx.needs_input_grad[0]:
+            v_means = None
+        if not ctx.needs_input_grad[1]:
+            v_covars = None
+        if not ctx.needs_input_grad[2]:
+            v_quats = None
+        if not ctx.needs_input_grad[3]:
+            v_scales = None
+        return (v_means, v_covars, v_quats, v_scales, v_viewmats, None, None, None, None, None, None, None, None, None)
+
+
+class _FullyFusedProjectionPacked(torch.autograd.Function):
+    """COO variant.  Internally: dense projection (packed radius rule) -> stream compaction; the
+    backward scatters the packed gradients to the dense layout and reuses the dense kernel."""
+
+    @staticmethod
+    def forward(ctx, means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                radius_clip, sparse_grad, calc_compensations, camera_model):
+        means, covars, quats, scales, viewmats, Ks = map(_f32, (means, covars, quats, scales, viewmats, Ks))
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        radii_d, means2d_d, depths_d, conics_d, comps_d = _projection_fwd(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+            calc_compensations, camera_model, True)
+        nb = (C * N + 2047) // 2048
+        block_offsets = torch.empty(nb + 1, dtype=torch.int32, device=dev)
+        nnz_host = ctypes.c_int64(0)
+        with torch.cuda.device(dev):
+            call("gsb200_compact_count", C, N, ptr(radii_d), ptr(block_offsets), ctypes.byref(nnz_host), stream_ptr(dev))
+        nnz = int(nnz_host.value)
+        indptr = torch.empty(C + 1, dtype=torch.int32, device=dev)
+        camera_ids = torch.empty(nnz, dtype=torch.int64, device=dev)
+        gaussian_ids = torch.empty(nnz, dtype=torch.int64, device=dev)
+        radii = torch.empty(nnz, dtype=torch.int32, device=dev)
+        means2d = torch.empty((nnz, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty(nnz, dtype=torch.float32, device=dev)
+        conics = torch.empty((nnz, 3), dtype=torch.float32, device=dev)
+        comps = torch.empty(nnz, dtype=torch.float32, device=dev) if calc_compensations else None
+        with torch.cuda.device(dev):
+            call("gsb200_compact_fill", C, N, ptr(radii_d), ptr(means2d_d), ptr(depths_d), ptr(conics_d), ptr(comps_d),
+                 ptr(block_offsets), ptr(indptr), ptr(camera_ids), ptr(gaussian_ids), ptr(radii), ptr(means2d),
+                 ptr(depths), ptr(conics), ptr(comps), stream_ptr(dev))
+        ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, camera_ids, gaussian_ids, radii_d, conics_d,
+                              comps_d)
+        ctx.dims = (width, height, eps2d, camera_model, sparse_grad)
+        ctx.mark_non_differentiable(camera_ids, gaussian_ids, radii)
+        return camera_ids, gaussian_ids, radii, means2d, depths, conics, comps
+
+    @staticmethod
+    def backward(ctx, v_camera_ids, v_gaussian_ids, v_radii, v_means2d, v_depths, v_conics, v_comps):
+        (means, covars, quats, scales, viewmats, Ks, camera_ids, gaussian_ids, radii_d, conics_d,
+         comps_d) = ctx.saved_tensors
+        width, height, eps2d, camera_model, sparse_grad = ctx.dims
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        nnz = camera_ids.numel()
+        if comps_d is None:
+            v_comps = None
+        elif v_comps is None:
+            v_comps = torch.zeros(nnz, dtype=torch.float32, device=dev)
+        d_means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
+        d_depths = torch.empty((C, N), dtype=torch.float32, device=dev)
+        d_conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+        d_comps = torch.empty((C, N), dtype=torch.float32, device=dev) if comps_d is not None else None
+        with torch.cuda.device(dev):
+            call("gsb200_scatter_rows", C, N, nnz, ptr(camera_ids), ptr(gaussian_ids), ptr(_f32(v_means2d.contiguous())),
+                 ptr(_f32(v_depths.contiguous())), ptr(_f32(v_conics.contiguous())),
+                 ptr(None if v_comps is None else _f32(v_comps.contiguous())), ptr(d_means2d), ptr(d_depths),
+                 ptr(d_conics), ptr(d_comps), stream_ptr(dev))
+        v_means, v_covars, v_quats, v_scales, v_viewmats = _projection_bwd(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, camera_model, radii_d, conics_d, comps_d,
+            d_means2d, d_depths, d_conics, d_comps, ctx.needs_input_grad[4])
+
+        def out(t, need):
+            if t is None or not need:
+                return None
+            if sparse_grad:  # same values as the reference's COO gradient once densified (_wrapper.py:1163-1203)
+                rows = torch.unique(gaussian_ids)
+                return torch.sparse_coo_tensor(rows[None], t[rows], size=t.shape, is_coalesced=True)
+            return t
+
+        return (out(v_means, ctx.needs_input_grad[0]), out(v_covars, ctx.needs_input_grad[1]),
+                out(v_quats, ctx.needs_input_grad[2]), out(v_scales, ctx.needs_input_grad[3]), v_viewmats,
+                None, None, None, None, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------
+# tile intersection
+# --------------------------------------------------------------------------------------
+@torch.no_grad()
+def isect_tiles(
+    means2d: Tensor,  # [C, N, 2] or [nnz, 2]
+    radii: Tensor,  # [C, N] or [nnz]
+    depths: Tensor,  # [C, N] or [nnz]
+    tile_size: int,
+    tile_width: int,
+    tile_height: int,
+    sort: bool = True,
+    packed: bool = False,
+    n_cameras: Optional[int] = None,
+    camera_ids: Optional[Tensor] = None,
+    gaussian_ids: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Maps projected Gaussians to intersecting tiles -> (tiles_per_gauss, isect_ids, flatten_ids)."""
+    tpg, isect_ids, flatten_ids, _ = _isect_tiles_with_offsets(
+        means2d, radii, depths, tile_size, tile_width, tile_height, sort, packed, n_cameras, camera_ids, gaussian_ids)
+    return tpg, isect_ids, flatten_ids
+
+
+@torch.no_grad()
+def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, packed=False,
+                              n_cameras=None, camera_ids=None, gaussian_ids=None):
+    """isect_tiles that also returns isect_offsets (a by-product of the per-tile design)."""
+    if packed:
+        nnz = means2d.size(0)
+        assert means2d.shape == (nnz, 2), means2d.size()
+        assert radii.shape == (nnz,), radii.size()
+        assert depths.shape == (nnz,), depths.size()
+        assert camera_ids is not None, "camera_ids is required if packed is True"
+        assert gaussian_ids is not None, "gaussian_ids is required if packed is True"
+        assert n_cameras is not None, "n_cameras is required if packed is True"
+        camera_ids = camera_ids.contiguous()
+        C, n_elems, per_cam = n_cameras, nnz, 0
+    else:
+        C, N, _ = means2d.shape
+        assert means2d.shape == (C, N, 2), means2d.size()
+        assert radii.shape == (C, N), radii.size()
+        assert depths.shape == (C, N), depths.size()
+        camera_ids = None
+        n_elems, per_cam = C * N, N
+    if not sort:
+        raise NotImplementedError("gscodec_studio_b200.isect_tiles: sort=False is not supported by the per-tile design")
+    dev = means2d.device
+    means2d, depths = _f32(means2d.detach()), _f32(depths.detach())
+    radii = radii.contiguous()
+    assert radii.dtype == torch.int32, radii.dtype
+    T = C * tile_width * tile_height
+    tiles_per_gauss = torch.empty(radii.shape, dtype=torch.int32, device=dev)
+    isect_offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
+    tile_cursor = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+    n_host = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        call("gsb200_isect_prepare", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), tile_size,
+             tile_width, tile_height, ptr(tiles_per_gauss), ptr(isect_offsets), ptr(tile_cursor), ctypes.byref(n_host),
+             stream_ptr(dev))
+        n_isects = int(n_host.value)
+        isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+        flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+        scratch = torch.empty(max(n_isects, 1), dtype=torch.int64, device=dev)
+        call("gsb200_isect_fill", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths), tile_size,
+             tile_width, tile_height, n_isects, ptr(isect_offsets), ptr(tile_cursor), ptr(scratch), ptr(isect_ids),
+             ptr(flatten_ids), stream_ptr(dev))
+    return tiles_per_gauss, isect_ids, flatten_ids, isect_offsets
+
+
+@torch.no_grad()
+def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile_height: int) -> Tensor:
+    """Encodes intersection ids to offsets [C, tile_height, tile_width] (int32)."""
+    isect_ids = isect_ids.contiguous()
+    assert isect_ids.dtype == torch.int64, isect_ids.dtype
+    dev = isect_ids.device
+    offsets = torch.empty((n_cameras, tile_height, tile_width), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("gsb200_isect_offset_encode", isect_ids.numel(), ptr(isect_ids), n_cameras, tile_width, tile_height,
+             ptr(offsets), stream_ptr(dev))
+    return offsets
+
+
+# --------------------------------------------------------------------------------------
+# alpha blend
+# --------------------------------------------------------------------------------------
+def rasterize_to_pixels(
+    means2d: Tensor,  # [C, N, 2] or [nnz, 2]
+    conics: Tensor,  # [C, N, 3] or [nnz, 3]
+    colors: Tensor,  # [C, N, channels] or [nnz, channels]
+    opacities: Tensor,  # [C, N] or [nnz]
+    image_width: int,
+    image_height: int,
+    tile_size: int,
+    isect_offsets: Tensor,  # [C, tile_height, tile_width]
+    flatten_ids: Tensor,  # [n_isects]
+    backgrounds: Optional[Tensor] = None,  # [C, channels]
+    masks: Optional[Tensor] = None,  # [C, tile_height, tile_width]
+    packed: bool = False,
+    absgrad: bool = False,
+) -> Tuple[Tensor, Tensor]:
+    """Rasterizes Gaussians to pixels -> (render_colors [C,H,W,channels], render_alphas [C,H,W,1])."""
+    C = isect_offsets.size(0)
+    device = means2d.device
+    if packed:
+        nnz = means2d.size(0)
+        assert means2d.shape == (nnz, 2), means2d.shape
+        assert conics.shape == (nnz, 3), conics.shape
+        assert colors.shape[0] == nnz, colors.shape
+        assert opacities.shape == (nnz,), opacities.shape
+    else:
+        N = means2d.size(1)
+        assert means2d.shape == (C, N, 2), means2d.shape
+        assert conics.shape == (C, N, 3), conics.shape
+        assert colors.shape[:2] == (C, N), colors.shape
+        assert opacities.shape == (C, N), opacities.shape
+    if backgrounds is not None:
+        assert backgrounds.shape == (C, colors.shape[-1]), backgrounds.shape
+        backgrounds = backgrounds.contiguous()
+    if masks is not None:
+        assert masks.shape == isect_offsets.shape, masks.shape
+        masks = masks.contiguous()
+
+    channels = colors.shape[-1]
+    if channels > 513 or channels == 0:
+        raise ValueError(f"Unsupported number of color channels: {channels}")
+
+    tile_height, tile_width = isect_offsets.shape[1:3]
+    assert tile_height * tile_size >= image_height, f"Assert Failed: {tile_height} * {tile_size} >= {image_height}"
+    assert tile_width * tile_size >= image_width, f"Assert Failed: {tile_width} * {tile_size} >= {image_width}"
+
+    if channels > 33:
+        # wide features: the kernels are instantiated up to 33 channels, wider inputs go through in
+        # slices of 32 (what rasterization() does with channel_chunk, rendering.py:528-556)
+        outs, alphas = [], None
+        for lo in range(0, channels, 32):
+            bg = None if backgrounds is None else backgrounds[..., lo:lo + 32]
+            rc, ra = rasterize_to_pixels(means2d, conics, colors[..., lo:lo + 32], opacities, image_width, image_height,
+                                         tile_size, isect_offsets, flatten_ids, bg, masks, packed, absgrad)
+            outs.append(rc)
+            alphas = ra if alphas is None else alphas
+        return torch.cat(outs, dim=-1), alphas
+
+    padded_channels = 0
+    if channels not in _SUPPORTED_CHANNELS:
+        padded_channels = (1 << (channels - 1).bit_length()) - channels
+        colors = torch.cat([colors, torch.zeros(*colors.shape[:-1], padded_channels, device=device)], dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat(
+                [backgrounds, torch.zeros(*backgrounds.shape[:-1], padded_channels, device=device)], dim=-1)
+
+    render_colors, render_alphas = _RasterizeToPixels.apply(
+        means2d.contiguous(), conics.contiguous(), colors.contiguous(), opacities.contiguous(), backgrounds, masks,
+        image_width, image_height, tile_size, isect_offsets.contiguous(), flatten_ids.contiguous(), absgrad)
+    if padded_channels > 0:
+        render_colors = render_colors[..., :-padded_channels]
+    return render_colors, render_alphas
+
+
+class _RasterizeToPixels(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets,
+                flatten_ids, absgrad):
+        means2d_in = means2d
+        means2d, conics, colors, opacities, backgrounds = map(_f32, (means2d, conics, colors, opacities, backgrounds))
+        masks_u8 = None if masks is None else masks.to(torch.uint8).contiguous()
+        C, th, tw = isect_offsets.shape
+        D = colors.shape[-1]
+        M = opacities.numel()
+        dev = means2d.device
+        render_colors = torch.empty((C, height, width, D), dtype=torch.float32, device=dev)
+        # alphas / last_ids of masked tiles are left untouched by the kernel (reference: uninitialised)
+        render_alphas = torch.zeros((C, height, width, 1), dtype=torch.float32, device=dev) if masks is not None \
+            else torch.empty((C, height, width, 1), dtype=torch.float32, device=dev)
+        last_ids = torch.zeros((C, height, width), dtype=torch.int32, device=dev) if masks is not None \
+            else torch.empty((C, height, width), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            call("gsb200_rasterize_fwd", C, M, flatten_ids.numel(), D, ptr(means2d), ptr(conics), ptr(colors),
+                 ptr(opacities), ptr(backgrounds), ptr(masks_u8), width, height, tile_size, tw, th, ptr(isect_offsets),
+                 ptr(flatten_ids), ptr(render_colors), ptr(render_alphas), ptr(last_ids), stream_ptr(dev))
+        ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, masks_u8, isect_offsets, flatten_ids,
+                              render_alphas, last_ids)
+        ctx.dims = (width, height, tile_size, absgrad)
+        ctx.means2d_in = means2d_in if absgrad else None
+        return render_colors, render_alphas
+
+    @staticmethod
+    def backward(ctx, v_render_colors, v_render_alphas):
+        (means2d, conics, colors, opacities, backgrounds, masks_u8, isect_offsets, flatten_ids, render_alphas,
+         last_ids) = ctx.saved_tensors
+        width, height, tile_size, absgrad = ctx.dims
+        C, th, tw = isect_offsets.shape
+        D = colors.shape[-1]
+        M = opacities.numel()
+        dev = means2d.device
+        v_render_colors = _f32(v_render_colors.contiguous())
+        v_render_alphas = _f32(v_render_alphas.contiguous())
+        v_means2d = torch.empty_like(means2d)
+        v_conics = torch.empty_like(conics)
+        v_colors = torch.empty_like(colors)
+        v_opacities = torch.empty_like(opacities)
+        v_abs = torch.empty_like(means2d) if absgrad else None
+        with torch.cuda.device(dev):
+            rec = int(_cabi.load_library().gsb200_grad_record(D))
+            scratch = torch.empty(max(M, 1) * rec, dtype=torch.float32, device=dev)
+            call("gsb200_rasterize_bwd", C, M, flatten_ids.numel(), D, ptr(means2d), ptr(conics), ptr(colors),
+                 ptr(opacities), ptr(backgrounds), ptr(masks_u8), width, height, tile_size, tw, th, ptr(isect_offsets),
+                 ptr(flatten_ids), ptr(render_alphas), ptr(last_ids), ptr(v_render_colors), ptr(v_render_alphas),
+                 ptr(scratch), ptr(v_abs), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opacities),
+                 stream_ptr(dev))
+        if absgrad:
+            ctx.means2d_in.absgrad = v_abs  # strategies read info["means2d"].absgrad (_wrapper.py:1005-1006)
+        v_backgrounds = None
+        if ctx.needs_input_grad[4]:
+            v_backgrounds = (v_render_colors * (1.0 - render_alphas).float()).sum(dim=(1, 2))
+        return (v_means2d, v_conics, v_colors, v_opacities, v_backgrounds, None, None, None, None, None, None, None)

@@ -1,0 +1,264 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU, torch.distributed over NCCL/NVLink.
+
+Keeps the helper API of the reference's ``gsplat/distributed.py`` (all_gather_int32 :10-52,
+all_to_all_int32 :55-99, all_gather_tensor_list :102-167, all_to_all_tensor_list :170-257,
+cli :304-360) and adds the collective the B200 design is built on:
+
+``all_gather_attributes`` -- one autograd-aware all-gather of the raw splat attributes per step
+(backward = reduce-scatter of the attribute gradients to their owner rank).  Every rank then runs
+all four stages for ITS cameras over the full set, so the render path has exactly one exchange each
+way with shapes that do not depend on visibility -- instead of the reference's project-everywhere
+followed by 5 variable-split all-to-alls (rendering.py:282-294, 397-478).
+
+The helpers are backend-agnostic (``gloo`` on CPU is used by the tests); tensors must live on the
+device the process group works with.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Callable, List, Optional, Sequence, Union
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def _backend_supports(op: str) -> bool:
+    backend = dist.get_backend()
+    if op in ("reduce_scatter_tensor", "all_to_all"):
+        return backend != "gloo"
+    return True
+
+
+def all_gather_int32(world_size: int, value: Union[int, Tensor], device: Optional[torch.device] = None) -> List:
+    """Gather one 32-bit integer from every rank (not differentiable)."""
+    if world_size == 1:
+        return [value]
+    if isinstance(value, int):
+        assert device is not None, "device is required for scalar input"
+        value_tensor = torch.tensor([value], dtype=torch.int, device=device)
+    else:
+        value_tensor = value.reshape(1)
+    collected = torch.empty(world_size, dtype=value_tensor.dtype, device=value_tensor.device)
+    dist.all_gather_into_tensor(collected, value_tensor)
+    return collected.tolist() if isinstance(value, int) else list(collected.unbind())
+
+
+def all_to_all_int32(world_size: int, values: List[Union[int, Tensor]], device: Optional[torch.device] = None) -> List:
+    """Many-to-many exchange of one 32-bit integer per peer (not differentiable)."""
+    if world_size == 1:
+        return values
+    assert len(values) == world_size, "The length of values should be equal to world_size"
+    if any(isinstance(v, int) for v in values):
+        assert device is not None, "device is required for scalar input"
+    send = torch.stack([
+        torch.tensor(v, dtype=torch.int, device=device) if isinstance(v, int) else v.reshape(()).to(torch.int)
+        for v in values
+    ])
+    if _backend_supports("all_to_all"):
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+    else:  # gloo: gather the whole matrix and read our column
+        mat = torch.empty(world_size * world_size, dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(mat, send)
+        recv = mat.view(world_size, world_size)[:, dist.get_rank()].contiguous()
+    if isinstance(values[0], int):
+        return recv.tolist()
+    return list(recv.unbind())
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """Concatenate per-rank row blocks [n_r, F] -> [sum n_r, F]; backward returns the local block of the
+    SUMMED gradient (reduce-scatter)."""
+
+    @staticmethod
+    def forward(ctx, data: Tensor, counts: Sequence[int]):
+        world = dist.get_world_size()
+        rank = dist.get_rank()
+        n_max = max(counts)
+        F = data.shape[1]
+        if all(c == n_max for c in counts):
+            out = torch.empty((world * n_max, F), dtype=data.dtype, device=data.device)
+            dist.all_gather_into_tensor(out, data.contiguous())
+        else:
+            padded = torch.zeros((n_max, F), dtype=data.dtype, device=data.device)
+            padded[: counts[rank]] = data
+            buf = torch.empty((world * n_max, F), dtype=data.dtype, device=data.device)
+            dist.all_gather_into_tensor(buf, padded)
+            out = torch.cat([buf[r * n_max: r * n_max + counts[r]] for r in range(world)], dim=0)
+        ctx.counts = list(counts)
+        return out
+
+    @staticmethod
+    def backward(ctx, v_out: Tensor):
+        counts = ctx.counts
+        world = dist.get_world_size()
+        rank = dist.get_rank()
+        n_max = max(counts)
+        F = v_out.shape[1]
+        v_out = v_out.contiguous()
+        if all(c == n_max for c in counts):
+            send = v_out
+        else:
+            send = torch.zeros((world * n_max, F), dtype=v_out.dtype, device=v_out.device)
+            start = 0
+            for r in range(world):
+                send[r * n_max: r * n_max + counts[r]] = v_out[start: start + counts[r]]
+                start += counts[r]
+        if _backend_supports("reduce_scatter_tensor"):
+            recv = torch.empty((n_max, F), dtype=v_out.dtype, device=v_out.device)
+            dist.reduce_scatter_tensor(recv, send, op=dist.ReduceOp.SUM)
+        else:
+            send = send.clone()
+            dist.all_reduce(send, op=dist.ReduceOp.SUM)
+            recv = send[rank * n_max: (rank + 1) * n_max]
+        return recv[: counts[rank]].contiguous(), None
+
+
+def all_gather_attributes(tensor_list: List[Tensor], counts: Optional[List[int]] = None) -> List[Tensor]:
+    """All-gather a list of per-Gaussian tensors [(n_r, *), ...] along dim 0 in ONE collective.
+
+    Differentiable: gradients w.r.t. the gathered tensors are summed over ranks and the local rows
+    are returned (reduce-scatter).  Row counts may differ between ranks.
+    """
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(tensor_list)
+    world = dist.get_world_size()
+    n = tensor_list[0].shape[0]
+    for t in tensor_list:
+        assert t.shape[0] == n, "All tensors should have the same first dimension size"
+    if counts is None:
+        counts = [int(c) for c in all_gather_int32(world, int(n), device=tensor_list[0].device)]
+    widths = [t.numel() // max(n, 1) if n > 0 else int(torch.tensor(t.shape[1:]).prod()) for t in tensor_list]
+    data = torch.cat([t.reshape(n, -1) for t in tensor_list], dim=-1)
+    gathered = _AllGatherRows.apply(data, counts)
+    outs = torch.split(gathered, widths, dim=-1)
+    return [o.reshape(-1, *t.shape[1:]) for o, t in zip(outs, tensor_list)]
+
+
+def all_gather_tensor_list(world_size: int, tensor_list: List[Tensor]) -> List[Tensor]:
+    """Gather a list of equally-shaped tensors from all ranks (differentiable); [(N*world, *), ...]."""
+    if world_size == 1:
+        return tensor_list
+    n = len(tensor_list[0])
+    return all_gather_attributes(tensor_list, counts=[n] * world_size)
+
+
+class _AllToAllRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, data: Tensor, in_splits: List[int], out_splits: List[int]):
+        ctx.splits = (list(in_splits), list(out_splits))
+        return _all_to_all_rows(data, in_splits, out_splits)
+
+    @staticmethod
+    def backward(ctx, v_out: Tensor):
+        in_splits, out_splits = ctx.splits
+        return _all_to_all_rows(v_out.contiguous(), out_splits, in_splits), None, None
+
+
+def _all_to_all_rows(data: Tensor, in_splits: List[int], out_splits: List[int]) -> Tensor:
+    F = data.shape[1]
+    out = torch.empty((sum(out_splits), F), dtype=data.dtype, device=data.device)
+    if _backend_supports("all_to_all"):
+        dist.all_to_all_single(out, data.contiguous(), output_split_sizes=out_splits, input_split_sizes=in_splits)
+        return out
+    # gloo: emulate with point-to-point exchanges
+    world, rank = dist.get_world_size(), dist.get_rank()
+    send_chunks = list(torch.split(data, in_splits, dim=0))
+    recv_chunks = list(torch.split(out, out_splits, dim=0))
+    reqs = []
+    for r in range(world):
+        if r == rank:
+            recv_chunks[r].copy_(send_chunks[r])
+            continue
+        reqs.append(dist.isend(send_chunks[r].contiguous(), r))
+        reqs.append(dist.irecv(recv_chunks[r], r))
+    for q in reqs:
+        q.wait()
+    return out
+
+
+def all_to_all_tensor_list(
+    world_size: int,
+    tensor_list: List[Tensor],
+    splits: List[Union[int, Tensor]],
+    output_splits: Optional[List[Union[int, Tensor]]] = None,
+) -> List[Tensor]:
+    """Split each tensor along dim 0 by `splits`, scatter the pieces to all ranks (differentiable)."""
+    if world_size == 1:
+        return tensor_list
+    n = len(tensor_list[0])
+    for t in tensor_list:
+        assert len(t) == n, "All tensors should have the same first dimension size"
+    assert len(splits) == world_size, "The length of splits should be equal to world_size"
+    in_splits = [int(s) for s in splits]
+    if output_splits is None:
+        output_splits = all_to_all_int32(world_size, in_splits, device=tensor_list[0].device)
+    out_splits = [int(s) for s in output_splits]
+    widths = [t[0].numel() if n > 0 else int(torch.tensor(t.shape[1:]).prod()) for t in tensor_list]
+    data = torch.cat([t.reshape(n, -1) for t in tensor_list], dim=-1)
+    if data.requires_grad:
+        collected = _AllToAllRows.apply(data, in_splits, out_splits)
+    else:
+        collected = _all_to_all_rows(data, in_splits, out_splits)
+    outs = torch.split(collected, widths, dim=-1)
+    return [o.reshape(-1, *t.shape[1:]) for o, t in zip(outs, tensor_list)]
+
+
+def _find_free_port() -> int:
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:
+        sock.bind(("127.0.0.1", 0))
+        return sock.getsockname()[1]
+
+
+def _distributed_worker(world_rank: int, world_size: int, fn: Callable, args: Any, local_rank: Optional[int] = None,
+                        verbose: bool = False) -> bool:
+    if local_rank is None:
+        local_rank = world_rank
+    if verbose:
+        print("Distributed worker: %d / %d" % (world_rank + 1, world_size))
+    if world_size > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", world_size=world_size, rank=world_rank,
+                                device_id=torch.device("cuda", local_rank))
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)  # build the communicator before the first timed collective
+    fn(local_rank, world_rank, world_size, args)
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if verbose:
+        print("Job Done for worker: %d / %d" % (world_rank + 1, world_size))
+    return True
+
+
+def cli(fn: Callable, args: Any, verbose: bool = False) -> bool:
+    """Run ``fn(local_rank, world_rank, world_size, args)`` on every visible GPU (one process each).
+
+    Launch modes: under torchrun / OpenMPI the env's rank is used; otherwise processes are spawned.
+    """
+    assert torch.cuda.is_available(), "CUDA device is required!"
+    for size_key, rank_key, local_key in (("WORLD_SIZE", "RANK", "LOCAL_RANK"),
+                                          ("OMPI_COMM_WORLD_SIZE", "OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_LOCAL_RANK")):
+        if size_key in os.environ and rank_key in os.environ:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29500")
+            return _distributed_worker(int(os.environ[rank_key]), int(os.environ[size_key]), fn, args,
+                                       int(os.environ.get(local_key, 0)), verbose)
+    world_size = torch.cuda.device_count()
+    if world_size <= 1:
+        return _distributed_worker(0, 1, fn=fn, args=args)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_find_free_port())
+    ctx = torch.multiprocessing.spawn(_distributed_worker, args=(world_size, fn, args, None, verbose),
+                                      nprocs=world_size, join=False)
+    try:
+        ctx.join()
+    except KeyboardInterrupt:
+        for p in ctx.processes:
+            if p.is_alive():
+                p.terminate()
+            p.join()
+    return True

@@ -1,0 +1,209 @@
+"""`rasterization()` -- the render API of the hot path, same signature / returns / `meta` schema as the
+reference's ``gsplat.rendering.rasterization`` (gsplat/rendering.py:28-582, meta keys :337-349 and
+:512-525) so ``examples/simple_trainer*.py`` and ``profiling/main.py`` call it unchanged.
+
+Orchestration differences from the reference (behaviour-preserving):
+  * tile offsets come out of the per-tile intersection stage; there is no separate
+    isect_offset_encode pass over the sorted keys;
+  * for SH colours the camera position is read off the rigid view matrix (-R^T t) instead of a
+    batched LU inverse of [C,4,4] (rendering.py:370); `torch.inverse` is used only if the matrix is
+    not rigid;
+  * distributed mode (view-parallel, attribute all-gather) lives in ``distributed.py``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+from typing_extensions import Literal
+
+from .cuda._wrapper import (
+    _isect_tiles_with_offsets,
+    fully_fused_projection,
+    rasterize_to_pixels,
+    spherical_harmonics,
+)
+
+
+def _camera_positions(viewmats: Tensor) -> Tensor:
+    """World-space camera centres [C,3] of world-to-camera matrices [C,4,4]."""
+    R = viewmats[:, :3, :3]
+    t = viewmats[:, :3, 3]
+    # rigid transform: inverse(viewmat)[:3,3] = -R^T t ; differentiable w.r.t. viewmats
+    return -(R.transpose(1, 2) @ t[..., None])[..., 0]
+
+
+def rasterization(
+    means: Tensor,  # [N, 3]
+    quats: Tensor,  # [N, 4]
+    scales: Tensor,  # [N, 3]
+    opacities: Tensor,  # [N]
+    colors: Tensor,  # [(C,) N, D] or [(C,) N, K, 3]
+    viewmats: Tensor,  # [C, 4, 4]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    eps2d: float = 0.3,
+    sh_degree: Optional[int] = None,
+    packed: bool = True,
+    tile_size: int = 16,
+    backgrounds: Optional[Tensor] = None,
+    render_mode: Literal["RGB", "D", "ED", "RGB+D", "RGB+ED"] = "RGB",
+    sparse_grad: bool = False,
+    absgrad: bool = False,
+    rasterize_mode: Literal["classic", "antialiased"] = "classic",
+    channel_chunk: int = 32,
+    distributed: bool = False,
+    camera_model: Literal["pinhole", "ortho", "fisheye"] = "pinhole",
+    covars: Optional[Tensor] = None,
+    rigid_viewmats: bool = True,
+) -> Tuple[Tensor, Tensor, Dict]:
+    """Rasterize a set of 3D Gaussians (N) to a batch of image planes (C).
+
+    Returns (render_colors [C,H,W,X], render_alphas [C,H,W,1], meta).  See the reference docstring
+    (gsplat/rendering.py:55-222) for the meaning of every argument; `rigid_viewmats` is additive.
+    """
+    meta: Dict = {}
+    N = means.shape[0]
+    C = viewmats.shape[0]
+    device = means.device
+    assert means.shape == (N, 3), means.shape
+    if covars is None:
+        assert quats.shape == (N, 4), quats.shape
+        assert scales.shape == (N, 3), scales.shape
+    else:
+        assert covars.shape == (N, 3, 3), covars.shape
+        quats, scales = None, None
+        tri = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
+        covars = covars[..., tri[0], tri[1]]
+    assert opacities.shape == (N,), opacities.shape
+    assert viewmats.shape == (C, 4, 4), viewmats.shape
+    assert Ks.shape == (C, 3, 3), Ks.shape
+    assert render_mode in ["RGB", "D", "ED", "RGB+D", "RGB+ED"], render_mode
+
+    if sh_degree is None:
+        assert (colors.dim() == 2 and colors.shape[0] == N) or (
+            colors.dim() == 3 and colors.shape[:2] == (C, N)
+        ), colors.shape
+        if distributed:
+            assert colors.dim() == 2, "Distributed mode only supports per-Gaussian colors."
+    else:
+        assert (colors.dim() == 3 and colors.shape[0] == N and colors.shape[2] == 3) or (
+            colors.dim() == 4 and colors.shape[:2] == (C, N) and colors.shape[3] == 3
+        ), colors.shape
+        assert (sh_degree + 1) ** 2 <= colors.shape[-2], colors.shape
+        if distributed:
+            assert colors.dim() == 3, "Distributed mode only supports per-Gaussian colors."
+
+    if absgrad:
+        assert not distributed, "AbsGrad is not supported in distributed mode."
+
+    if distributed:
+        # view-parallel: every rank owns a slice of the Gaussians and its own cameras; attributes are
+        # all-gathered (autograd-aware: the backward is a reduce-scatter of attribute gradients) and
+        # each rank then renders its cameras from the full set.  Replaces the reference's
+        # project-everywhere + all-to-all exchange (rendering.py:282-294, 397-478); same API, gradients
+        # reach the owner rank.
+        from .distributed import all_gather_attributes
+
+        gathered = all_gather_attributes(
+            [t for t in (means, quats, scales, opacities, colors, covars) if t is not None])
+        it = iter(gathered)
+        means = next(it)
+        if covars is None:
+            quats, scales = next(it), next(it)
+        opacities, colors = next(it), next(it)
+        if covars is not None:
+            covars = next(it)
+        N = means.shape[0]
+
+    proj_results = fully_fused_projection(
+        means, covars, quats, scales, viewmats, Ks, width, height,
+        eps2d=eps2d, packed=packed, near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip,
+        sparse_grad=sparse_grad, calc_compensations=(rasterize_mode == "antialiased"), camera_model=camera_model,
+    )
+    if packed:
+        camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = proj_results
+        opacities = opacities[gaussian_ids]  # [nnz]
+    else:
+        radii, means2d, depths, conics, compensations = proj_results
+        opacities = opacities.repeat(C, 1)  # [C, N]
+        camera_ids, gaussian_ids = None, None
+    if compensations is not None:
+        opacities = opacities * compensations
+
+    meta.update({
+        "camera_ids": camera_ids, "gaussian_ids": gaussian_ids, "radii": radii, "means2d": means2d,
+        "depths": depths, "conics": conics, "opacities": opacities,
+    })
+
+    if sh_degree is None:
+        if packed:
+            colors = colors[gaussian_ids] if colors.dim() == 2 else colors[camera_ids, gaussian_ids]
+        else:
+            colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
+    else:
+        campos = _camera_positions(viewmats) if rigid_viewmats else torch.inverse(viewmats)[:, :3, 3]
+        if packed:
+            dirs = means[gaussian_ids, :] - campos[camera_ids]  # [nnz, 3]
+            masks = radii > 0
+            shs = colors[gaussian_ids, :, :] if colors.dim() == 3 else colors[camera_ids, gaussian_ids, :, :]
+        else:
+            dirs = means[None, :, :] - campos[:, None, :]  # [C, N, 3]
+            masks = radii > 0
+            shs = colors.expand(C, -1, -1, -1) if colors.dim() == 3 else colors
+        colors = spherical_harmonics(sh_degree, dirs, shs, masks=masks)
+        colors = torch.clamp_min(colors + 0.5, 0.0)
+
+    if render_mode in ["RGB+D", "RGB+ED"]:
+        colors = torch.cat((colors, depths[..., None]), dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device)], dim=-1)
+    elif render_mode in ["D", "ED"]:
+        colors = depths[..., None]
+        if backgrounds is not None:
+            backgrounds = torch.zeros(C, 1, device=backgrounds.device)
+
+    tile_width = math.ceil(width / float(tile_size))
+    tile_height = math.ceil(height / float(tile_size))
+    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = _isect_tiles_with_offsets(
+        means2d, radii, depths, tile_size, tile_width, tile_height,
+        packed=packed, n_cameras=C, camera_ids=camera_ids, gaussian_ids=gaussian_ids,
+    )
+    meta.update({
+        "tile_width": tile_width, "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss,
+        "isect_ids": isect_ids, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets,
+        "width": width, "height": height, "tile_size": tile_size, "n_cameras": C,
+    })
+
+    if colors.shape[-1] > channel_chunk:
+        n_chunks = (colors.shape[-1] + channel_chunk - 1) // channel_chunk
+        render_colors, render_alphas = [], []
+        for i in range(n_chunks):
+            colors_chunk = colors[..., i * channel_chunk:(i + 1) * channel_chunk]
+            backgrounds_chunk = (
+                backgrounds[..., i * channel_chunk:(i + 1) * channel_chunk] if backgrounds is not None else None
+            )
+            rc, ra = rasterize_to_pixels(
+                means2d, conics, colors_chunk, opacities, width, height, tile_size, isect_offsets, flatten_ids,
+                backgrounds=backgrounds_chunk, packed=packed, absgrad=absgrad,
+            )
+            render_colors.append(rc)
+            render_alphas.append(ra)
+        render_colors = torch.cat(render_colors, dim=-1)
+        render_alphas = render_alphas[0]
+    else:
+        render_colors, render_alphas = rasterize_to_pixels(
+            means2d, conics, colors, opacities, width, height, tile_size, isect_offsets, flatten_ids,
+            backgrounds=backgrounds, packed=packed, absgrad=absgrad,
+        )
+    if render_mode in ["ED", "RGB+ED"]:
+        render_colors = torch.cat(
+            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1
+        )
+    return render_colors, render_alphas, meta

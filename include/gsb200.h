@@ -1,0 +1,191 @@
+/*
+ * gsb200.h -- C-ABI of the B200-native Gaussian-splat rasterization hot path.
+ *
+ * This is the drop-in boundary.  In the reference the same role is played by the pybind11 module
+ * `_C` (gsplat/cuda/csrc/ext.cpp:3-92, signatures in gsplat/cuda/include/bindings.h:41-502) that
+ * gsplat/cuda/_wrapper.py resolves by name (_wrapper.py:9-16).  Every entry point below names the
+ * `_C.<symbol>` it replaces.  Differences forced by a C ABI (no torch types):
+ *   - the CALLER allocates every output (the reference op allocates torch tensors itself,
+ *     e.g. fully_fused_projection_fwd.cu:236-245); data-dependent sizes use a two-call protocol
+ *     exactly where the reference synchronises with the host (isect_tiles.cu:199-200);
+ *   - all pointers are device pointers to contiguous float32/int32/int64 arrays unless stated;
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*) and returns immediately,
+ *     except gsb200_isect_prepare which returns the intersection count to the host;
+ *   - return value: 0 on success, non-zero error code otherwise; gsb200_last_error() gives the
+ *     message (the reference raises RuntimeError through TORCH_CHECK, bindings.h:10-16).
+ * Gradient outputs are OVERWRITTEN (not accumulated) unless documented otherwise.
+ */
+#ifndef GSB200_H
+#define GSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB200_ABI_VERSION 1
+
+/* camera models: bindings.h:34-39 / ext.cpp:4-8 */
+#define GSB200_CAMERA_PINHOLE 0
+#define GSB200_CAMERA_ORTHO 1
+#define GSB200_CAMERA_FISHEYE 2
+
+typedef void *gsb200_stream_t;
+
+int gsb200_abi_version(void);
+const char *gsb200_last_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t gsb200_launch_count(void);
+
+/* ---------------------------------------------------------------- stage 1: projection
+ * replaces _C.fully_fused_projection_fwd (bindings.h:94-115, fully_fused_projection_fwd.cu:22-196).
+ * means [N,3]; covars [N,6] (xx,xy,xz,yy,yz,zz) or NULL; quats [N,4] wxyz + scales [N,3] or NULL;
+ * viewmats [C,4,4]; Ks [C,3,3].  Outputs radii i32 [C,N], means2d [C,N,2], depths [C,N],
+ * conics [C,N,3], compensations [C,N] or NULL.  Culled entries get radii = 0 and ZERO in the other
+ * outputs (the reference leaves them uninitialised).  packed_radius_rule != 0 selects the radius
+ * formula of the packed reference kernel (fully_fused_projection_packed_fwd.cu:183-186). */
+int gsb200_projection_fwd(uint32_t C, uint32_t N, const float *means, const float *covars,
+                          const float *quats, const float *scales, const float *viewmats,
+                          const float *Ks, uint32_t image_width, uint32_t image_height, float eps2d,
+                          float near_plane, float far_plane, float radius_clip, int camera_model,
+                          int packed_radius_rule, int32_t *radii, float *means2d, float *depths,
+                          float *conics, float *compensations, gsb200_stream_t stream);
+
+/* replaces _C.fully_fused_projection_bwd (bindings.h:117-145, fully_fused_projection_bwd.cu:24-263).
+ * v_means [N,3], v_covars [N,6] (covars path) or v_quats [N,4] + v_scales [N,3], v_viewmats [C,4,4]
+ * or NULL.  All gradient outputs are overwritten with the sum over cameras. */
+int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means, const float *covars,
+                          const float *quats, const float *scales, const float *viewmats,
+                          const float *Ks, uint32_t image_width, uint32_t image_height, float eps2d,
+                          int camera_model, const int32_t *radii, const float *conics,
+                          const float *compensations, const float *v_means2d, const float *v_depths,
+                          const float *v_conics, const float *v_compensations, float *v_means,
+                          float *v_covars, float *v_quats, float *v_scales, float *v_viewmats,
+                          gsb200_stream_t stream);
+
+/* packed (COO) projection: replaces _C.fully_fused_projection_packed_fwd
+ * (bindings.h:253-276, fully_fused_projection_packed_fwd.cu:22-249).  Two calls:
+ *   1. gsb200_compact_count: from dense radii [C,N] count visible pairs; writes block_offsets
+ *      (scratch, (C*N+2047)/2048+1 int32) and returns nnz through *nnz_host (synchronises `stream`).
+ *   2. gsb200_compact_fill: writes indptr i32 [C+1], camera_ids/gaussian_ids i64 [nnz] and gathers
+ *      the dense rows into packed radii/means2d/depths/conics/compensations (row order =
+ *      (camera, gaussian) lexicographic, as the reference emits). */
+int gsb200_compact_count(uint32_t C, uint32_t N, const int32_t *radii, int32_t *block_offsets,
+                         int64_t *nnz_host, gsb200_stream_t stream);
+int gsb200_compact_fill(uint32_t C, uint32_t N, const int32_t *radii, const float *means2d,
+                        const float *depths, const float *conics, const float *compensations,
+                        const int32_t *block_offsets, int32_t *indptr, int64_t *camera_ids,
+                        int64_t *gaussian_ids, int32_t *p_radii, float *p_means2d, float *p_depths,
+                        float *p_conics, float *p_compensations, gsb200_stream_t stream);
+/* gradient scatter back to the dense layout used by gsb200_projection_bwd:
+ * dense v_means2d/v_depths/v_conics/v_compensations [C,N,*] are zero-filled then row r of the packed
+ * gradients is written at (camera_ids[r], gaussian_ids[r]).
+ * (stands in for _C.fully_fused_projection_packed_bwd, bindings.h:278-309, dense-gradient mode). */
+int gsb200_scatter_rows(uint32_t C, uint32_t N, int64_t nnz, const int64_t *camera_ids,
+                        const int64_t *gaussian_ids, const float *p_v_means2d,
+                        const float *p_v_depths, const float *p_v_conics,
+                        const float *p_v_compensations, float *v_means2d, float *v_depths,
+                        float *v_conics, float *v_compensations, gsb200_stream_t stream);
+
+/* ---------------------------------------------------------------- colour: spherical harmonics
+ * replaces _C.compute_sh_fwd / _C.compute_sh_bwd (bindings.h:234-248, compute_sh_fwd.cu:11-37,
+ * compute_sh_bwd.cu:13-51).  dirs [n,3] (un-normalised), coeffs [n,K,3], masks u8 [n] or NULL,
+ * colors [n,3].  Masked-out rows: colors = 0, v_coeffs = 0, v_dirs = 0.  Launched on `stream`
+ * (the reference uses the legacy default stream). */
+int gsb200_sh_fwd(uint32_t n, uint32_t K, uint32_t degree, const float *dirs, const float *coeffs,
+                  const uint8_t *masks, float *colors, gsb200_stream_t stream);
+int gsb200_sh_bwd(uint32_t n, uint32_t K, uint32_t degree, const float *dirs, const float *coeffs,
+                  const uint8_t *masks, const float *v_colors, float *v_coeffs, float *v_dirs,
+                  gsb200_stream_t stream);
+
+/* ---------------------------------------------------------------- stage 2: tile intersection
+ * replaces _C.isect_tiles + _C.isect_offset_encode (bindings.h:147-166, isect_tiles.cu:16-389) with
+ * a per-tile design: count -> tile histogram -> scan -> bucket scatter -> per-tile sort on
+ * (depth bits, flatten id).  Results are bit-identical to the reference's stable global radix sort.
+ *
+ *   1. gsb200_isect_prepare: n_elems = C*N (dense) or nnz (packed; camera_ids i64 [nnz] required).
+ *      Writes tiles_per_gauss i32 [n_elems] and isect_offsets i32 [C*tile_h*tile_w]; returns the
+ *      number of intersections through *n_isects_host (synchronises `stream`, like the reference's
+ *      .item() at isect_tiles.cu:200).  tile_cursor: scratch i32 [C*tile_h*tile_w].
+ *   2. gsb200_isect_fill: writes isect_ids i64 [I] and flatten_ids i32 [I], sorted.
+ *      scratch: u64 [I].  sort == 0 is not supported (returns an error). */
+int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
+                         const int64_t *camera_ids, const float *means2d, const int32_t *radii,
+                         uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                         int32_t *tiles_per_gauss, int32_t *isect_offsets, int32_t *tile_cursor,
+                         int64_t *n_isects_host, gsb200_stream_t stream);
+int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
+                      const int64_t *camera_ids, const float *means2d, const int32_t *radii,
+                      const float *depths, uint32_t tile_size, uint32_t tile_width,
+                      uint32_t tile_height, int64_t n_isects, const int32_t *isect_offsets,
+                      int32_t *tile_cursor, uint64_t *scratch, int64_t *isect_ids,
+                      int32_t *flatten_ids, gsb200_stream_t stream);
+/* stand-alone _C.isect_offset_encode (isect_tiles.cu:308-389) for callers that hold sorted ids */
+int gsb200_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, uint32_t C,
+                               uint32_t tile_width, uint32_t tile_height, int32_t *isect_offsets,
+                               gsb200_stream_t stream);
+
+/* ---------------------------------------------------------------- stage 3 / 4a: alpha blend
+ * replaces _C.rasterize_to_pixels_fwd (bindings.h:168-184, rasterize_to_pixels_fwd.cu:16-185).
+ * means2d [M,2], conics [M,3], colors [M,D], opacities [M] with M = C*N or nnz; backgrounds [C,D] or
+ * NULL; masks u8 [C,th,tw] or NULL; tile_offsets i32 [C,th,tw]; flatten_ids i32 [I].
+ * Outputs render_colors [C,H,W,D], render_alphas [C,H,W], last_ids i32 [C,H,W].
+ * D must be in {1,2,3,4,5,8,9,16,17,32,33} (the host pads others, as _wrapper.py:496-541 does). */
+int gsb200_rasterize_fwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
+                         const float *conics, const float *colors, const float *opacities,
+                         const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                         uint32_t image_height, uint32_t tile_size, uint32_t tile_width,
+                         uint32_t tile_height, const int32_t *tile_offsets,
+                         const int32_t *flatten_ids, float *render_colors, float *render_alphas,
+                         int32_t *last_ids, gsb200_stream_t stream);
+
+/* replaces _C.rasterize_to_pixels_bwd (bindings.h:186-215, rasterize_to_pixels_bwd.cu:17-277).
+ * Gradient outputs v_means2d [M,2], v_conics [M,3], v_colors [M,D], v_opacities [M] and, if not
+ * NULL, v_means2d_abs [M,2] are overwritten.  grad_scratch: float [M * gsb200_grad_record(D)],
+ * used for the packed per-Gaussian accumulation records. */
+uint32_t gsb200_grad_record(uint32_t D);
+int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
+                         const float *conics, const float *colors, const float *opacities,
+                         const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                         uint32_t image_height, uint32_t tile_size, uint32_t tile_width,
+                         uint32_t tile_height, const int32_t *tile_offsets,
+                         const int32_t *flatten_ids, const float *render_alphas,
+                         const int32_t *last_ids, const float *v_render_colors,
+                         const float *v_render_alphas, float *grad_scratch, float *v_means2d_abs,
+                         float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                         gsb200_stream_t stream);
+
+/* ---------------------------------------------------------------- quant-sim
+ * replaces the torch elementwise chain of fake_quantize_ste (compression_simulation/ops.py:39-75).
+ * mode 0 = "noise": y = act(clamp(x,lo,hi) + noise*q_step), noise [n] supplied or, if NULL, drawn
+ *          in-kernel from Philox(seed, offset); mask[i] = lo <= x <= hi (gradient gate).
+ * mode 1 = "round": x is clamped IN PLACE (ops.py:63), y = act(round_half_even((x-lo)/(hi-lo)/qs)
+ *          * qs * (hi-lo) + lo), qs = 1/(2^bits-1).
+ * act: 0 identity, 1 exp, 2 sigmoid -- the activation the trainer applies next
+ * (simple_trainer.py:758-776), fused here so the attribute is read once. */
+int gsb200_fake_quantize_fwd(int64_t n, float *x, float lo, float hi, int bitwidth, int mode, int act,
+                             const float *noise, uint64_t seed, uint64_t offset, float *y,
+                             gsb200_stream_t stream);
+/* v_x = v_y * act'(y) * (mode==0 ? [lo<=x<=hi] : 1) */
+int gsb200_fake_quantize_bwd(int64_t n, const float *x, const float *y, float lo, float hi, int mode,
+                             int act, const float *v_y, float *v_x, gsb200_stream_t stream);
+
+/* factorized-prior entropy model, replaces Entropy_factorized_optimized_refactor.forward
+ * (compression_simulation/entropy_model.py:201-254) incl. its channel-scrambled weight tiling.
+ * x [N,ch]; params: concatenated per layer i: softplus-ed matrix [ch,f(i+1),f(i)], bias [ch,f(i+1)],
+ * tanh-ed factor [ch,f(i+1)] (absent for the last layer), raw layout described in
+ * gscodec_studio_b200/compression_simulation/entropy_model.py.  n_hidden in {2,3} layers of width 3.
+ * bits [N,ch].  bwd: v_x [N,ch] and v_params (same layout as params, pre-activation chain rule is
+ * applied by the host).  v_params must be zero-initialised; it is accumulated atomically. */
+int gsb200_entropy_fwd(int64_t N, uint32_t ch, uint32_t n_hidden, const float *x, float q,
+                       const float *params, float likelihood_bound, float *bits,
+                       gsb200_stream_t stream);
+int gsb200_entropy_bwd(int64_t N, uint32_t ch, uint32_t n_hidden, const float *x, float q,
+                       const float *params, float likelihood_bound, const float *v_bits, float *v_x,
+                       float *v_params, gsb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H */

@@ -390,7 +390,7 @@ def rasterize_to_pixels(means2d, conics, colors, opacities, width, height, tile_
 def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, height,
                   near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, sh_degree=None,
                   tile_size=16, backgrounds=None, render_mode="RGB", rasterize_mode="classic",
-                  camera_model="pinhole", covars=None):
+                  camera_model="pinhole", covars=None, packed=False):
     C, N = viewmats.shape[0], means.shape[0]
     if covars is not None:
         idx = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
@@ -398,7 +398,7 @@ def rasterization(means, quats, scales, opacities, colors, viewmats, Ks, width, 
         quats = scales = None
     radii, means2d, depths, conics, comp = projection(
         means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
-        radius_clip, rasterize_mode == "antialiased", camera_model)
+        radius_clip, rasterize_mode == "antialiased", camera_model, packed_radius_rule=packed)
     opac = opacities[None, :].expand(C, N)
     if comp is not None:
         opac = opac * comp

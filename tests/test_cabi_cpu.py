@@ -1,0 +1,89 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/gsb200.h declares; the Python operator layer mirrors the reference's names; nothing silently
+falls back to the CPU.  No compute calls (there is no GPU here)."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gsb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gscodec_studio_b200 import _build, _cabi
+
+    _build.build_library()
+    lib = _cabi.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gsb200.h but not exported"
+        assert name in _cabi.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_cabi.SIGNATURES) == declared
+    assert lib.gsb200_abi_version() == _cabi.ABI_VERSION
+    assert lib.gsb200_grad_record(3) == 12 and lib.gsb200_grad_record(32) == 40
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    from gscodec_studio_b200 import _cabi
+
+    out = subprocess.run(["cuobjdump", "-lelf", _cabi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    archs = set(re.findall(r"sm_(\d+a?)", out.stdout))
+    assert archs == {"100a"}, archs
+
+
+def test_operator_layer_mirrors_reference_names():
+    import gscodec_studio_b200 as gs
+    from gscodec_studio_b200.cuda import _wrapper
+
+    expect = {
+        "spherical_harmonics": ["degrees_to_use", "dirs", "coeffs", "masks"],
+        "fully_fused_projection": ["means", "covars", "quats", "scales", "viewmats", "Ks", "width", "height", "eps2d",
+                                   "near_plane", "far_plane", "radius_clip", "packed", "sparse_grad",
+                                   "calc_compensations", "camera_model"],
+        "isect_tiles": ["means2d", "radii", "depths", "tile_size", "tile_width", "tile_height", "sort", "packed",
+                        "n_cameras", "camera_ids", "gaussian_ids"],
+        "isect_offset_encode": ["isect_ids", "n_cameras", "tile_width", "tile_height"],
+        "rasterize_to_pixels": ["means2d", "conics", "colors", "opacities", "image_width", "image_height", "tile_size",
+                                "isect_offsets", "flatten_ids", "backgrounds", "masks", "packed", "absgrad"],
+    }
+    for fn, params in expect.items():
+        assert list(inspect.signature(getattr(_wrapper, fn)).parameters) == params, fn
+        assert getattr(gs, fn) is getattr(_wrapper, fn)
+    sig = inspect.signature(gs.rasterization)
+    ref_order = ["means", "quats", "scales", "opacities", "colors", "viewmats", "Ks", "width", "height", "near_plane",
+                 "far_plane", "radius_clip", "eps2d", "sh_degree", "packed", "tile_size", "backgrounds", "render_mode",
+                 "sparse_grad", "absgrad", "rasterize_mode", "channel_chunk", "distributed", "camera_model", "covars"]
+    assert list(sig.parameters)[: len(ref_order)] == ref_order
+    assert sig.parameters["packed"].default is True and sig.parameters["tile_size"].default == 16
+    assert sig.parameters["eps2d"].default == 0.3 and sig.parameters["far_plane"].default == 1e10
+
+
+def test_no_cpu_fallback():
+    import gscodec_studio_b200 as gs
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gs.spherical_harmonics(1, torch.zeros(4, 3), torch.zeros(4, 4, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gs.fully_fused_projection(torch.zeros(4, 3), None, torch.ones(4, 4), torch.ones(4, 3), torch.eye(4)[None],
+                                  torch.eye(3)[None], 16, 16)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gscodec_studio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "_helper.py", os.path.join(dirpath, f)
