@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the rasterization hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload "M2" (SURVEY.md section 8d): load_test_data(scene_grid=3) -> 1 006 065 Gaussians in the trainer's
+parameterisation (log-scales, logit-opacities, SH degree 3 = sh0 + shN), one 1920x1080 view per GPU.
+One step = CompressionSimulation.simulate_compression (8-bit fake-quant, noise mode, on scales / quats /
+opacities / sh0) -> exp / sigmoid -> rasterization(sh_degree=3, packed=False) -> L1 loss against a
+target image -> backward to the RAW parameters.  Metric: Mpix/s = (pixels rendered per step over all
+GPUs) / (time of forward + backward).
+
+N > 1: the Gaussians are sharded across ranks (strided, like examples/simple_trainer.py:361-363), every
+rank renders its own view with rasterization(distributed=True): one NCCL all-gather of the attributes
+forward, one reduce-scatter of their gradients backward.  Weak scaling (one view per GPU).
+
+--impl reference: the reference's CPU path (oracle/: torch restatement of _torch_impl + the C blend,
+OpenMP over all host cores) on the same workload, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_IMG, H_IMG = 1920, 1080
+SH_C0 = 0.2820947917738781
+METRIC = "Mpix/s fwd+bwd @1M splats 1920x1080 w/ quant-sim"
+
+
+def build_workload(rank: int, world: int, scene_grid: int):
+    """CPU tensors of the raw trainer parameters for this rank's shard + this rank's camera + a target."""
+    from gscodec_studio_b200._helper import load_test_data
+
+    means, quats, scales, opac, colors, viewmats, Ks, w0, h0 = load_test_data(device="cpu", scene_grid=scene_grid, seed=42)
+    cam = rank % viewmats.shape[0]
+    viewmat, K = viewmats[cam:cam + 1].clone(), Ks[cam:cam + 1].clone()
+    K[:, 0, :] *= W_IMG / w0
+    K[:, 1, :] *= H_IMG / h0
+    n_total = means.shape[0]
+    gen = torch.Generator().manual_seed(7)
+    shN = torch.randn(n_total, 15, 3, generator=gen) * 0.05
+    raw = {
+        "means": means,
+        "scales": torch.log(scales.clamp_min(1e-8)),
+        "quats": quats,
+        "opacities": torch.logit(opac.clamp(1e-4, 1 - 1e-4)),
+        "sh0": ((colors - 0.5) / SH_C0)[:, None, :],
+        "shN": shN,
+    }
+    raw = {k: v[rank::world].contiguous() for k, v in raw.items()}
+    target = torch.rand(1, H_IMG, W_IMG, 3, generator=gen)
+    return raw, viewmat, K, target, n_total
+
+
+# ------------------------------------------------------------------------------------------ ours
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import gscodec_studio_b200 as gs
+    from gscodec_studio_b200 import _cabi
+    from gscodec_studio_b200.compression_simulation import CompressionSimulation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.load_library()  # fail loudly if the CUDA library is missing
+
+    raw_cpu, viewmat_cpu, K_cpu, target_cpu, n_total = build_workload(rank, world, args.scene_grid)
+    params = {k: v.to(dev).requires_grad_(True) for k, v in raw_cpu.items()}
+    # pinned host copies of the per-step inputs (camera + target image) for the end-to-end leg
+    host_in = [t.pin_memory() for t in (viewmat_cpu, K_cpu, target_cpu)]
+    dev_in = [t.to(dev) for t in host_in]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_in)
+    sim = CompressionSimulation(entropy_model_enable=args.entropy,
+                                entropy_steps={"means": -1, "scales": 0, "quats": 0, "opacities": -1, "sh0": 0, "shN": -1},
+                                device=dev)
+    sim_step = 20_000 if args.entropy else 100
+    state = {}
+
+    def step(viewmat, K, target):
+        for p in params.values():
+            p.grad = None
+        new, bits = sim.simulate_compression(params, sim_step, fuse_activations=True)
+        scales = new["scales_act"] if "scales_act" in new else torch.exp(new["scales"])
+        opac = new["opacities_act"] if "opacities_act" in new else torch.sigmoid(new["opacities"])
+        colors = torch.cat([new["sh0"], new["shN"]], 1)
+        rc, ra, meta = gs.rasterization(new["means"], new["quats"], scales, opac, colors, viewmat, K, W_IMG, H_IMG,
+                                        sh_degree=3, packed=False, near_plane=0.01, far_plane=100.0, radius_clip=3.0,
+                                        distributed=world > 1)
+        loss = (rc - target).abs().mean()
+        for b in bits.values():
+            if b is not None:
+                loss = loss + 1e-9 * b.sum()
+        loss.backward()
+        state["meta"] = meta
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        last = None
+        for _ in range(n_steps):
+            if e2e:
+                for h, d in zip(host_in, dev_in):
+                    d.copy_(h, non_blocking=True)
+                last = float(step(*dev_in).item())  # device -> host read of the step's result
+            else:
+                last = step(*dev_in)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), last
+
+    for _ in range(max(args.warmup, 3)):
+        step(*dev_in)
+    launches0 = _cabi.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _cabi.enable_stage_timing(True)
+    ms, loss = timed(args.steps, e2e=False)
+    stage_ms = _cabi.stage_timing_ms()  # per C-ABI entry point, averaged per call
+    _cabi.enable_stage_timing(False)
+    launches = _cabi.launch_count() - launches0
+    ms_e2e, _ = timed(args.steps, e2e=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    pix = W_IMG * H_IMG * world
+    value = pix * args.steps / (ms * 1e-3) / 1e6
+    value_e2e = pix * args.steps / (ms_e2e * 1e-3) / 1e6
+
+    if rank == 0:
+        meta = state["meta"]
+        n_isects = int(meta["isect_ids"].numel())
+        D, P = 3, W_IMG * H_IMG
+        bytes_fwd = (28 + 4 * D) * n_isects + (4 * D + 8) * P
+        bytes_bwd = (28 + 4 * D) * n_isects + (24 + 4 * D) * n_isects + (4 * D + 12) * P
+        t_fwd = stage_ms.get("gsb200_rasterize_fwd", float("nan"))
+        t_bwd = stage_ms.get("gsb200_rasterize_bwd", float("nan"))
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = (bytes_fwd + bytes_bwd) / ((t_fwd + t_bwd) * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"M2: load_test_data(scene_grid={args.scene_grid}) {n_total} Gaussians, 1 view 1920x1080 per GPU, "
+                            "SH deg 3, 8-bit noise fake-quant (scales,quats,opacities,sh0) fused with exp/sigmoid, "
+                            "packed=False, L1 loss, fwd+bwd to raw params" + (", factorized entropy model on" if args.entropy else ""),
+                "n_isects": n_isects, "l2": "inputs larger than L2 (236 MB of splat attributes + 25 MB image per step)",
+                "parallelism": f"view-parallel x{world}, attribute all-gather" if world > 1 else "single GPU",
+            },
+            "e2e": {"value": round(value_e2e, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": None,
+                "kernel": "blend fwd + bwd (gsb200_rasterize_fwd/_bwd)", "peak_source": "measured" if peaks else "fallback",
+                "algorithmic_bytes": {"fwd": bytes_fwd, "bwd": bytes_bwd},
+                "launch_ms": {"fwd": round(t_fwd, 4), "bwd": round(t_bwd, 4)},
+                "note": "blend is FP32/MUFU-issue bound, see DESIGN.md; stage_ms holds every stage",
+            },
+            "stage_ms": {k.replace("gsb200_", ""): round(v, 4) for k, v in sorted(stage_ms.items())},
+            "loss": float(loss.item()) if torch.is_tensor(loss) else loss,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.scene_grid, steps=1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_factory(scene_grid: int):
+    from oracle import oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    O.set_num_threads(os.cpu_count() or 1)
+    raw, viewmat, K, target, n_total = build_workload(0, 1, scene_grid)
+    params = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+    gen = torch.Generator().manual_seed(3)
+    bounds = {"scales": (-10, 2), "quats": (-1, 1), "opacities": (-15, 15), "sh0": (-2, 4)}
+
+    def step():
+        for p in params.values():
+            p.grad = None
+        q = {}
+        for name, (lo, hi) in bounds.items():
+            noise = torch.rand(params[name].shape, generator=gen) - 0.5
+            q[name], _ = O.fake_quantize_noise(params[name], lo, hi, 8, noise)
+        colors = torch.cat([q["sh0"], params["shN"] + 0.0], 1)
+        rc, ra, meta = O.rasterization(params["means"] + 0.0, q["quats"], torch.exp(q["scales"]), torch.sigmoid(q["opacities"]),
+                                       colors, viewmat, K, W_IMG, H_IMG, near_plane=0.01, far_plane=100.0, radius_clip=3.0,
+                                       sh_degree=3)
+        loss = (rc - target).abs().mean()
+        loss.backward()
+        return float(loss)
+
+    return step, n_total
+
+
+def cpu_baseline(scene_grid: int, steps: int = 1):
+    step, n_total = cpu_step_factory(scene_grid)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(W_IMG * H_IMG / dt / 1e6, 4), "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{steps} full step(s) of the same workload (1 view 1920x1080, {n_total} Gaussians, fwd+bwd) on the "
+                      "CPU oracle: torch restatement of _torch_impl + C/OpenMP blend", "s_per_step": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, n_total = cpu_step_factory(args.scene_grid)
+    steps = max(1, min(args.steps, 8))  # bounded: each CPU step is a full frame (seconds)
+    warm = 1 if args.warmup > 0 else 0
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = round(W_IMG * H_IMG / dt / 1e6, 4)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"M2: load_test_data(scene_grid={args.scene_grid}) {n_total} Gaussians, 1 view 1920x1080, SH deg 3, "
+                               "8-bit noise fake-quant, fwd+bwd to raw params -- reference CPU path (oracle port), rank 0 only"},
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{steps} full step(s), 1 warm-up; steps capped at 8 to bound CPU time"},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--scene-grid", dest="scene_grid", type=int, default=3)
+    ap.add_argument("--entropy", action="store_true", help="also run the factorized entropy model on scales/quats/sh0")
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -105,9 +105,34 @@ def aligned(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t
 
 
+_stage_events = None  # name -> list of (start, end) CUDA events, when stage timing is on
+
+
+def enable_stage_timing(on: bool) -> None:
+    """Record a CUDA-event pair around every C-ABI call (on the stream the kernels are launched on).
+    Used by bench.py to attribute device time to stages inside the timed region."""
+    global _stage_events
+    _stage_events = {} if on else None
+
+
+def stage_timing_ms() -> dict:
+    """Average device milliseconds per call for every entry point seen since enable_stage_timing(True)."""
+    if not _stage_events:
+        return {}
+    torch.cuda.synchronize()
+    return {name: sum(a.elapsed_time(b) for a, b in evs) / len(evs) for name, evs in _stage_events.items() if evs}
+
+
 def call(name: str, *args) -> None:
     lib = load_library()
-    rc = getattr(lib, name)(*args)
+    if _stage_events is not None:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        rc = getattr(lib, name)(*args)
+        end.record()
+        _stage_events.setdefault(name, []).append((start, end))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.gsb200_last_error()
         raise RuntimeError(f"{name} failed ({rc}): {msg.decode() if msg else 'unknown error'}")

@@ -15,7 +15,12 @@ from gscodec_studio_b200.cuda import _wrapper as W  # noqa: E402
 DEV = torch.device("cuda:0")
 
 
+ONCE = os.environ.get("ONCE") == "1"  # under ncu: one launch per kernel is enough
+
+
 def timeit(fn, n=20, warm=3):
+    if ONCE:
+        n, warm = 1, 0
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
