@@ -37,6 +37,8 @@ SIGNATURES = {
     "gsb200_scatter_rows": [_U, _U, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_fwd": [_U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_sh_bwd": [_U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_sh_view_fwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P],
+    "gsb200_sh_view_bwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_isect_prepare": [_U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_fill": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _L, _P, _P, _P, _P, _P, _P],
     "gsb200_isect_offset_encode": [_L, _P, _U, _U, _U, _P, _P],

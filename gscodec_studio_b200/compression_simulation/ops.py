@@ -62,9 +62,9 @@ class _FakeQuantize(torch.autograd.Function):
         with torch.cuda.device(x.device):
             call("gsb200_fake_quantize_fwd", xin.numel(), ptr(xin), float(lo), float(hi), int(bitwidth), mode, act,
                  ptr(noise), seed, offset, ptr(y), stream_ptr(x.device))
-        if mode == 1:
-            ctx.mark_dirty(x)
-        ctx.save_for_backward(xin, y)
+        # round mode wrote the clamped values through `x` (like the reference's input.clamp_ inside
+        # STE.forward, which also does not tell autograd about it)
+        ctx.save_for_backward(xin if mode == 0 else xin.detach(), y)
         ctx.cfg = (float(lo), float(hi), mode, act)
         return y.view_as(x)
 

@@ -49,21 +49,63 @@ __device__ __forceinline__ void pixel_in_tile(uint32_t ts, uint32_t tid, uint32_
     }
 }
 
-// half extents of the bounding box of { d : 0.5 d^T A d <= ln(255 * opac) } with safety margin;
-// +inf (always evaluate) when the conic is not positive definite, -inf when no pixel can pass.
-__device__ __forceinline__ void cull_extent(float a, float b, float c, float opac, float &hx, float &hy) {
-    const float det = a * c - b * b;
+// Cull parameter of one Gaussian: q_max = 2 ln(255 * opac) (+ margin).  A pixel at offset d from the
+// centre can pass the reference's alpha >= 1/255 test only if d^T A d <= q_max.  FLT_MAX (always
+// evaluate) when the conic is not positive definite, negative (never) when no pixel can pass.
+__device__ __forceinline__ float cull_qmax(float a, float b, float c, float opac) {
     const float tau = __logf(255.f * opac);
-    if (!(opac > 0.f) || !(tau >= 0.f)) {
-        if (opac * 255.f >= 1.f) { hx = hy = FLT_MAX; }  // NaN / inf guard: keep
-        else { hx = hy = -FLT_MAX; }
-        return;
-    }
-    if (!(det > 0.f) || !(a > 0.f) || !(c > 0.f)) { hx = hy = FLT_MAX; return; }
-    const float k = 2.f * (tau * 1.001f + 1e-3f) / det;
-    hx = sqrtf(k * c) * 1.001f + 0.05f;
-    hy = sqrtf(k * a) * 1.001f + 0.05f;
+    if (!(opac > 0.f) || !(tau >= 0.f)) return (opac * 255.f >= 1.f) ? FLT_MAX : -1.f;  // first case: NaN / inf guard
+    if (!(a * c - b * b > 0.f) || !(a > 0.f) || !(c > 0.f)) return FLT_MAX;
+    return 2.f * (tau * 1.001f + 1e-3f);
 }
+
+// Exact test "does the ellipse { d : d^T A d <= qmax } around (mx,my) meet the pixel-centre rectangle
+// [x0,x1] x [y0,y1]?" -- the minimum of the convex form over the rectangle is 0 if the centre is inside,
+// otherwise it is attained on one of the four edges (a clamped 1-D parabola each).  A margin proportional
+// to the magnitude of the terms keeps the test conservative under float32 rounding, so it never drops a
+// (pixel, Gaussian) pair the reference arithmetic would accept.
+__device__ __forceinline__ bool ellipse_hits_rect(float mx, float my, float a, float b, float c, float qmax, float x0,
+                                                  float x1, float y0, float y1) {
+    if (!(qmax >= 0.f)) return false;
+    if (qmax == FLT_MAX) return true;
+    const float lx0 = x0 - mx, lx1 = x1 - mx, ly0 = y0 - my, ly1 = y1 - my;
+    if (lx0 <= 0.f && lx1 >= 0.f && ly0 <= 0.f && ly1 >= 0.f) return true;
+    const float ia = __frcp_rn(a), ic = __frcp_rn(c);
+    float q = FLT_MAX;
+    {
+        float dy = fminf(fmaxf(-b * lx0 * ic, ly0), ly1);
+        q = fminf(q, a * lx0 * lx0 + 2.f * b * lx0 * dy + c * dy * dy);
+        dy = fminf(fmaxf(-b * lx1 * ic, ly0), ly1);
+        q = fminf(q, a * lx1 * lx1 + 2.f * b * lx1 * dy + c * dy * dy);
+        float dx = fminf(fmaxf(-b * ly0 * ia, lx0), lx1);
+        q = fminf(q, a * dx * dx + 2.f * b * dx * ly0 + c * ly0 * ly0);
+        dx = fminf(fmaxf(-b * ly1 * ia, lx0), lx1);
+        q = fminf(q, a * dx * dx + 2.f * b * dx * ly1 + c * ly1 * ly1);
+    }
+    const float ex = fmaxf(fabsf(lx0), fabsf(lx1)), ey = fmaxf(fabsf(ly0), fabsf(ly1));
+    const float slack = 1e-5f * (a * ex * ex + 2.f * fabsf(b) * ex * ey + c * ey * ey) + 1e-4f;
+    return q <= qmax + slack;
+}
+
+// shared-memory accesses through 32-bit shared-window addresses (keeps the address arithmetic out of
+// the inner loop; generic pointers make the compiler rebuild the window base every iteration)
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds1i(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+template <int CDIM> struct ColorPad { static constexpr int value = (CDIM + 3) / 4 * 4; };
 
 template <int CDIM>
 __global__ void __launch_bounds__(kBatch)
@@ -72,12 +114,15 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                  const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
                  const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
                  float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
+    constexpr int CP = ColorPad<CDIM>::value;
     extern __shared__ float4 smem4[];
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
-    const uint32_t batch = min(nthreads, (uint32_t)kBatch);
-    float4 *sA = smem4;                               // x, y, opacity, hx
-    float4 *sB = sA + batch;                          // conic a, b, c, hy
-    float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CDIM]
+    const uint32_t batch = nthreads;
+    float4 *sA = smem4;                                 // x, y, opacity, qmax
+    float4 *sB = sA + batch;                            // conic a, b, c, -
+    float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CP]
+    const uint32_t aA = (uint32_t)__cvta_generic_to_shared(sA), aB = (uint32_t)__cvta_generic_to_shared(sB),
+                   aC = (uint32_t)__cvta_generic_to_shared(sC);
 
     const uint32_t cam = blockIdx.z, tile_id = blockIdx.y * G.tw + blockIdx.x;
     uint32_t lx, ly;
@@ -117,18 +162,16 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
         // barrier protects the staging buffers; stop when every pixel of the tile is saturated
         if (__syncthreads_count(done) >= (int)nthreads) break;
         const int32_t idx = batch_start + (int32_t)tid;
-        if (tid < batch && idx < range_end) {
+        if (idx < range_end) {
             const int32_t g = flatten_ids[idx];
             const float2 xy = __ldg(means2d + g);
             const float opac = __ldg(opacities + g);
             const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
                         cc = __ldg(conics + (size_t)g * 3 + 2);
-            float hx, hy;
-            cull_extent(ca, cb, cc, opac, hx, hy);
-            sA[tid] = make_float4(xy.x, xy.y, opac, hx);
-            sB[tid] = make_float4(ca, cb, cc, hy);
+            sA[tid] = make_float4(xy.x, xy.y, opac, cull_qmax(ca, cb, cc, opac));
+            sB[tid] = make_float4(ca, cb, cc, 0.f);
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k) sC[tid * CDIM + k] = __ldg(colors + (size_t)g * CDIM + k);
+            for (int k = 0; k < CDIM; ++k) sC[tid * CP + k] = __ldg(colors + (size_t)g * CDIM + k);
         }
         __syncthreads();
         if (warp_done) continue;
@@ -137,17 +180,16 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
             const uint32_t e = c0 + lane;
             bool hit = false;
             if (e < bsize) {
-                const float4 A = sA[e];
-                const float hy = sB[e].w;
-                hit = (A.x + A.w >= wx0) && (A.x - A.w <= wx1) && (A.y + hy >= wy0) && (A.y - hy <= wy1);
+                const float4 A = lds4(aA + e * 16), B = lds4(aB + e * 16);
+                hit = ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, A.w, wx0, wx1, wy0, wy1);
             }
             unsigned m = __ballot_sync(wmask, hit);
             while (m) {
                 const uint32_t t = c0 + (uint32_t)__ffs(m) - 1u;
                 m &= m - 1;
                 if (!done) {
-                    const float4 A = sA[t];
-                    const float4 B = sB[t];
+                    const float4 A = lds4(aA + t * 16);
+                    const float4 B = lds4(aB + t * 16);
                     const float dx = A.x - px, dy = A.y - py;
                     const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
                     const float alpha = fminf(kAlphaMax, A.z * __expf(-sigma));
@@ -158,7 +200,13 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                         } else {
                             const float vis = alpha * T;
 #pragma unroll
-                            for (int k = 0; k < CDIM; ++k) pix_out[k] += sC[t * CDIM + k] * vis;
+                            for (int k4 = 0; k4 < CP; k4 += 4) {
+                                const float4 c4 = lds4(aC + (t * CP + k4) * 4);
+                                pix_out[k4] += c4.x * vis;
+                                if (k4 + 1 < CDIM) pix_out[k4 + 1] += c4.y * vis;
+                                if (k4 + 2 < CDIM) pix_out[k4 + 2] += c4.z * vis;
+                                if (k4 + 3 < CDIM) pix_out[k4 + 3] += c4.w * vis;
+                            }
                             cur_idx = (uint32_t)batch_start + t;
                             T = next_T;
                         }
@@ -209,26 +257,30 @@ __device__ __forceinline__ uint32_t spread_slot(uint32_t lane) {
 // packed gradient record (floats): [rgb(CDIM) | conic(3) | xy(2) | opac(1) | abs(2)] rounded up to 4
 __host__ __device__ constexpr uint32_t grad_record(uint32_t cdim) { return (cdim + 8 + 3) / 4 * 4; }
 
-template <int CDIM>
+template <int CDIM, bool ABS>
 __global__ void __launch_bounds__(kBatch)
 blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
                  const float *__restrict__ colors, const float *__restrict__ opacities,
                  const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
                  const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
                  const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
-                 const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas, bool absgrad,
+                 const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas,
                  float *__restrict__ grad_rec) {
     constexpr uint32_t REC = grad_record(CDIM);
-    constexpr int NVAL = CDIM + 8;          // rgb, conic, xy, opac, abs
-    constexpr int NGRP = (NVAL + 7) / 8;    // groups of 8 values, each reduced with reduce_spread<8>
+    constexpr int CP = ColorPad<CDIM>::value;
+    // values reduced per (warp, Gaussian): [rgb(CDIM) conic(3) xy(2)] in groups of 8, then the tail
+    // [opac] (one butterfly) or [opac absx absy 0] (one 4-wide spread) when abs-gradients are wanted
+    constexpr int NMAIN = CDIM + 5;
+    constexpr int NGRP = (NMAIN + 7) / 8;
     extern __shared__ float4 smem4[];
     __shared__ int s_binmax;
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
-    const uint32_t batch = min(nthreads, (uint32_t)kBatch);
-    float4 *sA = smem4;                                 // x, y, opacity, hx
-    float4 *sB = sA + batch;                            // conic a, b, c, hy
-    float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CDIM]
-    int32_t *sId = reinterpret_cast<int32_t *>(sC + batch * CDIM);
+    const uint32_t batch = nthreads;
+    float4 *sA = smem4;                                 // x, y, opacity, qmax
+    float4 *sB = sA + batch;                            // conic a, b, c, flatten id (bits)
+    float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CP]
+    const uint32_t aA = (uint32_t)__cvta_generic_to_shared(sA), aB = (uint32_t)__cvta_generic_to_shared(sB),
+                   aC = (uint32_t)__cvta_generic_to_shared(sC);
 
     const uint32_t cam = blockIdx.z, tile_id = blockIdx.y * G.tw + blockIdx.x;
     const size_t ct = (size_t)cam * G.tw * G.th + tile_id;
@@ -270,9 +322,9 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     __syncthreads();
     range_end = min(range_end, s_binmax + 1);
 
-    // lanes that publish totals: group gi, value slot -> record offset
-    const bool publisher = (lane & 3) == 0;
-    const uint32_t slot8 = spread_slot<8>(lane);
+    // lanes that publish totals after reduce_spread<8> / <4>
+    const uint32_t slot8 = spread_slot<8>(lane), slot4 = spread_slot<4>(lane);
+    const bool pub8 = (lane & 3) == 0, pub4 = (lane & 7) == 0;
 
     for (int32_t batch_end = range_end - 1; batch_end >= range_start; batch_end -= (int32_t)batch) {
         __syncthreads();
@@ -283,13 +335,10 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
             const float opac = __ldg(opacities + g);
             const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
                         cc = __ldg(conics + (size_t)g * 3 + 2);
-            float hx, hy;
-            cull_extent(ca, cb, cc, opac, hx, hy);
-            sA[tid] = make_float4(xy.x, xy.y, opac, hx);
-            sB[tid] = make_float4(ca, cb, cc, hy);
-            sId[tid] = g;
+            sA[tid] = make_float4(xy.x, xy.y, opac, cull_qmax(ca, cb, cc, opac));
+            sB[tid] = make_float4(ca, cb, cc, __int_as_float(g));
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k) sC[tid * CDIM + k] = __ldg(colors + (size_t)g * CDIM + k);
+            for (int k = 0; k < CDIM; ++k) sC[tid * CP + k] = __ldg(colors + (size_t)g * CDIM + k);
         }
         __syncthreads();
         if (warp_bin_final < 0) continue;
@@ -299,16 +348,15 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
             const int32_t e = c0 + (int32_t)lane;
             bool hit = false;
             if (e < bsize) {
-                const float4 A = sA[e];
-                const float hy = sB[e].w;
-                hit = (A.x + A.w >= wx0) && (A.x - A.w <= wx1) && (A.y + hy >= wy0) && (A.y - hy <= wy1);
+                const float4 A = lds4(aA + e * 16), B = lds4(aB + e * 16);
+                hit = ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, A.w, wx0, wx1, wy0, wy1);
             }
             unsigned m = __ballot_sync(wmask, hit);
             while (m) {
                 const int32_t t = c0 + __ffs(m) - 1;
                 m &= m - 1;
-                const float4 A = sA[t];
-                const float4 B = sB[t];
+                const float4 A = lds4(aA + t * 16);
+                const float4 B = lds4(aB + t * 16);
                 const float dx = A.x - px, dy = A.y - py;
                 const float opac = A.z;
                 const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
@@ -317,6 +365,7 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                 const bool valid = inside && (batch_end - t <= bin_final) && !(sigma < 0.f || alpha < kAlphaMin);
                 if (!__any_sync(wmask, valid)) continue;
                 float vals[NGRP * 8];
+                float tail[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int k = 0; k < NGRP * 8; ++k) vals[k] = 0.f;
                 if (valid) {
@@ -325,11 +374,18 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                     const float fac = alpha * T;
                     float v_alpha = 0.f;
 #pragma unroll
-                    for (int k = 0; k < CDIM; ++k) {
-                        const float ck = sC[t * CDIM + k];
-                        vals[k] = fac * v_c[k];
-                        v_alpha += (ck * T - buffer[k] * ra) * v_c[k];
-                        buffer[k] += ck * fac;
+                    for (int k4 = 0; k4 < CP; k4 += 4) {
+                        const float4 c4 = lds4(aC + (t * CP + k4) * 4);
+                        const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int k = k4 + q;
+                            if (k < CDIM) {
+                                vals[k] = fac * v_c[k];
+                                v_alpha += (cs[q] * T - buffer[k] * ra) * v_c[k];
+                                buffer[k] += cs[q] * fac;
+                            }
+                        }
                     }
                     v_alpha += T_final * ra * v_a;
                     if (bg) v_alpha += -T_final * ra * bg_dot;
@@ -342,19 +398,23 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                         const float gy = v_sigma * (B.y * dx + B.z * dy);
                         vals[CDIM + 3] = gx;
                         vals[CDIM + 4] = gy;
-                        vals[CDIM + 5] = vis * v_alpha;
-                        vals[CDIM + 6] = fabsf(gx);
-                        vals[CDIM + 7] = fabsf(gy);
+                        tail[0] = vis * v_alpha;
+                        if (ABS) { tail[1] = fabsf(gx); tail[2] = fabsf(gy); }
                     }
                 }
-                float *rec = grad_rec + (size_t)sId[t] * REC;
+                float *rec = grad_rec + (size_t)__float_as_int(B.w) * REC;
 #pragma unroll
                 for (int gi = 0; gi < NGRP; ++gi) {
                     reduce_spread<8>(vals + gi * 8, lane);
                     const uint32_t off = gi * 8 + slot8;
-                    // skip padding slots and, unless requested, the abs-gradient slots
-                    const bool live = off < (uint32_t)NVAL && (absgrad || off < (uint32_t)(CDIM + 6));
-                    if (publisher && live) red_add(rec + off, vals[gi * 8]);
+                    if (pub8 && off < (uint32_t)NMAIN) red_add(rec + off, vals[gi * 8]);
+                }
+                if (ABS) {
+                    reduce_spread<4>(tail, lane);
+                    if (pub4 && slot4 < 3) red_add(rec + NMAIN + slot4, tail[0]);
+                } else {
+                    const float s = warp_sum(tail[0]);
+                    if (lane == 0) red_add(rec + NMAIN, s);
                 }
             }
         }
@@ -390,7 +450,7 @@ static int launch_fwd(const BlendGeom &G, const float *means2d, const float *con
                       cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
     const uint32_t batch = nthreads;
-    const size_t smem = (size_t)batch * (32 + 4 * CDIM);
+    const size_t smem = (size_t)batch * (32 + 4 * ColorPad<CDIM>::value);
     if (smem > 48 * 1024)
         GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(G.tw, G.th, G.C);
@@ -408,16 +468,22 @@ static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, cons
                       float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
     const uint32_t batch = nthreads;
-    const size_t smem = (size_t)batch * (32 + 4 * CDIM + 4);
-    if (smem > 48 * 1024)
-        GSB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)batch * (32 + 4 * ColorPad<CDIM>::value);
+    if (smem > 48 * 1024) {
+        GSB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     GSB_CUDA_OK(cudaMemsetAsync(grad_scratch, 0, sizeof(float) * (size_t)M * grad_record(CDIM), s));
     if (G.n_isects > 0) {
         dim3 grid(G.tw, G.th, G.C);
-        blend_bwd_kernel<CDIM><<<grid, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
-                                                             opacities, backgrounds, masks, tile_offsets, flatten_ids,
-                                                             render_alphas, last_ids, v_render_colors, v_render_alphas,
-                                                             v_abs != nullptr, grad_scratch);
+        if (v_abs != nullptr)
+            blend_bwd_kernel<CDIM, true><<<grid, nthreads, smem, s>>>(
+                G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,
+                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch);
+        else
+            blend_bwd_kernel<CDIM, false><<<grid, nthreads, smem, s>>>(
+                G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,
+                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch);
         if (int e = check_launch("blend_bwd")) return e;
     }
     unpack_grads_kernel<CDIM><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors,

@@ -37,24 +37,58 @@ __device__ __forceinline__ TileBox tile_box(float mx, float my, float radius, fl
     return b;
 }
 
+// Warp-cooperative walk over the tile boxes of the 32 Gaussians a warp owns: for every Gaussian with a
+// non-empty box the whole warp visits its tiles as a (rows x columns) patch -- lanes along x first, so
+// one warp-wide atomic touches adjacent counters (one or two 32-byte sectors) instead of 32 unrelated
+// ones, and large boxes (up to ~200 tiles) are spread over the lanes instead of serialising one thread.
+// f(tile_index_within_camera, lane_is_active) is called convergently by all lanes.
+template <typename F>
+__device__ __forceinline__ void for_each_tile_coop(bool has, const TileBox &b, uint32_t tw, F &&f) {
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, has);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t x0 = __shfl_sync(0xffffffffu, b.x0, src), y0 = __shfl_sync(0xffffffffu, b.y0, src);
+        const uint32_t nx = __shfl_sync(0xffffffffu, b.x1, src) - x0, ny = __shfl_sync(0xffffffffu, b.y1, src) - y0;
+        for (uint32_t xb = 0; xb < nx; xb += 32) {
+            const uint32_t w = min(32u, nx - xb);
+            const uint32_t sh = w <= 1 ? 0 : 32 - __clz(w - 1);  // log2 of the padded patch width
+            const uint32_t c = lane & ((1u << sh) - 1u), r = lane >> sh, rows = 32u >> sh;
+            for (uint32_t yb = 0; yb < ny; yb += rows) {
+                const bool on = c < w && yb + r < ny;
+                f(src, (y0 + yb + r) * tw + x0 + xb + c, on);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 isect_count_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids, const float *__restrict__ means2d,
                    const int32_t *__restrict__ radii, float ts, uint32_t tw, uint32_t th,
                    int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts) {
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
-    const int32_t r = radii[i];
-    if (r <= 0) { tiles_per_gauss[i] = 0; return; }
-    const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + i);
-    const TileBox b = tile_box(m.x, m.y, (float)r, ts, tw, th);
-    const uint32_t nx = b.x1 > b.x0 ? b.x1 - b.x0 : 0, ny = b.y1 > b.y0 ? b.y1 - b.y0 : 0;
-    // (tile_max - tile_min) products are computed in uint32 in the reference; empty boxes give 0
-    tiles_per_gauss[i] = (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0));
-    if (nx == 0 || ny == 0) return;
-    const uint32_t cam = camera_ids ? (uint32_t)camera_ids[i] : i / per_cam;
-    int32_t *cnt = tile_counts + (size_t)cam * tw * th;
-    for (uint32_t y = b.y0; y < b.y1; ++y)
-        for (uint32_t x = b.x0; x < b.x1; ++x) atomicAdd(cnt + y * tw + x, 1);
+    TileBox b = {0, 0, 0, 0};
+    uint32_t cam = 0;
+    bool has = false;
+    if (i < n) {
+        const int32_t r = radii[i];
+        int32_t tiles = 0;
+        if (r > 0) {
+            const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + i);
+            b = tile_box(m.x, m.y, (float)r, ts, tw, th);
+            // the reference multiplies the two uint32 extents (isect_tiles.cu:73-76)
+            tiles = (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0));
+            has = b.x1 > b.x0 && b.y1 > b.y0;
+            cam = camera_ids ? (uint32_t)camera_ids[i] : i / per_cam;
+        }
+        tiles_per_gauss[i] = tiles;
+    }
+    const uint32_t n_tiles = tw * th;
+    for_each_tile_coop(has, b, tw, [&](int src, uint32_t tile, bool on) {
+        const uint32_t c = __shfl_sync(0xffffffffu, cam, src);
+        if (on) atomicAdd(tile_counts + (size_t)c * n_tiles + tile, 1);
+    });
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -62,20 +96,29 @@ isect_scatter_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ c
                      const int32_t *__restrict__ radii, const float *__restrict__ depths, float ts, uint32_t tw, uint32_t th,
                      int32_t *__restrict__ tile_cursor, uint64_t *__restrict__ bucket) {
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n) return;
-    const int32_t r = radii[i];
-    if (r <= 0) return;
-    const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + i);
-    const TileBox b = tile_box(m.x, m.y, (float)r, ts, tw, th);
-    if (b.x1 <= b.x0 || b.y1 <= b.y0) return;
-    const uint32_t cam = camera_ids ? (uint32_t)camera_ids[i] : i / per_cam;
-    int32_t *cur = tile_cursor + (size_t)cam * tw * th;
-    const uint64_t item = ((uint64_t)__float_as_uint(depths[i]) << 32) | (uint64_t)i;
-    for (uint32_t y = b.y0; y < b.y1; ++y)
-        for (uint32_t x = b.x0; x < b.x1; ++x) {
-            const int32_t slot = atomicAdd(cur + y * tw + x, 1);
-            bucket[slot] = item;
+    TileBox b = {0, 0, 0, 0};
+    uint32_t cam = 0, depth_bits = 0;
+    bool has = false;
+    if (i < n) {
+        const int32_t r = radii[i];
+        if (r > 0) {
+            const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + i);
+            b = tile_box(m.x, m.y, (float)r, ts, tw, th);
+            has = b.x1 > b.x0 && b.y1 > b.y0;
+            cam = camera_ids ? (uint32_t)camera_ids[i] : i / per_cam;
+            depth_bits = __float_as_uint(depths[i]);
         }
+    }
+    const uint32_t n_tiles = tw * th;
+    for_each_tile_coop(has, b, tw, [&](int src, uint32_t tile, bool on) {
+        const uint32_t c = __shfl_sync(0xffffffffu, cam, src);
+        const uint32_t d = __shfl_sync(0xffffffffu, depth_bits, src);
+        const uint32_t id = __shfl_sync(0xffffffffu, i, src);
+        if (on) {
+            const int32_t slot = atomicAdd(tile_cursor + (size_t)c * n_tiles + tile, 1);
+            bucket[slot] = ((uint64_t)d << 32) | (uint64_t)id;
+        }
+    });
 }
 
 // one compare-exchange sub-step of the normalized bitonic network over a[0..n): every comparison
@@ -114,26 +157,32 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *a, uint32_t n) {
     }
 }
 
-constexpr uint32_t kSortSmem = 4096;  // 32 KB of 64-bit items per CTA
+constexpr uint32_t kSortSmall = 2048;   // items a 256-thread CTA sorts in 16 KB of static shared memory
+constexpr uint32_t kSortLarge = 12288;  // items a 1024-thread CTA sorts in 96 KB of dynamic shared memory
 
-__global__ void __launch_bounds__(kThreads)
+// One CTA per (camera, tile).  LARGE = false handles segments of up to kSortSmall items, LARGE = true
+// the (few) longer ones -- in shared memory up to kSortLarge items, in place in global memory (L2
+// resident) beyond that.  Both kernels are launched over all tiles and exit early on the other class.
+template <bool LARGE>
+__global__ void __launch_bounds__(LARGE ? 1024 : kThreads)
 tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, int64_t n_isects,
                  const int32_t *__restrict__ offsets, uint64_t *__restrict__ bucket, int64_t *__restrict__ isect_ids,
                  int32_t *__restrict__ flatten_ids) {
-    __shared__ uint64_t s_items[kSortSmem];
+    extern __shared__ uint64_t s_dyn[];
+    __shared__ uint64_t s_static[LARGE ? 1 : kSortSmall];
     const uint32_t ct = blockIdx.x;
     const int64_t start = offsets[ct];
     const int64_t end = (ct + 1 == n_tiles_total) ? n_isects : (int64_t)offsets[ct + 1];
     const uint32_t n = (uint32_t)(end - start);
-    if (n == 0) return;
+    if (n == 0 || (LARGE ? n <= kSortSmall : n > kSortSmall)) return;
     const uint64_t cam = ct / n_tiles, tile = ct % n_tiles;
     const int64_t hi = (int64_t)((cam << (32 + tile_bits)) | (tile << 32));
     uint64_t *a;
-    if (n <= kSortSmem) {
-        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) s_items[t] = bucket[start + t];
-        a = s_items;
+    if (!LARGE || n <= kSortLarge) {
+        a = LARGE ? s_dyn : s_static;
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) a[t] = bucket[start + t];
     } else {
-        a = bucket + start;  // rare oversized tile: same network, in place in global memory (L2 resident)
+        a = bucket + start;
     }
     __syncthreads();
     if (n > 1) bitonic_sort(a, n);
@@ -225,9 +274,18 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
                                                                        camera_ids, means2d, radii, depths, (float)tile_size,
                                                                        tile_width, tile_height, tile_cursor, scratch);
     if (int e = check_launch("isect_scatter")) return e;
-    tile_sort_kernel<<<C * n_tiles, kThreads, 0, s>>>(C * n_tiles, n_tiles, bit_width(n_tiles), n_isects, isect_offsets,
-                                                       scratch, isect_ids, flatten_ids);
-    return check_launch("tile_sort");
+    tile_sort_kernel<false><<<C * n_tiles, kThreads, 0, s>>>(C * n_tiles, n_tiles, bit_width(n_tiles), n_isects,
+                                                              isect_offsets, scratch, isect_ids, flatten_ids);
+    if (int e = check_launch("tile_sort")) return e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kSortLarge * sizeof(uint64_t))));
+        attr_set = true;
+    }
+    tile_sort_kernel<true><<<C * n_tiles, 1024, kSortLarge * sizeof(uint64_t), s>>>(
+        C * n_tiles, n_tiles, bit_width(n_tiles), n_isects, isect_offsets, scratch, isect_ids, flatten_ids);
+    return check_launch("tile_sort_large");
 }
 
 extern "C" int gsb200_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, uint32_t C, uint32_t tile_width,

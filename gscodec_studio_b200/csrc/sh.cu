@@ -171,6 +171,147 @@ sh_bwd_kernel(uint32_t n, uint32_t K, const float *__restrict__ dirs, const floa
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// View-dependent colour of every (camera, Gaussian) pair in one pass: dirs = mean - camera position,
+// SH -> RGB, + 0.5, clamp at 0 (gsplat/rendering.py:370-392 does this with a batched inverse, a
+// subtraction, an expand, the SH op, an add and a clamp -- six kernels and an [C,N,K,3] broadcast whose
+// backward is a 193 MB reduction).  One thread owns one Gaussian and loops over the cameras: the
+// coefficient row is read once, the per-camera gradients are summed in registers and each v_coeffs row
+// is written exactly once.
+template <int DEG>
+__global__ void __launch_bounds__(kThreads)
+sh_view_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__ means, const float *__restrict__ campos,
+                   const float *__restrict__ coeffs, const int32_t *__restrict__ radii, float *__restrict__ colors, bool vec) {
+    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
+    if (g >= N) return;
+    constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
+    bool any = false;
+    for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
+    float cf[nb * 3 + 3];
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (any) {
+        const float *row = coeffs + (size_t)g * K * 3;
+        if (vec) {
+#pragma unroll
+            for (uint32_t k = 0; k < nb * 3; k += 4) {
+                const float4 v = ldg4(row + k);
+                cf[k] = v.x; cf[k + 1] = v.y; cf[k + 2] = v.z; cf[k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < nb * 3; ++k) cf[k] = __ldg(row + k);
+        }
+        mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
+    }
+    for (uint32_t c = 0; c < C; ++c) {
+        const size_t idx = (size_t)c * N + g;
+        float r = 0.f, gg = 0.f, b = 0.f;
+        if (radii[idx] > 0) {
+            float x = mx - campos[c * 3], y = my - campos[c * 3 + 1], z = mz - campos[c * 3 + 2];
+            if (DEG > 0) {
+                const float inorm = rsqrtf(x * x + y * y + z * z);
+                x *= inorm; y *= inorm; z *= inorm;
+            }
+            sh_terms(DEG, x, y, z, [&](int k, float Y, float, float, float) {
+                r += Y * cf[k * 3]; gg += Y * cf[k * 3 + 1]; b += Y * cf[k * 3 + 2];
+            });
+            r = fmaxf(r + 0.5f, 0.f); gg = fmaxf(gg + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
+        }
+        colors[idx * 3] = r; colors[idx * 3 + 1] = gg; colors[idx * 3 + 2] = b;
+    }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kThreads)
+sh_view_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__ means, const float *__restrict__ campos,
+                   const float *__restrict__ coeffs, const int32_t *__restrict__ radii, const float *__restrict__ v_colors,
+                   float *__restrict__ v_coeffs, float *__restrict__ v_means, float *__restrict__ v_campos, bool vec) {
+    __shared__ float s_red[kThreads / 32][3];
+    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
+    constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
+    const uint32_t nfl = K * 3;
+    float vc[nb * 3 + 3];
+#pragma unroll
+    for (uint32_t k = 0; k < nb * 3 + 3; ++k) vc[k] = 0.f;
+    float vmx = 0.f, vmy = 0.f, vmz = 0.f;
+    bool any = false;
+    if (g < N)
+        for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
+    float cf[nb * 3 + 3];
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (any) {
+        const float *row = coeffs + (size_t)g * K * 3;
+        if (vec) {
+#pragma unroll
+            for (uint32_t k = 0; k < nb * 3; k += 4) {
+                const float4 v = ldg4(row + k);
+                cf[k] = v.x; cf[k + 1] = v.y; cf[k + 2] = v.z; cf[k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < nb * 3; ++k) cf[k] = __ldg(row + k);
+        }
+        mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
+    }
+    for (uint32_t c = 0; c < C; ++c) {
+        float dxv = 0.f, dyv = 0.f, dzv = 0.f;
+        if (any && radii[(size_t)c * N + g] > 0) {
+            const size_t idx = (size_t)c * N + g;
+            float x = mx - campos[c * 3], y = my - campos[c * 3 + 1], z = mz - campos[c * 3 + 2];
+            float inorm = 1.f;
+            if (DEG > 0) {
+                inorm = rsqrtf(x * x + y * y + z * z);
+                x *= inorm; y *= inorm; z *= inorm;
+            }
+            // recompute the pre-clamp colour for the clamp gate (torch: gradient passes where x + 0.5 >= 0)
+            float r = 0.f, gg = 0.f, b = 0.f;
+            sh_terms(DEG, x, y, z, [&](int k, float Y, float, float, float) {
+                r += Y * cf[k * 3]; gg += Y * cf[k * 3 + 1]; b += Y * cf[k * 3 + 2];
+            });
+            const float vr = (r + 0.5f >= 0.f) ? v_colors[idx * 3] : 0.f;
+            const float vg = (gg + 0.5f >= 0.f) ? v_colors[idx * 3 + 1] : 0.f;
+            const float vb = (b + 0.5f >= 0.f) ? v_colors[idx * 3 + 2] : 0.f;
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+            sh_terms(DEG, x, y, z, [&](int k, float Y, float dx, float dy, float dz) {
+                vc[k * 3] += Y * vr; vc[k * 3 + 1] += Y * vg; vc[k * 3 + 2] += Y * vb;
+                const float wk = cf[k * 3] * vr + cf[k * 3 + 1] * vg + cf[k * 3 + 2] * vb;
+                gx += dx * wk; gy += dy * wk; gz += dz * wk;
+            });
+            if (DEG > 0) {
+                const float dotp = gx * x + gy * y + gz * z;
+                dxv = (gx - dotp * x) * inorm; dyv = (gy - dotp * y) * inorm; dzv = (gz - dotp * z) * inorm;
+                vmx += dxv; vmy += dyv; vmz += dzv;
+            }
+        }
+        if (v_campos != nullptr) {  // d dirs / d campos = -1: block reduction, one atomic set per block and camera
+            const float sx = warp_sum(dxv), sy = warp_sum(dyv), sz = warp_sum(dzv);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5][0] = sx; s_red[threadIdx.x >> 5][1] = sy; s_red[threadIdx.x >> 5][2] = sz; }
+            __syncthreads();
+            if (threadIdx.x < 3) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < kThreads / 32; ++w) t += s_red[w][threadIdx.x];
+                if (t != 0.f) atomicAdd(v_campos + c * 3 + threadIdx.x, -t);
+            }
+        }
+    }
+    if (g >= N) return;
+    float *vrow = v_coeffs + (size_t)g * nfl;
+    if (vec) {
+#pragma unroll
+        for (uint32_t k = 0; k + 3 < nb * 3; k += 4) stg4(vrow + k, make_float4(vc[k], vc[k + 1], vc[k + 2], vc[k + 3]));
+        for (uint32_t k = nb * 3; k < nfl; k += 4) stg4(vrow + k, make_float4(0.f, 0.f, 0.f, 0.f));
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < nb * 3; ++k) vrow[k] = vc[k];
+        for (uint32_t k = nb * 3; k < nfl; ++k) vrow[k] = 0.f;
+    }
+    if (v_means != nullptr) {
+        v_means[(size_t)g * 3] = vmx; v_means[(size_t)g * 3 + 1] = vmy; v_means[(size_t)g * 3 + 2] = vmz;
+    }
+}
+
 }  // namespace gsb200
 
 using namespace gsb200;
@@ -214,4 +355,47 @@ extern "C" int gsb200_sh_bwd(uint32_t n, uint32_t K, uint32_t degree, const floa
         default: sh_bwd_kernel<4><<<grid, kThreads, 0, s>>>(n, K, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs, false); break;
     }
     return check_launch("sh_bwd");
+}
+
+static bool sh_vec_ok(uint32_t K, uint32_t degree, const void *a, const void *b) {
+    return ((K * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && (b == nullptr || (reinterpret_cast<uintptr_t>(b) & 15) == 0) &&
+           (((degree + 1) * (degree + 1) * 3) % 4 == 0);
+}
+
+extern "C" int gsb200_sh_view_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
+                                  const float *coeffs, const int32_t *radii, float *colors, gsb200_stream_t stream) {
+    if (degree > 4) return fail(2, "gsb200_sh_view_fwd: degree must be <= 4");
+    if ((degree + 1) * (degree + 1) > K) return fail(2, "gsb200_sh_view_fwd: coeffs hold fewer than (degree+1)^2 bases");
+    if (C == 0 || N == 0) return 0;
+    const bool vec = sh_vec_ok(K, degree, coeffs, nullptr);
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t grid = cdiv(N, kThreads);
+    switch (degree) {
+        case 0: sh_view_fwd_kernel<0><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
+        case 1: sh_view_fwd_kernel<1><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
+        case 2: sh_view_fwd_kernel<2><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
+        case 3: sh_view_fwd_kernel<3><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
+        default: sh_view_fwd_kernel<4><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
+    }
+    return check_launch("sh_view_fwd");
+}
+
+extern "C" int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
+                                  const float *coeffs, const int32_t *radii, const float *v_colors, float *v_coeffs,
+                                  float *v_means, float *v_campos, gsb200_stream_t stream) {
+    if (degree > 4) return fail(2, "gsb200_sh_view_bwd: degree must be <= 4");
+    if ((degree + 1) * (degree + 1) > K) return fail(2, "gsb200_sh_view_bwd: coeffs hold fewer than (degree+1)^2 bases");
+    if (C == 0 || N == 0) return 0;
+    const bool vec = sh_vec_ok(K, degree, coeffs, v_coeffs);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (v_campos != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_campos, 0, sizeof(float) * 3 * C, s));
+    const uint32_t grid = cdiv(N, kThreads);
+    switch (degree) {
+        case 0: sh_view_bwd_kernel<0><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
+        case 1: sh_view_bwd_kernel<1><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
+        case 2: sh_view_bwd_kernel<2><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
+        case 3: sh_view_bwd_kernel<3><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
+        default: sh_view_bwd_kernel<4><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
+    }
+    return check_launch("sh_view_bwd");
 }

@@ -90,6 +90,46 @@ class _SphericalHarmonics(torch.autograd.Function):
         return None, v_dirs, v_coeffs, None
 
 
+def view_colors_from_sh(sh_degree: int, means: Tensor, campos: Tensor, coeffs: Tensor, radii: Tensor) -> Tensor:
+    """Fused dense colour stage: max(SH(means - campos) . coeffs + 0.5, 0) for every (camera, Gaussian)
+    with radii > 0 (zero elsewhere).  means [N,3], campos [C,3], coeffs [N,K,3], radii i32 [C,N] -> [C,N,3].
+    Equivalent to the dirs / expand / spherical_harmonics / +0.5 / clamp_min chain of
+    gsplat/rendering.py:370-392 (additive entry point; the un-fused ops stay available)."""
+    N, C = means.shape[0], campos.shape[0]
+    assert means.shape == (N, 3) and campos.shape == (C, 3), (means.shape, campos.shape)
+    assert coeffs.dim() == 3 and coeffs.shape[0] == N and coeffs.shape[2] == 3, coeffs.shape
+    assert (sh_degree + 1) ** 2 <= coeffs.shape[1], coeffs.shape
+    assert radii.shape == (C, N), radii.shape
+    return _ShView.apply(sh_degree, means.contiguous(), campos.contiguous(), coeffs.contiguous(), radii.contiguous())
+
+
+class _ShView(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree, means, campos, coeffs, radii):
+        means, campos, coeffs = _f32(means), _f32(campos), _f32(coeffs)
+        C, N, K = campos.shape[0], means.shape[0], coeffs.shape[1]
+        colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
+        with torch.cuda.device(means.device):
+            call("gsb200_sh_view_fwd", C, N, K, sh_degree, ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(colors),
+                 stream_ptr(means.device))
+        ctx.save_for_backward(means, campos, coeffs, radii)
+        ctx.sh_degree = sh_degree
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, campos, coeffs, radii = ctx.saved_tensors
+        C, N, K = campos.shape[0], means.shape[0], coeffs.shape[1]
+        v_colors = _f32(v_colors.contiguous())
+        v_coeffs = torch.empty_like(coeffs)
+        v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+        v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(means.device):
+            call("gsb200_sh_view_bwd", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ptr(coeffs), ptr(radii),
+                 ptr(v_colors), ptr(v_coeffs), ptr(v_means), ptr(v_campos), stream_ptr(means.device))
+        return None, v_means, v_campos, v_coeffs, None
+
+
 # --------------------------------------------------------------------------------------
 # projection
 # --------------------------------------------------------------------------------------

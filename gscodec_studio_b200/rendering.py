@@ -24,6 +24,7 @@ from .cuda._wrapper import (
     fully_fused_projection,
     rasterize_to_pixels,
     spherical_harmonics,
+    view_colors_from_sh,
 )
 
 
@@ -149,16 +150,18 @@ def rasterization(
             colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
     else:
         campos = _camera_positions(viewmats) if rigid_viewmats else torch.inverse(viewmats)[:, :3, 3]
-        if packed:
+        if not packed and colors.dim() == 3:
+            # dense layout, per-Gaussian coefficients: one fused kernel (dirs, SH, +0.5, clamp)
+            colors = view_colors_from_sh(sh_degree, means, campos, colors, radii)
+        elif packed:
             dirs = means[gaussian_ids, :] - campos[camera_ids]  # [nnz, 3]
             masks = radii > 0
             shs = colors[gaussian_ids, :, :] if colors.dim() == 3 else colors[camera_ids, gaussian_ids, :, :]
+            colors = torch.clamp_min(spherical_harmonics(sh_degree, dirs, shs, masks=masks) + 0.5, 0.0)
         else:
             dirs = means[None, :, :] - campos[:, None, :]  # [C, N, 3]
             masks = radii > 0
-            shs = colors.expand(C, -1, -1, -1) if colors.dim() == 3 else colors
-        colors = spherical_harmonics(sh_degree, dirs, shs, masks=masks)
-        colors = torch.clamp_min(colors + 0.5, 0.0)
+            colors = torch.clamp_min(spherical_harmonics(sh_degree, dirs, colors, masks=masks) + 0.5, 0.0)
 
     if render_mode in ["RGB+D", "RGB+ED"]:
         colors = torch.cat((colors, depths[..., None]), dim=-1)

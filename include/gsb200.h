@@ -99,6 +99,20 @@ int gsb200_sh_bwd(uint32_t n, uint32_t K, uint32_t degree, const float *dirs, co
                   const uint8_t *masks, const float *v_colors, float *v_coeffs, float *v_dirs,
                   gsb200_stream_t stream);
 
+/* fused view-dependent colour for the dense layout: for every camera c and Gaussian g with radii > 0
+ *   colors[c,g,:] = max(SH_degree(means[g] - campos[c]) . coeffs[g] + 0.5, 0)      (0 where radii <= 0)
+ * i.e. gsplat/rendering.py:370-392 (dirs, expand, compute_sh_fwd, + 0.5, clamp_min) in one pass over
+ * coeffs [N,K,3] shared by all cameras.  campos [C,3] are the camera centres.  The backward overwrites
+ * v_coeffs [N,K,3] (summed over cameras) and v_means [N,3] (may be NULL) and, when not NULL, v_campos
+ * [C,3] (= -sum of the direction gradients). */
+int gsb200_sh_view_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                       const float *campos, const float *coeffs, const int32_t *radii, float *colors,
+                       gsb200_stream_t stream);
+int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                       const float *campos, const float *coeffs, const int32_t *radii,
+                       const float *v_colors, float *v_coeffs, float *v_means, float *v_campos,
+                       gsb200_stream_t stream);
+
 /* ---------------------------------------------------------------- stage 2: tile intersection
  * replaces _C.isect_tiles + _C.isect_offset_encode (bindings.h:147-166, isect_tiles.cu:16-389) with
  * a per-tile design: count -> tile histogram -> scan -> bucket scatter -> per-tile sort on

@@ -567,3 +567,31 @@ def test_compression_simulation_policy():
     assert dyn["scales"].min() >= -10 and dyn["scales"].max() <= 2 and not torch.equal(before, dyn["scales"])
     levels = (new["scales"] + 10) / (12 / 255)
     assert (levels - levels.round()).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3, 4])
+def test_fused_view_colors_match_unfused_chain(deg):
+    """view_colors_from_sh == clamp_min(spherical_harmonics(means - campos, coeffs) + 0.5, 0), forward and
+    backward (incl. the sum over cameras and the camera-position gradient)."""
+    from gscodec_studio_b200.cuda._wrapper import view_colors_from_sh
+
+    g = torch.Generator().manual_seed(30 + deg)
+    N, C, K = 3001, 3, 25 if deg == 4 else 16
+    means = torch.randn(N, 3, generator=g)
+    campos = torch.randn(C, 3, generator=g) * 3
+    coeffs = torch.randn(N, K, 3, generator=g) * 0.7
+    radii = (torch.rand(C, N, generator=g) > 0.4).int() * 5
+    w = torch.randn(C, N, 3, generator=g)
+    a = [t.clone().to(DEV).requires_grad_(True) for t in (means, campos, coeffs)]
+    b = [t.clone().requires_grad_(True) for t in (means, campos, coeffs)]
+    fused = view_colors_from_sh(deg, a[0], a[1], a[2], radii.to(DEV))
+    dirs = b[0][None] - b[1][:, None]
+    ref = torch.clamp_min(O.spherical_harmonics(deg, dirs, b[2][None].expand(C, -1, -1, -1), radii > 0) + 0.5, 0.0)
+    ref = torch.where((radii > 0)[..., None], ref, torch.zeros_like(ref))
+    assert rel_err(fused, ref) < 1e-5
+    (fused * w.to(DEV)).sum().backward()
+    (ref * w).sum().backward()
+    assert rel_err(a[2].grad, b[2].grad) < 1e-4
+    if deg > 0:
+        assert rel_err(a[0].grad, b[0].grad) < 1e-3
+        assert rel_err(a[1].grad, b[1].grad) < 1e-3
