@@ -65,32 +65,49 @@ def build_workload(rank: int, world: int, scene_grid: int):
 
 # ------------------------------------------------------------------------------------------ ours
 class ClockSampler(threading.Thread):
-    def __init__(self, index: int):
+    """Samples SM clock and throttle reasons DURING the timed region through NVML (in-process: spawning
+    nvidia-smi next to a few-millisecond step perturbs the very thing being measured)."""
+
+    def __init__(self, index: int, period_s: float = 0.01):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.period, self.rows, self._halt = index, period_s, [], threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        if self.nv is None:
+            return
+        nv = self.nv
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((mhz, reasons))
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(self.period)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for _, r in self.rows:
+            bits |= r
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in names.items() if bits & b), "samples": len(sm)}
 
 
 def run_ours(args):

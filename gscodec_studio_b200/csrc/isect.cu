@@ -66,7 +66,7 @@ __device__ __forceinline__ void for_each_tile_coop(bool has, const TileBox &b, u
 __global__ void __launch_bounds__(kThreads)
 isect_count_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids, const float *__restrict__ means2d,
                    const int32_t *__restrict__ radii, float ts, uint32_t tw, uint32_t th,
-                   int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts) {
+                   uint32_t total_tiles, int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts) {
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
     TileBox b = {0, 0, 0, 0};
     uint32_t cam = 0;
@@ -84,17 +84,45 @@ isect_count_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ cam
         }
         tiles_per_gauss[i] = tiles;
     }
+    // counters are replicated GSB200_ISECT_REPLICAS times (replica = block index mod R) so that the
+    // ~500 increments every tile receives are spread over R cache lines instead of hammering one
     const uint32_t n_tiles = tw * th;
+    int32_t *mine = tile_counts + (size_t)(blockIdx.x % GSB200_ISECT_REPLICAS) * total_tiles;
     for_each_tile_coop(has, b, tw, [&](int src, uint32_t tile, bool on) {
         const uint32_t c = __shfl_sync(0xffffffffu, cam, src);
-        if (on) atomicAdd(tile_counts + (size_t)c * n_tiles + tile, 1);
+        if (on) atomicAdd(mine + (size_t)c * n_tiles + tile, 1);
     });
+}
+
+// per-tile total over the replicas (input of the exclusive scan that yields isect_offsets)
+__global__ void __launch_bounds__(kThreads)
+replica_totals_kernel(uint32_t total_tiles, const int32_t *__restrict__ counts, int32_t *__restrict__ totals) {
+    const uint32_t t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total_tiles) return;
+    int sum = 0;
+#pragma unroll 8
+    for (uint32_t r = 0; r < GSB200_ISECT_REPLICAS; ++r) sum += counts[(size_t)r * total_tiles + t];
+    totals[t] = sum;
+}
+
+// counts[r][t] -> first slot of replica r inside tile t's segment (in place)
+__global__ void __launch_bounds__(kThreads)
+replica_cursor_kernel(uint32_t total_tiles, const int32_t *__restrict__ offsets, int32_t *__restrict__ counts) {
+    const uint32_t t = blockIdx.x * kThreads + threadIdx.x;
+    if (t >= total_tiles) return;
+    int run = offsets[t];
+#pragma unroll 8
+    for (uint32_t r = 0; r < GSB200_ISECT_REPLICAS; ++r) {
+        const int c = counts[(size_t)r * total_tiles + t];
+        counts[(size_t)r * total_tiles + t] = run;
+        run += c;
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
 isect_scatter_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids, const float *__restrict__ means2d,
                      const int32_t *__restrict__ radii, const float *__restrict__ depths, float ts, uint32_t tw, uint32_t th,
-                     int32_t *__restrict__ tile_cursor, uint64_t *__restrict__ bucket) {
+                     uint32_t total_tiles, int32_t *__restrict__ tile_cursor, uint64_t *__restrict__ bucket) {
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
     TileBox b = {0, 0, 0, 0};
     uint32_t cam = 0, depth_bits = 0;
@@ -110,58 +138,142 @@ isect_scatter_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ c
         }
     }
     const uint32_t n_tiles = tw * th;
+    int32_t *mine = tile_cursor + (size_t)(blockIdx.x % GSB200_ISECT_REPLICAS) * total_tiles;  // same replica as in the count pass
     for_each_tile_coop(has, b, tw, [&](int src, uint32_t tile, bool on) {
         const uint32_t c = __shfl_sync(0xffffffffu, cam, src);
         const uint32_t d = __shfl_sync(0xffffffffu, depth_bits, src);
         const uint32_t id = __shfl_sync(0xffffffffu, i, src);
         if (on) {
-            const int32_t slot = atomicAdd(tile_cursor + (size_t)c * n_tiles + tile, 1);
+            const int32_t slot = atomicAdd(mine + (size_t)c * n_tiles + tile, 1);
             bucket[slot] = ((uint64_t)d << 32) | (uint64_t)id;
         }
     });
 }
 
-// one compare-exchange sub-step of the normalized bitonic network over a[0..n): every comparison
-// moves the smaller key to the lower index, so virtual +inf padding beyond n never moves and pairs
-// whose upper index is >= n are simply skipped.
-__device__ __forceinline__ void bitonic_substep(uint64_t *a, uint32_t n, uint32_t half_pairs, uint32_t k, uint32_t j,
-                                                bool mirror) {
+// ---- per-tile sort: normalized bitonic network, 64-bit unique keys ------------------------------
+// Every comparison moves the smaller key to the lower index, so +inf padding beyond n never moves.
+// Sub-steps whose partner distance is < 64 stay inside aligned 64-element blocks; a warp keeps such a
+// block in registers (2 keys per lane) and exchanges through shuffles, so only the long-distance
+// sub-steps (k >= 128) go through shared memory with a block barrier: 6 barriers for 512 keys
+// instead of 45.
+constexpr uint64_t kInf = ~0ull;
+
+__device__ __forceinline__ uint64_t shfl_xor64(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_idx64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src), hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void keep(uint64_t &x, uint64_t p, bool lower) { x = lower ? min(x, p) : max(x, p); }
+
+// partner distance j < 32 inside both 32-key halves held as (x0 = key[lane], x1 = key[32 + lane])
+__device__ __forceinline__ void warp_steps_below32(uint64_t &x0, uint64_t &x1, uint32_t lane, int j_first) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        if (j > j_first) continue;
+        const bool lower = (lane & j) == 0;
+        keep(x0, shfl_xor64(x0, j), lower);
+        keep(x1, shfl_xor64(x1, j), lower);
+    }
+}
+
+// full sort of the 64 keys of one block
+__device__ __forceinline__ void warp_sort64(uint64_t &x0, uint64_t &x1, uint32_t lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+        const bool lower = (lane & (k >> 1)) == 0;  // mirror step: partner = lane ^ (k - 1)
+        keep(x0, shfl_xor64(x0, k - 1), lower);
+        keep(x1, shfl_xor64(x1, k - 1), lower);
+        warp_steps_below32(x0, x1, lane, k >> 2);
+    }
+    // k = 64 mirror: key i pairs with key 63 - i, which lives in the other half of lane 31 - lane
+    const uint64_t p0 = shfl_idx64(x1, 31 - (int)lane), p1 = shfl_idx64(x0, 31 - (int)lane);
+    x0 = min(x0, p0);
+    x1 = max(x1, p1);
+    warp_steps_below32(x0, x1, lane, 16);
+}
+
+// tail of a merge (partner distances 32, 16, ..., 1) of one 64-key block
+__device__ __forceinline__ void warp_merge_tail64(uint64_t &x0, uint64_t &x1, uint32_t lane) {
+    const uint64_t lo = min(x0, x1), hi = max(x0, x1);
+    x0 = lo;
+    x1 = hi;
+    warp_steps_below32(x0, x1, lane, 16);
+}
+
+// one long-distance sub-step over a[0..n_pad) in shared or global memory (all distances are powers of two)
+__device__ __forceinline__ void block_substep(uint64_t *a, uint32_t n_pad, uint32_t half_pairs, uint32_t log_k, uint32_t j,
+                                              bool mirror) {
     for (uint32_t t = threadIdx.x; t < half_pairs; t += blockDim.x) {
         uint32_t lo, hi;
-        if (mirror) {  // block of size k: r-th element pairs with its mirror image
-            const uint32_t hk = k >> 1, blk = t / hk, r = t % hk;
-            lo = blk * k + r;
-            hi = blk * k + (k - 1 - r);
+        if (mirror) {
+            const uint32_t log_hk = log_k - 1, blk = t >> log_hk, r = t & ((1u << log_hk) - 1u);
+            lo = (blk << log_k) + r;
+            hi = (blk << log_k) + ((1u << log_k) - 1u - r);
         } else {
             lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
             hi = lo | j;
         }
-        if (hi < n) {
+        if (hi < n_pad) {
             const uint64_t x = a[lo], y = a[hi];
             if (x > y) { a[lo] = y; a[hi] = x; }
         }
     }
 }
 
-__device__ __forceinline__ void bitonic_sort(uint64_t *a, uint32_t n) {
-    uint32_t P = 1;
-    while (P < n) P <<= 1;
+// sort a[0..n_pad), n_pad a multiple of 64, entries in [n, n_pad) hold kInf
+__device__ __forceinline__ void block_sort_padded(uint64_t *a, uint32_t n_pad) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t nblk = n_pad >> 6;
+    for (uint32_t blk = warp; blk < nblk; blk += nwarps) {
+        uint64_t x0 = a[blk * 64 + lane], x1 = a[blk * 64 + 32 + lane];
+        warp_sort64(x0, x1, lane);
+        a[blk * 64 + lane] = x0;
+        a[blk * 64 + 32 + lane] = x1;
+    }
+    uint32_t P = 64, log_p = 6;
+    while (P < n_pad) { P <<= 1; ++log_p; }
     const uint32_t half_pairs = P >> 1;
-    for (uint32_t k = 2; k <= P; k <<= 1) {
-        bitonic_substep(a, n, half_pairs, k, 0, true);
+    for (uint32_t log_k = 7; log_k <= log_p; ++log_k) {
         __syncthreads();
-        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-            bitonic_substep(a, n, half_pairs, k, j, false);
+        block_substep(a, n_pad, half_pairs, log_k, 0, true);
+        for (uint32_t j = 1u << (log_k - 2); j >= 64; j >>= 1) {
+            __syncthreads();
+            block_substep(a, n_pad, half_pairs, log_k, j, false);
+        }
+        __syncthreads();
+        for (uint32_t blk = warp; blk < nblk; blk += nwarps) {
+            uint64_t x0 = a[blk * 64 + lane], x1 = a[blk * 64 + 32 + lane];
+            warp_merge_tail64(x0, x1, lane);
+            a[blk * 64 + lane] = x0;
+            a[blk * 64 + 32 + lane] = x1;
+        }
+    }
+    __syncthreads();
+}
+
+// generic in-place variant for oversized segments in global memory (rare): same network, no padding
+__device__ __forceinline__ void block_sort_global(uint64_t *a, uint32_t n) {
+    uint32_t P = 1, log_p = 0;
+    while (P < n) { P <<= 1; ++log_p; }
+    const uint32_t half_pairs = P >> 1;
+    for (uint32_t log_k = 1; log_k <= log_p; ++log_k) {
+        block_substep(a, n, half_pairs, log_k, 0, true);
+        __syncthreads();
+        for (uint32_t j = log_k >= 2 ? 1u << (log_k - 2) : 0; j > 0; j >>= 1) {
+            block_substep(a, n, half_pairs, log_k, j, false);
             __syncthreads();
         }
     }
 }
 
-constexpr uint32_t kSortSmall = 2048;   // items a 256-thread CTA sorts in 16 KB of static shared memory
-constexpr uint32_t kSortLarge = 12288;  // items a 1024-thread CTA sorts in 96 KB of dynamic shared memory
+constexpr uint32_t kSortSmall = 2048;   // keys a 256-thread CTA sorts in 16 KB of static shared memory
+constexpr uint32_t kSortLarge = 12288;  // keys a 1024-thread CTA sorts in 96 KB of dynamic shared memory
 
-// One CTA per (camera, tile).  LARGE = false handles segments of up to kSortSmall items, LARGE = true
-// the (few) longer ones -- in shared memory up to kSortLarge items, in place in global memory (L2
+// One CTA per (camera, tile).  LARGE = false handles segments of up to kSortSmall keys, LARGE = true
+// the (few) longer ones -- in shared memory up to kSortLarge keys, in place in global memory (L2
 // resident) beyond that.  Both kernels are launched over all tiles and exit early on the other class.
 template <bool LARGE>
 __global__ void __launch_bounds__(LARGE ? 1024 : kThreads)
@@ -180,12 +292,15 @@ tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, i
     uint64_t *a;
     if (!LARGE || n <= kSortLarge) {
         a = LARGE ? s_dyn : s_static;
-        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) a[t] = bucket[start + t];
+        const uint32_t n_pad = (n + 63u) & ~63u;
+        for (uint32_t t = threadIdx.x; t < n_pad; t += blockDim.x) a[t] = t < n ? bucket[start + t] : kInf;
+        __syncthreads();
+        if (n > 1) block_sort_padded(a, n_pad);
     } else {
         a = bucket + start;
+        __syncthreads();
+        block_sort_global(a, n);
     }
-    __syncthreads();
-    if (n > 1) bitonic_sort(a, n);
     for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
         const uint64_t it = a[t];
         // low word: sign-extending OR like the reference's (int64)(int32)depth cast (isect_tiles.cu:88)
@@ -235,22 +350,26 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
     if (bit_width(tile_width * tile_height) + bit_width(C) > 32)
         return fail(2, "gsb200_isect_prepare: camera and tile ids do not fit 32 bits");
     if (T == 0) return 0;
-    GSB_CUDA_OK(cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * T, s));
     if (n_elems == 0) {
-        GSB_CUDA_OK(cudaMemsetAsync(tile_cursor, 0, sizeof(int32_t) * T, s));
+        GSB_CUDA_OK(cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * T, s));
         return 0;
     }
+    GSB_CUDA_OK(cudaMemsetAsync(tile_cursor, 0, sizeof(int32_t) * (size_t)T * GSB200_ISECT_REPLICAS, s));
     isect_count_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
                                                                      camera_ids, means2d, radii, (float)tile_size,
-                                                                     tile_width, tile_height, tiles_per_gauss, isect_offsets);
+                                                                     tile_width, tile_height, T, tiles_per_gauss, tile_cursor);
     if (int e = check_launch("isect_count")) return e;
-    // block sums scratch: reuse the head of tile_cursor is not possible (it receives the copy), so a
-    // small side allocation from the stream-ordered pool is used.
+    replica_totals_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, tile_cursor, isect_offsets);
+    if (int e = check_launch("replica_totals")) return e;
     const uint32_t nb = cdiv(T, kScanTile);
     int32_t *scratch = nullptr;
     GSB_CUDA_OK(cudaMallocAsync((void **)&scratch, sizeof(int32_t) * (nb + 2), s));
-    int e = exclusive_scan(T, isect_offsets, tile_cursor, scratch, s);
+    int e = exclusive_scan(T, isect_offsets, nullptr, scratch, s);
     int32_t total = 0;
+    if (e == 0) {
+        replica_cursor_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, isect_offsets, tile_cursor);
+        e = check_launch("replica_cursor");
+    }
     if (e == 0) {
         cudaError_t ce = cudaMemcpyAsync(&total, scratch + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
@@ -272,7 +391,7 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
     const uint32_t n_tiles = tile_width * tile_height;
     isect_scatter_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
                                                                        camera_ids, means2d, radii, depths, (float)tile_size,
-                                                                       tile_width, tile_height, tile_cursor, scratch);
+                                                                       tile_width, tile_height, C * n_tiles, tile_cursor, scratch);
     if (int e = check_launch("isect_scatter")) return e;
     tile_sort_kernel<false><<<C * n_tiles, kThreads, 0, s>>>(C * n_tiles, n_tiles, bit_width(n_tiles), n_isects,
                                                               isect_offsets, scratch, isect_ids, flatten_ids);
