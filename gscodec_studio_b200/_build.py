@@ -35,10 +35,13 @@ def _deps_mtime() -> float:
     return max(os.path.getmtime(f) for f in files)
 
 
+EXTRA_FLAGS = [f for f in os.environ.get("GSB200_NVCC_EXTRA", "").split() if f]
+
+
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     log = obj + ".log"
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [_nvcc(), *NVCC_FLAGS, *EXTRA_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
     with open(log, "w") as fh:
         rc = subprocess.call(cmd, stdout=fh, stderr=subprocess.STDOUT)
     if rc != 0:
@@ -47,6 +50,11 @@ def _compile(src: str) -> str:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    global LIB, OBJ
+    if os.environ.get("GSB200_LIB_OUT"):  # A/B variant build: separate output and object directory
+        LIB = os.environ["GSB200_LIB_OUT"]
+        OBJ = LIB + "_obj"
+        force = True
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB
     os.makedirs(OBJ, exist_ok=True)

@@ -28,6 +28,17 @@
 namespace gsb200 {
 
 constexpr int kBatch = 256;
+// minimum resident CTAs per SM the register allocator must allow (occupancy knobs)
+#ifndef GSB_STAGE_PER_THREAD
+#define GSB_STAGE_PER_THREAD 2  // Gaussians staged per thread and barrier (batch = threads x this)
+#endif
+constexpr int kStagePerThread = GSB_STAGE_PER_THREAD;
+#ifndef GSB_FWD_BLOCKS
+#define GSB_FWD_BLOCKS 6
+#endif
+#ifndef GSB_BWD_BLOCKS
+#define GSB_BWD_BLOCKS 5
+#endif
 constexpr float kAlphaMax = 0.999f;
 constexpr float kAlphaMin = 1.f / 255.f;
 constexpr float kTStop = 1e-4f;  // reference compares against the double 1e-4; identical set of floats
@@ -108,7 +119,7 @@ __device__ __forceinline__ int lds1i(uint32_t addr) {
 template <int CDIM> struct ColorPad { static constexpr int value = (CDIM + 3) / 4 * 4; };
 
 template <int CDIM>
-__global__ void __launch_bounds__(kBatch)
+__global__ void __launch_bounds__(kBatch, CDIM <= 4 ? GSB_FWD_BLOCKS : 1)
 blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
                  const float *__restrict__ colors, const float *__restrict__ opacities,
                  const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
@@ -117,7 +128,7 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     constexpr int CP = ColorPad<CDIM>::value;
     extern __shared__ float4 smem4[];
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
-    const uint32_t batch = nthreads;
+    const uint32_t batch = nthreads * kStagePerThread;
     float4 *sA = smem4;                                 // x, y, opacity, qmax
     float4 *sB = sA + batch;                            // conic a, b, c, -
     float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CP]
@@ -161,17 +172,21 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     for (int32_t batch_start = range_start; batch_start < range_end; batch_start += (int32_t)batch) {
         // barrier protects the staging buffers; stop when every pixel of the tile is saturated
         if (__syncthreads_count(done) >= (int)nthreads) break;
-        const int32_t idx = batch_start + (int32_t)tid;
-        if (idx < range_end) {
-            const int32_t g = flatten_ids[idx];
-            const float2 xy = __ldg(means2d + g);
-            const float opac = __ldg(opacities + g);
-            const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
-                        cc = __ldg(conics + (size_t)g * 3 + 2);
-            sA[tid] = make_float4(xy.x, xy.y, opac, cull_qmax(ca, cb, cc, opac));
-            sB[tid] = make_float4(ca, cb, cc, 0.f);
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k) sC[tid * CP + k] = __ldg(colors + (size_t)g * CDIM + k);
+        for (int sp = 0; sp < kStagePerThread; ++sp) {
+            const uint32_t e = tid + sp * nthreads;
+            const int32_t idx = batch_start + (int32_t)e;
+            if (idx < range_end) {
+                const int32_t g = flatten_ids[idx];
+                const float2 xy = __ldg(means2d + g);
+                const float opac = __ldg(opacities + g);
+                const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
+                            cc = __ldg(conics + (size_t)g * 3 + 2);
+                sA[e] = make_float4(xy.x, xy.y, opac, cull_qmax(ca, cb, cc, opac));
+                sB[e] = make_float4(ca, cb, cc, 0.f);
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k) sC[e * CP + k] = __ldg(colors + (size_t)g * CDIM + k);
+            }
         }
         __syncthreads();
         if (warp_done) continue;
@@ -258,7 +273,7 @@ __device__ __forceinline__ uint32_t spread_slot(uint32_t lane) {
 __host__ __device__ constexpr uint32_t grad_record(uint32_t cdim) { return (cdim + 8 + 3) / 4 * 4; }
 
 template <int CDIM, bool ABS>
-__global__ void __launch_bounds__(kBatch)
+__global__ void __launch_bounds__(kBatch, CDIM <= 4 ? GSB_BWD_BLOCKS : 1)
 blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
                  const float *__restrict__ colors, const float *__restrict__ opacities,
                  const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
@@ -275,7 +290,7 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     extern __shared__ float4 smem4[];
     __shared__ int s_binmax;
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
-    const uint32_t batch = nthreads;
+    const uint32_t batch = nthreads * kStagePerThread;
     float4 *sA = smem4;                                 // x, y, opacity, qmax
     float4 *sB = sA + batch;                            // conic a, b, c, flatten id (bits)
     float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CP]
@@ -329,16 +344,20 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     for (int32_t batch_end = range_end - 1; batch_end >= range_start; batch_end -= (int32_t)batch) {
         __syncthreads();
         const int32_t bsize = min((int32_t)batch, batch_end + 1 - range_start);
-        if ((int32_t)tid < bsize) {
-            const int32_t g = flatten_ids[batch_end - (int32_t)tid];
-            const float2 xy = __ldg(means2d + g);
-            const float opac = __ldg(opacities + g);
-            const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
-                        cc = __ldg(conics + (size_t)g * 3 + 2);
-            sA[tid] = make_float4(xy.x, xy.y, opac, cull_qmax(ca, cb, cc, opac));
-            sB[tid] = make_float4(ca, cb, cc, __int_as_float(g));
 #pragma unroll
-            for (int k = 0; k < CDIM; ++k) sC[tid * CP + k] = __ldg(colors + (size_t)g * CDIM + k);
+        for (int sp = 0; sp < kStagePerThread; ++sp) {
+            const int32_t e = (int32_t)(tid + sp * nthreads);
+            if (e < bsize) {
+                const int32_t g = flatten_ids[batch_end - e];
+                const float2 xy = __ldg(means2d + g);
+                const float opac = __ldg(opacities + g);
+                const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
+                            cc = __ldg(conics + (size_t)g * 3 + 2);
+                sA[e] = make_float4(xy.x, xy.y, opac, cull_qmax(ca, cb, cc, opac));
+                sB[e] = make_float4(ca, cb, cc, __int_as_float(g));
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k) sC[e * CP + k] = __ldg(colors + (size_t)g * CDIM + k);
+            }
         }
         __syncthreads();
         if (warp_bin_final < 0) continue;
@@ -449,7 +468,7 @@ static int launch_fwd(const BlendGeom &G, const float *means2d, const float *con
                       const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
                       cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
-    const uint32_t batch = nthreads;
+    const uint32_t batch = nthreads * kStagePerThread;
     const size_t smem = (size_t)batch * (32 + 4 * ColorPad<CDIM>::value);
     if (smem > 48 * 1024)
         GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -467,7 +486,7 @@ static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, cons
                       const float *v_render_colors, const float *v_render_alphas, float *grad_scratch, float *v_abs,
                       float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
-    const uint32_t batch = nthreads;
+    const uint32_t batch = nthreads * kStagePerThread;
     const size_t smem = (size_t)batch * (32 + 4 * ColorPad<CDIM>::value);
     if (smem > 48 * 1024) {
         GSB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

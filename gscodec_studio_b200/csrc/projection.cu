@@ -10,7 +10,8 @@
 //     backward needs NO atomics and no warp-group partitions -- the sum over cameras is a register
 //     accumulation followed by one plain store (deterministic);
 //   * camera matrices live in shared memory (the reference re-reads them from global per thread);
-//   * [N,3] arrays are moved with 128-bit loads through a shared-memory transpose;
+//   * Gaussian parameters are read lazily: quats / scales only for Gaussians that survive the near/far
+//     test in some camera (forward) or are visible in some camera (backward);
 //   * culled entries are zero-filled, so downstream consumers never see uninitialised memory;
 //   * v_viewmats is block-reduced in shared memory, one atomic set per block and camera.
 #include "common.cuh"
@@ -118,23 +119,6 @@ __device__ __forceinline__ void project_covar(const CamProj &P, const Sym3 &S, f
     c11 = B10 * P.J[1][0] + B11 * P.J[1][1] + B12 * P.J[1][2];
 }
 
-// cooperative 128-bit load of a block's [kThreads,3] slice into shared memory
-__device__ __forceinline__ void load_vec3_block(const float *__restrict__ src, uint32_t first, uint32_t n_total,
-                                                float *smem /*kThreads*3*/) {
-    const uint32_t base = first * 3;
-    const uint32_t total = n_total * 3;
-    // base is a multiple of 3*kThreads floats = 3072 B, so 16-byte aligned
-    for (uint32_t i = threadIdx.x * 4; i < kThreads * 3; i += blockDim.x * 4) {
-        if (base + i + 3 < total) {
-            float4 v = ldg4(src + base + i);
-            smem[i] = v.x; smem[i + 1] = v.y; smem[i + 2] = v.z; smem[i + 3] = v.w;
-        } else {
-            for (uint32_t k = 0; k < 4; ++k)
-                if (base + i + k < total) smem[i + k] = __ldg(src + base + i + k);
-        }
-    }
-}
-
 constexpr int kMaxSmemCams = 64;  // cameras cached in shared memory per pass
 
 __global__ void __launch_bounds__(kThreads)
@@ -146,26 +130,13 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                       float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ comps) {
     __shared__ float s_vm[kMaxSmemCams][12];
     __shared__ float s_k[kMaxSmemCams][4];
-    __shared__ float s_a[kThreads * 3];
-    __shared__ float s_b[kThreads * 3];
-    const uint32_t first = blockIdx.x * kThreads;
-    const uint32_t g = first + threadIdx.x;
-    load_vec3_block(means, first, N, s_a);
-    if (covars == nullptr) load_vec3_block(scales, first, N, s_b);
-    __syncthreads();
+    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
     float px = 0.f, py = 0.f, pz = 0.f;
+    if (g < N) { px = __ldg(means + (size_t)g * 3); py = __ldg(means + (size_t)g * 3 + 1); pz = __ldg(means + (size_t)g * 3 + 2); }
+    // the world-space covariance is built lazily, the first time a camera keeps this Gaussian after the
+    // near/far test -- for most Gaussians of a large scene that never happens and quats/scales are never read
     Sym3 S = {0, 0, 0, 0, 0, 0};
-    if (g < N) {
-        px = s_a[threadIdx.x * 3]; py = s_a[threadIdx.x * 3 + 1]; pz = s_a[threadIdx.x * 3 + 2];
-        if (covars != nullptr) {
-            const float *c = covars + (size_t)g * 6;
-            S.xx = c[0]; S.xy = c[1]; S.xz = c[2]; S.yy = c[3]; S.yz = c[4]; S.zz = c[5];
-        } else {
-            float4 q = ldg4(quats + (size_t)g * 4);
-            Mat3 Rq = quat_to_rot(q.x, q.y, q.z, q.w, nullptr);
-            S = covar_from_quat_scale(Rq, s_b[threadIdx.x * 3], s_b[threadIdx.x * 3 + 1], s_b[threadIdx.x * 3 + 2]);
-        }
-    }
+    bool have_S = false;
     for (uint32_t c0 = 0; c0 < C; c0 += kMaxSmemCams) {
         const uint32_t nc = min((uint32_t)kMaxSmemCams, C - c0);
         __syncthreads();
@@ -185,6 +156,18 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
             int32_t rad = 0;
             float o_mx = 0.f, o_my = 0.f, o_d = 0.f, o_a = 0.f, o_b = 0.f, o_c = 0.f, o_comp = 0.f;
             if (!(mz < near_plane || mz > far_plane)) {
+                if (!have_S) {
+                    have_S = true;
+                    if (covars != nullptr) {
+                        const float *c = covars + (size_t)g * 6;
+                        S.xx = c[0]; S.xy = c[1]; S.xz = c[2]; S.yy = c[3]; S.yz = c[4]; S.zz = c[5];
+                    } else {
+                        const float4 q = ldg4(quats + (size_t)g * 4);
+                        const Mat3 Rq = quat_to_rot(q.x, q.y, q.z, q.w, nullptr);
+                        S = covar_from_quat_scale(Rq, __ldg(scales + (size_t)g * 3), __ldg(scales + (size_t)g * 3 + 1),
+                                                  __ldg(scales + (size_t)g * 3 + 2));
+                    }
+                }
                 Sym3 Sc = covar_to_cam(R, S);
                 CamProj P = project_point(model, mx, my, mz, s_k[ci][0], s_k[ci][1], s_k[ci][2], s_k[ci][3], W, H);
                 float c00, c01, c11;
@@ -223,7 +206,8 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+template <bool VIEWGRAD>
+__global__ void __launch_bounds__(kThreads, 3)
 projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
                       const float *__restrict__ quats, const float *__restrict__ scales,
                       const float *__restrict__ viewmats, const float *__restrict__ Ks, float W, float H,
@@ -234,32 +218,19 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                       float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_viewmats) {
     __shared__ float s_vm[kMaxSmemCams][12];
     __shared__ float s_k[kMaxSmemCams][4];
-    __shared__ float s_a[kThreads * 3];
-    __shared__ float s_b[kThreads * 3];
     __shared__ float s_red[kThreads / 32][12];
-    const uint32_t first = blockIdx.x * kThreads;
-    const uint32_t g = first + threadIdx.x;
+    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    load_vec3_block(means, first, N, s_a);
-    if (covars == nullptr) load_vec3_block(scales, first, N, s_b);
-    __syncthreads();
     float px = 0.f, py = 0.f, pz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
     float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
     Sym3 S = {0, 0, 0, 0, 0, 0};
     Mat3 Rq;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Rq.m[i][j] = 0.f;
     float inv_norm = 1.f;
-    if (g < N) {
-        px = s_a[threadIdx.x * 3]; py = s_a[threadIdx.x * 3 + 1]; pz = s_a[threadIdx.x * 3 + 2];
-        if (covars != nullptr) {
-            const float *c = covars + (size_t)g * 6;
-            S.xx = c[0]; S.xy = c[1]; S.xz = c[2]; S.yy = c[3]; S.yz = c[4]; S.zz = c[5];
-        } else {
-            q = ldg4(quats + (size_t)g * 4);
-            sx = s_b[threadIdx.x * 3]; sy = s_b[threadIdx.x * 3 + 1]; sz = s_b[threadIdx.x * 3 + 2];
-            Rq = quat_to_rot(q.x, q.y, q.z, q.w, &inv_norm);
-            S = covar_from_quat_scale(Rq, sx, sy, sz);
-        }
-    }
+    bool have_S = false;  // Gaussian parameters are read lazily: only Gaussians visible in some camera need them
     float vmean[3] = {0.f, 0.f, 0.f};
     float vS[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};  // full (non-symmetrised) v_Sigma
     for (uint32_t c0 = 0; c0 < C; c0 += kMaxSmemCams) {
@@ -278,6 +249,19 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
             float vt[3] = {0.f, 0.f, 0.f};
             const bool active = (g < N) && radii[idx] > 0;
             if (active) {
+                if (!have_S) {
+                    have_S = true;
+                    px = __ldg(means + (size_t)g * 3); py = __ldg(means + (size_t)g * 3 + 1); pz = __ldg(means + (size_t)g * 3 + 2);
+                    if (covars != nullptr) {
+                        const float *c = covars + (size_t)g * 6;
+                        S.xx = c[0]; S.xy = c[1]; S.xz = c[2]; S.yy = c[3]; S.yz = c[4]; S.zz = c[5];
+                    } else {
+                        q = ldg4(quats + (size_t)g * 4);
+                        sx = __ldg(scales + (size_t)g * 3); sy = __ldg(scales + (size_t)g * 3 + 1); sz = __ldg(scales + (size_t)g * 3 + 2);
+                        Rq = quat_to_rot(q.x, q.y, q.z, q.w, &inv_norm);
+                        S = covar_from_quat_scale(Rq, sx, sy, sz);
+                    }
+                }
                 const float ca = conics[idx * 3], cb = conics[idx * 3 + 1], cc = conics[idx * 3 + 2];
                 const float va = v_conics[idx * 3], vb = 0.5f * v_conics[idx * 3 + 1], vc = v_conics[idx * 3 + 2];
                 // v_cov2d = -Cn V Cn  (utils.cuh:24-29)
@@ -358,7 +342,7 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
                     for (int j = 0; j < 3; ++j) vS[i][j] += R[i] * Tm[0][j] + R[4 + i] * Tm[1][j] + R[8 + i] * Tm[2][j];
-                if (v_viewmats != nullptr) {
+                if (VIEWGRAD) {
                     const float p[3] = {px, py, pz};
                     const float SM[3][3] = {{S.xx, S.xy, S.xz}, {S.xy, S.yy, S.yz}, {S.xz, S.yz, S.zz}};
                     // v_R = outer(vmc, p) + vSc R Sigma^T + vSc^T R Sigma = outer + (vSc + vSc^T) R Sigma
@@ -377,7 +361,7 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                     }
                 }
             }
-            if (v_viewmats != nullptr) {  // block reduction over Gaussians, one atomic set per block and camera
+            if (VIEWGRAD) {  // block reduction over Gaussians, one atomic set per block and camera
                 float vals[12];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
@@ -399,6 +383,17 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
         }
     }
     if (g >= N) return;
+    if (!have_S) {  // invisible everywhere: all gradients are zero
+        v_means[(size_t)g * 3] = 0.f; v_means[(size_t)g * 3 + 1] = 0.f; v_means[(size_t)g * 3 + 2] = 0.f;
+        if (covars != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v_covars[(size_t)g * 6 + k] = 0.f;
+        } else {
+            stg4(v_quats + (size_t)g * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+            v_scales[(size_t)g * 3] = 0.f; v_scales[(size_t)g * 3 + 1] = 0.f; v_scales[(size_t)g * 3 + 2] = 0.f;
+        }
+        return;
+    }
     v_means[(size_t)g * 3] = vmean[0]; v_means[(size_t)g * 3 + 1] = vmean[1]; v_means[(size_t)g * 3 + 2] = vmean[2];
     if (covars != nullptr) {
         float *o = v_covars + (size_t)g * 6;
@@ -548,9 +543,14 @@ extern "C" int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means,
         return fail(2, "gsb200_projection_bwd: camera_model must be pinhole or ortho (fisheye not implemented)");
     if (C == 0 || N == 0) return 0;
     if (v_viewmats != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_viewmats, 0, sizeof(float) * 16 * C, (cudaStream_t)stream));
-    projection_bwd_kernel<<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,
-        compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats);
+    if (v_viewmats != nullptr)
+        projection_bwd_kernel<true><<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+            C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,
+            compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats);
+    else
+        projection_bwd_kernel<false><<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+            C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,
+            compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats);
     return check_launch("projection_bwd");
 }
 

@@ -67,73 +67,108 @@ def all_to_all_int32(world_size: int, values: List[Union[int, Tensor]], device: 
     return list(recv.unbind())
 
 
-class _AllGatherRows(torch.autograd.Function):
-    """Concatenate per-rank row blocks [n_r, F] -> [sum n_r, F]; backward returns the local block of the
-    SUMMED gradient (reduce-scatter)."""
+def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool):
+    """Start the all-gather of per-rank row blocks [n_r, ...] -> ([sum n_r, ...] tensor or padded buffer, work)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_max = max(counts)
+    tail = tuple(data.shape[1:])
+    data = data.contiguous()
+    if all(c == n_max for c in counts):
+        out = torch.empty((world * n_max,) + tail, dtype=data.dtype, device=data.device)
+        work = dist.all_gather_into_tensor(out, data, async_op=async_op)
+        return out, work, False
+    padded = torch.zeros((n_max,) + tail, dtype=data.dtype, device=data.device)
+    padded[: counts[rank]] = data
+    buf = torch.empty((world * n_max,) + tail, dtype=data.dtype, device=data.device)
+    work = dist.all_gather_into_tensor(buf, padded, async_op=async_op)
+    return buf, work, True
+
+
+def _gather_rows_finish(buf: Tensor, work, ragged: bool, counts: Sequence[int]) -> Tensor:
+    if work is not None:
+        work.wait()  # the current stream waits for the collective; the host does not block
+    if not ragged:
+        return buf
+    n_max = max(counts)
+    return torch.cat([buf[r * n_max: r * n_max + counts[r]] for r in range(len(counts))], dim=0)
+
+
+def _reduce_scatter_rows(v_out: Tensor, counts: Sequence[int]) -> Tensor:
+    """Sum over ranks of [sum n_r, ...] gradients, return this rank's [n_rank, ...] block."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_max = max(counts)
+    tail = tuple(v_out.shape[1:])
+    v_out = v_out.contiguous()
+    if all(c == n_max for c in counts):
+        send = v_out
+    else:
+        send = torch.zeros((world * n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
+        start = 0
+        for r in range(world):
+            send[r * n_max: r * n_max + counts[r]] = v_out[start: start + counts[r]]
+            start += counts[r]
+    if _backend_supports("reduce_scatter_tensor"):
+        recv = torch.empty((n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
+        dist.reduce_scatter_tensor(recv, send, op=dist.ReduceOp.SUM)
+    else:
+        send = send.clone() if send is v_out else send
+        dist.all_reduce(send, op=dist.ReduceOp.SUM)
+        recv = send[rank * n_max: (rank + 1) * n_max]
+    return recv[: counts[rank]].contiguous()
+
+
+class _FinishGather(torch.autograd.Function):
+    """Autograd node of one gathered tensor: forward waits for the (already running) collective, backward
+    reduce-scatters the gradient to the owner rank."""
 
     @staticmethod
-    def forward(ctx, data: Tensor, counts: Sequence[int]):
-        world = dist.get_world_size()
-        rank = dist.get_rank()
-        n_max = max(counts)
-        F = data.shape[1]
-        if all(c == n_max for c in counts):
-            out = torch.empty((world * n_max, F), dtype=data.dtype, device=data.device)
-            dist.all_gather_into_tensor(out, data.contiguous())
-        else:
-            padded = torch.zeros((n_max, F), dtype=data.dtype, device=data.device)
-            padded[: counts[rank]] = data
-            buf = torch.empty((world * n_max, F), dtype=data.dtype, device=data.device)
-            dist.all_gather_into_tensor(buf, padded)
-            out = torch.cat([buf[r * n_max: r * n_max + counts[r]] for r in range(world)], dim=0)
-        ctx.counts = list(counts)
-        return out
+    def forward(ctx, data: Tensor, pending: "PendingGather"):
+        ctx.counts = pending.counts
+        return _gather_rows_finish(pending.buf, pending.work, pending.ragged, pending.counts)
 
     @staticmethod
     def backward(ctx, v_out: Tensor):
-        counts = ctx.counts
-        world = dist.get_world_size()
-        rank = dist.get_rank()
-        n_max = max(counts)
-        F = v_out.shape[1]
-        v_out = v_out.contiguous()
-        if all(c == n_max for c in counts):
-            send = v_out
-        else:
-            send = torch.zeros((world * n_max, F), dtype=v_out.dtype, device=v_out.device)
-            start = 0
-            for r in range(world):
-                send[r * n_max: r * n_max + counts[r]] = v_out[start: start + counts[r]]
-                start += counts[r]
-        if _backend_supports("reduce_scatter_tensor"):
-            recv = torch.empty((n_max, F), dtype=v_out.dtype, device=v_out.device)
-            dist.reduce_scatter_tensor(recv, send, op=dist.ReduceOp.SUM)
-        else:
-            send = send.clone()
-            dist.all_reduce(send, op=dist.ReduceOp.SUM)
-            recv = send[rank * n_max: (rank + 1) * n_max]
-        return recv[: counts[rank]].contiguous(), None
+        return _reduce_scatter_rows(v_out, ctx.counts), None
+
+
+class PendingGather:
+    """An all-gather in flight.  `start_gather(t, counts)` enqueues it on NCCL's stream right away, `.finish()`
+    returns the gathered, differentiable tensor and makes the current stream wait for it -- kernels enqueued
+    between the two calls overlap with the transfer."""
+
+    def __init__(self, data: Tensor, counts: Sequence[int]):
+        self.data, self.counts = data, list(counts)
+        self.buf, self.work, self.ragged = _gather_rows_launch(data.detach(), self.counts, async_op=True)
+
+    def finish(self) -> Tensor:
+        return _FinishGather.apply(self.data, self)
+
+
+def gather_counts(n: int, device) -> List[int]:
+    world = dist.get_world_size()
+    return [int(c) for c in all_gather_int32(world, int(n), device=device)]
+
+
+def start_gather(t: Tensor, counts: Sequence[int]) -> PendingGather:
+    return PendingGather(t, counts)
 
 
 def all_gather_attributes(tensor_list: List[Tensor], counts: Optional[List[int]] = None) -> List[Tensor]:
-    """All-gather a list of per-Gaussian tensors [(n_r, *), ...] along dim 0 in ONE collective.
+    """All-gather a list of per-Gaussian tensors [(n_r, *), ...] along dim 0, one collective per tensor
+    written straight into its final buffer (no concatenate / split copies).
 
-    Differentiable: gradients w.r.t. the gathered tensors are summed over ranks and the local rows
-    are returned (reduce-scatter).  Row counts may differ between ranks.
+    Differentiable: gradients w.r.t. the gathered tensors are summed over ranks and the local rows are
+    returned (reduce-scatter).  Row counts may differ between ranks.
     """
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return list(tensor_list)
-    world = dist.get_world_size()
     n = tensor_list[0].shape[0]
     for t in tensor_list:
         assert t.shape[0] == n, "All tensors should have the same first dimension size"
     if counts is None:
-        counts = [int(c) for c in all_gather_int32(world, int(n), device=tensor_list[0].device)]
-    widths = [t.numel() // max(n, 1) if n > 0 else int(torch.tensor(t.shape[1:]).prod()) for t in tensor_list]
-    data = torch.cat([t.reshape(n, -1) for t in tensor_list], dim=-1)
-    gathered = _AllGatherRows.apply(data, counts)
-    outs = torch.split(gathered, widths, dim=-1)
-    return [o.reshape(-1, *t.shape[1:]) for o, t in zip(outs, tensor_list)]
+        counts = gather_counts(n, tensor_list[0].device)
+    pending = [start_gather(t, counts) for t in tensor_list]
+    return [p.finish() for p in pending]
 
 
 def all_gather_tensor_list(world_size: int, tensor_list: List[Tensor]) -> List[Tensor]:

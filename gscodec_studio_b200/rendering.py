@@ -110,18 +110,25 @@ def rasterization(
         # each rank then renders its cameras from the full set.  Replaces the reference's
         # project-everywhere + all-to-all exchange (rendering.py:282-294, 397-478); same API, gradients
         # reach the owner rank.
-        from .distributed import all_gather_attributes
+        from .distributed import gather_counts, start_gather
 
-        gathered = all_gather_attributes(
-            [t for t in (means, quats, scales, opacities, colors, covars) if t is not None])
-        it = iter(gathered)
-        means = next(it)
+        counts = gather_counts(N, device)
+        # every gather is enqueued now; the (large) colour / SH tensor is only waited for after projection
+        # and tile intersection have been enqueued, so its transfer overlaps with those kernels
+        pend = {name: start_gather(t, counts) for name, t in
+                (("means", means), ("quats", quats), ("scales", scales), ("opacities", opacities), ("colors", colors),
+                 ("covars", covars)) if t is not None}
+        means = pend["means"].finish()
         if covars is None:
-            quats, scales = next(it), next(it)
-        opacities, colors = next(it), next(it)
-        if covars is not None:
-            covars = next(it)
+            quats, scales = pend["quats"].finish(), pend["scales"].finish()
+        else:
+            covars = pend["covars"].finish()
+        opacities = pend["opacities"].finish()
+        pending_colors = pend["colors"]
+        colors = None
         N = means.shape[0]
+    else:
+        pending_colors = None
 
     proj_results = fully_fused_projection(
         means, covars, quats, scales, viewmats, Ks, width, height,
@@ -142,6 +149,17 @@ def rasterization(
         "camera_ids": camera_ids, "gaussian_ids": gaussian_ids, "radii": radii, "means2d": means2d,
         "depths": depths, "conics": conics, "opacities": opacities,
     })
+
+    # Tile intersection needs only the projection outputs: enqueue it before the colour stage so that, in
+    # distributed mode, the colour all-gather keeps overlapping with it.
+    tile_width = math.ceil(width / float(tile_size))
+    tile_height = math.ceil(height / float(tile_size))
+    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = _isect_tiles_with_offsets(
+        means2d, radii, depths, tile_size, tile_width, tile_height,
+        packed=packed, n_cameras=C, camera_ids=camera_ids, gaussian_ids=gaussian_ids,
+    )
+    if pending_colors is not None:
+        colors = pending_colors.finish()
 
     if sh_degree is None:
         if packed:
@@ -172,12 +190,6 @@ def rasterization(
         if backgrounds is not None:
             backgrounds = torch.zeros(C, 1, device=backgrounds.device)
 
-    tile_width = math.ceil(width / float(tile_size))
-    tile_height = math.ceil(height / float(tile_size))
-    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = _isect_tiles_with_offsets(
-        means2d, radii, depths, tile_size, tile_width, tile_height,
-        packed=packed, n_cameras=C, camera_ids=camera_ids, gaussian_ids=gaussian_ids,
-    )
     meta.update({
         "tile_width": tile_width, "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss,
         "isect_ids": isect_ids, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets,
