@@ -421,19 +421,27 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                         if (ABS) { tail[1] = fabsf(gx); tail[2] = fabsf(gy); }
                     }
                 }
+                // all reductions first (independent shuffle chains overlap), then the REDs: the asm memory
+                // clobber of red_add would otherwise serialise the chains
+#pragma unroll
+                for (int gi = 0; gi < NGRP; ++gi) reduce_spread<8>(vals + gi * 8, lane);
+                float tail_sum;
+                if (ABS) {
+                    reduce_spread<4>(tail, lane);
+                    tail_sum = tail[0];
+                } else {
+                    tail_sum = warp_sum(tail[0]);
+                }
                 float *rec = grad_rec + (size_t)__float_as_int(B.w) * REC;
 #pragma unroll
                 for (int gi = 0; gi < NGRP; ++gi) {
-                    reduce_spread<8>(vals + gi * 8, lane);
                     const uint32_t off = gi * 8 + slot8;
                     if (pub8 && off < (uint32_t)NMAIN) red_add(rec + off, vals[gi * 8]);
                 }
                 if (ABS) {
-                    reduce_spread<4>(tail, lane);
-                    if (pub4 && slot4 < 3) red_add(rec + NMAIN + slot4, tail[0]);
+                    if (pub4 && slot4 < 3) red_add(rec + NMAIN + slot4, tail_sum);
                 } else {
-                    const float s = warp_sum(tail[0]);
-                    if (lane == 0) red_add(rec + NMAIN, s);
+                    if (lane == 0) red_add(rec + NMAIN, tail_sum);
                 }
             }
         }

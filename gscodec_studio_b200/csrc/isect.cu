@@ -23,6 +23,9 @@
 
 namespace gsb200 {
 
+constexpr uint32_t kSortSmall = 2048;   // keys a 256-thread CTA sorts in 16 KB of static shared memory
+constexpr uint32_t kSortLarge = 12288;  // keys a 1024-thread CTA sorts in 96 KB of dynamic shared memory
+
 struct TileBox { uint32_t x0, y0, x1, y1; };
 
 // tile bbox of one Gaussian: min inclusive, max exclusive (isect_tiles.cu:59-71).  The float ->
@@ -105,17 +108,24 @@ replica_totals_kernel(uint32_t total_tiles, const int32_t *__restrict__ counts, 
     totals[t] = sum;
 }
 
-// counts[r][t] -> first slot of replica r inside tile t's segment (in place)
+// counts[r][t] -> first slot of replica r inside tile t's segment (in place); tiles too long for the
+// small sort kernel are appended to a work list (counter at counts[R*T], ids behind it)
 __global__ void __launch_bounds__(kThreads)
-replica_cursor_kernel(uint32_t total_tiles, const int32_t *__restrict__ offsets, int32_t *__restrict__ counts) {
+replica_cursor_kernel(uint32_t total_tiles, const int32_t *__restrict__ offsets, int32_t *__restrict__ counts,
+                      uint32_t large_threshold) {
     const uint32_t t = blockIdx.x * kThreads + threadIdx.x;
     if (t >= total_tiles) return;
     int run = offsets[t];
+    const int first = run;
 #pragma unroll 8
     for (uint32_t r = 0; r < GSB200_ISECT_REPLICAS; ++r) {
         const int c = counts[(size_t)r * total_tiles + t];
         counts[(size_t)r * total_tiles + t] = run;
         run += c;
+    }
+    if ((uint32_t)(run - first) > large_threshold) {
+        int32_t *list = counts + (size_t)GSB200_ISECT_REPLICAS * total_tiles;
+        list[1 + atomicAdd(list, 1)] = (int32_t)t;
     }
 }
 
@@ -269,43 +279,45 @@ __device__ __forceinline__ void block_sort_global(uint64_t *a, uint32_t n) {
     }
 }
 
-constexpr uint32_t kSortSmall = 2048;   // keys a 256-thread CTA sorts in 16 KB of static shared memory
-constexpr uint32_t kSortLarge = 12288;  // keys a 1024-thread CTA sorts in 96 KB of dynamic shared memory
-
 // One CTA per (camera, tile).  LARGE = false handles segments of up to kSortSmall keys, LARGE = true
 // the (few) longer ones -- in shared memory up to kSortLarge keys, in place in global memory (L2
 // resident) beyond that.  Both kernels are launched over all tiles and exit early on the other class.
 template <bool LARGE>
 __global__ void __launch_bounds__(LARGE ? 1024 : kThreads)
 tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, int64_t n_isects,
-                 const int32_t *__restrict__ offsets, uint64_t *__restrict__ bucket, int64_t *__restrict__ isect_ids,
-                 int32_t *__restrict__ flatten_ids) {
+                 const int32_t *__restrict__ offsets, const int32_t *__restrict__ large_list,
+                 uint64_t *__restrict__ bucket, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
     extern __shared__ uint64_t s_dyn[];
     __shared__ uint64_t s_static[LARGE ? 1 : kSortSmall];
-    const uint32_t ct = blockIdx.x;
-    const int64_t start = offsets[ct];
-    const int64_t end = (ct + 1 == n_tiles_total) ? n_isects : (int64_t)offsets[ct + 1];
-    const uint32_t n = (uint32_t)(end - start);
-    if (n == 0 || (LARGE ? n <= kSortSmall : n > kSortSmall)) return;
-    const uint64_t cam = ct / n_tiles, tile = ct % n_tiles;
-    const int64_t hi = (int64_t)((cam << (32 + tile_bits)) | (tile << 32));
-    uint64_t *a;
-    if (!LARGE || n <= kSortLarge) {
-        a = LARGE ? s_dyn : s_static;
-        const uint32_t n_pad = (n + 63u) & ~63u;
-        for (uint32_t t = threadIdx.x; t < n_pad; t += blockDim.x) a[t] = t < n ? bucket[start + t] : kInf;
-        __syncthreads();
-        if (n > 1) block_sort_padded(a, n_pad);
-    } else {
-        a = bucket + start;
-        __syncthreads();
-        block_sort_global(a, n);
-    }
-    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
-        const uint64_t it = a[t];
-        // low word: sign-extending OR like the reference's (int64)(int32)depth cast (isect_tiles.cu:88)
-        isect_ids[start + t] = hi | (int64_t)(int32_t)(uint32_t)(it >> 32);
-        flatten_ids[start + t] = (int32_t)(uint32_t)(it & 0xffffffffu);
+    // small: one CTA per tile; large: a few persistent CTAs walk the work list written by replica_cursor_kernel
+    const uint32_t n_work = LARGE ? (uint32_t)large_list[0] : n_tiles_total;
+    for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const uint32_t ct = LARGE ? (uint32_t)large_list[1 + w] : w;
+        const int64_t start = offsets[ct];
+        const int64_t end = (ct + 1 == n_tiles_total) ? n_isects : (int64_t)offsets[ct + 1];
+        const uint32_t n = (uint32_t)(end - start);
+        if (n == 0 || (!LARGE && n > kSortSmall)) continue;
+        const uint64_t cam = ct / n_tiles, tile = ct % n_tiles;
+        const int64_t hi = (int64_t)((cam << (32 + tile_bits)) | (tile << 32));
+        uint64_t *a;
+        if (!LARGE || n <= kSortLarge) {
+            a = LARGE ? s_dyn : s_static;
+            const uint32_t n_pad = (n + 63u) & ~63u;
+            for (uint32_t t = threadIdx.x; t < n_pad; t += blockDim.x) a[t] = t < n ? bucket[start + t] : kInf;
+            __syncthreads();
+            if (n > 1) block_sort_padded(a, n_pad);
+        } else {
+            a = bucket + start;
+            __syncthreads();
+            block_sort_global(a, n);
+        }
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+            const uint64_t it = a[t];
+            // low word: sign-extending OR like the reference's (int64)(int32)depth cast (isect_tiles.cu:88)
+            isect_ids[start + t] = hi | (int64_t)(int32_t)(uint32_t)(it >> 32);
+            flatten_ids[start + t] = (int32_t)(uint32_t)(it & 0xffffffffu);
+        }
+        if (LARGE) __syncthreads();  // the staging buffer is reused by the next work item
     }
 }
 
@@ -354,7 +366,7 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
         GSB_CUDA_OK(cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * T, s));
         return 0;
     }
-    GSB_CUDA_OK(cudaMemsetAsync(tile_cursor, 0, sizeof(int32_t) * (size_t)T * GSB200_ISECT_REPLICAS, s));
+    GSB_CUDA_OK(cudaMemsetAsync(tile_cursor, 0, sizeof(int32_t) * ((size_t)T * GSB200_ISECT_REPLICAS + 1), s));
     isect_count_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
                                                                      camera_ids, means2d, radii, (float)tile_size,
                                                                      tile_width, tile_height, T, tiles_per_gauss, tile_cursor);
@@ -367,7 +379,7 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
     int e = exclusive_scan(T, isect_offsets, nullptr, scratch, s);
     int32_t total = 0;
     if (e == 0) {
-        replica_cursor_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, isect_offsets, tile_cursor);
+        replica_cursor_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, isect_offsets, tile_cursor, kSortSmall);
         e = check_launch("replica_cursor");
     }
     if (e == 0) {
@@ -393,8 +405,9 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
                                                                        camera_ids, means2d, radii, depths, (float)tile_size,
                                                                        tile_width, tile_height, C * n_tiles, tile_cursor, scratch);
     if (int e = check_launch("isect_scatter")) return e;
+    const int32_t *large_list = tile_cursor + (size_t)GSB200_ISECT_REPLICAS * C * n_tiles;
     tile_sort_kernel<false><<<C * n_tiles, kThreads, 0, s>>>(C * n_tiles, n_tiles, bit_width(n_tiles), n_isects,
-                                                              isect_offsets, scratch, isect_ids, flatten_ids);
+                                                              isect_offsets, large_list, scratch, isect_ids, flatten_ids);
     if (int e = check_launch("tile_sort")) return e;
     static bool attr_set = false;
     if (!attr_set) {
@@ -402,8 +415,9 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
                                          (int)(kSortLarge * sizeof(uint64_t))));
         attr_set = true;
     }
-    tile_sort_kernel<true><<<C * n_tiles, 1024, kSortLarge * sizeof(uint64_t), s>>>(
-        C * n_tiles, n_tiles, bit_width(n_tiles), n_isects, isect_offsets, scratch, isect_ids, flatten_ids);
+    const uint32_t large_grid = min(C * n_tiles, 2u * 148u);
+    tile_sort_kernel<true><<<large_grid, 1024, kSortLarge * sizeof(uint64_t), s>>>(
+        C * n_tiles, n_tiles, bit_width(n_tiles), n_isects, isect_offsets, large_list, scratch, isect_ids, flatten_ids);
     return check_launch("tile_sort_large");
 }
 

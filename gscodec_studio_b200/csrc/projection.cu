@@ -71,6 +71,52 @@ __device__ __forceinline__ Sym3 covar_to_cam(const float *R /*3x4 rows*/, const 
     return O;
 }
 
+// Forward-mode dual number over (x, y, z): used to differentiate the fisheye projection exactly as written
+// (the reference hand-expands the same derivatives, proj.cuh:244-362).
+struct Dual3 {
+    float v, d[3];
+};
+__device__ __forceinline__ Dual3 dconst(float c) { return {c, {0.f, 0.f, 0.f}}; }
+__device__ __forceinline__ Dual3 dvar(float c, int k) { Dual3 r = dconst(c); r.d[k] = 1.f; return r; }
+__device__ __forceinline__ Dual3 operator+(Dual3 a, Dual3 b) { return {a.v + b.v, {a.d[0] + b.d[0], a.d[1] + b.d[1], a.d[2] + b.d[2]}}; }
+__device__ __forceinline__ Dual3 operator-(Dual3 a, Dual3 b) { return {a.v - b.v, {a.d[0] - b.d[0], a.d[1] - b.d[1], a.d[2] - b.d[2]}}; }
+__device__ __forceinline__ Dual3 operator+(Dual3 a, float b) { a.v += b; return a; }
+__device__ __forceinline__ Dual3 operator*(Dual3 a, Dual3 b) {
+    return {a.v * b.v, {a.d[0] * b.v + a.v * b.d[0], a.d[1] * b.v + a.v * b.d[1], a.d[2] * b.v + a.v * b.d[2]}};
+}
+__device__ __forceinline__ Dual3 operator*(Dual3 a, float b) { return {a.v * b, {a.d[0] * b, a.d[1] * b, a.d[2] * b}}; }
+__device__ __forceinline__ Dual3 operator/(Dual3 a, Dual3 b) {
+    const float inv = 1.f / b.v, q = a.v * inv;
+    return {q, {(a.d[0] - q * b.d[0]) * inv, (a.d[1] - q * b.d[1]) * inv, (a.d[2] - q * b.d[2]) * inv}};
+}
+__device__ __forceinline__ Dual3 dsqrt(Dual3 a) {
+    const float r = sqrtf(a.v), h = 0.5f / r;
+    return {r, {a.d[0] * h, a.d[1] * h, a.d[2] * h}};
+}
+__device__ __forceinline__ Dual3 datan2(Dual3 p, Dual3 q) {
+    const float inv = 1.f / (p.v * p.v + q.v * q.v);
+    return {atan2f(p.v, q.v), {(q.v * p.d[0] - p.v * q.d[0]) * inv, (q.v * p.d[1] - p.v * q.d[1]) * inv,
+                                (q.v * p.d[2] - p.v * q.d[2]) * inv}};
+}
+
+// fisheye projection (proj.cuh:202-241) evaluated on duals: projected mean and the 2x3 matrix J
+__device__ __forceinline__ void fisheye_dual(float x, float y, float z, float fx, float fy, float cx, float cy, Dual3 m[2],
+                                             Dual3 J[2][3]) {
+    const float eps = 0.0000001f;
+    const Dual3 X = dvar(x, 0), Y = dvar(y, 1), Z = dvar(z, 2);
+    const Dual3 xy_len = dsqrt(X * X + Y * Y) + eps;
+    const Dual3 theta = datan2(xy_len, Z + eps);
+    m[0] = X * fx * theta / xy_len + cx;
+    m[1] = Y * fy * theta / xy_len + cy;
+    const Dual3 x2 = X * X + eps, y2 = Y * Y, xy = X * Y;
+    const Dual3 x2y2 = x2 + y2;
+    const Dual3 inv = dconst(1.f) / (x2y2 + Z * Z);
+    const Dual3 b = datan2(xy_len, Z) / xy_len / x2y2;
+    const Dual3 a = Z * inv / x2y2;
+    J[0][0] = (x2 * a + y2 * b) * fx; J[0][1] = xy * (a - b) * fx; J[0][2] = X * inv * (-fx);
+    J[1][0] = xy * (a - b) * fy; J[1][1] = (y2 * a + x2 * b) * fy; J[1][2] = Y * inv * (-fy);
+}
+
 struct CamProj {
     float J[2][3];
     float mx, my;
@@ -98,6 +144,14 @@ __device__ __forceinline__ CamProj project_point(int model, float x, float y, fl
         P.J[1][0] = 0.f; P.J[1][1] = fy * rz; P.J[1][2] = -fy * ty * rz2;
         P.mx = fx * x * rz + cx; P.my = fy * y * rz + cy;
         P.tx = tx; P.ty = ty; P.rz = rz;
+    } else if (model == GSB200_CAMERA_FISHEYE) {
+        Dual3 m[2], J[2][3];
+        fisheye_dual(x, y, z, fx, fy, cx, cy, m, J);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) P.J[r][j] = J[r][j].v;
+        P.mx = m[0].v; P.my = m[1].v;
     } else {  // ORTHO
         P.J[0][0] = fx; P.J[0][1] = 0.f; P.J[0][2] = 0.f;
         P.J[1][0] = 0.f; P.J[1][1] = fy; P.J[1][2] = 0.f;
@@ -206,8 +260,8 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
     }
 }
 
-template <bool VIEWGRAD>
-__global__ void __launch_bounds__(kThreads, 3)
+template <bool VIEWGRAD, bool FISHEYE>
+__global__ void __launch_bounds__(kThreads, FISHEYE ? 1 : 3)
 projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
                       const float *__restrict__ quats, const float *__restrict__ scales,
                       const float *__restrict__ viewmats, const float *__restrict__ Ks, float W, float H,
@@ -325,6 +379,30 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                     else vmc[2] += -fy * rz3 * vJ[1][2] * P.ty;
                     vmc[2] += -fx * rz2 * vJ[0][0] - fy * rz2 * vJ[1][1] + 2.f * fx * P.tx * rz3 * vJ[0][2] +
                               2.f * fy * P.ty * rz3 * vJ[1][2];
+                } else if (FISHEYE && model == GSB200_CAMERA_FISHEYE) {
+                    // exact derivative of the fisheye map: duals give d(mean2d)/d(xyz) and dJ/d(xyz)
+                    Dual3 m[2], Jd[2][3];
+                    fisheye_dual(mx, my, mz, fx, fy, s_k[ci][2], s_k[ci][3], m, Jd);
+                    float ScM[3][3] = {{Sc.xx, Sc.xy, Sc.xz}, {Sc.xy, Sc.yy, Sc.yz}, {Sc.xz, Sc.yz, Sc.zz}};
+                    float vJ[2][3];
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            const float g0 = GJ[r][0] + (r == 0 ? G00 * P.J[0][0] + G10 * P.J[1][0] : G01 * P.J[0][0] + G11 * P.J[1][0]);
+                            const float g1 = GJ[r][1] + (r == 0 ? G00 * P.J[0][1] + G10 * P.J[1][1] : G01 * P.J[0][1] + G11 * P.J[1][1]);
+                            const float g2 = GJ[r][2] + (r == 0 ? G00 * P.J[0][2] + G10 * P.J[1][2] : G01 * P.J[0][2] + G11 * P.J[1][2]);
+                            vJ[r][j] = g0 * ScM[0][j] + g1 * ScM[1][j] + g2 * ScM[2][j];
+                        }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        float acc = vm0 * m[0].d[k] + vm1 * m[1].d[k];
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) acc += vJ[r][j] * Jd[r][j].d[k];
+                        vmc[k] = acc;
+                    }
                 } else {
                     vmc[0] = fx * vm0; vmc[1] = fy * vm1; vmc[2] = 0.f;
                 }
@@ -522,8 +600,8 @@ extern "C" int gsb200_projection_fwd(uint32_t C, uint32_t N, const float *means,
                                      float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
                                      int packed_radius_rule, int32_t *radii, float *means2d, float *depths, float *conics,
                                      float *compensations, gsb200_stream_t stream) {
-    if (camera_model != GSB200_CAMERA_PINHOLE && camera_model != GSB200_CAMERA_ORTHO)
-        return fail(2, "gsb200_projection_fwd: camera_model must be pinhole or ortho (fisheye not implemented)");
+    if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
+        return fail(2, "gsb200_projection_fwd: camera_model must be pinhole, ortho or fisheye");
     if (covars == nullptr && (quats == nullptr || scales == nullptr))
         return fail(2, "gsb200_projection_fwd: covars or (quats, scales) should be provided");
     if (C == 0 || N == 0) return 0;
@@ -539,18 +617,20 @@ extern "C" int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means,
                                      const float *compensations, const float *v_means2d, const float *v_depths,
                                      const float *v_conics, const float *v_compensations, float *v_means, float *v_covars,
                                      float *v_quats, float *v_scales, float *v_viewmats, gsb200_stream_t stream) {
-    if (camera_model != GSB200_CAMERA_PINHOLE && camera_model != GSB200_CAMERA_ORTHO)
-        return fail(2, "gsb200_projection_bwd: camera_model must be pinhole or ortho (fisheye not implemented)");
+    if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
+        return fail(2, "gsb200_projection_bwd: camera_model must be pinhole, ortho or fisheye");
     if (C == 0 || N == 0) return 0;
     if (v_viewmats != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_viewmats, 0, sizeof(float) * 16 * C, (cudaStream_t)stream));
-    if (v_viewmats != nullptr)
-        projection_bwd_kernel<true><<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-            C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,
-            compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats);
-    else
-        projection_bwd_kernel<false><<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-            C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,
-            compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats);
+    const dim3 grid(cdiv(N, kThreads));
+    cudaStream_t s = (cudaStream_t)stream;
+#define GSB_LAUNCH_PROJ_BWD(VG, FE)                                                                                  \
+    projection_bwd_kernel<VG, FE><<<grid, kThreads, 0, s>>>(                                                          \
+        C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,     \
+        compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats)
+    const bool fe = camera_model == GSB200_CAMERA_FISHEYE;
+    if (v_viewmats != nullptr) { if (fe) GSB_LAUNCH_PROJ_BWD(true, true); else GSB_LAUNCH_PROJ_BWD(true, false); }
+    else { if (fe) GSB_LAUNCH_PROJ_BWD(false, true); else GSB_LAUNCH_PROJ_BWD(false, false); }
+#undef GSB_LAUNCH_PROJ_BWD
     return check_launch("projection_bwd");
 }
 

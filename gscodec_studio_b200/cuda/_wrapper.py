@@ -382,7 +382,7 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
     T = C * tile_width * tile_height
     tiles_per_gauss = torch.empty(radii.shape, dtype=torch.int32, device=dev)
     isect_offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
-    tile_cursor = torch.empty(max(T, 1) * _ISECT_REPLICAS, dtype=torch.int32, device=dev)
+    tile_cursor = torch.empty(max(T, 1) * (_ISECT_REPLICAS + 1) + 1, dtype=torch.int32, device=dev)
     n_host = ctypes.c_int64(0)
     with torch.cuda.device(dev):
         call("gsb200_isect_prepare", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), tile_size,

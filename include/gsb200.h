@@ -124,7 +124,7 @@ int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, cons
  *   1. gsb200_isect_prepare: n_elems = C*N (dense) or nnz (packed; camera_ids i64 [nnz] required).
  *      Writes tiles_per_gauss i32 [n_elems] and isect_offsets i32 [C*tile_h*tile_w]; returns the
  *      number of intersections through *n_isects_host (synchronises `stream`, like the reference's
- *      .item() at isect_tiles.cu:200).  tile_cursor: scratch i32 [GSB200_ISECT_REPLICAS*C*tile_h*tile_w].
+ *      .item() at isect_tiles.cu:200).  tile_cursor: scratch i32 [(GSB200_ISECT_REPLICAS+1)*C*tile_h*tile_w + 1].
  *   2. gsb200_isect_fill: writes isect_ids i64 [I] and flatten_ids i32 [I], sorted.
  *      scratch: u64 [I].  sort == 0 is not supported (returns an error). */
 int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,

@@ -85,7 +85,7 @@ def _scene(C=3, scene_grid=1, width=None, height=None, seed=42):
 
 
 # ------------------------------------------------------------------------------------- projection
-@pytest.mark.parametrize("camera_model", ["pinhole", "ortho"])
+@pytest.mark.parametrize("camera_model", ["pinhole", "ortho", "fisheye"])
 @pytest.mark.parametrize("calc_comp", [False, True])
 def test_projection_matches_oracle(camera_model, calc_comp):
     z = np.load(os.path.join(ROOT, "tests", "golden", "ref_cpu_projection.npz"))
