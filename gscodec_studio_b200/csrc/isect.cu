@@ -132,7 +132,8 @@ replica_cursor_kernel(uint32_t total_tiles, const int32_t *__restrict__ offsets,
 __global__ void __launch_bounds__(kThreads)
 isect_scatter_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids, const float *__restrict__ means2d,
                      const int32_t *__restrict__ radii, const float *__restrict__ depths, float ts, uint32_t tw, uint32_t th,
-                     uint32_t total_tiles, int32_t *__restrict__ tile_cursor, uint64_t *__restrict__ bucket) {
+                     uint32_t total_tiles, int32_t *__restrict__ tile_cursor, uint64_t *__restrict__ bucket,
+                     int64_t capacity) {
     const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
     TileBox b = {0, 0, 0, 0};
     uint32_t cam = 0, depth_bits = 0;
@@ -155,7 +156,7 @@ isect_scatter_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ c
         const uint32_t id = __shfl_sync(0xffffffffu, i, src);
         if (on) {
             const int32_t slot = atomicAdd(mine + (size_t)c * n_tiles + tile, 1);
-            bucket[slot] = ((uint64_t)d << 32) | (uint64_t)id;
+            if (slot < capacity) bucket[slot] = ((uint64_t)d << 32) | (uint64_t)id;
         }
     });
 }
@@ -284,10 +285,15 @@ __device__ __forceinline__ void block_sort_global(uint64_t *a, uint32_t n) {
 // resident) beyond that.  Both kernels are launched over all tiles and exit early on the other class.
 template <bool LARGE>
 __global__ void __launch_bounds__(LARGE ? 1024 : kThreads)
-tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, int64_t n_isects,
-                 const int32_t *__restrict__ offsets, const int32_t *__restrict__ large_list,
-                 uint64_t *__restrict__ bucket, int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, int64_t n_isects_or_capacity,
+                 const int32_t *__restrict__ total_dev, const int32_t *__restrict__ offsets,
+                 const int32_t *__restrict__ large_list, uint64_t *__restrict__ bucket, int64_t *__restrict__ isect_ids,
+                 int32_t *__restrict__ flatten_ids) {
     extern __shared__ uint64_t s_dyn[];
+    // exact mode: the host knows the count; capacity mode: the count lives on the device and segments that
+    // do not fit the (speculatively sized) buffers are skipped -- the host re-runs the fill in that case
+    const int64_t n_isects = total_dev ? (int64_t)*total_dev : n_isects_or_capacity;
+    const int64_t capacity = n_isects_or_capacity;
     __shared__ uint64_t s_static[LARGE ? 1 : kSortSmall];
     // small: one CTA per tile; large: a few persistent CTAs walk the work list written by replica_cursor_kernel
     const uint32_t n_work = LARGE ? (uint32_t)large_list[0] : n_tiles_total;
@@ -296,7 +302,7 @@ tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, i
         const int64_t start = offsets[ct];
         const int64_t end = (ct + 1 == n_tiles_total) ? n_isects : (int64_t)offsets[ct + 1];
         const uint32_t n = (uint32_t)(end - start);
-        if (n == 0 || (!LARGE && n > kSortSmall)) continue;
+        if (n == 0 || (!LARGE && n > kSortSmall) || end > capacity) continue;
         const uint64_t cam = ct / n_tiles, tile = ct % n_tiles;
         const int64_t hi = (int64_t)((cam << (32 + tile_bits)) | (tile << 32));
         uint64_t *a;
@@ -358,12 +364,13 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
                                     int32_t *tile_cursor, int64_t *n_isects_host, gsb200_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t T = C * tile_width * tile_height;
-    *n_isects_host = 0;
+    if (n_isects_host != nullptr) *n_isects_host = 0;
     if (bit_width(tile_width * tile_height) + bit_width(C) > 32)
         return fail(2, "gsb200_isect_prepare: camera and tile ids do not fit 32 bits");
     if (T == 0) return 0;
     if (n_elems == 0) {
         GSB_CUDA_OK(cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * T, s));
+        GSB_CUDA_OK(cudaMemsetAsync(tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1, 0, sizeof(int32_t), s));
         return 0;
     }
     GSB_CUDA_OK(cudaMemsetAsync(tile_cursor, 0, sizeof(int32_t) * ((size_t)T * GSB200_ISECT_REPLICAS + 1), s));
@@ -378,18 +385,22 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
     GSB_CUDA_OK(cudaMallocAsync((void **)&scratch, sizeof(int32_t) * (nb + 2), s));
     int e = exclusive_scan(T, isect_offsets, nullptr, scratch, s);
     int32_t total = 0;
+    int32_t *total_dev = tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1;
     if (e == 0) {
         replica_cursor_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, isect_offsets, tile_cursor, kSortSmall);
         e = check_launch("replica_cursor");
     }
     if (e == 0) {
-        cudaError_t ce = cudaMemcpyAsync(&total, scratch + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        cudaError_t ce = cudaMemcpyAsync(total_dev, scratch + nb, sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+        if (ce == cudaSuccess && n_isects_host != nullptr) {
+            ce = cudaMemcpyAsync(&total, scratch + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        }
         if (ce != cudaSuccess) e = fail(101, cudaGetErrorString(ce));
     }
     cudaFreeAsync(scratch, s);
     if (e) return e;
-    *n_isects_host = total;
+    if (n_isects_host != nullptr) *n_isects_host = total;
     return 0;
 }
 
@@ -400,14 +411,17 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
                                  gsb200_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (n_isects == 0 || n_elems == 0) return 0;
-    const uint32_t n_tiles = tile_width * tile_height;
+    const uint32_t n_tiles = tile_width * tile_height, T = C * n_tiles;
+    // n_isects < 0: capacity mode (see include/gsb200.h)
+    const int64_t bound = n_isects < 0 ? -n_isects : n_isects;
+    const int32_t *total_dev = n_isects < 0 ? tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1 : nullptr;
     isect_scatter_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
                                                                        camera_ids, means2d, radii, depths, (float)tile_size,
-                                                                       tile_width, tile_height, C * n_tiles, tile_cursor, scratch);
+                                                                       tile_width, tile_height, T, tile_cursor, scratch, bound);
     if (int e = check_launch("isect_scatter")) return e;
-    const int32_t *large_list = tile_cursor + (size_t)GSB200_ISECT_REPLICAS * C * n_tiles;
-    tile_sort_kernel<false><<<C * n_tiles, kThreads, 0, s>>>(C * n_tiles, n_tiles, bit_width(n_tiles), n_isects,
-                                                              isect_offsets, large_list, scratch, isect_ids, flatten_ids);
+    const int32_t *large_list = tile_cursor + (size_t)GSB200_ISECT_REPLICAS * T;
+    tile_sort_kernel<false><<<T, kThreads, 0, s>>>(T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, large_list,
+                                                    scratch, isect_ids, flatten_ids);
     if (int e = check_launch("tile_sort")) return e;
     static bool attr_set = false;
     if (!attr_set) {
@@ -415,9 +429,9 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
                                          (int)(kSortLarge * sizeof(uint64_t))));
         attr_set = true;
     }
-    const uint32_t large_grid = min(C * n_tiles, 2u * 148u);
+    const uint32_t large_grid = min(T, 2u * 148u);
     tile_sort_kernel<true><<<large_grid, 1024, kSortLarge * sizeof(uint64_t), s>>>(
-        C * n_tiles, n_tiles, bit_width(n_tiles), n_isects, isect_offsets, large_list, scratch, isect_ids, flatten_ids);
+        T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, large_list, scratch, isect_ids, flatten_ids);
     return check_launch("tile_sort_large");
 }
 

@@ -382,20 +382,63 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
     T = C * tile_width * tile_height
     tiles_per_gauss = torch.empty(radii.shape, dtype=torch.int32, device=dev)
     isect_offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
-    tile_cursor = torch.empty(max(T, 1) * (_ISECT_REPLICAS + 1) + 1, dtype=torch.int32, device=dev)
-    n_host = ctypes.c_int64(0)
-    with torch.cuda.device(dev):
+    tile_cursor = torch.empty((_ISECT_REPLICAS + 1) * max(T, 1) + 2, dtype=torch.int32, device=dev)
+    total_index = (_ISECT_REPLICAS + 1) * max(T, 1) + 1
+    key = (dev.index, C, n_elems, tile_width, tile_height, tile_size)
+    capacity = _isect_capacity.get(key)
+
+    def prepare(n_host_ref):
         call("gsb200_isect_prepare", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), tile_size,
-             tile_width, tile_height, ptr(tiles_per_gauss), ptr(isect_offsets), ptr(tile_cursor), ctypes.byref(n_host),
+             tile_width, tile_height, ptr(tiles_per_gauss), ptr(isect_offsets), ptr(tile_cursor), n_host_ref,
              stream_ptr(dev))
+
+    def fill(n_arg, isect_ids, flatten_ids, scratch):
+        call("gsb200_isect_fill", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths), tile_size,
+             tile_width, tile_height, n_arg, ptr(isect_offsets), ptr(tile_cursor), ptr(scratch), ptr(isect_ids),
+             ptr(flatten_ids), stream_ptr(dev))
+
+    with torch.cuda.device(dev):
+        if capacity is not None and T > 0 and n_elems > 0:
+            # Speculative sizing: the intersection count of the previous call (+25 %) sizes the buffers, every
+            # kernel of the stage is enqueued, and only then does the host wait -- for an event recorded right
+            # after the count reached pinned memory, i.e. while scatter + sort are still running.  The GPU is
+            # never idle, unlike with the reference's mid-stage `.item()` (isect_tiles.cu:200).
+            isect_ids = torch.empty(capacity, dtype=torch.int64, device=dev)
+            flatten_ids = torch.empty(capacity, dtype=torch.int32, device=dev)
+            scratch = torch.empty(capacity, dtype=torch.int64, device=dev)
+            prepare(None)
+            pinned = _pinned_counter(dev)
+            pinned.copy_(tile_cursor[total_index:total_index + 1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            fill(-capacity, isect_ids, flatten_ids, scratch)
+            ev.synchronize()
+            n_isects = int(pinned.item())
+            if n_isects <= capacity:
+                _isect_capacity[key] = max(int(n_isects * 1.25) + 4096, 4096)
+                return tiles_per_gauss, isect_ids[:n_isects], flatten_ids[:n_isects], isect_offsets
+            # overflow (scene grew by more than 25 % in one step): fall through to the exact path
+        n_host = ctypes.c_int64(0)
+        prepare(ctypes.byref(n_host))
         n_isects = int(n_host.value)
+        _isect_capacity[key] = max(int(n_isects * 1.25) + 4096, 4096)
         isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
         flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
         scratch = torch.empty(max(n_isects, 1), dtype=torch.int64, device=dev)
-        call("gsb200_isect_fill", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths), tile_size,
-             tile_width, tile_height, n_isects, ptr(isect_offsets), ptr(tile_cursor), ptr(scratch), ptr(isect_ids),
-             ptr(flatten_ids), stream_ptr(dev))
+        fill(n_isects, isect_ids, flatten_ids, scratch)
     return tiles_per_gauss, isect_ids, flatten_ids, isect_offsets
+
+
+_isect_capacity = {}  # (device, C, n_elems, tile grid) -> speculative buffer capacity for the next call
+_pinned = {}
+
+
+def _pinned_counter(dev) -> Tensor:
+    buf = _pinned.get(dev.index)
+    if buf is None:
+        buf = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _pinned[dev.index] = buf
+    return buf
 
 
 @torch.no_grad()

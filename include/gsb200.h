@@ -124,9 +124,16 @@ int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, cons
  *   1. gsb200_isect_prepare: n_elems = C*N (dense) or nnz (packed; camera_ids i64 [nnz] required).
  *      Writes tiles_per_gauss i32 [n_elems] and isect_offsets i32 [C*tile_h*tile_w]; returns the
  *      number of intersections through *n_isects_host (synchronises `stream`, like the reference's
- *      .item() at isect_tiles.cu:200).  tile_cursor: scratch i32 [(GSB200_ISECT_REPLICAS+1)*C*tile_h*tile_w + 1].
- *   2. gsb200_isect_fill: writes isect_ids i64 [I] and flatten_ids i32 [I], sorted.
- *      scratch: u64 [I].  sort == 0 is not supported (returns an error). */
+ *      .item() at isect_tiles.cu:200).  With n_isects_host == NULL the call does not synchronise; the
+ *      count is then only available on the device, at tile_cursor[GSB200_ISECT_TOTAL_INDEX(T)].
+ *      tile_cursor: scratch i32 [GSB200_ISECT_CURSOR_SIZE(T)], T = C*tile_h*tile_w.
+ *   2. gsb200_isect_fill: writes isect_ids i64 [I] and flatten_ids i32 [I], sorted.  scratch: u64 [I].
+ *      n_isects >= 0: exact count (buffers hold I entries).  n_isects < 0: "capacity mode" -- buffers hold
+ *      -n_isects entries, the true count is read from the device; if it exceeds the capacity the outputs
+ *      are incomplete and the caller must call again with larger buffers once it knows the count
+ *      (lets the host size buffers speculatively and fetch the count without idling the GPU). */
+#define GSB200_ISECT_CURSOR_SIZE(T) ((GSB200_ISECT_REPLICAS + 1) * (size_t)(T) + 2)
+#define GSB200_ISECT_TOTAL_INDEX(T) ((GSB200_ISECT_REPLICAS + 1) * (size_t)(T) + 1)
 int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
                          const int64_t *camera_ids, const float *means2d, const int32_t *radii,
                          uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,

@@ -638,3 +638,29 @@ def test_kernels_match_reference_cuda_golden():
                        ("v_conics", ins[1].grad, g["v_conics"]), ("v_colors", ins[2].grad, g["v_colors"]),
                        ("v_opacities", ins[3].grad, g["v_opacities"])):
         assert_grad_close(a, b, name)
+
+
+def test_isect_speculative_capacity_mode():
+    """Second and later calls size the buffers from the previous count and fetch the count without idling the
+    GPU; results must be identical, also when the speculation overflows and the exact path is re-run."""
+    from gscodec_studio_b200.cuda import _wrapper as Wr
+
+    means, quats, scales, opac, colors, viewmats, Ks, W, H = [t.to(DEV) if torch.is_tensor(t) else t for t in _scene(C=2)]
+    radii, m2d, dep, con, _ = gs.fully_fused_projection(means, None, quats, scales, viewmats, Ks, W, H)
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    Wr._isect_capacity.clear()
+    first = _isect_tiles_with_offsets(m2d, radii, dep, 16, tw, th)       # exact path, primes the cache
+    assert len(Wr._isect_capacity) == 1
+    second = _isect_tiles_with_offsets(m2d, radii, dep, 16, tw, th)      # capacity mode
+    for a, b in zip(first, second):
+        assert torch.equal(a, b)
+    key = next(iter(Wr._isect_capacity))
+    Wr._isect_capacity[key] = 1000                                       # force an overflow
+    third = _isect_tiles_with_offsets(m2d, radii, dep, 16, tw, th)
+    for a, b in zip(first, third):
+        assert torch.equal(a, b)
+    assert Wr._isect_capacity[key] > first[1].numel()
+    # fewer intersections than last time (smaller radii): capacity mode with slack
+    fourth = _isect_tiles_with_offsets(m2d, (radii // 2).contiguous(), dep, 16, tw, th)
+    o = O.isect_tiles(m2d.cpu(), (radii // 2).cpu(), dep.cpu(), 16, tw, th, 2)
+    assert torch.equal(fourth[1].cpu(), o[1]) and torch.equal(fourth[2].cpu(), o[2])
