@@ -67,8 +67,14 @@ def all_to_all_int32(world_size: int, values: List[Union[int, Tensor]], device: 
     return list(recv.unbind())
 
 
+def _uneven_lists_ok() -> bool:
+    # NCCL's list-form all_gather / reduce_scatter accept per-rank blocks of different sizes (grouped
+    # broadcast / reduce); gloo does not.
+    return dist.get_backend() == "nccl"
+
+
 def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool):
-    """Start the all-gather of per-rank row blocks [n_r, ...] -> ([sum n_r, ...] tensor or padded buffer, work)."""
+    """Start the all-gather of per-rank row blocks [n_r, ...] straight into the final [sum n_r, ...] buffer."""
     world, rank = dist.get_world_size(), dist.get_rank()
     n_max = max(counts)
     tail = tuple(data.shape[1:])
@@ -76,6 +82,14 @@ def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool):
     if all(c == n_max for c in counts):
         out = torch.empty((world * n_max,) + tail, dtype=data.dtype, device=data.device)
         work = dist.all_gather_into_tensor(out, data, async_op=async_op)
+        return out, work, False
+    if _uneven_lists_ok():
+        out = torch.empty((sum(counts),) + tail, dtype=data.dtype, device=data.device)
+        views, start = [], 0
+        for c in counts:
+            views.append(out[start:start + c])
+            start += c
+        work = dist.all_gather(views, data, async_op=async_op)
         return out, work, False
     padded = torch.zeros((n_max,) + tail, dtype=data.dtype, device=data.device)
     padded[: counts[rank]] = data
@@ -99,22 +113,24 @@ def _reduce_scatter_rows(v_out: Tensor, counts: Sequence[int]) -> Tensor:
     n_max = max(counts)
     tail = tuple(v_out.shape[1:])
     v_out = v_out.contiguous()
-    if all(c == n_max for c in counts):
-        send = v_out
-    else:
-        send = torch.zeros((world * n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
-        start = 0
-        for r in range(world):
-            send[r * n_max: r * n_max + counts[r]] = v_out[start: start + counts[r]]
-            start += counts[r]
-    if _backend_supports("reduce_scatter_tensor"):
+    even = all(c == n_max for c in counts)
+    if even and _backend_supports("reduce_scatter_tensor"):
         recv = torch.empty((n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
-        dist.reduce_scatter_tensor(recv, send, op=dist.ReduceOp.SUM)
-    else:
-        send = send.clone() if send is v_out else send
-        dist.all_reduce(send, op=dist.ReduceOp.SUM)
-        recv = send[rank * n_max: (rank + 1) * n_max]
-    return recv[: counts[rank]].contiguous()
+        dist.reduce_scatter_tensor(recv, v_out, op=dist.ReduceOp.SUM)
+        return recv
+    if not even and _uneven_lists_ok():
+        recv = torch.empty((counts[rank],) + tail, dtype=v_out.dtype, device=v_out.device)
+        views, start = [], 0
+        for c in counts:
+            views.append(v_out[start:start + c])
+            start += c
+        dist.reduce_scatter(recv, views, op=dist.ReduceOp.SUM)
+        return recv
+    # generic fallback (gloo): all-reduce the whole gradient and keep the local rows
+    total = v_out.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM)
+    start = sum(counts[:rank])
+    return total[start:start + counts[rank]].contiguous()
 
 
 class _FinishGather(torch.autograd.Function):
@@ -144,9 +160,26 @@ class PendingGather:
         return _FinishGather.apply(self.data, self)
 
 
-def gather_counts(n: int, device) -> List[int]:
+_host_group = None
+
+
+def _get_host_group():
+    """A gloo side group for tiny host-side exchanges.  Going through NCCL for a single integer would
+    order the exchange behind all queued GPU work and block the host on it (the reference does exactly
+    that with all_gather_int32, rendering.py:287) -- the GPU then idles while the host catches up."""
+    global _host_group
+    if _host_group is None:
+        _host_group = dist.group.WORLD if dist.get_backend() == "gloo" else dist.new_group(backend="gloo")
+    return _host_group
+
+
+def gather_counts(n: int, device=None) -> List[int]:
+    """Number of rows every rank contributes (host-side exchange, does not touch the GPU stream)."""
     world = dist.get_world_size()
-    return [int(c) for c in all_gather_int32(world, int(n), device=device)]
+    mine = torch.tensor([int(n)], dtype=torch.int64)
+    out = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(out, mine, group=_get_host_group())
+    return [int(t.item()) for t in out]
 
 
 def start_gather(t: Tensor, counts: Sequence[int]) -> PendingGather:
