@@ -140,7 +140,30 @@ def run_ours(args):
     sim_step = 20_000 if args.entropy else 100
     state = {}
 
+    m1_attrs = None
+    if args.workload == "m1":
+        # protocol of the reference's profiling/main.py:63-133: activated attributes, 3 pre-activated colour
+        # channels, no quant-sim, loss = render_colors.sum()
+        with torch.no_grad():
+            m1_attrs = [params["means"].detach().clone(), params["quats"].detach().clone(),
+                        torch.exp(params["scales"]).detach(), torch.sigmoid(params["opacities"]).detach(),
+                        (params["sh0"][:, 0, :] * SH_C0 + 0.5).detach().contiguous()]
+        for t in m1_attrs:
+            t.requires_grad_(True)
+
+    def step_m1(viewmat, K, target):
+        for t in m1_attrs:
+            t.grad = None
+        rc, ra, meta = gs.rasterization(*m1_attrs, viewmat, K, W_IMG, H_IMG, packed=args.packed, near_plane=0.01,
+                                        far_plane=100.0, radius_clip=3.0, distributed=world > 1)
+        loss = rc.sum()
+        loss.backward()
+        state["meta"] = meta
+        return loss
+
     def step(viewmat, K, target):
+        if m1_attrs is not None:
+            return step_m1(viewmat, K, target)
         for p in params.values():
             p.grad = None
         new, bits = sim.simulate_compression(params, sim_step, fuse_activations=True)
@@ -246,9 +269,12 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"M2: load_test_data(scene_grid={args.scene_grid}) {n_total} Gaussians, 1 view 1920x1080 per GPU, "
-                            "SH deg 3, 8-bit noise fake-quant (scales,quats,opacities,sh0) fused with exp/sigmoid, "
-                            "packed=False, L1 loss, fwd+bwd to raw params" + (", factorized entropy model on" if args.entropy else ""),
+                "workload": (f"M1 (profiling/main.py protocol): load_test_data(scene_grid={args.scene_grid}) {n_total} Gaussians, "
+                             f"1 view 1920x1080 per GPU, 3 colour channels, packed={args.packed}, loss=sum, no quant-sim"
+                             if args.workload == "m1" else
+                             f"M2: load_test_data(scene_grid={args.scene_grid}) {n_total} Gaussians, 1 view 1920x1080 per GPU, "
+                             "SH deg 3, 8-bit noise fake-quant (scales,quats,opacities,sh0) fused with exp/sigmoid, "
+                             "packed=False, L1 loss, fwd+bwd to raw params" + (", factorized entropy model on" if args.entropy else "")),
                 "n_isects": n_isects, "l2": "inputs larger than L2 (236 MB of splat attributes + 25 MB image per step)",
                 "parallelism": f"view-parallel x{world}, attribute all-gather" if world > 1 else "single GPU",
             },
@@ -347,6 +373,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scene-grid", dest="scene_grid", type=int, default=3)
+    ap.add_argument("--workload", choices=["m2", "m1"], default="m2", help="m2 = headline (quant-sim + SH), m1 = profiling/main.py")
+    ap.add_argument("--packed", action="store_true", help="m1 only: packed=True (the reference API default)")
     ap.add_argument("--entropy", action="store_true", help="also run the factorized entropy model on scales/quats/sh0")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()

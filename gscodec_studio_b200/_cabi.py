@@ -41,6 +41,7 @@ SIGNATURES = {
     "gsb200_sh_view_bwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_isect_prepare": [_U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_fill": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _L, _P, _P, _P, _P, _P, _P],
+    "gsb200_isect_emit_unsorted": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_offset_encode": [_L, _P, _U, _U, _U, _P, _P],
     "gsb200_rasterize_fwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P],
     "gsb200_grad_record": [_U],

@@ -327,6 +327,31 @@ tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, i
     }
 }
 
+// sort == false variant of the reference op: keys in emission order (ascending flatten index, row-major
+// tiles inside each Gaussian), isect_tiles.cu:89-103.  `cum` = exclusive scan of tiles_per_gauss.
+__global__ void __launch_bounds__(kThreads)
+isect_emit_unsorted_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids,
+                           const float *__restrict__ means2d, const int32_t *__restrict__ radii,
+                           const float *__restrict__ depths, float ts, uint32_t tw, uint32_t th, uint32_t tile_bits,
+                           const int32_t *__restrict__ cum, int64_t *__restrict__ isect_ids,
+                           int32_t *__restrict__ flatten_ids) {
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const int32_t r = radii[i];
+    if (r <= 0) return;
+    const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + i);
+    const TileBox b = tile_box(m.x, m.y, (float)r, ts, tw, th);
+    const uint64_t cam = camera_ids ? (uint64_t)camera_ids[i] : i / per_cam;
+    const int64_t hi = (int64_t)(cam << (32 + tile_bits));
+    const int64_t lo = (int64_t)(int32_t)__float_as_uint(depths[i]);
+    int64_t at = cum[i];
+    for (uint32_t y = b.y0; y < b.y1; ++y)
+        for (uint32_t x = b.x0; x < b.x1; ++x, ++at) {
+            isect_ids[at] = hi | ((int64_t)(y * tw + x) << 32) | lo;
+            flatten_ids[at] = (int32_t)i;
+        }
+}
+
 // stand-alone offsets from already-sorted ids: one lower_bound per (camera, tile)
 __global__ void __launch_bounds__(kThreads)
 offset_encode_kernel(int64_t n_isects, const int64_t *__restrict__ isect_ids, uint32_t total_tiles, uint32_t n_tiles,
@@ -433,6 +458,27 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
     tile_sort_kernel<true><<<large_grid, 1024, kSortLarge * sizeof(uint64_t), s>>>(
         T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, large_list, scratch, isect_ids, flatten_ids);
     return check_launch("tile_sort_large");
+}
+
+extern "C" int gsb200_isect_emit_unsorted(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera, const int64_t *camera_ids,
+                                          const float *means2d, const int32_t *radii, const float *depths,
+                                          uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                                          const int32_t *tiles_per_gauss, int32_t *cum_scratch, int64_t *isect_ids,
+                                          int32_t *flatten_ids, gsb200_stream_t stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_elems == 0) return 0;
+    GSB_CUDA_OK(cudaMemcpyAsync(cum_scratch, tiles_per_gauss, sizeof(int32_t) * n_elems, cudaMemcpyDeviceToDevice, s));
+    const uint32_t nb = cdiv(n_elems, kScanTile);
+    int32_t *scratch = nullptr;
+    GSB_CUDA_OK(cudaMallocAsync((void **)&scratch, sizeof(int32_t) * (nb + 2), s));
+    int e = exclusive_scan(n_elems, cum_scratch, nullptr, scratch, s);
+    cudaFreeAsync(scratch, s);
+    if (e) return e;
+    const uint32_t n_tiles = tile_width * tile_height;
+    isect_emit_unsorted_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(
+        n_elems, elems_per_camera ? elems_per_camera : 1, camera_ids, means2d, radii, depths, (float)tile_size, tile_width,
+        tile_height, bit_width(n_tiles), cum_scratch, isect_ids, flatten_ids);
+    return check_launch("isect_emit_unsorted");
 }
 
 extern "C" int gsb200_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, uint32_t C, uint32_t tile_width,

@@ -373,8 +373,6 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
         assert depths.shape == (C, N), depths.size()
         camera_ids = None
         n_elems, per_cam = C * N, N
-    if not sort:
-        raise NotImplementedError("gscodec_studio_b200.isect_tiles: sort=False is not supported by the per-tile design")
     dev = means2d.device
     means2d, depths = _f32(means2d.detach()), _f32(depths.detach())
     radii = radii.contiguous()
@@ -396,6 +394,20 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
         call("gsb200_isect_fill", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths), tile_size,
              tile_width, tile_height, n_arg, ptr(isect_offsets), ptr(tile_cursor), ptr(scratch), ptr(isect_ids),
              ptr(flatten_ids), stream_ptr(dev))
+
+    if not sort:
+        # emission order (reference: sort=False): exact path + a scan over tiles_per_gauss
+        with torch.cuda.device(dev):
+            n_host = ctypes.c_int64(0)
+            prepare(ctypes.byref(n_host))
+            n_isects = int(n_host.value)
+            isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+            flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+            cum = torch.empty(max(n_elems, 1), dtype=torch.int32, device=dev)
+            call("gsb200_isect_emit_unsorted", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths),
+                 tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(cum), ptr(isect_ids), ptr(flatten_ids),
+                 stream_ptr(dev))
+        return tiles_per_gauss, isect_ids, flatten_ids, isect_offsets
 
     with torch.cuda.device(dev):
         if capacity is not None and T > 0 and n_elems > 0:

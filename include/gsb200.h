@@ -145,6 +145,15 @@ int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
                       uint32_t tile_height, int64_t n_isects, const int32_t *isect_offsets,
                       int32_t *tile_cursor, uint64_t *scratch, int64_t *isect_ids,
                       int32_t *flatten_ids, gsb200_stream_t stream);
+/* `sort = false` form of _C.isect_tiles: keys in emission order (ascending flatten index, row-major tiles per
+ * Gaussian).  Call after gsb200_isect_prepare (which gives tiles_per_gauss and the count);
+ * cum_scratch: i32 [n_elems]. */
+int gsb200_isect_emit_unsorted(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
+                               const int64_t *camera_ids, const float *means2d, const int32_t *radii,
+                               const float *depths, uint32_t tile_size, uint32_t tile_width,
+                               uint32_t tile_height, const int32_t *tiles_per_gauss,
+                               int32_t *cum_scratch, int64_t *isect_ids, int32_t *flatten_ids,
+                               gsb200_stream_t stream);
 /* stand-alone _C.isect_offset_encode (isect_tiles.cu:308-389) for callers that hold sorted ids */
 int gsb200_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, uint32_t C,
                                uint32_t tile_width, uint32_t tile_height, int32_t *isect_offsets,

@@ -664,3 +664,25 @@ def test_isect_speculative_capacity_mode():
     fourth = _isect_tiles_with_offsets(m2d, (radii // 2).contiguous(), dep, 16, tw, th)
     o = O.isect_tiles(m2d.cpu(), (radii // 2).cpu(), dep.cpu(), 16, tw, th, 2)
     assert torch.equal(fourth[1].cpu(), o[1]) and torch.equal(fourth[2].cpu(), o[2])
+
+
+def test_isect_unsorted_and_sparse_grad():
+    means, quats, scales, opac, colors, viewmats, Ks, W, H = [t.to(DEV) if torch.is_tensor(t) else t for t in _scene(C=2)]
+    radii, m2d, dep, con, _ = gs.fully_fused_projection(means, None, quats, scales, viewmats, Ks, W, H)
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    tpg, ids, fl = gs.isect_tiles(m2d, radii, dep, 16, tw, th, sort=False)
+    o = O.isect_tiles(m2d.cpu(), radii.cpu(), dep.cpu(), 16, tw, th, 2, sort=False)
+    assert torch.equal(tpg.cpu(), o[0]) and torch.equal(ids.cpu(), o[1]) and torch.equal(fl.cpu(), o[2])
+    # sparse_grad: COO gradients that densify to the dense-mode gradients
+    g = torch.Generator().manual_seed(4)
+    outs = {}
+    for sparse in (False, True):
+        m, q, s = [t.clone().requires_grad_(True) for t in (means, quats, scales)]
+        cam, gid, r, m2, d2, c2, _ = gs.fully_fused_projection(m, None, q, s, viewmats, Ks, W, H, packed=True,
+                                                               sparse_grad=sparse)
+        w = torch.randn(m2.shape, generator=torch.Generator().manual_seed(4)).to(DEV)
+        ((m2 * w).sum() + c2.sum() + d2.sum()).backward()
+        outs[sparse] = [t.grad for t in (m, q, s)]
+    for dense, sp in zip(outs[False], outs[True]):
+        assert sp.is_sparse and sp.shape == dense.shape
+        assert rel_err(sp.to_dense(), dense) < 1e-6
