@@ -180,7 +180,7 @@ __device__ __forceinline__ float entropy_logit_vjp(const float *__restrict__ P, 
 
 constexpr int kEntropyThreads = 128;
 
-// grid: (ceil(L / kEntropyThreads), 32 chunks, ch); element n = j*L + blockIdx.x*threads + tid
+// grid: (blocks per segment, 32 chunks, ch); element n = j*L + local, local grid-strided inside the segment
 template <int NH, bool BWD>
 __global__ void __launch_bounds__(kEntropyThreads)
 entropy_kernel(int64_t N, uint32_t ch, int64_t L, const float *__restrict__ x, float q, const float *__restrict__ params,
@@ -193,15 +193,17 @@ entropy_kernel(int64_t N, uint32_t ch, int64_t L, const float *__restrict__ x, f
     const uint32_t p = (32u * c + j) % ch;
     for (int k = threadIdx.x; k < PS; k += blockDim.x) { sP[k] = params[(size_t)p * PS + k]; if (BWD) sV[k] = 0.f; }
     __syncthreads();
-    const int64_t local = (int64_t)blockIdx.x * kEntropyThreads + threadIdx.x;
-    const int64_t n = (int64_t)j * L + local;
-    const bool on = local < L && n < N;
     float vP[PS];
     if (BWD) {
 #pragma unroll
         for (int k = 0; k < PS; ++k) vP[k] = 0.f;
     }
-    if (on) {
+    // grid-stride over the segment: a thread owns many elements, so the parameter-gradient reduction
+    // below runs once per thread instead of once per element
+    for (int64_t local = (int64_t)blockIdx.x * kEntropyThreads + threadIdx.x; local < L;
+         local += (int64_t)gridDim.x * kEntropyThreads) {
+        const int64_t n = (int64_t)j * L + local;
+        if (n >= N) break;
         const float xv = x[n * ch + c];
         const float ul = xv - 0.5f * q, uu = xv + 0.5f * q;
         const float lower = entropy_logit<NH>(sP, ul, nullptr, nullptr);
@@ -272,7 +274,10 @@ static int entropy_launch(bool bwd, int64_t N, uint32_t ch, uint32_t n_hidden, c
     if (N == 0) return 0;
     const int64_t Npad = N + (32 - N % 32);  // entropy_model.py:223 (a full extra 32 when N % 32 == 0)
     const int64_t L = Npad / 32;
-    dim3 grid((unsigned)((L + kEntropyThreads - 1) / kEntropyThreads), 32, ch);
+    const int64_t full = (L + kEntropyThreads - 1) / kEntropyThreads;
+    // backward: few blocks per segment so that each thread accumulates ~16 elements before the reduction
+    const int64_t per_seg = bwd ? (full < 16 ? full : 16) : full;
+    dim3 grid((unsigned)per_seg, 32, ch);
     if (!bwd) {
         if (n_hidden == 2) entropy_kernel<2, false><<<grid, kEntropyThreads, 0, s>>>(N, ch, L, x, q, params, bound, bits, nullptr, nullptr, nullptr);
         else entropy_kernel<3, false><<<grid, kEntropyThreads, 0, s>>>(N, ch, L, x, q, params, bound, bits, nullptr, nullptr, nullptr);
