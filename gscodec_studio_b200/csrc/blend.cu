@@ -124,8 +124,7 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                  const float *__restrict__ colors, const float *__restrict__ opacities,
                  const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
                  const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
-                 float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids,
-                 uint32_t *__restrict__ contrib) {
+                 float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
     constexpr int CP = ColorPad<CDIM>::value;
     extern __shared__ float4 smem4[];
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
@@ -161,13 +160,6 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     const int jmin = __reduce_min_sync(wmask, inside ? (int)j : INT_MAX), jmax = __reduce_max_sync(wmask, inside ? (int)j : -1);
     const int imin = __reduce_min_sync(wmask, inside ? (int)i : INT_MAX), imax = __reduce_max_sync(wmask, inside ? (int)i : -1);
     const float wx0 = (float)jmin + 0.5f, wx1 = (float)jmax + 0.5f, wy0 = (float)imin + 0.5f, wy1 = (float)imax + 0.5f;
-
-    // contribution masks (optional): one 32-bit word per (32-Gaussian chunk, warp); bit b is set iff some
-    // pixel of the warp blended Gaussian 32*chunk + b.  Chunk q of this tile lives at chunk_base + q
-    // (floor(start/32) + tile index never overlaps between tiles).  The backward reads them instead of
-    // re-deriving which (warp, Gaussian) pairs matter.
-    const uint32_t chunk_base = ((uint32_t)range_start >> 5) + (uint32_t)ct;
-    const uint32_t nwarps = nthreads >> 5, warp_id = tid >> 5;
 
     float T = 1.f;
     uint32_t cur_idx = 0;
@@ -207,12 +199,9 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                 hit = ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, A.w, wx0, wx1, wy0, wy1);
             }
             unsigned m = __ballot_sync(wmask, hit);
-            unsigned cm = 0;
             while (m) {
-                const uint32_t bit = (uint32_t)__ffs(m) - 1u;
-                const uint32_t t = c0 + bit;
+                const uint32_t t = c0 + (uint32_t)__ffs(m) - 1u;
                 m &= m - 1;
-                bool applied = false;
                 if (!done) {
                     const float4 A = lds4(aA + t * 16);
                     const float4 B = lds4(aB + t * 16);
@@ -235,14 +224,10 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                             }
                             cur_idx = (uint32_t)batch_start + t;
                             T = next_T;
-                            applied = true;
                         }
                     }
                 }
-                if (contrib != nullptr && __any_sync(wmask, applied)) cm |= 1u << bit;
             }
-            if (contrib != nullptr && cm != 0 && lane == 0)
-                contrib[(size_t)(chunk_base + (((uint32_t)(batch_start - range_start) + c0) >> 5)) * nwarps + warp_id] = cm;
             if (__ballot_sync(wmask, !done) == 0) { warp_done = true; break; }
         }
     }
@@ -284,12 +269,6 @@ __device__ __forceinline__ uint32_t spread_slot(uint32_t lane) {
     return slot;
 }
 
-// words of the contribution-mask buffer: ((I >> 5) + T + 2) chunks x warps per tile
-__host__ __device__ inline size_t contrib_mask_words(int64_t n_isects, uint32_t total_tiles, uint32_t tile_size) {
-    const size_t nwarps = (tile_size * tile_size + 31) / 32;
-    return ((size_t)(n_isects >> 5) + total_tiles + 2) * nwarps;
-}
-
 // packed gradient record (floats): [rgb(CDIM) | conic(3) | xy(2) | opac(1) | abs(2)] rounded up to 4
 __host__ __device__ constexpr uint32_t grad_record(uint32_t cdim) { return (cdim + 8 + 3) / 4 * 4; }
 
@@ -301,7 +280,7 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                  const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
                  const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
                  const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas,
-                 const uint32_t *__restrict__ contrib, float *__restrict__ grad_rec) {
+                 float *__restrict__ grad_rec) {
     constexpr uint32_t REC = grad_record(CDIM);
     constexpr int CP = ColorPad<CDIM>::value;
     // values reduced per (warp, Gaussian): [rgb(CDIM) conic(3) xy(2)] in groups of 8, then the tail
@@ -362,50 +341,39 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     const uint32_t slot8 = spread_slot<8>(lane), slot4 = spread_slot<4>(lane);
     const bool pub8 = (lane & 3) == 0, pub4 = (lane & 7) == 0;
 
-    // batches are aligned to the tile's first intersection (like the forward's) and walked back to front
-    const uint32_t chunk_base = ((uint32_t)range_start >> 5) + (uint32_t)ct;
-    const uint32_t nwarps = nthreads >> 5, warp_id = tid >> 5;
-    const int32_t n_batches = range_end > range_start ? (range_end - range_start + (int32_t)batch - 1) / (int32_t)batch : 0;
-    for (int32_t kb = n_batches - 1; kb >= 0; --kb) {
+    for (int32_t batch_end = range_end - 1; batch_end >= range_start; batch_end -= (int32_t)batch) {
         __syncthreads();
-        const int32_t bs = range_start + kb * (int32_t)batch;
-        const int32_t bsize = min((int32_t)batch, range_end - bs);
+        const int32_t bsize = min((int32_t)batch, batch_end + 1 - range_start);
 #pragma unroll
         for (int sp = 0; sp < kStagePerThread; ++sp) {
             const int32_t e = (int32_t)(tid + sp * nthreads);
             if (e < bsize) {
-                const int32_t g = flatten_ids[bs + e];
+                const int32_t g = flatten_ids[batch_end - e];
                 const float2 xy = __ldg(means2d + g);
                 const float opac = __ldg(opacities + g);
                 const float ca = __ldg(conics + (size_t)g * 3), cb = __ldg(conics + (size_t)g * 3 + 1),
                             cc = __ldg(conics + (size_t)g * 3 + 2);
-                sA[e] = make_float4(xy.x, xy.y, opac, contrib != nullptr ? 0.f : cull_qmax(ca, cb, cc, opac));
+                sA[e] = make_float4(xy.x, xy.y, opac, cull_qmax(ca, cb, cc, opac));
                 sB[e] = make_float4(ca, cb, cc, __int_as_float(g));
 #pragma unroll
                 for (int k = 0; k < CDIM; ++k) sC[e * CP + k] = __ldg(colors + (size_t)g * CDIM + k);
             }
         }
         __syncthreads();
-        if (warp_bin_final < bs) continue;  // this warp's pixels stopped before this batch
-        for (int32_t qc = (bsize + 31) / 32 - 1; qc >= 0; --qc) {
-            const int32_t c0 = qc * 32;
-            if (bs + c0 > warp_bin_final) continue;
-            unsigned m;
-            if (contrib != nullptr) {
-                m = __ldg(contrib + (size_t)(chunk_base + (uint32_t)((bs - range_start) >> 5) + (uint32_t)qc) * nwarps + warp_id);
-            } else {
-                const int32_t e = c0 + (int32_t)lane;
-                bool hit = false;
-                if (e < bsize) {
-                    const float4 A = lds4(aA + e * 16), B = lds4(aB + e * 16);
-                    hit = ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, A.w, wx0, wx1, wy0, wy1);
-                }
-                m = __ballot_sync(wmask, hit);
+        if (warp_bin_final < 0) continue;
+        // entry t <-> sorted index batch_end - t ; start at the warp's last contributing Gaussian
+        const int32_t t_first = max(0, batch_end - warp_bin_final);
+        for (int32_t c0 = t_first; c0 < bsize; c0 += 32) {
+            const int32_t e = c0 + (int32_t)lane;
+            bool hit = false;
+            if (e < bsize) {
+                const float4 A = lds4(aA + e * 16), B = lds4(aB + e * 16);
+                hit = ellipse_hits_rect(A.x, A.y, B.x, B.y, B.z, A.w, wx0, wx1, wy0, wy1);
             }
+            unsigned m = __ballot_sync(wmask, hit);
             while (m) {
-                const int32_t bit = 31 - __clz(m);  // back to front
-                m ^= 1u << bit;
-                const int32_t t = c0 + bit;
+                const int32_t t = c0 + __ffs(m) - 1;
+                m &= m - 1;
                 const float4 A = lds4(aA + t * 16);
                 const float4 B = lds4(aB + t * 16);
                 const float dx = A.x - px, dy = A.y - py;
@@ -413,7 +381,7 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                 const float sigma = 0.5f * (B.x * dx * dx + B.z * dy * dy) + B.y * dx * dy;
                 const float vis = __expf(-sigma);
                 const float alpha = fminf(kAlphaMax, opac * vis);
-                const bool valid = inside && (bs + t <= bin_final) && !(sigma < 0.f || alpha < kAlphaMin);
+                const bool valid = inside && (batch_end - t <= bin_final) && !(sigma < 0.f || alpha < kAlphaMin);
                 if (!__any_sync(wmask, valid)) continue;
                 float vals[NGRP * 8];
                 float tail[4] = {0.f, 0.f, 0.f, 0.f};
@@ -506,18 +474,16 @@ template <int CDIM>
 static int launch_fwd(const BlendGeom &G, const float *means2d, const float *conics, const float *colors,
                       const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
                       const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
-                      uint32_t *contrib, cudaStream_t s) {
+                      cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
     const uint32_t batch = nthreads * kStagePerThread;
     const size_t smem = (size_t)batch * (32 + 4 * ColorPad<CDIM>::value);
     if (smem > 48 * 1024)
         GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (contrib != nullptr)
-        GSB_CUDA_OK(cudaMemsetAsync(contrib, 0, sizeof(uint32_t) * contrib_mask_words(G.n_isects, G.C * G.tw * G.th, G.ts), s));
     dim3 grid(G.tw, G.th, G.C);
     blend_fwd_kernel<CDIM><<<grid, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
                                                          opacities, backgrounds, masks, tile_offsets, flatten_ids,
-                                                         render_colors, render_alphas, last_ids, contrib);
+                                                         render_colors, render_alphas, last_ids);
     return check_launch("blend_fwd");
 }
 
@@ -525,8 +491,7 @@ template <int CDIM>
 static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, const float *conics, const float *colors,
                       const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
                       const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
-                      const float *v_render_colors, const float *v_render_alphas, const uint32_t *contrib,
-                      float *grad_scratch, float *v_abs,
+                      const float *v_render_colors, const float *v_render_alphas, float *grad_scratch, float *v_abs,
                       float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
     const uint32_t batch = nthreads * kStagePerThread;
@@ -541,11 +506,11 @@ static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, cons
         if (v_abs != nullptr)
             blend_bwd_kernel<CDIM, true><<<grid, nthreads, smem, s>>>(
                 G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,
-                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, contrib, grad_scratch);
+                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch);
         else
             blend_bwd_kernel<CDIM, false><<<grid, nthreads, smem, s>>>(
                 G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,
-                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, contrib, grad_scratch);
+                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch);
         if (int e = check_launch("blend_bwd")) return e;
     }
     unpack_grads_kernel<CDIM><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors,
@@ -587,18 +552,14 @@ extern "C" int gsb200_rasterize_fwd(uint32_t C, uint32_t M, int64_t n_isects, ui
                                     const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_size,
                                     uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
                                     const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
-                                    uint32_t *contrib_masks, gsb200_stream_t stream) {
+                                    gsb200_stream_t stream) {
     (void)M;
     if (int e = check_geom(tile_size, W, H, tile_width, tile_height)) return e;
     if (C == 0 || W == 0 || H == 0) return 0;
     BlendGeom G{C, W, H, tile_size, tile_width, tile_height, n_isects};
     cudaStream_t s = (cudaStream_t)stream;
     GSB_DISPATCH_CDIM(D, (launch_fwd<CD>(G, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
-                                         render_colors, render_alphas, last_ids, contrib_masks, s)));
-}
-
-extern "C" uint64_t gsb200_contrib_mask_words(int64_t n_isects, uint32_t total_tiles, uint32_t tile_size) {
-    return contrib_mask_words(n_isects, total_tiles, tile_size);
+                                         render_colors, render_alphas, last_ids, s)));
 }
 
 extern "C" int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
@@ -606,14 +567,14 @@ extern "C" int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, ui
                                     const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_size,
                                     uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
                                     const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
-                                    const float *v_render_colors, const float *v_render_alphas,
-                                    const uint32_t *contrib_masks, float *grad_scratch, float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                                    const float *v_render_colors, const float *v_render_alphas, float *grad_scratch,
+                                    float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                                     gsb200_stream_t stream) {
     if (int e = check_geom(tile_size, W, H, tile_width, tile_height)) return e;
     if (M == 0) return 0;
     BlendGeom G{C, W, H, tile_size, tile_width, tile_height, n_isects};
     cudaStream_t s = (cudaStream_t)stream;
     GSB_DISPATCH_CDIM(D, (launch_bwd<CD>(G, M, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets,
-                                         flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, contrib_masks,
-                                         grad_scratch, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s)));
+                                         flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch,
+                                         v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s)));
 }

@@ -164,19 +164,14 @@ int gsb200_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, uint3
  * means2d [M,2], conics [M,3], colors [M,D], opacities [M] with M = C*N or nnz; backgrounds [C,D] or
  * NULL; masks u8 [C,th,tw] or NULL; tile_offsets i32 [C,th,tw]; flatten_ids i32 [I].
  * Outputs render_colors [C,H,W,D], render_alphas [C,H,W], last_ids i32 [C,H,W].
- * D must be in {1,2,3,4,5,8,9,16,17,32,33} (the host pads others, as _wrapper.py:496-541 does).
- * contrib_masks (optional, may be NULL): u32 [gsb200_contrib_mask_words(I, C*th*tw, tile_size)], written by
- * the forward (one word per 32-Gaussian chunk and warp: which Gaussians some pixel of the warp blended) and
- * read by the backward, which then skips every (warp, Gaussian) pair that contributed nothing without
- * re-evaluating it. */
-uint64_t gsb200_contrib_mask_words(int64_t n_isects, uint32_t total_tiles, uint32_t tile_size);
+ * D must be in {1,2,3,4,5,8,9,16,17,32,33} (the host pads others, as _wrapper.py:496-541 does). */
 int gsb200_rasterize_fwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
                          const float *conics, const float *colors, const float *opacities,
                          const float *backgrounds, const uint8_t *masks, uint32_t image_width,
                          uint32_t image_height, uint32_t tile_size, uint32_t tile_width,
                          uint32_t tile_height, const int32_t *tile_offsets,
                          const int32_t *flatten_ids, float *render_colors, float *render_alphas,
-                         int32_t *last_ids, uint32_t *contrib_masks, gsb200_stream_t stream);
+                         int32_t *last_ids, gsb200_stream_t stream);
 
 /* replaces _C.rasterize_to_pixels_bwd (bindings.h:186-215, rasterize_to_pixels_bwd.cu:17-277).
  * Gradient outputs v_means2d [M,2], v_conics [M,3], v_colors [M,D], v_opacities [M] and, if not
@@ -190,8 +185,7 @@ int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, c
                          uint32_t tile_height, const int32_t *tile_offsets,
                          const int32_t *flatten_ids, const float *render_alphas,
                          const int32_t *last_ids, const float *v_render_colors,
-                         const float *v_render_alphas, const uint32_t *contrib_masks,
-                         float *grad_scratch, float *v_means2d_abs,
+                         const float *v_render_alphas, float *grad_scratch, float *v_means2d_abs,
                          float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                          gsb200_stream_t stream);
 
