@@ -427,18 +427,24 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
             ev.synchronize()
             n_isects = int(pinned.item())
             if n_isects <= capacity:
-                _isect_capacity[key] = max(int(n_isects * 1.25) + 4096, 4096)
+                if n_isects < capacity // 2:  # shrink only on a big drop: a stable size keeps the allocator's blocks
+                    _isect_capacity[key] = _round_capacity(n_isects)
                 return tiles_per_gauss, isect_ids[:n_isects], flatten_ids[:n_isects], isect_offsets
             # overflow (scene grew by more than 25 % in one step): fall through to the exact path
         n_host = ctypes.c_int64(0)
         prepare(ctypes.byref(n_host))
         n_isects = int(n_host.value)
-        _isect_capacity[key] = max(int(n_isects * 1.25) + 4096, 4096)
+        _isect_capacity[key] = _round_capacity(n_isects)
         isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
         flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
         scratch = torch.empty(max(n_isects, 1), dtype=torch.int64, device=dev)
         fill(n_isects, isect_ids, flatten_ids, scratch)
     return tiles_per_gauss, isect_ids, flatten_ids, isect_offsets
+
+
+def _round_capacity(n: int) -> int:
+    """25 % head-room, rounded up to 256 Ki entries so that the capacity (hence the allocation size) is stable."""
+    return ((int(n * 1.25) + 4096 + (1 << 18) - 1) >> 18) << 18
 
 
 _isect_capacity = {}  # (device, C, n_elems, tile grid) -> speculative buffer capacity for the next call
