@@ -73,34 +73,50 @@ def _uneven_lists_ok() -> bool:
     return dist.get_backend() == "nccl"
 
 
+def _row_views(buf: Tensor, counts: Sequence[int], rows: Optional[int] = None, skip: int = 0) -> List[Tensor]:
+    """Per-rank row blocks of a rank-major [sum n_r, ...] buffer: rows [skip, skip+rows) of each block (all of it
+    when rows is None)."""
+    views, start = [], 0
+    for c in counts:
+        n = c - skip if rows is None else rows
+        views.append(buf[start + skip: start + skip + n])
+        start += c
+    return views
+
+
 def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool):
-    """Start the all-gather of per-rank row blocks [n_r, ...] straight into the final [sum n_r, ...] buffer."""
+    """Start the all-gather of per-rank row blocks [n_r, ...] into the final rank-major [sum n_r, ...] buffer.
+
+    Equal counts: one ncclAllGather straight into the buffer.  Ragged counts on NCCL: the first min(n_r) rows
+    of every rank go through the same-size list form (NCCL's fast all-gather plus one device copy inside
+    torch), the few remaining rows through the uneven list form (grouped broadcasts) -- no zero padding, no
+    compaction pass."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    n_max = max(counts)
+    n_max, n_min = max(counts), min(counts)
     tail = tuple(data.shape[1:])
     data = data.contiguous()
-    if all(c == n_max for c in counts):
+    if n_max == n_min:
         out = torch.empty((world * n_max,) + tail, dtype=data.dtype, device=data.device)
         work = dist.all_gather_into_tensor(out, data, async_op=async_op)
-        return out, work, False
+        return out, [work], False
     if _uneven_lists_ok():
         out = torch.empty((sum(counts),) + tail, dtype=data.dtype, device=data.device)
-        views, start = [], 0
-        for c in counts:
-            views.append(out[start:start + c])
-            start += c
-        work = dist.all_gather(views, data, async_op=async_op)
-        return out, work, False
+        works = []
+        if n_min > 0:
+            works.append(dist.all_gather(_row_views(out, counts, rows=n_min), data[:n_min], async_op=async_op))
+        works.append(dist.all_gather(_row_views(out, counts, skip=n_min), data[n_min:], async_op=async_op))
+        return out, works, False
     padded = torch.zeros((n_max,) + tail, dtype=data.dtype, device=data.device)
     padded[: counts[rank]] = data
     buf = torch.empty((world * n_max,) + tail, dtype=data.dtype, device=data.device)
     work = dist.all_gather_into_tensor(buf, padded, async_op=async_op)
-    return buf, work, True
+    return buf, [work], True
 
 
-def _gather_rows_finish(buf: Tensor, work, ragged: bool, counts: Sequence[int]) -> Tensor:
-    if work is not None:
-        work.wait()  # the current stream waits for the collective; the host does not block
+def _gather_rows_finish(buf: Tensor, works, ragged: bool, counts: Sequence[int]) -> Tensor:
+    for work in works:
+        if work is not None:
+            work.wait()  # the current stream waits for the collective; the host does not block
     if not ragged:
         return buf
     n_max = max(counts)
@@ -110,21 +126,18 @@ def _gather_rows_finish(buf: Tensor, work, ragged: bool, counts: Sequence[int]) 
 def _reduce_scatter_rows(v_out: Tensor, counts: Sequence[int]) -> Tensor:
     """Sum over ranks of [sum n_r, ...] gradients, return this rank's [n_rank, ...] block."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    n_max = max(counts)
+    n_max, n_min = max(counts), min(counts)
     tail = tuple(v_out.shape[1:])
     v_out = v_out.contiguous()
-    even = all(c == n_max for c in counts)
-    if even and _backend_supports("reduce_scatter_tensor"):
+    if n_max == n_min and _backend_supports("reduce_scatter_tensor"):
         recv = torch.empty((n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
         dist.reduce_scatter_tensor(recv, v_out, op=dist.ReduceOp.SUM)
         return recv
-    if not even and _uneven_lists_ok():
+    if n_max != n_min and _uneven_lists_ok():
         recv = torch.empty((counts[rank],) + tail, dtype=v_out.dtype, device=v_out.device)
-        views, start = [], 0
-        for c in counts:
-            views.append(v_out[start:start + c])
-            start += c
-        dist.reduce_scatter(recv, views, op=dist.ReduceOp.SUM)
+        if n_min > 0:  # same-size list form: NCCL's fast reduce-scatter
+            dist.reduce_scatter(recv[:n_min], _row_views(v_out, counts, rows=n_min), op=dist.ReduceOp.SUM)
+        dist.reduce_scatter(recv[n_min:], _row_views(v_out, counts, skip=n_min), op=dist.ReduceOp.SUM)
         return recv
     # generic fallback (gloo): all-reduce the whole gradient and keep the local rows
     total = v_out.clone()
@@ -140,7 +153,7 @@ class _FinishGather(torch.autograd.Function):
     @staticmethod
     def forward(ctx, data: Tensor, pending: "PendingGather"):
         ctx.counts = pending.counts
-        return _gather_rows_finish(pending.buf, pending.work, pending.ragged, pending.counts)
+        return _gather_rows_finish(pending.buf, pending.works, pending.ragged, pending.counts)
 
     @staticmethod
     def backward(ctx, v_out: Tensor):
@@ -154,7 +167,7 @@ class PendingGather:
 
     def __init__(self, data: Tensor, counts: Sequence[int]):
         self.data, self.counts = data, list(counts)
-        self.buf, self.work, self.ragged = _gather_rows_launch(data.detach(), self.counts, async_op=True)
+        self.buf, self.works, self.ragged = _gather_rows_launch(data.detach(), self.counts, async_op=True)
 
     def finish(self) -> Tensor:
         return _FinishGather.apply(self.data, self)
