@@ -104,7 +104,16 @@ def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool):
         works = []
         if n_min > 0:
             works.append(dist.all_gather(_row_views(out, counts, rows=n_min), data[:n_min], async_op=async_op))
-        works.append(dist.all_gather(_row_views(out, counts, skip=n_min), data[n_min:], async_op=async_op))
+        # tails (n_r - n_min rows, a handful at most for a strided split): zero-padded to a common size, gathered
+        # with the plain tensor form and copied into place
+        t_max = n_max - n_min
+        tail_in = torch.zeros((t_max,) + tail, dtype=data.dtype, device=data.device)
+        tail_in[: counts[rank] - n_min] = data[n_min:]
+        tail_out = torch.empty((world * t_max,) + tail, dtype=data.dtype, device=data.device)
+        dist.all_gather_into_tensor(tail_out, tail_in)
+        for r, view in enumerate(_row_views(out, counts, skip=n_min)):
+            if view.shape[0] > 0:
+                view.copy_(tail_out[r * t_max: r * t_max + view.shape[0]])
         return out, works, False
     padded = torch.zeros((n_max,) + tail, dtype=data.dtype, device=data.device)
     padded[: counts[rank]] = data
@@ -137,7 +146,15 @@ def _reduce_scatter_rows(v_out: Tensor, counts: Sequence[int]) -> Tensor:
         recv = torch.empty((counts[rank],) + tail, dtype=v_out.dtype, device=v_out.device)
         if n_min > 0:  # same-size list form: NCCL's fast reduce-scatter
             dist.reduce_scatter(recv[:n_min], _row_views(v_out, counts, rows=n_min), op=dist.ReduceOp.SUM)
-        dist.reduce_scatter(recv[n_min:], _row_views(v_out, counts, skip=n_min), op=dist.ReduceOp.SUM)
+        t_max = n_max - n_min  # tails: tiny, zero-padded to a common size
+        tail_in = torch.zeros((world * t_max,) + tail, dtype=v_out.dtype, device=v_out.device)
+        for r, view in enumerate(_row_views(v_out, counts, skip=n_min)):
+            if view.shape[0] > 0:
+                tail_in[r * t_max: r * t_max + view.shape[0]] = view
+        tail_out = torch.empty((t_max,) + tail, dtype=v_out.dtype, device=v_out.device)
+        dist.reduce_scatter_tensor(tail_out, tail_in, op=dist.ReduceOp.SUM)
+        if counts[rank] > n_min:
+            recv[n_min:] = tail_out[: counts[rank] - n_min]
         return recv
     # generic fallback (gloo): all-reduce the whole gradient and keep the local rows
     total = v_out.clone()
