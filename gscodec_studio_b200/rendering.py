@@ -113,18 +113,20 @@ def rasterization(
         from .distributed import gather_counts, start_gather
 
         counts = gather_counts(N, device)
-        # every gather is enqueued now; the (large) colour / SH tensor is only waited for after projection
-        # and tile intersection have been enqueued, so its transfer overlaps with those kernels
-        pend = {name: start_gather(t, counts) for name, t in
-                (("means", means), ("quats", quats), ("scales", scales), ("opacities", opacities), ("colors", colors),
-                 ("covars", covars)) if t is not None}
-        means = pend["means"].finish()
+        # two collectives each way: the geometry attributes travel as ONE [n, 11 | 10] tensor (every collective has
+        # a fixed cost), the (large) colour / SH tensor separately -- it is only waited for after projection and
+        # tile intersection have been enqueued, so its transfer overlaps with those kernels
+        geo_parts = [means] + ([quats, scales] if covars is None else [covars]) + [opacities[:, None]]
+        widths = [t.shape[1] for t in geo_parts]
+        pending_geo = start_gather(torch.cat(geo_parts, dim=1), counts)
+        pending_colors = start_gather(colors, counts)
+        geo = torch.split(pending_geo.finish(), widths, dim=1)
+        means = geo[0]
         if covars is None:
-            quats, scales = pend["quats"].finish(), pend["scales"].finish()
+            quats, scales = geo[1], geo[2]
         else:
-            covars = pend["covars"].finish()
-        opacities = pend["opacities"].finish()
-        pending_colors = pend["colors"]
+            covars = geo[1]
+        opacities = geo[-1][:, 0]
         colors = None
         N = means.shape[0]
     else:
