@@ -80,8 +80,9 @@ def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool):
     data = data.contiguous()
     ragged = any(c != n_max for c in counts)
     if ragged:
-        padded = torch.zeros((n_max,) + tail, dtype=data.dtype, device=data.device)
+        padded = torch.empty((n_max,) + tail, dtype=data.dtype, device=data.device)
         padded[: counts[rank]] = data
+        padded[counts[rank]:] = 0  # only the (few) padding rows are zero-filled
         data = padded
     buf = torch.empty((world * n_max,) + tail, dtype=data.dtype, device=data.device)
     work = dist.all_gather_into_tensor(buf, data, async_op=async_op)
@@ -111,10 +112,11 @@ def _reduce_scatter_rows(v_out: Tensor, counts: Sequence[int]) -> Tensor:
     if all(c == n_max for c in counts):
         send = v_out
     else:
-        send = torch.zeros((world * n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
+        send = torch.empty((world * n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
         start = 0
         for r in range(world):
             send[r * n_max: r * n_max + counts[r]] = v_out[start: start + counts[r]]
+            send[r * n_max + counts[r]: (r + 1) * n_max] = 0  # padding rows only
             start += counts[r]
     recv = torch.empty((n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
     dist.reduce_scatter_tensor(recv, send, op=dist.ReduceOp.SUM)
