@@ -602,9 +602,9 @@ extern "C" int gsb200_projection_fwd(uint32_t C, uint32_t N, const float *means,
                                      float *compensations, gsb200_stream_t stream) {
     if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
         return fail(2, "gsb200_projection_fwd: camera_model must be pinhole, ortho or fisheye");
+    if (C == 0 || N == 0) return 0;  // (empty tensors have NULL data pointers)
     if (covars == nullptr && (quats == nullptr || scales == nullptr))
         return fail(2, "gsb200_projection_fwd: covars or (quats, scales) should be provided");
-    if (C == 0 || N == 0) return 0;
     projection_fwd_kernel<<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip,
         camera_model, packed_radius_rule, radii, means2d, depths, conics, compensations);

@@ -686,3 +686,77 @@ def test_isect_unsorted_and_sparse_grad():
     for dense, sp in zip(outs[False], outs[True]):
         assert sp.is_sparse and sp.shape == dense.shape
         assert rel_err(sp.to_dense(), dense) < 1e-6
+
+
+# ------------------------------------------------------------------------------------- edge cases
+def test_empty_and_degenerate_inputs():
+    dev = DEV
+    vm = torch.eye(4, device=dev)[None]
+    vm[:, 2, 3] = 5.0
+    K = torch.tensor([[[50.0, 0, 32], [0, 50.0, 24], [0, 0, 1]]], device=dev)
+    # no Gaussians at all
+    z = lambda *s: torch.zeros(*s, device=dev, requires_grad=True)
+    rc, ra, meta = gs.rasterization(z(0, 3), z(0, 4), z(0, 3), z(0), z(0, 3), vm, K, 64, 48, packed=False,
+                                    backgrounds=torch.full((1, 3), 0.25, device=dev))
+    assert rc.shape == (1, 48, 64, 3) and torch.all(rc == 0.25) and torch.all(ra == 0)
+    assert meta["isect_ids"].numel() == 0 and torch.all(meta["isect_offsets"] == 0)
+    rc.sum().backward()
+    # Gaussians exist but none is visible (behind the camera)
+    means = torch.randn(100, 3, device=dev) - torch.tensor([0.0, 0.0, 50.0], device=dev)
+    attrs = [means.requires_grad_(True), torch.randn(100, 4, device=dev).requires_grad_(True),
+             (torch.rand(100, 3, device=dev) * 0.1).requires_grad_(True), torch.rand(100, device=dev).requires_grad_(True),
+             torch.rand(100, 3, device=dev).requires_grad_(True)]
+    for packed in (False, True):
+        rc, ra, meta = gs.rasterization(*attrs, vm, K, 64, 48, packed=packed)
+        assert torch.all(rc == 0) and torch.all(ra == 0) and meta["isect_ids"].numel() == 0
+        (rc.sum() + ra.sum()).backward()
+        assert all(torch.all(a.grad == 0) for a in attrs)
+    # image smaller than one tile, width/height not multiples of the tile size, single Gaussian
+    one = [torch.zeros(1, 3, device=dev), torch.tensor([[1.0, 0, 0, 0]], device=dev), torch.full((1, 3), 0.2, device=dev),
+           torch.tensor([0.9], device=dev), torch.tensor([[1.0, 0.5, 0.25]], device=dev)]
+    K2 = torch.tensor([[[20.0, 0, 5], [0, 20.0, 3.5], [0, 0, 1]]], device=dev)
+    rc, ra, _ = gs.rasterization(*one, vm, K2, 10, 7, packed=False)
+    rc_o, ra_o, _ = O.rasterization(*[t.cpu() for t in one], vm.cpu(), K2.cpu(), 10, 7)
+    assert_render_close(rc, rc_o)
+    assert_render_close(ra, ra_o)
+
+
+@pytest.mark.parametrize("tile_size", [8, 16])
+def test_per_view_colors_sh_and_tile_sizes(tile_size):
+    """colors given per camera ([C,N,D] and [C,N,K,3]) and a non-default tile size."""
+    means, quats, scales, opac, colors, viewmats, Ks, W, H = _scene(C=2, width=200, height=136)
+    sel = slice(0, None, 5)
+    means, quats, scales, opac, colors = [t[sel].contiguous() for t in (means, quats, scales, opac, colors)]
+    N = means.shape[0]
+    g = torch.Generator().manual_seed(77)
+    col_cn = torch.rand(2, N, 3, generator=g)
+    sh_cn = torch.randn(2, N, 9, 3, generator=g) * 0.3
+    for cols, deg in ((col_cn, None), (sh_cn, 2)):
+        cpu = [t.clone().requires_grad_(True) for t in (means, quats, scales, opac, cols)]
+        gpu = [t.clone().to(DEV).requires_grad_(True) for t in (means, quats, scales, opac, cols)]
+        rc_o, ra_o, _ = O.rasterization(*cpu, viewmats, Ks, W, H, sh_degree=deg, tile_size=tile_size)
+        rc_g, ra_g, _ = gs.rasterization(*gpu, viewmats.to(DEV), Ks.to(DEV), W, H, sh_degree=deg, tile_size=tile_size,
+                                         packed=False)
+        assert_render_close(rc_g, rc_o, tol=2e-4)
+        w = torch.randn(rc_o.shape, generator=g)
+        (rc_o * w).sum().backward()
+        (rc_g * w.to(DEV)).sum().backward()
+        for name, a, b in zip(("means", "quats", "scales", "opacities", "colors"), gpu, cpu):
+            assert_grad_close(a.grad, b.grad, name)
+
+
+def test_antialiased_and_depth_modes():
+    means, quats, scales, opac, colors, viewmats, Ks, W, H = _scene(C=1, width=324, height=210)
+    cpu = [t.clone().requires_grad_(True) for t in (means, quats, scales, opac, colors)]
+    gpu = [t.clone().to(DEV).requires_grad_(True) for t in (means, quats, scales, opac, colors)]
+    for mode in ("D", "ED", "RGB+D"):
+        rc_o, ra_o, _ = O.rasterization(*cpu, viewmats, Ks, W, H, render_mode=mode, rasterize_mode="antialiased")
+        rc_g, ra_g, _ = gs.rasterization(*gpu, viewmats.to(DEV), Ks.to(DEV), W, H, render_mode=mode,
+                                         rasterize_mode="antialiased", packed=False)
+        assert rc_g.shape == rc_o.shape
+        assert_render_close(rc_g, rc_o, tol=1e-3, flip_mag=0.5 if mode == "ED" else 8e-3)
+        assert_render_close(ra_g, ra_o, tol=2e-4)
+    rc_o.sum().backward()
+    rc_g.sum().backward()
+    for name, a, b in zip(("means", "quats", "scales", "opacities", "colors"), gpu, cpu):
+        assert_grad_close(a.grad, b.grad, name)
