@@ -124,7 +124,8 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                  const float *__restrict__ colors, const float *__restrict__ opacities,
                  const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
                  const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
-                 float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids) {
+                 float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids,
+                 const int32_t *__restrict__ tile_order) {
     constexpr int CP = ColorPad<CDIM>::value;
     extern __shared__ float4 smem4[];
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
@@ -135,10 +136,13 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     const uint32_t aA = (uint32_t)__cvta_generic_to_shared(sA), aB = (uint32_t)__cvta_generic_to_shared(sB),
                    aC = (uint32_t)__cvta_generic_to_shared(sC);
 
-    const uint32_t cam = blockIdx.z, tile_id = blockIdx.y * G.tw + blockIdx.x;
+    // 1-D grid; with a work order the longest tiles are scheduled first (no straggler tail at the end)
+    const uint32_t ct_lin = tile_order ? (uint32_t)tile_order[blockIdx.x] : blockIdx.x;
+    const uint32_t cam = ct_lin / (G.tw * G.th), tile_id = ct_lin % (G.tw * G.th);
+    const uint32_t tile_y = tile_id / G.tw, tile_x = tile_id % G.tw;
     uint32_t lx, ly;
     pixel_in_tile(G.ts, tid, lx, ly);
-    const uint32_t i = blockIdx.y * G.ts + ly, j = blockIdx.x * G.ts + lx;
+    const uint32_t i = tile_y * G.ts + ly, j = tile_x * G.ts + lx;
     const bool inside = ly < G.ts && i < G.H && j < G.W;
     const size_t pix = ((size_t)cam * G.H + i) * G.W + j;
     const float *bg = backgrounds ? backgrounds + (size_t)cam * CDIM : nullptr;
@@ -280,7 +284,7 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                  const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
                  const float *__restrict__ render_alphas, const int32_t *__restrict__ last_ids,
                  const float *__restrict__ v_render_colors, const float *__restrict__ v_render_alphas,
-                 float *__restrict__ grad_rec) {
+                 const int32_t *__restrict__ tile_order, float *__restrict__ grad_rec) {
     constexpr uint32_t REC = grad_record(CDIM);
     constexpr int CP = ColorPad<CDIM>::value;
     // values reduced per (warp, Gaussian): [rgb(CDIM) conic(3) xy(2)] in groups of 8, then the tail
@@ -297,12 +301,14 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     const uint32_t aA = (uint32_t)__cvta_generic_to_shared(sA), aB = (uint32_t)__cvta_generic_to_shared(sB),
                    aC = (uint32_t)__cvta_generic_to_shared(sC);
 
-    const uint32_t cam = blockIdx.z, tile_id = blockIdx.y * G.tw + blockIdx.x;
+    const uint32_t ct_lin = tile_order ? (uint32_t)tile_order[blockIdx.x] : blockIdx.x;
+    const uint32_t cam = ct_lin / (G.tw * G.th), tile_id = ct_lin % (G.tw * G.th);
+    const uint32_t tile_y = tile_id / G.tw, tile_x = tile_id % G.tw;
     const size_t ct = (size_t)cam * G.tw * G.th + tile_id;
     if (masks != nullptr && !masks[ct]) return;
     uint32_t lx, ly;
     pixel_in_tile(G.ts, tid, lx, ly);
-    const uint32_t i = blockIdx.y * G.ts + ly, j = blockIdx.x * G.ts + lx;
+    const uint32_t i = tile_y * G.ts + ly, j = tile_x * G.ts + lx;
     const bool inside = ly < G.ts && i < G.H && j < G.W;
     const size_t pix = inside ? ((size_t)cam * G.H + i) * G.W + j : 0;
     const float *bg = backgrounds ? backgrounds + (size_t)cam * CDIM : nullptr;
@@ -448,6 +454,32 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     }
 }
 
+// Work order for the blend kernels: (camera, tile) indices bucketed by floor(log2(#intersections)),
+// longest first.  One block; the order inside a bucket is irrelevant.
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(uint32_t total_tiles, int64_t n_isects, const int32_t *__restrict__ offsets, int32_t *__restrict__ order) {
+    __shared__ int s_hist[33];
+    __shared__ int s_cursor[33];
+    if (threadIdx.x < 33) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < total_tiles; t += blockDim.x) {
+        const int64_t end = t + 1 == total_tiles ? n_isects : (int64_t)offsets[t + 1];
+        const uint32_t n = (uint32_t)(end - offsets[t]);
+        atomicAdd(&s_hist[n == 0 ? 32 : __clz(n)], 1);  // clz ascending == length descending
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < 33; ++b) { s_cursor[b] = run; run += s_hist[b]; }
+    }
+    __syncthreads();
+    for (uint32_t t = threadIdx.x; t < total_tiles; t += blockDim.x) {
+        const int64_t end = t + 1 == total_tiles ? n_isects : (int64_t)offsets[t + 1];
+        const uint32_t n = (uint32_t)(end - offsets[t]);
+        order[atomicAdd(&s_cursor[n == 0 ? 32 : __clz(n)], 1)] = (int32_t)t;
+    }
+}
+
 // packed gradient records -> the reference's tensors
 template <int CDIM>
 __global__ void __launch_bounds__(kThreads)
@@ -474,16 +506,20 @@ template <int CDIM>
 static int launch_fwd(const BlendGeom &G, const float *means2d, const float *conics, const float *colors,
                       const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
                       const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
-                      cudaStream_t s) {
+                      int32_t *tile_order, cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
     const uint32_t batch = nthreads * kStagePerThread;
     const size_t smem = (size_t)batch * (32 + 4 * ColorPad<CDIM>::value);
     if (smem > 48 * 1024)
         GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(G.tw, G.th, G.C);
-    blend_fwd_kernel<CDIM><<<grid, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
-                                                         opacities, backgrounds, masks, tile_offsets, flatten_ids,
-                                                         render_colors, render_alphas, last_ids);
+    const uint32_t T = G.C * G.tw * G.th;
+    if (tile_order != nullptr) {
+        tile_order_kernel<<<1, 1024, 0, s>>>(T, G.n_isects, tile_offsets, tile_order);
+        if (int e = check_launch("tile_order")) return e;
+    }
+    blend_fwd_kernel<CDIM><<<T, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
+                                                      opacities, backgrounds, masks, tile_offsets, flatten_ids,
+                                                      render_colors, render_alphas, last_ids, tile_order);
     return check_launch("blend_fwd");
 }
 
@@ -491,7 +527,8 @@ template <int CDIM>
 static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, const float *conics, const float *colors,
                       const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
                       const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
-                      const float *v_render_colors, const float *v_render_alphas, float *grad_scratch, float *v_abs,
+                      const float *v_render_colors, const float *v_render_alphas, const int32_t *tile_order,
+                      float *grad_scratch, float *v_abs,
                       float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
     const uint32_t batch = nthreads * kStagePerThread;
@@ -502,15 +539,15 @@ static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, cons
     }
     GSB_CUDA_OK(cudaMemsetAsync(grad_scratch, 0, sizeof(float) * (size_t)M * grad_record(CDIM), s));
     if (G.n_isects > 0) {
-        dim3 grid(G.tw, G.th, G.C);
+        const uint32_t T = G.C * G.tw * G.th;
         if (v_abs != nullptr)
-            blend_bwd_kernel<CDIM, true><<<grid, nthreads, smem, s>>>(
+            blend_bwd_kernel<CDIM, true><<<T, nthreads, smem, s>>>(
                 G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,
-                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch);
+                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, grad_scratch);
         else
-            blend_bwd_kernel<CDIM, false><<<grid, nthreads, smem, s>>>(
+            blend_bwd_kernel<CDIM, false><<<T, nthreads, smem, s>>>(
                 G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,
-                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch);
+                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, grad_scratch);
         if (int e = check_launch("blend_bwd")) return e;
     }
     unpack_grads_kernel<CDIM><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors,
@@ -552,14 +589,14 @@ extern "C" int gsb200_rasterize_fwd(uint32_t C, uint32_t M, int64_t n_isects, ui
                                     const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_size,
                                     uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
                                     const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
-                                    gsb200_stream_t stream) {
+                                    int32_t *tile_order, gsb200_stream_t stream) {
     (void)M;
     if (int e = check_geom(tile_size, W, H, tile_width, tile_height)) return e;
     if (C == 0 || W == 0 || H == 0) return 0;
     BlendGeom G{C, W, H, tile_size, tile_width, tile_height, n_isects};
     cudaStream_t s = (cudaStream_t)stream;
     GSB_DISPATCH_CDIM(D, (launch_fwd<CD>(G, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
-                                         render_colors, render_alphas, last_ids, s)));
+                                         render_colors, render_alphas, last_ids, tile_order, s)));
 }
 
 extern "C" int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
@@ -567,14 +604,14 @@ extern "C" int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, ui
                                     const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_size,
                                     uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
                                     const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
-                                    const float *v_render_colors, const float *v_render_alphas, float *grad_scratch,
-                                    float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
+                                    const float *v_render_colors, const float *v_render_alphas, const int32_t *tile_order,
+                                    float *grad_scratch, float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                                     gsb200_stream_t stream) {
     if (int e = check_geom(tile_size, W, H, tile_width, tile_height)) return e;
     if (M == 0) return 0;
     BlendGeom G{C, W, H, tile_size, tile_width, tile_height, n_isects};
     cudaStream_t s = (cudaStream_t)stream;
     GSB_DISPATCH_CDIM(D, (launch_bwd<CD>(G, M, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets,
-                                         flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, grad_scratch,
-                                         v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s)));
+                                         flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order,
+                                         grad_scratch, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s)));
 }

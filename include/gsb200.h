@@ -164,14 +164,17 @@ int gsb200_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, uint3
  * means2d [M,2], conics [M,3], colors [M,D], opacities [M] with M = C*N or nnz; backgrounds [C,D] or
  * NULL; masks u8 [C,th,tw] or NULL; tile_offsets i32 [C,th,tw]; flatten_ids i32 [I].
  * Outputs render_colors [C,H,W,D], render_alphas [C,H,W], last_ids i32 [C,H,W].
- * D must be in {1,2,3,4,5,8,9,16,17,32,33} (the host pads others, as _wrapper.py:496-541 does). */
+ * D must be in {1,2,3,4,5,8,9,16,17,32,33} (the host pads others, as _wrapper.py:496-541 does).
+ * tile_order (optional, may be NULL): i32 [C*th*tw] scratch.  The forward fills it with the (camera, tile)
+ * indices sorted longest-list-first and schedules its CTAs in that order (no straggler tail); pass the same
+ * buffer to the backward. */
 int gsb200_rasterize_fwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
                          const float *conics, const float *colors, const float *opacities,
                          const float *backgrounds, const uint8_t *masks, uint32_t image_width,
                          uint32_t image_height, uint32_t tile_size, uint32_t tile_width,
                          uint32_t tile_height, const int32_t *tile_offsets,
                          const int32_t *flatten_ids, float *render_colors, float *render_alphas,
-                         int32_t *last_ids, gsb200_stream_t stream);
+                         int32_t *last_ids, int32_t *tile_order, gsb200_stream_t stream);
 
 /* replaces _C.rasterize_to_pixels_bwd (bindings.h:186-215, rasterize_to_pixels_bwd.cu:17-277).
  * Gradient outputs v_means2d [M,2], v_conics [M,3], v_colors [M,D], v_opacities [M] and, if not
@@ -185,7 +188,8 @@ int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, c
                          uint32_t tile_height, const int32_t *tile_offsets,
                          const int32_t *flatten_ids, const float *render_alphas,
                          const int32_t *last_ids, const float *v_render_colors,
-                         const float *v_render_alphas, float *grad_scratch, float *v_means2d_abs,
+                         const float *v_render_alphas, const int32_t *tile_order, float *grad_scratch,
+                         float *v_means2d_abs,
                          float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                          gsb200_stream_t stream);
 
