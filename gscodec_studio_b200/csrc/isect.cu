@@ -406,8 +406,9 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
     replica_totals_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, tile_cursor, isect_offsets);
     if (int e = check_launch("replica_totals")) return e;
     const uint32_t nb = cdiv(T, kScanTile);
-    int32_t *scratch = nullptr;
-    GSB_CUDA_OK(cudaMallocAsync((void **)&scratch, sizeof(int32_t) * (nb + 2), s));
+    // scan scratch lives at the end of the caller's tile_cursor buffer (a stream-ordered allocation here would
+    // go back to the driver after every host synchronisation -- milliseconds)
+    int32_t *scratch = tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 2;
     int e = exclusive_scan(T, isect_offsets, nullptr, scratch, s);
     int32_t total = 0;
     int32_t *total_dev = tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1;
@@ -423,7 +424,6 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
         }
         if (ce != cudaSuccess) e = fail(101, cudaGetErrorString(ce));
     }
-    cudaFreeAsync(scratch, s);
     if (e) return e;
     if (n_isects_host != nullptr) *n_isects_host = total;
     return 0;
@@ -468,11 +468,8 @@ extern "C" int gsb200_isect_emit_unsorted(uint32_t C, uint32_t n_elems, uint32_t
     cudaStream_t s = (cudaStream_t)stream;
     if (n_elems == 0) return 0;
     GSB_CUDA_OK(cudaMemcpyAsync(cum_scratch, tiles_per_gauss, sizeof(int32_t) * n_elems, cudaMemcpyDeviceToDevice, s));
-    const uint32_t nb = cdiv(n_elems, kScanTile);
-    int32_t *scratch = nullptr;
-    GSB_CUDA_OK(cudaMallocAsync((void **)&scratch, sizeof(int32_t) * (nb + 2), s));
+    int32_t *scratch = cum_scratch + n_elems;  // block sums behind the prefix array
     int e = exclusive_scan(n_elems, cum_scratch, nullptr, scratch, s);
-    cudaFreeAsync(scratch, s);
     if (e) return e;
     const uint32_t n_tiles = tile_width * tile_height;
     isect_emit_unsorted_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(

@@ -380,7 +380,7 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
     T = C * tile_width * tile_height
     tiles_per_gauss = torch.empty(radii.shape, dtype=torch.int32, device=dev)
     isect_offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
-    tile_cursor = torch.empty((_ISECT_REPLICAS + 1) * max(T, 1) + 2, dtype=torch.int32, device=dev)
+    tile_cursor = torch.empty((_ISECT_REPLICAS + 1) * max(T, 1) + 2 + max(T, 1) // 2048 + 3, dtype=torch.int32, device=dev)
     total_index = (_ISECT_REPLICAS + 1) * max(T, 1) + 1
     key = (dev.index, C, n_elems, tile_width, tile_height, tile_size)
     capacity = _isect_capacity.get(key)
@@ -403,7 +403,7 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
             n_isects = int(n_host.value)
             isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
             flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
-            cum = torch.empty(max(n_elems, 1), dtype=torch.int32, device=dev)
+            cum = torch.empty(max(n_elems, 1) + n_elems // 2048 + 3, dtype=torch.int32, device=dev)
             call("gsb200_isect_emit_unsorted", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths),
                  tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(cum), ptr(isect_ids), ptr(flatten_ids),
                  stream_ptr(dev))

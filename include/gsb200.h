@@ -132,7 +132,7 @@ int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, cons
  *      -n_isects entries, the true count is read from the device; if it exceeds the capacity the outputs
  *      are incomplete and the caller must call again with larger buffers once it knows the count
  *      (lets the host size buffers speculatively and fetch the count without idling the GPU). */
-#define GSB200_ISECT_CURSOR_SIZE(T) ((GSB200_ISECT_REPLICAS + 1) * (size_t)(T) + 2)
+#define GSB200_ISECT_CURSOR_SIZE(T) ((GSB200_ISECT_REPLICAS + 1) * (size_t)(T) + 2 + ((size_t)(T) / 2048 + 3))
 #define GSB200_ISECT_TOTAL_INDEX(T) ((GSB200_ISECT_REPLICAS + 1) * (size_t)(T) + 1)
 int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
                          const int64_t *camera_ids, const float *means2d, const int32_t *radii,
@@ -147,7 +147,7 @@ int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
                       int32_t *flatten_ids, gsb200_stream_t stream);
 /* `sort = false` form of _C.isect_tiles: keys in emission order (ascending flatten index, row-major tiles per
  * Gaussian).  Call after gsb200_isect_prepare (which gives tiles_per_gauss and the count);
- * cum_scratch: i32 [n_elems]. */
+ * cum_scratch: i32 [n_elems + n_elems / 2048 + 3]. */
 int gsb200_isect_emit_unsorted(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
                                const int64_t *camera_ids, const float *means2d, const int32_t *radii,
                                const float *depths, uint32_t tile_size, uint32_t tile_width,
