@@ -36,6 +36,9 @@ sys.path.insert(0, ROOT)
 W_IMG, H_IMG = 1920, 1080
 SH_C0 = 0.2820947917738781
 METRIC = "Mpix/s fwd+bwd @1M splats 1920x1080 w/ quant-sim"
+# dram__bytes_read.sum + dram__bytes_write.sum of blend_fwd_kernel<3> (26.24 + 2.74 MB) and blend_bwd_kernel<3,0>
+# (85.65 + 5.07 MB) per launch, from the round-1 `ncu --set full` capture (profiles/r01_kernels_ncu_full.md)
+NCU_DRAM_TRAFFIC_BYTES = int((26.24 + 2.741 + 85.65 + 5.071) * 1e6)
 
 
 def build_workload(rank: int, world: int, scene_grid: int):
@@ -283,7 +286,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4), "traffic": NCU_DRAM_TRAFFIC_BYTES if args.workload == "m2" else None,
                 "kernel": "blend fwd + bwd (gsb200_rasterize_fwd/_bwd)", "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes": {"fwd": bytes_fwd, "bwd": bytes_bwd},
                 "launch_ms": {"fwd": round(t_fwd, 4), "bwd": round(t_bwd, 4)},
