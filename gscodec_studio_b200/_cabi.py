@@ -39,6 +39,9 @@ SIGNATURES = {
     "gsb200_sh_bwd": [_U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_view_fwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_view_bwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_sh_view_fwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _P, _P, _P],
+    "gsb200_sh_view_bwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_shard_reduce_rows": [_U, _U, _U, _U, _P, _P, _P, _P],
     "gsb200_isect_prepare": [_U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_fill": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _L, _P, _P, _P, _P, _P, _P],
     "gsb200_isect_emit_unsorted": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],

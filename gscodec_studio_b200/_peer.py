@@ -1,0 +1,182 @@
+"""Peer-memory (NVLink / NVSwitch) exchange of the SH coefficient shards for view-parallel rendering.
+
+The reference moves whole attribute tensors between ranks with NCCL (gsplat/distributed.py:90-215, called from
+rendering.py:282-294 and :397-478).  For the colour stage that is 16x3 floats per Gaussian per direction -- 193 MB
+for 1 M splats -- although a view only touches the ~30 % of them it can see.  Here every rank keeps its block of
+coefficients in symmetric memory (one allocation, mapped into every peer's address space over NVLink) and
+
+  forward   sh_view_fwd_sharded PULLS the rows of visible Gaussians straight from their owners;
+  backward  sh_view_bwd_sharded PUSHES the coefficient-gradient rows of visible Gaussians into the owner's staging
+            array (slot [source rank][row]; posted NVLink stores, coalesced per row) plus a 0/1 flag per row, and
+            after a cross-rank barrier each owner runs shard_reduce_rows over its LOCAL staging: the flagged rows
+            are summed in source-rank order, so the result is reproducible.
+
+No all-gather of coefficients, no dense reduce-scatter of their gradients, and the backward kernel stops writing
+zero rows for invisible Gaussians.  torch.distributed._symmetric_memory provides the allocation, the peer pointers
+and the stream-ordered barrier; the kernels are ours (csrc/sh.cu).  Geometry (11 floats per Gaussian, needed for
+EVERY row by the projection) keeps travelling by NCCL all-gather / reduce-scatter (distributed.py).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import warnings
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from ._cabi import call, ptr, stream_ptr
+
+MAX_SHARDS = 16  # GSB200_MAX_SHARDS in include/gsb200.h
+
+_workspaces: Dict[Tuple[int, int], "PeerWorkspace"] = {}
+_unavailable: Optional[str] = None
+
+
+def _ptr_table(ptrs: Sequence[int], byte_offset: int):
+    arr = (ctypes.c_void_p * len(ptrs))(*[p + byte_offset for p in ptrs])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+class PeerWorkspace:
+    """One symmetric allocation per (device, row width), carved into
+         [ coefficient block  cap_block x row_floats ]   this rank's published rows
+         [ gradient staging   world x cap_block x row_floats ]   slot [p] is written by rank p (push)
+         [ row flags          world x cap_block (int32) ]
+    Every rank uses the same capacities, so a region sits at the same offset in every peer's buffer."""
+
+    def __init__(self, device: torch.device, row_floats: int, cap_block: int):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.row_floats, self.cap_block = row_floats, cap_block
+        n_coeff = cap_block * row_floats
+        n_stage = self.world * cap_block * row_floats
+        n_flags = self.world * cap_block
+        self.buf = symm_mem.empty(n_coeff + n_stage + n_flags, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(ptrs) == self.world and all(p % 16 == 0 for p in ptrs), ptrs
+        self.coeff = self.buf[:n_coeff].view(cap_block, row_floats)
+        self.staging = self.buf[n_coeff:n_coeff + n_stage]
+        self.flags = self.buf[n_coeff + n_stage:].view(torch.int32)
+        self._coeff_tab = _ptr_table(ptrs, 0)
+        self._stage_tab = _ptr_table(ptrs, 4 * n_coeff)
+        self._flag_tab = _ptr_table(ptrs, 4 * (n_coeff + n_stage))
+        self.version = 0      # bumped by every publish(); a backward re-publishes if its forward's rows were replaced
+        self.readers = False  # a pull kernel was launched since the last barrier: peers may still be reading
+
+    def barrier(self) -> None:
+        """Stream-ordered barrier over all ranks (a small kernel on the current stream; the host does not block)."""
+        self.hdl.barrier(channel=0)
+        self.readers = False
+
+    def publish(self, rows: Tensor) -> None:
+        if self.readers:
+            self.barrier()
+        n = rows.shape[0]
+        self.coeff[:n].copy_(rows.reshape(n, self.row_floats))
+        self.barrier()
+        self.version += 1
+
+    @property
+    def coeff_table(self):
+        return self._coeff_tab[1]
+
+    @property
+    def stage_table(self):
+        return self._stage_tab[1]
+
+    @property
+    def flag_table(self):
+        return self._flag_tab[1]
+
+
+def workspace(device: torch.device, row_floats: int, n_block: int) -> PeerWorkspace:
+    """The workspace for this device and row width, grown (collectively: every rank sees the same n_block) when a
+    block no longer fits."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), row_floats)
+    ws = _workspaces.get(key)
+    if ws is None or ws.cap_block < n_block or ws.world != dist.get_world_size():
+        if ws is not None:
+            ws.barrier()
+            _workspaces.pop(key)
+            del ws
+        cap = (int(n_block * 1.1) + 64 + 3) // 4 * 4
+        _workspaces[key] = ws = PeerWorkspace(device, row_floats, cap)
+    return ws
+
+
+def available(device: torch.device, row_floats: int, n_block: int) -> bool:
+    """True if the peer-memory path can be used: NCCL job on CUDA, <= MAX_SHARDS ranks, 16-byte rows, and a
+    symmetric allocation that works on this machine.  GSB200_PEER_EXCHANGE=0 forces the NCCL collectives."""
+    global _unavailable
+    if _unavailable is not None:
+        return False
+    if os.environ.get("GSB200_PEER_EXCHANGE", "1") == "0":
+        _unavailable = "disabled by GSB200_PEER_EXCHANGE=0"
+        return False
+    if device.type != "cuda" or dist.get_backend() != "nccl":
+        return False
+    if dist.get_world_size() > MAX_SHARDS or row_floats % 4 != 0:
+        return False
+    try:
+        workspace(device, row_floats, n_block)
+    except Exception as e:  # no P2P mapping on this machine: every rank fails alike and falls back to NCCL
+        _unavailable = f"{type(e).__name__}: {e}"
+        warnings.warn(f"peer-memory exchange unavailable ({_unavailable}); using NCCL collectives")
+        return False
+    return True
+
+
+class _ShViewSharded(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree, means, campos, coeffs_local, radii, n_block):
+        C, N, K = campos.shape[0], means.shape[0], coeffs_local.shape[1]
+        ws = workspace(means.device, K * 3, n_block)
+        colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
+        with torch.cuda.device(means.device):
+            ws.publish(coeffs_local)
+            call("gsb200_sh_view_fwd_sharded", C, N, K, sh_degree, ptr(means), ptr(campos), ws.coeff_table, ws.world, n_block,
+                 ptr(radii), ptr(colors), stream_ptr(means.device))
+        ws.readers = True
+        ctx.save_for_backward(means, campos, coeffs_local, radii)
+        ctx.sh_degree, ctx.n_block, ctx.version = sh_degree, n_block, ws.version
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, campos, coeffs_local, radii = ctx.saved_tensors
+        C, N, K = campos.shape[0], means.shape[0], coeffs_local.shape[1]
+        n_block = ctx.n_block
+        ws = workspace(means.device, K * 3, n_block)
+        v_colors = v_colors.contiguous()
+        v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+        v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
+        v_coeffs = torch.empty_like(coeffs_local)
+        with torch.cuda.device(means.device):
+            if ws.version != ctx.version:  # another forward replaced the published rows since ours
+                ws.publish(coeffs_local)
+            call("gsb200_sh_view_bwd_sharded", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ws.coeff_table, ws.world, n_block,
+                 ws.rank, ptr(radii), ptr(v_colors), ws.stage_table, ws.flag_table, ptr(v_means), ptr(v_campos),
+                 stream_ptr(means.device))
+            ws.barrier()  # every rank's pushes have landed
+            call("gsb200_shard_reduce_rows", ws.world, n_block, coeffs_local.shape[0], K * 3, ptr(ws.staging), ptr(ws.flags),
+                 ptr(v_coeffs), stream_ptr(means.device))
+            ws.barrier()  # every owner is done reducing: staging and published rows may be overwritten
+        return None, v_means, v_campos, v_coeffs, None, None
+
+
+def view_colors_from_sh_sharded(sh_degree: int, means: Tensor, campos: Tensor, coeffs_local: Tensor, radii: Tensor,
+                                n_block: int) -> Tensor:
+    """Distributed form of cuda._wrapper.view_colors_from_sh: `means` [N,3] and `radii` [C,N] cover the gathered set
+    (N = world * n_block, rank r's rows at r * n_block), `coeffs_local` [n_local,K,3] is this rank's shard."""
+    N, C = means.shape[0], campos.shape[0]
+    assert N == dist.get_world_size() * n_block, (N, n_block)
+    assert radii.shape == (C, N), radii.shape
+    assert coeffs_local.dim() == 3 and coeffs_local.shape[2] == 3 and coeffs_local.shape[0] <= n_block, coeffs_local.shape
+    assert (sh_degree + 1) ** 2 <= coeffs_local.shape[1], coeffs_local.shape
+    return _ShViewSharded.apply(sh_degree, means.float().contiguous(), campos.float().contiguous(),
+                                coeffs_local.float().contiguous(), radii.contiguous(), n_block)

@@ -16,6 +16,12 @@ inline int fail(int code, const char *msg) {
     return code;
 }
 
+template <typename... Args>
+inline int failf(int code, const char *fmt, Args... args) {
+    snprintf(g_err, sizeof(g_err), fmt, args...);
+    return code;
+}
+
 inline int check_launch(const char *what) {
     ++g_launches;
     cudaError_t e = cudaPeekAtLastError();

@@ -178,19 +178,126 @@ sh_bwd_kernel(uint32_t n, uint32_t K, const float *__restrict__ dirs, const floa
 // backward is a 193 MB reduction).  One thread owns one Gaussian and loops over the cameras: the
 // coefficient row is read once, the per-camera gradients are summed in registers and each v_coeffs row
 // is written exactly once.
+// Where the coefficient rows live.  Single GPU: one [N, K, 3] array (n_block == 0).  View-parallel multi-GPU: rank r
+// owns rows [r * n_block, (r + 1) * n_block) of the gathered set and publishes them in peer-accessible memory;
+// base[r] is rank r's block as mapped into THIS process (NVLink peer mapping), so a kernel pulls the rows it
+// needs -- only the visible ones -- straight from the owner instead of receiving an all-gathered copy.
+constexpr int kMaxShards = GSB200_MAX_SHARDS;
+struct CoeffShards {
+    const float *base[kMaxShards];
+    uint32_t n_block;
+};
+
+__device__ __forceinline__ const float *coeff_row(const CoeffShards &sh, uint32_t g, uint32_t nfl) {
+    if (sh.n_block == 0) return sh.base[0] + (size_t)g * nfl;
+    const uint32_t r = g / sh.n_block;
+    return sh.base[r] + (size_t)(g - r * sh.n_block) * nfl;
+}
+
+// Where the coefficient GRADIENT rows go.  Single GPU (rows[0] == nullptr): the dense local array v_coeffs.
+// Multi-GPU: rank `src` PUSHES the row of gathered Gaussian g into slot [src][g % n_block] of the staging array of
+// g's owner (remote stores over NVLink are posted, nobody waits on a round trip), and a 0/1 flag per row next to
+// it, so that the owner's reduction afterwards reads local memory only and skips rows nobody wrote.
+struct PushTargets {
+    float *rows[kMaxShards];     // owner o's staging array [world, n_block, nfl]
+    int32_t *flags[kMaxShards];  // owner o's flags [world, n_block]
+    uint32_t src;
+};
+
+__device__ __forceinline__ size_t push_slot(const PushTargets &t, uint32_t g, uint32_t n_block, uint32_t &owner) {
+    owner = g / n_block;
+    return (size_t)t.src * n_block + (g - owner * n_block);
+}
+
+constexpr int kCoopThreads = 128;
+
+// Cooperative row staging of the COOP kernels: a warp moves the rows of its visible Gaussians between global
+// (possibly remote) memory and shared memory with fully coalesced 16-byte accesses -- L consecutive lanes cover one
+// row, 32 / L rows per instruction -- instead of every lane walking its own row at a 4 * nfl byte stride, which
+// over NVLink fetches every 32-byte sector twice.  Row stride in shared memory is an odd number of 16-byte units,
+// so the per-lane row reads afterwards are conflict-free.
 template <int DEG>
-__global__ void __launch_bounds__(kThreads)
+struct CoopRows {
+    static constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
+    static constexpr uint32_t L = nb * 3 / 4;            // float4 per row
+    static constexpr uint32_t RPI = 32 / L;              // rows per warp-wide instruction
+    static constexpr uint32_t U = (L & 1) ? L : L + 1;   // padded row stride, in float4
+    static constexpr uint32_t kWarpFloat4 = 32 * U;
+};
+
+template <int DEG>
+__device__ __forceinline__ uint32_t coop_list_visible(bool any, uint8_t *list) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t mask = __ballot_sync(0xffffffffu, any);
+    if (any) list[__popc(mask & ((1u << lane) - 1u))] = (uint8_t)lane;
+    __syncwarp();
+    return __popc(mask);
+}
+
+template <int DEG>
+__device__ __forceinline__ void coop_pull_rows(const CoeffShards &coeffs, uint32_t g0, uint32_t nfl, uint32_t nvis,
+                                               const uint8_t *list, float4 *rows) {
+    using R = CoopRows<DEG>;
+    const uint32_t lane = threadIdx.x & 31, sub = lane / R::L, kk = lane - sub * R::L;
+#pragma unroll 4
+    for (uint32_t q0 = 0; q0 < nvis; q0 += R::RPI) {
+        const uint32_t q = q0 + sub;
+        if (sub < R::RPI && q < nvis) {
+            const uint32_t j = list[q];
+            rows[j * R::U + kk] = ldg4(coeff_row(coeffs, g0 + j, nfl) + kk * 4);
+        }
+    }
+    __syncwarp();
+}
+
+template <int DEG>
+__device__ __forceinline__ void coop_push_rows(const PushTargets &t, uint32_t g0, uint32_t n_block, uint32_t nfl, uint32_t nvis,
+                                               const uint8_t *list, const float4 *rows) {
+    using R = CoopRows<DEG>;
+    const uint32_t lane = threadIdx.x & 31, sub = lane / R::L, kk = lane - sub * R::L;
+#pragma unroll 4
+    for (uint32_t q0 = 0; q0 < nvis; q0 += R::RPI) {
+        const uint32_t q = q0 + sub;
+        if (sub < R::RPI && q < nvis) {
+            const uint32_t j = list[q];
+            uint32_t owner;
+            const size_t slot = push_slot(t, g0 + j, n_block, owner);
+            stg4(t.rows[owner] + slot * nfl + kk * 4, rows[j * R::U + kk]);
+        }
+    }
+}
+
+template <int DEG, bool COOP>
+__global__ void __launch_bounds__(COOP ? kCoopThreads : kThreads)
 sh_view_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__ means, const float *__restrict__ campos,
-                   const float *__restrict__ coeffs, const int32_t *__restrict__ radii, float *__restrict__ colors, bool vec) {
-    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
-    if (g >= N) return;
+                   const CoeffShards coeffs, const int32_t *__restrict__ radii, float *__restrict__ colors, bool vec) {
     constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!COOP && g >= N) return;
     bool any = false;
-    for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
+    if (g < N)
+        for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
     float cf[nb * 3 + 3];
     float mx = 0.f, my = 0.f, mz = 0.f;
-    if (any) {
-        const float *row = coeffs + (size_t)g * K * 3;
+    if constexpr (COOP) {
+        using R = CoopRows<DEG>;
+        __shared__ float4 s_rows[(kCoopThreads / 32) * R::kWarpFloat4];
+        __shared__ uint8_t s_list[kCoopThreads];
+        float4 *rows = s_rows + (threadIdx.x >> 5) * R::kWarpFloat4;
+        uint8_t *list = s_list + (threadIdx.x & ~31u);
+        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t nvis = coop_list_visible<DEG>(any, list);
+        coop_pull_rows<DEG>(coeffs, g - lane, K * 3, nvis, list, rows);
+        if (any) {
+#pragma unroll
+            for (uint32_t k = 0; k < R::L; ++k) {
+                const float4 v = rows[lane * R::U + k];
+                cf[4 * k] = v.x; cf[4 * k + 1] = v.y; cf[4 * k + 2] = v.z; cf[4 * k + 3] = v.w;
+            }
+        }
+        if (g >= N) return;
+    } else if (any) {
+        const float *row = coeff_row(coeffs, g, K * 3);
         if (vec) {
 #pragma unroll
             for (uint32_t k = 0; k < nb * 3; k += 4) {
@@ -201,8 +308,8 @@ sh_view_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
 #pragma unroll
             for (uint32_t k = 0; k < nb * 3; ++k) cf[k] = __ldg(row + k);
         }
-        mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
     }
+    if (any) { mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2]; }
     for (uint32_t c = 0; c < C; ++c) {
         const size_t idx = (size_t)c * N + g;
         float r = 0.f, gg = 0.f, b = 0.f;
@@ -221,13 +328,18 @@ sh_view_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
     }
 }
 
-template <int DEG>
-__global__ void __launch_bounds__(kThreads)
+template <int DEG, bool COOP>
+__global__ void __launch_bounds__(COOP ? kCoopThreads : kThreads)
 sh_view_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__ means, const float *__restrict__ campos,
-                   const float *__restrict__ coeffs, const int32_t *__restrict__ radii, const float *__restrict__ v_colors,
-                   float *__restrict__ v_coeffs, float *__restrict__ v_means, float *__restrict__ v_campos, bool vec) {
+                   const CoeffShards coeffs, const int32_t *__restrict__ radii, const float *__restrict__ v_colors,
+                   float *__restrict__ v_coeffs, const PushTargets push, float *__restrict__ v_means,
+                   float *__restrict__ v_campos, bool vec) {
     __shared__ float s_red[kThreads / 32][3];
-    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
+    using R = CoopRows<COOP ? DEG : 3>;
+    __shared__ float4 s_rows[COOP ? (kCoopThreads / 32) * R::kWarpFloat4 : 1];
+    __shared__ uint8_t s_list[COOP ? kCoopThreads : 1];
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
     constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
     const uint32_t nfl = K * 3;
     float vc[nb * 3 + 3];
@@ -239,8 +351,22 @@ sh_view_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
         for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
     float cf[nb * 3 + 3];
     float mx = 0.f, my = 0.f, mz = 0.f;
-    if (any) {
-        const float *row = coeffs + (size_t)g * K * 3;
+    float4 *rows = s_rows + (COOP ? (threadIdx.x >> 5) * R::kWarpFloat4 : 0);
+    uint8_t *list = s_list + (COOP ? (threadIdx.x & ~31u) : 0);
+    uint32_t nvis = 0;
+    if constexpr (COOP) {
+        nvis = coop_list_visible<DEG>(any, list);
+        coop_pull_rows<DEG>(coeffs, g - lane, nfl, nvis, list, rows);
+        if (any) {
+#pragma unroll
+            for (uint32_t k = 0; k < R::L; ++k) {
+                const float4 v = rows[lane * R::U + k];
+                cf[4 * k] = v.x; cf[4 * k + 1] = v.y; cf[4 * k + 2] = v.z; cf[4 * k + 3] = v.w;
+            }
+        }
+        __syncwarp();  // rows[] is reused for the gradient rows below
+    } else if (any) {
+        const float *row = coeff_row(coeffs, g, nfl);
         if (vec) {
 #pragma unroll
             for (uint32_t k = 0; k < nb * 3; k += 4) {
@@ -251,8 +377,8 @@ sh_view_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
 #pragma unroll
             for (uint32_t k = 0; k < nb * 3; ++k) cf[k] = __ldg(row + k);
         }
-        mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
     }
+    if (any) { mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2]; }
     for (uint32_t c = 0; c < C; ++c) {
         float dxv = 0.f, dyv = 0.f, dzv = 0.f;
         if (any && radii[(size_t)c * N + g] > 0) {
@@ -286,30 +412,73 @@ sh_view_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
         if (v_campos != nullptr) {  // d dirs / d campos = -1: block reduction, one atomic set per block and camera
             const float sx = warp_sum(dxv), sy = warp_sum(dyv), sz = warp_sum(dzv);
             __syncthreads();
-            if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5][0] = sx; s_red[threadIdx.x >> 5][1] = sy; s_red[threadIdx.x >> 5][2] = sz; }
+            if (lane == 0) { s_red[threadIdx.x >> 5][0] = sx; s_red[threadIdx.x >> 5][1] = sy; s_red[threadIdx.x >> 5][2] = sz; }
             __syncthreads();
             if (threadIdx.x < 3) {
                 float t = 0.f;
-#pragma unroll
-                for (int w = 0; w < kThreads / 32; ++w) t += s_red[w][threadIdx.x];
+                for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += s_red[w][threadIdx.x];
                 if (t != 0.f) atomicAdd(v_campos + c * 3 + threadIdx.x, -t);
             }
         }
     }
+    const bool pushing = push.rows[0] != nullptr;
+    if constexpr (COOP) {  // always pushing; nb * 3 == nfl
+        if (any) {
+#pragma unroll
+            for (uint32_t k = 0; k < R::L; ++k)
+                rows[lane * R::U + k] = make_float4(vc[4 * k], vc[4 * k + 1], vc[4 * k + 2], vc[4 * k + 3]);
+        }
+        __syncwarp();
+        coop_push_rows<DEG>(push, g - lane, coeffs.n_block, nfl, nvis, list, rows);
+    }
     if (g >= N) return;
-    float *vrow = v_coeffs + (size_t)g * nfl;
-    if (vec) {
+    float *vrow = nullptr;
+    if (pushing) {  // only visible rows travel; the flag tells the owner which
+        uint32_t owner;
+        const size_t slot = push_slot(push, g, coeffs.n_block, owner);
+        push.flags[owner][slot] = any ? 1 : 0;
+        if (!COOP && any) vrow = push.rows[owner] + slot * nfl;
+    } else if (v_coeffs != nullptr) {
+        vrow = v_coeffs + (size_t)g * nfl;
+    }
+    if (vrow != nullptr) {
+        if (vec) {
 #pragma unroll
-        for (uint32_t k = 0; k + 3 < nb * 3; k += 4) stg4(vrow + k, make_float4(vc[k], vc[k + 1], vc[k + 2], vc[k + 3]));
-        for (uint32_t k = nb * 3; k < nfl; k += 4) stg4(vrow + k, make_float4(0.f, 0.f, 0.f, 0.f));
-    } else {
+            for (uint32_t k = 0; k + 3 < nb * 3; k += 4) stg4(vrow + k, make_float4(vc[k], vc[k + 1], vc[k + 2], vc[k + 3]));
+            for (uint32_t k = nb * 3; k < nfl; k += 4) stg4(vrow + k, make_float4(0.f, 0.f, 0.f, 0.f));
+        } else {
 #pragma unroll
-        for (uint32_t k = 0; k < nb * 3; ++k) vrow[k] = vc[k];
-        for (uint32_t k = nb * 3; k < nfl; ++k) vrow[k] = 0.f;
+            for (uint32_t k = 0; k < nb * 3; ++k) vrow[k] = vc[k];
+            for (uint32_t k = nb * 3; k < nfl; ++k) vrow[k] = 0.f;
+        }
     }
     if (v_means != nullptr) {
         v_means[(size_t)g * 3] = vmx; v_means[(size_t)g * 3 + 1] = vmy; v_means[(size_t)g * 3 + 2] = vmz;
     }
+}
+
+// Owner-side half of the sparse reduce-scatter: sums, in source-rank order (reproducible), the rows the ranks pushed
+// into this rank's staging array [world, n_block, row] -- local memory only, rows nobody flagged are skipped.
+__global__ void __launch_bounds__(kThreads)
+shard_reduce_rows_kernel(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_vec4, const float *__restrict__ staging,
+                         const int32_t *__restrict__ flags, float *__restrict__ out) {
+    const size_t idx = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (size_t)n_rows * row_vec4) return;
+    const uint32_t i = idx / row_vec4, k = idx - (size_t)i * row_vec4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t p0 = 0; p0 < world; p0 += 4) {
+        float4 v[4];
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+            const uint32_t p = p0 + u;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < world && __ldg(flags + (size_t)p * n_block + i) != 0)
+                v[u] = ldg4(staging + (((size_t)p * n_block + i) * row_vec4 + k) * 4);
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    stg4(out + idx * 4, acc);
 }
 
 }  // namespace gsb200
@@ -362,40 +531,147 @@ static bool sh_vec_ok(uint32_t K, uint32_t degree, const void *a, const void *b)
            (((degree + 1) * (degree + 1) * 3) % 4 == 0);
 }
 
+template <int DEG, bool COOP>
+static void launch_view_fwd(cudaStream_t s, uint32_t C, uint32_t N, uint32_t K, const float *means, const float *campos,
+                            const CoeffShards &sh, const int32_t *radii, float *colors, bool vec) {
+    const uint32_t threads = COOP ? kCoopThreads : kThreads;
+    sh_view_fwd_kernel<DEG, COOP><<<cdiv(N, threads), threads, 0, s>>>(C, N, K, means, campos, sh, radii, colors, vec);
+}
+
+template <int DEG, bool COOP>
+static void launch_view_bwd(cudaStream_t s, uint32_t C, uint32_t N, uint32_t K, const float *means, const float *campos,
+                            const CoeffShards &sh, const int32_t *radii, const float *v_colors, float *v_coeffs,
+                            const PushTargets &push, float *v_means, float *v_campos, bool vec) {
+    const uint32_t threads = COOP ? kCoopThreads : kThreads;
+    sh_view_bwd_kernel<DEG, COOP><<<cdiv(N, threads), threads, 0, s>>>(C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push,
+                                                                        v_means, v_campos, vec);
+}
+
+// coop: warp-cooperative row staging (multi-GPU form, 16-byte rows, every coefficient of the row used)
+static bool coop_ok(uint32_t K, uint32_t degree, bool vec) { return vec && (degree == 1 || degree == 3) && (degree + 1) * (degree + 1) == K; }
+
+static int view_fwd(const char *who, uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
+                    const CoeffShards &sh, bool vec, bool coop, const int32_t *radii, float *colors, cudaStream_t s) {
+    if (coop && degree == 3) launch_view_fwd<3, true>(s, C, N, K, means, campos, sh, radii, colors, vec);
+    else if (coop) launch_view_fwd<1, true>(s, C, N, K, means, campos, sh, radii, colors, vec);
+    else switch (degree) {
+        case 0: launch_view_fwd<0, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
+        case 1: launch_view_fwd<1, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
+        case 2: launch_view_fwd<2, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
+        case 3: launch_view_fwd<3, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
+        default: launch_view_fwd<4, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
+    }
+    return check_launch(who);
+}
+
+static int view_bwd(const char *who, uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
+                    const CoeffShards &sh, bool vec, bool coop, const int32_t *radii, const float *v_colors, float *v_coeffs,
+                    const PushTargets &push, float *v_means, float *v_campos, cudaStream_t s) {
+    if (v_campos != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_campos, 0, sizeof(float) * 3 * C, s));
+    if (coop && degree == 3) launch_view_bwd<3, true>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec);
+    else if (coop) launch_view_bwd<1, true>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec);
+    else switch (degree) {
+        case 0: launch_view_bwd<0, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
+        case 1: launch_view_bwd<1, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
+        case 2: launch_view_bwd<2, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
+        case 3: launch_view_bwd<3, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
+        default: launch_view_bwd<4, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
+    }
+    return check_launch(who);
+}
+
+static int check_view_args(const char *who, uint32_t K, uint32_t degree) {
+    if (degree > 4) return failf(2, "%s: degree must be <= 4", who);
+    if ((degree + 1) * (degree + 1) > K) return failf(2, "%s: coeffs hold fewer than (degree+1)^2 bases", who);
+    return 0;
+}
+
+// fills the shard table from a host array of `world` device pointers; the vector path needs every block 16-byte aligned
+static int make_shards(const char *who, const float *const *shard_coeffs, uint32_t world, uint32_t n_block, uint32_t N,
+                       CoeffShards &sh, bool &aligned) {
+    if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "%s: world must be in [1, %d]", who, kMaxShards);
+    if (n_block == 0 || (uint64_t)n_block * world < N) return failf(2, "%s: world * n_block must cover N", who);
+    aligned = true;
+    for (uint32_t r = 0; r < (uint32_t)kMaxShards; ++r) {
+        sh.base[r] = r < world ? shard_coeffs[r] : nullptr;
+        if (r < world && sh.base[r] == nullptr) return failf(2, "%s: null shard pointer", who);
+        aligned = aligned && (reinterpret_cast<uintptr_t>(sh.base[r]) & 15) == 0;
+    }
+    sh.n_block = n_block;
+    return 0;
+}
+
 extern "C" int gsb200_sh_view_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
                                   const float *coeffs, const int32_t *radii, float *colors, gsb200_stream_t stream) {
-    if (degree > 4) return fail(2, "gsb200_sh_view_fwd: degree must be <= 4");
-    if ((degree + 1) * (degree + 1) > K) return fail(2, "gsb200_sh_view_fwd: coeffs hold fewer than (degree+1)^2 bases");
+    if (int rc = check_view_args("gsb200_sh_view_fwd", K, degree)) return rc;
     if (C == 0 || N == 0) return 0;
-    const bool vec = sh_vec_ok(K, degree, coeffs, nullptr);
-    cudaStream_t s = (cudaStream_t)stream;
-    const uint32_t grid = cdiv(N, kThreads);
-    switch (degree) {
-        case 0: sh_view_fwd_kernel<0><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
-        case 1: sh_view_fwd_kernel<1><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
-        case 2: sh_view_fwd_kernel<2><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
-        case 3: sh_view_fwd_kernel<3><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
-        default: sh_view_fwd_kernel<4><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, colors, vec); break;
-    }
-    return check_launch("sh_view_fwd");
+    CoeffShards sh{};
+    sh.base[0] = coeffs;
+    return view_fwd("sh_view_fwd", C, N, K, degree, means, campos, sh, sh_vec_ok(K, degree, coeffs, nullptr), false, radii, colors,
+                    (cudaStream_t)stream);
 }
 
 extern "C" int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
                                   const float *coeffs, const int32_t *radii, const float *v_colors, float *v_coeffs,
                                   float *v_means, float *v_campos, gsb200_stream_t stream) {
-    if (degree > 4) return fail(2, "gsb200_sh_view_bwd: degree must be <= 4");
-    if ((degree + 1) * (degree + 1) > K) return fail(2, "gsb200_sh_view_bwd: coeffs hold fewer than (degree+1)^2 bases");
+    if (int rc = check_view_args("gsb200_sh_view_bwd", K, degree)) return rc;
     if (C == 0 || N == 0) return 0;
-    const bool vec = sh_vec_ok(K, degree, coeffs, v_coeffs);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (v_campos != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_campos, 0, sizeof(float) * 3 * C, s));
-    const uint32_t grid = cdiv(N, kThreads);
-    switch (degree) {
-        case 0: sh_view_bwd_kernel<0><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
-        case 1: sh_view_bwd_kernel<1><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
-        case 2: sh_view_bwd_kernel<2><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
-        case 3: sh_view_bwd_kernel<3><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
-        default: sh_view_bwd_kernel<4><<<grid, kThreads, 0, s>>>(C, N, K, means, campos, coeffs, radii, v_colors, v_coeffs, v_means, v_campos, vec); break;
+    CoeffShards sh{};
+    sh.base[0] = coeffs;
+    const PushTargets none{};
+    return view_bwd("sh_view_bwd", C, N, K, degree, means, campos, sh, sh_vec_ok(K, degree, coeffs, v_coeffs), false, radii, v_colors,
+                    v_coeffs, none, v_means, v_campos, (cudaStream_t)stream);
+}
+
+extern "C" int gsb200_sh_view_fwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                                          const float *campos, const float *const *shard_coeffs, uint32_t world, uint32_t n_block,
+                                          const int32_t *radii, float *colors, gsb200_stream_t stream) {
+    if (int rc = check_view_args("gsb200_sh_view_fwd_sharded", K, degree)) return rc;
+    if (C == 0 || N == 0) return 0;
+    CoeffShards sh{};
+    bool aligned = false;
+    if (int rc = make_shards("gsb200_sh_view_fwd_sharded", shard_coeffs, world, n_block, N, sh, aligned)) return rc;
+    const bool vec = aligned && sh_vec_ok(K, degree, nullptr, nullptr);
+    return view_fwd("sh_view_fwd_sharded", C, N, K, degree, means, campos, sh, vec, coop_ok(K, degree, vec), radii, colors,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int gsb200_sh_view_bwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                                          const float *campos, const float *const *shard_coeffs, uint32_t world, uint32_t n_block,
+                                          uint32_t rank, const int32_t *radii, const float *v_colors, float *const *peer_rows,
+                                          int32_t *const *peer_flags, float *v_means, float *v_campos, gsb200_stream_t stream) {
+    const char *who = "gsb200_sh_view_bwd_sharded";
+    if (int rc = check_view_args(who, K, degree)) return rc;
+    if (peer_rows == nullptr || peer_flags == nullptr) return fail(2, "gsb200_sh_view_bwd_sharded: null peer tables");
+    if (C == 0 || N == 0) return 0;
+    CoeffShards sh{};
+    bool aligned = false;
+    if (int rc = make_shards(who, shard_coeffs, world, n_block, N, sh, aligned)) return rc;
+    if (rank >= world) return fail(2, "gsb200_sh_view_bwd_sharded: rank >= world");
+    PushTargets push{};
+    push.src = rank;
+    for (uint32_t r = 0; r < world; ++r) {
+        push.rows[r] = peer_rows[r];
+        push.flags[r] = peer_flags[r];
+        if (push.rows[r] == nullptr || push.flags[r] == nullptr) return fail(2, "gsb200_sh_view_bwd_sharded: null peer pointer");
+        aligned = aligned && (reinterpret_cast<uintptr_t>(push.rows[r]) & 15) == 0;
     }
-    return check_launch("sh_view_bwd");
+    const bool vec = aligned && sh_vec_ok(K, degree, nullptr, nullptr);
+    return view_bwd("sh_view_bwd_sharded", C, N, K, degree, means, campos, sh, vec, coop_ok(K, degree, vec), radii, v_colors, nullptr,
+                    push, v_means, v_campos, (cudaStream_t)stream);
+}
+
+extern "C" int gsb200_shard_reduce_rows(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_floats, const float *staging,
+                                        const int32_t *flags, float *out, gsb200_stream_t stream) {
+    if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "gsb200_shard_reduce_rows: world must be in [1, %d]", kMaxShards);
+    if (n_rows > n_block) return fail(2, "gsb200_shard_reduce_rows: n_rows > n_block");
+    if (row_floats % 4 != 0) return fail(2, "gsb200_shard_reduce_rows: row_floats must be a multiple of 4");
+    if (n_rows == 0) return 0;
+    if (staging == nullptr || flags == nullptr || out == nullptr || ((reinterpret_cast<uintptr_t>(staging) | reinterpret_cast<uintptr_t>(out)) & 15) != 0)
+        return fail(2, "gsb200_shard_reduce_rows: pointers must be non-null and 16-byte aligned");
+    const uint32_t row_vec4 = row_floats / 4;
+    const size_t total = (size_t)n_rows * row_vec4;
+    shard_reduce_rows_kernel<<<(uint32_t)((total + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        world, n_block, n_rows, row_vec4, staging, flags, out);
+    return check_launch("shard_reduce_rows");
 }

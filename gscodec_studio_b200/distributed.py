@@ -67,11 +67,11 @@ def all_to_all_int32(world_size: int, values: List[Union[int, Tensor]], device: 
     return list(recv.unbind())
 
 
-def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool):
-    """Start the all-gather of per-rank row blocks [n_r, ...].
+def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool, pad_row: Optional[Tensor] = None):
+    """Start the all-gather of per-rank row blocks [n_r, ...] into a [world * max(n_r), ...] buffer.
 
-    NCCL's tensor-form all-gather (one ncclAllGather, 0.33 ms for 193 MB on 8 B200s) needs equal blocks, so
-    ragged shards are zero-padded to max(n_r) rows locally and compacted after the transfer.  The list forms of
+    NCCL's tensor-form all-gather (one ncclAllGather, 0.33 ms for 193 MB on 8 B200s) needs equal blocks, so a
+    ragged shard is padded locally to max(n_r) rows (with `pad_row`, zeros by default).  The list forms of
     torch.distributed were measured and rejected: the uneven form is emulated with grouped broadcasts (~0.45 ms
     fixed cost per call on 8 GPUs), the same-size list form adds flatten copies on the NCCL stream."""
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -79,37 +79,35 @@ def _gather_rows_launch(data: Tensor, counts: Sequence[int], async_op: bool):
     tail = tuple(data.shape[1:])
     data = data.contiguous()
     ragged = any(c != n_max for c in counts)
-    if ragged:
+    if counts[rank] != n_max:
         padded = torch.empty((n_max,) + tail, dtype=data.dtype, device=data.device)
         padded[: counts[rank]] = data
-        padded[counts[rank]:] = 0  # only the (few) padding rows are zero-filled
+        padded[counts[rank]:] = 0 if pad_row is None else pad_row.to(data.dtype)
         data = padded
     buf = torch.empty((world * n_max,) + tail, dtype=data.dtype, device=data.device)
     work = dist.all_gather_into_tensor(buf, data, async_op=async_op)
     return buf, work, ragged
 
 
-def _gather_rows_finish(buf: Tensor, work, ragged: bool, counts: Sequence[int]) -> Tensor:
-    if work is not None:
-        work.wait()  # the current stream waits for the collective; the host does not block
-    if not ragged:
-        return buf
+def _compact_rows(buf: Tensor, counts: Sequence[int]) -> Tensor:
     n_max = max(counts)
     return torch.cat([buf[r * n_max: r * n_max + counts[r]] for r in range(len(counts))], dim=0)
 
 
-def _reduce_scatter_rows(v_out: Tensor, counts: Sequence[int]) -> Tensor:
-    """Sum over ranks of [sum n_r, ...] gradients, return this rank's [n_rank, ...] block."""
+def _reduce_scatter_rows(v_out: Tensor, counts: Sequence[int], padded_layout: bool) -> Tensor:
+    """Sum over ranks of the gathered-layout gradients, return this rank's [n_rank, ...] block.
+    padded_layout: v_out has world * max(n_r) rows (blocks padded), else sum(n_r) rows (rank-major, compact)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     n_max = max(counts)
     tail = tuple(v_out.shape[1:])
     v_out = v_out.contiguous()
+    even = all(c == n_max for c in counts)
     if not _backend_supports("reduce_scatter_tensor"):
         total = v_out.clone()  # gloo: all-reduce the whole gradient and keep the local rows
         dist.all_reduce(total, op=dist.ReduceOp.SUM)
-        start = sum(counts[:rank])
+        start = rank * n_max if (padded_layout or even) else sum(counts[:rank])
         return total[start:start + counts[rank]].contiguous()
-    if all(c == n_max for c in counts):
+    if padded_layout or even:
         send = v_out
     else:
         send = torch.empty((world * n_max,) + tail, dtype=v_out.dtype, device=v_out.device)
@@ -129,22 +127,30 @@ class _FinishGather(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, data: Tensor, pending: "PendingGather"):
-        ctx.counts = pending.counts
-        return _gather_rows_finish(pending.buf, pending.work, pending.ragged, pending.counts)
+        ctx.counts, ctx.keep_padding = pending.counts, pending.keep_padding
+        if pending.work is not None:
+            pending.work.wait()  # the current stream waits for the collective; the host does not block
+        if pending.ragged and not pending.keep_padding:
+            return _compact_rows(pending.buf, pending.counts)
+        return pending.buf
 
     @staticmethod
     def backward(ctx, v_out: Tensor):
-        return _reduce_scatter_rows(v_out, ctx.counts), None
+        return _reduce_scatter_rows(v_out, ctx.counts, ctx.keep_padding), None
 
 
 class PendingGather:
     """An all-gather in flight.  `start_gather(t, counts)` enqueues it on NCCL's stream right away, `.finish()`
     returns the gathered, differentiable tensor and makes the current stream wait for it -- kernels enqueued
-    between the two calls overlap with the transfer."""
+    between the two calls overlap with the transfer.
 
-    def __init__(self, data: Tensor, counts: Sequence[int]):
-        self.data, self.counts = data, list(counts)
-        self.buf, self.work, self.ragged = _gather_rows_launch(data.detach(), self.counts, async_op=True)
+    keep_padding=False: result has sum(n_r) rows in rank-major order (ragged shards cost a compaction copy each
+    way).  keep_padding=True: result has world * max(n_r) rows, rank r's rows start at r * max(n_r) and the
+    (at most world - 1) padding rows hold `pad_row`; no copies besides the local pad."""
+
+    def __init__(self, data: Tensor, counts: Sequence[int], keep_padding: bool = False, pad_row: Optional[Tensor] = None):
+        self.data, self.counts, self.keep_padding = data, list(counts), keep_padding
+        self.buf, self.work, self.ragged = _gather_rows_launch(data.detach(), self.counts, True, pad_row)
 
     def finish(self) -> Tensor:
         return _FinishGather.apply(self.data, self)
@@ -172,8 +178,9 @@ def gather_counts(n: int, device=None) -> List[int]:
     return [int(t.item()) for t in out]
 
 
-def start_gather(t: Tensor, counts: Sequence[int]) -> PendingGather:
-    return PendingGather(t, counts)
+def start_gather(t: Tensor, counts: Sequence[int], keep_padding: bool = False,
+                 pad_row: Optional[Tensor] = None) -> PendingGather:
+    return PendingGather(t, counts, keep_padding, pad_row)
 
 
 def all_gather_attributes(tensor_list: List[Tensor], counts: Optional[List[int]] = None) -> List[Tensor]:

@@ -36,6 +36,22 @@ def _camera_positions(viewmats: Tensor) -> Tensor:
     return -(R.transpose(1, 2) @ t[..., None])[..., 0]
 
 
+_inert_rows: Dict = {}
+
+
+def _inert_row(widths: Tuple[int, ...], has_quats: bool, device) -> Tensor:
+    """Attribute row of an inert padding splat: NaN mean (culled by the projection), identity quaternion, zero
+    scale and opacity.  Cached per device: building it costs a synchronising pageable H2D copy."""
+    key = (widths, has_quats, str(device))
+    row = _inert_rows.get(key)
+    if row is None:
+        vals = [float("nan")] * 3 + [0.0] * (sum(widths) - 3)
+        if has_quats:
+            vals[3] = 1.0
+        _inert_rows[key] = row = torch.tensor(vals, dtype=torch.float32, device=device)
+    return row
+
+
 def rasterization(
     means: Tensor,  # [N, 3]
     quats: Tensor,  # [N, 4]
@@ -116,10 +132,22 @@ def rasterization(
         # two collectives each way: the geometry attributes travel as ONE [n, 11 | 10] tensor (every collective has
         # a fixed cost), the (large) colour / SH tensor separately -- it is only waited for after projection and
         # tile intersection have been enqueued, so its transfer overlaps with those kernels
+        # Ragged shards are padded to a common length with INERT splats (NaN mean: culled by the projection, so
+        # they never reach a tile, get zero gradients, and cost no compaction pass); the gathered set then has
+        # world * max(N_r) rows, i.e. up to world - 1 more than sum(N_r).
         geo_parts = [means] + ([quats, scales] if covars is None else [covars]) + [opacities[:, None]]
         widths = [t.shape[1] for t in geo_parts]
-        pending_geo = start_gather(torch.cat(geo_parts, dim=1), counts)
-        pending_colors = start_gather(colors, counts)
+        pad_row = _inert_row(tuple(widths), covars is None, device)
+        pending_geo = start_gather(torch.cat(geo_parts, dim=1), counts, keep_padding=True, pad_row=pad_row)
+        # SH coefficients (the bulk of the bytes) are not gathered at all when the peer-memory path is usable: the
+        # colour kernels pull the visible rows from their owners over NVLink (_peer.py)
+        from . import _peer
+
+        n_block = max(counts)
+        pull_colors = (sh_degree is not None and not packed and colors.dim() == 3
+                       and _peer.available(device, colors.shape[1] * 3, n_block))
+        colors_local = colors
+        pending_colors = None if pull_colors else start_gather(colors, counts, keep_padding=True)
         geo = torch.split(pending_geo.finish(), widths, dim=1)
         means = geo[0]
         if covars is None:
@@ -130,7 +158,7 @@ def rasterization(
         colors = None
         N = means.shape[0]
     else:
-        pending_colors = None
+        pending_colors, pull_colors = None, False
 
     proj_results = fully_fused_projection(
         means, covars, quats, scales, viewmats, Ks, width, height,
@@ -170,7 +198,9 @@ def rasterization(
             colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
     else:
         campos = _camera_positions(viewmats) if rigid_viewmats else torch.inverse(viewmats)[:, :3, 3]
-        if not packed and colors.dim() == 3:
+        if pull_colors:
+            colors = _peer.view_colors_from_sh_sharded(sh_degree, means, campos, colors_local, radii, n_block)
+        elif not packed and colors.dim() == 3:
             # dense layout, per-Gaussian coefficients: one fused kernel (dirs, SH, +0.5, clamp)
             colors = view_colors_from_sh(sh_degree, means, campos, colors, radii)
         elif packed:

@@ -116,6 +116,32 @@ int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, cons
                        const float *v_colors, float *v_coeffs, float *v_means, float *v_campos,
                        gsb200_stream_t stream);
 
+/* View-parallel multi-GPU form of the same stage.  The reference all-gathers / all-to-alls whole attribute
+ * tensors between ranks around these ops (rendering.py:282-294, 397-478; distributed.py:90-215).  Here the SH
+ * coefficients -- 16x3 floats per Gaussian, the bulk of the exchange -- stay on their owner: rank r publishes
+ * its block in peer-accessible (NVLink-mapped) memory and the kernels PULL the rows of visible Gaussians only.
+ *   shard_coeffs : HOST array of `world` device pointers; shard_coeffs[r] = rank r's [n_block, K, 3] block as
+ *                  mapped into this process.  Gathered row g lives at shard_coeffs[g / n_block][g % n_block].
+ *   N            : rows of the gathered set, N <= world * n_block.
+ * The backward PUSHES: rank `rank` stores the coefficient-gradient row of every visible gathered Gaussian g into
+ * slot [rank][g % n_block] of the staging array of g's owner, and a 0/1 flag for EVERY row next to it:
+ *   peer_rows[o]  : owner o's staging array [world, n_block, K*3] as mapped into this process (HOST array of ptrs)
+ *   peer_flags[o] : owner o's flags [world, n_block] (int32)
+ * gsb200_shard_reduce_rows is the owner-side half of the reduce-scatter, on LOCAL memory:
+ *   out[i] = sum over source ranks p (in rank order) of staging[p][i] where flags[p][i] != 0,  i < n_rows.
+ * The caller orders the phases across ranks (publish -> barrier -> pull; push -> barrier -> reduce -> barrier). */
+#define GSB200_MAX_SHARDS 16
+int gsb200_sh_view_fwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                               const float *campos, const float *const *shard_coeffs, uint32_t world,
+                               uint32_t n_block, const int32_t *radii, float *colors, gsb200_stream_t stream);
+int gsb200_sh_view_bwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                               const float *campos, const float *const *shard_coeffs, uint32_t world,
+                               uint32_t n_block, uint32_t rank, const int32_t *radii, const float *v_colors,
+                               float *const *peer_rows, int32_t *const *peer_flags, float *v_means,
+                               float *v_campos, gsb200_stream_t stream);
+int gsb200_shard_reduce_rows(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_floats,
+                             const float *staging, const int32_t *flags, float *out, gsb200_stream_t stream);
+
 /* ---------------------------------------------------------------- stage 2: tile intersection
  * replaces _C.isect_tiles + _C.isect_offset_encode (bindings.h:147-166, isect_tiles.cu:16-389) with
  * a per-tile design: count -> tile histogram -> scan -> bucket scatter -> per-tile sort on

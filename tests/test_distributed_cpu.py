@@ -50,6 +50,18 @@ def _worker(rank, world, port, out):
         rows = w[:2] if rank == 0 else w[2:]
         assert torch.equal(means.grad, (rows * 3)[:, None].expand(-1, 3))
         assert torch.equal(opac.grad, rows * 2)
+        # padded layout used by rasterization(distributed=True): world * max(n_r) rows, inert padding rows
+        from gscodec_studio_b200.distributed import gather_counts, start_gather
+        geo = (torch.arange(n * 4, dtype=torch.float32).reshape(n, 4) + 100 * rank).requires_grad_(True)
+        pad = torch.tensor([float("nan"), 1.0, 0.0, 0.0])
+        gg = start_gather(geo, gather_counts(n, dev), keep_padding=True, pad_row=pad).finish()
+        assert gg.shape == (6, 4)
+        assert torch.equal(gg[3:], torch.arange(12, dtype=torch.float32).reshape(3, 4) + 100)
+        assert torch.isnan(gg[2, 0]) and torch.equal(gg[2, 1:], pad[1:]) and torch.equal(gg[:2], geo.detach() if rank == 0 else gg[:2])
+        w6 = torch.arange(6, dtype=torch.float32)
+        (gg.nan_to_num(0.0) * w6[:, None]).sum().backward()
+        rows = w6[:2] if rank == 0 else w6[3:]
+        assert torch.equal(geo.grad, (rows * 2)[:, None].expand(-1, 4))
         # all-to-all with variable splits, differentiable
         t = torch.arange(4, dtype=torch.float32)[:, None].repeat(1, 2) + 10 * rank
         t.requires_grad_(True)

@@ -760,3 +760,75 @@ def test_antialiased_and_depth_modes():
     rc_g.sum().backward()
     for name, a, b in zip(("means", "quats", "scales", "opacities", "colors"), gpu, cpu):
         assert_grad_close(a.grad, b.grad, name)
+
+
+@pytest.mark.parametrize("world,deg", [(2, 3), (3, 3), (5, 3), (2, 1), (3, 2)])
+def test_sharded_view_colors_and_row_reduce_single_process(world, deg):
+    """The multi-GPU colour kernels (pull visible SH rows from owner blocks; push gradient rows + flags into the
+    owners' staging; owner-side row reduce) driven from ONE process: the `peer` blocks are separate allocations on
+    this GPU, so the indexing, the visible-only traffic and the rank-ordered sum are checked against the
+    single-array kernels bit for bit."""
+    import ctypes
+
+    from gscodec_studio_b200._cabi import call, ptr, stream_ptr
+    from gscodec_studio_b200.cuda._wrapper import view_colors_from_sh
+
+    g = torch.Generator().manual_seed(77 + world)
+    K, C = {3: 16, 1: 4, 2: 16}[deg], 2  # (3,16) and (1,4) take the warp-cooperative kernels, (2,16) the per-thread ones
+    counts = [1000 - 7 * r for r in range(world)]
+    n_block = max(counts) + 4
+    N = world * n_block
+    means = torch.randn(N, 3, generator=g).to(DEV)
+    campos = (torch.randn(C, 3, generator=g) * 3).to(DEV)
+    radii = ((torch.rand(C, N, generator=g) > 0.6).int() * 4).to(DEV)
+    blocks = [(torch.randn(n_block, K, 3, generator=g) * 0.7).to(DEV) for _ in range(world)]
+    for r in range(world):  # padding rows of every block are never visible
+        radii[:, r * n_block + counts[r]:(r + 1) * n_block] = 0
+    full = torch.cat(blocks, 0).requires_grad_(True)
+    means_ref = means.clone().requires_grad_(True)
+    ref = view_colors_from_sh(deg, means_ref, campos, full, radii)
+    w = torch.randn(C, N, 3, generator=g).to(DEV)
+    (ref * w).sum().backward()
+
+    def table(tensors):
+        arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+    coeff_tab = table(blocks)
+    colors = torch.empty(C, N, 3, device=DEV)
+    call("gsb200_sh_view_fwd_sharded", C, N, K, deg, ptr(means), ptr(campos), coeff_tab[1], world, n_block, ptr(radii),
+         ptr(colors), stream_ptr(DEV))
+    assert torch.equal(colors, ref.detach())
+
+    # every fake rank `p` renders its own weights and PUSHES rows + flags into the owners' staging arrays (slot p)
+    stagings = [torch.full((world, n_block, K, 3), float("nan"), device=DEV) for _ in range(world)]
+    flags = [torch.full((world, n_block), -1, dtype=torch.int32, device=DEV) for _ in range(world)]
+    st_tab, fl_tab = table(stagings), table(flags)
+    dense = []
+    for p in range(world):
+        wp = (w * (p + 1)).contiguous()
+        vis = radii.clone()
+        vis[:, p::world] = 0  # a different visible set per rank
+        v_means = torch.empty(N, 3, device=DEV)
+        call("gsb200_sh_view_bwd_sharded", C, N, K, deg, ptr(means), ptr(campos), coeff_tab[1], world, n_block, p, ptr(vis),
+             ptr(wp), st_tab[1], fl_tab[1], ptr(v_means), None, stream_ptr(DEV))
+        f2 = full.detach().clone().requires_grad_(True)
+        m2 = means.clone().requires_grad_(True)
+        (view_colors_from_sh(deg, m2, campos, f2, vis) * wp).sum().backward()
+        any_vis = (vis > 0).any(0)
+        pushed_flags = torch.cat([flags[o][p] for o in range(world)])
+        pushed_rows = torch.cat([stagings[o][p] for o in range(world)])
+        assert torch.equal(pushed_flags, any_vis.int())
+        assert torch.equal(pushed_rows[any_vis], f2.grad[any_vis]) and torch.isnan(pushed_rows[~any_vis]).all()
+        assert torch.equal(v_means, m2.grad)
+        dense.append(f2.grad)
+    for r in range(world):
+        out = torch.empty(counts[r], K, 3, device=DEV)
+        call("gsb200_shard_reduce_rows", world, n_block, counts[r], K * 3, ptr(stagings[r]), ptr(flags[r]), ptr(out),
+             stream_ptr(DEV))
+        expect = torch.zeros_like(out)
+        for p in range(world):  # same (rank) order as the kernel: bit-exact
+            expect = expect + dense[p][r * n_block: r * n_block + counts[r]]
+        assert torch.equal(out, expect)
+    with pytest.raises(RuntimeError):
+        call("gsb200_shard_reduce_rows", 17, n_block, 1, K * 3, ptr(stagings[0]), ptr(flags[0]), ptr(out), stream_ptr(DEV))

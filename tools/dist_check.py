@@ -23,10 +23,23 @@ def main():
     vm, K = viewmats[cam:cam + 1], Ks[cam:cam + 1]
     # the gathered set is the rank-major concatenation of the strided shards: render that order locally too, so
     # that exact depth ties (duplicate points of the garden cloud) are broken identically in both runs
-    full = [torch.cat([t[r::world] for r in range(world)], 0).clone().requires_grad_(True)
-            for t in (means, quats, scales, opac, colors)]
     counts = [means[r::world].shape[0] for r in range(world)]
-    lo = sum(counts[:rank])
+    n_max = max(counts)
+
+    def padded_full(t, pad):
+        blocks = []
+        for r in range(world):
+            blk = t[r::world]
+            if blk.shape[0] < n_max:
+                fill = torch.full((n_max - blk.shape[0],) + tuple(blk.shape[1:]), pad, device=dev, dtype=blk.dtype)
+                blk = torch.cat([blk, fill], 0)
+            blocks.append(blk)
+        return torch.cat(blocks, 0).clone().requires_grad_(True)
+
+    # the gathered set: rank-major blocks padded to max(N_r) rows with inert splats (NaN mean)
+    full = [padded_full(means, float("nan")), padded_full(quats, 0.0), padded_full(scales, 0.0), padded_full(opac, 0.0),
+            padded_full(colors, 0.0)]
+    lo = rank * n_max
     rc_f, ra_f, _ = gs.rasterization(*full, vm, K, W, H, packed=False)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     w = torch.randn(rc_f.shape, generator=g).to(dev)
