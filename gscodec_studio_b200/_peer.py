@@ -40,9 +40,13 @@ def _ptr_table(ptrs: Sequence[int], byte_offset: int):
     return arr, ctypes.cast(arr, ctypes.c_void_p)
 
 
+GEO_WIDTH = 12  # floats reserved per row of the geometry block (means 3 + quats 4 + scales 3 + opacity 1, or covars)
+
+
 class PeerWorkspace:
     """One symmetric allocation per (device, row width), carved into
-         [ coefficient block  cap_block x row_floats ]   this rank's published rows
+         [ coefficient block  cap_block x row_floats ]   this rank's published SH rows
+         [ geometry block     cap_block x GEO_WIDTH ]    this rank's published geometry rows (packed [n_block, w])
          [ gradient staging   world x cap_block x row_floats ]   slot [p] is written by rank p (push)
          [ row flags          world x cap_block (int32) ]
     Every rank uses the same capacities, so a region sits at the same offset in every peer's buffer."""
@@ -53,18 +57,22 @@ class PeerWorkspace:
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.row_floats, self.cap_block = row_floats, cap_block
         n_coeff = cap_block * row_floats
+        n_geo = cap_block * GEO_WIDTH
         n_stage = self.world * cap_block * row_floats
         n_flags = self.world * cap_block
-        self.buf = symm_mem.empty(n_coeff + n_stage + n_flags, dtype=torch.float32, device=device)
+        self.buf = symm_mem.empty(n_coeff + n_geo + n_stage + n_flags, dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(ptrs) == self.world and all(p % 16 == 0 for p in ptrs), ptrs
-        self.coeff = self.buf[:n_coeff].view(cap_block, row_floats)
-        self.staging = self.buf[n_coeff:n_coeff + n_stage]
-        self.flags = self.buf[n_coeff + n_stage:].view(torch.int32)
+        o_geo, o_stage, o_flags = n_coeff, n_coeff + n_geo, n_coeff + n_geo + n_stage
+        self.coeff = self.buf[:o_geo].view(cap_block, row_floats)
+        self.geo = self.buf[o_geo:o_stage]
+        self.staging = self.buf[o_stage:o_flags]
+        self.flags = self.buf[o_flags:].view(torch.int32)
         self._coeff_tab = _ptr_table(ptrs, 0)
-        self._stage_tab = _ptr_table(ptrs, 4 * n_coeff)
-        self._flag_tab = _ptr_table(ptrs, 4 * (n_coeff + n_stage))
+        self._geo_tab = _ptr_table(ptrs, 4 * o_geo)
+        self._stage_tab = _ptr_table(ptrs, 4 * o_stage)
+        self._flag_tab = _ptr_table(ptrs, 4 * o_flags)
         self.version = 0      # bumped by every publish(); a backward re-publishes if its forward's rows were replaced
         self.readers = False  # a pull kernel was launched since the last barrier: peers may still be reading
 
@@ -73,25 +81,28 @@ class PeerWorkspace:
         self.hdl.barrier(channel=0)
         self.readers = False
 
-    def publish(self, rows: Tensor) -> None:
+    def publish(self, coeff_rows: Tensor, geo_parts: Optional[Sequence[Tensor]] = None, pad_row: Optional[Tensor] = None,
+                n_block: int = 0) -> int:
+        """Copy this rank's rows into the symmetric buffer and make them visible to every peer (ONE barrier for
+        both blocks).  Returns the version number of what is now published."""
         if self.readers:
             self.barrier()
-        n = rows.shape[0]
-        self.coeff[:n].copy_(rows.reshape(n, self.row_floats))
+        n = coeff_rows.shape[0]
+        self.coeff[:n].copy_(coeff_rows.reshape(n, self.row_floats))
+        if geo_parts is not None:
+            w = sum(t.shape[1] for t in geo_parts)
+            block = self.geo[: n_block * w].view(n_block, w)
+            torch.cat(list(geo_parts), dim=1, out=block[:n])
+            if n < n_block:
+                block[n:] = pad_row  # inert splats
         self.barrier()
         self.version += 1
+        return self.version
 
-    @property
-    def coeff_table(self):
-        return self._coeff_tab[1]
-
-    @property
-    def stage_table(self):
-        return self._stage_tab[1]
-
-    @property
-    def flag_table(self):
-        return self._flag_tab[1]
+    coeff_table = property(lambda self: self._coeff_tab[1])
+    geo_table = property(lambda self: self._geo_tab[1])
+    stage_table = property(lambda self: self._stage_tab[1])
+    flag_table = property(lambda self: self._flag_tab[1])
 
 
 def workspace(device: torch.device, row_floats: int, n_block: int) -> PeerWorkspace:
@@ -133,12 +144,13 @@ def available(device: torch.device, row_floats: int, n_block: int) -> bool:
 
 class _ShViewSharded(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, sh_degree, means, campos, coeffs_local, radii, n_block):
+    def forward(ctx, sh_degree, means, campos, coeffs_local, radii, n_block, published):
         C, N, K = campos.shape[0], means.shape[0], coeffs_local.shape[1]
         ws = workspace(means.device, K * 3, n_block)
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
         with torch.cuda.device(means.device):
-            ws.publish(coeffs_local)
+            if published is None or published != ws.version:
+                ws.publish(coeffs_local)
             call("gsb200_sh_view_fwd_sharded", C, N, K, sh_degree, ptr(means), ptr(campos), ws.coeff_table, ws.world, n_block,
                  ptr(radii), ptr(colors), stream_ptr(means.device))
         ws.readers = True
@@ -166,17 +178,54 @@ class _ShViewSharded(torch.autograd.Function):
             call("gsb200_shard_reduce_rows", ws.world, n_block, coeffs_local.shape[0], K * 3, ptr(ws.staging), ptr(ws.flags),
                  ptr(v_coeffs), stream_ptr(means.device))
             ws.barrier()  # every owner is done reducing: staging and published rows may be overwritten
-        return None, v_means, v_campos, v_coeffs, None, None
+        return None, v_means, v_campos, v_coeffs, None, None, None
+
+
+class _GatherGeometry(torch.autograd.Function):
+    """Gathered geometry [world * n_block, w] from the published blocks (pull kernel); the backward is the NCCL
+    reduce-scatter of the (dense) geometry gradients to their owners."""
+
+    @staticmethod
+    def forward(ctx, ws, n_block, *geo_parts):
+        w = sum(t.shape[1] for t in geo_parts)
+        dev = geo_parts[0].device
+        out = torch.empty((ws.world * n_block, w), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("gsb200_shard_gather_rows", ws.world, n_block * w, ws.geo_table, ptr(out), stream_ptr(dev))
+        ws.readers = True
+        ctx.n_block, ctx.n_local, ctx.widths = n_block, geo_parts[0].shape[0], [t.shape[1] for t in geo_parts]
+        return out
+
+    @staticmethod
+    def backward(ctx, v_out):
+        v_out = v_out.contiguous()
+        recv = torch.empty((ctx.n_block, v_out.shape[1]), dtype=v_out.dtype, device=v_out.device)
+        dist.reduce_scatter_tensor(recv, v_out, op=dist.ReduceOp.SUM)
+        return (None, None) + tuple(torch.split(recv[: ctx.n_local], ctx.widths, dim=1))
+
+
+def publish_and_gather_geometry(geo_parts: Sequence[Tensor], pad_row: Tensor, coeffs_local: Tensor, n_block: int):
+    """Start of a distributed render: publish this rank's geometry rows and SH rows (one barrier), pull everybody's
+    geometry.  Returns (gathered geometry [world * n_block, w] -- differentiable w.r.t. geo_parts --, version token to
+    hand to view_colors_from_sh_sharded).  n_block must be a multiple of 4 and >= every rank's row count."""
+    assert n_block % 4 == 0, n_block
+    dev = coeffs_local.device
+    ws = workspace(dev, coeffs_local.shape[1] * 3, n_block)
+    parts = [t.detach().float() for t in geo_parts]
+    with torch.cuda.device(dev):
+        version = ws.publish(coeffs_local.detach().float(), parts, pad_row, n_block)
+    return _GatherGeometry.apply(ws, n_block, *[t.float() for t in geo_parts]), version
 
 
 def view_colors_from_sh_sharded(sh_degree: int, means: Tensor, campos: Tensor, coeffs_local: Tensor, radii: Tensor,
-                                n_block: int) -> Tensor:
+                                n_block: int, published: Optional[int] = None) -> Tensor:
     """Distributed form of cuda._wrapper.view_colors_from_sh: `means` [N,3] and `radii` [C,N] cover the gathered set
-    (N = world * n_block, rank r's rows at r * n_block), `coeffs_local` [n_local,K,3] is this rank's shard."""
+    (N = world * n_block, rank r's rows at r * n_block), `coeffs_local` [n_local,K,3] is this rank's shard;
+    `published`: version token if the rows were already published by publish_and_gather_geometry."""
     N, C = means.shape[0], campos.shape[0]
     assert N == dist.get_world_size() * n_block, (N, n_block)
     assert radii.shape == (C, N), radii.shape
     assert coeffs_local.dim() == 3 and coeffs_local.shape[2] == 3 and coeffs_local.shape[0] <= n_block, coeffs_local.shape
     assert (sh_degree + 1) ** 2 <= coeffs_local.shape[1], coeffs_local.shape
     return _ShViewSharded.apply(sh_degree, means.float().contiguous(), campos.float().contiguous(),
-                                coeffs_local.float().contiguous(), radii.contiguous(), n_block)
+                                coeffs_local.float().contiguous(), radii.contiguous(), n_block, published)

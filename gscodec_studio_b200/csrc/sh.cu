@@ -481,6 +481,26 @@ shard_reduce_rows_kernel(uint32_t world, uint32_t n_block, uint32_t n_rows, uint
     stg4(out + idx * 4, acc);
 }
 
+// All-gather by pull: every rank copies the published block of every peer (NVLink peer mappings) into its own
+// gathered array.  One launch, 64 bytes in flight per thread, no staging copies, no protocol overhead.
+struct BlockShards {
+    const float *base[kMaxShards];
+};
+
+__global__ void __launch_bounds__(kThreads)
+shard_gather_rows_kernel(uint64_t block_vec4, const BlockShards blocks, float *__restrict__ out) {
+    const float *src = blocks.base[blockIdx.y];
+    float *dst = out + (size_t)blockIdx.y * block_vec4 * 4;
+    const uint64_t i0 = ((uint64_t)blockIdx.x * kThreads) * 4 + threadIdx.x;
+    float4 v[4];
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u)
+        if (i0 + u * kThreads < block_vec4) v[u] = ldg4(src + (i0 + u * kThreads) * 4);
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u)
+        if (i0 + u * kThreads < block_vec4) stg4(dst + (i0 + u * kThreads) * 4, v[u]);
+}
+
 }  // namespace gsb200
 
 using namespace gsb200;
@@ -674,4 +694,22 @@ extern "C" int gsb200_shard_reduce_rows(uint32_t world, uint32_t n_block, uint32
     shard_reduce_rows_kernel<<<(uint32_t)((total + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         world, n_block, n_rows, row_vec4, staging, flags, out);
     return check_launch("shard_reduce_rows");
+}
+
+extern "C" int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float *const *blocks, float *out,
+                                        gsb200_stream_t stream) {
+    if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "gsb200_shard_gather_rows: world must be in [1, %d]", kMaxShards);
+    if (block_floats % 4 != 0) return fail(2, "gsb200_shard_gather_rows: block_floats must be a multiple of 4");
+    if (block_floats == 0) return 0;
+    BlockShards sh{};
+    for (uint32_t r = 0; r < world; ++r) {
+        sh.base[r] = blocks[r];
+        if (sh.base[r] == nullptr || (reinterpret_cast<uintptr_t>(sh.base[r]) & 15) != 0)
+            return fail(2, "gsb200_shard_gather_rows: block pointers must be non-null and 16-byte aligned");
+    }
+    if (out == nullptr || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return fail(2, "gsb200_shard_gather_rows: out must be 16-byte aligned");
+    const uint64_t block_vec4 = block_floats / 4;
+    const dim3 grid((uint32_t)((block_vec4 + kThreads * 4 - 1) / (kThreads * 4)), world);
+    shard_gather_rows_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(block_vec4, sh, out);
+    return check_launch("shard_gather_rows");
 }

@@ -169,12 +169,77 @@ def _get_host_group():
     return _host_group
 
 
+class _HostBoard:
+    """Single-node fast path of the per-call row-count exchange: a tiny file in /dev/shm mapped by every rank.
+    A gloo all-gather of one integer costs 0.1-0.3 ms of HOST time per call (sockets, thread wake-ups) -- in a
+    3 ms training step that is what lets the GPU run dry.  Here a rank publishes (sequence number, count) as ONE
+    aligned 64-bit store and spins until every peer has published the same sequence number: about a microsecond
+    when the ranks are in step.  Two slots alternate, so a rank that is already one call ahead cannot overwrite
+    a value a slower rank has not read yet."""
+
+    SEQ_SHIFT = 40  # count < 2^40, sequence number in the upper 24 bits
+
+    def __init__(self, group):
+        import socket
+        import tempfile
+
+        import numpy as np
+
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        hosts = [None] * self.world
+        dist.all_gather_object(hosts, socket.gethostname(), group=group)
+        self.ok = len(set(hosts)) == 1 and os.path.isdir("/dev/shm")
+        if not self.ok:
+            return
+        name = [None]
+        if self.rank == 0:
+            fd, path = tempfile.mkstemp(prefix="gsb200_board_", dir="/dev/shm")
+            os.write(fd, bytes(8 * 2 * self.world))
+            os.close(fd)
+            name[0] = path
+        dist.broadcast_object_list(name, src=0, group=group)
+        self.words = np.memmap(name[0], dtype=np.int64, mode="r+", shape=(2, self.world))
+        dist.barrier(group=group)
+        if self.rank == 0:
+            os.unlink(name[0])  # every rank holds its mapping; nothing is left behind in /dev/shm
+        self.seq = 0
+
+    def exchange(self, n: int) -> List[int]:
+        import time
+
+        self.seq = (self.seq + 1) & 0x7FFFFF
+        slot = self.words[self.seq & 1]
+        want = self.seq
+        slot[self.rank] = (want << self.SEQ_SHIFT) | int(n)
+        deadline, polls = None, 0
+        while True:
+            vals = slot.tolist()
+            if all((v >> self.SEQ_SHIFT) == want for v in vals):
+                return [v & ((1 << self.SEQ_SHIFT) - 1) for v in vals]
+            polls += 1
+            if polls % 256 == 0:
+                time.sleep(0)  # let a peer that shares this core run
+                now = time.monotonic()
+                deadline = deadline or now + 600.0
+                if now > deadline:
+                    raise RuntimeError("gather_counts: a peer rank did not reach the exchange within 600 s")
+
+
+_host_board: Optional[_HostBoard] = None
+
+
 def gather_counts(n: int, device=None) -> List[int]:
     """Number of rows every rank contributes (host-side exchange, does not touch the GPU stream)."""
+    global _host_board
     world = dist.get_world_size()
+    group = _get_host_group()
+    if _host_board is None or _host_board.world != world:
+        _host_board = _HostBoard(group)
+    if _host_board.ok:
+        return _host_board.exchange(n)
     mine = torch.tensor([int(n)], dtype=torch.int64)
     out = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(out, mine, group=_get_host_group())
+    dist.all_gather(out, mine, group=group)
     return [int(t.item()) for t in out]
 
 

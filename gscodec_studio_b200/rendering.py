@@ -138,17 +138,23 @@ def rasterization(
         geo_parts = [means] + ([quats, scales] if covars is None else [covars]) + [opacities[:, None]]
         widths = [t.shape[1] for t in geo_parts]
         pad_row = _inert_row(tuple(widths), covars is None, device)
-        pending_geo = start_gather(torch.cat(geo_parts, dim=1), counts, keep_padding=True, pad_row=pad_row)
         # SH coefficients (the bulk of the bytes) are not gathered at all when the peer-memory path is usable: the
-        # colour kernels pull the visible rows from their owners over NVLink (_peer.py)
+        # colour kernels pull the visible rows from their owners over NVLink, and the geometry all-gather is one
+        # pull kernel on the same symmetric buffer (_peer.py)
         from . import _peer
 
-        n_block = max(counts)
+        n_block = (max(counts) + 3) // 4 * 4
         pull_colors = (sh_degree is not None and not packed and colors.dim() == 3
                        and _peer.available(device, colors.shape[1] * 3, n_block))
         colors_local = colors
-        pending_colors = None if pull_colors else start_gather(colors, counts, keep_padding=True)
-        geo = torch.split(pending_geo.finish(), widths, dim=1)
+        if pull_colors:
+            gathered_geo, published = _peer.publish_and_gather_geometry(geo_parts, pad_row, colors_local, n_block)
+            pending_colors = None
+        else:
+            pending_geo = start_gather(torch.cat(geo_parts, dim=1), counts, keep_padding=True, pad_row=pad_row)
+            pending_colors = start_gather(colors, counts, keep_padding=True)
+            gathered_geo = pending_geo.finish()
+        geo = torch.split(gathered_geo, widths, dim=1)
         means = geo[0]
         if covars is None:
             quats, scales = geo[1], geo[2]
@@ -199,7 +205,7 @@ def rasterization(
     else:
         campos = _camera_positions(viewmats) if rigid_viewmats else torch.inverse(viewmats)[:, :3, 3]
         if pull_colors:
-            colors = _peer.view_colors_from_sh_sharded(sh_degree, means, campos, colors_local, radii, n_block)
+            colors = _peer.view_colors_from_sh_sharded(sh_degree, means, campos, colors_local, radii, n_block, published)
         elif not packed and colors.dim() == 3:
             # dense layout, per-Gaussian coefficients: one fused kernel (dirs, SH, +0.5, clamp)
             colors = view_colors_from_sh(sh_degree, means, campos, colors, radii)

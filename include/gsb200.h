@@ -141,6 +141,11 @@ int gsb200_sh_view_bwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degr
                                float *v_campos, gsb200_stream_t stream);
 int gsb200_shard_reduce_rows(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_floats,
                              const float *staging, const int32_t *flags, float *out, gsb200_stream_t stream);
+/* All-gather by pull, used for the geometry attributes (needed for EVERY row, so nothing to skip): out
+ * [world, block_floats] <- blocks[r][0 .. block_floats) for every rank r (HOST array of peer-mapped device
+ * pointers).  Replaces the all-gather of all_gather_tensor_list (distributed.py:102-167) for that tensor. */
+int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float *const *blocks, float *out,
+                             gsb200_stream_t stream);
 
 /* ---------------------------------------------------------------- stage 2: tile intersection
  * replaces _C.isect_tiles + _C.isect_offset_encode (bindings.h:147-166, isect_tiles.cu:16-389) with

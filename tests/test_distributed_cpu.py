@@ -62,6 +62,16 @@ def _worker(rank, world, port, out):
         (gg.nan_to_num(0.0) * w6[:, None]).sum().backward()
         rows = w6[:2] if rank == 0 else w6[3:]
         assert torch.equal(geo.grad, (rows * 2)[:, None].expand(-1, 4))
+        # per-call count exchange (shared-memory board on one node): ranks drift in and out of step
+        import random
+        import time
+        from gscodec_studio_b200 import distributed as D
+        rnd = random.Random(rank)
+        for i in range(3000):
+            if rnd.random() < 0.01:
+                time.sleep(rnd.random() * 1e-3)
+            assert gather_counts(i * 3 + rank, dev) == [i * 3, i * 3 + 1]
+        assert D._host_board is not None and D._host_board.ok
         # all-to-all with variable splits, differentiable
         t = torch.arange(4, dtype=torch.float32)[:, None].repeat(1, 2) + 10 * rank
         t.requires_grad_(True)

@@ -832,3 +832,8 @@ def test_sharded_view_colors_and_row_reduce_single_process(world, deg):
         assert torch.equal(out, expect)
     with pytest.raises(RuntimeError):
         call("gsb200_shard_reduce_rows", 17, n_block, 1, K * 3, ptr(stagings[0]), ptr(flags[0]), ptr(out), stream_ptr(DEV))
+    # all-gather by pull of [n_block, 11] geometry blocks
+    geo_blocks = [torch.randn(n_block, 11, generator=g).to(DEV) for _ in range(world)]
+    gathered = torch.empty(world * n_block, 11, device=DEV)
+    call("gsb200_shard_gather_rows", world, n_block * 11, table(geo_blocks)[1], ptr(gathered), stream_ptr(DEV))
+    assert torch.equal(gathered, torch.cat(geo_blocks, 0))

@@ -25,6 +25,8 @@ def main():
     # that exact depth ties (duplicate points of the garden cloud) are broken identically in both runs
     counts = [means[r::world].shape[0] for r in range(world)]
     n_max = max(counts)
+    if os.environ.get("GSB200_PEER_EXCHANGE", "1") != "0":
+        n_max = (n_max + 3) // 4 * 4  # the peer-memory path pads blocks to a multiple of 4 rows
 
     def padded_full(t, pad):
         blocks = []
