@@ -73,7 +73,7 @@ class PeerWorkspace:
         self._geo_tab = _ptr_table(ptrs, 4 * o_geo)
         self._stage_tab = _ptr_table(ptrs, 4 * o_stage)
         self._flag_tab = _ptr_table(ptrs, 4 * o_flags)
-        self.version = 0      # bumped by every publish(); a backward re-publishes if its forward's rows were replaced
+        self.version = 0      # bumped by every publish()
         self.readers = False  # a pull kernel was launched since the last barrier: peers may still be reading
 
     def barrier(self) -> None:
@@ -151,31 +151,32 @@ class _ShViewSharded(torch.autograd.Function):
         with torch.cuda.device(means.device):
             if published is None or published != ws.version:
                 ws.publish(coeffs_local)
+            # local copy of every pulled row: the backward needs the same rows again (d colour / d direction)
+            row_cache = torch.empty((N, K, 3), dtype=torch.float32, device=means.device) if any(ctx.needs_input_grad) else None
             call("gsb200_sh_view_fwd_sharded", C, N, K, sh_degree, ptr(means), ptr(campos), ws.coeff_table, ws.world, n_block,
-                 ptr(radii), ptr(colors), stream_ptr(means.device))
+                 ptr(radii), ptr(colors), ptr(row_cache), stream_ptr(means.device))
         ws.readers = True
-        ctx.save_for_backward(means, campos, coeffs_local, radii)
-        ctx.sh_degree, ctx.n_block, ctx.version = sh_degree, n_block, ws.version
+        ctx.save_for_backward(means, campos, radii, row_cache)
+        ctx.sh_degree, ctx.n_block, ctx.local_shape = sh_degree, n_block, tuple(coeffs_local.shape)
         return colors
 
     @staticmethod
     def backward(ctx, v_colors):
-        means, campos, coeffs_local, radii = ctx.saved_tensors
-        C, N, K = campos.shape[0], means.shape[0], coeffs_local.shape[1]
+        means, campos, radii, row_cache = ctx.saved_tensors
+        n_local, K = ctx.local_shape[0], ctx.local_shape[1]
+        C, N = campos.shape[0], means.shape[0]
         n_block = ctx.n_block
         ws = workspace(means.device, K * 3, n_block)
         v_colors = v_colors.contiguous()
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
-        v_coeffs = torch.empty_like(coeffs_local)
+        v_coeffs = torch.empty(ctx.local_shape, dtype=torch.float32, device=means.device)
         with torch.cuda.device(means.device):
-            if ws.version != ctx.version:  # another forward replaced the published rows since ours
-                ws.publish(coeffs_local)
             call("gsb200_sh_view_bwd_sharded", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ws.coeff_table, ws.world, n_block,
-                 ws.rank, ptr(radii), ptr(v_colors), ws.stage_table, ws.flag_table, ptr(v_means), ptr(v_campos),
+                 ws.rank, ptr(row_cache), ptr(radii), ptr(v_colors), ws.stage_table, ws.flag_table, ptr(v_means), ptr(v_campos),
                  stream_ptr(means.device))
             ws.barrier()  # every rank's pushes have landed
-            call("gsb200_shard_reduce_rows", ws.world, n_block, coeffs_local.shape[0], K * 3, ptr(ws.staging), ptr(ws.flags),
+            call("gsb200_shard_reduce_rows", ws.world, n_block, n_local, K * 3, ptr(ws.staging), ptr(ws.flags),
                  ptr(v_coeffs), stream_ptr(means.device))
             ws.barrier()  # every owner is done reducing: staging and published rows may be overwritten
         return None, v_means, v_campos, v_coeffs, None, None, None

@@ -236,7 +236,7 @@ __device__ __forceinline__ uint32_t coop_list_visible(bool any, uint8_t *list) {
 
 template <int DEG>
 __device__ __forceinline__ void coop_pull_rows(const CoeffShards &coeffs, uint32_t g0, uint32_t nfl, uint32_t nvis,
-                                               const uint8_t *list, float4 *rows) {
+                                               const uint8_t *list, float4 *rows, float *row_cache) {
     using R = CoopRows<DEG>;
     const uint32_t lane = threadIdx.x & 31, sub = lane / R::L, kk = lane - sub * R::L;
 #pragma unroll 4
@@ -244,7 +244,9 @@ __device__ __forceinline__ void coop_pull_rows(const CoeffShards &coeffs, uint32
         const uint32_t q = q0 + sub;
         if (sub < R::RPI && q < nvis) {
             const uint32_t j = list[q];
-            rows[j * R::U + kk] = ldg4(coeff_row(coeffs, g0 + j, nfl) + kk * 4);
+            const float4 v = ldg4(coeff_row(coeffs, g0 + j, nfl) + kk * 4);
+            rows[j * R::U + kk] = v;
+            if (row_cache != nullptr) stg4(row_cache + (size_t)(g0 + j) * nfl + kk * 4, v);  // local copy for the backward
         }
     }
     __syncwarp();
@@ -270,7 +272,8 @@ __device__ __forceinline__ void coop_push_rows(const PushTargets &t, uint32_t g0
 template <int DEG, bool COOP>
 __global__ void __launch_bounds__(COOP ? kCoopThreads : kThreads)
 sh_view_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__ means, const float *__restrict__ campos,
-                   const CoeffShards coeffs, const int32_t *__restrict__ radii, float *__restrict__ colors, bool vec) {
+                   const CoeffShards coeffs, const int32_t *__restrict__ radii, float *__restrict__ colors,
+                   float *__restrict__ row_cache, bool vec) {
     constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (!COOP && g >= N) return;
@@ -287,7 +290,7 @@ sh_view_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
         uint8_t *list = s_list + (threadIdx.x & ~31u);
         const uint32_t lane = threadIdx.x & 31;
         const uint32_t nvis = coop_list_visible<DEG>(any, list);
-        coop_pull_rows<DEG>(coeffs, g - lane, K * 3, nvis, list, rows);
+        coop_pull_rows<DEG>(coeffs, g - lane, K * 3, nvis, list, rows, row_cache);
         if (any) {
 #pragma unroll
             for (uint32_t k = 0; k < R::L; ++k) {
@@ -298,15 +301,20 @@ sh_view_fwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
         if (g >= N) return;
     } else if (any) {
         const float *row = coeff_row(coeffs, g, K * 3);
+        float *keep = row_cache != nullptr ? row_cache + (size_t)g * K * 3 : nullptr;
         if (vec) {
 #pragma unroll
             for (uint32_t k = 0; k < nb * 3; k += 4) {
                 const float4 v = ldg4(row + k);
                 cf[k] = v.x; cf[k + 1] = v.y; cf[k + 2] = v.z; cf[k + 3] = v.w;
+                if (keep != nullptr) stg4(keep + k, v);
             }
         } else {
 #pragma unroll
-            for (uint32_t k = 0; k < nb * 3; ++k) cf[k] = __ldg(row + k);
+            for (uint32_t k = 0; k < nb * 3; ++k) {
+                cf[k] = __ldg(row + k);
+                if (keep != nullptr) keep[k] = cf[k];
+            }
         }
     }
     if (any) { mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2]; }
@@ -332,7 +340,7 @@ template <int DEG, bool COOP>
 __global__ void __launch_bounds__(COOP ? kCoopThreads : kThreads)
 sh_view_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__ means, const float *__restrict__ campos,
                    const CoeffShards coeffs, const int32_t *__restrict__ radii, const float *__restrict__ v_colors,
-                   float *__restrict__ v_coeffs, const PushTargets push, float *__restrict__ v_means,
+                   float *__restrict__ v_coeffs, const PushTargets push, uint32_t push_block, float *__restrict__ v_means,
                    float *__restrict__ v_campos, bool vec) {
     __shared__ float s_red[kThreads / 32][3];
     using R = CoopRows<COOP ? DEG : 3>;
@@ -356,7 +364,7 @@ sh_view_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
     uint32_t nvis = 0;
     if constexpr (COOP) {
         nvis = coop_list_visible<DEG>(any, list);
-        coop_pull_rows<DEG>(coeffs, g - lane, nfl, nvis, list, rows);
+        coop_pull_rows<DEG>(coeffs, g - lane, nfl, nvis, list, rows, nullptr);
         if (any) {
 #pragma unroll
             for (uint32_t k = 0; k < R::L; ++k) {
@@ -429,13 +437,13 @@ sh_view_bwd_kernel(uint32_t C, uint32_t N, uint32_t K, const float *__restrict__
                 rows[lane * R::U + k] = make_float4(vc[4 * k], vc[4 * k + 1], vc[4 * k + 2], vc[4 * k + 3]);
         }
         __syncwarp();
-        coop_push_rows<DEG>(push, g - lane, coeffs.n_block, nfl, nvis, list, rows);
+        coop_push_rows<DEG>(push, g - lane, push_block, nfl, nvis, list, rows);
     }
     if (g >= N) return;
     float *vrow = nullptr;
     if (pushing) {  // only visible rows travel; the flag tells the owner which
         uint32_t owner;
-        const size_t slot = push_slot(push, g, coeffs.n_block, owner);
+        const size_t slot = push_slot(push, g, push_block, owner);
         push.flags[owner][slot] = any ? 1 : 0;
         if (!COOP && any) vrow = push.rows[owner] + slot * nfl;
     } else if (v_coeffs != nullptr) {
@@ -553,49 +561,49 @@ static bool sh_vec_ok(uint32_t K, uint32_t degree, const void *a, const void *b)
 
 template <int DEG, bool COOP>
 static void launch_view_fwd(cudaStream_t s, uint32_t C, uint32_t N, uint32_t K, const float *means, const float *campos,
-                            const CoeffShards &sh, const int32_t *radii, float *colors, bool vec) {
+                            const CoeffShards &sh, const int32_t *radii, float *colors, float *row_cache, bool vec) {
     const uint32_t threads = COOP ? kCoopThreads : kThreads;
-    sh_view_fwd_kernel<DEG, COOP><<<cdiv(N, threads), threads, 0, s>>>(C, N, K, means, campos, sh, radii, colors, vec);
+    sh_view_fwd_kernel<DEG, COOP><<<cdiv(N, threads), threads, 0, s>>>(C, N, K, means, campos, sh, radii, colors, row_cache, vec);
 }
 
 template <int DEG, bool COOP>
 static void launch_view_bwd(cudaStream_t s, uint32_t C, uint32_t N, uint32_t K, const float *means, const float *campos,
                             const CoeffShards &sh, const int32_t *radii, const float *v_colors, float *v_coeffs,
-                            const PushTargets &push, float *v_means, float *v_campos, bool vec) {
+                            const PushTargets &push, uint32_t push_block, float *v_means, float *v_campos, bool vec) {
     const uint32_t threads = COOP ? kCoopThreads : kThreads;
     sh_view_bwd_kernel<DEG, COOP><<<cdiv(N, threads), threads, 0, s>>>(C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push,
-                                                                        v_means, v_campos, vec);
+                                                                        push_block, v_means, v_campos, vec);
 }
 
 // coop: warp-cooperative row staging (multi-GPU form, 16-byte rows, every coefficient of the row used)
 static bool coop_ok(uint32_t K, uint32_t degree, bool vec) { return vec && (degree == 1 || degree == 3) && (degree + 1) * (degree + 1) == K; }
 
 static int view_fwd(const char *who, uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
-                    const CoeffShards &sh, bool vec, bool coop, const int32_t *radii, float *colors, cudaStream_t s) {
-    if (coop && degree == 3) launch_view_fwd<3, true>(s, C, N, K, means, campos, sh, radii, colors, vec);
-    else if (coop) launch_view_fwd<1, true>(s, C, N, K, means, campos, sh, radii, colors, vec);
+                    const CoeffShards &sh, bool vec, bool coop, const int32_t *radii, float *colors, float *row_cache, cudaStream_t s) {
+    if (coop && degree == 3) launch_view_fwd<3, true>(s, C, N, K, means, campos, sh, radii, colors, row_cache, vec);
+    else if (coop) launch_view_fwd<1, true>(s, C, N, K, means, campos, sh, radii, colors, row_cache, vec);
     else switch (degree) {
-        case 0: launch_view_fwd<0, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
-        case 1: launch_view_fwd<1, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
-        case 2: launch_view_fwd<2, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
-        case 3: launch_view_fwd<3, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
-        default: launch_view_fwd<4, false>(s, C, N, K, means, campos, sh, radii, colors, vec); break;
+        case 0: launch_view_fwd<0, false>(s, C, N, K, means, campos, sh, radii, colors, row_cache, vec); break;
+        case 1: launch_view_fwd<1, false>(s, C, N, K, means, campos, sh, radii, colors, row_cache, vec); break;
+        case 2: launch_view_fwd<2, false>(s, C, N, K, means, campos, sh, radii, colors, row_cache, vec); break;
+        case 3: launch_view_fwd<3, false>(s, C, N, K, means, campos, sh, radii, colors, row_cache, vec); break;
+        default: launch_view_fwd<4, false>(s, C, N, K, means, campos, sh, radii, colors, row_cache, vec); break;
     }
     return check_launch(who);
 }
 
 static int view_bwd(const char *who, uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
                     const CoeffShards &sh, bool vec, bool coop, const int32_t *radii, const float *v_colors, float *v_coeffs,
-                    const PushTargets &push, float *v_means, float *v_campos, cudaStream_t s) {
+                    const PushTargets &push, uint32_t push_block, float *v_means, float *v_campos, cudaStream_t s) {
     if (v_campos != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_campos, 0, sizeof(float) * 3 * C, s));
-    if (coop && degree == 3) launch_view_bwd<3, true>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec);
-    else if (coop) launch_view_bwd<1, true>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec);
+    if (coop && degree == 3) launch_view_bwd<3, true>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, push_block, v_means, v_campos, vec);
+    else if (coop) launch_view_bwd<1, true>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, push_block, v_means, v_campos, vec);
     else switch (degree) {
-        case 0: launch_view_bwd<0, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
-        case 1: launch_view_bwd<1, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
-        case 2: launch_view_bwd<2, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
-        case 3: launch_view_bwd<3, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
-        default: launch_view_bwd<4, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, v_means, v_campos, vec); break;
+        case 0: launch_view_bwd<0, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, push_block, v_means, v_campos, vec); break;
+        case 1: launch_view_bwd<1, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, push_block, v_means, v_campos, vec); break;
+        case 2: launch_view_bwd<2, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, push_block, v_means, v_campos, vec); break;
+        case 3: launch_view_bwd<3, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, push_block, v_means, v_campos, vec); break;
+        default: launch_view_bwd<4, false>(s, C, N, K, means, campos, sh, radii, v_colors, v_coeffs, push, push_block, v_means, v_campos, vec); break;
     }
     return check_launch(who);
 }
@@ -628,7 +636,7 @@ extern "C" int gsb200_sh_view_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t d
     CoeffShards sh{};
     sh.base[0] = coeffs;
     return view_fwd("sh_view_fwd", C, N, K, degree, means, campos, sh, sh_vec_ok(K, degree, coeffs, nullptr), false, radii, colors,
-                    (cudaStream_t)stream);
+                    nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
@@ -640,26 +648,27 @@ extern "C" int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t d
     sh.base[0] = coeffs;
     const PushTargets none{};
     return view_bwd("sh_view_bwd", C, N, K, degree, means, campos, sh, sh_vec_ok(K, degree, coeffs, v_coeffs), false, radii, v_colors,
-                    v_coeffs, none, v_means, v_campos, (cudaStream_t)stream);
+                    v_coeffs, none, 0, v_means, v_campos, (cudaStream_t)stream);
 }
 
 extern "C" int gsb200_sh_view_fwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
                                           const float *campos, const float *const *shard_coeffs, uint32_t world, uint32_t n_block,
-                                          const int32_t *radii, float *colors, gsb200_stream_t stream) {
+                                          const int32_t *radii, float *colors, float *row_cache, gsb200_stream_t stream) {
     if (int rc = check_view_args("gsb200_sh_view_fwd_sharded", K, degree)) return rc;
     if (C == 0 || N == 0) return 0;
     CoeffShards sh{};
     bool aligned = false;
     if (int rc = make_shards("gsb200_sh_view_fwd_sharded", shard_coeffs, world, n_block, N, sh, aligned)) return rc;
-    const bool vec = aligned && sh_vec_ok(K, degree, nullptr, nullptr);
+    const bool vec = aligned && sh_vec_ok(K, degree, row_cache, nullptr);
     return view_fwd("sh_view_fwd_sharded", C, N, K, degree, means, campos, sh, vec, coop_ok(K, degree, vec), radii, colors,
-                    (cudaStream_t)stream);
+                    row_cache, (cudaStream_t)stream);
 }
 
 extern "C" int gsb200_sh_view_bwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
                                           const float *campos, const float *const *shard_coeffs, uint32_t world, uint32_t n_block,
-                                          uint32_t rank, const int32_t *radii, const float *v_colors, float *const *peer_rows,
-                                          int32_t *const *peer_flags, float *v_means, float *v_campos, gsb200_stream_t stream) {
+                                          uint32_t rank, const float *row_cache, const int32_t *radii, const float *v_colors,
+                                          float *const *peer_rows, int32_t *const *peer_flags, float *v_means, float *v_campos,
+                                          gsb200_stream_t stream) {
     const char *who = "gsb200_sh_view_bwd_sharded";
     if (int rc = check_view_args(who, K, degree)) return rc;
     if (peer_rows == nullptr || peer_flags == nullptr) return fail(2, "gsb200_sh_view_bwd_sharded: null peer tables");
@@ -676,9 +685,14 @@ extern "C" int gsb200_sh_view_bwd_sharded(uint32_t C, uint32_t N, uint32_t K, ui
         if (push.rows[r] == nullptr || push.flags[r] == nullptr) return fail(2, "gsb200_sh_view_bwd_sharded: null peer pointer");
         aligned = aligned && (reinterpret_cast<uintptr_t>(push.rows[r]) & 15) == 0;
     }
+    if (row_cache != nullptr) {  // the forward kept a local copy of every visible row: no second pull over the link
+        sh = CoeffShards{};
+        sh.base[0] = row_cache;
+        aligned = aligned && (reinterpret_cast<uintptr_t>(row_cache) & 15) == 0;
+    }
     const bool vec = aligned && sh_vec_ok(K, degree, nullptr, nullptr);
     return view_bwd("sh_view_bwd_sharded", C, N, K, degree, means, campos, sh, vec, coop_ok(K, degree, vec), radii, v_colors, nullptr,
-                    push, v_means, v_campos, (cudaStream_t)stream);
+                    push, n_block, v_means, v_campos, (cudaStream_t)stream);
 }
 
 extern "C" int gsb200_shard_reduce_rows(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_floats, const float *staging,

@@ -123,6 +123,9 @@ int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, cons
  *   shard_coeffs : HOST array of `world` device pointers; shard_coeffs[r] = rank r's [n_block, K, 3] block as
  *                  mapped into this process.  Gathered row g lives at shard_coeffs[g / n_block][g % n_block].
  *   N            : rows of the gathered set, N <= world * n_block.
+ *   row_cache    : optional local [N, K, 3] array; the forward stores every row it pulled there (rows of invisible
+ *                  Gaussians stay untouched) and the backward, given the same array, reads it instead of pulling
+ *                  the rows over the link a second time.
  * The backward PUSHES: rank `rank` stores the coefficient-gradient row of every visible gathered Gaussian g into
  * slot [rank][g % n_block] of the staging array of g's owner, and a 0/1 flag for EVERY row next to it:
  *   peer_rows[o]  : owner o's staging array [world, n_block, K*3] as mapped into this process (HOST array of ptrs)
@@ -133,10 +136,12 @@ int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, cons
 #define GSB200_MAX_SHARDS 16
 int gsb200_sh_view_fwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
                                const float *campos, const float *const *shard_coeffs, uint32_t world,
-                               uint32_t n_block, const int32_t *radii, float *colors, gsb200_stream_t stream);
+                               uint32_t n_block, const int32_t *radii, float *colors, float *row_cache,
+                               gsb200_stream_t stream);
 int gsb200_sh_view_bwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
                                const float *campos, const float *const *shard_coeffs, uint32_t world,
-                               uint32_t n_block, uint32_t rank, const int32_t *radii, const float *v_colors,
+                               uint32_t n_block, uint32_t rank, const float *row_cache, const int32_t *radii,
+                               const float *v_colors,
                                float *const *peer_rows, int32_t *const *peer_flags, float *v_means,
                                float *v_campos, gsb200_stream_t stream);
 int gsb200_shard_reduce_rows(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_floats,

@@ -797,8 +797,16 @@ def test_sharded_view_colors_and_row_reduce_single_process(world, deg):
     coeff_tab = table(blocks)
     colors = torch.empty(C, N, 3, device=DEV)
     call("gsb200_sh_view_fwd_sharded", C, N, K, deg, ptr(means), ptr(campos), coeff_tab[1], world, n_block, ptr(radii),
-         ptr(colors), stream_ptr(DEV))
+         ptr(colors), None, stream_ptr(DEV))
     assert torch.equal(colors, ref.detach())
+    cache = torch.full((N, K, 3), float("nan"), device=DEV)  # the forward's local copy of every row it pulled
+    colors.zero_()
+    call("gsb200_sh_view_fwd_sharded", C, N, K, deg, ptr(means), ptr(campos), coeff_tab[1], world, n_block, ptr(radii),
+         ptr(colors), ptr(cache), stream_ptr(DEV))
+    seen = (radii > 0).any(0)
+    nb3 = (deg + 1) ** 2 * 3
+    assert torch.equal(colors, ref.detach())
+    assert torch.equal(cache[seen].flatten(1)[:, :nb3], full.detach()[seen].flatten(1)[:, :nb3]) and torch.isnan(cache[~seen]).all()
 
     # every fake rank `p` renders its own weights and PUSHES rows + flags into the owners' staging arrays (slot p)
     stagings = [torch.full((world, n_block, K, 3), float("nan"), device=DEV) for _ in range(world)]
@@ -810,8 +818,9 @@ def test_sharded_view_colors_and_row_reduce_single_process(world, deg):
         vis = radii.clone()
         vis[:, p::world] = 0  # a different visible set per rank
         v_means = torch.empty(N, 3, device=DEV)
-        call("gsb200_sh_view_bwd_sharded", C, N, K, deg, ptr(means), ptr(campos), coeff_tab[1], world, n_block, p, ptr(vis),
-             ptr(wp), st_tab[1], fl_tab[1], ptr(v_means), None, stream_ptr(DEV))
+        # even source ranks read the rows from the forward's cache, odd ones pull them again
+        call("gsb200_sh_view_bwd_sharded", C, N, K, deg, ptr(means), ptr(campos), coeff_tab[1], world, n_block, p,
+             ptr(cache) if p % 2 == 0 else None, ptr(vis), ptr(wp), st_tab[1], fl_tab[1], ptr(v_means), None, stream_ptr(DEV))
         f2 = full.detach().clone().requires_grad_(True)
         m2 = means.clone().requires_grad_(True)
         (view_colors_from_sh(deg, m2, campos, f2, vis) * wp).sum().backward()
