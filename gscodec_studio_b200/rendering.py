@@ -176,7 +176,7 @@ def rasterization(
         opacities = opacities[gaussian_ids]  # [nnz]
     else:
         radii, means2d, depths, conics, compensations = proj_results
-        opacities = opacities.repeat(C, 1)  # [C, N]
+        opacities = opacities.unsqueeze(0) if C == 1 else opacities.repeat(C, 1)  # [C, N] (a view for one camera)
         camera_ids, gaussian_ids = None, None
     if compensations is not None:
         opacities = opacities * compensations

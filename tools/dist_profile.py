@@ -58,6 +58,17 @@ def main():
             gap = e.time_range.start - prev_end
             print(f"{s / 1e3:8.3f} ms  {d:7.1f} us  gap {gap:7.1f}  {e.name[:90]}")
             prev_end = max(prev_end, e.time_range.end)
+        # host side of the same step: top-level CPU ops / python functions, start relative to the step's first kernel
+        t1 = evs[hi].time_range.start
+        cpu = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU and e.cpu_parent is None]
+        cpu.sort(key=lambda e: e.time_range.start)
+        print("---- host timeline (top-level ops; offsets relative to the first kernel of the step)")
+        for e in cpu:
+            s0 = e.time_range.start - t0
+            if -3000 <= s0 <= (t1 - t0):
+                d = e.time_range.end - e.time_range.start
+                if d >= 15:
+                    print(f"{s0 / 1e3:8.3f} ms  {d:7.1f} us  {e.name[:100]}")
     dist.destroy_process_group()
 
 
