@@ -39,6 +39,8 @@ SIGNATURES = {
     "gsb200_sh_bwd": [_U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_view_fwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_view_bwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_sh_view_split_fwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_sh_view_split_bwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_view_fwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _P, _P, _P, _P],
     "gsb200_sh_view_bwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_shard_reduce_rows": [_U, _U, _U, _U, _P, _P, _P, _P],

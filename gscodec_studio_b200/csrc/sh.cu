@@ -509,6 +509,166 @@ shard_gather_rows_kernel(uint64_t block_vec4, const BlockShards blocks, float *_
         if (i0 + u * kThreads < block_vec4) stg4(dst + (i0 + u * kThreads) * 4, v[u]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split-coefficient form of the fused view-colour stage.  The trainers keep the DC band and the higher bands as
+// two parameters, sh0 [N,1,3] and shN [N,K-1,3], and concatenate them every step only to hand one [N,K,3] tensor
+// to rasterization() (examples/simple_trainer.py:776: a 193 MB copy forward and two strided copies backward at
+// 1 M Gaussians).  These kernels read / write the two arrays in place: the visible rows are read by their owner
+// thread (4-byte loads -- a (K-1)*12-byte row is not 16-byte aligned), the gradient rows of a block -- one
+// contiguous [kSplitThreads, (K-1)*3] slab of v_shN, zeros for invisible Gaussians and unused bands included --
+// are staged in shared memory and written with coalesced 16-byte stores, exactly once.
+constexpr int kSplitThreads = 128;
+
+template <int DEG>
+__global__ void __launch_bounds__(kSplitThreads)
+sh_view_split_fwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__restrict__ means, const float *__restrict__ campos,
+                         const float *__restrict__ sh0, const float *__restrict__ shN, const int32_t *__restrict__ radii,
+                         float *__restrict__ colors) {
+    constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
+    const uint32_t g = blockIdx.x * kSplitThreads + threadIdx.x;
+    if (g >= N) return;
+    bool any = false;
+    for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
+    float cf[nb * 3];
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (any) {
+        cf[0] = __ldg(sh0 + (size_t)g * 3); cf[1] = __ldg(sh0 + (size_t)g * 3 + 1); cf[2] = __ldg(sh0 + (size_t)g * 3 + 2);
+        if (DEG > 0) {
+            const float *row = shN + (size_t)g * RF;
+#pragma unroll
+            for (uint32_t k = 0; k + 3 < nb * 3; ++k) cf[3 + k] = __ldg(row + k);
+        }
+        mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
+    }
+    for (uint32_t c = 0; c < C; ++c) {
+        const size_t idx = (size_t)c * N + g;
+        float r = 0.f, gg = 0.f, b = 0.f;
+        if (radii[idx] > 0) {
+            float x = mx - campos[c * 3], y = my - campos[c * 3 + 1], z = mz - campos[c * 3 + 2];
+            if (DEG > 0) {
+                const float inorm = rsqrtf(x * x + y * y + z * z);
+                x *= inorm; y *= inorm; z *= inorm;
+            }
+            sh_terms(DEG, x, y, z, [&](int k, float Y, float, float, float) {
+                r += Y * cf[k * 3]; gg += Y * cf[k * 3 + 1]; b += Y * cf[k * 3 + 2];
+            });
+            r = fmaxf(r + 0.5f, 0.f); gg = fmaxf(gg + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
+        }
+        colors[idx * 3] = r; colors[idx * 3 + 1] = gg; colors[idx * 3 + 2] = b;
+    }
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kSplitThreads)
+sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__restrict__ means, const float *__restrict__ campos,
+                         const float *__restrict__ sh0, const float *__restrict__ shN, const int32_t *__restrict__ radii,
+                         const float *__restrict__ v_colors, float *__restrict__ v_sh0, float *__restrict__ v_shN,
+                         float *__restrict__ v_means, float *__restrict__ v_campos) {
+    extern __shared__ float s_slab[];  // [kSplitThreads][RF | 1]: the block's v_shN rows
+    __shared__ float s_red[kSplitThreads / 32][3];
+    constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
+    constexpr uint32_t nact = nb * 3 - 3;  // floats of an shN row that the active bands cover
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t g = blockIdx.x * kSplitThreads + tid;
+    float vc[nb * 3];
+#pragma unroll
+    for (uint32_t k = 0; k < nb * 3; ++k) vc[k] = 0.f;
+    float vmx = 0.f, vmy = 0.f, vmz = 0.f;
+    bool any = false;
+    if (g < N)
+        for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
+    float cf[nb * 3];
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    if (any) {
+        cf[0] = __ldg(sh0 + (size_t)g * 3); cf[1] = __ldg(sh0 + (size_t)g * 3 + 1); cf[2] = __ldg(sh0 + (size_t)g * 3 + 2);
+        if (DEG > 0) {
+            const float *row = shN + (size_t)g * RF;
+#pragma unroll
+            for (uint32_t k = 0; k + 3 < nb * 3; ++k) cf[3 + k] = __ldg(row + k);
+        }
+        mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
+    }
+    for (uint32_t c = 0; c < C; ++c) {
+        float dxv = 0.f, dyv = 0.f, dzv = 0.f;
+        if (any && radii[(size_t)c * N + g] > 0) {
+            const size_t idx = (size_t)c * N + g;
+            float x = mx - campos[c * 3], y = my - campos[c * 3 + 1], z = mz - campos[c * 3 + 2];
+            float inorm = 1.f;
+            if (DEG > 0) {
+                inorm = rsqrtf(x * x + y * y + z * z);
+                x *= inorm; y *= inorm; z *= inorm;
+            }
+            float r = 0.f, gg = 0.f, b = 0.f;  // pre-clamp colour: the gradient passes where x + 0.5 >= 0
+            sh_terms(DEG, x, y, z, [&](int k, float Y, float, float, float) {
+                r += Y * cf[k * 3]; gg += Y * cf[k * 3 + 1]; b += Y * cf[k * 3 + 2];
+            });
+            const float vr = (r + 0.5f >= 0.f) ? v_colors[idx * 3] : 0.f;
+            const float vg = (gg + 0.5f >= 0.f) ? v_colors[idx * 3 + 1] : 0.f;
+            const float vb = (b + 0.5f >= 0.f) ? v_colors[idx * 3 + 2] : 0.f;
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+            sh_terms(DEG, x, y, z, [&](int k, float Y, float dx, float dy, float dz) {
+                vc[k * 3] += Y * vr; vc[k * 3 + 1] += Y * vg; vc[k * 3 + 2] += Y * vb;
+                const float wk = cf[k * 3] * vr + cf[k * 3 + 1] * vg + cf[k * 3 + 2] * vb;
+                gx += dx * wk; gy += dy * wk; gz += dz * wk;
+            });
+            if (DEG > 0) {
+                const float dotp = gx * x + gy * y + gz * z;
+                dxv = (gx - dotp * x) * inorm; dyv = (gy - dotp * y) * inorm; dzv = (gz - dotp * z) * inorm;
+                vmx += dxv; vmy += dyv; vmz += dzv;
+            }
+        }
+        if (v_campos != nullptr) {  // d dirs / d campos = -1: block reduction, one atomic set per block and camera
+            const float sx = warp_sum(dxv), sy = warp_sum(dyv), sz = warp_sum(dzv);
+            __syncthreads();
+            if (lane == 0) { s_red[tid >> 5][0] = sx; s_red[tid >> 5][1] = sy; s_red[tid >> 5][2] = sz; }
+            __syncthreads();
+            if (tid < 3) {
+                float t = 0.f;
+                for (uint32_t w = 0; w < kSplitThreads / 32; ++w) t += s_red[w][tid];
+                if (t != 0.f) atomicAdd(v_campos + c * 3 + tid, -t);
+            }
+        }
+    }
+    if (g < N) {
+        v_sh0[(size_t)g * 3] = vc[0]; v_sh0[(size_t)g * 3 + 1] = vc[1]; v_sh0[(size_t)g * 3 + 2] = vc[2];
+        if (v_means != nullptr) {
+            v_means[(size_t)g * 3] = vmx; v_means[(size_t)g * 3 + 1] = vmy; v_means[(size_t)g * 3 + 2] = vmz;
+        }
+    }
+    if (RF == 0) return;
+    const uint32_t stride = RF | 1u;  // odd: the per-thread row writes below are bank-conflict free
+    if (DEG > 0) {
+#pragma unroll
+        for (uint32_t k = 0; k < nact; ++k) s_slab[tid * stride + k] = vc[3 + k];
+    }
+    __syncthreads();
+    // coalesced copy of the slab: element i of the block's region is (row i / RF, column i % RF); columns past the
+    // active bands are zero.  The region starts at a multiple of kSplitThreads * RF floats, i.e. 16-byte aligned.
+    const uint32_t row0 = blockIdx.x * kSplitThreads;
+    const uint32_t nrows = min((uint32_t)kSplitThreads, N - row0);
+    const uint32_t total = nrows * RF, nvec = total / 4;
+    float *dst = v_shN + (size_t)row0 * RF;
+    uint32_t row = (4 * tid) / RF, col = (4 * tid) - row * RF;
+    const uint32_t step_row = (4 * kSplitThreads) / RF, step_col = (4 * kSplitThreads) - step_row * RF;
+    for (uint32_t v = tid; v < nvec; v += kSplitThreads) {
+        float e[4];
+        uint32_t r = row, cc = col;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            e[q] = cc < nact ? s_slab[r * stride + cc] : 0.f;
+            if (++cc == RF) { cc = 0; ++r; }
+        }
+        stg4(dst + (size_t)v * 4, make_float4(e[0], e[1], e[2], e[3]));
+        row += step_row; col += step_col;
+        if (col >= RF) { col -= RF; ++row; }
+    }
+    const uint32_t i = nvec * 4 + tid;  // ragged tail of the last block
+    if (i < total) {
+        const uint32_t r = i / RF, cc = i - r * RF;
+        dst[i] = cc < nact ? s_slab[r * stride + cc] : 0.f;
+    }
+}
+
 }  // namespace gsb200
 
 using namespace gsb200;
@@ -726,4 +886,55 @@ extern "C" int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, c
     const dim3 grid((uint32_t)((block_vec4 + kThreads * 4 - 1) / (kThreads * 4)), world);
     shard_gather_rows_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(block_vec4, sh, out);
     return check_launch("shard_gather_rows");
+}
+
+// ---- split-coefficient entry points (sh0 [N,1,3] + shN [N,K-1,3] in place of one [N,K,3] tensor) -------------
+static int check_split_args(const char *who, uint32_t K, uint32_t degree, const float *sh0, const float *shN) {
+    if (int rc = check_view_args(who, K, degree)) return rc;
+    if (K - 1 > GSB200_SH_SPLIT_MAX_REST) return failf(2, "%s: at most %d higher-band coefficients per Gaussian", who, GSB200_SH_SPLIT_MAX_REST);
+    if (sh0 == nullptr || (degree > 0 && shN == nullptr)) return failf(2, "%s: null coefficient pointer", who);
+    return 0;
+}
+
+extern "C" int gsb200_sh_view_split_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
+                                        const float *sh0, const float *shN, const int32_t *radii, float *colors,
+                                        gsb200_stream_t stream) {
+    if (int rc = check_split_args("gsb200_sh_view_split_fwd", K, degree, sh0, shN)) return rc;
+    if (C == 0 || N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t grid = cdiv(N, kSplitThreads), RF = (K - 1) * 3;
+    switch (degree) {
+        case 0: sh_view_split_fwd_kernel<0><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
+        case 1: sh_view_split_fwd_kernel<1><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
+        case 2: sh_view_split_fwd_kernel<2><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
+        case 3: sh_view_split_fwd_kernel<3><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
+        default: sh_view_split_fwd_kernel<4><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
+    }
+    return check_launch("sh_view_split_fwd");
+}
+
+extern "C" int gsb200_sh_view_split_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
+                                        const float *sh0, const float *shN, const int32_t *radii, const float *v_colors,
+                                        float *v_sh0, float *v_shN, float *v_means, float *v_campos, gsb200_stream_t stream) {
+    const char *who = "gsb200_sh_view_split_bwd";
+    if (int rc = check_split_args(who, K, degree, sh0, shN)) return rc;
+    if (C == 0 || N == 0) return 0;
+    if (v_sh0 == nullptr || (K > 1 && v_shN == nullptr)) return failf(2, "%s: null gradient pointer", who);
+    if ((reinterpret_cast<uintptr_t>(v_shN) & 15) != 0) return failf(2, "%s: v_shN must be 16-byte aligned", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (v_campos != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_campos, 0, sizeof(float) * 3 * C, s));
+    const uint32_t grid = cdiv(N, kSplitThreads), RF = (K - 1) * 3;
+    const size_t smem = sizeof(float) * kSplitThreads * (RF | 1u);
+#define GSB_SPLIT_BWD(D)                                                                                                   \
+    sh_view_split_bwd_kernel<D><<<grid, kSplitThreads, smem, s>>>(C, N, RF, means, campos, sh0, shN, radii, v_colors, v_sh0, \
+                                                                  v_shN, v_means, v_campos)
+    switch (degree) {
+        case 0: GSB_SPLIT_BWD(0); break;
+        case 1: GSB_SPLIT_BWD(1); break;
+        case 2: GSB_SPLIT_BWD(2); break;
+        case 3: GSB_SPLIT_BWD(3); break;
+        default: GSB_SPLIT_BWD(4); break;
+    }
+#undef GSB_SPLIT_BWD
+    return check_launch("sh_view_split_bwd");
 }

@@ -131,6 +131,53 @@ class _ShView(torch.autograd.Function):
         return None, v_means, v_campos, v_coeffs, None
 
 
+SH_SPLIT_MAX_REST = 31  # GSB200_SH_SPLIT_MAX_REST in include/gsb200.h
+
+
+def view_colors_from_sh_split(sh_degree: int, means: Tensor, campos: Tensor, sh0: Tensor, shN: Tensor, radii: Tensor) -> Tensor:
+    """`view_colors_from_sh` for coefficients kept as the trainers keep them: sh0 [N,1,3] (DC band) and shN
+    [N,K-1,3] (higher bands) as two tensors.  Same result as ``view_colors_from_sh(..., torch.cat([sh0, shN], 1),
+    ...)`` (examples/simple_trainer.py:776) without the [N,K,3] copy forward and the two strided gradient copies
+    backward; gradients reach sh0 and shN directly."""
+    N, C = means.shape[0], campos.shape[0]
+    assert means.shape == (N, 3) and campos.shape == (C, 3), (means.shape, campos.shape)
+    assert sh0.shape == (N, 1, 3), sh0.shape
+    assert shN.dim() == 3 and shN.shape[0] == N and shN.shape[2] == 3, shN.shape
+    assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1], shN.shape
+    assert shN.shape[1] <= SH_SPLIT_MAX_REST, shN.shape
+    assert radii.shape == (C, N), radii.shape
+    return _ShViewSplit.apply(sh_degree, means.contiguous(), campos.contiguous(), sh0.contiguous(), shN.contiguous(),
+                              radii.contiguous())
+
+
+class _ShViewSplit(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree, means, campos, sh0, shN, radii):
+        means, campos, sh0, shN = _f32(means), _f32(campos), _f32(sh0), _f32(shN)
+        C, N, K = campos.shape[0], means.shape[0], 1 + shN.shape[1]
+        colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
+        with torch.cuda.device(means.device):
+            call("gsb200_sh_view_split_fwd", C, N, K, sh_degree, ptr(means), ptr(campos), ptr(sh0), ptr(shN), ptr(radii),
+                 ptr(colors), stream_ptr(means.device))
+        ctx.save_for_backward(means, campos, sh0, shN, radii)
+        ctx.sh_degree = sh_degree
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means, campos, sh0, shN, radii = ctx.saved_tensors
+        C, N, K = campos.shape[0], means.shape[0], 1 + shN.shape[1]
+        v_colors = _f32(v_colors.contiguous())
+        v_sh0 = torch.empty_like(sh0)
+        v_shN = torch.empty_like(shN)
+        v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
+        v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(means.device):
+            call("gsb200_sh_view_split_bwd", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ptr(sh0), ptr(shN), ptr(radii),
+                 ptr(v_colors), ptr(v_sh0), ptr(v_shN), ptr(v_means), ptr(v_campos), stream_ptr(means.device))
+        return None, v_means, v_campos, v_sh0, v_shN, None
+
+
 # --------------------------------------------------------------------------------------
 # projection
 # --------------------------------------------------------------------------------------

@@ -24,7 +24,9 @@ from .cuda._wrapper import (
     fully_fused_projection,
     rasterize_to_pixels,
     spherical_harmonics,
+    SH_SPLIT_MAX_REST,
     view_colors_from_sh,
+    view_colors_from_sh_split,
 )
 
 
@@ -57,7 +59,7 @@ def rasterization(
     quats: Tensor,  # [N, 4]
     scales: Tensor,  # [N, 3]
     opacities: Tensor,  # [N]
-    colors: Tensor,  # [(C,) N, D] or [(C,) N, K, 3]
+    colors,  # Tensor [(C,) N, D] or [(C,) N, K, 3]; or the pair (sh0 [N,1,3], shN [N,K-1,3]) -- additive
     viewmats: Tensor,  # [C, 4, 4]
     Ks: Tensor,  # [C, 3, 3]
     width: int,
@@ -84,6 +86,12 @@ def rasterization(
 
     Returns (render_colors [C,H,W,X], render_alphas [C,H,W,1], meta).  See the reference docstring
     (gsplat/rendering.py:55-222) for the meaning of every argument; `rigid_viewmats` is additive.
+
+    Additive: with `sh_degree` set, `colors` may also be the pair ``(sh0, shN)`` of the trainers' two SH
+    parameters ([N,1,3] and [N,K-1,3]) instead of ``torch.cat([sh0, shN], 1)`` (examples/simple_trainer.py:776).
+    The dense single-process path then reads both arrays in place and writes their gradients directly (no
+    [N,K,3] copy forward, no strided gradient copies backward); every other mode concatenates them first, so the
+    result is the same as for the concatenated tensor.
     """
     meta: Dict = {}
     N = means.shape[0]
@@ -103,7 +111,21 @@ def rasterization(
     assert Ks.shape == (C, 3, 3), Ks.shape
     assert render_mode in ["RGB", "D", "ED", "RGB+D", "RGB+ED"], render_mode
 
-    if sh_degree is None:
+    sh_pair = None
+    if isinstance(colors, (tuple, list)):
+        assert sh_degree is not None and len(colors) == 2, "colors=(sh0, shN) needs sh_degree"
+        sh0, shN = colors
+        assert sh0.shape == (N, 1, 3), sh0.shape
+        assert shN.dim() == 3 and shN.shape[0] == N and shN.shape[2] == 3, shN.shape
+        assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1], shN.shape
+        if not distributed and not packed and shN.shape[1] <= SH_SPLIT_MAX_REST:
+            sh_pair, colors = (sh0, shN), None
+        else:
+            colors = torch.cat([sh0, shN], dim=1)
+
+    if sh_pair is not None:
+        pass
+    elif sh_degree is None:
         assert (colors.dim() == 2 and colors.shape[0] == N) or (
             colors.dim() == 3 and colors.shape[:2] == (C, N)
         ), colors.shape
@@ -204,7 +226,9 @@ def rasterization(
             colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
     else:
         campos = _camera_positions(viewmats) if rigid_viewmats else torch.inverse(viewmats)[:, :3, 3]
-        if pull_colors:
+        if sh_pair is not None:
+            colors = view_colors_from_sh_split(sh_degree, means, campos, sh_pair[0], sh_pair[1], radii)
+        elif pull_colors:
             colors = _peer.view_colors_from_sh_sharded(sh_degree, means, campos, colors_local, radii, n_block, published)
         elif not packed and colors.dim() == 3:
             # dense layout, per-Gaussian coefficients: one fused kernel (dirs, SH, +0.5, clamp)

@@ -116,6 +116,20 @@ int gsb200_sh_view_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, cons
                        const float *v_colors, float *v_coeffs, float *v_means, float *v_campos,
                        gsb200_stream_t stream);
 
+/* Split-coefficient form of the two calls above: the DC band sh0 [N,1,3] and the higher bands shN [N,K-1,3]
+ * stay two arrays (the trainers' parameters, examples/simple_trainer.py:776 concatenates them every step only
+ * to build the [N,K,3] argument of rasterization(); gsplat/rendering.py:386 then consumes that copy).  K counts
+ * sh0 too, K - 1 <= GSB200_SH_SPLIT_MAX_REST.  The backward overwrites v_sh0 [N,1,3] and v_shN [N,K-1,3]
+ * (16-byte aligned; zero rows for invisible Gaussians and unused bands included), v_means / v_campos as above. */
+#define GSB200_SH_SPLIT_MAX_REST 31
+int gsb200_sh_view_split_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                             const float *campos, const float *sh0, const float *shN, const int32_t *radii,
+                             float *colors, gsb200_stream_t stream);
+int gsb200_sh_view_split_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                             const float *campos, const float *sh0, const float *shN, const int32_t *radii,
+                             const float *v_colors, float *v_sh0, float *v_shN, float *v_means,
+                             float *v_campos, gsb200_stream_t stream);
+
 /* View-parallel multi-GPU form of the same stage.  The reference all-gathers / all-to-alls whole attribute
  * tensors between ranks around these ops (rendering.py:282-294, 397-478; distributed.py:90-215).  Here the SH
  * coefficients -- 16x3 floats per Gaussian, the bulk of the exchange -- stay on their owner: rank r publishes
