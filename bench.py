@@ -174,7 +174,9 @@ def run_ours(args):
         new, bits = sim.simulate_compression(params, sim_step, fuse_activations=True)
         scales = new["scales_act"] if "scales_act" in new else torch.exp(new["scales"])
         opac = new["opacities_act"] if "opacities_act" in new else torch.sigmoid(new["opacities"])
-        colors = torch.cat([new["sh0"], new["shN"]], 1)
+        # additive fusion hook: hand the two SH parameters over as a pair instead of the trainer's
+        # torch.cat([sh0, shN], 1) (examples/simple_trainer.py:776); --cat-colors keeps the reference's call
+        colors = torch.cat([new["sh0"], new["shN"]], 1) if args.cat_colors else (new["sh0"], new["shN"])
         rc, ra, meta = gs.rasterization(new["means"], new["quats"], scales, opac, colors, viewmat, K, W_IMG, H_IMG,
                                         sh_degree=3, packed=False, near_plane=0.01, far_plane=100.0, radius_clip=3.0,
                                         distributed=world > 1)
@@ -279,7 +281,9 @@ def run_ours(args):
                              if args.workload == "m1" else
                              f"M2: load_test_data(scene_grid={args.scene_grid}) {n_total} Gaussians, 1 view 1920x1080 per GPU, "
                              "SH deg 3, 8-bit noise fake-quant (scales,quats,opacities,sh0) fused with exp/sigmoid, "
-                             "packed=False, L1 loss, fwd+bwd to raw params" + (", factorized entropy model on" if args.entropy else "")),
+                             "packed=False, L1 loss, fwd+bwd to raw params"
+                             + (", colors=torch.cat([sh0, shN], 1)" if args.cat_colors or world > 1 else ", colors=(sh0, shN) pair")
+                             + (", factorized entropy model on" if args.entropy else "")),
                 "n_isects": n_isects, "l2": "inputs larger than L2 (236 MB of splat attributes + 25 MB image per step)",
                 "parallelism": (f"view-parallel x{world} (each rank renders view 0 from the all-gathered attributes of "
                                 f"{world} Gaussian shards; gradients reduce-scattered to the owners)") if world > 1 else "single GPU",
@@ -382,6 +386,8 @@ def main():
     ap.add_argument("--workload", choices=["m2", "m1"], default="m2", help="m2 = headline (quant-sim + SH), m1 = profiling/main.py")
     ap.add_argument("--packed", action="store_true", help="m1 only: packed=True (the reference API default)")
     ap.add_argument("--entropy", action="store_true", help="also run the factorized entropy model on scales/quats/sh0")
+    ap.add_argument("--cat-colors", dest="cat_colors", action="store_true",
+                    help="m2: pass torch.cat([sh0, shN], 1) (the reference trainer's call) instead of the (sh0, shN) pair")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -57,7 +57,19 @@ SIGNATURES = {
     "gsb200_fake_quantize_bwd": [_L, _P, _P, _F, _F, _I, _I, _P, _P, _P],
     "gsb200_entropy_fwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P],
     "gsb200_entropy_bwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P, _P, _P],
+    "gsb200_selective_adam_update": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _U, _U, _P],
+    "gsb200_adam_multi": [_U, _P, _P],
 }
+
+
+class AdamTensor(ctypes.Structure):
+    """struct gsb200_adam_tensor (include/gsb200.h)."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("n", c_int64), ("step_size", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+                ("inv_sqrt_bias2", c_float)]
+
+
+ADAM_MAX_TENSORS = 16  # GSB200_ADAM_MAX_TENSORS
 _RESTYPES = {"gsb200_last_error": c_char_p, "gsb200_launch_count": c_uint64, "gsb200_grad_record": c_uint32}
 
 _lib = None

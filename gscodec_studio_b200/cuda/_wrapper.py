@@ -42,6 +42,40 @@ def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
 
 
 # --------------------------------------------------------------------------------------
+# optimizer step
+# --------------------------------------------------------------------------------------
+def selective_adam_update(
+    param: Tensor,
+    param_grad: Tensor,
+    exp_avg: Tensor,
+    exp_avg_sq: Tensor,
+    tiles_touched: Tensor,
+    lr: float,
+    b1: float,
+    b2: float,
+    eps: float,
+    N: int,
+    M: int,
+) -> None:
+    """In-place Adam update of the rows of `param` [N, M] whose flag in `tiles_touched` (bool [N]) is set
+    (reference: _wrapper.py:19-34 -> adam.cu:13-83; no bias correction)."""
+    param_c, exp_avg_c, exp_avg_sq_c = _f32(param), _f32(exp_avg), _f32(exp_avg_sq)
+    if param_c.data_ptr() != param.data_ptr() or exp_avg_c.data_ptr() != exp_avg.data_ptr() \
+            or exp_avg_sq_c.data_ptr() != exp_avg_sq.data_ptr():
+        raise RuntimeError("selective_adam_update: param / exp_avg / exp_avg_sq must be contiguous (updated in place)")
+    assert param.numel() == N * M and param_grad.numel() == N * M, (param.shape, N, M)
+    assert tiles_touched.numel() == N, tiles_touched.shape
+    grad = param_grad.contiguous()
+    if not grad.is_cuda or grad.dtype != torch.float32:
+        raise RuntimeError("selective_adam_update: param_grad must be a float32 CUDA tensor")
+    vis = tiles_touched.contiguous()
+    vis = vis.view(torch.uint8) if vis.dtype == torch.bool else (vis != 0).view(torch.uint8)
+    with torch.cuda.device(param.device):
+        call("gsb200_selective_adam_update", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(vis), float(lr),
+             float(b1), float(b2), float(eps), N, M, stream_ptr(param.device))
+
+
+# --------------------------------------------------------------------------------------
 # spherical harmonics
 # --------------------------------------------------------------------------------------
 def spherical_harmonics(

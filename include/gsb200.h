@@ -272,6 +272,29 @@ int gsb200_entropy_bwd(int64_t N, uint32_t ch, uint32_t n_hidden, const float *x
                        const float *params, float likelihood_bound, const float *v_bits, float *v_x,
                        float *v_params, gsb200_stream_t stream);
 
+/* ---------------------------------------------------------------- optimizer step
+ * gsb200_selective_adam_update replaces _C.selective_adam_update (ext.cpp, adam.cu:13-83; caller
+ * gsplat/optimizers/selective_adam.py:42-94): param / param_grad / exp_avg / exp_avg_sq are [N, M] row-major,
+ * visibility u8 [N] (NULL = every row); rows with a clear flag keep parameter and moments untouched:
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  param += -lr m / (sqrt(v) + eps)      (no bias correction). */
+int gsb200_selective_adam_update(float *param, const float *param_grad, float *exp_avg, float *exp_avg_sq,
+                                 const uint8_t *visibility, float lr, float b1, float b2, float eps,
+                                 uint32_t N, uint32_t M, gsb200_stream_t stream);
+/* torch.optim.Adam's update (the optimizer examples/simple_trainer.py:396-408 creates per attribute) for up
+ * to GSB200_ADAM_MAX_TENSORS tensors in one launch.  `tensors` is a HOST array; per tensor, with t = step count:
+ *   step_size = lr / (1 - beta1^t),  inv_sqrt_bias2 = 1 / sqrt(1 - beta2^t)
+ *   m = beta1 m + (1-beta1) g;  v = beta2 v + (1-beta2) g^2;  param -= step_size m / (sqrt(v) inv_sqrt_bias2 + eps) */
+#define GSB200_ADAM_MAX_TENSORS 16
+typedef struct gsb200_adam_tensor {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    int64_t n; /* elements */
+    float step_size, beta1, beta2, eps, inv_sqrt_bias2;
+} gsb200_adam_tensor;
+int gsb200_adam_multi(uint32_t n_tensors, const gsb200_adam_tensor *tensors, gsb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,83 @@ def test_rasterization_accepts_sh_pair(packed):
     assert rel_err(rc1, rc2) < 1e-5 and rel_err(ra1, ra2) < 1e-5
     for x, y, name in zip(g1, g2, ("means", "quats", "scales", "opacities", "sh0", "shN")):
         assert rel_err(x, y) < 1e-4, name  # atomics: summation order differs between runs
+
+
+# ------------------------------------------------------------------------------- optimizer step (8f.2)
+def test_selective_adam_matches_reference_semantics():
+    """SelectiveAdam.step(visibility): flagged rows follow adam.cu:31-40 (no bias correction), the other rows keep
+    parameter and moments bit for bit."""
+    from gscodec_studio_b200.optimizers import SelectiveAdam
+
+    g = torch.Generator().manual_seed(11)
+    for shape in [(1000, 3), (777, 1, 3), (513,), (301, 15, 3), (5, 4)]:
+        N = shape[0]
+        p0 = torch.randn(*shape, generator=g)
+        param = torch.nn.Parameter(p0.clone().to(DEV))
+        opt = SelectiveAdam([{"params": param, "lr": 1.6e-4, "name": "x"}], eps=1e-15, betas=(0.9, 0.999))
+        p, m, v = p0.double(), torch.zeros_like(p0).double(), torch.zeros_like(p0).double()
+        for step in range(3):
+            grad = torch.randn(*shape, generator=g) * 10 ** float(torch.randint(-6, 1, (1,), generator=g))
+            vis = torch.rand(N, generator=g) > 0.5
+            param.grad = grad.clone().to(DEV)
+            before = param.detach().clone()
+            opt.step(vis.to(DEV))
+            gd = grad.double()
+            sel = vis.view(-1, *([1] * (len(shape) - 1))).expand(*shape)
+            m = torch.where(sel, 0.9 * m + (1 - 0.9) * gd, m)
+            v = torch.where(sel, 0.999 * v + (1 - 0.999) * gd * gd, v)
+            p = torch.where(sel, p - 1.6e-4 * m / (v.sqrt() + 1e-15), p)
+            assert torch.equal(param.detach()[~vis.to(DEV)], before[~vis.to(DEV)])
+            st = opt.state[param]
+            assert rel_err(st["exp_avg"], m) < 1e-6 and rel_err(st["exp_avg_sq"], v) < 1e-6
+            assert (param.detach().double().cpu() - p).abs().max().item() < 1e-6 * p.abs().max().item()  # a step is ~5e-4
+
+
+def test_grouped_adam_matches_torch_adam():
+    """GroupedAdam == torch.optim.Adam (per-group lr / betas / eps, bias correction) over several steps, for
+    aligned, ragged (n % 4 != 0), tiny and 4-byte-offset tensors, all in one launch per step."""
+    from gscodec_studio_b200.optimizers import GroupedAdam
+
+    g = torch.Generator().manual_seed(12)
+    shapes = [(1001, 3), (640, 4), (333,), (200, 15, 3), (3,), (1,), (64, 1, 3)]
+    lrs = [1.6e-4, 1e-3, 5e-2, 1.25e-4, 1e-3, 1e-2, 2.5e-3]
+    init = [torch.randn(*s, generator=g) for s in shapes]
+    offset_store = torch.zeros(1025, device=DEV)  # a parameter whose storage is only 4-byte aligned
+    init.append(torch.randn(1024, generator=g))
+    lrs.append(3e-3)
+
+    def make(dev):
+        ps = [torch.nn.Parameter(t.clone().to(dev)) for t in init[:-1]]
+        if dev == DEV:
+            last = offset_store[1:]
+            last.copy_(init[-1].to(dev))
+            assert last.data_ptr() % 16 != 0
+            ps.append(torch.nn.Parameter(last))
+        else:
+            ps.append(torch.nn.Parameter(init[-1].clone().double()))
+        return ps
+
+    ours = make(DEV)
+    ref = [torch.nn.Parameter(p.detach().double()) for p in make("cpu")]
+    groups = lambda ps: [{"params": [p], "lr": lr, "name": str(i)} for i, (p, lr) in enumerate(zip(ps, lrs))]
+    opt_a = GroupedAdam(groups(ours), eps=1e-15, betas=(0.9, 0.999))
+    opt_b = torch.optim.Adam(groups(ref), eps=1e-15, betas=(0.9, 0.999))
+    opt_a.param_groups[1]["betas"] = opt_b.param_groups[1]["betas"] = (0.8, 0.99)
+    opt_a.param_groups[2]["eps"] = opt_b.param_groups[2]["eps"] = 1e-8
+    for step in range(4):
+        for pa, pb in zip(ours, ref):
+            grad = torch.randn(*pb.shape, generator=g) * 10 ** float(torch.randint(-5, 1, (1,), generator=g))
+            if step == 2:
+                grad[::3] = 0.0
+            pa.grad = grad.to(DEV)
+            pb.grad = grad.double()
+        opt_a.step()
+        opt_b.step()
+        for i, (pa, pb, lr) in enumerate(zip(ours, ref, lrs)):
+            sa, sb = opt_a.state[pa], opt_b.state[pb]
+            assert float(sa["step"]) == float(sb["step"]) == step + 1
+            assert rel_err(sa["exp_avg"], sb["exp_avg"]) < 1e-6, i
+            assert rel_err(sa["exp_avg_sq"], sb["exp_avg_sq"]) < 1e-6, i
+            # an Adam step moves a parameter by ~lr; fp32 keeps ~1e-7 relative of the parameter itself per step
+            tol = lr * 1e-4 + 1e-6 * pb.abs().max().item()
+            assert (pa.detach().double().cpu() - pb.detach()).abs().max().item() < tol, (i, step)
