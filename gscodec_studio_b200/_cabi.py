@@ -59,6 +59,9 @@ SIGNATURES = {
     "gsb200_entropy_bwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P, _P, _P],
     "gsb200_selective_adam_update": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _U, _U, _P],
     "gsb200_adam_multi": [_U, _P, _P],
+    "gsb200_photometric_workspace_bytes": [],
+    "gsb200_photometric_loss_fwd": [_U, _U, _U, _U, _P, _P, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_photometric_loss_bwd": [_U, _U, _U, _U, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P],
 }
 
 
@@ -70,7 +73,8 @@ class AdamTensor(ctypes.Structure):
 
 
 ADAM_MAX_TENSORS = 16  # GSB200_ADAM_MAX_TENSORS
-_RESTYPES = {"gsb200_last_error": c_char_p, "gsb200_launch_count": c_uint64, "gsb200_grad_record": c_uint32}
+_RESTYPES = {"gsb200_last_error": c_char_p, "gsb200_launch_count": c_uint64, "gsb200_grad_record": c_uint32,
+             "gsb200_photometric_workspace_bytes": c_uint64}
 
 _lib = None
 

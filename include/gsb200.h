@@ -295,6 +295,28 @@ typedef struct gsb200_adam_tensor {
 } gsb200_adam_tensor;
 int gsb200_adam_multi(uint32_t n_tensors, const gsb200_adam_tensor *tensors, gsb200_stream_t stream);
 
+/* ---------------------------------------------------------------- photometric loss
+ * replaces the loss chain of examples/simple_trainer.py:948-953: F.l1_loss + (1 - fused_ssim(..., padding="valid")),
+ * where fused_ssim is the un-vendored dependency pinned at examples/requirements.txt:26 (rahul-goel/fused-ssim@1272e21a;
+ * 11-tap Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2, gradient to the first image only).
+ * img1 (rendered) / img2 (target) are [B,H,W,CH] -- the renderer's layout, no NCHW permute copy.
+ *   out[0] = coef_l1 * mean|img1 - img2| + coef_ssim * mean(ssim map) + bias;  stats (2 floats, may be NULL) = the L1
+ *   mean and the SSIM mean
+ *   (trainer loss: coef_l1 = 1 - lambda, coef_ssim = -lambda, bias = lambda; plain fused_ssim: 0, 1, 0)
+ * padding_valid != 0 averages the SSIM map without its 5-pixel border (padding="valid"), else over all pixels.
+ * map_mu / map_s1 / map_s12 [B,H,W,CH]: derivative maps saved for the backward (all NULL = inference only).
+ * workspace: gsb200_photometric_workspace_bytes() bytes of device memory, 8-byte aligned (zeroed by the call).
+ * bwd: v_img1 [B,H,W,CH] is overwritten with v_loss[0] * d out[0] / d img1 (v_loss is a DEVICE scalar). */
+uint64_t gsb200_photometric_workspace_bytes(void);
+int gsb200_photometric_loss_fwd(uint32_t B, uint32_t H, uint32_t W, uint32_t CH, const float *img1,
+                                const float *img2, float coef_l1, float coef_ssim, float bias,
+                                int padding_valid, float *map_mu, float *map_s1, float *map_s12,
+                                void *workspace, float *out, float *stats, gsb200_stream_t stream);
+int gsb200_photometric_loss_bwd(uint32_t B, uint32_t H, uint32_t W, uint32_t CH, const float *img1,
+                                const float *img2, float coef_l1, float coef_ssim, int padding_valid,
+                                const float *map_mu, const float *map_s1, const float *map_s12,
+                                const float *v_loss, float *v_img1, gsb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -505,3 +505,64 @@ def entropy_factorized_bits(x: Tensor, q: float, matrices, biases, factors, like
     lik = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
     lik = _LowerBound.apply(lik, likelihood_bound)
     return (-torch.log2(lik)).t()
+
+
+# --------------------------------------------------------------------------------------
+# photometric loss: L1 + SSIM, examples/simple_trainer.py:948-953
+# --------------------------------------------------------------------------------------
+# PARITY UNPINNED: `fused_ssim` is a third-party dependency that is absent from /root/reference
+# (examples/requirements.txt:26 pins rahul-goel/fused-ssim@1272e21a) and the reference holds no test or golden
+# vector for it.  Restated from its published algorithm: SSIM (Wang et al. 2004) with an 11-tap Gaussian window of
+# sigma 1.5 applied separably with ZERO padding, C1 = 0.01^2, C2 = 0.03^2, per channel; padding="valid" drops the
+# 5-pixel border of the map before the mean; only the first image receives a gradient.  tests/test_oracle_golden.py
+# checks this restatement against a brute-force float64 evaluation of the definition and by finite differences.
+def ssim_window(dtype=torch.float64) -> Tensor:
+    d = torch.arange(11, dtype=torch.float64) - 5
+    g = torch.exp(-(d * d) / (2 * 1.5 * 1.5))
+    return (g / g.sum()).to(dtype)
+
+
+def ssim_map(img1: Tensor, img2: Tensor) -> Tensor:
+    """SSIM map [B,CH,H,W] of [B,CH,H,W] images (zero-padded Gaussian window, "same" size)."""
+    B, CH, H, W = img1.shape
+    w1 = ssim_window(img1.dtype)
+    win = (w1[:, None] * w1[None, :]).expand(CH, 1, 11, 11).contiguous()
+
+    def blur(t):
+        return F.conv2d(t, win, padding=5, groups=CH)
+
+    mu1, mu2 = blur(img1), blur(img2)
+    s1 = blur(img1 * img1) - mu1 * mu1
+    s2 = blur(img2 * img2) - mu2 * mu2
+    s12 = blur(img1 * img2) - mu1 * mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    return ((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2))
+
+
+def fused_ssim(img1: Tensor, img2: Tensor, padding: str = "same") -> Tensor:
+    """Mean SSIM of [B,CH,H,W] images; the second image is treated as a constant."""
+    m = ssim_map(img1, img2.detach())
+    if padding == "valid":
+        m = m[:, :, 5:-5, 5:-5]
+    return m.mean()
+
+
+def photometric_loss(colors: Tensor, pixels: Tensor, ssim_lambda: float = 0.2, padding: str = "valid") -> Tensor:
+    """The trainer's loss on [B,H,W,CH] images (examples/simple_trainer.py:948-953)."""
+    l1 = (colors - pixels).abs().mean()
+    ssim = fused_ssim(colors.permute(0, 3, 1, 2), pixels.permute(0, 3, 1, 2), padding)
+    return l1 * (1.0 - ssim_lambda) + (1.0 - ssim) * ssim_lambda
+
+
+# --------------------------------------------------------------------------------------
+# optimizer step (SURVEY.md 8f.2): gsplat/cuda/csrc/adam.cu:13-43
+# --------------------------------------------------------------------------------------
+def selective_adam_update(param, grad, exp_avg, exp_avg_sq, visible, lr, b1, b2, eps):
+    """In-place reference update of the rows flagged in `visible` [N] (no bias correction, adam.cu:31-40)."""
+    sel = visible.view(-1, *([1] * (param.dim() - 1))).expand_as(param)
+    m = b1 * exp_avg + (1.0 - b1) * grad
+    v = b2 * exp_avg_sq + (1.0 - b2) * grad * grad
+    step = -lr * m / (v.sqrt() + eps)
+    param.copy_(torch.where(sel, param + step, param))
+    exp_avg.copy_(torch.where(sel, m, exp_avg))
+    exp_avg_sq.copy_(torch.where(sel, v, exp_avg_sq))

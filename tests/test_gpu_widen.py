@@ -167,3 +167,69 @@ def test_grouped_adam_matches_torch_adam():
             # an Adam step moves a parameter by ~lr; fp32 keeps ~1e-7 relative of the parameter itself per step
             tol = lr * 1e-4 + 1e-6 * pb.abs().max().item()
             assert (pa.detach().double().cpu() - pb.detach()).abs().max().item() < tol, (i, step)
+
+
+# ------------------------------------------------------------------------------- photometric loss (8f.2)
+@pytest.mark.parametrize("shape", [(1, 37, 53, 3), (2, 16, 16, 1), (1, 70, 33, 4), (3, 11, 40, 3)])
+@pytest.mark.parametrize("padding", ["valid", "same"])
+def test_photometric_loss_matches_oracle(shape, padding):
+    """photometric_loss == (1-l) L1 + l (1 - fused_ssim) of the float64 oracle, value and gradient, on image
+    sizes that are not multiples of the 16x16 tile (and one barely larger than the 11-tap window)."""
+    from gscodec_studio_b200.losses import photometric_loss
+
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.rand(*shape, generator=g)
+    y = (x + 0.3 * torch.randn(*shape, generator=g)).clamp(0, 1)
+    y[0, :5] = x[0, :5]  # exact ties: sign(0) = 0 in the L1 term
+    a = x.clone().to(DEV).requires_grad_(True)
+    b = x.clone().double().requires_grad_(True)
+    (loss, stats) = photometric_loss(a, y.to(DEV), 0.2, padding, return_stats=True)
+    ref = O.photometric_loss(b, y.double(), 0.2, padding)
+    assert abs(loss.item() - ref.item()) < 2e-6
+    assert abs(stats[0].item() - (b - y.double()).abs().mean().item()) < 1e-6
+    (loss * 3.0).backward()
+    (ref * 3.0).backward()
+    assert rel_err(a.grad, b.grad) < 2e-4
+
+
+def test_fused_ssim_signature_and_permuted_views():
+    """fused_ssim(img1, img2, padding, train) on [B,CH,H,W] inputs, both truly contiguous NCHW and the permuted
+    NHWC views the trainers pass; train=False gives the value without a graph."""
+    from gscodec_studio_b200.losses import fused_ssim
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 45, 38, 3, generator=g)
+    y = (x + 0.1 * torch.randn(2, 45, 38, 3, generator=g)).clamp(0, 1)
+    ref_in = x.clone().double().requires_grad_(True)
+    ref = O.fused_ssim(ref_in.permute(0, 3, 1, 2), y.double().permute(0, 3, 1, 2), "valid")
+    ref.backward()
+    a = x.clone().to(DEV).requires_grad_(True)
+    v1 = fused_ssim(a.permute(0, 3, 1, 2), y.to(DEV).permute(0, 3, 1, 2), padding="valid")
+    v1.backward()
+    assert abs(v1.item() - ref.item()) < 2e-6 and rel_err(a.grad, ref_in.grad) < 2e-4
+    c = x.permute(0, 3, 1, 2).contiguous().to(DEV).requires_grad_(True)  # real NCHW memory
+    v2 = fused_ssim(c, y.permute(0, 3, 1, 2).contiguous().to(DEV), padding="valid")
+    v2.backward()
+    assert abs(v2.item() - ref.item()) < 2e-6 and rel_err(c.grad.permute(0, 2, 3, 1), ref_in.grad) < 2e-4
+    v3 = fused_ssim(c.detach(), y.permute(0, 3, 1, 2).contiguous().to(DEV), padding="same", train=False)
+    assert abs(v3.item() - O.fused_ssim(x.double().permute(0, 3, 1, 2), y.double().permute(0, 3, 1, 2), "same").item()) < 2e-6
+    same = fused_ssim(c.detach(), c.detach())
+    assert abs(same.item() - 1.0) < 1e-5
+
+
+def test_photometric_loss_full_frame_properties():
+    """1080p x 3 channels (the headline frame): loss of an image against itself is exactly the bias-free 0 and its
+    SSIM is 1; the loss equals the value assembled from its parts; gradient of a constant shift has the L1 sign."""
+    from gscodec_studio_b200.losses import photometric_loss
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(1, 1080, 1920, 3, generator=g, device=DEV)
+    loss, stats = photometric_loss(x, x.clone(), 0.2, return_stats=True)
+    assert abs(loss.item()) < 1e-6 and stats[0].item() == 0.0 and abs(stats[1].item() - 1.0) < 1e-6
+    y = (x + 0.05).clamp(0, 1)
+    xr = x.clone().requires_grad_(True)
+    loss, stats = photometric_loss(xr, y, 0.2, return_stats=True)
+    assert abs(loss.item() - (0.8 * stats[0].item() + 0.2 * (1 - stats[1].item()))) < 1e-6
+    assert abs(stats[0].item() - (x - y).abs().mean().item()) < 1e-6
+    loss.backward()
+    assert torch.isfinite(xr.grad).all() and xr.grad.abs().max().item() < 1e-3

@@ -186,3 +186,53 @@ def test_oracle_projection_backward_matches_reference_cuda(golden_dir):
     ((m2d * g["v_means2d"] * keep[..., None]).sum() + (con * g["v_conics"] * keep[..., None]).sum()).backward()
     for name, t in (("v_means", m), ("v_quats", q), ("v_scales", s), ("v_viewmats", v)):
         _close(t.grad, g[name], 1e-3, frac=1e-4, cap=3e-2)
+
+
+# ------------------------------------------------------------------------------- photometric loss oracle
+def test_ssim_oracle_matches_bruteforce_definition():
+    """The conv-based SSIM restatement against a brute-force float64 evaluation of the definition (explicit
+    zero-padded 11x11 Gaussian-weighted moments per pixel), for "same" and "valid" averaging; SSIM(x, x) = 1."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(0)
+    B, CH, H, W = 1, 2, 17, 23
+    x = rng.random((B, CH, H, W))
+    y = np.clip(x + 0.2 * rng.standard_normal((B, CH, H, W)), 0, 1)
+    d = np.arange(11) - 5.0
+    g = np.exp(-d * d / (2 * 1.5 ** 2))
+    g /= g.sum()
+    w2 = np.outer(g, g)
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ref = np.zeros((B, CH, H, W))
+    for b in range(B):
+        for c in range(CH):
+            xp = np.pad(x[b, c], 5)
+            yp = np.pad(y[b, c], 5)
+            for i in range(H):
+                for j in range(W):
+                    a, e = xp[i:i + 11, j:j + 11], yp[i:i + 11, j:j + 11]
+                    mu1, mu2 = (w2 * a).sum(), (w2 * e).sum()
+                    s1, s2 = (w2 * a * a).sum() - mu1 ** 2, (w2 * e * e).sum() - mu2 ** 2
+                    s12 = (w2 * a * e).sum() - mu1 * mu2
+                    ref[b, c, i, j] = (2 * mu1 * mu2 + C1) * (2 * s12 + C2) / ((mu1 ** 2 + mu2 ** 2 + C1) * (s1 + s2 + C2))
+    tx, ty = torch.from_numpy(x), torch.from_numpy(y)
+    got = O.ssim_map(tx, ty).numpy()
+    assert np.abs(got - ref).max() < 1e-12
+    assert abs(O.fused_ssim(tx, ty, "same").item() - ref.mean()) < 1e-12
+    assert abs(O.fused_ssim(tx, ty, "valid").item() - ref[:, :, 5:-5, 5:-5].mean()) < 1e-12
+    assert abs(O.fused_ssim(tx, tx, "valid").item() - 1.0) < 1e-12
+
+
+def test_photometric_oracle_gradient_by_finite_differences():
+    from oracle import oracle as O
+
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(1, 14, 13, 3, generator=g, dtype=torch.float64).requires_grad_(True)
+    y = torch.rand(1, 14, 13, 3, generator=g, dtype=torch.float64)
+    assert torch.autograd.gradcheck(lambda t: O.photometric_loss(t, y, 0.2, "valid"), (x,), eps=1e-6, atol=1e-7)
+    loss = O.photometric_loss(x, y, 0.2, "valid")
+    l1 = (x - y).abs().mean()
+    ssim = O.fused_ssim(x.permute(0, 3, 1, 2), y.permute(0, 3, 1, 2), "valid")
+    assert abs(loss.item() - (0.8 * l1.item() + 0.2 * (1 - ssim.item()))) < 1e-14
