@@ -9,8 +9,12 @@ from .cuda._wrapper import (  # noqa: F401
     fully_fused_projection,
     isect_offset_encode,
     isect_tiles,
+    persp_proj,
+    proj,
+    quat_scale_to_covar_preci,
     rasterize_to_pixels,
     spherical_harmonics,
+    world_to_cam,
 )
 from .rendering import rasterization  # noqa: F401
 from . import distributed  # noqa: F401
@@ -23,5 +27,9 @@ __all__ = [
     "isect_offset_encode",
     "rasterize_to_pixels",
     "spherical_harmonics",
+    "quat_scale_to_covar_preci",
+    "proj",
+    "persp_proj",
+    "world_to_cam",
     "distributed",
 ]

@@ -59,6 +59,12 @@ SIGNATURES = {
     "gsb200_entropy_bwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P, _P, _P],
     "gsb200_selective_adam_update": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _U, _U, _P],
     "gsb200_adam_multi": [_U, _P, _P],
+    "gsb200_quat_scale_to_covar_preci_fwd": [_U, _P, _P, _I, _P, _P, _P],
+    "gsb200_quat_scale_to_covar_preci_bwd": [_U, _P, _P, _I, _P, _P, _P, _P, _P],
+    "gsb200_proj_fwd": [_U, _U, _P, _P, _P, _U, _U, _I, _P, _P, _P],
+    "gsb200_proj_bwd": [_U, _U, _P, _P, _P, _U, _U, _I, _P, _P, _P, _P, _P],
+    "gsb200_world_to_cam_fwd": [_U, _U, _P, _P, _P, _P, _P, _P],
+    "gsb200_world_to_cam_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_photometric_workspace_bytes": [],
     "gsb200_photometric_loss_fwd": [_U, _U, _U, _U, _P, _P, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_photometric_loss_bwd": [_U, _U, _U, _U, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P],

@@ -213,6 +213,151 @@ class _ShViewSplit(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------
+# un-fused geometry ops (reference: _wrapper.py:76-200, autograd classes :646-772)
+# --------------------------------------------------------------------------------------
+def quat_scale_to_covar_preci(
+    quats: Tensor,  # [N, 4],
+    scales: Tensor,  # [N, 3],
+    compute_covar: bool = True,
+    compute_preci: bool = True,
+    triu: bool = False,
+) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """Converts quaternions (wxyz, need not be normalised) and scales to covariance and precision matrices:
+    [N,3,3] each, or [N,6] (upper triangle) if `triu`; a matrix that is not asked for is returned as None."""
+    assert quats.dim() == 2 and quats.size(1) == 4, quats.size()
+    assert scales.dim() == 2 and scales.size(1) == 3, scales.size()
+    covars, precis = _QuatScaleToCovarPreci.apply(quats.contiguous(), scales.contiguous(), compute_covar, compute_preci, triu)
+    return covars if compute_covar else None, precis if compute_preci else None
+
+
+class _QuatScaleToCovarPreci(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, quats, scales, compute_covar, compute_preci, triu):
+        quats, scales = _f32(quats), _f32(scales)
+        N, dev = quats.shape[0], quats.device
+        shape = (N, 6) if triu else (N, 3, 3)
+        covars = torch.empty(shape, dtype=torch.float32, device=dev) if compute_covar else None
+        precis = torch.empty(shape, dtype=torch.float32, device=dev) if compute_preci else None
+        with torch.cuda.device(dev):
+            call("gsb200_quat_scale_to_covar_preci_fwd", N, ptr(quats), ptr(scales), int(triu), ptr(covars), ptr(precis),
+                 stream_ptr(dev))
+        ctx.save_for_backward(quats, scales)
+        ctx.flags = (compute_covar, compute_preci, triu)
+        return covars, precis
+
+    @staticmethod
+    def backward(ctx, v_covars, v_precis):
+        quats, scales = ctx.saved_tensors
+        compute_covar, compute_preci, triu = ctx.flags
+        v_covars = _f32(_dense(v_covars)) if compute_covar and v_covars is not None else None
+        v_precis = _f32(_dense(v_precis)) if compute_preci and v_precis is not None else None
+        v_quats, v_scales = torch.empty_like(quats), torch.empty_like(scales)
+        with torch.cuda.device(quats.device):
+            call("gsb200_quat_scale_to_covar_preci_bwd", quats.shape[0], ptr(quats), ptr(scales), int(triu), ptr(v_covars),
+                 ptr(v_precis), ptr(v_quats), ptr(v_scales), stream_ptr(quats.device))
+        return v_quats, v_scales, None, None, None
+
+
+def _dense(t: Tensor) -> Tensor:
+    return (t.to_dense() if t.is_sparse else t).contiguous()
+
+
+def persp_proj(means: Tensor, covars: Tensor, Ks: Tensor, width: int, height: int) -> Tuple[Tensor, Tensor]:
+    """Perspective projection on Gaussians.  DEPRECATED: please use `proj` with the pinhole camera model instead."""
+    import warnings
+
+    warnings.warn("persp_proj is deprecated and will be removed in a future release. Use proj with ortho=False instead.",
+                  DeprecationWarning)
+    return proj(means, covars, Ks, width, height, camera_model="pinhole")
+
+
+def proj(
+    means: Tensor,  # [C, N, 3]
+    covars: Tensor,  # [C, N, 3, 3]
+    Ks: Tensor,  # [C, 3, 3]
+    width: int,
+    height: int,
+    camera_model: Literal["pinhole", "ortho", "fisheye"] = "pinhole",
+) -> Tuple[Tensor, Tensor]:
+    """Projection of camera-space Gaussians -> (means2d [C,N,2], covars2d [C,N,2,2])."""
+    C, N, _ = means.shape
+    assert means.shape == (C, N, 3), means.size()
+    assert covars.shape == (C, N, 3, 3), covars.size()
+    assert Ks.shape == (C, 3, 3), Ks.size()
+    if camera_model not in _CAMERA_MODELS:
+        raise ValueError(f"Unsupported camera model: {camera_model}")
+    return _Proj.apply(means.contiguous(), covars.contiguous(), Ks.contiguous(), width, height, camera_model)
+
+
+class _Proj(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, covars, Ks, width, height, camera_model):
+        means, covars, Ks = _f32(means), _f32(covars), _f32(Ks)
+        C, N, dev = means.shape[0], means.shape[1], means.device
+        means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
+        covars2d = torch.empty((C, N, 2, 2), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("gsb200_proj_fwd", C, N, ptr(means), ptr(covars), ptr(Ks), width, height, _CAMERA_MODELS[camera_model],
+                 ptr(means2d), ptr(covars2d), stream_ptr(dev))
+        ctx.save_for_backward(means, covars, Ks)
+        ctx.args = (width, height, camera_model)
+        return means2d, covars2d
+
+    @staticmethod
+    def backward(ctx, v_means2d, v_covars2d):
+        means, covars, Ks = ctx.saved_tensors
+        width, height, camera_model = ctx.args
+        C, N, dev = means.shape[0], means.shape[1], means.device
+        v_means2d, v_covars2d = _f32(v_means2d.contiguous()), _f32(v_covars2d.contiguous())
+        v_means, v_covars = torch.empty_like(means), torch.empty_like(covars)
+        with torch.cuda.device(dev):
+            call("gsb200_proj_bwd", C, N, ptr(means), ptr(covars), ptr(Ks), width, height, _CAMERA_MODELS[camera_model],
+                 ptr(v_means2d), ptr(v_covars2d), ptr(v_means), ptr(v_covars), stream_ptr(dev))
+        return v_means, v_covars, None, None, None, None
+
+
+def world_to_cam(
+    means: Tensor,  # [N, 3]
+    covars: Tensor,  # [N, 3, 3]
+    viewmats: Tensor,  # [C, 4, 4]
+) -> Tuple[Tensor, Tensor]:
+    """Transforms Gaussians from world to camera space -> (means_c [C,N,3], covars_c [C,N,3,3])."""
+    C = viewmats.size(0)
+    N = means.size(0)
+    assert means.size() == (N, 3), means.size()
+    assert covars.size() == (N, 3, 3), covars.size()
+    assert viewmats.size() == (C, 4, 4), viewmats.size()
+    return _WorldToCam.apply(means.contiguous(), covars.contiguous(), viewmats.contiguous())
+
+
+class _WorldToCam(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, covars, viewmats):
+        means, covars, viewmats = _f32(means), _f32(covars), _f32(viewmats)
+        C, N, dev = viewmats.shape[0], means.shape[0], means.device
+        means_c = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+        covars_c = torch.empty((C, N, 3, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            call("gsb200_world_to_cam_fwd", C, N, ptr(means), ptr(covars), ptr(viewmats), ptr(means_c), ptr(covars_c),
+                 stream_ptr(dev))
+        ctx.save_for_backward(means, covars, viewmats)
+        return means_c, covars_c
+
+    @staticmethod
+    def backward(ctx, v_means_c, v_covars_c):
+        means, covars, viewmats = ctx.saved_tensors
+        C, N, dev = viewmats.shape[0], means.shape[0], means.device
+        v_means_c, v_covars_c = _f32(v_means_c.contiguous()), _f32(v_covars_c.contiguous())
+        v_means = torch.empty_like(means) if ctx.needs_input_grad[0] else None
+        v_covars = torch.empty_like(covars) if ctx.needs_input_grad[1] else None
+        v_viewmats = torch.empty_like(viewmats) if ctx.needs_input_grad[2] else None
+        with torch.cuda.device(dev):
+            call("gsb200_world_to_cam_bwd", C, N, ptr(means), ptr(covars), ptr(viewmats), ptr(v_means_c), ptr(v_covars_c),
+                 ptr(v_means), ptr(v_covars), ptr(v_viewmats), stream_ptr(dev))
+        return v_means, v_covars, v_viewmats
+
+
+# --------------------------------------------------------------------------------------
 # projection
 # --------------------------------------------------------------------------------------
 def fully_fused_projection(

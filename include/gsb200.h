@@ -317,6 +317,38 @@ int gsb200_photometric_loss_bwd(uint32_t B, uint32_t H, uint32_t W, uint32_t CH,
                                 const float *map_mu, const float *map_s1, const float *map_s12,
                                 const float *v_loss, float *v_img1, gsb200_stream_t stream);
 
+/* ---------------------------------------------------------------- un-fused geometry ops
+ * The projection stage as separate differentiable pieces, exported by gsplat/__init__.py:7-20 and tested by
+ * the reference's tests/test_basic.py:53-173.  Covariances are FULL row-major matrices (need not be symmetric).
+ *
+ * replaces _C.quat_scale_to_covar_preci_fwd / _bwd (bindings.h, quat_scale_to_covar_preci_{fwd,bwd}.cu):
+ * quats [N,4] wxyz (normalised inside), scales [N,3]; covars / precis [N,3,3], or [N,6] (xx,xy,xz,yy,yz,zz) when
+ * triu != 0; either output may be NULL.  bwd: v_covars / v_precis in the same layout (NULL = no gradient from it);
+ * a packed off-diagonal gradient counts half for each mirrored entry.  v_quats [N,4], v_scales [N,3] overwritten. */
+int gsb200_quat_scale_to_covar_preci_fwd(uint32_t N, const float *quats, const float *scales, int triu,
+                                         float *covars, float *precis, gsb200_stream_t stream);
+int gsb200_quat_scale_to_covar_preci_bwd(uint32_t N, const float *quats, const float *scales, int triu,
+                                         const float *v_covars, const float *v_precis, float *v_quats,
+                                         float *v_scales, gsb200_stream_t stream);
+/* replaces _C.proj_fwd / _C.proj_bwd (proj_{fwd,bwd}.cu, include/proj.cuh): camera-space means [C,N,3] and covars
+ * [C,N,3,3], Ks [C,3,3] -> means2d [C,N,2], covars2d [C,N,2,2] = J covar J^T for the pinhole (with the reference's
+ * field-of-view clamp of the Jacobian), orthographic or fisheye model. */
+int gsb200_proj_fwd(uint32_t C, uint32_t N, const float *means, const float *covars, const float *Ks,
+                    uint32_t width, uint32_t height, int camera_model, float *means2d, float *covars2d,
+                    gsb200_stream_t stream);
+int gsb200_proj_bwd(uint32_t C, uint32_t N, const float *means, const float *covars, const float *Ks,
+                    uint32_t width, uint32_t height, int camera_model, const float *v_means2d,
+                    const float *v_covars2d, float *v_means, float *v_covars, gsb200_stream_t stream);
+/* replaces _C.world_to_cam_fwd / _bwd (world_to_cam_{fwd,bwd}.cu, include/transform.cuh:9-71): means [N,3], covars
+ * [N,3,3], viewmats [C,4,4] -> means_c [C,N,3] = R p + t, covars_c [C,N,3,3] = R covar R^T.  bwd: v_means [N,3] and
+ * v_covars [N,3,3] (summed over cameras) and v_viewmats [C,4,4] (summed over Gaussians, last row zero) are
+ * overwritten; any of the three may be NULL. */
+int gsb200_world_to_cam_fwd(uint32_t C, uint32_t N, const float *means, const float *covars,
+                            const float *viewmats, float *means_c, float *covars_c, gsb200_stream_t stream);
+int gsb200_world_to_cam_bwd(uint32_t C, uint32_t N, const float *means, const float *covars,
+                            const float *viewmats, const float *v_means_c, const float *v_covars_c,
+                            float *v_means, float *v_covars, float *v_viewmats, gsb200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

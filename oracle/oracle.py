@@ -566,3 +566,73 @@ def selective_adam_update(param, grad, exp_avg, exp_avg_sq, visible, lr, b1, b2,
     param.copy_(torch.where(sel, param + step, param))
     exp_avg.copy_(torch.where(sel, m, exp_avg))
     exp_avg_sq.copy_(torch.where(sel, v, exp_avg_sq))
+
+
+# --------------------------------------------------------------------------------------
+# un-fused geometry ops (SURVEY.md 8f.4), pinned against the reference's _torch_impl.py:41-247 by
+# tests/golden/ref_cpu_geom_ops.npz (generator: oracle/make_golden_geom.py)
+# --------------------------------------------------------------------------------------
+def _triu6(m: Tensor) -> Tensor:
+    """[...,3,3] -> [...,6]: the mean of the mirrored entries (_torch_impl.py:55-59)."""
+    iu, ju = [0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2]
+    return 0.5 * (m[..., iu, ju] + m[..., ju, iu])
+
+
+def quat_scale_to_covar_preci(quats: Tensor, scales: Tensor, compute_covar=True, compute_preci=True, triu=False):
+    R = quat_to_rotmat(quats)
+    covars = precis = None
+    if compute_covar:
+        M = R * scales[..., None, :]
+        covars = M @ M.transpose(-1, -2)
+        covars = _triu6(covars) if triu else covars
+    if compute_preci:
+        P = R / scales[..., None, :]
+        precis = P @ P.transpose(-1, -2)
+        precis = _triu6(precis) if triu else precis
+    return covars, precis
+
+
+def proj(means: Tensor, covars: Tensor, Ks: Tensor, width: int, height: int, camera_model: str = "pinhole"):
+    """Camera-space means [C,N,3] / full covars [C,N,3,3] -> means2d [C,N,2], covars2d [C,N,2,2] = J covar J^T
+    (proj.cuh:9-36 ortho, :80-119 pinhole with the fov clamp of the Jacobian, :202-241 fisheye)."""
+    C, N, _ = means.shape
+    x, y, z = means.unbind(-1)
+    fx, fy = Ks[:, 0, 0, None], Ks[:, 1, 1, None]
+    cx, cy = Ks[:, 0, 2, None], Ks[:, 1, 2, None]
+    O = torch.zeros_like(z)
+    if camera_model == "pinhole":
+        tan_fovx, tan_fovy = 0.5 * width / fx, 0.5 * height / fy
+        lim_xp, lim_xn = (width - cx) / fx + 0.3 * tan_fovx, cx / fx + 0.3 * tan_fovx
+        lim_yp, lim_yn = (height - cy) / fy + 0.3 * tan_fovy, cy / fy + 0.3 * tan_fovy
+        rz = 1.0 / z
+        tx = z * torch.minimum(lim_xp.expand_as(z), torch.maximum(-lim_xn.expand_as(z), x * rz))
+        ty = z * torch.minimum(lim_yp.expand_as(z), torch.maximum(-lim_yn.expand_as(z), y * rz))
+        J = torch.stack([fx * rz, O, -fx * tx * rz * rz, O, fy * rz, -fy * ty * rz * rz], -1)
+        means2d = torch.stack([fx * x * rz + cx, fy * y * rz + cy], -1)
+    elif camera_model == "ortho":
+        J = torch.stack([fx + O, O, O, O, fy + O, O], -1)
+        means2d = torch.stack([fx * x + cx, fy * y + cy], -1)
+    elif camera_model == "fisheye":
+        eps = 1e-7
+        xy_len = torch.sqrt(x * x + y * y) + eps
+        theta = torch.atan2(xy_len, z + eps)
+        means2d = torch.stack([x * fx * theta / xy_len + cx, y * fy * theta / xy_len + cy], -1)
+        x2, y2, xy = x * x + eps, y * y, x * y
+        x2y2 = x2 + y2
+        inv = 1.0 / (x2y2 + z * z)
+        b = torch.atan2(xy_len, z) / xy_len / x2y2
+        a = z * inv / x2y2
+        J = torch.stack([fx * (x2 * a + y2 * b), fx * xy * (a - b), -fx * x * inv,
+                         fy * xy * (a - b), fy * (y2 * a + x2 * b), -fy * y * inv], -1)
+    else:
+        raise ValueError(camera_model)
+    J = J.reshape(C, N, 2, 3)
+    return means2d, J @ covars @ J.transpose(-1, -2)
+
+
+def world_to_cam(means: Tensor, covars: Tensor, viewmats: Tensor):
+    """means_c = R p + t, covars_c = R covar R^T for every camera (transform.cuh:9-49)."""
+    R, t = viewmats[:, :3, :3], viewmats[:, :3, 3]
+    means_c = torch.einsum("cij,nj->cni", R, means) + t[:, None, :]
+    covars_c = torch.einsum("cij,njk,clk->cnil", R, covars, R)
+    return means_c, covars_c

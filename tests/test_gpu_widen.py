@@ -233,3 +233,68 @@ def test_photometric_loss_full_frame_properties():
     assert abs(stats[0].item() - (x - y).abs().mean().item()) < 1e-6
     loss.backward()
     assert torch.isfinite(xr.grad).all() and xr.grad.abs().max().item() < 1e-3
+
+
+# ------------------------------------------------------------------------------- un-fused geometry ops (8f.4)
+def _golden_geom():
+    import numpy as np
+
+    path = os.path.join(ROOT, "tests", "golden", "ref_cpu_geom_ops.npz")
+    return {k: torch.from_numpy(v) if v.ndim else v for k, v in np.load(path).items()}
+
+
+@pytest.mark.parametrize("triu", [False, True])
+def test_quat_scale_to_covar_preci_matches_reference(triu):
+    """Against the reference's _torch_impl._quat_scale_to_covar_preci (golden fixture): values and gradients, both
+    outputs, full and upper-triangular layouts; and each output on its own."""
+    G = _golden_geom()
+    tag = "triu" if triu else "full"
+    q, s = G["quats"].to(DEV).requires_grad_(True), G["scales"].to(DEV).requires_grad_(True)
+    cov, pre = gs.quat_scale_to_covar_preci(q, s, True, True, triu)
+    assert rel_err(cov, G[f"qs_{tag}_covars"]) < 1e-5 and rel_err(pre, G[f"qs_{tag}_precis"]) < 1e-4
+    ((cov * G[f"qs_{tag}_wc"].to(DEV)).sum() + (pre * G[f"qs_{tag}_wp"].to(DEV)).sum()).backward()
+    assert rel_err(q.grad, G[f"qs_{tag}_v_quats"]) < 1e-3 and rel_err(s.grad, G[f"qs_{tag}_v_scales"]) < 1e-3
+    only_c, none_p = gs.quat_scale_to_covar_preci(q.detach(), s.detach(), True, False, triu)
+    none_c, only_p = gs.quat_scale_to_covar_preci(q.detach(), s.detach(), False, True, triu)
+    assert none_p is None and none_c is None
+    assert torch.equal(only_c, cov.detach()) and torch.equal(only_p, pre.detach())
+    q2, s2 = G["quats"].double().requires_grad_(True), G["scales"].double().requires_grad_(True)
+    q3, s3 = G["quats"].to(DEV).requires_grad_(True), G["scales"].to(DEV).requires_grad_(True)
+    w = G[f"qs_{tag}_wc"]
+    (O.quat_scale_to_covar_preci(q2, s2, True, False, triu)[0] * w.double()).sum().backward()
+    (gs.quat_scale_to_covar_preci(q3, s3, True, False, triu)[0] * w.to(DEV)).sum().backward()
+    assert rel_err(q3.grad, q2.grad) < 1e-3 and rel_err(s3.grad, s2.grad) < 1e-3
+
+
+def test_world_to_cam_matches_reference():
+    G = _golden_geom()
+    m, c, v = (G[k].to(DEV).requires_grad_(True) for k in ("w2c_means", "w2c_covars", "w2c_viewmats"))
+    mc, cc = gs.world_to_cam(m, c, v)
+    assert rel_err(mc, G["w2c_means_c"]) < 1e-5 and rel_err(cc, G["w2c_covars_c"]) < 1e-5
+    ((mc * G["w2c_wm"].to(DEV)).sum() + (cc * G["w2c_wc"].to(DEV)).sum()).backward()
+    for t, k in ((m, "w2c_v_means"), (c, "w2c_v_covars"), (v, "w2c_v_viewmats")):
+        assert rel_err(t.grad, G[k]) < 1e-3, k
+    # only some inputs need gradients; more Gaussians than one block
+    g = torch.Generator().manual_seed(9)
+    means, covars = torch.randn(1000, 3, generator=g), torch.randn(1000, 3, 3, generator=g)
+    a = means.to(DEV).requires_grad_(True)
+    b = means.double().requires_grad_(True)
+    o1 = gs.world_to_cam(a, covars.to(DEV), G["w2c_viewmats"].to(DEV))
+    o2 = O.world_to_cam(b, covars.double(), G["w2c_viewmats"].double())
+    (o1[0].sum() + o1[1].sum()).backward()
+    (o2[0].sum() + o2[1].sum()).backward()
+    assert rel_err(o1[1], o2[1]) < 1e-5 and rel_err(a.grad, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize("camera_model", ["pinhole", "ortho", "fisheye"])
+def test_proj_matches_reference(camera_model):
+    """Against the reference's _persp_proj / _ortho_proj / _fisheye_proj (golden fixture), including points whose
+    x/z lies beyond the field-of-view clamp of the pinhole Jacobian."""
+    G = _golden_geom()
+    W, H = int(G["W"]), int(G["H"])
+    a, b = G["proj_means"].to(DEV).requires_grad_(True), G["proj_covars"].to(DEV).requires_grad_(True)
+    m2, c2 = gs.proj(a, b, G["proj_Ks"].to(DEV), W, H, camera_model)
+    n = camera_model
+    assert rel_err(m2, G[f"proj_{n}_means2d"]) < 1e-4 and rel_err(c2, G[f"proj_{n}_covars2d"]) < 1e-4
+    ((m2 * G[f"proj_{n}_w1"].to(DEV)).sum() + (c2 * G[f"proj_{n}_w2"].to(DEV)).sum()).backward()
+    assert rel_err(a.grad, G[f"proj_{n}_v_means"]) < 1e-3 and rel_err(b.grad, G[f"proj_{n}_v_covars"]) < 1e-4

@@ -236,3 +236,38 @@ def test_photometric_oracle_gradient_by_finite_differences():
     l1 = (x - y).abs().mean()
     ssim = O.fused_ssim(x.permute(0, 3, 1, 2), y.permute(0, 3, 1, 2), "valid")
     assert abs(loss.item() - (0.8 * l1.item() + 0.2 * (1 - ssim.item()))) < 1e-14
+
+
+# ------------------------------------------------------------------------------- un-fused geometry ops
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-12)
+
+
+def test_geom_ops_oracle_matches_reference_torch_impl(golden_dir):
+    """oracle.quat_scale_to_covar_preci / proj / world_to_cam against the reference's _torch_impl.py:41-247
+    (values and autograd gradients, fixture made by oracle/make_golden_geom.py)."""
+    import numpy as np
+
+    from oracle import oracle as O
+
+    G = {k: torch.from_numpy(v) if v.ndim else v for k, v in np.load(os.path.join(golden_dir, "ref_cpu_geom_ops.npz")).items()}
+    for tag, triu in (("full", False), ("triu", True)):
+        q, s = G["quats"].clone().requires_grad_(True), G["scales"].clone().requires_grad_(True)
+        cov, pre = O.quat_scale_to_covar_preci(q, s, True, True, triu)
+        assert _rel(cov, G[f"qs_{tag}_covars"]) < 1e-6 and _rel(pre, G[f"qs_{tag}_precis"]) < 1e-5
+        ((cov * G[f"qs_{tag}_wc"]).sum() + (pre * G[f"qs_{tag}_wp"]).sum()).backward()
+        assert _rel(q.grad, G[f"qs_{tag}_v_quats"]) < 1e-4 and _rel(s.grad, G[f"qs_{tag}_v_scales"]) < 1e-4
+    m, c, v = (G[k].clone().requires_grad_(True) for k in ("w2c_means", "w2c_covars", "w2c_viewmats"))
+    mc, cc = O.world_to_cam(m, c, v)
+    assert _rel(mc, G["w2c_means_c"]) < 1e-6 and _rel(cc, G["w2c_covars_c"]) < 1e-6
+    ((mc * G["w2c_wm"]).sum() + (cc * G["w2c_wc"]).sum()).backward()
+    for t, k in ((m, "w2c_v_means"), (c, "w2c_v_covars"), (v, "w2c_v_viewmats")):
+        assert _rel(t.grad, G[k]) < 1e-5, k
+    W, H = int(G["W"]), int(G["H"])
+    for name in ("pinhole", "ortho", "fisheye"):
+        a, b = G["proj_means"].clone().requires_grad_(True), G["proj_covars"].clone().requires_grad_(True)
+        m2, c2 = O.proj(a, b, G["proj_Ks"], W, H, name)
+        assert _rel(m2, G[f"proj_{name}_means2d"]) < 1e-5 and _rel(c2, G[f"proj_{name}_covars2d"]) < 1e-5, name
+        ((m2 * G[f"proj_{name}_w1"]).sum() + (c2 * G[f"proj_{name}_w2"]).sum()).backward()
+        assert _rel(a.grad, G[f"proj_{name}_v_means"]) < 1e-4 and _rel(b.grad, G[f"proj_{name}_v_covars"]) < 1e-5, name
