@@ -59,6 +59,7 @@ SIGNATURES = {
     "gsb200_entropy_bwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P, _P, _P],
     "gsb200_selective_adam_update": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _U, _U, _P],
     "gsb200_adam_multi": [_U, _P, _P],
+    "gsb200_compute_relocation": [_U, _P, _P, _P, _P, _I, _P, _P, _P],
     "gsb200_quat_scale_to_covar_preci_fwd": [_U, _P, _P, _I, _P, _P, _P],
     "gsb200_quat_scale_to_covar_preci_bwd": [_U, _P, _P, _I, _P, _P, _P, _P, _P],
     "gsb200_proj_fwd": [_U, _U, _P, _P, _P, _U, _U, _I, _P, _P, _P],

@@ -125,6 +125,31 @@ selective_adam_scalar_kernel(float *__restrict__ param, const float *__restrict_
     param[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
 }
 
+// MCMC relocation (gsplat/cuda/csrc/compute_relocation.cu:13-40; Eq. 9 of "3D Gaussian Splatting as Markov Chain
+// Monte Carlo"): opacity and scale of a Gaussian that is split into `ratio` copies.
+__global__ void __launch_bounds__(kThreads)
+relocation_kernel(uint32_t N, const float *__restrict__ opacities, const float *__restrict__ scales, const int32_t *__restrict__ ratios,
+                  const float *__restrict__ binoms, int n_max, float *__restrict__ new_opacities, float *__restrict__ new_scales) {
+    const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
+    if (g >= N) return;
+    const int n = ratios[g];
+    const float opac = opacities[g];
+    const float new_opac = 1.0f - powf(1.0f - opac, 1.0f / (float)n);
+    new_opacities[g] = new_opac;
+    float denom = 0.0f;
+    for (int i = 1; i <= n; ++i) {
+        float pw = new_opac;  // new_opac^(k+1)
+        for (int k = 0; k <= i - 1; ++k) {
+            const float term = ((k & 1) ? -1.0f : 1.0f) / sqrtf((float)(k + 1)) * pw;
+            denom += __ldg(binoms + (size_t)(i - 1) * n_max + k) * term;
+            pw *= new_opac;
+        }
+    }
+    const float coeff = opac / denom;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) new_scales[(size_t)g * 3 + k] = coeff * scales[(size_t)g * 3 + k];
+}
+
 static bool aligned16(const void *a, const void *b, const void *c, const void *d) {
     return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
              reinterpret_cast<uintptr_t>(d)) & 15) == 0;
@@ -177,4 +202,17 @@ extern "C" int gsb200_adam_multi(uint32_t n_tensors, const gsb200_adam_tensor *t
     if (T.n == 0) return 0;
     adam_multi_kernel<<<(uint32_t)blocks, kThreads, 0, (cudaStream_t)stream>>>(T);
     return check_launch("adam_multi");
+}
+
+extern "C" int gsb200_compute_relocation(uint32_t N, const float *opacities, const float *scales, const int32_t *ratios,
+                                         const float *binoms, int n_max, float *new_opacities, float *new_scales,
+                                         gsb200_stream_t stream) {
+    if (N == 0) return 0;
+    if (opacities == nullptr || scales == nullptr || ratios == nullptr || binoms == nullptr || new_opacities == nullptr ||
+        new_scales == nullptr)
+        return fail(2, "gsb200_compute_relocation: null pointer");
+    if (n_max <= 0) return fail(2, "gsb200_compute_relocation: n_max must be positive");
+    relocation_kernel<<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(N, opacities, scales, ratios, binoms, n_max,
+                                                                                 new_opacities, new_scales);
+    return check_launch("compute_relocation");
 }

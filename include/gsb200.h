@@ -295,6 +295,14 @@ typedef struct gsb200_adam_tensor {
 } gsb200_adam_tensor;
 int gsb200_adam_multi(uint32_t n_tensors, const gsb200_adam_tensor *tensors, gsb200_stream_t stream);
 
+/* replaces _C.compute_relocation (ext.cpp, compute_relocation.cu:13-74; caller gsplat/relocation.py:10-49, the MCMC
+ * strategy): opacities [N], scales [N,3], ratios i32 [N] in [1, n_max], binoms [n_max, n_max] ->
+ * new_opacities [N] = 1 - (1 - o)^(1/ratio), new_scales [N,3] = scales * o / sum_{i<=ratio} sum_{k<i} binom(i-1,k)
+ * (-1)^k new_o^(k+1) / sqrt(k+1). */
+int gsb200_compute_relocation(uint32_t N, const float *opacities, const float *scales, const int32_t *ratios,
+                              const float *binoms, int n_max, float *new_opacities, float *new_scales,
+                              gsb200_stream_t stream);
+
 /* ---------------------------------------------------------------- photometric loss
  * replaces the loss chain of examples/simple_trainer.py:948-953: F.l1_loss + (1 - fused_ssim(..., padding="valid")),
  * where fused_ssim is the un-vendored dependency pinned at examples/requirements.txt:26 (rahul-goel/fused-ssim@1272e21a;

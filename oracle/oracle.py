@@ -636,3 +636,17 @@ def world_to_cam(means: Tensor, covars: Tensor, viewmats: Tensor):
     means_c = torch.einsum("cij,nj->cni", R, means) + t[:, None, :]
     covars_c = torch.einsum("cij,njk,clk->cnil", R, covars, R)
     return means_c, covars_c
+
+
+def compute_relocation(opacities: Tensor, scales: Tensor, ratios: Tensor, binoms: Tensor):
+    """gsplat/cuda/csrc/compute_relocation.cu:13-40 restated (float64 inside); ratios already clamped to [1, n_max]."""
+    n_max = binoms.shape[0]
+    o = opacities.double()
+    n = ratios.long()
+    new_o = 1.0 - (1.0 - o) ** (1.0 / n.double())
+    k = torch.arange(n_max, dtype=torch.float64)
+    term = ((-1.0) ** k) / torch.sqrt(k + 1.0) * new_o[:, None] ** (k + 1.0)  # [N, n_max]
+    row_sums = torch.einsum("ik,nk->ni", torch.tril(binoms.double()), term)  # sum_k binom(i-1, k) term_k, k <= i-1
+    use = (torch.arange(n_max)[None, :] < n[:, None]).double()  # rows i-1 = 0 .. n-1
+    denom = (row_sums * use).sum(-1)
+    return new_o.to(opacities.dtype), (scales.double() * (o / denom)[:, None]).to(scales.dtype)

@@ -298,3 +298,31 @@ def test_proj_matches_reference(camera_model):
     assert rel_err(m2, G[f"proj_{n}_means2d"]) < 1e-4 and rel_err(c2, G[f"proj_{n}_covars2d"]) < 1e-4
     ((m2 * G[f"proj_{n}_w1"].to(DEV)).sum() + (c2 * G[f"proj_{n}_w2"].to(DEV)).sum()).backward()
     assert rel_err(a.grad, G[f"proj_{n}_v_means"]) < 1e-3 and rel_err(b.grad, G[f"proj_{n}_v_covars"]) < 1e-4
+
+
+def test_compute_relocation_matches_oracle():
+    """compute_relocation against the float64 restatement of compute_relocation.cu:13-40; ratios are clamped in
+    place to [1, n_max] like the reference wrapper does (relocation.py:43)."""
+    import math
+
+    from gscodec_studio_b200.relocation import compute_relocation
+
+    n_max = 51
+    binoms = torch.zeros(n_max, n_max)
+    for n in range(n_max):
+        for k in range(n + 1):
+            binoms[n, k] = math.comb(n, k)
+    g = torch.Generator().manual_seed(21)
+    N = 5000
+    opac = torch.rand(N, generator=g) * 0.98 + 0.01
+    scales = torch.rand(N, 3, generator=g) * 0.1
+    ratios = torch.randint(0, 12, (N,), generator=g)
+    ratios[:5] = torch.tensor([0, 1, 2, 51, 80])
+    r_dev = ratios.to(DEV)
+    new_o, new_s = compute_relocation(opac.to(DEV), scales.to(DEV), r_dev, binoms.to(DEV))
+    assert r_dev.min().item() == 1 and r_dev.max().item() == n_max
+    ref_o, ref_s = O.compute_relocation(opac, scales, ratios.clamp(1, n_max), binoms)
+    small = ratios.clamp(1, n_max) <= 12  # the alternating binomial sum loses all float32 digits for large ratios
+    assert rel_err(new_o, ref_o) < 1e-4  # __powf under --use_fast_math
+    assert rel_err(new_s[small.to(DEV)], ref_s[small]) < 1e-3
+    assert torch.allclose(new_s[ratios.to(DEV) == 1], scales.to(DEV)[ratios.to(DEV) == 1], rtol=1e-3)
