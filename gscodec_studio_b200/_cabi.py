@@ -66,6 +66,8 @@ SIGNATURES = {
     "gsb200_proj_bwd": [_U, _U, _P, _P, _P, _U, _U, _I, _P, _P, _P, _P, _P],
     "gsb200_world_to_cam_fwd": [_U, _U, _P, _P, _P, _P, _P, _P],
     "gsb200_world_to_cam_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_stg_temporal_fwd": [_U, _F] + [_P] * 14,
+    "gsb200_stg_temporal_bwd": [_U, _F] + [_P] * 19,
     "gsb200_photometric_workspace_bytes": [],
     "gsb200_photometric_loss_fwd": [_U, _U, _U, _U, _P, _P, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_photometric_loss_bwd": [_U, _U, _U, _U, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _P],
@@ -76,7 +78,7 @@ class AdamTensor(ctypes.Structure):
     """struct gsb200_adam_tensor (include/gsb200.h)."""
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
                 ("n", c_int64), ("step_size", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
-                ("inv_sqrt_bias2", c_float)]
+                ("inv_sqrt_bias2", c_float), ("one_minus_beta1", c_float), ("one_minus_beta2", c_float)]
 
 
 ADAM_MAX_TENSORS = 16  # GSB200_ADAM_MAX_TENSORS

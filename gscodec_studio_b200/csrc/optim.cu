@@ -25,8 +25,8 @@ struct AdamTable {
 };
 
 __device__ __forceinline__ void adam_elem(float &p, float g, float &m, float &v, const gsb200_adam_tensor &h) {
-    m = h.beta1 * m + (1.f - h.beta1) * g;
-    v = h.beta2 * v + (1.f - h.beta2) * g * g;
+    m = h.beta1 * m + h.one_minus_beta1 * g;  // 1 - beta is rounded from double on the host, as torch does
+    v = h.beta2 * v + h.one_minus_beta2 * g * g;
     const float denom = sqrtf(v) * h.inv_sqrt_bias2 + h.eps;
     p -= h.step_size * (m / denom);
 }

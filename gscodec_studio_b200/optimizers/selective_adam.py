@@ -95,7 +95,7 @@ class GroupedAdam(torch.optim.Adam):
                 keep.append(grad)
                 rows.append(_cabi.AdamTensor(
                     ptr(param), ptr(grad), ptr(state["exp_avg"]), ptr(state["exp_avg_sq"]), param.numel(),
-                    lr / (1.0 - beta1 ** t), beta1, beta2, eps, 1.0 / math.sqrt(1.0 - beta2 ** t)))
+                    lr / (1.0 - beta1 ** t), beta1, beta2, eps, 1.0 / math.sqrt(1.0 - beta2 ** t), 1.0 - beta1, 1.0 - beta2))
         with torch.cuda.device(device) if device is not None else _null():
             for i in range(0, len(rows), _cabi.ADAM_MAX_TENSORS):
                 part = rows[i:i + _cabi.ADAM_MAX_TENSORS]

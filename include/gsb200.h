@@ -282,7 +282,8 @@ int gsb200_selective_adam_update(float *param, const float *param_grad, float *e
                                  uint32_t N, uint32_t M, gsb200_stream_t stream);
 /* torch.optim.Adam's update (the optimizer examples/simple_trainer.py:396-408 creates per attribute) for up
  * to GSB200_ADAM_MAX_TENSORS tensors in one launch.  `tensors` is a HOST array; per tensor, with t = step count:
- *   step_size = lr / (1 - beta1^t),  inv_sqrt_bias2 = 1 / sqrt(1 - beta2^t)
+ *   step_size = lr / (1 - beta1^t),  inv_sqrt_bias2 = 1 / sqrt(1 - beta2^t),  one_minus_beta = 1 - beta (all rounded
+ *   to float from double arithmetic on the host, as torch does with its Python scalars)
  *   m = beta1 m + (1-beta1) g;  v = beta2 v + (1-beta2) g^2;  param -= step_size m / (sqrt(v) inv_sqrt_bias2 + eps) */
 #define GSB200_ADAM_MAX_TENSORS 16
 typedef struct gsb200_adam_tensor {
@@ -291,7 +292,7 @@ typedef struct gsb200_adam_tensor {
     float *exp_avg;
     float *exp_avg_sq;
     int64_t n; /* elements */
-    float step_size, beta1, beta2, eps, inv_sqrt_bias2;
+    float step_size, beta1, beta2, eps, inv_sqrt_bias2, one_minus_beta1, one_minus_beta2;
 } gsb200_adam_tensor;
 int gsb200_adam_multi(uint32_t n_tensors, const gsb200_adam_tensor *tensors, gsb200_stream_t stream);
 
@@ -356,6 +357,26 @@ int gsb200_world_to_cam_fwd(uint32_t C, uint32_t N, const float *means, const fl
 int gsb200_world_to_cam_bwd(uint32_t C, uint32_t N, const float *means, const float *covars,
                             const float *viewmats, const float *v_means_c, const float *v_covars_c,
                             float *v_means, float *v_covars, float *v_viewmats, gsb200_stream_t stream);
+
+/* ---------------------------------------------------------------- dynamic splats: temporal pre-transform
+ * The per-timestamp attribute chain of examples/simple_trainer_dyngs.py:476-520 (BASELINE config 4) in one pass:
+ *   d = timestamp - trbf_center;  trbf = exp(-(d / (sqrt(2) exp(trbf_scale_raw)))^2)
+ *   opacities = sigmoid(opacities_raw) * trbf;  scales = exp(scales_raw)
+ *   means_t = means + motion[0:3] d + motion[3:6] d^2 + motion[6:9] d^3;  quats_t = normalize(quats + d omega)
+ * All arrays have N rows: means [N,3], quats / omega [N,4], scales_raw [N,3], opacities_raw / trbf_center /
+ * trbf_scale_raw [N], motion [N,9].  In the polynomial and the rotation d is a constant (the trainer detaches it),
+ * so trbf_center / trbf_scale_raw receive gradients through the opacity only.  bwd overwrites every v_* output. */
+int gsb200_stg_temporal_fwd(uint32_t N, float timestamp, const float *means, const float *quats,
+                            const float *scales_raw, const float *opacities_raw, const float *trbf_center,
+                            const float *trbf_scale_raw, const float *motion, const float *omega,
+                            float *means_t, float *quats_t, float *scales, float *opacities, float *trbf,
+                            gsb200_stream_t stream);
+int gsb200_stg_temporal_bwd(uint32_t N, float timestamp, const float *quats, const float *scales_raw,
+                            const float *opacities_raw, const float *trbf_center, const float *trbf_scale_raw,
+                            const float *omega, const float *v_means_t, const float *v_quats_t,
+                            const float *v_scales, const float *v_opacities, float *v_means, float *v_quats,
+                            float *v_scales_raw, float *v_opacities_raw, float *v_trbf_center,
+                            float *v_trbf_scale_raw, float *v_motion, float *v_omega, gsb200_stream_t stream);
 
 #ifdef __cplusplus
 }

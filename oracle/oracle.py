@@ -650,3 +650,17 @@ def compute_relocation(opacities: Tensor, scales: Tensor, ratios: Tensor, binoms
     use = (torch.arange(n_max)[None, :] < n[:, None]).double()  # rows i-1 = 0 .. n-1
     denom = (row_sums * use).sum(-1)
     return new_o.to(opacities.dtype), (scales.double() * (o / denom)[:, None]).to(scales.dtype)
+
+
+# --------------------------------------------------------------------------------------
+# dynamic splats: temporal pre-transform, examples/simple_trainer_dyngs.py:476-520 restated
+# --------------------------------------------------------------------------------------
+def stg_temporal_transform(means, quats, scales, opacities, trbf_center, trbf_scale, motion, omega, timestamp: float):
+    d = timestamp - trbf_center.reshape(-1, 1)  # [N,1]
+    x = d / (math.sqrt(2) * torch.exp(trbf_scale.reshape(-1, 1)))
+    trbf = torch.exp(-x * x)
+    opacity = torch.sigmoid(opacities) * trbf.squeeze(-1)
+    dd = d.detach()
+    means_t = means + motion[:, 0:3] * dd + motion[:, 3:6] * dd * dd + motion[:, 6:9] * dd * dd * dd
+    quats_t = F.normalize(quats + dd * omega)
+    return means_t, quats_t, torch.exp(scales), opacity, trbf.squeeze(-1).detach()

@@ -3,6 +3,7 @@ split SH coefficients, the fused optimizer step, the un-fused public ops.  Same 
 tests/test_gpu_parity.py (tolerances relative to the largest reference magnitude)."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -110,12 +111,15 @@ def test_selective_adam_matches_reference_semantics():
             opt.step(vis.to(DEV))
             gd = grad.double()
             sel = vis.view(-1, *([1] * (len(shape) - 1))).expand(*shape)
-            m = torch.where(sel, 0.9 * m + (1 - 0.9) * gd, m)
-            v = torch.where(sel, 0.999 * v + (1 - 0.999) * gd * gd, v)
+            # the reference kernel forms 1 - beta in float32 (adam.cu:34-35): 1.0f - 0.999f = 0.00100004673
+            b1, b2 = float(np.float32(0.9)), float(np.float32(0.999))
+            w1, w2 = float(np.float32(1) - np.float32(0.9)), float(np.float32(1) - np.float32(0.999))
+            m = torch.where(sel, b1 * m + w1 * gd, m)
+            v = torch.where(sel, b2 * v + w2 * gd * gd, v)
             p = torch.where(sel, p - 1.6e-4 * m / (v.sqrt() + 1e-15), p)
             assert torch.equal(param.detach()[~vis.to(DEV)], before[~vis.to(DEV)])
             st = opt.state[param]
-            assert rel_err(st["exp_avg"], m) < 1e-6 and rel_err(st["exp_avg_sq"], v) < 1e-6
+            assert rel_err(st["exp_avg"], m) < 2e-6 and rel_err(st["exp_avg_sq"], v) < 2e-6
             assert (param.detach().double().cpu() - p).abs().max().item() < 1e-6 * p.abs().max().item()  # a step is ~5e-4
 
 
@@ -162,8 +166,8 @@ def test_grouped_adam_matches_torch_adam():
         for i, (pa, pb, lr) in enumerate(zip(ours, ref, lrs)):
             sa, sb = opt_a.state[pa], opt_b.state[pb]
             assert float(sa["step"]) == float(sb["step"]) == step + 1
-            assert rel_err(sa["exp_avg"], sb["exp_avg"]) < 1e-6, i
-            assert rel_err(sa["exp_avg_sq"], sb["exp_avg_sq"]) < 1e-6, i
+            assert rel_err(sa["exp_avg"], sb["exp_avg"]) < 2e-6, i  # beta itself is a float32 in the kernel
+            assert rel_err(sa["exp_avg_sq"], sb["exp_avg_sq"]) < 2e-6, i
             # an Adam step moves a parameter by ~lr; fp32 keeps ~1e-7 relative of the parameter itself per step
             tol = lr * 1e-4 + 1e-6 * pb.abs().max().item()
             assert (pa.detach().double().cpu() - pb.detach()).abs().max().item() < tol, (i, step)
@@ -326,3 +330,59 @@ def test_compute_relocation_matches_oracle():
     assert rel_err(new_o, ref_o) < 1e-4  # __powf under --use_fast_math
     assert rel_err(new_s[small.to(DEV)], ref_s[small]) < 1e-3
     assert torch.allclose(new_s[ratios.to(DEV) == 1], scales.to(DEV)[ratios.to(DEV) == 1], rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------- dynamic splats (config 4)
+@pytest.mark.parametrize("timestamp", [0.0, 0.37, 1.0])
+def test_stg_temporal_transform_matches_oracle(timestamp):
+    """The fused per-timestamp attribute chain of simple_trainer_dyngs.py:476-520 against its float64 torch
+    restatement: all five outputs and the gradients of all eight inputs."""
+    from gscodec_studio_b200.dynamic import stg_temporal_transform
+
+    g = torch.Generator().manual_seed(17)
+    N = 2049
+    ins = [torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g), torch.randn(N, 3, generator=g) - 3,
+           torch.randn(N, generator=g) * 2, torch.rand(N, 1, generator=g), torch.randn(N, 1, generator=g) * 0.5 - 1,
+           torch.randn(N, 9, generator=g) * 0.3, torch.randn(N, 4, generator=g) * 0.2]
+    ws = [torch.randn(N, 3, generator=g), torch.randn(N, 4, generator=g), torch.randn(N, 3, generator=g), torch.randn(N, generator=g)]
+    a = [t.clone().to(DEV).requires_grad_(True) for t in ins]
+    b = [t.clone().double().requires_grad_(True) for t in ins]
+    out_a = stg_temporal_transform(*a, timestamp)
+    out_b = O.stg_temporal_transform(*b, timestamp)
+    names = ("means_t", "quats_t", "scales", "opacities", "trbf")
+    for x, y, n in zip(out_a, out_b, names):
+        assert rel_err(x, y) < 1e-5, n
+    assert not out_a[4].requires_grad
+    sum((o * w.to(DEV)).sum() for o, w in zip(out_a[:4], ws)).backward()
+    sum((o * w.double()).sum() for o, w in zip(out_b[:4], ws)).backward()
+    for x, y, n in zip(a, b, ("means", "quats", "scales", "opacities", "trbf_center", "trbf_scale", "motion", "omega")):
+        assert rel_err(x.grad, y.grad) < 1e-4, n
+
+
+def test_dynamic_step_renders_like_torch_chain():
+    """config-4 shaped step (2 views of one timestamp, 3 colour channels, no SH): fused temporal transform ->
+    rasterization equals the torch chain -> rasterization, images and parameter gradients."""
+    from gscodec_studio_b200.dynamic import stg_temporal_transform
+
+    means, quats, scales, opac, colors, viewmats, Ks, W, H = load_test_data(device="cpu", scene_grid=1)
+    sel = slice(0, None, 6)
+    g = torch.Generator().manual_seed(23)
+    N = means[sel].shape[0]
+    raw = [means[sel], quats[sel], torch.log(scales[sel]), torch.logit(opac[sel].clamp(1e-4, 1 - 1e-4)),
+           torch.rand(N, 1, generator=g), torch.randn(N, 1, generator=g) * 0.3 - 0.5, torch.randn(N, 9, generator=g) * 0.05,
+           torch.randn(N, 4, generator=g) * 0.05]
+    cols = colors[sel].to(DEV)
+    vm, K = viewmats[:2].to(DEV), Ks[:2].to(DEV)
+
+    def run(fused: bool):
+        p = [t.clone().to(DEV).requires_grad_(True) for t in raw]
+        m, q, s, o, _ = stg_temporal_transform(*p, 0.4) if fused else O.stg_temporal_transform(*p, 0.4)
+        rc, ra, _ = gs.rasterization(m, q, s, o, cols, vm, K, W, H, packed=False)
+        (rc.sum() + 0.5 * ra.sum()).backward()
+        return rc, [t.grad for t in p]
+
+    rc1, g1 = run(True)
+    rc2, g2 = run(False)
+    assert rel_err(rc1, rc2) < 1e-4
+    for x, y, n in zip(g1, g2, ("means", "quats", "scales", "opacities", "trbf_center", "trbf_scale", "motion", "omega")):
+        assert rel_err(x, y) < 1e-3, n

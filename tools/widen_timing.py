@@ -8,6 +8,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from gscodec_studio_b200 import _cabi  # noqa: E402
 from gscodec_studio_b200.cuda._wrapper import view_colors_from_sh, view_colors_from_sh_split  # noqa: E402
 from gscodec_studio_b200.losses import photometric_loss  # noqa: E402
 from gscodec_studio_b200.optimizers import GroupedAdam  # noqa: E402
@@ -29,6 +30,17 @@ def timeit(fn, n=20, warm=3):
     return ts[len(ts) // 2] * 1e3  # median, us
 
 
+def device_ms(fn, n=10):
+    """Device time of every C-ABI call inside fn (CUDA events around the calls), averaged, in us."""
+    fn()
+    _cabi.enable_stage_timing(True)
+    for _ in range(n):
+        fn()
+    ms = _cabi.stage_timing_ms()
+    _cabi.enable_stage_timing(False)
+    return ", ".join(f"{k.replace('gsb200_', '')} {v * 1e3:.1f} us" for k, v in sorted(ms.items()))
+
+
 def main():
     g = torch.Generator(device="cuda").manual_seed(0)
     # ---- loss
@@ -43,6 +55,7 @@ def main():
         x.grad = None
         (x - y).abs().mean().backward()
 
+    print("  device:", device_ms(ours))
     print(f"photometric_loss (L1+SSIM) fwd+bwd 1080p: {timeit(ours):8.1f} us   | torch L1 only fwd+bwd: {timeit(torch_l1):8.1f} us")
 
     # ---- Adam
@@ -60,6 +73,7 @@ def main():
     _, foreach = build(torch.optim.Adam)
     _, fused = build(torch.optim.Adam, fused=True)
     n_bytes = 28 * sum(int(torch.tensor(s).prod()) for s in shapes.values())
+    print("  device:", device_ms(grouped.step))
     t = timeit(grouped.step)
     print(f"GroupedAdam 6 tensors / 1 launch: {t:8.1f} us ({n_bytes / t / 1e3:7.1f} GB/s of 28 B/float) | "
           f"torch Adam foreach (one optimizer): {timeit(foreach.step):8.1f} us | torch Adam fused=True: {timeit(fused.step):8.1f} us")
@@ -80,6 +94,7 @@ def main():
         sh0.grad = shN.grad = None
         (view_colors_from_sh(3, means, campos, torch.cat([sh0, shN], 1), radii) * w).sum().backward()
 
+    print("  device:", device_ms(split), "|", device_ms(cat))
     print(f"colour stage fwd+bwd, 29% visible: split (sh0, shN) {timeit(split):8.1f} us | torch.cat + fused kernel {timeit(cat):8.1f} us")
 
 
