@@ -121,6 +121,7 @@ def run_ours(args):
     import gscodec_studio_b200 as gs
     from gscodec_studio_b200 import _cabi
     from gscodec_studio_b200.compression_simulation import CompressionSimulation
+    from gscodec_studio_b200.losses import photometric_loss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -180,7 +181,8 @@ def run_ours(args):
         rc, ra, meta = gs.rasterization(new["means"], new["quats"], scales, opac, colors, viewmat, K, W_IMG, H_IMG,
                                         sh_degree=3, packed=False, near_plane=0.01, far_plane=100.0, radius_clip=3.0,
                                         distributed=world > 1)
-        loss = (rc - target).abs().mean()
+        # L1 loss against the target: the fused loss kernel (ssim_lambda = 0 -> pure L1) unless --torch-loss
+        loss = (rc - target).abs().mean() if args.torch_loss else photometric_loss(rc, target, ssim_lambda=0.0)
         for b in bits.values():
             if b is not None:
                 loss = loss + 1e-9 * b.sum()
@@ -388,6 +390,8 @@ def main():
     ap.add_argument("--entropy", action="store_true", help="also run the factorized entropy model on scales/quats/sh0")
     ap.add_argument("--cat-colors", dest="cat_colors", action="store_true",
                     help="m2: pass torch.cat([sh0, shN], 1) (the reference trainer's call) instead of the (sh0, shN) pair")
+    ap.add_argument("--torch-loss", dest="torch_loss", action="store_true",
+                    help="m2: L1 loss as the torch chain (rc - target).abs().mean() instead of the fused loss kernel")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -22,8 +22,13 @@
 namespace gsb200 {
 
 constexpr int kWin = 11, kHalo = 5;
-constexpr int kTile = 16;
-constexpr int kSpan = kTile + 2 * kHalo;  // 26
+constexpr int kTW = 32, kTH = 32;                                // output tile of one CTA
+constexpr int kSpanX = kTW + 2 * kHalo, kSpanY = kTH + 2 * kHalo;  // 42 x 42 staged inputs
+constexpr int kLossThreads = 256;
+constexpr int kRowsPerThread = kTH / (kLossThreads / kTW);  // vertical pass: 4 output rows per thread
+constexpr int kColsPerItem = 4;                             // horizontal pass: 4 output columns per work item
+constexpr int kTaps = kColsPerItem + kWin - 1;              // 14 inputs feed 4 outputs
+static_assert(kRowsPerThread == 4 && kTW % kColsPerItem == 0, "tiling");
 
 struct SsimWindow {
     float w[kWin];
@@ -45,74 +50,126 @@ __device__ __forceinline__ bool ssim_counts(const LossGeom &G, int y, int x) {
     return y >= kHalo && x >= kHalo && y < (int)G.H - kHalo && x < (int)G.W - kHalo;
 }
 
-__global__ void __launch_bounds__(kTile * kTile)
+// Stage one channel of a (kSpanY x kSpanX) window around the tile, zero outside the image.
+template <int NA>
+__device__ __forceinline__ void stage_window(const LossGeom &G, size_t img_base, int x0, int y0, uint32_t ch,
+                                             const float *const (&src)[NA], float (*const (&dst)[NA])[kSpanX + 1]) {
+    for (int i = threadIdx.x; i < kSpanY * kSpanX; i += kLossThreads) {
+        const int r = i / kSpanX, c = i - r * kSpanX;
+        const int gy = y0 - kHalo + r, gx = x0 - kHalo + c;
+        const bool in = gy >= 0 && gy < (int)G.H && gx >= 0 && gx < (int)G.W;
+        const size_t o = (img_base + (size_t)gy * G.W + gx) * G.CH + ch;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) dst[a][r][c] = in ? __ldg(src[a] + o) : 0.f;
+    }
+}
+
+// The separable 11-tap window is applied with register tiling, because the kernel is bound by shared-memory
+// wavefronts, not by FMAs: a horizontal work item reads 14 inputs for 4 adjacent outputs (lanes of a warp own
+// different rows, odd row stride: conflict-free), a thread of the vertical pass reads 14 rows for its 4 output rows
+// (lanes own adjacent columns).  ~1.4 shared-memory wavefronts per pixel and channel instead of 6 for the
+// one-output-per-thread form.
+__global__ void __launch_bounds__(kLossThreads)
 photometric_fwd_kernel(LossGeom G, SsimWindow win, const float *__restrict__ img1, const float *__restrict__ img2,
                        float *__restrict__ map_mu, float *__restrict__ map_s1, float *__restrict__ map_s12, LossWork *work,
                        float *__restrict__ out, float *__restrict__ stats) {
-    __shared__ float sX[kSpan][kSpan + 1], sY[kSpan][kSpan + 1];
-    __shared__ float sH[5][kSpan][kTile + 1];
-    __shared__ double s_red[2][kTile * kTile / 32];
-    const int tid = threadIdx.x, lx = tid % kTile, ly = tid / kTile;
-    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile, b = blockIdx.z;
-    const int px = x0 + lx, py = y0 + ly;
-    const bool inside = px < (int)G.W && py < (int)G.H;
+    __shared__ float sX[kSpanY][kSpanX + 1], sY[kSpanY][kSpanX + 1];
+    __shared__ float sH[5][kSpanY][kTW + 1];
+    __shared__ double s_red[2][kLossThreads / 32];
+    const int tid = threadIdx.x, lx = tid % kTW, rg = tid / kTW;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, b = blockIdx.z;
+    const int px = x0 + lx, py0 = y0 + rg * kRowsPerThread;
     const size_t img_base = (size_t)b * G.H * G.W;
     const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+    const bool with_ssim = G.coef_ssim != 0.f;
     float l1_acc = 0.f, ssim_acc = 0.f;
 
-    for (uint32_t ch = 0; ch < G.CH; ++ch) {
-        __syncthreads();  // previous channel's readers are done with the staging arrays
-        for (int i = tid; i < kSpan * kSpan; i += kTile * kTile) {
-            const int r = i / kSpan, c = i - r * kSpan;
-            const int gy = y0 - kHalo + r, gx = x0 - kHalo + c;
-            float a = 0.f, d = 0.f;
-            if (gy >= 0 && gy < (int)G.H && gx >= 0 && gx < (int)G.W) {
-                const size_t o = (img_base + (size_t)gy * G.W + gx) * G.CH + ch;
-                a = __ldg(img1 + o);
-                d = __ldg(img2 + o);
+    if (!with_ssim) {  // L1 only: no window, nothing staged
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) {
+            const int py = py0 + j;
+            if (px < (int)G.W && py < (int)G.H) {
+                const size_t o = (img_base + (size_t)py * G.W + px) * G.CH;
+                for (uint32_t ch = 0; ch < G.CH; ++ch) l1_acc += fabsf(__ldg(img1 + o + ch) - __ldg(img2 + o + ch));
             }
-            sX[r][c] = a;
-            sY[r][c] = d;
+        }
+    }
+    for (uint32_t ch = 0; with_ssim && ch < G.CH; ++ch) {
+        __syncthreads();  // the previous channel's readers are done with the staging arrays
+        {
+            const float *const src[2] = {img1, img2};
+            float(*const dst[2])[kSpanX + 1] = {sX, sY};
+            stage_window<2>(G, img_base, x0, y0, ch, src, dst);
         }
         __syncthreads();
-        for (int i = tid; i < kSpan * kTile; i += kTile * kTile) {  // horizontal pass
-            const int r = i / kTile, c = i - r * kTile;
-            float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
+        // horizontal pass: item = (row r, column group cg); a warp covers 32 consecutive rows of one column group
+        for (int it = tid; it < (kTW / kColsPerItem) * 64; it += kLossThreads) {
+            const int cg = it >> 6, r = it & 63;
+            if (r < kSpanY) {
+                float xa[kTaps], ya[kTaps];
 #pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                const float a = sX[r][c + k], d = sY[r][c + k], w = win.w[k];
-                h0 += w * a; h1 += w * d; h2 += w * a * a; h3 += w * d * d; h4 += w * a * d;
+                for (int k = 0; k < kTaps; ++k) { xa[k] = sX[r][cg * kColsPerItem + k]; ya[k] = sY[r][cg * kColsPerItem + k]; }
+#pragma unroll
+                for (int j = 0; j < kColsPerItem; ++j) {
+                    float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
+#pragma unroll
+                    for (int k = 0; k < kWin; ++k) {
+                        const float a = xa[j + k], d = ya[j + k], w = win.w[k];
+                        h0 += w * a; h1 += w * d; h2 += w * a * a; h3 += w * d * d; h4 += w * a * d;
+                    }
+                    const int c = cg * kColsPerItem + j;
+                    sH[0][r][c] = h0; sH[1][r][c] = h1; sH[2][r][c] = h2; sH[3][r][c] = h3; sH[4][r][c] = h4;
+                }
             }
-            sH[0][r][c] = h0; sH[1][r][c] = h1; sH[2][r][c] = h2; sH[3][r][c] = h3; sH[4][r][c] = h4;
         }
         __syncthreads();
-        float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+        // vertical pass: this thread's column lx, output rows rg*4 .. rg*4+3
+        float acc[kRowsPerThread][5];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {  // vertical pass
-            const float w = win.w[k];
-            mu1 += w * sH[0][ly + k][lx]; mu2 += w * sH[1][ly + k][lx];
-            e11 += w * sH[2][ly + k][lx]; e22 += w * sH[3][ly + k][lx]; e12 += w * sH[4][ly + k][lx];
-        }
-        if (inside) {
-            const float s1 = e11 - mu1 * mu1, s2 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
-            const float A = mu1 * mu1 + mu2 * mu2 + C1, Bq = s1 + s2 + C2;
-            const float Cq = 2.f * mu1 * mu2 + C1, D = 2.f * s12 + C2;
-            const float iA = 1.f / A, iB = 1.f / Bq;
-            const float m = Cq * D * iA * iB;
-            // partials with (mu1, sigma1^2, sigma12) independent, then the chain through sigma1^2 = E11 - mu1^2 and
-            // sigma12 = E12 - mu1 mu2 folded into the mu term:  dm/dx(p) = w(q - p) [ M + 2 x(p) S1 + y(p) S12 ]
-            const float dS1 = -m * iB;
-            const float dS12 = 2.f * Cq * iA * iB;
-            const float dMu = 2.f * D * iA * iB * (mu2 - mu1 * Cq * iA);
-            const bool counts = ssim_counts(G, py, px);
-            const size_t o = (img_base + (size_t)py * G.W + px) * G.CH + ch;
-            if (map_mu != nullptr) {
-                map_mu[o] = counts ? dMu - 2.f * mu1 * dS1 - mu2 * dS12 : 0.f;
-                map_s1[o] = counts ? dS1 : 0.f;
-                map_s12[o] = counts ? dS12 : 0.f;
+        for (int j = 0; j < kRowsPerThread; ++j)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) acc[j][q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+            const int row = rg * kRowsPerThread + k;
+            float v[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) v[q] = sH[q][row][lx];
+#pragma unroll
+            for (int j = 0; j < kRowsPerThread; ++j) {
+                if (k - j >= 0 && k - j < kWin) {
+                    const float w = win.w[k - j];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) acc[j][q] += w * v[q];
+                }
             }
-            if (counts) ssim_acc += m;
-            l1_acc += fabsf(sX[ly + kHalo][lx + kHalo] - sY[ly + kHalo][lx + kHalo]);
+        }
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) {
+            const int py = py0 + j;
+            if (px < (int)G.W && py < (int)G.H) {
+                const float mu1 = acc[j][0], mu2 = acc[j][1], e11 = acc[j][2], e22 = acc[j][3], e12 = acc[j][4];
+                const float s1 = e11 - mu1 * mu1, s2 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
+                const float A = mu1 * mu1 + mu2 * mu2 + C1, Bq = s1 + s2 + C2;
+                const float Cq = 2.f * mu1 * mu2 + C1, D = 2.f * s12 + C2;
+                const float iA = 1.f / A, iB = 1.f / Bq;
+                const float m = Cq * D * iA * iB;
+                // partials with (mu1, sigma1^2, sigma12) independent, then the chain through sigma1^2 = E11 - mu1^2 and
+                // sigma12 = E12 - mu1 mu2 folded into the mu term:  dm/dx(p) = w(q - p) [ M + 2 x(p) S1 + y(p) S12 ]
+                const float dS1 = -m * iB;
+                const float dS12 = 2.f * Cq * iA * iB;
+                const float dMu = 2.f * D * iA * iB * (mu2 - mu1 * Cq * iA);
+                const bool counts = ssim_counts(G, py, px);
+                const size_t o = (img_base + (size_t)py * G.W + px) * G.CH + ch;
+                if (map_mu != nullptr) {
+                    map_mu[o] = counts ? dMu - 2.f * mu1 * dS1 - mu2 * dS12 : 0.f;
+                    map_s1[o] = counts ? dS1 : 0.f;
+                    map_s12[o] = counts ? dS12 : 0.f;
+                }
+                if (counts) ssim_acc += m;
+                const int r = rg * kRowsPerThread + j + kHalo;
+                l1_acc += fabsf(sX[r][lx + kHalo] - sY[r][lx + kHalo]);
+            }
         }
     }
     // block reduction (double: 6 M terms at 1080p), then the last block to arrive writes the scalars
@@ -126,7 +183,7 @@ photometric_fwd_kernel(LossGeom G, SsimWindow win, const float *__restrict__ img
     __syncthreads();
     if (tid == 0) {
         double t1 = 0.0, t2 = 0.0;
-        for (int w = 0; w < kTile * kTile / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
+        for (int w = 0; w < kLossThreads / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
         atomicAdd(&work->l1_sum, t1);
         atomicAdd(&work->ssim_sum, t2);
         __threadfence();
@@ -144,58 +201,88 @@ photometric_fwd_kernel(LossGeom G, SsimWindow win, const float *__restrict__ img
 }
 
 // v_img1 = v_loss * [ coef_l1 / n_all * sign(x - y) + coef_ssim / n_ssim * (conv(M) + 2 x conv(S1) + y conv(S12)) ]
-__global__ void __launch_bounds__(kTile * kTile)
+__global__ void __launch_bounds__(kLossThreads)
 photometric_bwd_kernel(LossGeom G, SsimWindow win, const float *__restrict__ img1, const float *__restrict__ img2,
                        const float *__restrict__ map_mu, const float *__restrict__ map_s1, const float *__restrict__ map_s12,
                        const float *__restrict__ v_loss, float *__restrict__ v_img1) {
-    __shared__ float sM[3][kSpan][kSpan + 1];
-    __shared__ float sH[3][kSpan][kTile + 1];
-    const int tid = threadIdx.x, lx = tid % kTile, ly = tid / kTile;
-    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile, b = blockIdx.z;
-    const int px = x0 + lx, py = y0 + ly;
-    const bool inside = px < (int)G.W && py < (int)G.H;
+    __shared__ float sM[3][kSpanY][kSpanX + 1];
+    __shared__ float sH[3][kSpanY][kTW + 1];
+    const int tid = threadIdx.x, lx = tid % kTW, rg = tid / kTW;
+    const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, b = blockIdx.z;
+    const int px = x0 + lx, py0 = y0 + rg * kRowsPerThread;
     const size_t img_base = (size_t)b * G.H * G.W;
     const double n_all = (double)G.B * G.H * G.W * G.CH;
     const double n_ssim = G.valid ? (double)G.B * G.CH * (double)(G.H - 2 * kHalo) * (double)(G.W - 2 * kHalo) : n_all;
     const float up = __ldg(v_loss);
     const float k_l1 = up * (float)((double)G.coef_l1 / n_all), k_ssim = up * (float)((double)G.coef_ssim / n_ssim);
+    const bool with_ssim = G.coef_ssim != 0.f;
 
+    if (!with_ssim) {
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) {
+            const int py = py0 + j;
+            if (px < (int)G.W && py < (int)G.H) {
+                const size_t o = (img_base + (size_t)py * G.W + px) * G.CH;
+                for (uint32_t ch = 0; ch < G.CH; ++ch) {
+                    const float d = __ldg(img1 + o + ch) - __ldg(img2 + o + ch);
+                    v_img1[o + ch] = k_l1 * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+                }
+            }
+        }
+        return;
+    }
     for (uint32_t ch = 0; ch < G.CH; ++ch) {
         __syncthreads();
-        for (int i = tid; i < kSpan * kSpan; i += kTile * kTile) {
-            const int r = i / kSpan, c = i - r * kSpan;
-            const int gy = y0 - kHalo + r, gx = x0 - kHalo + c;
-            float a = 0.f, d = 0.f, e = 0.f;
-            if (gy >= 0 && gy < (int)G.H && gx >= 0 && gx < (int)G.W) {
-                const size_t o = (img_base + (size_t)gy * G.W + gx) * G.CH + ch;
-                a = __ldg(map_mu + o); d = __ldg(map_s1 + o); e = __ldg(map_s12 + o);
-            }
-            sM[0][r][c] = a; sM[1][r][c] = d; sM[2][r][c] = e;
+        {
+            const float *const src[3] = {map_mu, map_s1, map_s12};
+            float(*const dst[3])[kSpanX + 1] = {sM[0], sM[1], sM[2]};
+            stage_window<3>(G, img_base, x0, y0, ch, src, dst);
         }
         __syncthreads();
-        for (int i = tid; i < kSpan * kTile; i += kTile * kTile) {
-            const int r = i / kTile, c = i - r * kTile;
-            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        for (int it = tid; it < (kTW / kColsPerItem) * 64; it += kLossThreads) {
+            const int cg = it >> 6, r = it & 63;
+            if (r < kSpanY) {
 #pragma unroll
-            for (int k = 0; k < kWin; ++k) {
-                const float w = win.w[k];
-                h0 += w * sM[0][r][c + k]; h1 += w * sM[1][r][c + k]; h2 += w * sM[2][r][c + k];
+                for (int q = 0; q < 3; ++q) {
+                    float ma[kTaps];
+#pragma unroll
+                    for (int k = 0; k < kTaps; ++k) ma[k] = sM[q][r][cg * kColsPerItem + k];
+#pragma unroll
+                    for (int j = 0; j < kColsPerItem; ++j) {
+                        float h = 0.f;
+#pragma unroll
+                        for (int k = 0; k < kWin; ++k) h += win.w[k] * ma[j + k];
+                        sH[q][r][cg * kColsPerItem + j] = h;
+                    }
+                }
             }
-            sH[0][r][c] = h0; sH[1][r][c] = h1; sH[2][r][c] = h2;
         }
         __syncthreads();
-        float cM = 0.f, cS1 = 0.f, cS12 = 0.f;
+        float acc[kRowsPerThread][3];
 #pragma unroll
-        for (int k = 0; k < kWin; ++k) {
-            const float w = win.w[k];
-            cM += w * sH[0][ly + k][lx]; cS1 += w * sH[1][ly + k][lx]; cS12 += w * sH[2][ly + k][lx];
+        for (int j = 0; j < kRowsPerThread; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < kTaps; ++k) {
+            const int row = rg * kRowsPerThread + k;
+            const float v0 = sH[0][row][lx], v1 = sH[1][row][lx], v2 = sH[2][row][lx];
+#pragma unroll
+            for (int j = 0; j < kRowsPerThread; ++j) {
+                if (k - j >= 0 && k - j < kWin) {
+                    const float w = win.w[k - j];
+                    acc[j][0] += w * v0; acc[j][1] += w * v1; acc[j][2] += w * v2;
+                }
+            }
         }
-        if (inside) {
-            const size_t o = (img_base + (size_t)py * G.W + px) * G.CH + ch;
-            const float x = __ldg(img1 + o), y = __ldg(img2 + o);
-            const float d = x - y;
-            const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-            v_img1[o] = k_l1 * sgn + k_ssim * (cM + 2.f * x * cS1 + y * cS12);
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j) {
+            const int py = py0 + j;
+            if (px < (int)G.W && py < (int)G.H) {
+                const size_t o = (img_base + (size_t)py * G.W + px) * G.CH + ch;
+                const float x = __ldg(img1 + o), y = __ldg(img2 + o);
+                const float d = x - y;
+                const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+                v_img1[o] = k_l1 * sgn + k_ssim * (acc[j][0] + 2.f * x * acc[j][1] + y * acc[j][2]);
+            }
         }
     }
 }
@@ -239,8 +326,8 @@ extern "C" int gsb200_photometric_loss_fwd(uint32_t B, uint32_t H, uint32_t W, u
     GSB_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(LossWork), s));
     if (B == 0 || H == 0 || W == 0) return 0;
     const LossGeom G{B, H, W, CH, padding_valid ? 1 : 0, coef_l1, coef_ssim, bias};
-    const dim3 grid(cdiv(W, kTile), cdiv(H, kTile), B);
-    photometric_fwd_kernel<<<grid, kTile * kTile, 0, s>>>(G, make_window(), img1, img2, map_mu, map_s1, map_s12,
+    const dim3 grid(cdiv(W, kTW), cdiv(H, kTH), B);
+    photometric_fwd_kernel<<<grid, kLossThreads, 0, s>>>(G, make_window(), img1, img2, map_mu, map_s1, map_s12,
                                                           reinterpret_cast<LossWork *>(workspace), out, stats);
     return check_launch("photometric_loss_fwd");
 }
@@ -252,12 +339,12 @@ extern "C" int gsb200_photometric_loss_bwd(uint32_t B, uint32_t H, uint32_t W, u
     const char *who = "gsb200_photometric_loss_bwd";
     if (int rc = check_loss_geom(who, B, H, W, CH, padding_valid)) return rc;
     if (B == 0 || H == 0 || W == 0) return 0;
-    if (img1 == nullptr || img2 == nullptr || map_mu == nullptr || map_s1 == nullptr || map_s12 == nullptr || v_loss == nullptr ||
-        v_img1 == nullptr)
-        return failf(2, "%s: null pointer", who);
+    if (img1 == nullptr || img2 == nullptr || v_loss == nullptr || v_img1 == nullptr) return failf(2, "%s: null pointer", who);
+    if (coef_ssim != 0.f && (map_mu == nullptr || map_s1 == nullptr || map_s12 == nullptr))
+        return failf(2, "%s: the derivative maps of the forward are required when coef_ssim != 0", who);
     const LossGeom G{B, H, W, CH, padding_valid ? 1 : 0, coef_l1, coef_ssim, 0.f};
-    const dim3 grid(cdiv(W, kTile), cdiv(H, kTile), B);
-    photometric_bwd_kernel<<<grid, kTile * kTile, 0, (cudaStream_t)stream>>>(G, make_window(), img1, img2, map_mu, map_s1, map_s12,
+    const dim3 grid(cdiv(W, kTW), cdiv(H, kTH), B);
+    photometric_bwd_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(G, make_window(), img1, img2, map_mu, map_s1, map_s12,
                                                                              v_loss, v_img1);
     return check_launch("photometric_loss_bwd");
 }

@@ -48,7 +48,8 @@ class _Photometric(torch.autograd.Function):
             raise ValueError("photometric loss of an empty image")
         dev = img1.device
         keep = train and ctx.needs_input_grad[0]
-        maps = torch.empty((3, B, H, W, CH), dtype=torch.float32, device=dev) if keep else None
+        # derivative maps for the backward; not needed for inference or for a pure L1 loss (coef_ssim == 0)
+        maps = torch.empty((3, B, H, W, CH), dtype=torch.float32, device=dev) if keep and coef_ssim != 0 else None
         lib = _cabi.load_library()
         work = torch.empty(int(lib.gsb200_photometric_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
         out = torch.empty((), dtype=torch.float32, device=dev)
@@ -57,6 +58,7 @@ class _Photometric(torch.autograd.Function):
             call("gsb200_photometric_loss_fwd", B, H, W, CH, ptr(img1), ptr(img2), float(coef_l1), float(coef_ssim), float(bias),
                  int(valid), ptr(None if maps is None else maps[0]), ptr(None if maps is None else maps[1]),
                  ptr(None if maps is None else maps[2]), ptr(work), ptr(out), ptr(stats), stream_ptr(dev))
+        ctx.trained = keep
         if keep:
             ctx.save_for_backward(img1, img2, maps)
         ctx.coefs = (float(coef_l1), float(coef_ssim), bool(valid))
@@ -65,7 +67,7 @@ class _Photometric(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, v_loss, _v_stats):
-        if not ctx.saved_tensors:
+        if not ctx.trained:
             raise RuntimeError("photometric loss was evaluated with train=False; no gradient available")
         img1, img2, maps = ctx.saved_tensors
         coef_l1, coef_ssim, valid = ctx.coefs
@@ -73,8 +75,9 @@ class _Photometric(torch.autograd.Function):
         v_loss = v_loss.to(torch.float32).contiguous()
         v_img1 = torch.empty_like(img1)
         with torch.cuda.device(img1.device):
-            call("gsb200_photometric_loss_bwd", B, H, W, CH, ptr(img1), ptr(img2), coef_l1, coef_ssim, int(valid), ptr(maps[0]),
-                 ptr(maps[1]), ptr(maps[2]), ptr(v_loss), ptr(v_img1), stream_ptr(img1.device))
+            m = (None, None, None) if maps is None else (maps[0], maps[1], maps[2])
+            call("gsb200_photometric_loss_bwd", B, H, W, CH, ptr(img1), ptr(img2), coef_l1, coef_ssim, int(valid), ptr(m[0]),
+                 ptr(m[1]), ptr(m[2]), ptr(v_loss), ptr(v_img1), stream_ptr(img1.device))
         return v_img1, None, None, None, None, None, None
 
 
@@ -82,7 +85,8 @@ def photometric_loss(colors: Tensor, pixels: Tensor, ssim_lambda: float = 0.2, p
                      return_stats: bool = False):
     """``F.l1_loss(colors, pixels) * (1 - ssim_lambda) + (1 - fused_ssim(colors, pixels, padding)) * ssim_lambda`` for
     [B,H,W,CH] images (examples/simple_trainer.py:948-953) in one forward and one backward kernel.
-    With ``return_stats`` also returns a [2] tensor (L1 mean, SSIM mean) for logging."""
+    With ``return_stats`` also returns a [2] tensor (L1 mean, SSIM mean) for logging.  ``ssim_lambda == 0`` is a
+    pure L1 loss: the SSIM window is skipped altogether (the SSIM statistic is then reported as 0)."""
     assert padding in ("valid", "same"), padding
     loss, stats = _Photometric.apply(colors, pixels, 1.0 - ssim_lambda, -ssim_lambda, ssim_lambda, padding == "valid", True)
     return (loss, stats) if return_stats else loss
