@@ -102,24 +102,30 @@ photometric_fwd_kernel(LossGeom G, SsimWindow win, const float *__restrict__ img
             stage_window<2>(G, img_base, x0, y0, ch, src, dst);
         }
         __syncthreads();
-        // horizontal pass: item = (row r, column group cg); a warp covers 32 consecutive rows of one column group
-        for (int it = tid; it < (kTW / kColsPerItem) * 64; it += kLossThreads) {
-            const int cg = it >> 6, r = it & 63;
-            if (r < kSpanY) {
-                float xa[kTaps], ya[kTaps];
+        // horizontal pass: item = (row r, column group cg); the lanes of a warp cover consecutive rows
+        for (int it = tid; it < (kTW / kColsPerItem) * kSpanY; it += kLossThreads) {
+            const int cg = it / kSpanY, r = it - cg * kSpanY;
+            float h[kColsPerItem][5];
 #pragma unroll
-                for (int k = 0; k < kTaps; ++k) { xa[k] = sX[r][cg * kColsPerItem + k]; ya[k] = sY[r][cg * kColsPerItem + k]; }
+            for (int j = 0; j < kColsPerItem; ++j)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) h[j][q] = 0.f;
+#pragma unroll
+            for (int k = 0; k < kTaps; ++k) {  // every input and its three products are formed once
+                const float a = sX[r][cg * kColsPerItem + k], d = sY[r][cg * kColsPerItem + k];
+                const float aa = a * a, dd = d * d, ad = a * d;
 #pragma unroll
                 for (int j = 0; j < kColsPerItem; ++j) {
-                    float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
-#pragma unroll
-                    for (int k = 0; k < kWin; ++k) {
-                        const float a = xa[j + k], d = ya[j + k], w = win.w[k];
-                        h0 += w * a; h1 += w * d; h2 += w * a * a; h3 += w * d * d; h4 += w * a * d;
+                    if (k - j >= 0 && k - j < kWin) {
+                        const float w = win.w[k - j];
+                        h[j][0] += w * a; h[j][1] += w * d; h[j][2] += w * aa; h[j][3] += w * dd; h[j][4] += w * ad;
                     }
-                    const int c = cg * kColsPerItem + j;
-                    sH[0][r][c] = h0; sH[1][r][c] = h1; sH[2][r][c] = h2; sH[3][r][c] = h3; sH[4][r][c] = h4;
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < kColsPerItem; ++j) {
+                const int c = cg * kColsPerItem + j;
+                sH[0][r][c] = h[j][0]; sH[1][r][c] = h[j][1]; sH[2][r][c] = h[j][2]; sH[3][r][c] = h[j][3]; sH[4][r][c] = h[j][4];
             }
         }
         __syncthreads();
@@ -239,21 +245,19 @@ photometric_bwd_kernel(LossGeom G, SsimWindow win, const float *__restrict__ img
             stage_window<3>(G, img_base, x0, y0, ch, src, dst);
         }
         __syncthreads();
-        for (int it = tid; it < (kTW / kColsPerItem) * 64; it += kLossThreads) {
-            const int cg = it >> 6, r = it & 63;
-            if (r < kSpanY) {
+        for (int it = tid; it < (kTW / kColsPerItem) * kSpanY; it += kLossThreads) {
+            const int cg = it / kSpanY, r = it - cg * kSpanY;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    float ma[kTaps];
+            for (int q = 0; q < 3; ++q) {
+                float ma[kTaps];
 #pragma unroll
-                    for (int k = 0; k < kTaps; ++k) ma[k] = sM[q][r][cg * kColsPerItem + k];
+                for (int k = 0; k < kTaps; ++k) ma[k] = sM[q][r][cg * kColsPerItem + k];
 #pragma unroll
-                    for (int j = 0; j < kColsPerItem; ++j) {
-                        float h = 0.f;
+                for (int j = 0; j < kColsPerItem; ++j) {
+                    float h = 0.f;
 #pragma unroll
-                        for (int k = 0; k < kWin; ++k) h += win.w[k] * ma[j + k];
-                        sH[q][r][cg * kColsPerItem + j] = h;
-                    }
+                    for (int k = 0; k < kWin; ++k) h += win.w[k] * ma[j + k];
+                    sH[q][r][cg * kColsPerItem + j] = h;
                 }
             }
         }
