@@ -12,6 +12,7 @@ from .cuda._wrapper import (  # noqa: F401
     persp_proj,
     proj,
     quat_scale_to_covar_preci,
+    rasterize_to_indices_in_range,
     rasterize_to_pixels,
     spherical_harmonics,
     world_to_cam,
@@ -31,5 +32,6 @@ __all__ = [
     "proj",
     "persp_proj",
     "world_to_cam",
+    "rasterize_to_indices_in_range",
     "distributed",
 ]

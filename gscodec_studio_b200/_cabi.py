@@ -53,6 +53,8 @@ SIGNATURES = {
     "gsb200_grad_record": [_U],
     "gsb200_rasterize_bwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P,
                              _P, _P, _P, _P, _P, _P],
+    "gsb200_indices_in_range_count": [_U, _U, _U, _U, _L, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P],
+    "gsb200_indices_in_range_fill": [_U, _U, _U, _U, _L, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_fake_quantize_fwd": [_L, _P, _F, _F, _I, _I, _I, _P, c_uint64, c_uint64, _P, _P],
     "gsb200_fake_quantize_bwd": [_L, _P, _P, _F, _F, _I, _I, _P, _P, _P],
     "gsb200_entropy_fwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P],

@@ -774,6 +774,56 @@ def rasterize_to_pixels(
     return render_colors, render_alphas
 
 
+@torch.no_grad()
+def rasterize_to_indices_in_range(
+    range_start: int,
+    range_end: int,
+    transmittances: Tensor,  # [C, image_height, image_width]
+    means2d: Tensor,  # [C, N, 2]
+    conics: Tensor,  # [C, N, 3]
+    opacities: Tensor,  # [C, N]
+    image_width: int,
+    image_height: int,
+    tile_size: int,
+    isect_offsets: Tensor,  # [C, tile_height, tile_width]
+    flatten_ids: Tensor,  # [n_isects]
+) -> Tuple[Tensor, Tensor, Tensor]:
+    """Rasterizes a depth slice of the Gaussians but only returns who hits which pixel (reference:
+    _wrapper.py:572-643).  `[range_start, range_end)` counts batches of tile_size^2 intersections per tile; a
+    one-step full rasterization uses 0 and a very large number.  -> (gaussian_ids [M], pixel_ids [M] row-major,
+    camera_ids [M]), all int64, per pixel front to back."""
+    C, N, _ = means2d.shape
+    assert conics.shape == (C, N, 3), conics.shape
+    assert opacities.shape == (C, N), opacities.shape
+    assert isect_offsets.shape[0] == C, isect_offsets.shape
+    tile_height, tile_width = isect_offsets.shape[1:3]
+    assert tile_height * tile_size >= image_height, f"Assert Failed: {tile_height} * {tile_size} >= {image_height}"
+    assert tile_width * tile_size >= image_width, f"Assert Failed: {tile_width} * {tile_size} >= {image_width}"
+    assert transmittances.shape == (C, image_height, image_width), transmittances.shape
+    means2d, conics, opacities, transmittances = map(_f32, (means2d.detach(), conics.detach(), opacities.detach(),
+                                                            transmittances.detach()))
+    isect_offsets, flatten_ids = isect_offsets.contiguous(), flatten_ids.contiguous()
+    dev = means2d.device
+    n_isects = flatten_ids.numel()
+    rs = int(min(max(range_start, 0), 0xFFFFFFFF))
+    re = int(min(max(range_end, 0), 0xFFFFFFFF))
+    geom = (rs, re, C, N, n_isects, ptr(means2d), ptr(conics), ptr(opacities), image_width, image_height, tile_size,
+            tile_width, tile_height, ptr(isect_offsets), ptr(flatten_ids), ptr(transmittances))
+    chunk_cnts = torch.empty((C, image_height, image_width), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        call("gsb200_indices_in_range_count", *geom, ptr(chunk_cnts), stream_ptr(dev))
+        ends = torch.cumsum(chunk_cnts.view(-1), 0, dtype=torch.int64)
+        n_elems = int(ends[-1].item()) if ends.numel() else 0  # the host needs the size here, as in the reference
+        gaussian_ids = torch.empty(n_elems, dtype=torch.int64, device=dev)
+        out_indices = torch.empty(n_elems, dtype=torch.int64, device=dev)
+        if n_elems:
+            chunk_starts = (ends - chunk_cnts.view(-1)).contiguous()
+            call("gsb200_indices_in_range_fill", *geom, ptr(chunk_starts), ptr(gaussian_ids), ptr(out_indices), stream_ptr(dev))
+    out_pixel_ids = out_indices % (image_width * image_height)
+    out_camera_ids = out_indices // (image_width * image_height)
+    return gaussian_ids, out_pixel_ids, out_camera_ids
+
+
 class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, backgrounds, masks, width, height, tile_size, isect_offsets,

@@ -243,6 +243,26 @@ int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, c
                          float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                          gsb200_stream_t stream);
 
+/* replaces _C.rasterize_to_indices_in_range (bindings.h:217-232, rasterize_to_indices_in_range.cu:13-330), the op the
+ * reference's pure-torch rasterizer loops over (_torch_impl.py:522-617).  The slice [range_start, range_end) counts
+ * BATCHES of tile_size^2 intersections per tile; transmittances [C,H,W] is what the previous slices left.  Two calls
+ * where the reference synchronises for the output size: _count fills chunk_cnts i32 [C,H,W] (hits per pixel); the
+ * caller turns them into exclusive starts (int64 [C,H,W]) and allocates; _fill writes, per pixel front to back,
+ * gaussian_ids i64 [M] (index within the camera's N) and pixel_ids i64 [M] (pixel + camera * H * W). */
+int gsb200_indices_in_range_count(uint32_t range_start, uint32_t range_end, uint32_t C, uint32_t N,
+                                  int64_t n_isects, const float *means2d, const float *conics,
+                                  const float *opacities, uint32_t image_width, uint32_t image_height,
+                                  uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                                  const int32_t *tile_offsets, const int32_t *flatten_ids,
+                                  const float *transmittances, int32_t *chunk_cnts, gsb200_stream_t stream);
+int gsb200_indices_in_range_fill(uint32_t range_start, uint32_t range_end, uint32_t C, uint32_t N,
+                                 int64_t n_isects, const float *means2d, const float *conics,
+                                 const float *opacities, uint32_t image_width, uint32_t image_height,
+                                 uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                                 const int32_t *tile_offsets, const int32_t *flatten_ids,
+                                 const float *transmittances, const int64_t *chunk_starts,
+                                 int64_t *gaussian_ids, int64_t *pixel_ids, gsb200_stream_t stream);
+
 /* ---------------------------------------------------------------- quant-sim
  * replaces the torch elementwise chain of fake_quantize_ste (compression_simulation/ops.py:39-75).
  * mode 0 = "noise": y = act(clamp(x,lo,hi) + noise*q_step), noise [n] supplied or, if NULL, drawn

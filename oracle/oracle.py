@@ -664,3 +664,54 @@ def stg_temporal_transform(means, quats, scales, opacities, trbf_center, trbf_sc
     means_t = means + motion[:, 0:3] * dd + motion[:, 3:6] * dd * dd + motion[:, 6:9] * dd * dd * dd
     quats_t = F.normalize(quats + dd * omega)
     return means_t, quats_t, torch.exp(scales), opacity, trbf.squeeze(-1).detach()
+
+
+# --------------------------------------------------------------------------------------
+# rasterize_to_indices_in_range (gsplat/cuda/csrc/rasterize_to_indices_in_range.cu:13-176) restated; python loops,
+# for SMALL cases only
+# --------------------------------------------------------------------------------------
+def rasterize_to_indices_in_range(range_start, range_end, transmittances, means2d, conics, opacities, width, height,
+                                  tile_size, isect_offsets, flatten_ids):
+    """-> (gaussian_ids, pixel_ids, camera_ids) int64, per pixel (camera-major, row-major) front to back.  A slice is
+    counted in batches of tile_size^2 intersections per tile; float32 arithmetic like the kernel (expf, not __expf)."""
+    C, N = means2d.shape[0], means2d.shape[1]
+    th, tw = isect_offsets.shape[1:3]
+    m2 = means2d.reshape(-1, 2).numpy().astype(np.float32)
+    cn = conics.reshape(-1, 3).numpy().astype(np.float32)
+    op = opacities.reshape(-1).numpy().astype(np.float32)
+    offs = isect_offsets.reshape(-1).numpy()
+    fl = flatten_ids.numpy()
+    trans_in = transmittances.numpy().astype(np.float32)
+    n_isects = fl.shape[0]
+    block = tile_size * tile_size
+    gids, pids, cids = [], [], []
+    f32 = np.float32
+    for c in range(C):
+        for i in range(height):
+            for j in range(width):
+                tile = (i // tile_size) * tw + (j // tile_size)
+                ct = c * th * tw + tile
+                lo = int(offs[ct])
+                hi = n_isects if ct == C * th * tw - 1 else int(offs[ct + 1])
+                nb = (hi - lo + block - 1) // block
+                if range_start >= nb:
+                    continue
+                a, b = lo + block * range_start, min(hi, lo + block * min(range_end, nb))
+                T = trans_in[c, i, j]
+                px, py = f32(j + 0.5), f32(i + 0.5)
+                for idx in range(a, b):
+                    g = int(fl[idx])
+                    dx, dy = m2[g, 0] - px, m2[g, 1] - py
+                    sigma = f32(0.5) * (cn[g, 0] * dx * dx + cn[g, 2] * dy * dy) + cn[g, 1] * dx * dy
+                    alpha = min(f32(0.999), op[g] * np.exp(-sigma, dtype=np.float32))
+                    if sigma < 0 or alpha < f32(1.0 / 255.0):
+                        continue
+                    nT = T * (f32(1.0) - alpha)
+                    if nT <= f32(1e-4):
+                        break
+                    gids.append(g % N)
+                    pids.append(i * width + j)
+                    cids.append(c)
+                    T = nT
+    mk = lambda v: torch.tensor(v, dtype=torch.int64)
+    return mk(gids), mk(pids), mk(cids)

@@ -23,4 +23,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("isect_offset_encode", &gsplat::isect_offset_encode_tensor);
     m.def("rasterize_to_pixels_fwd", &gsplat::rasterize_to_pixels_fwd_tensor);
     m.def("rasterize_to_pixels_bwd", &gsplat::rasterize_to_pixels_bwd_tensor);
+    // SURVEY.md section 8(f) rows
+    m.def("rasterize_to_indices_in_range", &gsplat::rasterize_to_indices_in_range_tensor);
+    m.def("quat_scale_to_covar_preci_fwd", &gsplat::quat_scale_to_covar_preci_fwd_tensor);
+    m.def("quat_scale_to_covar_preci_bwd", &gsplat::quat_scale_to_covar_preci_bwd_tensor);
+    m.def("proj_fwd", &gsplat::proj_fwd_tensor);
+    m.def("proj_bwd", &gsplat::proj_bwd_tensor);
+    m.def("world_to_cam_fwd", &gsplat::world_to_cam_fwd_tensor);
+    m.def("world_to_cam_bwd", &gsplat::world_to_cam_bwd_tensor);
+    m.def("selective_adam_update", &gsplat::selective_adam_update);
+    m.def("compute_relocation", &gsplat::compute_relocation_tensor);
 }

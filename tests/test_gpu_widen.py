@@ -412,3 +412,177 @@ def test_dynamic_step_renders_like_torch_chain():
     assert close_frac(rc1, rc2, 1e-4) <= 5e-5 and rel_err(rc1, rc2) < 8e-3
     for x, y, n in zip(g1, g2, ("means", "quats", "scales", "opacities", "trbf_center", "trbf_scale", "motion", "omega")):
         assert close_frac(x, y, 1e-3) <= 1e-4 and rel_err(x, y) < 3e-2, n
+
+
+# ------------------------------------------------------------------------------- rasterize_to_indices_in_range (8f.4)
+def _indices_scene(C=2, step=8, W=None, H=None):
+    means, quats, scales, opac, colors, viewmats, Ks, w0, h0 = load_test_data(device="cpu", scene_grid=1)
+    sel = slice(0, None, step)
+    W, H = W or w0, H or h0
+    K = Ks[:C].clone()
+    K[:, 0, :] *= W / w0
+    K[:, 1, :] *= H / h0
+    dev = [t.to(DEV) for t in (means[sel], quats[sel], scales[sel], opac[sel], colors[sel])]
+    radii, means2d, depths, conics, _ = gs.fully_fused_projection(dev[0], None, dev[1], dev[2], viewmats[:C].to(DEV), K.to(DEV),
+                                                                  W, H, packed=False)
+    tw, th = -(-W // 16), -(-H // 16)
+    _, isect_ids, flatten_ids = gs.isect_tiles(means2d, radii, depths, 16, tw, th)
+    offsets = gs.isect_offset_encode(isect_ids, C, tw, th)
+    opacities = dev[3][None].expand(C, -1).contiguous()
+    colors_c = dev[4][None].expand(C, -1, -1).contiguous()
+    return means2d, conics, opacities, colors_c, offsets, flatten_ids, W, H
+
+
+def _ref_cuda_module():
+    import sys
+
+    path = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(path, "gsplat_ref_cuda.so")):
+        return None
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    try:
+        import gsplat_ref_cuda
+        return gsplat_ref_cuda if hasattr(gsplat_ref_cuda, "rasterize_to_indices_in_range") else None
+    except Exception:  # pragma: no cover
+        return None
+
+
+def test_indices_in_range_matches_oracle_small():
+    """Small image against the python restatement of rasterize_to_indices_in_range.cu: the full range and two
+    consecutive slices chained through the transmittances."""
+    means2d, conics, opacities, colors, offsets, flatten_ids, W, H = _indices_scene(C=2, step=30, W=80, H=48)
+    T0 = torch.ones(2, H, W, device=DEV)
+    cpu = lambda t: t.detach().cpu()
+    for rs, re in ((0, 10 ** 9), (0, 1), (1, 3)):
+        got = gs.rasterize_to_indices_in_range(rs, re, T0, means2d, conics, opacities, W, H, 16, offsets, flatten_ids)
+        ref = O.rasterize_to_indices_in_range(rs, re, cpu(T0), cpu(means2d), cpu(conics), cpu(opacities), W, H, 16,
+                                              cpu(offsets), cpu(flatten_ids))
+        a = torch.stack([cpu(t) for t in got], 1)
+        b = torch.stack(list(ref), 1)
+        if a.shape == b.shape:
+            assert (a != b).any(1).double().mean().item() < 1e-3, (rs, re)  # expf vs __expf at the 1/255 cut
+        else:
+            assert abs(a.shape[0] - b.shape[0]) <= max(2, int(1e-3 * b.shape[0])), (rs, re, a.shape, b.shape)
+        assert got[0].dtype == torch.int64 and got[1].max().item() < W * H and got[2].max().item() < 2
+
+
+def test_indices_in_range_reproduces_the_blend_and_the_reference():
+    """Full-range indices + a torch accumulation of alpha * T * colour equal rasterize_to_pixels on the same inputs
+    (648x420, 2 views); slices chained through their transmittances partition the full list; and, when the reference
+    CUDA module travelled with the repo, all three outputs are bit-identical to the reference kernel's."""
+    means2d, conics, opacities, colors, offsets, flatten_ids, W, H = _indices_scene(C=2, step=3)
+    C = 2
+    T0 = torch.ones(C, H, W, device=DEV)
+    gids, pids, cids = gs.rasterize_to_indices_in_range(0, 10 ** 9, T0, means2d, conics, opacities, W, H, 16, offsets, flatten_ids)
+    rc, ra = gs.rasterize_to_pixels(means2d, conics, colors, opacities, W, H, 16, offsets, flatten_ids)
+    # per-hit alpha in float64, per-pixel exclusive transmittance through a segmented cumulative sum of log(1 - alpha)
+    px = (pids % W).double() + 0.5
+    py = (pids // W).double() + 0.5
+    mu, cn = means2d[cids, gids].double(), conics[cids, gids].double()
+    dx, dy = mu[:, 0] - px, mu[:, 1] - py
+    sigma = 0.5 * (cn[:, 0] * dx * dx + cn[:, 2] * dy * dy) + cn[:, 1] * dx * dy
+    alpha = torch.clamp(opacities[cids, gids].double() * torch.exp(-sigma), max=0.999)
+    lin = cids * (H * W) + pids
+    assert (lin[1:] >= lin[:-1]).all()  # grouped per pixel, camera-major
+    logs = torch.log1p(-alpha)
+    cum = torch.cumsum(logs, 0) - logs
+    first = torch.ones_like(lin, dtype=torch.bool)
+    first[1:] = lin[1:] != lin[:-1]
+    seg_start = torch.cummax(torch.where(first, torch.arange(lin.numel(), device=DEV), torch.zeros_like(lin)), 0)[0]
+    Tk = torch.exp(cum - cum[seg_start])
+    wgt = (alpha * Tk)
+    img = torch.zeros(C * H * W, 3, dtype=torch.float64, device=DEV).index_add_(0, lin, wgt[:, None] * colors[cids, gids].double())
+    acc = torch.zeros(C * H * W, dtype=torch.float64, device=DEV).index_add_(0, lin, wgt)
+    assert rel_err(img.view(C, H, W, 3), rc) < 1e-4 and rel_err(acc.view(C, H, W, 1), ra) < 1e-4
+    # two slices: [0, 1) then [1, inf) starting from the transmittance the first one left
+    g1, p1, c1 = gs.rasterize_to_indices_in_range(0, 1, T0, means2d, conics, opacities, W, H, 16, offsets, flatten_ids)
+    lin1 = c1 * (H * W) + p1
+    mu1, cn1 = means2d[c1, g1], conics[c1, g1]
+    dx1, dy1 = mu1[:, 0] - ((p1 % W).float() + 0.5), mu1[:, 1] - ((p1 // W).float() + 0.5)
+    a1 = torch.clamp(opacities[c1, g1] * torch.exp(-(0.5 * (cn1[:, 0] * dx1 * dx1 + cn1[:, 2] * dy1 * dy1) + cn1[:, 1] * dx1 * dy1)),
+                     max=0.999)
+    T1 = torch.exp(torch.zeros(C * H * W, dtype=torch.float64, device=DEV).index_add_(0, lin1, torch.log1p(-a1.double())))
+    g2, p2, c2 = gs.rasterize_to_indices_in_range(1, 10 ** 9, T1.float().view(C, H, W), means2d, conics, opacities, W, H, 16,
+                                                  offsets, flatten_ids)
+    assert abs((g1.numel() + g2.numel()) - gids.numel()) <= max(4, int(2e-5 * gids.numel()))  # T handed over in float32
+    ref = _ref_cuda_module()
+    if ref is not None:
+        r_g, r_idx = ref.rasterize_to_indices_in_range(0, 10 ** 9, T0, means2d, conics, opacities, W, H, 16, offsets, flatten_ids)
+        assert torch.equal(r_g, gids) and torch.equal(r_idx, lin)
+        r_g, r_idx = ref.rasterize_to_indices_in_range(0, 1, T0, means2d, conics, opacities, W, H, 16, offsets, flatten_ids)
+        assert torch.equal(r_g, g1) and torch.equal(r_idx, lin1)
+
+
+def test_widen_ops_match_reference_cuda_live():
+    """The section-8(f) ops against the UNMODIFIED reference CUDA kernels run on the same GPU (oracle/_ref module,
+    when it travelled with the repo): un-fused geometry ops forward + backward, selective Adam, relocation."""
+    ref = _ref_cuda_module()
+    if ref is None or not hasattr(ref, "proj_fwd"):
+        pytest.skip("reference CUDA module with the 8(f) symbols not available")
+    G = _golden_geom()
+    d = lambda k: G[k].to(DEV).contiguous()
+    # quat_scale_to_covar_preci
+    for triu in (False, True):
+        tag = "triu" if triu else "full"
+        q, s = d("quats").requires_grad_(True), d("scales").requires_grad_(True)
+        cov, pre = gs.quat_scale_to_covar_preci(q, s, True, True, triu)
+        r_cov, r_pre = ref.quat_scale_to_covar_preci_fwd(d("quats"), d("scales"), True, True, triu)
+        assert rel_err(cov, r_cov) < 1e-5 and rel_err(pre, r_pre) < 1e-5
+        wc, wp = d(f"qs_{tag}_wc"), d(f"qs_{tag}_wp")
+        ((cov * wc).sum() + (pre * wp).sum()).backward()
+        r_vq, r_vs = ref.quat_scale_to_covar_preci_bwd(d("quats"), d("scales"), wc, wp, triu)
+        assert rel_err(q.grad, r_vq) < 1e-4 and rel_err(s.grad, r_vs) < 1e-4
+    # world_to_cam
+    m, c, v = (d(k).requires_grad_(True) for k in ("w2c_means", "w2c_covars", "w2c_viewmats"))
+    mc, cc = gs.world_to_cam(m, c, v)
+    r_mc, r_cc = ref.world_to_cam_fwd(d("w2c_means"), d("w2c_covars"), d("w2c_viewmats"))
+    assert rel_err(mc, r_mc) < 1e-5 and rel_err(cc, r_cc) < 1e-5
+    ((mc * d("w2c_wm")).sum() + (cc * d("w2c_wc")).sum()).backward()
+    r_vm, r_vc, r_vv = ref.world_to_cam_bwd(d("w2c_means"), d("w2c_covars"), d("w2c_viewmats"), d("w2c_wm"), d("w2c_wc"),
+                                            True, True, True)
+    assert rel_err(m.grad, r_vm) < 1e-4 and rel_err(c.grad, r_vc) < 1e-4 and rel_err(v.grad, r_vv) < 1e-3
+    # proj, three camera models
+    W, H = int(G["W"]), int(G["H"])
+    for name, cm in (("pinhole", ref.CameraModelType.PINHOLE), ("ortho", ref.CameraModelType.ORTHO),
+                     ("fisheye", ref.CameraModelType.FISHEYE)):
+        a, b = d("proj_means").requires_grad_(True), d("proj_covars").requires_grad_(True)
+        m2, c2 = gs.proj(a, b, d("proj_Ks"), W, H, name)
+        r_m2, r_c2 = ref.proj_fwd(d("proj_means"), d("proj_covars"), d("proj_Ks"), W, H, cm)
+        assert rel_err(m2, r_m2) < 1e-5 and rel_err(c2, r_c2) < 1e-4, name
+        w1, w2 = d(f"proj_{name}_w1"), d(f"proj_{name}_w2")
+        ((m2 * w1).sum() + (c2 * w2).sum()).backward()
+        r_va, r_vb = ref.proj_bwd(d("proj_means"), d("proj_covars"), d("proj_Ks"), W, H, cm, w1, w2)
+        assert rel_err(a.grad, r_va) < 1e-3 and rel_err(b.grad, r_vb) < 1e-4, name
+    # selective Adam: same float32 formula -> (near) bit-identical state after three steps
+    from gscodec_studio_b200.cuda._wrapper import selective_adam_update
+
+    g = torch.Generator().manual_seed(31)
+    N, M = 4001, 3
+    p_a = torch.randn(N, M, generator=g).to(DEV)
+    p_b = p_a.clone()
+    st_a = [torch.zeros_like(p_a), torch.zeros_like(p_a)]
+    st_b = [torch.zeros_like(p_a), torch.zeros_like(p_a)]
+    for _ in range(3):
+        grad = (torch.randn(N, M, generator=g) * 1e-3).to(DEV)
+        vis = (torch.rand(N, generator=g) > 0.4).to(DEV)
+        selective_adam_update(p_a, grad, st_a[0], st_a[1], vis, 1e-3, 0.9, 0.999, 1e-15, N, M)
+        ref.selective_adam_update(p_b, grad, st_b[0], st_b[1], vis, 1e-3, 0.9, 0.999, 1e-15, N, M)
+    assert rel_err(st_a[0], st_b[0]) < 1e-6 and rel_err(st_a[1], st_b[1]) < 1e-6 and rel_err(p_a, p_b) < 1e-6
+    # relocation
+    import math
+
+    from gscodec_studio_b200.relocation import compute_relocation
+
+    n_max = 51
+    binoms = torch.zeros(n_max, n_max)
+    for n in range(n_max):
+        for k in range(n + 1):
+            binoms[n, k] = math.comb(n, k)
+    binoms = binoms.to(DEV)
+    opac = (torch.rand(3000, generator=g) * 0.98 + 0.01).to(DEV)
+    scales = (torch.rand(3000, 3, generator=g) * 0.1).to(DEV)
+    ratios = torch.randint(1, 9, (3000,), generator=g).to(DEV)
+    new_o, new_s = compute_relocation(opac, scales, ratios.clone(), binoms)
+    r_o, r_s = ref.compute_relocation(opac, scales, ratios.int(), binoms, n_max)
+    assert rel_err(new_o, r_o) < 1e-5 and rel_err(new_s, r_s) < 1e-4
