@@ -469,8 +469,8 @@ def test_indices_in_range_matches_oracle_small():
 
 def test_indices_in_range_reproduces_the_blend_and_the_reference():
     """Full-range indices + a torch accumulation of alpha * T * colour equal rasterize_to_pixels on the same inputs
-    (648x420, 2 views); slices chained through their transmittances partition the full list; and, when the reference
-    CUDA module travelled with the repo, all three outputs are bit-identical to the reference kernel's."""
+    (648x420, 2 views); and, when the reference CUDA module travelled with the repo, the outputs of the full range and
+    of two slices chained through their transmittances are bit-identical to the reference kernel's."""
     means2d, conics, opacities, colors, offsets, flatten_ids, W, H = _indices_scene(C=2, step=3)
     C = 2
     T0 = torch.ones(C, H, W, device=DEV)
@@ -505,13 +505,15 @@ def test_indices_in_range_reproduces_the_blend_and_the_reference():
     T1 = torch.exp(torch.zeros(C * H * W, dtype=torch.float64, device=DEV).index_add_(0, lin1, torch.log1p(-a1.double())))
     g2, p2, c2 = gs.rasterize_to_indices_in_range(1, 10 ** 9, T1.float().view(C, H, W), means2d, conics, opacities, W, H, 16,
                                                   offsets, flatten_ids)
-    assert abs((g1.numel() + g2.numel()) - gids.numel()) <= max(4, int(2e-5 * gids.numel()))  # T handed over in float32
+    # (chained slices are NOT a partition of the full list, in the reference either: a pixel that stopped inside the
+    # first slice starts the next one from a transmittance just above 1e-4 and may take further, fainter hits)
+    assert 0 < g1.numel() < gids.numel() and g2.numel() > 0
     ref = _ref_cuda_module()
     if ref is not None:
-        r_g, r_idx = ref.rasterize_to_indices_in_range(0, 10 ** 9, T0, means2d, conics, opacities, W, H, 16, offsets, flatten_ids)
-        assert torch.equal(r_g, gids) and torch.equal(r_idx, lin)
-        r_g, r_idx = ref.rasterize_to_indices_in_range(0, 1, T0, means2d, conics, opacities, W, H, 16, offsets, flatten_ids)
-        assert torch.equal(r_g, g1) and torch.equal(r_idx, lin1)
+        T1f = T1.float().view(C, H, W).contiguous()
+        for (rs, re, T_in, mine) in ((0, 10 ** 9, T0, (gids, lin)), (0, 1, T0, (g1, lin1)), (1, 10 ** 9, T1f, (g2, c2 * (H * W) + p2))):
+            r_g, r_idx = ref.rasterize_to_indices_in_range(rs, re, T_in, means2d, conics, opacities, W, H, 16, offsets, flatten_ids)
+            assert torch.equal(r_g, mine[0]) and torch.equal(r_idx, mine[1]), (rs, re)
 
 
 def test_widen_ops_match_reference_cuda_live():
@@ -533,27 +535,31 @@ def test_widen_ops_match_reference_cuda_live():
         ((cov * wc).sum() + (pre * wp).sum()).backward()
         r_vq, r_vs = ref.quat_scale_to_covar_preci_bwd(d("quats"), d("scales"), wc, wp, triu)
         assert rel_err(q.grad, r_vq) < 1e-4 and rel_err(s.grad, r_vs) < 1e-4
-    # world_to_cam
-    m, c, v = (d(k).requires_grad_(True) for k in ("w2c_means", "w2c_covars", "w2c_viewmats"))
+    # world_to_cam.  The reference CUDA kernels read a row-major [3,3] matrix into glm's column-major mat3, i.e. they
+    # see the TRANSPOSE of a non-symmetric "covariance" (their own torch implementation does not); the two agree
+    # for symmetric matrices, which is what the comparison uses -- inputs, upstream weights and gradients symmetrised.
+    sym = lambda t: 0.5 * (t + t.transpose(-1, -2))
+    cov_s, wc_s = sym(d("w2c_covars")).contiguous(), sym(d("w2c_wc")).contiguous()
+    m, c, v = d("w2c_means").requires_grad_(True), cov_s.clone().requires_grad_(True), d("w2c_viewmats").requires_grad_(True)
     mc, cc = gs.world_to_cam(m, c, v)
-    r_mc, r_cc = ref.world_to_cam_fwd(d("w2c_means"), d("w2c_covars"), d("w2c_viewmats"))
+    r_mc, r_cc = ref.world_to_cam_fwd(d("w2c_means"), cov_s, d("w2c_viewmats"))
     assert rel_err(mc, r_mc) < 1e-5 and rel_err(cc, r_cc) < 1e-5
-    ((mc * d("w2c_wm")).sum() + (cc * d("w2c_wc")).sum()).backward()
-    r_vm, r_vc, r_vv = ref.world_to_cam_bwd(d("w2c_means"), d("w2c_covars"), d("w2c_viewmats"), d("w2c_wm"), d("w2c_wc"),
-                                            True, True, True)
-    assert rel_err(m.grad, r_vm) < 1e-4 and rel_err(c.grad, r_vc) < 1e-4 and rel_err(v.grad, r_vv) < 1e-3
+    ((mc * d("w2c_wm")).sum() + (cc * wc_s).sum()).backward()
+    r_vm, r_vc, r_vv = ref.world_to_cam_bwd(d("w2c_means"), cov_s, d("w2c_viewmats"), d("w2c_wm"), wc_s, True, True, True)
+    assert rel_err(m.grad, r_vm) < 1e-4 and rel_err(sym(c.grad), sym(r_vc)) < 1e-4 and rel_err(v.grad, r_vv) < 1e-3
     # proj, three camera models
     W, H = int(G["W"]), int(G["H"])
     for name, cm in (("pinhole", ref.CameraModelType.PINHOLE), ("ortho", ref.CameraModelType.ORTHO),
                      ("fisheye", ref.CameraModelType.FISHEYE)):
-        a, b = d("proj_means").requires_grad_(True), d("proj_covars").requires_grad_(True)
+        pc_s = sym(d("proj_covars")).contiguous()
+        a, b = d("proj_means").requires_grad_(True), pc_s.clone().requires_grad_(True)
         m2, c2 = gs.proj(a, b, d("proj_Ks"), W, H, name)
-        r_m2, r_c2 = ref.proj_fwd(d("proj_means"), d("proj_covars"), d("proj_Ks"), W, H, cm)
+        r_m2, r_c2 = ref.proj_fwd(d("proj_means"), pc_s, d("proj_Ks"), W, H, cm)
         assert rel_err(m2, r_m2) < 1e-5 and rel_err(c2, r_c2) < 1e-4, name
-        w1, w2 = d(f"proj_{name}_w1"), d(f"proj_{name}_w2")
+        w1, w2 = d(f"proj_{name}_w1"), sym(d(f"proj_{name}_w2")).contiguous()
         ((m2 * w1).sum() + (c2 * w2).sum()).backward()
-        r_va, r_vb = ref.proj_bwd(d("proj_means"), d("proj_covars"), d("proj_Ks"), W, H, cm, w1, w2)
-        assert rel_err(a.grad, r_va) < 1e-3 and rel_err(b.grad, r_vb) < 1e-4, name
+        r_va, r_vb = ref.proj_bwd(d("proj_means"), pc_s, d("proj_Ks"), W, H, cm, w1, w2)
+        assert rel_err(a.grad, r_va) < 1e-3 and rel_err(sym(b.grad), sym(r_vb)) < 1e-4, name
     # selective Adam: same float32 formula -> (near) bit-identical state after three steps
     from gscodec_studio_b200.cuda._wrapper import selective_adam_update
 
