@@ -159,9 +159,18 @@ def stage_timing_ms() -> dict:
     return {name: sum(a.elapsed_time(b) for a, b in evs) / len(evs) for name, evs in _stage_events.items() if evs}
 
 
+_NVTX = os.environ.get("GSB200_NVTX", "0") == "1"  # one NVTX range per C-ABI call (Nsight timelines)
+
+
 def call(name: str, *args) -> None:
     lib = load_library()
-    if _stage_events is not None:
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+        try:
+            rc = getattr(lib, name)(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    elif _stage_events is not None:
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         rc = getattr(lib, name)(*args)

@@ -105,3 +105,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["metric"].startswith("Mpix/s fwd+bwd")
+
+
+def test_profile_helpers_are_inert_without_timeit(monkeypatch):
+    """gscodec_studio_b200.profile mirrors gsplat/profile.py's surface; without TIMEIT=1 it must cost nothing and
+    record nothing (and never touch CUDA)."""
+    from gscodec_studio_b200 import profile
+
+    monkeypatch.delenv("TIMEIT", raising=False)
+    profile.profiler.clear()
+
+    @profile.timeit()
+    def f(x):
+        return x + 1
+
+    with profile.timeit(name="region"):
+        assert f(1) == 2
+    assert profile.profiler_summary() == {} and f.__name__ == "f"
