@@ -19,8 +19,6 @@ Both run the CUDA kernels of ``csrc/loss.cu`` through the C-ABI; there is no CPU
 """
 from __future__ import annotations
 
-from typing import Tuple
-
 import torch
 from torch import Tensor
 

@@ -2,7 +2,6 @@
 tests/test_gpu_parity.py (test garden, quant-sim) and tests/test_gpu_widen.py (dynamic splats); the 8-GPU form of
 config 5 is tools/dist_check.py under torchrun."""
 import math
-import os
 
 import pytest
 import torch
