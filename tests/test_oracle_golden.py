@@ -271,3 +271,57 @@ def test_geom_ops_oracle_matches_reference_torch_impl(golden_dir):
         assert _rel(m2, G[f"proj_{name}_means2d"]) < 1e-5 and _rel(c2, G[f"proj_{name}_covars2d"]) < 1e-5, name
         ((m2 * G[f"proj_{name}_w1"]).sum() + (c2 * G[f"proj_{name}_w2"]).sum()).backward()
         assert _rel(a.grad, G[f"proj_{name}_v_means"]) < 1e-4 and _rel(b.grad, G[f"proj_{name}_v_covars"]) < 1e-5, name
+
+
+# ------------------------------------------------------------------------------- hash-grid entropy model oracle (prep)
+def test_hashgrid_oracle_properties():
+    """oracle/hashgrid.py (restatement of the reference's third-party grid encoder; UNPINNED until it can be run next
+    to the reference extension on a GPU): exact value on grid nodes, zero for out-of-range inputs, the embedding
+    gradient is the adjoint of the interpolation, the input gradient is the multilinear derivative."""
+    from oracle import hashgrid as H
+
+    g = torch.Generator().manual_seed(0)
+    res, D = (6, 9), 3
+    offs = H.grid_layout(D, res, 13)
+    assert offs == [0, 216, 216 + 736]  # 6^3 = 216 (already a multiple of 8), 9^3 = 729 -> 736
+    emb = torch.randn(offs[-1], 2, generator=g)
+    node = torch.tensor([[2, 3, 1]])
+    out, _, coef, _ = H.encode_level((node.float() - 0.5) / (res[0] - 2), emb[:216], res[0], False)
+    assert torch.equal(out[0], emb[H.grid_index(node, 216, res[0])][0]) and coef.sum().item() == 1.0
+    assert H.grid_encode(torch.tensor([[1.2, 0.5, 0.5], [0.5, -0.1, 0.5]]), emb, offs, res).abs().max().item() == 0.0
+    # hashed level: 33^3 > 2^13 entries -> XOR-of-primes hash, always inside the table
+    big = H.grid_index(torch.randint(0, 33, (1000, 3), generator=g), 8192, 33)
+    assert big.min().item() >= 0 and big.max().item() < 8192
+    assert H.grid_index(torch.tensor([[1, 2, 3]]), 8192, 33).item() == ((1 * 1) ^ ((2 * 2654435761) & 0xFFFFFFFF) ^ ((3 * 805459861) & 0xFFFFFFFF)) % 8192
+    x = torch.rand(64, D, generator=g) * 0.5 + 0.25
+    xi, ei = x.clone().requires_grad_(True), emb.clone().requires_grad_(True)
+    o = H.grid_encode(xi, ei, offs, res)
+    w = torch.randn(o.shape, generator=g)
+    (o * w).sum().backward()
+    e2 = emb.clone().requires_grad_(True)
+    parts = []
+    for lvl, r in enumerate(res):
+        table = e2[offs[lvl]:offs[lvl + 1]]
+        _, rows, coef, _ = H.encode_level(x, table.detach(), r, False)
+        parts.append((coef[..., None] * table[rows]).sum(1))
+    (torch.cat(parts, 1) * w).sum().backward()
+    assert torch.allclose(ei.grad, e2.grad, atol=1e-6)
+    eps, fd = 1e-3, torch.zeros_like(x)
+    inside = torch.ones(64, dtype=torch.bool)
+    for d in range(D):
+        xp, xm = x.clone(), x.clone()
+        xp[:, d] += eps
+        xm[:, d] -= eps
+        fd[:, d] = ((H.grid_encode(xp, emb, offs, res) - H.grid_encode(xm, emb, offs, res)) * w).sum(-1) / (2 * eps)
+        for r in res:
+            c0 = H._level_terms(x, r)[0]
+            inside &= (H._level_terms(xp, r)[0] == c0).all(-1) & (H._level_terms(xm, r)[0] == c0).all(-1)
+    assert inside.sum().item() > 32
+    assert (xi.grad - fd)[inside].abs().max().item() < 1e-2 * fd.abs().max().item()
+    # the whole estimator + Gaussian rate runs and differentiates
+    est = H.HashBasedEstimator(3)
+    pos = (torch.randn(50, 3, generator=g) * 3).requires_grad_(True)
+    mean, scale = est(pos)
+    bits = H.entropy_gaussian_bits(torch.randn(50, 3, generator=g), 0.05, mean, scale.abs() + 0.1)
+    bits.sum().backward()
+    assert bits.shape == (50, 3) and torch.isfinite(bits).all() and est.encoding_xy.params.grad.abs().sum().item() > 0
