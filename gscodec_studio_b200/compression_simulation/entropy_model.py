@@ -122,12 +122,64 @@ Entropy_factorized = Entropy_factorized_optimized_refactor
 Entropy_factorized_optimized = Entropy_factorized_optimized_refactor
 
 
-class Entropy_gaussian(nn.Module):
-    """Hash-grid conditioned Gaussian entropy model (entropy_model.py:313-345).  It depends on the
-    third-party `_gridencoder` extension and is outside the round-1 hot path."""
+class _LowerBoundFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, bound):
+        ctx.save_for_backward(inputs)
+        ctx.bound = bound
+        return torch.clamp_min(inputs, bound)
 
-    def __init__(self, *args, **kwargs):
+    @staticmethod
+    def backward(ctx, grad_output):
+        (inputs,) = ctx.saved_tensors
+        passes = (inputs >= ctx.bound) | (grad_output < 0)  # the bound still lets the value be pushed up
+        return passes.type(grad_output.dtype) * grad_output, None
+
+
+class LowerBound(nn.Module):
+    """max(x, bound) whose gradient still flows when it moves x towards the feasible side (reference
+    entropy_model.py:347-390); used by the hash-grid model only -- the factorized model has it fused in its kernel."""
+
+    def __init__(self, bound):
         super().__init__()
-        raise NotImplementedError(
-            "gscodec_studio_b200: entropy_model_type='gaussian_model' (hash-grid Entropy_gaussian) is not built yet; "
-            "use the default 'factorized_model'")
+        self.register_buffer("bound", torch.Tensor([float(bound)]))  # a buffer, as in the reference's state_dict
+        self._bound = float(bound)
+
+    def forward(self, x):
+        return _LowerBoundFn.apply(x, self._bound)
+
+
+class Entropy_gaussian(nn.Module):
+    """Hash-grid conditioned Gaussian entropy model (reference entropy_model.py:313-345): a hash-grid + MLP regressor
+    predicts a per-channel (mean, scale) from the Gaussian's position, the rate is -log2 of the Normal mass of the
+    quantisation bin.  EXPERIMENTAL: the grid kernels have not been validated on a GPU and
+    their restatement is not pinned against the reference's CUDA-only `_gridencoder`, so constructing the model needs
+    GSB200_EXPERIMENTAL_HASHGRID=1; otherwise it raises like before."""
+
+    def __init__(self, channel=3, Q=1, likelihood_bound=1e-6):
+        super().__init__()
+        from .gaussian_distribution_model import experimental_enabled, hash_based_estimator
+
+        if not experimental_enabled():
+            raise NotImplementedError(
+                "gscodec_studio_b200: entropy_model_type='gaussian_model' (hash-grid Entropy_gaussian) is experimental and "
+                "unvalidated; set GSB200_EXPERIMENTAL_HASHGRID=1 to try it, or use the default 'factorized_model'")
+        self.Q = Q
+        self.likelihood_lower_bound = LowerBound(likelihood_bound)
+        self.mean, self.scale = 0, 1
+        self.param_regressor = hash_based_estimator(channel)
+
+    def forward(self, x, Q=None, pos=None):
+        assert pos is not None
+        assert x.size()[0] == pos.size()[0]
+        self.mean, self.scale = self.param_regressor(pos)
+        self.scale = torch.clamp(self.scale, min=1e-9)
+        normal = torch.distributions.normal.Normal(self.mean, self.scale)
+        if Q is None:
+            Q = self.Q
+        likelihood = torch.abs(normal.cdf(x + 0.5 * Q) - normal.cdf(x - 0.5 * Q))
+        return -torch.log2(self.likelihood_lower_bound(likelihood))
+
+    def get_means_and_scales(self, pos):
+        means, scales = self.param_regressor(pos)
+        return means, torch.clamp(scales, min=1e-9)

@@ -80,24 +80,45 @@ class _SimulationBase:
                     self.entropy_model_option[name] = False
         if not entropy_model_enable:
             return
-        if entropy_model_type == "gaussian_model":
-            Entropy_gaussian()
-        elif entropy_model_type != "factorized_model":
+        if entropy_model_type not in ("factorized_model", "gaussian_model"):
             raise NotImplementedError("Not implemented entropy model type")
+        self.entropy_model_type = entropy_model_type
         self.entropy_models = {}
         self.entropy_model_optimizers = {}
         self.entropy_model_schedulers = {}
         for name, p in self.policy.items():
-            model = None
+            model, opt, sch = None, None, None
             if p.entropy:
                 ch = {"quats": 4}.get(name, 3)
-                model = Entropy_factorized_optimized_refactor(channel=ch, filters=p.entropy_filters).to(device)
+                if entropy_model_type == "gaussian_model":
+                    # hash-grid conditioned Gaussian model (simulation.py:99-107, optimizer :124-128, scheduler :142-145);
+                    # experimental: the constructor raises unless GSB200_EXPERIMENTAL_HASHGRID=1
+                    model = Entropy_gaussian(channel=ch).to(device)
+                    opt = torch.optim.Adam([
+                        {"params": model.param_regressor.hash_grid.parameters(), "lr": 5e-3, "name": "hash_grid"},
+                        {"params": model.param_regressor.mlp_regressor.parameters(), "lr": 5e-3, "name": "mlp_regressor"}])
+                    sch = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.01 ** (1.0 / (30000 - entropy_steps[name])))
+                else:
+                    model = Entropy_factorized_optimized_refactor(channel=ch, filters=p.entropy_filters).to(device)
+                    opt = torch.optim.Adam([{"params": prm, "lr": 1e-4, "name": n} for n, prm in model.named_parameters()])
             self.entropy_models[name] = model
-            self.entropy_model_optimizers[name] = None if model is None else torch.optim.Adam(
-                [{"params": prm, "lr": 1e-4, "name": n} for n, prm in model.named_parameters()])
-            self.entropy_model_schedulers[name] = None
+            self.entropy_model_optimizers[name] = opt
+            self.entropy_model_schedulers[name] = sch
         positive = [k for k, v in entropy_steps.items() if v > 0]
         self.entropy_min_step = entropy_steps[min(positive, key=lambda k: entropy_steps[k])] if positive else 0
+
+    # ---- position sampling of the hash-grid model (simulation.py:185-204; the trainer calls _estiblish_bbox, sic)
+    def _estiblish_bbox(self, pos: Tensor, k: float = 1.5):
+        self.bbox_lower_bound, self.bbox_upper_bound = torch.quantile(pos, torch.tensor([0.01, 0.99], device=pos.device), dim=0)
+
+    def _get_pts_inside_bbox(self, pos: Tensor) -> Tensor:
+        return torch.all((pos >= self.bbox_lower_bound) & (pos <= self.bbox_upper_bound), dim=1)
+
+    def _random_sample_pts(self, mask: Tensor, ratio: float = 0.05) -> Tensor:
+        random_values = torch.rand_like(mask.float())
+        random_values[~mask] = 0
+        threshold = torch.quantile(random_values[mask], 1 - ratio)
+        return random_values >= threshold
 
     def _setup_mask(self, ada_mask_opt, ada_mask_step, strategy, device, kwargs):
         self.shN_qat = False
@@ -122,7 +143,7 @@ class _SimulationBase:
 
     # ------------------------------------------------------------------ the one routine
     def _simulate_attr(self, name: str, param: Tensor, step: int, q_type: Optional[str], noise: Optional[Tensor],
-                       fuse_act: bool):
+                       fuse_act: bool, choose_idx: Optional[Tensor] = None, pos: Optional[Tensor] = None):
         p = self.policy[name]
         lo, hi = p.bounds
         bits = 8 if step < 10_000 else p.bits  # simulation.py:242-245 (both branches give 8 today)
@@ -139,16 +160,25 @@ class _SimulationBase:
                 flat = value.squeeze(1)
             elif p.entropy_view == "unsqueeze":
                 flat = value.unsqueeze(1)
-            esti_bits = self.entropy_models[name](flat, fq["q_step"])
+            if choose_idx is not None:  # hash-grid model: rate of a ~5 % random sample, conditioned on the positions
+                esti_bits = self.entropy_models[name](flat[choose_idx], fq["q_step"], pos=pos)
+            else:
+                esti_bits = self.entropy_models[name](flat, fq["q_step"])
         return value, esti_bits, act
 
     def _simulate(self, splats: Dict[str, Tensor], step: int, q_type, noise, fuse_activations):
         new_splats, esti_bits_dict = {}, {}
+        choose_idx, pos = None, None
+        if (self.entropy_model_enable and getattr(self, "entropy_model_type", "factorized_model") == "gaussian_model"
+                and step > self.entropy_min_step):
+            choose_idx = self._random_sample_pts(self._get_pts_inside_bbox(splats["means"]))  # simulation.py:216-220
+            pos = splats["means"][choose_idx]
         for name in splats.keys():
             esti_bits_dict[name] = None
             if self.policy[name].bounds is not None and self.simulation_option[name]:
                 value, bits, act = self._simulate_attr(name, splats[name], step, q_type,
-                                                       None if noise is None else noise.get(name), fuse_activations)
+                                                       None if noise is None else noise.get(name), fuse_activations,
+                                                       choose_idx, pos)
                 new_splats[name + "_act" if act is not None else name] = value
                 esti_bits_dict[name] = bits
             elif name in self.returns_self:

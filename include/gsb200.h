@@ -292,6 +292,23 @@ int gsb200_entropy_bwd(int64_t N, uint32_t ch, uint32_t n_hidden, const float *x
                        const float *params, float likelihood_bound, const float *v_bits, float *v_x,
                        float *v_params, gsb200_stream_t stream);
 
+/* ---------------------------------------------------------------- hash-grid encoder -- EXPERIMENTAL
+ * Not yet validated on a GPU; the Python layer only reaches it with GSB200_EXPERIMENTAL_HASHGRID=1.
+ * replaces _gridencoder.grid_encode_forward / _backward (third_party/gridencoder/src/gridencoder.cu:100-884,
+ * bindings.cpp) as called by compression_simulation/gaussian_distribution_model.py:60-182 (no voxel mask, all levels),
+ * with the STE_binary embedding transform (:19-38) fused when ste_binary != 0.
+ * inputs [N,num_dim] in [0,1] (num_dim 2 or 3); params [offsets[n_levels], 2]; offsets i32 [n_levels+1] (rows) and
+ * resolutions i32 [n_levels] are HOST arrays, n_levels <= GSB200_GRID_MAX_LEVELS; outputs [N, n_levels*2] level-major.
+ * bwd overwrites v_params (same shape as params) and, when not NULL, v_inputs [N,num_dim]. */
+#define GSB200_GRID_MAX_LEVELS 16
+int gsb200_grid_encode_fwd(uint32_t N, uint32_t num_dim, uint32_t n_features, uint32_t n_levels,
+                           const int32_t *offsets, const int32_t *resolutions, int ste_binary,
+                           const float *inputs, const float *params, float *outputs, gsb200_stream_t stream);
+int gsb200_grid_encode_bwd(uint32_t N, uint32_t num_dim, uint32_t n_features, uint32_t n_levels,
+                           const int32_t *offsets, const int32_t *resolutions, int ste_binary,
+                           const float *inputs, const float *params, const float *v_outputs, float *v_params,
+                           float *v_inputs, gsb200_stream_t stream);
+
 /* ---------------------------------------------------------------- optimizer step
  * gsb200_selective_adam_update replaces _C.selective_adam_update (ext.cpp, adam.cu:13-83; caller
  * gsplat/optimizers/selective_adam.py:42-94): param / param_grad / exp_avg / exp_avg_sq are [N, M] row-major,

@@ -592,3 +592,35 @@ def test_widen_ops_match_reference_cuda_live():
     new_o, new_s = compute_relocation(opac, scales, ratios.clone(), binoms)
     r_o, r_s = ref.compute_relocation(opac, scales, ratios.int(), binoms, n_max)
     assert rel_err(new_o, r_o) < 1e-5 and rel_err(new_s, r_s) < 1e-4
+
+
+# ------------------------------------------------------------------------------- hash-grid entropy model (8f.3, experimental)
+@pytest.mark.skipif(os.environ.get("GSB200_EXPERIMENTAL_HASHGRID") != "1",
+                    reason="experimental hash-grid kernels: opt in with GSB200_EXPERIMENTAL_HASHGRID=1 (not yet validated on a GPU)")
+@pytest.mark.parametrize("num_dim", [3, 2])
+def test_hashgrid_encoder_matches_oracle(num_dim):
+    """csrc/hashgrid.cu against oracle/hashgrid.py: forward, embedding gradient (through the binary straight-through
+    gate) and input gradient, on positions that include the shell, the exact borders and out-of-range values."""
+    from gscodec_studio_b200.compression_simulation.gaussian_distribution_model import GridEncoder
+    from oracle import hashgrid as H
+
+    res, log2 = ((18, 24, 33, 44, 59, 80, 108, 148, 201, 275, 376, 514), 13) if num_dim == 3 else ((130, 258, 514, 1026), 15)
+    g = torch.Generator().manual_seed(40 + num_dim)
+    enc = GridEncoder(num_dim=num_dim, n_features=2, resolutions_list=res, log2_hashmap_size=log2, ste_binary=True).to(DEV)
+    with torch.no_grad():
+        enc.params.copy_((torch.randn(enc.params.shape, generator=g) * 0.8).to(DEV))  # some |p| > 1: gate closed
+    x = torch.rand(3000, num_dim, generator=g)
+    x[:8] = torch.tensor([0.0, 1.0, 1.2, -0.1, 0.5, 0.999, 0.001, 0.25])[:, None]
+    w = torch.randn(3000, len(res) * 2, generator=g)
+    xa = x.clone().to(DEV).requires_grad_(True)
+    out = enc(xa)
+    (out * w.to(DEV)).sum().backward()
+    ref_enc = H.GridEncoder(num_dim, 2, res, log2, ste_binary=True)
+    with torch.no_grad():
+        ref_enc.params.copy_(enc.params.detach().cpu())
+    xb = x.clone().requires_grad_(True)
+    ref = ref_enc(xb)
+    (ref * w).sum().backward()
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(enc.params.grad, ref_enc.params.grad) < 1e-4
+    assert rel_err(xa.grad, xb.grad) < 1e-3
