@@ -122,3 +122,51 @@ def test_profile_helpers_are_inert_without_timeit(monkeypatch):
     with profile.timeit(name="region"):
         assert f(1) == 2
     assert profile.profiler_summary() == {} and f.__name__ == "f"
+
+
+def test_compression_simulation_host_logic_with_stubbed_kernels(monkeypatch):
+    """Host-side policy of CompressionSimulation on the CPU with the two kernels stubbed out: which attributes are
+    quantised, which get a rate estimate and from which step, pass-through of means / shN -- for the default
+    factorized model and for the (opt-in, experimental) hash-grid model with its position sampling."""
+    from gscodec_studio_b200.compression_simulation import simulation as S
+
+    calls = []
+
+    def fake_fq(x, lo, hi, bits, noise=None, activation=None, **kw):
+        calls.append((tuple(x.shape), lo, hi, bits, activation))
+        return {"output_value": torch.clamp(x, lo, hi), "q_step": (hi - lo) / (2 ** bits - 1)}
+
+    class StubModel(torch.nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(1))
+            self.param_regressor = torch.nn.ModuleDict({"hash_grid": torch.nn.Linear(1, 1), "mlp_regressor": torch.nn.Linear(1, 1)})
+
+        def forward(self, x, q, pos=None):
+            assert pos is None or pos.shape[0] == x.shape[0]
+            return x.abs() * self.w
+
+    monkeypatch.setattr(S, "fake_quantize_ste", fake_fq)
+    monkeypatch.setattr(S, "Entropy_factorized_optimized_refactor", StubModel)
+    monkeypatch.setattr(S, "Entropy_gaussian", StubModel)
+    g = torch.Generator().manual_seed(0)
+    N = 400
+    splats = {"means": torch.randn(N, 3, generator=g), "scales": torch.randn(N, 3, generator=g), "quats": torch.randn(N, 4, generator=g),
+              "opacities": torch.randn(N, generator=g), "sh0": torch.randn(N, 1, 3, generator=g), "shN": torch.randn(N, 15, 3, generator=g)}
+    steps = {"means": -1, "scales": 10, "quats": 10, "opacities": -1, "sh0": 20, "shN": -1}
+    sim = S.CompressionSimulation(entropy_model_enable=True, entropy_steps=steps, device="cpu")
+    new, bits = sim.simulate_compression(splats, 15)
+    assert set(new) == set(splats) and new["shN"] is splats["shN"] and torch.equal(new["means"], splats["means"])
+    assert bits["scales"].shape == (N, 3) and bits["quats"].shape == (N, 4) and bits["sh0"] is None and bits["opacities"] is None
+    assert [c[1:3] for c in calls] == [(-10, 2), (-1, 1), (-15, 15), (-2, 4)]
+    new, bits = sim.simulate_compression(splats, 25)
+    assert bits["sh0"].shape == (N, 3)
+    # hash-grid policy: ~5 % of the points inside the 1-99 % box, rate conditioned on their positions
+    gsim = S.CompressionSimulation(entropy_model_enable=True, entropy_model_type="gaussian_model", entropy_steps=steps, device="cpu")
+    gsim._estiblish_bbox(splats["means"])
+    assert isinstance(gsim.entropy_model_schedulers["scales"], torch.optim.lr_scheduler.ExponentialLR)
+    new, bits = gsim.simulate_compression(splats, 25)
+    n_s = bits["scales"].shape[0]
+    assert 0 < n_s < N // 5 and bits["quats"].shape == (n_s, 4) and bits["sh0"].shape == (n_s, 3)
+    new, bits = gsim.simulate_compression(splats, 5)  # before the first entropy step: nothing sampled, no rates
+    assert all(b is None for b in bits.values())
