@@ -20,12 +20,24 @@ from .._cabi import call, ptr, stream_ptr
 from ..cuda._wrapper import selective_adam_update
 
 
+def _moments(optimizer: torch.optim.Optimizer, param: torch.Tensor):
+    """The (lazily created) Adam state of `param`, laid out like torch.optim.Adam's: step, exp_avg, exp_avg_sq."""
+    state = optimizer.state[param]
+    if not state:
+        state["step"] = torch.tensor(0.0, dtype=torch.float32)
+        for key in ("exp_avg", "exp_avg_sq"):
+            state[key] = torch.zeros_like(param, memory_format=torch.preserve_format)
+    return state
+
+
 class SelectiveAdam(torch.optim.Adam):
-    """Adam with selective (visibility-masked) updates; one fused kernel per parameter tensor.
+    """Adam whose ``step(visibility)`` touches only the rows flagged in ``visibility`` (bool [N]) -- parameter AND
+    moments of the other rows stay as they are -- with one fused kernel per parameter tensor (the second of the two
+    optimizers of the Taming-3DGS paper, as in the reference).  One tensor per parameter group; no bias correction.
 
     >>> optimizer = SelectiveAdam([param], eps=1e-8, betas=(0.9, 0.999))
     >>> loss.backward()
-    >>> optimizer.step(visibility=visibility_mask)   # bool [N]
+    >>> optimizer.step(visibility=visibility_mask)
     """
 
     def __init__(self, params, eps, betas):
@@ -33,23 +45,16 @@ class SelectiveAdam(torch.optim.Adam):
 
     @torch.no_grad()
     def step(self, visibility):
-        N = visibility.numel()
+        n_rows = visibility.numel()
         for group in self.param_groups:
-            lr = group["lr"]
-            eps = group["eps"]
-            beta1, beta2 = group["betas"]
             assert len(group["params"]) == 1, "more than one tensor in group"
-            param = group["params"][0]
+            (param,) = group["params"]
             if param.grad is None:
                 continue
-            state = self.state[param]
-            if len(state) == 0:  # lazy state initialisation, as torch.optim.Adam
-                state["step"] = torch.tensor(0.0, dtype=torch.float32)
-                state["exp_avg"] = torch.zeros_like(param, memory_format=torch.preserve_format)
-                state["exp_avg_sq"] = torch.zeros_like(param, memory_format=torch.preserve_format)
-            M = param.numel() // N
-            selective_adam_update(param, param.grad, state["exp_avg"], state["exp_avg_sq"], visibility, lr, beta1, beta2,
-                                  eps, N, M)
+            state = _moments(self, param)
+            beta1, beta2 = group["betas"]
+            selective_adam_update(param, param.grad, state["exp_avg"], state["exp_avg_sq"], visibility, group["lr"], beta1,
+                                  beta2, group["eps"], n_rows, param.numel() // n_rows)
 
 
 class GroupedAdam(torch.optim.Adam):
@@ -84,11 +89,7 @@ class GroupedAdam(torch.optim.Adam):
                 device = param.device if device is None else device
                 if param.device != device:
                     raise RuntimeError("GroupedAdam: all parameters must live on one device")
-                state = self.state[param]
-                if len(state) == 0:
-                    state["step"] = torch.tensor(0.0, dtype=torch.float32)
-                    state["exp_avg"] = torch.zeros_like(param, memory_format=torch.preserve_format)
-                    state["exp_avg_sq"] = torch.zeros_like(param, memory_format=torch.preserve_format)
+                state = _moments(self, param)
                 state["step"] += 1
                 t = float(state["step"])
                 grad = param.grad.contiguous()

@@ -1,36 +1,32 @@
 // TEST INFRASTRUCTURE ONLY -- not part of the product path.
 //
-// pybind11 table for the UNMODIFIED reference CUDA kernels of the hot path
-// (sources compiled in place from /root/reference/gsplat/cuda/csrc by
-// oracle/Makefile; nothing is copied into this repo).  The resulting module
-// oracle/_ref/gsplat_ref_cuda.so is the GPU-side oracle / "reference CUDA on the
-// same B200" baseline.  Signatures come from the reference header
-// gsplat/cuda/include/bindings.h:94-309 which this file includes directly.
+// Python entry table for the UNMODIFIED reference CUDA kernels (sources compiled in place from
+// /root/reference/gsplat/cuda/csrc by oracle/Makefile; nothing is copied into this repo).  The resulting module
+// oracle/_ref/gsplat_ref_cuda.so is the GPU-side oracle / "reference CUDA on the same B200" baseline.  The C++
+// signatures come from the reference header gsplat/cuda/include/bindings.h, which this file includes directly; the
+// Python names are the ones gsplat/cuda/_wrapper.py looks up on its `_C` module.
 #include "bindings.h"
 
-PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
-    py::enum_<gsplat::CameraModelType>(m, "CameraModelType")
-        .value("PINHOLE", gsplat::CameraModelType::PINHOLE)
-        .value("ORTHO", gsplat::CameraModelType::ORTHO)
-        .value("FISHEYE", gsplat::CameraModelType::FISHEYE);
-    m.def("compute_sh_fwd", &gsplat::compute_sh_fwd_tensor);
-    m.def("compute_sh_bwd", &gsplat::compute_sh_bwd_tensor);
-    m.def("fully_fused_projection_fwd", &gsplat::fully_fused_projection_fwd_tensor);
-    m.def("fully_fused_projection_bwd", &gsplat::fully_fused_projection_bwd_tensor);
-    m.def("fully_fused_projection_packed_fwd", &gsplat::fully_fused_projection_packed_fwd_tensor);
-    m.def("fully_fused_projection_packed_bwd", &gsplat::fully_fused_projection_packed_bwd_tensor);
-    m.def("isect_tiles", &gsplat::isect_tiles_tensor);
-    m.def("isect_offset_encode", &gsplat::isect_offset_encode_tensor);
-    m.def("rasterize_to_pixels_fwd", &gsplat::rasterize_to_pixels_fwd_tensor);
-    m.def("rasterize_to_pixels_bwd", &gsplat::rasterize_to_pixels_bwd_tensor);
-    // SURVEY.md section 8(f) rows
-    m.def("rasterize_to_indices_in_range", &gsplat::rasterize_to_indices_in_range_tensor);
-    m.def("quat_scale_to_covar_preci_fwd", &gsplat::quat_scale_to_covar_preci_fwd_tensor);
-    m.def("quat_scale_to_covar_preci_bwd", &gsplat::quat_scale_to_covar_preci_bwd_tensor);
-    m.def("proj_fwd", &gsplat::proj_fwd_tensor);
-    m.def("proj_bwd", &gsplat::proj_bwd_tensor);
-    m.def("world_to_cam_fwd", &gsplat::world_to_cam_fwd_tensor);
-    m.def("world_to_cam_bwd", &gsplat::world_to_cam_bwd_tensor);
-    m.def("selective_adam_update", &gsplat::selective_adam_update);
-    m.def("compute_relocation", &gsplat::compute_relocation_tensor);
+// ops whose C++ entry point is `gsplat::<python name>_tensor`
+#define GSB_REF_TENSOR_OPS(OP)                                                                               \
+    OP(compute_sh_fwd) OP(compute_sh_bwd)                           /* colour */                             \
+    OP(fully_fused_projection_fwd) OP(fully_fused_projection_bwd)   /* stage 1 / 4b, dense */                \
+    OP(fully_fused_projection_packed_fwd) OP(fully_fused_projection_packed_bwd)                              \
+    OP(isect_tiles) OP(isect_offset_encode)                         /* stage 2 */                            \
+    OP(rasterize_to_pixels_fwd) OP(rasterize_to_pixels_bwd)         /* stage 3 / 4a */                       \
+    OP(rasterize_to_indices_in_range)                               /* SURVEY.md section 8(f) rows below */  \
+    OP(quat_scale_to_covar_preci_fwd) OP(quat_scale_to_covar_preci_bwd)                                      \
+    OP(proj_fwd) OP(proj_bwd) OP(world_to_cam_fwd) OP(world_to_cam_bwd)                                      \
+    OP(compute_relocation)
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod) {
+    namespace ref = gsplat;
+    py::enum_<ref::CameraModelType>(mod, "CameraModelType")
+        .value("PINHOLE", ref::CameraModelType::PINHOLE)
+        .value("ORTHO", ref::CameraModelType::ORTHO)
+        .value("FISHEYE", ref::CameraModelType::FISHEYE);
+#define GSB_BIND(name) mod.def(#name, &ref::name##_tensor);
+    GSB_REF_TENSOR_OPS(GSB_BIND)
+#undef GSB_BIND
+    mod.def("selective_adam_update", &ref::selective_adam_update);  // the one op without the _tensor suffix
 }
