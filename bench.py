@@ -8,11 +8,14 @@ parameterisation (log-scales, logit-opacities, SH degree 3 = sh0 + shN), one 192
 One step = CompressionSimulation.simulate_compression (8-bit fake-quant, noise mode, on scales / quats /
 opacities / sh0) -> exp / sigmoid -> rasterization(sh_degree=3, packed=False) -> L1 loss against a
 target image -> backward to the RAW parameters.  Metric: Mpix/s = (pixels rendered per step over all
-GPUs) / (time of forward + backward).
+GPUs) / (time of forward + backward).  Two additive hooks of the package are on by default and can be switched off
+to get the reference trainer's literal call sequence: --cat-colors (pass torch.cat([sh0, shN], 1) instead of the
+(sh0, shN) pair) and --torch-loss (torch's L1 chain instead of the fused loss kernel).
 
 N > 1: the Gaussians are sharded across ranks (strided, like examples/simple_trainer.py:361-363), every
-rank renders its own view with rasterization(distributed=True): one NCCL all-gather of the attributes
-forward, one reduce-scatter of their gradients backward.  Weak scaling (one view per GPU).
+rank renders its own view with rasterization(distributed=True): geometry pulled from the peers' published blocks
+over NVLink, SH rows of visible Gaussians pulled on demand, gradients pushed back / reduce-scattered to the owners
+(NCCL all-gather + reduce-scatter when no peer mapping exists).  Weak scaling (one view per GPU).
 
 --impl reference: the reference's CPU path (oracle/: torch restatement of _torch_impl + the C blend,
 OpenMP over all host cores) on the same workload, rank 0 only.
