@@ -18,6 +18,9 @@
 // Ordering contract: the reference's stable LSD radix sort keeps emission order (ascending flatten
 // index) among equal keys, i.e. it sorts by (camera, tile, depth bits, flatten id).  That composite
 // key is unique, so any correct sort of it reproduces the reference bit for bit.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -327,6 +330,129 @@ tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, i
     }
 }
 
+// ---- EXPERIMENTAL alternative to tile_sort_kernel<false> (opt-in: GSB200_TILE_SORT=radix, not yet run on a GPU) -----------
+// The bitonic network above spends ~860 lane-instructions per key (64-bit compare-exchange, 45-66 stages).  Here a CTA
+// sorts its segment (<= kSortSmall keys) with a stable LSD radix sort on the depth word -- four 8-bit passes, passes in
+// which all keys share the digit are skipped -- and then orders the (rare) runs of exactly equal depth by flatten id,
+// which gives the same ascending (depth bits, flatten id) order.  Stability inside a pass comes from processing the
+// keys in index order: warp w owns a contiguous chunk, walks it 32 keys at a time, and ranks equal digits inside a
+// group with __match_any_sync (rank = number of lower lanes with the same digit).
+constexpr uint32_t kRadixWarps = kThreads / 32;
+
+__device__ __forceinline__ void block_sort_radix(uint64_t *a, uint64_t *b, uint32_t n, uint16_t (*hist)[256], uint32_t *s_warp_sums,
+                                                 uint32_t *s_flag) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = ((n + kRadixWarps - 1) / kRadixWarps + 31u) & ~31u;  // keys per warp, whole groups of 32
+    const uint32_t w_begin = min(n, warp * chunk), w_end = min(n, w_begin + chunk);
+    uint64_t *src = a, *dst = b;
+    if (threadIdx.x < 4) s_flag[threadIdx.x] = 0;  // one skip flag per pass: never reset while it may still be read
+    for (uint32_t pass = 0; pass < 4; ++pass) {
+        const uint32_t shift = 32 + 8 * pass;
+        for (uint32_t t = threadIdx.x; t < kRadixWarps * 256; t += blockDim.x) hist[t >> 8][t & 255] = 0;
+        __syncthreads();
+        // (1) per-warp digit histogram
+        for (uint32_t g0 = w_begin; g0 < w_end; g0 += 32) {
+            const uint32_t i = g0 + lane;
+            const bool valid = i < w_end;
+            const uint32_t d = valid ? (uint32_t)(src[i] >> shift) & 255u : 256u + lane;  // invalid lanes match nobody
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            if (valid && lane == (uint32_t)__ffs(peers) - 1u) hist[warp][d] += (uint16_t)__popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // (2) exclusive scan over (digit major, warp minor); thread t owns digit t
+        {
+            const uint32_t d = threadIdx.x;  // kThreads == 256 digits
+            uint32_t total = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < kRadixWarps; ++w) total += hist[w][d];
+            if (total == n) s_flag[pass] = 1;  // every key has this digit: the pass would not move anything
+            uint32_t incl = total;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            if (lane == 31) s_warp_sums[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0;
+            for (uint32_t w = 0; w < warp; ++w) before += s_warp_sums[w];
+            uint32_t running = before + incl - total;
+#pragma unroll
+            for (uint32_t w = 0; w < kRadixWarps; ++w) {
+                const uint32_t c = hist[w][d];
+                hist[w][d] = (uint16_t)running;
+                running += c;
+            }
+        }
+        __syncthreads();
+        if (s_flag[pass]) continue;  // uniform: written before the barrier above, never rewritten
+        // (3) stable scatter
+        for (uint32_t g0 = w_begin; g0 < w_end; g0 += 32) {
+            const uint32_t i = g0 + lane;
+            const bool valid = i < w_end;
+            const uint64_t key = valid ? src[i] : 0ull;
+            const uint32_t d = valid ? (uint32_t)(key >> shift) & 255u : 256u + lane;
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t pos = 0;
+            if (valid) pos = hist[warp][d] + rank;
+            __syncwarp();
+            if (valid && lane == (uint32_t)__ffs(peers) - 1u) hist[warp][d] += (uint16_t)__popc(peers);
+            __syncwarp();
+            if (valid) dst[pos] = key;
+        }
+        __syncthreads();
+        uint64_t *tmp = src; src = dst; dst = tmp;
+    }
+    if (src != a) {
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) a[t] = src[t];
+        __syncthreads();
+    }
+    // (4) runs of exactly equal depth: order by flatten id (insertion sort by the thread that owns the run's first key)
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t depth = (uint32_t)(a[i] >> 32);
+        const bool first = i == 0 || (uint32_t)(a[i - 1] >> 32) != depth;
+        if (first && i + 1 < n && (uint32_t)(a[i + 1] >> 32) == depth) {
+            uint32_t j = i + 1;
+            while (j < n && (uint32_t)(a[j] >> 32) == depth) ++j;
+            for (uint32_t u = i + 1; u < j; ++u) {
+                const uint64_t x = a[u];
+                uint32_t v = u;
+                while (v > i && a[v - 1] > x) { a[v] = a[v - 1]; --v; }
+                a[v] = x;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+tile_sort_radix_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, int64_t n_isects_or_capacity,
+                       const int32_t *__restrict__ total_dev, const int32_t *__restrict__ offsets, uint64_t *__restrict__ bucket,
+                       int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+    __shared__ uint64_t s_a[kSortSmall], s_b[kSortSmall];
+    __shared__ uint16_t s_hist[kRadixWarps][256];
+    __shared__ uint32_t s_warp_sums[kRadixWarps], s_flag[4];
+    const int64_t n_isects = total_dev ? (int64_t)*total_dev : n_isects_or_capacity;
+    const int64_t capacity = n_isects_or_capacity;
+    const uint32_t ct = blockIdx.x;
+    const int64_t start = offsets[ct];
+    const int64_t end = (ct + 1 == n_tiles_total) ? n_isects : (int64_t)offsets[ct + 1];
+    const uint32_t n = (uint32_t)(end - start);
+    if (n == 0 || n > kSortSmall || end > capacity) return;  // longer segments belong to tile_sort_kernel<true>
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) s_a[t] = bucket[start + t];
+    __syncthreads();
+    if (n > 1) block_sort_radix(s_a, s_b, n, s_hist, s_warp_sums, s_flag);
+    const uint64_t cam = ct / n_tiles, tile = ct % n_tiles;
+    const int64_t hi = (int64_t)((cam << (32 + tile_bits)) | (tile << 32));
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+        const uint64_t it = s_a[t];
+        isect_ids[start + t] = hi | (int64_t)(int32_t)(uint32_t)(it >> 32);
+        flatten_ids[start + t] = (int32_t)(uint32_t)(it & 0xffffffffu);
+    }
+}
+
 // sort == false variant of the reference op: keys in emission order (ascending flatten index, row-major
 // tiles inside each Gaussian), isect_tiles.cu:89-103.  `cum` = exclusive scan of tiles_per_gauss.
 __global__ void __launch_bounds__(kThreads)
@@ -445,8 +571,16 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
                                                                        tile_width, tile_height, T, tile_cursor, scratch, bound);
     if (int e = check_launch("isect_scatter")) return e;
     const int32_t *large_list = tile_cursor + (size_t)GSB200_ISECT_REPLICAS * T;
-    tile_sort_kernel<false><<<T, kThreads, 0, s>>>(T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, large_list,
-                                                    scratch, isect_ids, flatten_ids);
+    static const bool radix_small = [] {  // experimental, opt-in (see tile_sort_radix_kernel)
+        const char *v = getenv("GSB200_TILE_SORT");
+        return v != nullptr && strcmp(v, "radix") == 0;
+    }();
+    if (radix_small)
+        tile_sort_radix_kernel<<<T, kThreads, 0, s>>>(T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, scratch,
+                                                       isect_ids, flatten_ids);
+    else
+        tile_sort_kernel<false><<<T, kThreads, 0, s>>>(T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, large_list,
+                                                        scratch, isect_ids, flatten_ids);
     if (int e = check_launch("tile_sort")) return e;
     static bool attr_set = false;
     if (!attr_set) {
