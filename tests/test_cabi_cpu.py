@@ -170,3 +170,37 @@ def test_compression_simulation_host_logic_with_stubbed_kernels(monkeypatch):
     assert 0 < n_s < N // 5 and bits["quats"].shape == (n_s, 4) and bits["sh0"].shape == (n_s, 3)
     new, bits = gsim.simulate_compression(splats, 5)  # before the first entropy step: nothing sampled, no rates
     assert all(b is None for b in bits.values())
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/gsb200.h against _cabi.SIGNATURES, parameter by parameter (count and C type class):
+    a drifted ctypes table would otherwise only show up as a wrong argument on the GPU."""
+    import ctypes
+
+    from gscodec_studio_b200 import _cabi
+
+    text = open(os.path.join(ROOT, "include", "gsb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef struct.*?\}\s*\w+;", "", text, flags=re.S)
+    protos = re.findall(r"\b([\w\s\*]+?)\b(gsb200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 40
+
+    def classify(param: str):
+        p = " ".join(param.split())
+        if p in ("void", ""):
+            return None
+        if "*" in p or "gsb200_stream_t" in p:
+            return ctypes.c_void_p
+        base = p.replace("const ", "").split(" ")[0]
+        return {"uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32, "int": ctypes.c_int, "float": ctypes.c_float,
+                "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64}[base]
+
+    seen = set()
+    for _ret, name, params in protos:
+        want = [c for c in (classify(p) for p in params.split(",")) if c is not None]
+        got = _cabi.SIGNATURES[name]
+        assert len(got) == len(want), (name, len(got), len(want))
+        for k, (g, w) in enumerate(zip(got, want)):
+            assert g is w, (name, k, g, w)
+        seen.add(name)
+    assert seen == set(_cabi.SIGNATURES), set(_cabi.SIGNATURES) ^ seen
