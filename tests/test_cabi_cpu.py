@@ -204,3 +204,33 @@ def test_ctypes_signatures_match_the_header_prototypes():
             assert g is w, (name, k, g, w)
         seen.add(name)
     assert seen == set(_cabi.SIGNATURES), set(_cabi.SIGNATURES) ^ seen
+
+
+def test_python_call_sites_pass_the_declared_number_of_arguments():
+    """Static check of every `call("gsb200_...", ...)` in the package: the number of positional arguments equals the
+    length of the ctypes signature (call sites that splat a tuple are checked for a plausible lower bound)."""
+    import ast
+
+    from gscodec_studio_b200 import _cabi
+
+    checked = 0
+    roots = [os.path.join(ROOT, "gscodec_studio_b200"), os.path.join(ROOT, "tools")]
+    for dirpath, _, files in (item for r in roots for item in os.walk(r)):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(dirpath, f)).read())
+            for node in ast.walk(tree):
+                if not (isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id == "call" and node.args):
+                    continue
+                first = node.args[0]
+                if not (isinstance(first, ast.Constant) and isinstance(first.value, str) and first.value.startswith("gsb200_")):
+                    continue
+                want = len(_cabi.SIGNATURES[first.value])
+                rest = node.args[1:]
+                if any(isinstance(a, ast.Starred) for a in rest):
+                    assert sum(not isinstance(a, ast.Starred) for a in rest) < want, (f, first.value)
+                else:
+                    assert len(rest) == want, (f, node.lineno, first.value, len(rest), want)
+                checked += 1
+    assert checked >= 30
