@@ -234,3 +234,10 @@ def test_python_call_sites_pass_the_declared_number_of_arguments():
                     assert len(rest) == want, (f, node.lineno, first.value, len(rest), want)
                 checked += 1
     assert checked >= 30
+
+
+def test_every_kernel_source_is_in_the_build_list():
+    from gscodec_studio_b200 import _build
+
+    on_disk = sorted(f for f in os.listdir(_build.CSRC) if f.endswith(".cu"))
+    assert on_disk == sorted(_build.SOURCES), (on_disk, _build.SOURCES)
