@@ -49,10 +49,13 @@ SIGNATURES = {
     "gsb200_isect_fill": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _L, _P, _P, _P, _P, _P, _P],
     "gsb200_isect_emit_unsorted": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_offset_encode": [_L, _P, _U, _U, _U, _P, _P],
-    "gsb200_rasterize_fwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_blend_stream_record": [_U, _U],
+    "gsb200_set_blend_mode": [_I],
+    "gsb200_rasterize_fwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P,
+                             _P],
     "gsb200_grad_record": [_U],
     "gsb200_rasterize_bwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P,
-                             _P, _P, _P, _P, _P, _P],
+                             _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_indices_in_range_count": [_U, _U, _U, _U, _L, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_indices_in_range_fill": [_U, _U, _U, _U, _L, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_fake_quantize_fwd": [_L, _P, _F, _F, _I, _I, _I, _P, c_uint64, c_uint64, _P, _P],
@@ -87,6 +90,7 @@ class AdamTensor(ctypes.Structure):
 
 ADAM_MAX_TENSORS = 16  # GSB200_ADAM_MAX_TENSORS
 _RESTYPES = {"gsb200_last_error": c_char_p, "gsb200_launch_count": c_uint64, "gsb200_grad_record": c_uint32,
+             "gsb200_blend_stream_record": c_uint32,
              "gsb200_photometric_workspace_bytes": c_uint64}
 
 _lib = None

@@ -81,8 +81,16 @@ class Entropy_factorized_optimized_refactor(nn.Module):
                 np.random.uniform(-0.5, 0.5, (channel, widths[i + 1], 1)).astype(np.float32))))
             if i < len(self.filters):
                 self._factor.append(nn.Parameter(torch.zeros(channel, widths[i + 1], 1)))
+        # checkpoint compatibility: the reference leaves the LAST layer's parameters registered on the module as well
+        # (entropy_model.py:216-232 assigns self.matrix / self.bias / self.factor in its loop), so its state_dict carries
+        # `matrix`, `bias`, `factor` (aliases of _matrices[-1], _bias[-1], _factor[-1]) and `likelihood_lower_bound.bound`;
+        # the trainer saves and strictly re-loads that dict (examples/simple_trainer.py:1093-1095, 1474)
+        self.matrix = self._matrices[-1]
+        self.bias = self._bias[-1]
+        self.factor = self._factor[-1]
         self.register_buffer("filters_len", torch.tensor(len(self.filters)))
         self.register_buffer("factor_len", torch.tensor(len(self._factor)))
+        self.likelihood_lower_bound = LowerBound(likelihood_bound)
 
     def _activated_params(self) -> Tensor:
         """[channel, PS] tensor in the kernel's layout; differentiable w.r.t. the raw parameters."""
@@ -152,18 +160,13 @@ class LowerBound(nn.Module):
 class Entropy_gaussian(nn.Module):
     """Hash-grid conditioned Gaussian entropy model (reference entropy_model.py:313-345): a hash-grid + MLP regressor
     predicts a per-channel (mean, scale) from the Gaussian's position, the rate is -log2 of the Normal mass of the
-    quantisation bin.  EXPERIMENTAL: the grid kernels have not been validated on a GPU and
-    their restatement is not pinned against the reference's CUDA-only `_gridencoder`, so constructing the model needs
-    GSB200_EXPERIMENTAL_HASHGRID=1; otherwise it raises like before."""
+    quantisation bin.  The grid encode / decode is csrc/hashgrid.cu, validated on B200 against a CPU restatement
+    and, live, against the reference's unmodified `_gridencoder` extension (tests/test_gpu_widen.py)."""
 
     def __init__(self, channel=3, Q=1, likelihood_bound=1e-6):
         super().__init__()
-        from .gaussian_distribution_model import experimental_enabled, hash_based_estimator
+        from .gaussian_distribution_model import hash_based_estimator
 
-        if not experimental_enabled():
-            raise NotImplementedError(
-                "gscodec_studio_b200: entropy_model_type='gaussian_model' (hash-grid Entropy_gaussian) is experimental and "
-                "unvalidated; set GSB200_EXPERIMENTAL_HASHGRID=1 to try it, or use the default 'factorized_model'")
         self.Q = Q
         self.likelihood_lower_bound = LowerBound(likelihood_bound)
         self.mean, self.scale = 0, 1

@@ -1,17 +1,16 @@
-"""Hash-grid parameter regressor of the alternative in-loop entropy model -- EXPERIMENTAL.
+"""Hash-grid parameter regressor of the alternative in-loop entropy model.
 
 Mirrors the class names, constructor arguments and ``state_dict`` keys of the reference's
 ``gsplat/compression_simulation/gaussian_distribution_model.py`` (``GridEncoder`` :184-274, ``mix_3D2D_encoding``
 :276-346, ``hash_based_estimator`` :348-382) so that checkpoints are interchangeable.  The grid encode / decode runs in
 the CUDA kernels of ``csrc/hashgrid.cu`` (STE-binary transform fused); the two small ``nn.Linear`` layers stay torch.
-The kernels have not been run on a GPU yet and their CPU restatement could not be pinned against the reference's
-CUDA-only extension, so nothing here is reachable unless ``GSB200_EXPERIMENTAL_HASHGRID=1`` is set.
+The kernels are tested on B200 against a CPU restatement and, live, against the reference's CUDA-only ``_gridencoder``
+extension built unmodified (tests/test_gpu_widen.py; DESIGN.md section 2 has the pinning numbers).
 """
 from __future__ import annotations
 
 import ctypes
 import math
-import os
 from typing import Sequence
 
 import torch
@@ -19,10 +18,6 @@ import torch.nn as nn
 from torch import Tensor
 
 from .._cabi import call, ptr, stream_ptr
-
-
-def experimental_enabled() -> bool:
-    return os.environ.get("GSB200_EXPERIMENTAL_HASHGRID", "0") == "1"
 
 
 class _GridEncode(torch.autograd.Function):

@@ -66,7 +66,8 @@ _FUSED_ACT = {"scales": "exp", "opacities": "sigmoid"}
 class _SimulationBase:
     policy: Dict[str, _AttrPolicy]
 
-    def _setup(self, entropy_model_enable, entropy_steps, device, entropy_model_type="factorized_model"):
+    def _setup(self, entropy_model_enable, entropy_steps, device, entropy_model_type="factorized_model",
+               gate_negative_steps=True):
         self.entropy_model_enable = entropy_model_enable
         self.entropy_steps = entropy_steps
         self.device = device
@@ -74,9 +75,12 @@ class _SimulationBase:
         self.q_bitwidth = {k: p.bits for k, p in self.policy.items()}
         self.bds = {k: (list(p.bounds) if p.bounds is not None else None) for k, p in self.policy.items()}
         self.entropy_model_option = {k: p.entropy for k, p in self.policy.items()}
-        if entropy_steps is not None:
+        if entropy_steps is not None and gate_negative_steps:
+            # static policy only (simulation.py:70-73): a negative step switches the rate term of that attribute off;
+            # a missing key is an error there too.  The dynamic policy has no such gate (simulation.py:575-583):
+            # `step > -1` simply holds from step 0
             for name in self.entropy_model_option:
-                if entropy_steps.get(name, -1) < 0:
+                if entropy_steps[name] < 0:
                     self.entropy_model_option[name] = False
         if not entropy_model_enable:
             return
@@ -91,8 +95,7 @@ class _SimulationBase:
             if p.entropy:
                 ch = {"quats": 4}.get(name, 3)
                 if entropy_model_type == "gaussian_model":
-                    # hash-grid conditioned Gaussian model (simulation.py:99-107, optimizer :124-128, scheduler :142-145);
-                    # experimental: the constructor raises unless GSB200_EXPERIMENTAL_HASHGRID=1
+                    # hash-grid conditioned Gaussian model (simulation.py:99-107, optimizer :124-128, scheduler :142-145)
                     model = Entropy_gaussian(channel=ch).to(device)
                     opt = torch.optim.Adam([
                         {"params": model.param_regressor.hash_grid.parameters(), "lr": 5e-3, "name": "hash_grid"},
@@ -173,6 +176,7 @@ class _SimulationBase:
                 and step > self.entropy_min_step):
             choose_idx = self._random_sample_pts(self._get_pts_inside_bbox(splats["means"]))  # simulation.py:216-220
             pos = splats["means"][choose_idx]
+            self._last_sample_idx = choose_idx  # which points carried the rate estimate (debugging / tests)
         for name in splats.keys():
             esti_bits_dict[name] = None
             if self.policy[name].bounds is not None and self.simulation_option[name]:
@@ -238,7 +242,7 @@ class STGCompressionSimulation(_SimulationBase):
         self.quantization_sim_type = quantization_sim_type
         if entropy_steps is None:
             entropy_steps = {k: -1 for k in self.policy}
-        self._setup(entropy_model_enable, entropy_steps, device)
+        self._setup(entropy_model_enable, entropy_steps, device, gate_negative_steps=False)
         self._setup_mask(ada_mask_opt, ada_mask_step, "learnable", device, kwargs)
 
     def simulate_compression(self, splats: Dict[str, Tensor], step: int, noise: Optional[Dict[str, Tensor]] = None,

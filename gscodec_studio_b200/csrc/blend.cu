@@ -20,103 +20,13 @@
 //     sector for D=3) instead of 9+D scalar atomics to four tensors; an unpack pass then writes the
 //     reference's v_means2d / v_conics / v_colors / v_opacities layout;
 //   * backward skips staging of batches that lie behind every pixel's last contributing Gaussian.
-#include <float.h>
-#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
 
-#include "common.cuh"
+#include "blend.cuh"
 
 namespace gsb200 {
 
-constexpr int kBatch = 256;
-// minimum resident CTAs per SM the register allocator must allow (occupancy knobs)
-#ifndef GSB_STAGE_PER_THREAD
-#define GSB_STAGE_PER_THREAD 2  // Gaussians staged per thread and barrier (batch = threads x this)
-#endif
-constexpr int kStagePerThread = GSB_STAGE_PER_THREAD;
-#ifndef GSB_FWD_BLOCKS
-#define GSB_FWD_BLOCKS 6
-#endif
-#ifndef GSB_BWD_BLOCKS
-#define GSB_BWD_BLOCKS 5
-#endif
-constexpr float kAlphaMax = 0.999f;
-constexpr float kAlphaMin = 1.f / 255.f;
-constexpr float kTStop = 1e-4f;  // reference compares against the double 1e-4; identical set of floats
-
-struct BlendGeom {
-    uint32_t C, W, H, ts, tw, th;
-    int64_t n_isects;
-};
-
-// pixel owned by this thread inside its tile: 8x4 warp blocks for 16x16 tiles, row-major otherwise
-__device__ __forceinline__ void pixel_in_tile(uint32_t ts, uint32_t tid, uint32_t &lx, uint32_t &ly) {
-    if (ts == 16) {
-        const uint32_t w = tid >> 5, l = tid & 31;
-        lx = (w & 1) * 8 + (l & 7);
-        ly = (w >> 1) * 4 + (l >> 3);
-    } else {
-        lx = tid % ts;
-        ly = tid / ts;  // >= ts for the padding threads of a block rounded up to a full warp
-    }
-}
-
-// Cull parameter of one Gaussian: q_max = 2 ln(255 * opac) (+ margin).  A pixel at offset d from the
-// centre can pass the reference's alpha >= 1/255 test only if d^T A d <= q_max.  FLT_MAX (always
-// evaluate) when the conic is not positive definite, negative (never) when no pixel can pass.
-__device__ __forceinline__ float cull_qmax(float a, float b, float c, float opac) {
-    const float tau = __logf(255.f * opac);
-    if (!(opac > 0.f) || !(tau >= 0.f)) return (opac * 255.f >= 1.f) ? FLT_MAX : -1.f;  // first case: NaN / inf guard
-    if (!(a * c - b * b > 0.f) || !(a > 0.f) || !(c > 0.f)) return FLT_MAX;
-    return 2.f * (tau * 1.001f + 1e-3f);
-}
-
-// Exact test "does the ellipse { d : d^T A d <= qmax } around (mx,my) meet the pixel-centre rectangle
-// [x0,x1] x [y0,y1]?" -- the minimum of the convex form over the rectangle is 0 if the centre is inside,
-// otherwise it is attained on one of the four edges (a clamped 1-D parabola each).  A margin proportional
-// to the magnitude of the terms keeps the test conservative under float32 rounding, so it never drops a
-// (pixel, Gaussian) pair the reference arithmetic would accept.
-__device__ __forceinline__ bool ellipse_hits_rect(float mx, float my, float a, float b, float c, float qmax, float x0,
-                                                  float x1, float y0, float y1) {
-    if (!(qmax >= 0.f)) return false;
-    if (qmax == FLT_MAX) return true;
-    const float lx0 = x0 - mx, lx1 = x1 - mx, ly0 = y0 - my, ly1 = y1 - my;
-    if (lx0 <= 0.f && lx1 >= 0.f && ly0 <= 0.f && ly1 >= 0.f) return true;
-    const float ia = __frcp_rn(a), ic = __frcp_rn(c);
-    float q = FLT_MAX;
-    {
-        float dy = fminf(fmaxf(-b * lx0 * ic, ly0), ly1);
-        q = fminf(q, a * lx0 * lx0 + 2.f * b * lx0 * dy + c * dy * dy);
-        dy = fminf(fmaxf(-b * lx1 * ic, ly0), ly1);
-        q = fminf(q, a * lx1 * lx1 + 2.f * b * lx1 * dy + c * dy * dy);
-        float dx = fminf(fmaxf(-b * ly0 * ia, lx0), lx1);
-        q = fminf(q, a * dx * dx + 2.f * b * dx * ly0 + c * ly0 * ly0);
-        dx = fminf(fmaxf(-b * ly1 * ia, lx0), lx1);
-        q = fminf(q, a * dx * dx + 2.f * b * dx * ly1 + c * ly1 * ly1);
-    }
-    const float ex = fmaxf(fabsf(lx0), fabsf(lx1)), ey = fmaxf(fabsf(ly0), fabsf(ly1));
-    const float slack = 1e-5f * (a * ex * ex + 2.f * fabsf(b) * ex * ey + c * ey * ey) + 1e-4f;
-    return q <= qmax + slack;
-}
-
-// shared-memory accesses through 32-bit shared-window addresses (keeps the address arithmetic out of
-// the inner loop; generic pointers make the compiler rebuild the window base every iteration)
-__device__ __forceinline__ float4 lds4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float lds1(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ int lds1i(uint32_t addr) {
-    int v;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-
-template <int CDIM> struct ColorPad { static constexpr int value = (CDIM + 3) / 4 * 4; };
 
 template <int CDIM>
 __global__ void __launch_bounds__(kBatch, CDIM <= 4 ? GSB_FWD_BLOCKS : 1)
@@ -242,39 +152,6 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
         last_ids[pix] = (int32_t)cur_idx;
     }
 }
-
-// ---- warp reductions that leave each of NV totals in a distinct lane group --------------------
-// After reduce_spread<NV>(v): the total of value `slot` is held in v[0] by every lane whose
-// (lane >> shift) & (NV-1), bit-reversed over log2(NV) bits, equals slot -- see spread_slot().
-template <int NV>
-__device__ __forceinline__ void reduce_spread(float *v, uint32_t lane) {
-    // halving steps: partner distance 16, 8, ... while more than one value is alive
-    int alive = NV;
-    int dist = 16;
-#pragma unroll
-    for (; alive > 1; alive >>= 1, dist >>= 1) {
-        const bool upper = (lane & dist) != 0;
-        const int half = alive >> 1;
-#pragma unroll
-        for (int q = 0; q < half; ++q) {
-            const float keep = upper ? v[half + q] : v[q];
-            const float send = upper ? v[q] : v[half + q];
-            v[q] = keep + __shfl_xor_sync(0xffffffffu, send, dist);
-        }
-    }
-#pragma unroll
-    for (; dist > 0; dist >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], dist);
-}
-// value slot held by `lane` after reduce_spread<NV>
-template <int NV>
-__device__ __forceinline__ uint32_t spread_slot(uint32_t lane) {
-    uint32_t slot = 0, alive = NV, dist = 16;
-    for (; alive > 1; alive >>= 1, dist >>= 1) slot += (lane & dist) ? (alive >> 1) : 0;
-    return slot;
-}
-
-// packed gradient record (floats): [rgb(CDIM) | conic(3) | xy(2) | opac(1) | abs(2)] rounded up to 4
-__host__ __device__ constexpr uint32_t grad_record(uint32_t cdim) { return (cdim + 8 + 3) / 4 * 4; }
 
 template <int CDIM, bool ABS>
 __global__ void __launch_bounds__(kBatch, CDIM <= 4 ? GSB_BWD_BLOCKS : 1)
@@ -480,6 +357,11 @@ tile_order_kernel(uint32_t total_tiles, int64_t n_isects, const int32_t *__restr
     }
 }
 
+int launch_tile_order(uint32_t total_tiles, int64_t n_isects, const int32_t *offsets, int32_t *order, cudaStream_t s) {
+    tile_order_kernel<<<1, 1024, 0, s>>>(total_tiles, n_isects, offsets, order);
+    return check_launch("tile_order");
+}
+
 // packed gradient records -> the reference's tensors
 template <int CDIM>
 __global__ void __launch_bounds__(kThreads)
@@ -503,6 +385,14 @@ unpack_grads_kernel(uint32_t M, const float *__restrict__ rec, float *__restrict
 }
 
 template <int CDIM>
+static int launch_unpack(uint32_t M, const float *grad_scratch, float *v_abs, float *v_means2d, float *v_conics, float *v_colors,
+                         float *v_opacities, cudaStream_t s) {
+    unpack_grads_kernel<CDIM><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors,
+                                                                      v_opacities);
+    return check_launch("unpack_grads");
+}
+
+template <int CDIM>
 static int launch_fwd(const BlendGeom &G, const float *means2d, const float *conics, const float *colors,
                       const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
                       const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
@@ -513,10 +403,8 @@ static int launch_fwd(const BlendGeom &G, const float *means2d, const float *con
     if (smem > 48 * 1024)
         GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t T = G.C * G.tw * G.th;
-    if (tile_order != nullptr) {
-        tile_order_kernel<<<1, 1024, 0, s>>>(T, G.n_isects, tile_offsets, tile_order);
-        if (int e = check_launch("tile_order")) return e;
-    }
+    if (tile_order != nullptr)
+        if (int e = launch_tile_order(T, G.n_isects, tile_offsets, tile_order, s)) return e;
     blend_fwd_kernel<CDIM><<<T, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
                                                       opacities, backgrounds, masks, tile_offsets, flatten_ids,
                                                       render_colors, render_alphas, last_ids, tile_order);
@@ -550,9 +438,7 @@ static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, cons
                 flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, grad_scratch);
         if (int e = check_launch("blend_bwd")) return e;
     }
-    unpack_grads_kernel<CDIM><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors,
-                                                                      v_opacities);
-    return check_launch("unpack_grads");
+    return launch_unpack<CDIM>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors, v_opacities, s);
 }
 
 }  // namespace gsb200
@@ -577,6 +463,24 @@ using namespace gsb200;
 
 extern "C" uint32_t gsb200_grad_record(uint32_t D) { return grad_record(D); }
 
+// GSB200_BLEND=tile (or gsb200_set_blend_mode(1)) selects the generic per-tile kernels for every configuration
+// (A/B timing and the stream-vs-tile parity tests)
+static int g_blend_mode = [] {
+    const char *v = getenv("GSB200_BLEND");
+    return (v != nullptr && strcmp(v, "tile") == 0) ? 1 : 0;
+}();
+static bool stream_blend_enabled() { return g_blend_mode == 0; }
+
+extern "C" int gsb200_set_blend_mode(int mode) {
+    const int old = g_blend_mode;
+    g_blend_mode = mode;
+    return old;
+}
+
+extern "C" uint32_t gsb200_blend_stream_record(uint32_t D, uint32_t tile_size) {
+    return stream_blend_enabled() && blend_stream_supported(tile_size, D, 0) ? 12u : 0u;
+}
+
 static int check_geom(uint32_t tile_size, uint32_t W, uint32_t H, uint32_t tw, uint32_t th) {
     if (tile_size == 0 || tile_size > 16) return fail(2, "gsb200_rasterize: tile_size must be in [1, 16]");
     if (tw * tile_size < W || th * tile_size < H)
@@ -589,12 +493,16 @@ extern "C" int gsb200_rasterize_fwd(uint32_t C, uint32_t M, int64_t n_isects, ui
                                     const float *backgrounds, const uint8_t *masks, uint32_t W, uint32_t H, uint32_t tile_size,
                                     uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
                                     const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
-                                    int32_t *tile_order, gsb200_stream_t stream) {
+                                    int32_t *tile_order, float *blend_stream, int32_t *tile_counts,
+                                    gsb200_stream_t stream) {
     (void)M;
     if (int e = check_geom(tile_size, W, H, tile_width, tile_height)) return e;
     if (C == 0 || W == 0 || H == 0) return 0;
     BlendGeom G{C, W, H, tile_size, tile_width, tile_height, n_isects};
     cudaStream_t s = (cudaStream_t)stream;
+    if (stream_blend_enabled() && blend_stream_supported(tile_size, D, n_isects))
+        return blend_stream_fwd(G, D, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
+                                render_colors, render_alphas, last_ids, tile_order, blend_stream, tile_counts, s);
     GSB_DISPATCH_CDIM(D, (launch_fwd<CD>(G, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
                                          render_colors, render_alphas, last_ids, tile_order, s)));
 }
@@ -605,12 +513,23 @@ extern "C" int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, ui
                                     uint32_t tile_width, uint32_t tile_height, const int32_t *tile_offsets,
                                     const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
                                     const float *v_render_colors, const float *v_render_alphas, const int32_t *tile_order,
+                                    const float *blend_stream, const int32_t *tile_counts,
                                     float *grad_scratch, float *v_means2d_abs, float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                                     gsb200_stream_t stream) {
     if (int e = check_geom(tile_size, W, H, tile_width, tile_height)) return e;
     if (M == 0) return 0;
     BlendGeom G{C, W, H, tile_size, tile_width, tile_height, n_isects};
     cudaStream_t s = (cudaStream_t)stream;
+    if (blend_stream != nullptr && tile_counts != nullptr && stream_blend_enabled() &&
+        blend_stream_supported(tile_size, D, n_isects)) {
+        GSB_CUDA_OK(cudaMemsetAsync(grad_scratch, 0, sizeof(float) * (size_t)M * grad_record(D), s));
+        if (n_isects > 0)
+            if (int e = blend_stream_bwd(G, D, M, backgrounds, masks, tile_offsets, render_alphas, last_ids, v_render_colors,
+                                         v_render_alphas, tile_order, blend_stream, tile_counts, grad_scratch,
+                                         v_means2d_abs != nullptr, s))
+                return e;
+        GSB_DISPATCH_CDIM(D, (launch_unpack<CD>(M, grad_scratch, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s)));
+    }
     GSB_DISPATCH_CDIM(D, (launch_bwd<CD>(G, M, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets,
                                          flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order,
                                          grad_scratch, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s)));

@@ -1,0 +1,666 @@
+// Stage 3 / 4a for 16x16 tiles and <= 4 colour channels: producer/consumer alpha blend over a packed,
+// pre-culled per-tile record stream (sm_100a).
+//
+// Same per-pixel arithmetic as blend.cu (i.e. the reference's, rasterize_to_pixels_fwd.cu:121-166 and
+// rasterize_to_pixels_bwd.cu:192-241), different organisation:
+//
+//   * one CTA per tile = 4/NP consumer warps + 1 producer warp.  A consumer thread owns NP pairs of pixels
+//     (x, y) / (x, y + 4) of an 8x8 block and evaluates each pair with packed FP32 (FFMA2 / FMUL2 / FADD2):
+//     one instruction stream for two pixels, per-lane results bit-identical to the scalar expression;
+//   * forward: the producer warp gathers the tile's Gaussians through flatten_ids (software-pipelined,
+//     L2-resident attributes), tests each 1/255-alpha ellipse against the four 8x8 blocks of the tile
+//     (exact, conservative -- blend.cuh), drops the ones that miss the tile, and appends a 48-byte record
+//     {x, y, opacity, (local index << 4 | block mask)} {conic a, b, c, flatten id} {colour[4]} to a ring of
+//     shared-memory stages guarded by mbarriers -- and to a per-tile stream in global memory.  Consumers
+//     never stage, never cull and never meet a block-wide barrier: one LDS + ballot per 32 records;
+//   * backward: the stream the forward left behind is contiguous per tile, so one elected thread stages it
+//     back-to-front with cp.async.bulk (TMA, mbarrier complete_tx) -- no gather, no re-culling; the per-warp
+//     reductions and the packed-record REDs are the ones of blend.cu, amortised over 64 pixels per warp
+//     instead of 32.
+#include "blend.cuh"
+
+namespace gsb200 {
+
+constexpr int kStageRecs = 64;  // records per pipeline stage
+#ifndef GSB_STREAM_STAGES
+#define GSB_STREAM_STAGES 4
+#endif
+constexpr int kStages = GSB_STREAM_STAGES;
+constexpr int kRecBytes = 48;
+constexpr uint32_t kEndFlag = 0x100;
+constexpr float kNegLog2e = -1.4426950408889634f;
+
+// ---- mbarrier / bulk-copy primitives (32-bit shared-window addresses) ----------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// global -> shared bulk copy (TMA, non-tensor form); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t lds1u(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }
+// per-thread gradient partials: with one pixel pair per thread the first (only) contribution is an assignment
+template <bool ASSIGN>
+__device__ __forceinline__ void acc(float &dst, float v) {
+    if (ASSIGN) dst = v; else dst += v;
+}
+
+struct StreamShared {
+    float4 rec[kStages * kStageRecs * 3];
+    unsigned long long full[kStages];
+    unsigned long long empty[kStages];
+    int count[kStages];
+    int done;        // consumer warps that need no more records (forward)
+    int last_stage;  // last stage in which any pixel of the tile took a contribution (forward)
+    int emitted;     // records the producer emitted (forward)
+};
+
+// pixel pair p of warp w: block b = w * NP + p at (b & 1, b >> 1) * 8; lane -> column lane & 7, rows lane >> 3 and + 4
+template <int NP>
+__device__ __forceinline__ void pair_pixels(uint32_t w, uint32_t lane, uint32_t p, uint32_t tile_x, uint32_t tile_y, uint32_t &j,
+                                            uint32_t &i0) {
+    const uint32_t b = w * NP + p;
+    j = tile_x * 16 + (b & 1) * 8 + (lane & 7);
+    i0 = tile_y * 16 + (b >> 1) * 8 + (lane >> 3);
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+template <int CDIM, int NP>
+__global__ void __launch_bounds__((4 / NP + 1) * 32, NP == 1 ? 6 : 8)
+blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
+                        const float *__restrict__ colors, const float *__restrict__ opacities,
+                        const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
+                        const int32_t *__restrict__ tile_offsets, const int32_t *__restrict__ flatten_ids,
+                        float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids,
+                        const int32_t *__restrict__ tile_order, float4 *__restrict__ stream, int32_t *__restrict__ tile_counts) {
+    constexpr uint32_t NCONS = 4 / NP;
+    __shared__ __align__(128) StreamShared S;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ct_lin = tile_order ? (uint32_t)tile_order[blockIdx.x] : blockIdx.x;
+    const uint32_t cam = ct_lin / (G.tw * G.th), tile_id = ct_lin % (G.tw * G.th);
+    const uint32_t tile_y = tile_id / G.tw, tile_x = tile_id % G.tw;
+    const size_t ct = (size_t)cam * G.tw * G.th + tile_id;
+    const float *bg = backgrounds ? backgrounds + (size_t)cam * CDIM : nullptr;
+
+    if (masks != nullptr && !masks[ct]) {  // rasterize_to_pixels_fwd.cu:70-76
+        if (warp < NCONS) {
+#pragma unroll
+            for (uint32_t p = 0; p < NP; ++p) {
+                uint32_t j, i0;
+                pair_pixels<NP>(warp, lane, p, tile_x, tile_y, j, i0);
+#pragma unroll
+                for (uint32_t r = 0; r < 2; ++r) {
+                    const uint32_t i = i0 + 4 * r;
+                    if (i < G.H && j < G.W) {
+                        const size_t pix = ((size_t)cam * G.H + i) * G.W + j;
+#pragma unroll
+                        for (int k = 0; k < CDIM; ++k) render_colors[pix * CDIM + k] = bg ? bg[k] : 0.f;
+                    }
+                }
+            }
+        }
+        if (tid == 0 && tile_counts) tile_counts[ct] = 0;
+        return;
+    }
+    const int32_t range_start = tile_offsets[ct];
+    const int32_t range_end = (cam == G.C - 1 && tile_id == G.tw * G.th - 1) ? (int32_t)G.n_isects : tile_offsets[ct + 1];
+    const uint32_t n = (uint32_t)(range_end - range_start);
+
+    const uint32_t a_rec = (uint32_t)__cvta_generic_to_shared(S.rec);
+    const uint32_t a_full = (uint32_t)__cvta_generic_to_shared(S.full), a_empty = (uint32_t)__cvta_generic_to_shared(S.empty);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(a_full + 8 * s, 32);      // every producer lane arrives
+            mbar_init(a_empty + 8 * s, NCONS);  // lane 0 of every consumer warp arrives
+        }
+        S.done = 0;
+        S.last_stage = -1;
+        S.emitted = 0;
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == NCONS) {
+        // ------------------------------------------------------------------ producer warp
+        // pixel-centre rectangles of the four 8x8 blocks, clipped to the image (empty: x1 < x0)
+        float bx0[4], bx1[4], by0[4], by1[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int xl = (int)(tile_x * 16 + (b & 1) * 8), yl = (int)(tile_y * 16 + (b >> 1) * 8);
+            const int xh = min(xl + 7, (int)G.W - 1), yh = min(yl + 7, (int)G.H - 1);
+            const bool ok = xl <= xh && yl <= yh;
+            bx0[b] = (float)xl + 0.5f;
+            bx1[b] = ok ? (float)xh + 0.5f : -FLT_MAX;
+            by0[b] = (float)yl + 0.5f;
+            by1[b] = ok ? (float)yh + 0.5f : -FLT_MAX;
+        }
+        struct Cand {
+            float2 xy;
+            float a, b, c, o;
+            float col[4];
+            int32_t g;
+        };
+        auto load = [&](int32_t g) {
+            Cand q;
+            q.g = g;
+            q.col[0] = q.col[1] = q.col[2] = q.col[3] = 0.f;
+            if (g >= 0) {
+                q.xy = __ldg(means2d + g);
+                q.o = __ldg(opacities + g);
+                q.a = __ldg(conics + (size_t)g * 3);
+                q.b = __ldg(conics + (size_t)g * 3 + 1);
+                q.c = __ldg(conics + (size_t)g * 3 + 2);
+#pragma unroll
+                for (int k = 0; k < CDIM; ++k) q.col[k] = __ldg(colors + (size_t)g * CDIM + k);
+            } else {
+                q.xy = make_float2(0.f, 0.f);
+                q.a = q.b = q.c = q.o = 0.f;
+            }
+            return q;
+        };
+        auto ids = [&](uint32_t at) { return at + lane < n ? __ldg(flatten_ids + range_start + at + lane) : -1; };
+
+        uint32_t total = 0;            // records emitted so far
+        uint32_t acquired = kStages;   // stages [0, acquired) may be written (the first ring round is free)
+        auto acquire_to = [&](uint32_t stage) {
+            while (acquired <= stage) {
+                mbar_wait(a_empty + 8 * (acquired % kStages), ((acquired / kStages) - 1) & 1);
+                ++acquired;
+            }
+        };
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        int32_t g_next = ids(32);
+        Cand cur = load(ids(0));
+        for (uint32_t base = 0; base < n; base += 32) {
+            if (*reinterpret_cast<volatile int *>(&S.done) >= (int)NCONS) break;
+            // software pipeline: attributes of the next chunk and ids of the one after it are in flight while this
+            // chunk is tested
+            const Cand nxt = load(g_next);
+            g_next = ids(base + 64);
+
+            uint32_t hitmask = 0;
+            if (cur.g >= 0) {
+                const float qmax = cull_qmax(cur.a, cur.b, cur.c, cur.o);
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (bx1[b] >= bx0[b] &&
+                        ellipse_hits_rect(cur.xy.x, cur.xy.y, cur.a, cur.b, cur.c, qmax, bx0[b], bx1[b], by0[b], by1[b]))
+                        hitmask |= 1u << b;
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, hitmask != 0);
+            const uint32_t cnt = __popc(ballot);
+            if (cnt) {
+                acquire_to((total + cnt - 1) / kStageRecs);
+                if (hitmask) {
+                    const uint32_t pos = total + __popc(ballot & lt_mask);
+                    const uint32_t slot = pos % (kStages * kStageRecs);
+                    const float4 q0 = make_float4(cur.xy.x, cur.xy.y, cur.o, __uint_as_float(((base + lane) << 4) | hitmask));
+                    const float4 q1 = make_float4(cur.a, cur.b, cur.c, __int_as_float(cur.g));
+                    const float4 q2 = make_float4(cur.col[0], cur.col[1], cur.col[2], cur.col[3]);
+                    const uint32_t dst = a_rec + slot * kRecBytes;
+                    sts4(dst, q0);
+                    sts4(dst + 16, q1);
+                    sts4(dst + 32, q2);
+                    if (stream != nullptr) {
+                        float4 *out = stream + ((size_t)range_start + pos) * 3;
+                        out[0] = q0;
+                        out[1] = q1;
+                        out[2] = q2;
+                    }
+                }
+                const uint32_t st_old = total / kStageRecs;
+                total += cnt;
+                if (total / kStageRecs != st_old) {  // stage st_old is complete: publish it
+                    if (lane == 0) S.count[st_old % kStages] = kStageRecs;
+                    __syncwarp();
+                    mbar_arrive(a_full + 8 * (st_old % kStages));
+                }
+            }
+            cur = nxt;
+        }
+        // last (possibly empty) stage carries the end flag
+        const uint32_t st_last = total / kStageRecs;
+        acquire_to(st_last);
+        if (lane == 0) {
+            S.count[st_last % kStages] = (int)(total % kStageRecs) | (int)kEndFlag;
+            S.emitted = (int)total;
+        }
+        __syncwarp();
+        mbar_arrive(a_full + 8 * (st_last % kStages));
+    } else {
+        // ------------------------------------------------------------------ consumer warps
+        uint32_t pj[NP], pi0[NP];
+        float px[NP];
+        float2 npy[NP];  // minus the pixel-centre rows
+        // T <= 0 marks a pixel that takes no more Gaussians (saturated: -T is its transmittance; outside the image: -1)
+        float2 T[NP], out[NP][CDIM];
+        uint32_t cur0[NP], cur1[NP];  // record word (local index << 4 | mask, never 0) of the last contribution
+        bool all_done = true;
+#pragma unroll
+        for (uint32_t p = 0; p < NP; ++p) {
+            pair_pixels<NP>(warp, lane, p, tile_x, tile_y, pj[p], pi0[p]);
+            px[p] = (float)pj[p] + 0.5f;
+            npy[p] = make_float2(-((float)pi0[p] + 0.5f), -((float)(pi0[p] + 4) + 0.5f));
+            const bool in0 = pj[p] < G.W && pi0[p] < G.H, in1 = pj[p] < G.W && pi0[p] + 4 < G.H;
+            all_done = all_done && !in0 && !in1;
+            T[p] = make_float2(in0 ? 1.f : -1.f, in1 ? 1.f : -1.f);
+            cur0[p] = cur1[p] = 0;
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k) out[p][k] = make_float2(0.f, 0.f);
+        }
+        bool warp_done = __ballot_sync(0xffffffffu, !all_done) == 0;
+        if (warp_done && lane == 0) atomicAdd(&S.done, 1);
+        const uint32_t hitsel = ((1u << NP) - 1u) << (warp * NP);
+        int my_last_stage = -1;
+
+        for (uint32_t k = 0;; ++k) {
+            const uint32_t slot = k % kStages;
+            mbar_wait(a_full + 8 * slot, (k / kStages) & 1);
+            const int cf = *reinterpret_cast<volatile int *>(&S.count[slot]);
+            const uint32_t nrec = (uint32_t)cf & 0xffu;
+            if (!warp_done) {
+                uint32_t cur_sig = 0;  // changes iff some pixel of this thread takes a Gaussian of this stage
+#pragma unroll
+                for (uint32_t p = 0; p < NP; ++p) cur_sig += cur0[p] + cur1[p];
+                const uint32_t a_stage = a_rec + slot * (kStageRecs * kRecBytes);
+                for (uint32_t c0 = 0; c0 < nrec; c0 += 32) {
+                    const uint32_t e = c0 + lane;
+                    const uint32_t word = e < nrec ? lds1u(a_stage + e * kRecBytes + 12) : 0u;
+                    unsigned m = __ballot_sync(0xffffffffu, (word & hitsel) != 0);
+                    while (m) {
+                        const uint32_t t = c0 + (uint32_t)__ffs(m) - 1u;
+                        m &= m - 1;
+                        const float4 A = lds4(a_stage + t * kRecBytes);
+                        const float4 B = lds4(a_stage + t * kRecBytes + 16);
+                        const float4 C4 = lds4(a_stage + t * kRecBytes + 32);
+                        const float cs[4] = {C4.x, C4.y, C4.z, C4.w};
+                        const uint32_t wt = __float_as_uint(A.w);
+#pragma unroll
+                        for (uint32_t p = 0; p < NP; ++p) {
+                            if (NP > 1 && !((wt >> (warp * NP + p)) & 1u)) continue;
+                            // the scalar expression of blend.cu, two rows at a time (contraction spelled out)
+                            const float dx = A.x - px[p];
+                            const float2 dy = __fadd2_rn(bc(A.y), npy[p]);
+                            float2 tt = __fmul2_rn(bc(B.z), dy);
+                            const float u = B.x * dx, v = B.y * dx;
+                            tt = __fmul2_rn(dy, tt);
+                            float2 uu = __ffma2_rn(bc(dx), bc(u), tt);
+                            uu = __fmul2_rn(uu, bc(0.5f));
+                            const float2 sigma = __ffma2_rn(dy, bc(v), uu);
+                            const float2 ee = __fmul2_rn(sigma, bc(kNegLog2e));
+                            const float2 ov = __fmul2_rn(bc(A.z), make_float2(exp2f(ee.x), exp2f(ee.y)));
+                            const float2 alpha = make_float2(fminf(kAlphaMax, ov.x), fminf(kAlphaMax, ov.y));
+                            const float2 next_T = __fmul2_rn(T[p], __ffma2_rn(alpha, bc(-1.f), bc(1.f)));
+                            const bool ok0 = !(sigma.x < 0.f || alpha.x < kAlphaMin), ok1 = !(sigma.y < 0.f || alpha.y < kAlphaMin);
+                            // a finished pixel has T <= 0, hence next_T <= 0 <= 1e-4: it can never take
+                            const bool take0 = ok0 && !(next_T.x <= kTStop), take1 = ok1 && !(next_T.y <= kTStop);
+                            float2 vis = __fmul2_rn(alpha, T[p]);
+                            vis.x = take0 ? vis.x : 0.f;
+                            vis.y = take1 ? vis.y : 0.f;
+#pragma unroll
+                            for (int c = 0; c < CDIM; ++c) out[p][c] = __ffma2_rn(bc(cs[c]), vis, out[p][c]);
+                            T[p].x = take0 ? next_T.x : (ok0 ? -fabsf(T[p].x) : T[p].x);
+                            T[p].y = take1 ? next_T.y : (ok1 ? -fabsf(T[p].y) : T[p].y);
+                            cur0[p] = take0 ? wt : cur0[p];
+                            cur1[p] = take1 ? wt : cur1[p];
+                        }
+                    }
+                    bool pending = false;
+#pragma unroll
+                    for (uint32_t p = 0; p < NP; ++p) pending = pending || T[p].x > 0.f || T[p].y > 0.f;
+                    if (__ballot_sync(0xffffffffu, pending) == 0) {
+                        warp_done = true;
+                        if (lane == 0) atomicAdd(&S.done, 1);
+                        break;
+                    }
+                }
+                uint32_t cur_now = 0;
+#pragma unroll
+                for (uint32_t p = 0; p < NP; ++p) cur_now += cur0[p] + cur1[p];
+                if (__any_sync(0xffffffffu, cur_now != cur_sig)) my_last_stage = (int)k;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_empty + 8 * slot);
+            if (cf & (int)kEndFlag) break;
+        }
+        if (lane == 0 && my_last_stage >= 0) atomicMax(&S.last_stage, my_last_stage);
+
+#pragma unroll
+        for (uint32_t p = 0; p < NP; ++p) {
+#pragma unroll
+            for (uint32_t r = 0; r < 2; ++r) {
+                const uint32_t i = pi0[p] + 4 * r;
+                if (i < G.H && pj[p] < G.W) {
+                    const size_t pix = ((size_t)cam * G.H + i) * G.W + pj[p];
+                    const float Tf = fabsf(r ? T[p].y : T[p].x);
+                    render_alphas[pix] = 1.f - Tf;
+#pragma unroll
+                    for (int k = 0; k < CDIM; ++k) {
+                        const float o = r ? out[p][k].y : out[p][k].x;
+                        render_colors[pix * CDIM + k] = bg ? (o + Tf * bg[k]) : o;
+                    }
+                    const uint32_t cl = r ? cur1[p] : cur0[p];
+                    // reference: index into the sorted list of the last contributing Gaussian, 0 if none
+                    last_ids[pix] = cl ? range_start + (int32_t)(cl >> 4) : 0;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // the backward needs the stream up to the last stage that contributed to any pixel
+    if (tid == 0 && tile_counts != nullptr)
+        tile_counts[ct] = min(S.emitted, (S.last_stage + 1) * kStageRecs);
+}
+
+// --------------------------------------------------------------------------------------------- backward
+template <int CDIM, int NP, bool ABS>
+__global__ void __launch_bounds__((4 / NP + 1) * 32, NP == 1 ? 5 : 6)
+blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
+                        const int32_t *__restrict__ tile_offsets, const float *__restrict__ render_alphas,
+                        const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
+                        const float *__restrict__ v_render_alphas, const int32_t *__restrict__ tile_order,
+                        const float4 *__restrict__ stream, const int32_t *__restrict__ tile_counts,
+                        float *__restrict__ grad_rec) {
+    constexpr uint32_t NCONS = 4 / NP;
+    constexpr uint32_t REC = grad_record(CDIM);
+    constexpr int NMAIN = CDIM + 5;  // [rgb(CDIM) conic(3) xy(2)] reduced in groups of 8, then [opac (absx absy)]
+    constexpr int NGRP = (NMAIN + 7) / 8;
+    __shared__ __align__(128) StreamShared S;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t ct_lin = tile_order ? (uint32_t)tile_order[blockIdx.x] : blockIdx.x;
+    const uint32_t cam = ct_lin / (G.tw * G.th), tile_id = ct_lin % (G.tw * G.th);
+    const uint32_t tile_y = tile_id / G.tw, tile_x = tile_id % G.tw;
+    const size_t ct = (size_t)cam * G.tw * G.th + tile_id;
+    if (masks != nullptr && !masks[ct]) return;
+    const int32_t cnt = tile_counts[ct];
+    if (cnt <= 0) return;
+    const int32_t range_start = tile_offsets[ct];
+    const uint32_t nst = ((uint32_t)cnt + kStageRecs - 1) / kStageRecs;
+    const float *bg = backgrounds ? backgrounds + (size_t)cam * CDIM : nullptr;
+
+    const uint32_t a_rec = (uint32_t)__cvta_generic_to_shared(S.rec);
+    const uint32_t a_full = (uint32_t)__cvta_generic_to_shared(S.full), a_empty = (uint32_t)__cvta_generic_to_shared(S.empty);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(a_full + 8 * s, 1);       // the issuing thread's arrive.expect_tx (+ the copy's bytes)
+            mbar_init(a_empty + 8 * s, NCONS);  // lane 0 of every consumer warp
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == NCONS) {
+        // ------------------------------------------------------------------ producer: one thread, bulk copies
+        if (lane == 0) {
+            const char *src = reinterpret_cast<const char *>(stream) + (size_t)range_start * kRecBytes;
+            for (uint32_t j = 0; j < nst; ++j) {  // stages back to front
+                const uint32_t st = nst - 1 - j, slot = j % kStages;
+                if (j >= kStages) mbar_wait(a_empty + 8 * slot, ((j / kStages) - 1) & 1);
+                const uint32_t nrec = min((uint32_t)kStageRecs, (uint32_t)cnt - st * kStageRecs);
+                const uint32_t bytes = nrec * kRecBytes;
+                mbar_arrive_expect_tx(a_full + 8 * slot, bytes);
+                bulk_g2s(a_rec + slot * (kStageRecs * kRecBytes), src + (size_t)st * kStageRecs * kRecBytes, bytes,
+                         a_full + 8 * slot);
+            }
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- consumer warps
+    float px[NP];
+    float2 npy[NP], T[NP], Tfin[NP], v_a[NP], bg_dot[NP];
+    float2 buffer[NP][CDIM], v_c[NP][CDIM];
+    int32_t bin0[NP], bin1[NP];
+    int32_t warp_bin = -1;
+#pragma unroll
+    for (uint32_t p = 0; p < NP; ++p) {
+        uint32_t j, i0;
+        pair_pixels<NP>(warp, lane, p, tile_x, tile_y, j, i0);
+        px[p] = (float)j + 0.5f;
+        npy[p] = make_float2(-((float)i0 + 0.5f), -((float)(i0 + 4) + 0.5f));
+        const bool in0 = j < G.W && i0 < G.H, in1 = j < G.W && i0 + 4 < G.H;
+        const size_t pix0 = ((size_t)cam * G.H + i0) * G.W + j, pix1 = pix0 + (size_t)4 * G.W;
+        Tfin[p] = make_float2(in0 ? 1.f - render_alphas[pix0] : 1.f, in1 ? 1.f - render_alphas[pix1] : 1.f);
+        T[p] = Tfin[p];
+        v_a[p] = make_float2(in0 ? v_render_alphas[pix0] : 0.f, in1 ? v_render_alphas[pix1] : 0.f);
+        bg_dot[p] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k) {
+            buffer[p][k] = make_float2(0.f, 0.f);
+            v_c[p][k] = make_float2(in0 ? v_render_colors[pix0 * CDIM + k] : 0.f, in1 ? v_render_colors[pix1 * CDIM + k] : 0.f);
+            if (bg) bg_dot[p] = __ffma2_rn(bc(bg[k]), v_c[p][k], bg_dot[p]);
+        }
+        // local (per-tile) index of the last contributing Gaussian; -1: nothing to do for this pixel
+        bin0[p] = in0 ? last_ids[pix0] - range_start : -1;
+        bin1[p] = in1 ? last_ids[pix1] - range_start : -1;
+        warp_bin = max(warp_bin, max(bin0[p], bin1[p]));
+    }
+    warp_bin = __reduce_max_sync(0xffffffffu, warp_bin);
+    const uint32_t hitsel = ((1u << NP) - 1u) << (warp * NP);
+    const uint32_t slot8 = spread_slot<8>(lane), slot4 = spread_slot<4>(lane);
+    const bool pub8 = (lane & 3) == 0, pub4 = (lane & 7) == 0;
+
+    for (uint32_t j = 0; j < nst; ++j) {
+        const uint32_t st = nst - 1 - j, slot = j % kStages;
+        mbar_wait(a_full + 8 * slot, (j / kStages) & 1);
+        const int32_t nrec = (int32_t)min((uint32_t)kStageRecs, (uint32_t)cnt - st * kStageRecs);
+        const uint32_t a_stage = a_rec + slot * (kStageRecs * kRecBytes);
+        if (warp_bin >= 0) {
+            for (int32_t c0 = 0; c0 < nrec; c0 += 32) {
+                const int32_t r = nrec - 1 - c0 - (int32_t)lane;  // records back to front
+                const uint32_t word = r >= 0 ? lds1u(a_stage + (uint32_t)r * kRecBytes + 12) : 0u;
+                unsigned m = __ballot_sync(0xffffffffu, (word & hitsel) != 0 && (int32_t)(word >> 4) <= warp_bin);
+                while (m) {
+                    const uint32_t t = (uint32_t)(nrec - 1 - c0) - ((uint32_t)__ffs(m) - 1u);
+                    m &= m - 1;
+                    const float4 A = lds4(a_stage + t * kRecBytes);
+                    const float4 B = lds4(a_stage + t * kRecBytes + 16);
+                    const float4 C4 = lds4(a_stage + t * kRecBytes + 32);
+                    const float cs[4] = {C4.x, C4.y, C4.z, C4.w};
+                    const uint32_t wt = __float_as_uint(A.w);
+                    const int32_t idx = (int32_t)(wt >> 4);
+                    const float opac = A.z;
+                    float vals[NGRP * 8];
+                    float tail[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < NGRP * 8; ++k) vals[k] = 0.f;
+                    bool any_valid = false;
+#pragma unroll
+                    for (uint32_t p = 0; p < NP; ++p) {
+                        if (NP > 1 && !((wt >> (warp * NP + p)) & 1u)) continue;
+                        const float dx = A.x - px[p];
+                        const float2 dy = __fadd2_rn(bc(A.y), npy[p]);
+                        float2 tt = __fmul2_rn(bc(B.z), dy);
+                        const float u = B.x * dx, v = B.y * dx;
+                        tt = __fmul2_rn(dy, tt);
+                        float2 uu = __ffma2_rn(bc(dx), bc(u), tt);
+                        uu = __fmul2_rn(uu, bc(0.5f));
+                        const float2 sigma = __ffma2_rn(dy, bc(v), uu);
+                        const float2 ee = __fmul2_rn(sigma, bc(kNegLog2e));
+                        const float2 vis = make_float2(exp2f(ee.x), exp2f(ee.y));
+                        const float2 ov = __fmul2_rn(bc(opac), vis);
+                        const float2 alpha = make_float2(fminf(kAlphaMax, ov.x), fminf(kAlphaMax, ov.y));
+                        const bool valid0 = idx <= bin0[p] && !(sigma.x < 0.f || alpha.x < kAlphaMin);
+                        const bool valid1 = idx <= bin1[p] && !(sigma.y < 0.f || alpha.y < kAlphaMin);
+                        if (!__any_sync(0xffffffffu, valid0 || valid1)) continue;
+                        any_valid = true;
+                        // packed operands have no negate modifier: carry the sign in ra (nra = -1 / (1 - alpha), exact) and in
+                        // the v_sigma chain (nvs = -v_sigma) and restore it in the per-thread sums, where negation is free
+                        const float2 nom = __fadd2_rn(alpha, bc(-1.f));
+                        const float2 nra = make_float2(1.f / nom.x, 1.f / nom.y);
+                        const float2 ra = make_float2(-nra.x, -nra.y);
+                        const float2 Tn = __fmul2_rn(T[p], ra);
+                        T[p].x = valid0 ? Tn.x : T[p].x;
+                        T[p].y = valid1 ? Tn.y : T[p].y;
+                        float2 fac = __fmul2_rn(alpha, Tn);
+                        fac.x = valid0 ? fac.x : 0.f;
+                        fac.y = valid1 ? fac.y : 0.f;
+                        float2 v_alpha = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < CDIM; ++k) {
+                            const float2 gk = __fmul2_rn(fac, v_c[p][k]);
+                            acc<NP == 1>(vals[k], gk.x + gk.y);
+                            const float2 nbr = __fmul2_rn(buffer[p][k], nra);  // -(buffer * ra)
+                            const float2 diff = __ffma2_rn(bc(cs[k]), Tn, nbr);
+                            v_alpha = k == 0 ? __fmul2_rn(diff, v_c[p][k]) : __ffma2_rn(diff, v_c[p][k], v_alpha);
+                            buffer[p][k] = __ffma2_rn(bc(cs[k]), fac, buffer[p][k]);
+                        }
+                        v_alpha = __ffma2_rn(__fmul2_rn(Tfin[p], ra), v_a[p], v_alpha);
+                        if (bg) v_alpha = __ffma2_rn(__fmul2_rn(Tfin[p], nra), bg_dot[p], v_alpha);
+                        const bool gate0 = valid0 && ov.x <= kAlphaMax, gate1 = valid1 && ov.y <= kAlphaMax;
+                        float2 nvs = __fmul2_rn(ov, v_alpha);  // -v_sigma
+                        nvs.x = gate0 ? nvs.x : 0.f;
+                        nvs.y = gate1 ? nvs.y : 0.f;
+                        const float2 hs = __fmul2_rn(nvs, bc(0.5f));
+                        const float2 ga = __fmul2_rn(__fmul2_rn(hs, bc(dx)), bc(dx));
+                        const float2 gb = __fmul2_rn(__fmul2_rn(nvs, bc(dx)), dy);
+                        const float2 gc = __fmul2_rn(__fmul2_rn(hs, dy), dy);
+                        const float2 gx = __fmul2_rn(nvs, __ffma2_rn(bc(B.y), dy, bc(u)));
+                        const float2 gy = __fmul2_rn(nvs, __ffma2_rn(bc(B.z), dy, bc(v)));
+                        acc<NP == 1>(vals[CDIM + 0], -ga.x - ga.y);
+                        acc<NP == 1>(vals[CDIM + 1], -gb.x - gb.y);
+                        acc<NP == 1>(vals[CDIM + 2], -gc.x - gc.y);
+                        acc<NP == 1>(vals[CDIM + 3], -gx.x - gx.y);
+                        acc<NP == 1>(vals[CDIM + 4], -gy.x - gy.y);
+                        const float2 go = __fmul2_rn(vis, v_alpha);
+                        acc<NP == 1>(tail[0], (gate0 ? go.x : 0.f) + (gate1 ? go.y : 0.f));
+                        if (ABS) {
+                            acc<NP == 1>(tail[1], fabsf(gx.x) + fabsf(gx.y));
+                            acc<NP == 1>(tail[2], fabsf(gy.x) + fabsf(gy.y));
+                        }
+                    }
+                    if (!any_valid) continue;
+#pragma unroll
+                    for (int gi = 0; gi < NGRP; ++gi) reduce_spread<8>(vals + gi * 8, lane);
+                    float tail_sum;
+                    if (ABS) {
+                        reduce_spread<4>(tail, lane);
+                        tail_sum = tail[0];
+                    } else {
+                        tail_sum = warp_sum(tail[0]);
+                    }
+                    float *rec = grad_rec + (size_t)__float_as_int(B.w) * REC;
+#pragma unroll
+                    for (int gi = 0; gi < NGRP; ++gi) {
+                        const uint32_t off = gi * 8 + slot8;
+                        if (pub8 && off < (uint32_t)NMAIN) red_add(rec + off, vals[gi * 8]);
+                    }
+                    if (ABS) {
+                        if (pub4 && slot4 < 3) red_add(rec + NMAIN + slot4, tail_sum);
+                    } else {
+                        if (lane == 0) red_add(rec + NMAIN, tail_sum);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_empty + 8 * slot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+#ifndef GSB_STREAM_NP
+#define GSB_STREAM_NP 1
+#endif
+constexpr int kNP = GSB_STREAM_NP;
+
+bool blend_stream_supported(uint32_t tile_size, uint32_t cdim, int64_t n_isects) {
+    return tile_size == 16 && cdim >= 1 && cdim <= 4 && n_isects < (int64_t(1) << 28);
+}
+
+template <int CDIM>
+static int fwd_t(const BlendGeom &G, const float *means2d, const float *conics, const float *colors, const float *opacities,
+                 const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                 float *render_colors, float *render_alphas, int32_t *last_ids, int32_t *tile_order, float *blend_stream,
+                 int32_t *tile_counts, cudaStream_t s) {
+    const uint32_t T = G.C * G.tw * G.th;
+    if (tile_order != nullptr)
+        if (int e = launch_tile_order(T, G.n_isects, tile_offsets, tile_order, s)) return e;
+    blend_stream_fwd_kernel<CDIM, kNP><<<T, (4 / kNP + 1) * 32, 0, s>>>(
+        G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
+        render_colors, render_alphas, last_ids, tile_order, reinterpret_cast<float4 *>(blend_stream), tile_counts);
+    return check_launch("blend_stream_fwd");
+}
+
+int blend_stream_fwd(const BlendGeom &G, uint32_t cdim, const float *means2d, const float *conics, const float *colors,
+                     const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
+                     const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
+                     int32_t *tile_order, float *blend_stream, int32_t *tile_counts, cudaStream_t s) {
+#define GSB_FWD_CASE(D)                                                                                                \
+    case D:                                                                                                            \
+        return fwd_t<D>(G, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids, render_colors, \
+                        render_alphas, last_ids, tile_order, blend_stream, tile_counts, s);
+    switch (cdim) {
+        GSB_FWD_CASE(1) GSB_FWD_CASE(2) GSB_FWD_CASE(3) GSB_FWD_CASE(4)
+        default: return fail(2, "gsb200_rasterize: stream blend supports 1..4 channels");
+    }
+#undef GSB_FWD_CASE
+}
+
+template <int CDIM>
+static int bwd_t(const BlendGeom &G, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
+                 const float *render_alphas, const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
+                 const int32_t *tile_order, const float *blend_stream, const int32_t *tile_counts, float *grad_scratch,
+                 bool absgrad, cudaStream_t s) {
+    const uint32_t T = G.C * G.tw * G.th;
+    const float4 *st = reinterpret_cast<const float4 *>(blend_stream);
+    if (absgrad)
+        blend_stream_bwd_kernel<CDIM, kNP, true><<<T, (4 / kNP + 1) * 32, 0, s>>>(
+            G, backgrounds, masks, tile_offsets, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, st,
+            tile_counts, grad_scratch);
+    else
+        blend_stream_bwd_kernel<CDIM, kNP, false><<<T, (4 / kNP + 1) * 32, 0, s>>>(
+            G, backgrounds, masks, tile_offsets, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, st,
+            tile_counts, grad_scratch);
+    return check_launch("blend_stream_bwd");
+}
+
+int blend_stream_bwd(const BlendGeom &G, uint32_t cdim, uint32_t M, const float *backgrounds, const uint8_t *masks,
+                     const int32_t *tile_offsets, const float *render_alphas, const int32_t *last_ids,
+                     const float *v_render_colors, const float *v_render_alphas, const int32_t *tile_order,
+                     const float *blend_stream, const int32_t *tile_counts, float *grad_scratch, bool absgrad, cudaStream_t s) {
+    (void)M;
+#define GSB_BWD_CASE(D)                                                                                                  \
+    case D:                                                                                                              \
+        return bwd_t<D>(G, backgrounds, masks, tile_offsets, render_alphas, last_ids, v_render_colors, v_render_alphas,   \
+                        tile_order, blend_stream, tile_counts, grad_scratch, absgrad, s);
+    switch (cdim) {
+        GSB_BWD_CASE(1) GSB_BWD_CASE(2) GSB_BWD_CASE(3) GSB_BWD_CASE(4)
+        default: return fail(2, "gsb200_rasterize: stream blend supports 1..4 channels");
+    }
+#undef GSB_BWD_CASE
+}
+
+}  // namespace gsb200

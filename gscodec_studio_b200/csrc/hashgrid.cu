@@ -1,5 +1,5 @@
-// EXPERIMENTAL (not yet run on a GPU, opt-in from Python): multi-resolution hash-grid
-// encoder of the reference's alternative ("gaussian_model") in-loop entropy model.
+// Multi-resolution hash-grid encoder of the reference's alternative ("gaussian_model") in-loop entropy model
+// (SURVEY.md section 8f.3).
 //
 // Replaces _gridencoder.grid_encode_forward / grid_encode_backward (third_party/gridencoder/src/gridencoder.cu:100-884,
 // bindings.cpp) for the way gsplat/compression_simulation/gaussian_distribution_model.py:60-182 calls them
@@ -78,7 +78,7 @@ grid_encode_fwd_kernel(uint32_t N, GridLevels L, bool ste_binary, const float *_
         uint32_t cell[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const float p = x[d] * (float)(R - 2u) + 0.5f;
+            const float p = __fadd_rn(__fmul_rn(x[d], (float)(R - 2u)), 0.5f);  // two roundings, as the reference (gridencoder.cu:183): no FMA
             const float fl = floorf(p);
             cell[d] = (uint32_t)fl;
             frac[d] = p - fl;
@@ -137,7 +137,7 @@ grid_encode_bwd_kernel(uint32_t N, GridLevels L, bool ste_binary, const float *_
     uint32_t cell[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        const float p = x[d] * (float)(R - 2u) + 0.5f;
+        const float p = __fadd_rn(__fmul_rn(x[d], (float)(R - 2u)), 0.5f);  // two roundings, as the reference (gridencoder.cu:183): no FMA
         const float fl = floorf(p);
         cell[d] = (uint32_t)fl;
         frac[d] = p - fl;

@@ -842,12 +842,19 @@ class _RasterizeToPixels(torch.autograd.Function):
         last_ids = torch.zeros((C, height, width), dtype=torch.int32, device=dev) if masks is not None \
             else torch.empty((C, height, width), dtype=torch.int32, device=dev)
         tile_order = torch.empty(max(C * th * tw, 1), dtype=torch.int32, device=dev)  # longest tiles first
+        # pre-culled per-tile record stream the forward leaves for the backward (16x16 tiles, D <= 4; see gsb200.h)
+        blend_stream = tile_counts = None
+        rec = int(_cabi.load_library().gsb200_blend_stream_record(D, tile_size))
+        if rec and any(ctx.needs_input_grad[:5]):
+            blend_stream = torch.empty(max(flatten_ids.numel(), 1) * rec, dtype=torch.float32, device=dev)
+            tile_counts = torch.empty(max(C * th * tw, 1), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             call("gsb200_rasterize_fwd", C, M, flatten_ids.numel(), D, ptr(means2d), ptr(conics), ptr(colors),
                  ptr(opacities), ptr(backgrounds), ptr(masks_u8), width, height, tile_size, tw, th, ptr(isect_offsets),
-                 ptr(flatten_ids), ptr(render_colors), ptr(render_alphas), ptr(last_ids), ptr(tile_order), stream_ptr(dev))
+                 ptr(flatten_ids), ptr(render_colors), ptr(render_alphas), ptr(last_ids), ptr(tile_order),
+                 ptr(blend_stream), ptr(tile_counts), stream_ptr(dev))
         ctx.save_for_backward(means2d, conics, colors, opacities, backgrounds, masks_u8, isect_offsets, flatten_ids,
-                              render_alphas, last_ids, tile_order)
+                              render_alphas, last_ids, tile_order, blend_stream, tile_counts)
         ctx.dims = (width, height, tile_size, absgrad)
         ctx.means2d_in = means2d_in if absgrad else None
         return render_colors, render_alphas
@@ -855,7 +862,7 @@ class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_render_colors, v_render_alphas):
         (means2d, conics, colors, opacities, backgrounds, masks_u8, isect_offsets, flatten_ids, render_alphas,
-         last_ids, tile_order) = ctx.saved_tensors
+         last_ids, tile_order, blend_stream, tile_counts) = ctx.saved_tensors
         width, height, tile_size, absgrad = ctx.dims
         C, th, tw = isect_offsets.shape
         D = colors.shape[-1]
@@ -874,7 +881,7 @@ class _RasterizeToPixels(torch.autograd.Function):
             call("gsb200_rasterize_bwd", C, M, flatten_ids.numel(), D, ptr(means2d), ptr(conics), ptr(colors),
                  ptr(opacities), ptr(backgrounds), ptr(masks_u8), width, height, tile_size, tw, th, ptr(isect_offsets),
                  ptr(flatten_ids), ptr(render_alphas), ptr(last_ids), ptr(v_render_colors), ptr(v_render_alphas),
-                 ptr(tile_order), ptr(scratch), ptr(v_abs), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opacities),
+                 ptr(tile_order), ptr(blend_stream), ptr(tile_counts), ptr(scratch), ptr(v_abs), ptr(v_means2d), ptr(v_conics), ptr(v_colors), ptr(v_opacities),
                  stream_ptr(dev))
         if absgrad:
             ctx.means2d_in.absgrad = v_abs  # strategies read info["means2d"].absgrad (_wrapper.py:1005-1006)

@@ -217,14 +217,23 @@ int gsb200_isect_offset_encode(int64_t n_isects, const int64_t *isect_ids, uint3
  * D must be in {1,2,3,4,5,8,9,16,17,32,33} (the host pads others, as _wrapper.py:496-541 does).
  * tile_order (optional, may be NULL): i32 [C*th*tw] scratch.  The forward fills it with the (camera, tile)
  * indices sorted longest-list-first and schedules its CTAs in that order (no straggler tail); pass the same
- * buffer to the backward. */
+ * buffer to the backward.
+ * blend_stream / tile_counts (optional, may be NULL): float [n_isects * gsb200_blend_stream_record(D, tile_size)] and
+ * i32 [C*th*tw].  When the record size is non-zero (16x16 tiles, D <= 4) the forward leaves its pre-culled,
+ * front-to-back per-tile record stream there (tile t's records start at tile_offsets[t]) and the backward stages it
+ * with bulk copies instead of gathering through flatten_ids again; NULL in the backward selects the gathering kernel. */
+uint32_t gsb200_blend_stream_record(uint32_t D, uint32_t tile_size);
+/* 0 (default): stream kernels where supported; 1: the generic per-tile kernels everywhere (also GSB200_BLEND=tile).
+ * Returns the previous mode.  Process-wide; meant for A/B timing and parity tests. */
+int gsb200_set_blend_mode(int mode);
 int gsb200_rasterize_fwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
                          const float *conics, const float *colors, const float *opacities,
                          const float *backgrounds, const uint8_t *masks, uint32_t image_width,
                          uint32_t image_height, uint32_t tile_size, uint32_t tile_width,
                          uint32_t tile_height, const int32_t *tile_offsets,
                          const int32_t *flatten_ids, float *render_colors, float *render_alphas,
-                         int32_t *last_ids, int32_t *tile_order, gsb200_stream_t stream);
+                         int32_t *last_ids, int32_t *tile_order, float *blend_stream,
+                         int32_t *tile_counts, gsb200_stream_t stream);
 
 /* replaces _C.rasterize_to_pixels_bwd (bindings.h:186-215, rasterize_to_pixels_bwd.cu:17-277).
  * Gradient outputs v_means2d [M,2], v_conics [M,3], v_colors [M,D], v_opacities [M] and, if not
@@ -238,7 +247,8 @@ int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, c
                          uint32_t tile_height, const int32_t *tile_offsets,
                          const int32_t *flatten_ids, const float *render_alphas,
                          const int32_t *last_ids, const float *v_render_colors,
-                         const float *v_render_alphas, const int32_t *tile_order, float *grad_scratch,
+                         const float *v_render_alphas, const int32_t *tile_order,
+                         const float *blend_stream, const int32_t *tile_counts, float *grad_scratch,
                          float *v_means2d_abs,
                          float *v_means2d, float *v_conics, float *v_colors, float *v_opacities,
                          gsb200_stream_t stream);

@@ -241,3 +241,37 @@ def test_every_kernel_source_is_in_the_build_list():
 
     on_disk = sorted(f for f in os.listdir(_build.CSRC) if f.endswith(".cu"))
     assert on_disk == sorted(_build.SOURCES), (on_disk, _build.SOURCES)
+
+
+def test_policy_tables_and_checkpoint_keys_match_the_reference_fixture():
+    """tests/golden/ref_policy.json was written by oracle/make_golden_policy.py from the REFERENCE's own
+    compression_simulation/simulation.py (run on the CPU with a stub _gridencoder): policy tables of both classes, the
+    negative-step gate (static only), entropy-model state_dict keys / shapes and optimizer group names."""
+    import json
+
+    from gscodec_studio_b200.compression_simulation import simulation as S
+
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_policy.json")))
+    sim = S.CompressionSimulation(entropy_model_enable=True, entropy_steps=dict(ref["static"]["entropy_steps"]), device="cpu")
+    stg = S.STGCompressionSimulation(quantization_sim_type="round", entropy_model_enable=True,
+                                     entropy_steps=dict(ref["stg"]["entropy_steps"]), device="cpu")
+    for ours, theirs in ((sim, ref["static"]), (stg, ref["stg"])):
+        assert ours.simulation_option == theirs["simulation_option"]
+        assert ours.q_bitwidth == theirs["q_bitwidth"]
+        assert {k: (None if v is None else [float(x) for x in v]) for k, v in ours.bds.items()} == \
+               {k: (None if v is None else [float(x) for x in v]) for k, v in theirs["bds"].items()}
+        for k, v in theirs["entropy_model_option"].items():  # the reference's dynamic table lists fewer keys
+            assert ours.entropy_model_option[k] == v, k
+        assert all(not ours.entropy_model_option[k] for k in ours.entropy_model_option if k not in theirs["entropy_model_option"])
+        for k, keys in theirs["state_dict"].items():
+            got = {n: list(v.shape) for n, v in ours.entropy_models[k].state_dict().items()}
+            assert got == keys, k  # same keys, same shapes: either side's checkpoint loads strictly into the other
+    assert sim.entropy_min_step == ref["static"]["entropy_min_step"]
+    for k, names in ref["static"]["optimizer_param_names"].items():
+        assert [g["name"] for g in sim.entropy_model_optimizers[k].param_groups] == names
+    # the dynamic policy has no negative-step gate: its rate term is active from step 0 (reference :575-583)
+    stg2 = S.STGCompressionSimulation(quantization_sim_type="round", entropy_model_enable=True,
+                                      entropy_steps={k: -1 for k in ref["stg"]["entropy_steps"]}, device="cpu")
+    assert stg2.entropy_model_option["scales"] and stg2.entropy_model_option["colors"]
+    with pytest.raises(KeyError):
+        S.CompressionSimulation(entropy_model_enable=True, entropy_steps={"scales": 1}, device="cpu")

@@ -619,7 +619,7 @@ def test_kernels_match_reference_cuda_golden():
     th, tw = g["isect_offsets"].shape[1:]
     radii, m2d, dep, con, comp = gs.fully_fused_projection(g["means"], None, g["quats"], g["scales"], g["viewmats"], g["Ks"],
                                                            W, H, near_plane=0.01, far_plane=100.0, calc_compensations=True)
-    assert (radii != g["radii"]).float().mean() < 1e-4
+    assert torch.equal(radii, g["radii"])
     valid = (radii > 0) & (g["radii"] > 0)
     assert torch.equal(dep[valid], g["depths"][valid])  # depth bits feed the sort keys
     assert rel_err(m2d[valid], g["means2d"][valid]) < 1e-5
@@ -846,3 +846,120 @@ def test_sharded_view_colors_and_row_reduce_single_process(world, deg):
     gathered = torch.empty(world * n_block, 11, device=DEV)
     call("gsb200_shard_gather_rows", world, n_block * 11, table(geo_blocks)[1], ptr(gathered), stream_ptr(DEV))
     assert torch.equal(gathered, torch.cat(geo_blocks, 0))
+
+
+# ------------------------------------------------------------------------------------- reference simulation.py fixture
+def _load_ref_model(model, z, prefix):
+    sd = {n: torch.from_numpy(z[prefix + n]).to(DEV) for n in model.state_dict()}
+    model.load_state_dict(sd, strict=True)  # the reference's own checkpoint keys (matrix / bias / factor / ...bound included)
+
+
+@pytest.mark.parametrize("N", [777, 1024])
+def test_static_simulation_matches_reference_simulation_py(N):
+    """CompressionSimulation against tests/golden/ref_policy.npz = the REFERENCE's simulation.py run on the CPU
+    (oracle/make_golden_policy.py) with the noise it drew recorded: simulated values BIT-exact, rate estimates to 1e-4,
+    the entropy gates at steps 5 / 15 / 25 (gates at 10 and 20), weights loaded strictly from the reference's state_dict."""
+    import json
+
+    from gscodec_studio_b200.compression_simulation import CompressionSimulation
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_policy.npz"))
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_policy.json")))["static"]
+    sim = CompressionSimulation(entropy_model_enable=True, entropy_steps=dict(meta["entropy_steps"]), device=DEV)
+    for k, m in sim.entropy_models.items():
+        if m is not None:
+            _load_ref_model(m, z, f"static/model/{k}/")
+    names = ("means", "scales", "quats", "opacities", "sh0", "shN")
+    for step in (5, 15, 25):
+        splats = {k: torch.from_numpy(z[f"static/{N}/in/{k}"]).to(DEV) for k in names}
+        noise = {k: torch.from_numpy(z[f"static/{N}/{step}/noise/{k}"]).to(DEV) for k in ("scales", "quats", "opacities", "sh0")}
+        new, bits = sim.simulate_compression(splats, step, noise=noise)
+        for k in names:
+            assert torch.equal(new[k].cpu(), torch.from_numpy(z[f"static/{N}/{step}/out/{k}"])), (step, k)
+        present = sorted(k for k, b in bits.items() if b is not None)
+        assert present == meta["bits_present"][f"{N}/{step}"], (step, present)
+        for k in present:
+            ref_bits = torch.from_numpy(z[f"static/{N}/{step}/bits/{k}"])
+            assert bits[k].shape == ref_bits.shape
+            assert rel_err(bits[k], ref_bits) < 1e-4, (step, k)
+
+
+def test_dynamic_simulation_matches_reference_simulation_py():
+    """STGCompressionSimulation (round mode) against the reference's own class: values bit-exact, the PARAMETERS clamped
+    in place exactly as the reference leaves them (ops.py:63), rates to 1e-4."""
+    import json
+
+    from gscodec_studio_b200.compression_simulation import STGCompressionSimulation
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ref_policy.npz"))
+    meta = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_policy.json")))["stg"]
+    sim = STGCompressionSimulation(quantization_sim_type="round", entropy_model_enable=True,
+                                   entropy_steps=dict(meta["entropy_steps"]), device=DEV)
+    for k, m in sim.entropy_models.items():
+        if m is not None:
+            _load_ref_model(m, z, f"stg/model/{k}/")
+    names = [k[len("stg/in/"):] for k in z.files if k.startswith("stg/in/")]
+    for step in (5, 15):
+        splats = {k: torch.from_numpy(z[f"stg/in/{k}"]).to(DEV) for k in names}
+        new, bits = sim.simulate_compression(splats, step)
+        for k in names:
+            assert torch.equal(new[k].cpu(), torch.from_numpy(z[f"stg/{step}/out/{k}"])), (step, k)
+            assert torch.equal(splats[k].cpu(), torch.from_numpy(z[f"stg/{step}/param_after/{k}"])), (step, k)
+        present = sorted(k for k, b in bits.items() if b is not None)
+        assert present == meta["bits_present"][str(step)], (step, present)
+        for k in present:
+            assert rel_err(bits[k], torch.from_numpy(z[f"stg/{step}/bits/{k}"])) < 1e-4, (step, k)
+
+
+# ------------------------------------------------------------------------------------- headline size, from RAW parameters
+def assert_elementwise_close(a, b, name, rtol=1e-3, atol_scale=1e-3, flip_frac=1e-4):
+    """Per-element check next to the max-normalised one (the reference's own tests use rtol + atol per element,
+    tests/test_basic.py:549-576): |a - b| <= rtol |b| + atol with atol = atol_scale * median |b| over the non-zero
+    reference entries, for all but a vanishing fraction of entries (owners of a flipped borderline pair)."""
+    a, b = a.detach().double().flatten(), b.detach().double().flatten()
+    nz = b.abs() > 0
+    atol = atol_scale * (b[nz].abs().median().item() if nz.any() else 0.0)
+    bad = ((a - b).abs() > rtol * b.abs() + atol)
+    frac = bad.double().mean().item()
+    assert frac <= flip_frac, f"{name}: {frac:.2e} of the entries fail rtol={rtol} atol={atol:.2e}"
+
+
+def test_headline_m2_step_from_raw_parameters_matches_reference_cuda():
+    """One M2 step (1 006 065 Gaussians, 1920x1080, SH degree 3, 8-bit noise fake-quant with injected noise) from the RAW
+    trainer parameters, ours against the unmodified reference CUDA kernels driven through the reference's op sequence
+    (oracle/ref_pipeline.py): radii / isect_ids / flatten_ids / isect_offsets / tiles_per_gauss EQUAL, RGB and alpha
+    <= 1e-4, gradients of means / scales / quats / opacities / sh0 / shN <= 1e-3 (max-normalised and per element)."""
+    from oracle import ref_pipeline as RP
+
+    ref = RP.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/gsplat_ref_cuda.so not built")
+    import bench
+    from gscodec_studio_b200.compression_simulation import CompressionSimulation
+
+    raw_cpu, viewmat, K, _, n_total = bench.build_workload(0, 1, 3)
+    assert n_total == 1006065
+    viewmat, K = viewmat.to(DEV), K.to(DEV)
+    W, H = 1920, 1080
+    g = torch.Generator().manual_seed(123)
+    noise = {k: (torch.rand(raw_cpu[k].shape, generator=g) - 0.5).to(DEV) for k in RP.BOUNDS}
+    v_rc = torch.randn(1, H, W, 3, generator=g).to(DEV)
+    ours = {k: v.to(DEV).requires_grad_(True) for k, v in raw_cpu.items()}
+    theirs = {k: v.to(DEV).requires_grad_(True) for k, v in raw_cpu.items()}
+
+    sim = CompressionSimulation(device=DEV)
+    new, _ = sim.simulate_compression(ours, 100, noise=noise, fuse_activations=True)
+    rc, ra, meta = gs.rasterization(new["means"], new["quats"], new["scales_act"], new["opacities_act"], (new["sh0"], new["shN"]),
+                                    viewmat, K, W, H, sh_degree=3, packed=False, near_plane=0.01, far_plane=100.0, radius_clip=3.0)
+    (rc * v_rc).sum().backward()
+    out = RP.RefStep(ref, W, H).run(theirs, viewmat, K, v_rc, noise)
+
+    assert torch.equal(meta["radii"], out["radii"])
+    assert torch.equal(meta["tiles_per_gauss"], out["tiles_per_gauss"])
+    assert torch.equal(meta["isect_ids"], out["isect_ids"]) and torch.equal(meta["flatten_ids"], out["flatten_ids"])
+    assert torch.equal(meta["isect_offsets"], out["isect_offsets"])
+    assert meta["isect_ids"].numel() > 3_500_000
+    assert rel_err(rc, out["render_colors"]) < 1e-4 and rel_err(ra, out["render_alphas"]) < 1e-4
+    for k in ("means", "scales", "quats", "opacities", "sh0", "shN"):
+        assert_grad_close(ours[k].grad, theirs[k].grad, k)
+        assert_elementwise_close(ours[k].grad, theirs[k].grad, k)

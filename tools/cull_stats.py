@@ -61,3 +61,17 @@ for wy in range(4):
 n=len(mx)
 print("warp-rect survivors: %.2f M of %.2f M candidates (%.3f); bbox-pass %.2f M (%.3f)"%(tot/1e6,8*n/1e6,tot/(8*n),tot_bb/1e6,tot_bb/(8*n)))
 print("warp-rect survivors per tile-hit isect: %.2f"%(tot/hit_tile.sum()))
+# ---- round 2: survivors per rectangle size (sizes the pixels-per-thread trade-off of the stream blend) ----------------
+for (rw, rh) in ((4, 4), (8, 4), (8, 8), (16, 8), (16, 16)):
+    tot = 0
+    for wy in range(16 // rh):
+        for wxx in range(16 // rw):
+            X0 = tx * 16 + wxx * rw + 0.5; X1 = X0 + rw - 1; Y0 = ty * 16 + wy * rh + 0.5; Y1 = Y0 + rh - 1
+            ok = (X0 < W) & (Y0 < H)
+            q = minq(X0, np.minimum(X1, W - 0.5), Y0, np.minimum(Y1, H - 0.5)); tot += ((q <= qmax) & (o * 255 >= 1) & ok).sum()
+    print("rect %2dx%-2d: %.2f M (rect, Gaussian) survivors = %.1f M pixel slots" % (rw, rh, tot / 1e6, tot * rw * rh / 1e6))
+# pixels that can pass alpha >= 1/255: area of the ellipse d^T A d <= qmax (unclipped)
+gv = vis; av = conics[gv, 0].astype(np.float64); bv = conics[gv, 1].astype(np.float64); cv = conics[gv, 2].astype(np.float64)
+qv = 2 * np.log(np.maximum(255 * op[gv].astype(np.float64), 1e-30)); dv = av * cv - bv * bv
+area = np.where((qv > 0) & (dv > 0), math.pi * np.maximum(qv, 0) / np.sqrt(np.maximum(dv, 1e-30)), 0)
+print("sum of 1/255-ellipse areas: %.1f M pixel pairs (upper bound of contributing pairs before saturation)" % (area.sum() / 1e6))

@@ -68,9 +68,16 @@ def main():
 
     order = None if os.environ.get("NO_ORDER") == "1" else torch.empty(tw * th, dtype=torch.int32, device=DEV)
 
+    from gscodec_studio_b200._cabi import load_library
+
+    rec = int(load_library().gsb200_blend_stream_record(3, 16))
+    bstream = torch.empty(max(I, 1) * rec, device=DEV) if rec else None
+    tcnt = torch.empty(tw * th, dtype=torch.int32, device=DEV) if rec else None
+    print("blend record floats:", rec)
+
     def fwd():
         call("gsb200_rasterize_fwd", 1, N, I, 3, ptr(m2d), ptr(con), ptr(cols), ptr(ops), ptr(None), ptr(None), Wd, Hd,
-             16, tw, th, ptr(offs), ptr(fl), ptr(rc), ptr(ra), ptr(last), ptr(order), stream_ptr(DEV))
+             16, tw, th, ptr(offs), ptr(fl), ptr(rc), ptr(ra), ptr(last), ptr(order), ptr(bstream), ptr(tcnt), stream_ptr(DEV))
 
     res["blend_fwd"] = timeit(fwd)
     v_c = torch.ones(1, Hd, Wd, 3, device=DEV)
@@ -80,7 +87,8 @@ def main():
 
     def bwd():
         call("gsb200_rasterize_bwd", 1, N, I, 3, ptr(m2d), ptr(con), ptr(cols), ptr(ops), ptr(None), ptr(None), Wd, Hd,
-             16, tw, th, ptr(offs), ptr(fl), ptr(ra), ptr(last), ptr(v_c), ptr(v_a), ptr(order), ptr(scratch), ptr(None), ptr(vm),
+             16, tw, th, ptr(offs), ptr(fl), ptr(ra), ptr(last), ptr(v_c), ptr(v_a), ptr(order), ptr(bstream), ptr(tcnt),
+             ptr(scratch), ptr(None), ptr(vm),
              ptr(vc), ptr(vcol), ptr(vo), stream_ptr(DEV))
 
     res["blend_bwd"] = timeit(bwd)
