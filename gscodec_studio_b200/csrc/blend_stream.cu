@@ -17,6 +17,8 @@
 //     back-to-front with cp.async.bulk (TMA, mbarrier complete_tx) -- no gather, no re-culling; the per-warp
 //     reductions and the packed-record REDs are the ones of blend.cu, amortised over 64 pixels per warp
 //     instead of 32.
+#include <stdlib.h>
+
 #include "blend.cuh"
 
 namespace gsb200 {
@@ -26,6 +28,12 @@ constexpr int kStageRecs = 64;  // records per pipeline stage
 #define GSB_STREAM_STAGES 4
 #endif
 constexpr int kStages = GSB_STREAM_STAGES;
+#ifndef GSB_PRODUCER_SLEEP_NS
+#define GSB_PRODUCER_SLEEP_NS 256  // ring full: the consumers need ~10^3 cycles per stage
+#endif
+#ifndef GSB_CONSUMER_SLEEP_NS
+#define GSB_CONSUMER_SLEEP_NS 32
+#endif
 constexpr int kRecBytes = 48;
 constexpr uint32_t kEndFlag = 0x100;
 constexpr float kNegLog2e = -1.4426950408889634f;
@@ -40,15 +48,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// A waiting warp must not burn issue slots of the warps it waits for (the first profile had 19 % of the forward's
+// instructions in this loop): back off with nanosleep between probes.
+template <int SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    do {
+    while (true) {
         asm volatile(
             "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
             : "=r"(ok)
             : "r"(bar), "r"(parity)
             : "memory");
-    } while (!ok);
+        if (ok) break;
+        if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    }
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -74,6 +87,53 @@ __device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }
 template <bool ASSIGN>
 __device__ __forceinline__ void acc(float &dst, float v) {
     if (ASSIGN) dst = v; else dst += v;
+}
+
+
+// Which of the four 8x8 blocks of a tile does the ellipse { d : d^T A d <= qmax } around (mx, my) meet?  Same exact,
+// conservative test as ellipse_hits_rect (blend.cuh) -- the minimum of the convex form over a block's pixel-centre
+// rectangle is 0 if the centre is inside, else it lies on one of the four edges -- evaluated for the 2 x 2 blocks at
+// once: the unconstrained minimiser along each of the 4 vertical / 4 horizontal grid lines is shared by the two blocks
+// the line bounds.  xs / ys: pixel-centre coordinates of the block edges {lo0, hi0, lo1, hi1}; an interval that lies
+// outside the image has hi < lo (block never hit).  ~150 instructions instead of 4 x 100.
+__device__ __forceinline__ uint32_t blocks_hit_mask(float mx, float my, float a, float b, float c, float qmax, const float *xs,
+                                                    const float *ys) {
+    if (!(qmax >= 0.f)) return 0u;
+    uint32_t valid = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (xs[2 * (k & 1) + 1] >= xs[2 * (k & 1)] && ys[2 * (k >> 1) + 1] >= ys[2 * (k >> 1)]) valid |= 1u << k;
+    if (qmax == FLT_MAX) return valid;
+    float lx[4], ly[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { lx[k] = xs[k] - mx; ly[k] = ys[k] - my; }
+    const float nbc = -b * __frcp_rn(c), nba = -b * __frcp_rn(a), b2 = 2.f * b;
+    // qv[k][j]: minimum along the vertical line x = xs[k] over y-interval j;  qh[k][i]: horizontal line y = ys[k], x-interval i
+    float qv[4][2], qh[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float ystar = nbc * lx[k], a2 = a * lx[k] * lx[k], bl = b2 * lx[k];
+        const float xstar = nba * ly[k], c2 = c * ly[k] * ly[k], bt = b2 * ly[k];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float dy = fminf(fmaxf(ystar, ly[2 * j]), ly[2 * j + 1]);
+            qv[k][j] = (c * dy + bl) * dy + a2;
+            const float dx = fminf(fmaxf(xstar, lx[2 * j]), lx[2 * j + 1]);
+            qh[k][j] = (a * dx + bt) * dx + c2;
+        }
+    }
+    // rounding margin, as in ellipse_hits_rect, with the extents of the whole tile
+    const float ex = fmaxf(fabsf(lx[0]), fabsf(lx[3])), ey = fmaxf(fabsf(ly[0]), fabsf(ly[3]));
+    const float bound = qmax + 1e-5f * (a * ex * ex + 2.f * fabsf(b) * ex * ey + c * ey * ey) + 1e-4f;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = k & 1, j = k >> 1;  // x-interval i, y-interval j
+        const bool inside = lx[2 * i] <= 0.f && lx[2 * i + 1] >= 0.f && ly[2 * j] <= 0.f && ly[2 * j + 1] >= 0.f;
+        const float q = fminf(fminf(qv[2 * i][j], qv[2 * i + 1][j]), fminf(qh[2 * j][i], qh[2 * j + 1][i]));
+        if (inside || q <= bound) mask |= 1u << k;
+    }
+    return mask & valid;
 }
 
 struct StreamShared {
@@ -154,17 +214,16 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
 
     if (warp == NCONS) {
         // ------------------------------------------------------------------ producer warp
-        // pixel-centre rectangles of the four 8x8 blocks, clipped to the image (empty: x1 < x0)
-        float bx0[4], bx1[4], by0[4], by1[4];
+        // pixel-centre coordinates of the block edges {lo0, hi0, lo1, hi1} along x and y, clipped to the image (an
+        // interval outside the image: hi < lo)
+        float xs[4], ys[4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int xl = (int)(tile_x * 16 + (b & 1) * 8), yl = (int)(tile_y * 16 + (b >> 1) * 8);
-            const int xh = min(xl + 7, (int)G.W - 1), yh = min(yl + 7, (int)G.H - 1);
-            const bool ok = xl <= xh && yl <= yh;
-            bx0[b] = (float)xl + 0.5f;
-            bx1[b] = ok ? (float)xh + 0.5f : -FLT_MAX;
-            by0[b] = (float)yl + 0.5f;
-            by1[b] = ok ? (float)yh + 0.5f : -FLT_MAX;
+        for (int i = 0; i < 2; ++i) {
+            const int xl = (int)(tile_x * 16 + i * 8), yl = (int)(tile_y * 16 + i * 8);
+            xs[2 * i] = (float)xl + 0.5f;
+            xs[2 * i + 1] = (float)min(xl + 7, (int)G.W - 1) + 0.5f;
+            ys[2 * i] = (float)yl + 0.5f;
+            ys[2 * i + 1] = (float)min(yl + 7, (int)G.H - 1) + 0.5f;
         }
         struct Cand {
             float2 xy;
@@ -196,7 +255,7 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
         uint32_t acquired = kStages;   // stages [0, acquired) may be written (the first ring round is free)
         auto acquire_to = [&](uint32_t stage) {
             while (acquired <= stage) {
-                mbar_wait(a_empty + 8 * (acquired % kStages), ((acquired / kStages) - 1) & 1);
+                mbar_wait<GSB_PRODUCER_SLEEP_NS>(a_empty + 8 * (acquired % kStages), ((acquired / kStages) - 1) & 1);
                 ++acquired;
             }
         };
@@ -211,14 +270,8 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
             g_next = ids(base + 64);
 
             uint32_t hitmask = 0;
-            if (cur.g >= 0) {
-                const float qmax = cull_qmax(cur.a, cur.b, cur.c, cur.o);
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (bx1[b] >= bx0[b] &&
-                        ellipse_hits_rect(cur.xy.x, cur.xy.y, cur.a, cur.b, cur.c, qmax, bx0[b], bx1[b], by0[b], by1[b]))
-                        hitmask |= 1u << b;
-            }
+            if (cur.g >= 0)
+                hitmask = blocks_hit_mask(cur.xy.x, cur.xy.y, cur.a, cur.b, cur.c, cull_qmax(cur.a, cur.b, cur.c, cur.o), xs, ys);
             const unsigned ballot = __ballot_sync(0xffffffffu, hitmask != 0);
             const uint32_t cnt = __popc(ballot);
             if (cnt) {
@@ -287,7 +340,7 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
 
         for (uint32_t k = 0;; ++k) {
             const uint32_t slot = k % kStages;
-            mbar_wait(a_full + 8 * slot, (k / kStages) & 1);
+            mbar_wait<GSB_CONSUMER_SLEEP_NS>(a_full + 8 * slot, (k / kStages) & 1);
             const int cf = *reinterpret_cast<volatile int *>(&S.count[slot]);
             const uint32_t nrec = (uint32_t)cf & 0xffu;
             if (!warp_done) {
@@ -385,8 +438,10 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
 }
 
 // --------------------------------------------------------------------------------------------- backward
+// No producer warp here: staging is one bulk copy per stage, so the LAST consumer warp to release a ring slot refills it
+// (a shared-memory counter per slot plays the "empty" barrier) and every warp of the CTA does blend work.
 template <int CDIM, int NP, bool ABS>
-__global__ void __launch_bounds__((4 / NP + 1) * 32, NP == 1 ? 5 : 6)
+__global__ void __launch_bounds__((4 / NP) * 32, NP == 1 ? 7 : 8)
 blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
                         const int32_t *__restrict__ tile_offsets, const float *__restrict__ render_alphas,
                         const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
@@ -411,33 +466,25 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
     const float *bg = backgrounds ? backgrounds + (size_t)cam * CDIM : nullptr;
 
     const uint32_t a_rec = (uint32_t)__cvta_generic_to_shared(S.rec);
-    const uint32_t a_full = (uint32_t)__cvta_generic_to_shared(S.full), a_empty = (uint32_t)__cvta_generic_to_shared(S.empty);
+    const uint32_t a_full = (uint32_t)__cvta_generic_to_shared(S.full);
+    const char *src = reinterpret_cast<const char *>(stream) + (size_t)range_start * kRecBytes;
+    // stage j of the walk (back to front) = records [st * 64, st * 64 + nrec) of the tile's stream, st = nst - 1 - j
+    auto issue = [&](uint32_t j) {
+        const uint32_t st = nst - 1 - j, slot = j % kStages;
+        const uint32_t bytes = min((uint32_t)kStageRecs, (uint32_t)cnt - st * kStageRecs) * kRecBytes;
+        mbar_arrive_expect_tx(a_full + 8 * slot, bytes);
+        bulk_g2s(a_rec + slot * (kStageRecs * kRecBytes), src + (size_t)st * kStageRecs * kRecBytes, bytes, a_full + 8 * slot);
+    };
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(a_full + 8 * s, 1);       // the issuing thread's arrive.expect_tx (+ the copy's bytes)
-            mbar_init(a_empty + 8 * s, NCONS);  // lane 0 of every consumer warp
+            mbar_init(a_full + 8 * s, 1);  // the issuing thread's arrive.expect_tx (+ the copy's bytes)
+            S.count[s] = 0;                // warps that have released the slot
         }
         fence_barrier_init();
+        for (uint32_t j = 0; j < min(nst, (uint32_t)kStages); ++j) issue(j);
     }
     __syncthreads();
-
-    if (warp == NCONS) {
-        // ------------------------------------------------------------------ producer: one thread, bulk copies
-        if (lane == 0) {
-            const char *src = reinterpret_cast<const char *>(stream) + (size_t)range_start * kRecBytes;
-            for (uint32_t j = 0; j < nst; ++j) {  // stages back to front
-                const uint32_t st = nst - 1 - j, slot = j % kStages;
-                if (j >= kStages) mbar_wait(a_empty + 8 * slot, ((j / kStages) - 1) & 1);
-                const uint32_t nrec = min((uint32_t)kStageRecs, (uint32_t)cnt - st * kStageRecs);
-                const uint32_t bytes = nrec * kRecBytes;
-                mbar_arrive_expect_tx(a_full + 8 * slot, bytes);
-                bulk_g2s(a_rec + slot * (kStageRecs * kRecBytes), src + (size_t)st * kStageRecs * kRecBytes, bytes,
-                         a_full + 8 * slot);
-            }
-        }
-        return;
-    }
     // ---------------------------------------------------------------------- consumer warps
     float px[NP];
     float2 npy[NP], T[NP], Tfin[NP], v_a[NP], bg_dot[NP];
@@ -474,7 +521,7 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
 
     for (uint32_t j = 0; j < nst; ++j) {
         const uint32_t st = nst - 1 - j, slot = j % kStages;
-        mbar_wait(a_full + 8 * slot, (j / kStages) & 1);
+        mbar_wait<GSB_CONSUMER_SLEEP_NS>(a_full + 8 * slot, (j / kStages) & 1);
         const int32_t nrec = (int32_t)min((uint32_t)kStageRecs, (uint32_t)cnt - st * kStageRecs);
         const uint32_t a_stage = a_rec + slot * (kStageRecs * kRecBytes);
         if (warp_bin >= 0) {
@@ -585,16 +632,31 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                 }
             }
         }
+        // release the slot; the last warp to do so refills it with the stage kStages further along the walk.  The warp's
+        // shared-memory reads of the slot have been consumed (their values are in registers) before this point.
         __syncwarp();
-        if (lane == 0) mbar_arrive(a_empty + 8 * slot);
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&S.count[slot], 1) == (int)NCONS - 1) {
+                S.count[slot] = 0;
+                if (j + kStages < nst) issue(j + kStages);
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ host
+// pixel pairs per consumer thread: 1 (four 8x8 warps per tile) or 2 (two 16x8 warps); GSB200_STREAM_NP overrides
 #ifndef GSB_STREAM_NP
 #define GSB_STREAM_NP 1
 #endif
-constexpr int kNP = GSB_STREAM_NP;
+static int stream_np() {
+    static const int np = [] {
+        const char *v = getenv("GSB200_STREAM_NP");
+        return (v != nullptr && (v[0] == '1' || v[0] == '2')) ? v[0] - '0' : GSB_STREAM_NP;
+    }();
+    return np;
+}
 
 bool blend_stream_supported(uint32_t tile_size, uint32_t cdim, int64_t n_isects) {
     return tile_size == 16 && cdim >= 1 && cdim <= 4 && n_isects < (int64_t(1) << 28);
@@ -608,9 +670,14 @@ static int fwd_t(const BlendGeom &G, const float *means2d, const float *conics, 
     const uint32_t T = G.C * G.tw * G.th;
     if (tile_order != nullptr)
         if (int e = launch_tile_order(T, G.n_isects, tile_offsets, tile_order, s)) return e;
-    blend_stream_fwd_kernel<CDIM, kNP><<<T, (4 / kNP + 1) * 32, 0, s>>>(
-        G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
-        render_colors, render_alphas, last_ids, tile_order, reinterpret_cast<float4 *>(blend_stream), tile_counts);
+    if (stream_np() == 2)
+        blend_stream_fwd_kernel<CDIM, 2><<<T, 3 * 32, 0, s>>>(
+            G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
+            render_colors, render_alphas, last_ids, tile_order, reinterpret_cast<float4 *>(blend_stream), tile_counts);
+    else
+        blend_stream_fwd_kernel<CDIM, 1><<<T, 5 * 32, 0, s>>>(
+            G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
+            render_colors, render_alphas, last_ids, tile_order, reinterpret_cast<float4 *>(blend_stream), tile_counts);
     return check_launch("blend_stream_fwd");
 }
 
@@ -636,14 +703,16 @@ static int bwd_t(const BlendGeom &G, const float *backgrounds, const uint8_t *ma
                  bool absgrad, cudaStream_t s) {
     const uint32_t T = G.C * G.tw * G.th;
     const float4 *st = reinterpret_cast<const float4 *>(blend_stream);
-    if (absgrad)
-        blend_stream_bwd_kernel<CDIM, kNP, true><<<T, (4 / kNP + 1) * 32, 0, s>>>(
-            G, backgrounds, masks, tile_offsets, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, st,
-            tile_counts, grad_scratch);
-    else
-        blend_stream_bwd_kernel<CDIM, kNP, false><<<T, (4 / kNP + 1) * 32, 0, s>>>(
-            G, backgrounds, masks, tile_offsets, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, st,
-            tile_counts, grad_scratch);
+#define GSB_BWD_LAUNCH(NPV, ABSV)                                                                                     \
+    blend_stream_bwd_kernel<CDIM, NPV, ABSV><<<T, (4 / NPV) * 32, 0, s>>>(G, backgrounds, masks, tile_offsets, render_alphas, \
+                                                                         last_ids, v_render_colors, v_render_alphas,     \
+                                                                         tile_order, st, tile_counts, grad_scratch)
+    if (stream_np() == 2) {
+        if (absgrad) GSB_BWD_LAUNCH(2, true); else GSB_BWD_LAUNCH(2, false);
+    } else {
+        if (absgrad) GSB_BWD_LAUNCH(1, true); else GSB_BWD_LAUNCH(1, false);
+    }
+#undef GSB_BWD_LAUNCH
     return check_launch("blend_stream_bwd");
 }
 

@@ -118,7 +118,10 @@ class RefStep:
                    isect_ids=isect_ids, flatten_ids=flatten_ids, isect_offsets=offsets, render_colors=rc, render_alphas=ra,
                    last_ids=last)
         if backward:
-            v_rc = torch.ones_like(rc) if v_render_colors is None else v_render_colors.contiguous()
+            if callable(v_render_colors):  # gradient of the caller's loss as a function of the rendered image
+                v_rc = self._timed("loss (torch)", lambda: v_render_colors(rc).contiguous(), timed)
+            else:
+                v_rc = torch.ones_like(rc) if v_render_colors is None else v_render_colors.contiguous()
             v_ra = torch.zeros_like(ra)
             _, v_m2d, v_con, v_col, v_op = self._timed("rasterize_to_pixels_bwd", lambda: ref.rasterize_to_pixels_bwd(
                 means2d, conics, colors, opac_c, None, None, W, H, ts, offsets, flatten_ids, ra, last, v_rc, v_ra, False), timed)
