@@ -44,8 +44,10 @@ SIGNATURES = {
     "gsb200_sh_view_fwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _P, _P, _P, _P],
     "gsb200_sh_view_bwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_shard_reduce_rows": [_U, _U, _U, _U, _P, _P, _P, _P],
+    "gsb200_shard_reduce_rows_split": [_U, _U, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_shard_gather_rows": [_U, c_uint64, _P, _P, _P],
-    "gsb200_isect_prepare": [_U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
+    "gsb200_isect_plan": [_U, _U, _U, _U, _P, _P],
+    "gsb200_isect_prepare": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_fill": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _L, _P, _P, _P, _P, _P, _P],
     "gsb200_isect_emit_unsorted": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_offset_encode": [_L, _P, _U, _U, _U, _P, _P],

@@ -87,8 +87,15 @@ class PeerWorkspace:
         both blocks).  Returns the version number of what is now published."""
         if self.readers:
             self.barrier()
-        n = coeff_rows.shape[0]
-        self.coeff[:n].copy_(coeff_rows.reshape(n, self.row_floats))
+        if isinstance(coeff_rows, (tuple, list)):  # the trainers' (sh0 [n,1,3], shN [n,K-1,3]): written side by side,
+            sh0, shN = coeff_rows                  # the [n,K,3] concatenation never exists outside this buffer
+            n = sh0.shape[0]
+            rows = self.coeff[:n].view(n, self.row_floats // 3, 3)
+            rows[:, :1].copy_(sh0)
+            rows[:, 1:].copy_(shN)
+        else:
+            n = coeff_rows.shape[0]
+            self.coeff[:n].copy_(coeff_rows.reshape(n, self.row_floats))
         if geo_parts is not None:
             w = sum(t.shape[1] for t in geo_parts)
             block = self.geo[: n_block * w].view(n_block, w)
@@ -143,43 +150,55 @@ def available(device: torch.device, row_floats: int, n_block: int) -> bool:
 
 
 class _ShViewSharded(torch.autograd.Function):
+    """coeffs_local: this rank's [n_local,K,3] coefficients, or -- with coeffs_rest given -- the trainers' sh0 [n,1,3]
+    next to shN [n,K-1,3]; gradients come back in the same form."""
+
     @staticmethod
-    def forward(ctx, sh_degree, means, campos, coeffs_local, radii, n_block, published):
-        C, N, K = campos.shape[0], means.shape[0], coeffs_local.shape[1]
+    def forward(ctx, sh_degree, means, campos, coeffs_local, coeffs_rest, radii, n_block, published):
+        C, N = campos.shape[0], means.shape[0]
+        K = coeffs_local.shape[1] + (coeffs_rest.shape[1] if coeffs_rest is not None else 0)
         ws = workspace(means.device, K * 3, n_block)
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
         with torch.cuda.device(means.device):
             if published is None or published != ws.version:
-                ws.publish(coeffs_local)
+                ws.publish(coeffs_local if coeffs_rest is None else (coeffs_local, coeffs_rest))
             # local copy of every pulled row: the backward needs the same rows again (d colour / d direction)
             row_cache = torch.empty((N, K, 3), dtype=torch.float32, device=means.device) if any(ctx.needs_input_grad) else None
             call("gsb200_sh_view_fwd_sharded", C, N, K, sh_degree, ptr(means), ptr(campos), ws.coeff_table, ws.world, n_block,
                  ptr(radii), ptr(colors), ptr(row_cache), stream_ptr(means.device))
         ws.readers = True
         ctx.save_for_backward(means, campos, radii, row_cache)
-        ctx.sh_degree, ctx.n_block, ctx.local_shape = sh_degree, n_block, tuple(coeffs_local.shape)
+        ctx.sh_degree, ctx.n_block, ctx.K = sh_degree, n_block, K
+        ctx.n_local, ctx.split = coeffs_local.shape[0], coeffs_rest is not None
         return colors
 
     @staticmethod
     def backward(ctx, v_colors):
         means, campos, radii, row_cache = ctx.saved_tensors
-        n_local, K = ctx.local_shape[0], ctx.local_shape[1]
+        n_local, K = ctx.n_local, ctx.K
         C, N = campos.shape[0], means.shape[0]
         n_block = ctx.n_block
-        ws = workspace(means.device, K * 3, n_block)
+        dev = means.device
+        ws = workspace(dev, K * 3, n_block)
         v_colors = v_colors.contiguous()
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
-        v_coeffs = torch.empty(ctx.local_shape, dtype=torch.float32, device=means.device)
-        with torch.cuda.device(means.device):
+        with torch.cuda.device(dev):
             call("gsb200_sh_view_bwd_sharded", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ws.coeff_table, ws.world, n_block,
                  ws.rank, ptr(row_cache), ptr(radii), ptr(v_colors), ws.stage_table, ws.flag_table, ptr(v_means), ptr(v_campos),
-                 stream_ptr(means.device))
+                 stream_ptr(dev))
             ws.barrier()  # every rank's pushes have landed
-            call("gsb200_shard_reduce_rows", ws.world, n_block, n_local, K * 3, ptr(ws.staging), ptr(ws.flags),
-                 ptr(v_coeffs), stream_ptr(means.device))
+            if ctx.split:
+                v_first = torch.empty((n_local, 1, 3), dtype=torch.float32, device=dev)
+                v_rest = torch.empty((n_local, K - 1, 3), dtype=torch.float32, device=dev)
+                call("gsb200_shard_reduce_rows_split", ws.world, n_block, n_local, K * 3, 3, ptr(ws.staging), ptr(ws.flags),
+                     ptr(v_first), ptr(v_rest), stream_ptr(dev))
+            else:
+                v_first, v_rest = torch.empty((n_local, K, 3), dtype=torch.float32, device=dev), None
+                call("gsb200_shard_reduce_rows", ws.world, n_block, n_local, K * 3, ptr(ws.staging), ptr(ws.flags),
+                     ptr(v_first), stream_ptr(dev))
             ws.barrier()  # every owner is done reducing: staging and published rows may be overwritten
-        return None, v_means, v_campos, v_coeffs, None, None, None
+        return None, v_means, v_campos, v_first, v_rest, None, None, None
 
 
 class _GatherGeometry(torch.autograd.Function):
@@ -210,11 +229,14 @@ def publish_and_gather_geometry(geo_parts: Sequence[Tensor], pad_row: Tensor, co
     geometry.  Returns (gathered geometry [world * n_block, w] -- differentiable w.r.t. geo_parts --, version token to
     hand to view_colors_from_sh_sharded).  n_block must be a multiple of 4 and >= every rank's row count."""
     assert n_block % 4 == 0, n_block
-    dev = coeffs_local.device
-    ws = workspace(dev, coeffs_local.shape[1] * 3, n_block)
+    pair = isinstance(coeffs_local, (tuple, list))
+    dev = coeffs_local[0].device if pair else coeffs_local.device
+    K = coeffs_local[0].shape[1] + coeffs_local[1].shape[1] if pair else coeffs_local.shape[1]
+    ws = workspace(dev, K * 3, n_block)
     parts = [t.detach().float() for t in geo_parts]
+    rows = tuple(t.detach().float() for t in coeffs_local) if pair else coeffs_local.detach().float()
     with torch.cuda.device(dev):
-        version = ws.publish(coeffs_local.detach().float(), parts, pad_row, n_block)
+        version = ws.publish(rows, parts, pad_row, n_block)
     return _GatherGeometry.apply(ws, n_block, *[t.float() for t in geo_parts]), version
 
 
@@ -226,7 +248,8 @@ def view_colors_from_sh_sharded(sh_degree: int, means: Tensor, campos: Tensor, c
     N, C = means.shape[0], campos.shape[0]
     assert N == dist.get_world_size() * n_block, (N, n_block)
     assert radii.shape == (C, N), radii.shape
-    assert coeffs_local.dim() == 3 and coeffs_local.shape[2] == 3 and coeffs_local.shape[0] <= n_block, coeffs_local.shape
-    assert (sh_degree + 1) ** 2 <= coeffs_local.shape[1], coeffs_local.shape
-    return _ShViewSharded.apply(sh_degree, means.float().contiguous(), campos.float().contiguous(),
-                                coeffs_local.float().contiguous(), radii.contiguous(), n_block, published)
+    first, rest = coeffs_local if isinstance(coeffs_local, (tuple, list)) else (coeffs_local, None)
+    assert first.dim() == 3 and first.shape[2] == 3 and first.shape[0] <= n_block, first.shape
+    assert (sh_degree + 1) ** 2 <= first.shape[1] + (rest.shape[1] if rest is not None else 0)
+    return _ShViewSharded.apply(sh_degree, means.float().contiguous(), campos.float().contiguous(), first.float().contiguous(),
+                                None if rest is None else rest.float().contiguous(), radii.contiguous(), n_block, published)

@@ -21,53 +21,12 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
-#include "scan.cuh"
+#include "isect.cuh"
 
 namespace gsb200 {
 
 constexpr uint32_t kSortSmall = 2048;   // keys a 256-thread CTA sorts in 16 KB of static shared memory
 constexpr uint32_t kSortLarge = 12288;  // keys a 1024-thread CTA sorts in 96 KB of dynamic shared memory
-
-struct TileBox { uint32_t x0, y0, x1, y1; };
-
-// tile bbox of one Gaussian: min inclusive, max exclusive (isect_tiles.cu:59-71).  The float ->
-// uint32 conversion saturates (negative -> 0) exactly like the reference's cast.
-__device__ __forceinline__ TileBox tile_box(float mx, float my, float radius, float ts, uint32_t tw, uint32_t th) {
-    const float tr = radius / ts, tx = mx / ts, ty = my / ts;
-    TileBox b;
-    b.x0 = min(__float2uint_rz(floorf(tx - tr)), tw);
-    b.y0 = min(__float2uint_rz(floorf(ty - tr)), th);
-    b.x1 = min(__float2uint_rz(ceilf(tx + tr)), tw);
-    b.y1 = min(__float2uint_rz(ceilf(ty + tr)), th);
-    return b;
-}
-
-// Warp-cooperative walk over the tile boxes of the 32 Gaussians a warp owns: for every Gaussian with a
-// non-empty box the whole warp visits its tiles as a (rows x columns) patch -- lanes along x first, so
-// one warp-wide atomic touches adjacent counters (one or two 32-byte sectors) instead of 32 unrelated
-// ones, and large boxes (up to ~200 tiles) are spread over the lanes instead of serialising one thread.
-// f(tile_index_within_camera, lane_is_active) is called convergently by all lanes.
-template <typename F>
-__device__ __forceinline__ void for_each_tile_coop(bool has, const TileBox &b, uint32_t tw, F &&f) {
-    const uint32_t lane = threadIdx.x & 31;
-    unsigned todo = __ballot_sync(0xffffffffu, has);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t x0 = __shfl_sync(0xffffffffu, b.x0, src), y0 = __shfl_sync(0xffffffffu, b.y0, src);
-        const uint32_t nx = __shfl_sync(0xffffffffu, b.x1, src) - x0, ny = __shfl_sync(0xffffffffu, b.y1, src) - y0;
-        for (uint32_t xb = 0; xb < nx; xb += 32) {
-            const uint32_t w = min(32u, nx - xb);
-            const uint32_t sh = w <= 1 ? 0 : 32 - __clz(w - 1);  // log2 of the padded patch width
-            const uint32_t c = lane & ((1u << sh) - 1u), r = lane >> sh, rows = 32u >> sh;
-            for (uint32_t yb = 0; yb < ny; yb += rows) {
-                const bool on = c < w && yb + r < ny;
-                f(src, (y0 + yb + r) * tw + x0 + xb + c, on);
-            }
-        }
-    }
-}
 
 __global__ void __launch_bounds__(kThreads)
 isect_count_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids, const float *__restrict__ means2d,
@@ -494,7 +453,7 @@ offset_encode_kernel(int64_t n_isects, const int64_t *__restrict__ isect_ids, ui
     offsets[ct] = (int32_t)lo;
 }
 
-static int exclusive_scan(uint32_t n, int32_t *data, int32_t *copy, int32_t *block_scratch, cudaStream_t s) {
+int exclusive_scan(uint32_t n, int32_t *data, int32_t *copy, int32_t *block_scratch, cudaStream_t s) {
     // data[0..n) -> exclusive prefix in place (+ optional copy); total -> block_scratch[nb]
     const uint32_t nb = cdiv(n, kScanTile);
     scan_block_sums_kernel<<<nb, kThreads, 0, s>>>(n, data, block_scratch);
@@ -509,9 +468,39 @@ static int exclusive_scan(uint32_t n, int32_t *data, int32_t *copy, int32_t *blo
 
 using namespace gsb200;
 
+// GSB200_ISECT=ordered selects the depth pre-sort + ordered scatter path (csrc/isect_ordered.cu) where it applies.  It is
+// bit-exact (the whole GPU suite passes on it) but, as measured on B200 at the headline size, SLOWER than the per-tile sort
+// path (580 us vs 316 us: its per-piece walks are serial chains of shared-memory atomics, ~550 cycles per Gaussian), so
+// the per-tile sort path stays the default.  Kept because its first half (13x fewer, 32-bit keys to sort) is the right
+// starting point for a faster stage 2 -- see DESIGN.md section 6.
+static bool use_ordered(uint32_t C, uint32_t n_elems, uint32_t tw, uint32_t th) {
+    static const bool on = [] {
+        const char *v = getenv("GSB200_ISECT");
+        return v != nullptr && strcmp(v, "ordered") == 0;
+    }();
+    return on && n_elems > 0 && ordered_plan(C, n_elems, tw, th).ok;
+}
+
+static size_t tilesort_scratch_ints(uint32_t T) { return (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 2 + T / kScanTile + 3; }
+static size_t tilesort_total_index(uint32_t T) { return (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1; }
+
+extern "C" int gsb200_isect_plan(uint32_t C, uint32_t n_elems, uint32_t tile_width, uint32_t tile_height, int64_t *scratch_ints,
+                                 int64_t *total_index) {
+    const uint32_t T = max(C * tile_width * tile_height, 1u);
+    if (use_ordered(C, n_elems, tile_width, tile_height)) {
+        const OrderedPlan P = ordered_plan(C, n_elems, tile_width, tile_height);
+        *scratch_ints = (int64_t)P.scratch_ints;
+        *total_index = (int64_t)P.total_index;
+    } else {
+        *scratch_ints = (int64_t)tilesort_scratch_ints(T);
+        *total_index = (int64_t)tilesort_total_index(T);
+    }
+    return 0;
+}
+
 extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera, const int64_t *camera_ids,
-                                    const float *means2d, const int32_t *radii, uint32_t tile_size, uint32_t tile_width,
-                                    uint32_t tile_height, int32_t *tiles_per_gauss, int32_t *isect_offsets,
+                                    const float *means2d, const int32_t *radii, const float *depths, uint32_t tile_size,
+                                    uint32_t tile_width, uint32_t tile_height, int32_t *tiles_per_gauss, int32_t *isect_offsets,
                                     int32_t *tile_cursor, int64_t *n_isects_host, gsb200_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t T = C * tile_width * tile_height;
@@ -519,6 +508,20 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
     if (bit_width(tile_width * tile_height) + bit_width(C) > 32)
         return fail(2, "gsb200_isect_prepare: camera and tile ids do not fit 32 bits");
     if (T == 0) return 0;
+    if (use_ordered(C, n_elems, tile_width, tile_height)) {
+        if (depths == nullptr) return fail(2, "gsb200_isect_prepare: depths is required");
+        if (int e = ordered_prepare(C, n_elems, elems_per_camera, camera_ids, means2d, radii, depths, tile_size, tile_width,
+                                    tile_height, tiles_per_gauss, isect_offsets, tile_cursor, s))
+            return e;
+        if (n_isects_host != nullptr) {
+            int32_t total = 0;
+            const OrderedPlan P = ordered_plan(C, n_elems, tile_width, tile_height);
+            GSB_CUDA_OK(cudaMemcpyAsync(&total, tile_cursor + P.total_index, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            GSB_CUDA_OK(cudaStreamSynchronize(s));
+            *n_isects_host = total;
+        }
+        return 0;
+    }
     if (n_elems == 0) {
         GSB_CUDA_OK(cudaMemsetAsync(isect_offsets, 0, sizeof(int32_t) * T, s));
         GSB_CUDA_OK(cudaMemsetAsync(tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1, 0, sizeof(int32_t), s));
@@ -565,6 +568,9 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
     const uint32_t n_tiles = tile_width * tile_height, T = C * n_tiles;
     // n_isects < 0: capacity mode (see include/gsb200.h)
     const int64_t bound = n_isects < 0 ? -n_isects : n_isects;
+    if (use_ordered(C, n_elems, tile_width, tile_height))
+        return ordered_fill(C, n_elems, elems_per_camera, camera_ids, means2d, radii, tile_size, tile_width, tile_height, bound,
+                            isect_offsets, tile_cursor, isect_ids, flatten_ids, s);
     const int32_t *total_dev = n_isects < 0 ? tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1 : nullptr;
     isect_scatter_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
                                                                        camera_ids, means2d, radii, depths, (float)tile_size,

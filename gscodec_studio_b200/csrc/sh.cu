@@ -489,6 +489,31 @@ shard_reduce_rows_kernel(uint32_t world, uint32_t n_block, uint32_t n_rows, uint
     stg4(out + idx * 4, acc);
 }
 
+// Same reduction, written to TWO tensors: the first `split` floats of a row go to out0 [n_rows, split], the rest to
+// out1 [n_rows, row - split] (the trainers' sh0 / shN gradients; a (K-1)*12-byte row is not 16-byte aligned -> scalar stores)
+__global__ void __launch_bounds__(kThreads)
+shard_reduce_rows_split_kernel(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_vec4, uint32_t split,
+                               const float *__restrict__ staging, const int32_t *__restrict__ flags, float *__restrict__ out0,
+                               float *__restrict__ out1) {
+    const size_t idx = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= (size_t)n_rows * row_vec4) return;
+    const uint32_t i = idx / row_vec4, k = idx - (size_t)i * row_vec4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t p = 0; p < world; ++p)
+        if (__ldg(flags + (size_t)p * n_block + i) != 0) {
+            const float4 v = ldg4(staging + (((size_t)p * n_block + i) * row_vec4 + k) * 4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+    const uint32_t rest = row_vec4 * 4 - split;
+#pragma unroll
+    for (uint32_t u = 0; u < 4; ++u) {
+        const uint32_t f = k * 4 + u;
+        if (f < split) out0[(size_t)i * split + f] = vals[u];
+        else out1[(size_t)i * rest + (f - split)] = vals[u];
+    }
+}
+
 // All-gather by pull: every rank copies the published block of every peer (NVLink peer mappings) into its own
 // gathered array.  One launch, 64 bytes in flight per thread, no staging copies, no protocol overhead.
 struct BlockShards {
@@ -868,6 +893,22 @@ extern "C" int gsb200_shard_reduce_rows(uint32_t world, uint32_t n_block, uint32
     shard_reduce_rows_kernel<<<(uint32_t)((total + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         world, n_block, n_rows, row_vec4, staging, flags, out);
     return check_launch("shard_reduce_rows");
+}
+
+extern "C" int gsb200_shard_reduce_rows_split(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_floats, uint32_t split,
+                                              const float *staging, const int32_t *flags, float *out0, float *out1,
+                                              gsb200_stream_t stream) {
+    if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "gsb200_shard_reduce_rows_split: world must be in [1, %d]", kMaxShards);
+    if (n_rows > n_block) return fail(2, "gsb200_shard_reduce_rows_split: n_rows > n_block");
+    if (row_floats % 4 != 0 || split == 0 || split >= row_floats) return fail(2, "gsb200_shard_reduce_rows_split: bad row / split size");
+    if (n_rows == 0) return 0;
+    if (staging == nullptr || flags == nullptr || out0 == nullptr || out1 == nullptr || (reinterpret_cast<uintptr_t>(staging) & 15) != 0)
+        return fail(2, "gsb200_shard_reduce_rows_split: pointers must be non-null, staging 16-byte aligned");
+    const uint32_t row_vec4 = row_floats / 4;
+    const size_t total = (size_t)n_rows * row_vec4;
+    shard_reduce_rows_split_kernel<<<(uint32_t)((total + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        world, n_block, n_rows, row_vec4, split, staging, flags, out0, out1);
+    return check_launch("shard_reduce_rows_split");
 }
 
 extern "C" int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float *const *blocks, float *out,

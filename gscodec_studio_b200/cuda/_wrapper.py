@@ -28,7 +28,6 @@ from .._cabi import aligned, call, ptr, stream_ptr
 
 _CAMERA_MODELS = {"pinhole": 0, "ortho": 1, "fisheye": 2}
 _SUPPORTED_CHANNELS = (1, 2, 3, 4, 5, 8, 9, 16, 17, 32, 33)
-_ISECT_REPLICAS = 32  # GSB200_ISECT_REPLICAS in include/gsb200.h
 
 
 def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
@@ -606,13 +605,15 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
     T = C * tile_width * tile_height
     tiles_per_gauss = torch.empty(radii.shape, dtype=torch.int32, device=dev)
     isect_offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
-    tile_cursor = torch.empty((_ISECT_REPLICAS + 1) * max(T, 1) + 2 + max(T, 1) // 2048 + 3, dtype=torch.int32, device=dev)
-    total_index = (_ISECT_REPLICAS + 1) * max(T, 1) + 1
+    n_scratch, total_at = ctypes.c_int64(0), ctypes.c_int64(0)
+    call("gsb200_isect_plan", C, n_elems, tile_width, tile_height, ctypes.byref(n_scratch), ctypes.byref(total_at))
+    tile_cursor = torch.empty(int(n_scratch.value), dtype=torch.int32, device=dev)
+    total_index = int(total_at.value)
     key = (dev.index, C, n_elems, tile_width, tile_height, tile_size)
     capacity = _isect_capacity.get(key)
 
     def prepare(n_host_ref):
-        call("gsb200_isect_prepare", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), tile_size,
+        call("gsb200_isect_prepare", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths), tile_size,
              tile_width, tile_height, ptr(tiles_per_gauss), ptr(isect_offsets), ptr(tile_cursor), n_host_ref,
              stream_ptr(dev))
 

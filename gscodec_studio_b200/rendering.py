@@ -111,7 +111,7 @@ def rasterization(
     assert Ks.shape == (C, 3, 3), Ks.shape
     assert render_mode in ["RGB", "D", "ED", "RGB+D", "RGB+ED"], render_mode
 
-    sh_pair = None
+    sh_pair, sh_pair_dist = None, None
     if isinstance(colors, (tuple, list)):
         assert sh_degree is not None and len(colors) == 2, "colors=(sh0, shN) needs sh_degree"
         sh0, shN = colors
@@ -120,10 +120,12 @@ def rasterization(
         assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1], shN.shape
         if not distributed and not packed and shN.shape[1] <= SH_SPLIT_MAX_REST:
             sh_pair, colors = (sh0, shN), None
+        elif distributed and not packed:
+            sh_pair_dist, colors = (sh0, shN), None  # concatenated below only if the peer-memory path is unavailable
         else:
             colors = torch.cat([sh0, shN], dim=1)
 
-    if sh_pair is not None:
+    if sh_pair is not None or sh_pair_dist is not None:
         pass
     elif sh_degree is None:
         assert (colors.dim() == 2 and colors.shape[0] == N) or (
@@ -166,8 +168,15 @@ def rasterization(
         from . import _peer
 
         n_block = (max(counts) + 3) // 4 * 4
-        pull_colors = (sh_degree is not None and not packed and colors.dim() == 3
-                       and _peer.available(device, colors.shape[1] * 3, n_block))
+        if sh_pair_dist is not None:
+            k_all = 1 + sh_pair_dist[1].shape[1]
+            if _peer.available(device, k_all * 3, n_block):
+                colors = sh_pair_dist  # published side by side, gradients come back per parameter
+            else:
+                colors = torch.cat(sh_pair_dist, dim=1)
+        pull_colors = (sh_degree is not None and not packed and (isinstance(colors, tuple) or colors.dim() == 3)
+                       and _peer.available(device, (1 + colors[1].shape[1] if isinstance(colors, tuple) else colors.shape[1]) * 3,
+                                           n_block))
         colors_local = colors
         if pull_colors:
             gathered_geo, published = _peer.publish_and_gather_geometry(geo_parts, pad_row, colors_local, n_block)

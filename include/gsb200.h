@@ -160,6 +160,11 @@ int gsb200_sh_view_bwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degr
                                float *v_campos, gsb200_stream_t stream);
 int gsb200_shard_reduce_rows(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_floats,
                              const float *staging, const int32_t *flags, float *out, gsb200_stream_t stream);
+/* same reduction written to two tensors: floats [0, split) of a row to out0 [n_rows, split], the rest to out1
+ * [n_rows, row_floats - split] -- the gradients of the trainers' two SH parameters sh0 / shN (no [n,K,3] detour) */
+int gsb200_shard_reduce_rows_split(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t row_floats,
+                                   uint32_t split, const float *staging, const int32_t *flags, float *out0,
+                                   float *out1, gsb200_stream_t stream);
 /* All-gather by pull, used for the geometry attributes (needed for EVERY row, so nothing to skip): out
  * [world, block_floats] <- blocks[r][0 .. block_floats) for every rank r (HOST array of peer-mapped device
  * pointers).  Replaces the all-gather of all_gather_tensor_list (distributed.py:102-167) for that tensor. */
@@ -167,28 +172,32 @@ int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float 
                              gsb200_stream_t stream);
 
 /* ---------------------------------------------------------------- stage 2: tile intersection
- * replaces _C.isect_tiles + _C.isect_offset_encode (bindings.h:147-166, isect_tiles.cu:16-389) with
- * a per-tile design: count -> tile histogram -> scan -> bucket scatter -> per-tile sort on
- * (depth bits, flatten id).  Results are bit-identical to the reference's stable global radix sort.
+ * replaces _C.isect_tiles + _C.isect_offset_encode (bindings.h:147-166, isect_tiles.cu:16-389).  Results are
+ * bit-identical to the reference's stable global radix sort.  Two implementations behind the same calls:
+ * the per-tile sort path (csrc/isect.cu: tile histogram -> scatter -> one CTA sorts each tile; default) and the ordered
+ * path (csrc/isect_ordered.cu: depth pre-sort of the visible Gaussians + ordered scatter; GSB200_ISECT=ordered, validated
+ * bit-exact but currently slower).
  *
+ *   0. gsb200_isect_plan: size (int32 entries) of the scratch buffer `tile_cursor` the other two calls need for this
+ *      configuration, and the index inside it where the intersection count is left on the device.
  *   1. gsb200_isect_prepare: n_elems = C*N (dense) or nnz (packed; camera_ids i64 [nnz] required).
  *      Writes tiles_per_gauss i32 [n_elems] and isect_offsets i32 [C*tile_h*tile_w]; returns the
  *      number of intersections through *n_isects_host (synchronises `stream`, like the reference's
  *      .item() at isect_tiles.cu:200).  With n_isects_host == NULL the call does not synchronise; the
- *      count is then only available on the device, at tile_cursor[GSB200_ISECT_TOTAL_INDEX(T)].
- *      tile_cursor: scratch i32 [GSB200_ISECT_CURSOR_SIZE(T)], T = C*tile_h*tile_w.
- *   2. gsb200_isect_fill: writes isect_ids i64 [I] and flatten_ids i32 [I], sorted.  scratch: u64 [I].
+ *      count is then only available on the device, at tile_cursor[total_index].
+ *   2. gsb200_isect_fill: writes isect_ids i64 [I] and flatten_ids i32 [I], sorted.  scratch: u64 [I] (only the
+ *      per-tile sort path uses it).
  *      n_isects >= 0: exact count (buffers hold I entries).  n_isects < 0: "capacity mode" -- buffers hold
  *      -n_isects entries, the true count is read from the device; if it exceeds the capacity the outputs
  *      are incomplete and the caller must call again with larger buffers once it knows the count
  *      (lets the host size buffers speculatively and fetch the count without idling the GPU). */
-#define GSB200_ISECT_CURSOR_SIZE(T) ((GSB200_ISECT_REPLICAS + 1) * (size_t)(T) + 2 + ((size_t)(T) / 2048 + 3))
-#define GSB200_ISECT_TOTAL_INDEX(T) ((GSB200_ISECT_REPLICAS + 1) * (size_t)(T) + 1)
+int gsb200_isect_plan(uint32_t C, uint32_t n_elems, uint32_t tile_width, uint32_t tile_height,
+                      int64_t *scratch_ints, int64_t *total_index);
 int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
                          const int64_t *camera_ids, const float *means2d, const int32_t *radii,
-                         uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-                         int32_t *tiles_per_gauss, int32_t *isect_offsets, int32_t *tile_cursor,
-                         int64_t *n_isects_host, gsb200_stream_t stream);
+                         const float *depths, uint32_t tile_size, uint32_t tile_width,
+                         uint32_t tile_height, int32_t *tiles_per_gauss, int32_t *isect_offsets,
+                         int32_t *tile_cursor, int64_t *n_isects_host, gsb200_stream_t stream);
 int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
                       const int64_t *camera_ids, const float *means2d, const int32_t *radii,
                       const float *depths, uint32_t tile_size, uint32_t tile_width,
