@@ -32,6 +32,11 @@ SIGNATURES = {
     "gsb200_projection_fwd": [_U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _F, _F, _F, _I, _I, _P, _P, _P, _P, _P, _P],
     "gsb200_projection_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                               _P, _P],
+    "gsb200_projection_packed_count": [_U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _F, _F, _F, _I, _P, _P, _P],
+    "gsb200_projection_packed_fill": [_U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P,
+                                      _P, _P],
+    "gsb200_projection_packed_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                     _P, _P, _P],
     "gsb200_compact_count": [_U, _U, _P, _P, _P, _P],
     "gsb200_compact_fill": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_scatter_rows": [_U, _U, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -61,6 +66,8 @@ SIGNATURES = {
     "gsb200_indices_in_range_count": [_U, _U, _U, _U, _L, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_indices_in_range_fill": [_U, _U, _U, _U, _L, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_fake_quantize_fwd": [_L, _P, _F, _F, _I, _I, _I, _P, c_uint64, c_uint64, _P, _P],
+    "gsb200_fake_quantize_multi_fwd": [_U, _P, _P],
+    "gsb200_fake_quantize_multi_bwd": [_U, _P, _P],
     "gsb200_fake_quantize_bwd": [_L, _P, _P, _F, _F, _I, _I, _P, _P, _P],
     "gsb200_entropy_fwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P],
     "gsb200_entropy_bwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P, _P, _P],
@@ -90,6 +97,14 @@ class AdamTensor(ctypes.Structure):
                 ("inv_sqrt_bias2", c_float), ("one_minus_beta1", c_float), ("one_minus_beta2", c_float)]
 
 
+class FqTensor(ctypes.Structure):
+    """struct gsb200_fq_tensor (include/gsb200.h)."""
+    _fields_ = [("n", c_int64), ("x", c_void_p), ("y", c_void_p), ("noise", c_void_p), ("v_y", c_void_p), ("v_x", c_void_p),
+                ("seed", c_uint64), ("offset", c_uint64), ("lo", c_float), ("hi", c_float), ("bitwidth", c_int), ("mode", c_int),
+                ("act", c_int)]
+
+
+FQ_MAX_TENSORS = 8  # GSB200_FQ_MAX_TENSORS
 ADAM_MAX_TENSORS = 16  # GSB200_ADAM_MAX_TENSORS
 _RESTYPES = {"gsb200_last_error": c_char_p, "gsb200_launch_count": c_uint64, "gsb200_grad_record": c_uint32,
              "gsb200_blend_stream_record": c_uint32,

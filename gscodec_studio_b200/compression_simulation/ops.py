@@ -82,6 +82,105 @@ class _FakeQuantize(torch.autograd.Function):
         return v_x.view_as(v_y), None, None, None, None, None, None
 
 
+class _FakeQuantizeMulti(torch.autograd.Function):
+    """Several tensors quantised by ONE launch each way (gsb200_fake_quantize_multi_fwd / _bwd): the policy quantises
+    4-7 attributes per training step and at 1 M Gaussians a launch per attribute costs more host time than device time.
+    apply(cfgs, *tensors) with cfgs = [(lo, hi, bitwidth, mode, act, noise-or-None), ...] -> tuple of outputs."""
+
+    @staticmethod
+    def forward(ctx, cfgs, *xs):
+        from .._cabi import FqTensor
+
+        dev = xs[0].device
+        table = (FqTensor * len(xs))()
+        ins, outs, keep = [], [], []
+        for i, (x, (lo, hi, bits, mode, act, noise)) in enumerate(zip(xs, cfgs)):
+            if not x.is_cuda:
+                raise RuntimeError("gscodec_studio_b200: fake_quantize needs a CUDA tensor (no CPU implementation)")
+            if x.dtype != torch.float32:
+                raise RuntimeError(f"gscodec_studio_b200: expected float32 tensor, got {x.dtype}")
+            if mode == 1:
+                if not x.is_contiguous():
+                    raise RuntimeError("gscodec_studio_b200: round-mode fake quantisation needs a contiguous tensor")
+                xin = x
+            else:
+                xin = aligned(x)
+            y = torch.empty_like(xin)
+            seed, offset = (0, 0)
+            if mode == 0 and noise is None:
+                seed, offset = _philox_args(dev, x.numel())
+            if noise is not None:
+                noise = aligned(noise.to(torch.float32))
+                assert noise.numel() == x.numel(), "noise must have as many elements as the input"
+                keep.append(noise)
+            t = table[i]
+            t.n, t.x, t.y, t.noise = xin.numel(), ptr(xin), ptr(y), ptr(noise)
+            t.seed, t.offset, t.lo, t.hi, t.bitwidth, t.mode, t.act = seed, offset, float(lo), float(hi), int(bits), mode, act
+            ins.append(xin if mode == 0 else xin.detach())
+            outs.append(y)
+        import ctypes as _ct
+
+        with torch.cuda.device(dev):
+            call("gsb200_fake_quantize_multi_fwd", len(xs), _ct.cast(table, _ct.c_void_p), stream_ptr(dev))
+        ctx.save_for_backward(*ins, *outs)
+        ctx.cfgs = [(float(lo), float(hi), int(bits), mode, act) for (lo, hi, bits, mode, act, _n) in cfgs]
+        return tuple(y.view_as(x) for y, x in zip(outs, xs))
+
+    @staticmethod
+    def backward(ctx, *v_ys):
+        from .._cabi import FqTensor
+        import ctypes as _ct
+
+        k = len(ctx.cfgs)
+        ins, outs = ctx.saved_tensors[:k], ctx.saved_tensors[k:]
+        dev = ins[0].device
+        table = (FqTensor * k)()
+        grads, keep, m = [], [], 0
+        for i, (x, y, v_y, (lo, hi, bits, mode, act)) in enumerate(zip(ins, outs, v_ys, ctx.cfgs)):
+            if v_y is None or not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            if mode == 1 and act == 0:
+                grads.append(v_y)  # pure straight-through (ops.py:73-75)
+                continue
+            v_y = aligned(v_y.contiguous())
+            v_x = torch.empty_like(x)
+            t = table[m]
+            t.n, t.x, t.y, t.v_y, t.v_x = x.numel(), ptr(x), ptr(y), ptr(v_y), ptr(v_x)
+            t.lo, t.hi, t.bitwidth, t.mode, t.act = lo, hi, bits, mode, act
+            keep.append(v_y)
+            grads.append(v_x.view_as(v_y))
+            m += 1
+        if m:
+            with torch.cuda.device(dev):
+                call("gsb200_fake_quantize_multi_bwd", m, _ct.cast(table, _ct.c_void_p), stream_ptr(dev))
+        return (None, *grads)
+
+
+def fake_quantize_ste_multi(items) -> list:
+    """Additive: fake_quantize_ste for several tensors in one launch per direction.  items: sequence of dicts with the
+    keyword arguments of fake_quantize_ste (input, lower_bd, upper_bd, bitwidth, q_type, noise, activation); returns the
+    list of {"output_value", "q_step"} dicts in the same order."""
+    from .._cabi import FQ_MAX_TENSORS
+
+    items = list(items)
+    out = []
+    for lo_i in range(0, len(items), FQ_MAX_TENSORS):
+        chunk = items[lo_i:lo_i + FQ_MAX_TENSORS]
+        cfgs, xs = [], []
+        for it in chunk:
+            q_type = it.get("q_type", "noise")
+            if q_type not in _MODE:
+                raise NotImplementedError(f"q_type {q_type!r} is not supported")
+            cfgs.append((it["lower_bd"], it["upper_bd"], it.get("bitwidth", 8), _MODE[q_type], _ACT[it.get("activation")],
+                         it.get("noise")))
+            xs.append(it["input"])
+        ys = _FakeQuantizeMulti.apply(cfgs, *xs)
+        for it, y in zip(chunk, ys):
+            out.append({"output_value": y, "q_step": (it["upper_bd"] - it["lower_bd"]) / (2 ** it.get("bitwidth", 8) - 1)})
+    return out
+
+
 class STE(torch.autograd.Function):
     """Round-mode straight-through estimator with the reference's signature (ops.py:57-75)."""
 

@@ -25,7 +25,7 @@ import torch
 from torch import Tensor
 
 from .entropy_model import Entropy_factorized_optimized_refactor, Entropy_gaussian
-from .ops import fake_quantize_ste
+from .ops import fake_quantize_ste, fake_quantize_ste_multi
 
 
 @dataclass(frozen=True)
@@ -145,16 +145,21 @@ class _SimulationBase:
             raise NotImplementedError(f"'shN_ada_mask_strategy': {strategy} has not been implemented.")
 
     # ------------------------------------------------------------------ the one routine
-    def _simulate_attr(self, name: str, param: Tensor, step: int, q_type: Optional[str], noise: Optional[Tensor],
-                       fuse_act: bool, choose_idx: Optional[Tensor] = None, pos: Optional[Tensor] = None):
+    def _plan_attr(self, name: str, param: Tensor, step: int, q_type: Optional[str], noise: Optional[Tensor], fuse_act: bool):
+        """Arguments of this attribute's fake_quantize_ste call (+ whether a rate term follows, the fused activation)."""
         p = self.policy[name]
         lo, hi = p.bounds
         bits = 8 if step < 10_000 else p.bits  # simulation.py:242-245 (both branches give 8 today)
-        kw = {} if q_type is None else {"q_type": q_type}
         want_entropy = (self.entropy_model_enable and self.entropy_model_option.get(name, False)
                         and step > self.entropy_steps[name])
         act = _FUSED_ACT.get(name) if (fuse_act and not want_entropy) else None
-        fq = fake_quantize_ste(param, lo, hi, bits, noise=noise, activation=act, **kw)
+        item = dict(input=param, lower_bd=lo, upper_bd=hi, bitwidth=bits, noise=noise, activation=act)
+        if q_type is not None:
+            item["q_type"] = q_type
+        return item, want_entropy, act
+
+    def _finish_attr(self, name: str, fq: Dict, want_entropy: bool, choose_idx: Optional[Tensor], pos: Optional[Tensor]):
+        p = self.policy[name]
         value = fq["output_value"]
         esti_bits = None
         if want_entropy:
@@ -167,7 +172,7 @@ class _SimulationBase:
                 esti_bits = self.entropy_models[name](flat[choose_idx], fq["q_step"], pos=pos)
             else:
                 esti_bits = self.entropy_models[name](flat, fq["q_step"])
-        return value, esti_bits, act
+        return value, esti_bits
 
     def _simulate(self, splats: Dict[str, Tensor], step: int, q_type, noise, fuse_activations):
         new_splats, esti_bits_dict = {}, {}
@@ -177,12 +182,19 @@ class _SimulationBase:
             choose_idx = self._random_sample_pts(self._get_pts_inside_bbox(splats["means"]))  # simulation.py:216-220
             pos = splats["means"][choose_idx]
             self._last_sample_idx = choose_idx  # which points carried the rate estimate (debugging / tests)
+        # every quantised attribute of the step goes through ONE fused kernel launch (and one more in the backward)
+        plans = {name: self._plan_attr(name, splats[name], step, q_type, None if noise is None else noise.get(name),
+                                       fuse_activations)
+                 for name in splats.keys() if self.policy[name].bounds is not None and self.simulation_option[name]}
+        if len(plans) > 1:
+            fqs = dict(zip(plans, fake_quantize_ste_multi([pl[0] for pl in plans.values()])))
+        else:
+            fqs = {name: fake_quantize_ste(**pl[0]) for name, pl in plans.items()}
         for name in splats.keys():
             esti_bits_dict[name] = None
-            if self.policy[name].bounds is not None and self.simulation_option[name]:
-                value, bits, act = self._simulate_attr(name, splats[name], step, q_type,
-                                                       None if noise is None else noise.get(name), fuse_activations,
-                                                       choose_idx, pos)
+            if name in plans:
+                _item, want_entropy, act = plans[name]
+                value, bits = self._finish_attr(name, fqs[name], want_entropy, choose_idx, pos)
                 new_splats[name + "_act" if act is not None else name] = value
                 esti_bits_dict[name] = bits
             elif name in self.returns_self:

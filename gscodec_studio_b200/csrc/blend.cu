@@ -28,8 +28,10 @@
 namespace gsb200 {
 
 
-template <int CDIM>
-__global__ void __launch_bounds__(kBatch, CDIM <= 4 ? GSB_FWD_BLOCKS : 1)
+// BIG: tiles of 17..32 pixels, i.e. up to 1024 threads per CTA (the reference launches tile_size^2 threads for any size,
+// rasterize_to_pixels_fwd.cu:228, 244-263); one Gaussian staged per thread there, so the buffers stay within 227 KB
+template <int CDIM, bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : kBatch, (!BIG && CDIM <= 4) ? GSB_FWD_BLOCKS : 1)
 blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
                  const float *__restrict__ colors, const float *__restrict__ opacities,
                  const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
@@ -37,9 +39,10 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
                  float *__restrict__ render_colors, float *__restrict__ render_alphas, int32_t *__restrict__ last_ids,
                  const int32_t *__restrict__ tile_order) {
     constexpr int CP = ColorPad<CDIM>::value;
+    constexpr int SP = BIG ? 1 : kStagePerThread;
     extern __shared__ float4 smem4[];
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
-    const uint32_t batch = nthreads * kStagePerThread;
+    const uint32_t batch = nthreads * SP;
     float4 *sA = smem4;                                 // x, y, opacity, qmax
     float4 *sB = sA + batch;                            // conic a, b, c, -
     float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CP]
@@ -87,7 +90,7 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
         // barrier protects the staging buffers; stop when every pixel of the tile is saturated
         if (__syncthreads_count(done) >= (int)nthreads) break;
 #pragma unroll
-        for (int sp = 0; sp < kStagePerThread; ++sp) {
+        for (int sp = 0; sp < SP; ++sp) {
             const uint32_t e = tid + sp * nthreads;
             const int32_t idx = batch_start + (int32_t)e;
             if (idx < range_end) {
@@ -153,8 +156,8 @@ blend_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     }
 }
 
-template <int CDIM, bool ABS>
-__global__ void __launch_bounds__(kBatch, CDIM <= 4 ? GSB_BWD_BLOCKS : 1)
+template <int CDIM, bool ABS, bool BIG>
+__global__ void __launch_bounds__(BIG ? 1024 : kBatch, (!BIG && CDIM <= 4) ? GSB_BWD_BLOCKS : 1)
 blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
                  const float *__restrict__ colors, const float *__restrict__ opacities,
                  const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
@@ -168,10 +171,11 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
     // [opac] (one butterfly) or [opac absx absy 0] (one 4-wide spread) when abs-gradients are wanted
     constexpr int NMAIN = CDIM + 5;
     constexpr int NGRP = (NMAIN + 7) / 8;
+    constexpr int SP = BIG ? 1 : kStagePerThread;
     extern __shared__ float4 smem4[];
     __shared__ int s_binmax;
     const uint32_t nthreads = blockDim.x, tid = threadIdx.x;
-    const uint32_t batch = nthreads * kStagePerThread;
+    const uint32_t batch = nthreads * SP;
     float4 *sA = smem4;                                 // x, y, opacity, qmax
     float4 *sB = sA + batch;                            // conic a, b, c, flatten id (bits)
     float *sC = reinterpret_cast<float *>(sB + batch);  // [batch][CP]
@@ -228,7 +232,7 @@ blend_bwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *_
         __syncthreads();
         const int32_t bsize = min((int32_t)batch, batch_end + 1 - range_start);
 #pragma unroll
-        for (int sp = 0; sp < kStagePerThread; ++sp) {
+        for (int sp = 0; sp < SP; ++sp) {
             const int32_t e = (int32_t)(tid + sp * nthreads);
             if (e < bsize) {
                 const int32_t g = flatten_ids[batch_end - e];
@@ -398,16 +402,24 @@ static int launch_fwd(const BlendGeom &G, const float *means2d, const float *con
                       const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,
                       int32_t *tile_order, cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
-    const uint32_t batch = nthreads * kStagePerThread;
+    const bool big = nthreads > (uint32_t)kBatch;
+    const uint32_t batch = nthreads * (big ? 1 : kStagePerThread);
     const size_t smem = (size_t)batch * (32 + 4 * ColorPad<CDIM>::value);
-    if (smem > 48 * 1024)
-        GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) {  // (the kernels also hold a little static shared memory)
+        if (big) GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else GSB_CUDA_OK(cudaFuncSetAttribute(blend_fwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const uint32_t T = G.C * G.tw * G.th;
     if (tile_order != nullptr)
         if (int e = launch_tile_order(T, G.n_isects, tile_offsets, tile_order, s)) return e;
-    blend_fwd_kernel<CDIM><<<T, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
-                                                      opacities, backgrounds, masks, tile_offsets, flatten_ids,
-                                                      render_colors, render_alphas, last_ids, tile_order);
+    if (big)
+        blend_fwd_kernel<CDIM, true><<<T, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
+                                                                opacities, backgrounds, masks, tile_offsets, flatten_ids,
+                                                                render_colors, render_alphas, last_ids, tile_order);
+    else
+        blend_fwd_kernel<CDIM, false><<<T, nthreads, smem, s>>>(G, reinterpret_cast<const float2 *>(means2d), conics, colors,
+                                                                 opacities, backgrounds, masks, tile_offsets, flatten_ids,
+                                                                 render_colors, render_alphas, last_ids, tile_order);
     return check_launch("blend_fwd");
 }
 
@@ -419,25 +431,26 @@ static int launch_bwd(const BlendGeom &G, uint32_t M, const float *means2d, cons
                       float *grad_scratch, float *v_abs,
                       float *v_means2d, float *v_conics, float *v_colors, float *v_opacities, cudaStream_t s) {
     const uint32_t nthreads = (G.ts * G.ts + 31) / 32 * 32;
-    const uint32_t batch = nthreads * kStagePerThread;
+    const bool big = nthreads > (uint32_t)kBatch;
+    const uint32_t batch = nthreads * (big ? 1 : kStagePerThread);
     const size_t smem = (size_t)batch * (32 + 4 * ColorPad<CDIM>::value);
-    if (smem > 48 * 1024) {
-        GSB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+#define GSB_BWD_GO(ABSV, BIGV)                                                                                              \
+    do {                                                                                                                    \
+        if (smem > 40 * 1024)                                                                                               \
+            GSB_CUDA_OK(cudaFuncSetAttribute(blend_bwd_kernel<CDIM, ABSV, BIGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                                   \
+        blend_bwd_kernel<CDIM, ABSV, BIGV><<<T, nthreads, smem, s>>>(                                                        \
+            G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,      \
+            flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, grad_scratch);              \
+    } while (0)
     GSB_CUDA_OK(cudaMemsetAsync(grad_scratch, 0, sizeof(float) * (size_t)M * grad_record(CDIM), s));
     if (G.n_isects > 0) {
         const uint32_t T = G.C * G.tw * G.th;
-        if (v_abs != nullptr)
-            blend_bwd_kernel<CDIM, true><<<T, nthreads, smem, s>>>(
-                G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,
-                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, grad_scratch);
-        else
-            blend_bwd_kernel<CDIM, false><<<T, nthreads, smem, s>>>(
-                G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets,
-                flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order, grad_scratch);
+        if (v_abs != nullptr) { if (big) GSB_BWD_GO(true, true); else GSB_BWD_GO(true, false); }
+        else { if (big) GSB_BWD_GO(false, true); else GSB_BWD_GO(false, false); }
         if (int e = check_launch("blend_bwd")) return e;
     }
+#undef GSB_BWD_GO
     return launch_unpack<CDIM>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors, v_opacities, s);
 }
 
@@ -482,7 +495,7 @@ extern "C" uint32_t gsb200_blend_stream_record(uint32_t D, uint32_t tile_size) {
 }
 
 static int check_geom(uint32_t tile_size, uint32_t W, uint32_t H, uint32_t tw, uint32_t th) {
-    if (tile_size == 0 || tile_size > 16) return fail(2, "gsb200_rasterize: tile_size must be in [1, 16]");
+    if (tile_size == 0 || tile_size > 32) return fail(2, "gsb200_rasterize: tile_size must be in [1, 32]");
     if (tw * tile_size < W || th * tile_size < H)
         return fail(2, "gsb200_rasterize: tile grid does not cover the image (Assert Failed: tile_height * tile_size >= image_height)");
     return 0;

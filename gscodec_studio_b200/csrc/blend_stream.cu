@@ -28,6 +28,12 @@ constexpr int kStageRecs = 64;  // records per pipeline stage
 #define GSB_STREAM_STAGES 4
 #endif
 constexpr int kStages = GSB_STREAM_STAGES;
+#ifndef GSB_SFWD_BLOCKS
+#define GSB_SFWD_BLOCKS 6  // minimum resident CTAs per SM the register allocator must allow (forward, NP = 1)
+#endif
+#ifndef GSB_SBWD_BLOCKS
+#define GSB_SBWD_BLOCKS 7  // (backward, NP = 1)
+#endif
 #ifndef GSB_PRODUCER_SLEEP_NS
 #define GSB_PRODUCER_SLEEP_NS 256  // ring full: the consumers need ~10^3 cycles per stage
 #endif
@@ -157,7 +163,7 @@ __device__ __forceinline__ void pair_pixels(uint32_t w, uint32_t lane, uint32_t 
 
 // ---------------------------------------------------------------------------------------------- forward
 template <int CDIM, int NP>
-__global__ void __launch_bounds__((4 / NP + 1) * 32, NP == 1 ? 6 : 8)
+__global__ void __launch_bounds__((4 / NP + 1) * 32, NP == 1 ? GSB_SFWD_BLOCKS : 8)
 blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const float *__restrict__ conics,
                         const float *__restrict__ colors, const float *__restrict__ opacities,
                         const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
@@ -441,7 +447,7 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
 // No producer warp here: staging is one bulk copy per stage, so the LAST consumer warp to release a ring slot refills it
 // (a shared-memory counter per slot plays the "empty" barrier) and every warp of the CTA does blend work.
 template <int CDIM, int NP, bool ABS>
-__global__ void __launch_bounds__((4 / NP) * 32, NP == 1 ? 7 : 8)
+__global__ void __launch_bounds__((4 / NP) * 32, NP == 1 ? GSB_SBWD_BLOCKS : 8)
 blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
                         const int32_t *__restrict__ tile_offsets, const float *__restrict__ render_alphas,
                         const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,

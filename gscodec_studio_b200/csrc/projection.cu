@@ -22,15 +22,23 @@ namespace gsb200 {
 
 constexpr int kMaxSmemCams = 64;  // cameras cached in shared memory per pass
 
+// MODE 0: dense outputs [C,N,...].  MODE 1 / 2: the two passes of the packed (COO) form -- memory proportional to the
+// number of visible (camera, Gaussian) pairs, never C * N (reference: fully_fused_projection_packed_fwd.cu:200-247):
+//   1  only counts the visible Gaussians of every (camera, block) -> pk_counts[c * n_blocks + block]
+//   2  recomputes the projection and writes row pk_counts[c * n_blocks + block] (now the exclusive scan) + rank inside
+//      the block; rows therefore come out in (camera, Gaussian) lexicographic order, like the reference's
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
                       const float *__restrict__ quats, const float *__restrict__ scales,
                       const float *__restrict__ viewmats, const float *__restrict__ Ks, float W, float H,
                       float eps2d, float near_plane, float far_plane, float radius_clip, int model,
                       int packed_rule, int32_t *__restrict__ radii, float *__restrict__ means2d,
-                      float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ comps) {
+                      float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ comps,
+                      int32_t *__restrict__ pk_counts, int64_t *__restrict__ pk_camera_ids, int64_t *__restrict__ pk_gaussian_ids) {
     __shared__ float s_vm[kMaxSmemCams][12];
     __shared__ float s_k[kMaxSmemCams][4];
+    __shared__ int s_wcnt[kThreads / 32];
     const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (g < N) { px = __ldg(means + (size_t)g * 3); py = __ldg(means + (size_t)g * 3 + 1); pz = __ldg(means + (size_t)g * 3 + 2); }
@@ -47,7 +55,7 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
             s_k[i][0] = K[0]; s_k[i][1] = K[4]; s_k[i][2] = K[2]; s_k[i][3] = K[5];
         }
         __syncthreads();
-        if (g >= N) continue;
+        if (MODE == 0 && g >= N) continue;  // (the packed passes meet block barriers inside the camera loop)
         for (uint32_t ci = 0; ci < nc; ++ci) {
             const float *R = s_vm[ci];
             const size_t idx = (size_t)(c0 + ci) * N + g;
@@ -56,7 +64,7 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
             float mz = R[8] * px + R[9] * py + R[10] * pz + R[11];
             int32_t rad = 0;
             float o_mx = 0.f, o_my = 0.f, o_d = 0.f, o_a = 0.f, o_b = 0.f, o_c = 0.f, o_comp = 0.f;
-            if (!(mz < near_plane || mz > far_plane)) {
+            if (g < N && !(mz < near_plane || mz > far_plane)) {
                 if (!have_S) {
                     have_S = true;
                     if (covars != nullptr) {
@@ -98,16 +106,44 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                     }
                 }
             }
-            radii[idx] = rad;
-            *reinterpret_cast<float2 *>(means2d + idx * 2) = make_float2(o_mx, o_my);
-            depths[idx] = o_d;
-            conics[idx * 3] = o_a; conics[idx * 3 + 1] = o_b; conics[idx * 3 + 2] = o_c;
-            if (comps != nullptr) comps[idx] = o_comp;
+            if (MODE == 0) {
+                radii[idx] = rad;
+                *reinterpret_cast<float2 *>(means2d + idx * 2) = make_float2(o_mx, o_my);
+                depths[idx] = o_d;
+                conics[idx * 3] = o_a; conics[idx * 3 + 1] = o_b; conics[idx * 3 + 2] = o_c;
+                if (comps != nullptr) comps[idx] = o_comp;
+            } else if (MODE == 1) {
+                const int cnt = __syncthreads_count(rad > 0);
+                if (threadIdx.x == 0) pk_counts[(size_t)(c0 + ci) * gridDim.x + blockIdx.x] = cnt;
+            } else {
+                const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                const unsigned bal = __ballot_sync(0xffffffffu, rad > 0);
+                if (lane == 0) s_wcnt[warp] = __popc(bal);
+                __syncthreads();
+                int before = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < kThreads / 32; ++w) before += w < warp ? s_wcnt[w] : 0;
+                if (rad > 0) {
+                    const size_t row = (size_t)pk_counts[(size_t)(c0 + ci) * gridDim.x + blockIdx.x] + before +
+                                       __popc(bal & ((1u << lane) - 1u));
+                    pk_camera_ids[row] = c0 + ci;
+                    pk_gaussian_ids[row] = g;
+                    radii[row] = rad;
+                    *reinterpret_cast<float2 *>(means2d + row * 2) = make_float2(o_mx, o_my);
+                    depths[row] = o_d;
+                    conics[row * 3] = o_a; conics[row * 3 + 1] = o_b; conics[row * 3 + 2] = o_c;
+                    if (comps != nullptr) comps[row] = o_comp;
+                }
+                __syncthreads();
+            }
         }
     }
 }
 
-template <bool VIEWGRAD, bool FISHEYE>
+// PACKED: radii / conics / comps / v_* are [nnz, ...] rows in (camera, Gaussian) order and `pk_offsets` / `pk_gaussian_ids`
+// (the forward's per-(camera, block) row offsets and the rows' Gaussian indices) tell every block which of its threads
+// own a row for the current camera: same ownership as the dense form -- no atomics, no dense scatter of the gradients.
+template <bool VIEWGRAD, bool FISHEYE, bool PACKED>
 __global__ void __launch_bounds__(kThreads, FISHEYE ? 1 : 3)
 projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
                       const float *__restrict__ quats, const float *__restrict__ scales,
@@ -116,10 +152,12 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                       const float *__restrict__ comps, const float *__restrict__ v_means2d,
                       const float *__restrict__ v_depths, const float *__restrict__ v_conics,
                       const float *__restrict__ v_comps, float *__restrict__ v_means, float *__restrict__ v_covars,
-                      float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_viewmats) {
+                      float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_viewmats,
+                      const int32_t *__restrict__ pk_offsets, const int64_t *__restrict__ pk_gaussian_ids) {
     __shared__ float s_vm[kMaxSmemCams][12];
     __shared__ float s_k[kMaxSmemCams][4];
     __shared__ float s_red[kThreads / 32][12];
+    __shared__ int s_row[PACKED ? kThreads : 1];
     const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float px = 0.f, py = 0.f, pz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
@@ -145,10 +183,25 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
         __syncthreads();
         for (uint32_t ci = 0; ci < nc; ++ci) {
             const float *R = s_vm[ci];
-            const size_t idx = (size_t)(c0 + ci) * N + g;
+            size_t idx = (size_t)(c0 + ci) * N + g;
             float vR[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
             float vt[3] = {0.f, 0.f, 0.f};
-            const bool active = (g < N) && radii[idx] > 0;
+            bool active;
+            if (PACKED) {
+                // rows of this block for this camera: [lo, hi); their Gaussian indices say which thread owns which row
+                const size_t ob = (size_t)(c0 + ci) * gridDim.x + blockIdx.x;
+                const int lo = pk_offsets[ob], hi = pk_offsets[ob + 1];
+                __syncthreads();
+                s_row[threadIdx.x] = -1;
+                __syncthreads();
+                if ((int)threadIdx.x < hi - lo) s_row[(uint32_t)pk_gaussian_ids[lo + threadIdx.x] - blockIdx.x * kThreads] = lo + (int)threadIdx.x;
+                __syncthreads();
+                const int row = s_row[threadIdx.x];
+                active = row >= 0;
+                idx = active ? (size_t)row : 0;
+            } else {
+                active = (g < N) && radii[idx] > 0;
+            }
             if (active) {
                 if (!have_S) {
                     have_S = true;
@@ -452,10 +505,70 @@ extern "C" int gsb200_projection_fwd(uint32_t C, uint32_t N, const float *means,
     if (C == 0 || N == 0) return 0;  // (empty tensors have NULL data pointers)
     if (covars == nullptr && (quats == nullptr || scales == nullptr))
         return fail(2, "gsb200_projection_fwd: covars or (quats, scales) should be provided");
-    projection_fwd_kernel<<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+    projection_fwd_kernel<0><<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip,
-        camera_model, packed_radius_rule, radii, means2d, depths, conics, compensations);
+        camera_model, packed_radius_rule, radii, means2d, depths, conics, compensations, nullptr, nullptr, nullptr);
     return check_launch("projection_fwd");
+}
+
+// ---- packed (COO) projection: two passes, nothing of size C * N ------------------------------------------------------------
+extern "C" int gsb200_projection_packed_count(uint32_t C, uint32_t N, const float *means, const float *covars, const float *quats,
+                                              const float *scales, const float *viewmats, const float *Ks, uint32_t W, uint32_t H,
+                                              float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
+                                              int32_t *block_offsets, int64_t *nnz_host, gsb200_stream_t stream) {
+    if (nnz_host != nullptr) *nnz_host = 0;
+    if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
+        return fail(2, "gsb200_projection_packed_count: camera_model must be pinhole, ortho or fisheye");
+    if (C == 0 || N == 0) return 0;
+    if (covars == nullptr && (quats == nullptr || scales == nullptr))
+        return fail(2, "gsb200_projection_packed_count: covars or (quats, scales) should be provided");
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nb = cdiv(N, kThreads), n = C * nb;
+    projection_fwd_kernel<1><<<nb, kThreads, 0, s>>>(C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d,
+                                                     near_plane, far_plane, radius_clip, camera_model, 1, nullptr, nullptr, nullptr,
+                                                     nullptr, nullptr, block_offsets, nullptr, nullptr);
+    if (int e = check_launch("projection_packed_count")) return e;
+    // exclusive scan over (camera, block): block_offsets[0..n) in place, total -> block_offsets[n]; scratch behind it
+    int32_t *scratch = block_offsets + n + 1;
+    const uint32_t nsb = cdiv(n, kScanTile);
+    scan_block_sums_kernel<<<nsb, kThreads, 0, s>>>(n, block_offsets, scratch);
+    if (int e = check_launch("scan_block_sums")) return e;
+    scan_single_block_kernel<<<1, 1024, 0, s>>>(nsb, scratch);
+    if (int e = check_launch("scan_single_block")) return e;
+    scan_apply_kernel<<<nsb, kThreads, 0, s>>>(n, block_offsets, scratch, block_offsets, nullptr);
+    if (int e = check_launch("scan_apply")) return e;
+    GSB_CUDA_OK(cudaMemcpyAsync(block_offsets + n, scratch + nsb, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (nnz_host != nullptr) {
+        int32_t total = 0;
+        GSB_CUDA_OK(cudaMemcpyAsync(&total, scratch + nsb, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        GSB_CUDA_OK(cudaStreamSynchronize(s));
+        *nnz_host = total;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(kThreads)
+packed_indptr_kernel(uint32_t C, uint32_t nb, const int32_t *__restrict__ block_offsets, int32_t *__restrict__ indptr) {
+    const uint32_t c = blockIdx.x * kThreads + threadIdx.x;
+    if (c <= C) indptr[c] = block_offsets[(size_t)c * nb];  // c == C: the total behind the prefixes
+}
+
+extern "C" int gsb200_projection_packed_fill(uint32_t C, uint32_t N, const float *means, const float *covars, const float *quats,
+                                             const float *scales, const float *viewmats, const float *Ks, uint32_t W, uint32_t H,
+                                             float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
+                                             const int32_t *block_offsets, int32_t *indptr, int64_t *camera_ids,
+                                             int64_t *gaussian_ids, int32_t *radii, float *means2d, float *depths, float *conics,
+                                             float *compensations, gsb200_stream_t stream) {
+    if (C == 0 || N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nb = cdiv(N, kThreads);
+    projection_fwd_kernel<2><<<nb, kThreads, 0, s>>>(C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d,
+                                                     near_plane, far_plane, radius_clip, camera_model, 1, radii, means2d, depths,
+                                                     conics, compensations, const_cast<int32_t *>(block_offsets), camera_ids,
+                                                     gaussian_ids);
+    if (int e = check_launch("projection_packed_fill")) return e;
+    packed_indptr_kernel<<<cdiv(C + 1, kThreads), kThreads, 0, s>>>(C, nb, block_offsets, indptr);
+    return check_launch("packed_indptr");
 }
 
 extern "C" int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means, const float *covars, const float *quats,
@@ -471,14 +584,42 @@ extern "C" int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means,
     const dim3 grid(cdiv(N, kThreads));
     cudaStream_t s = (cudaStream_t)stream;
 #define GSB_LAUNCH_PROJ_BWD(VG, FE)                                                                                  \
-    projection_bwd_kernel<VG, FE><<<grid, kThreads, 0, s>>>(                                                          \
+    projection_bwd_kernel<VG, FE, false><<<grid, kThreads, 0, s>>>(                                                   \
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,     \
-        compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats)
+        compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats, \
+        nullptr, nullptr)
     const bool fe = camera_model == GSB200_CAMERA_FISHEYE;
     if (v_viewmats != nullptr) { if (fe) GSB_LAUNCH_PROJ_BWD(true, true); else GSB_LAUNCH_PROJ_BWD(true, false); }
     else { if (fe) GSB_LAUNCH_PROJ_BWD(false, true); else GSB_LAUNCH_PROJ_BWD(false, false); }
 #undef GSB_LAUNCH_PROJ_BWD
     return check_launch("projection_bwd");
+}
+
+/* packed backward: conics / compensations / v_* are the [nnz, ...] rows of gsb200_projection_packed_fill; block_offsets and
+ * gaussian_ids are the forward's.  Gradient outputs are dense [N, ...] (sum over cameras), written once, no atomics. */
+extern "C" int gsb200_projection_packed_bwd(uint32_t C, uint32_t N, const float *means, const float *covars, const float *quats,
+                                            const float *scales, const float *viewmats, const float *Ks, uint32_t W, uint32_t H,
+                                            float eps2d, int camera_model, const int32_t *block_offsets,
+                                            const int64_t *gaussian_ids, const float *conics, const float *compensations,
+                                            const float *v_means2d, const float *v_depths, const float *v_conics,
+                                            const float *v_compensations, float *v_means, float *v_covars, float *v_quats,
+                                            float *v_scales, float *v_viewmats, gsb200_stream_t stream) {
+    if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
+        return fail(2, "gsb200_projection_packed_bwd: camera_model must be pinhole, ortho or fisheye");
+    if (C == 0 || N == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (v_viewmats != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_viewmats, 0, sizeof(float) * 16 * C, s));
+    const dim3 grid(cdiv(N, kThreads));
+#define GSB_LAUNCH_PROJ_PBWD(VG, FE)                                                                                 \
+    projection_bwd_kernel<VG, FE, true><<<grid, kThreads, 0, s>>>(                                                    \
+        C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, nullptr, conics,   \
+        compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats, \
+        block_offsets, gaussian_ids)
+    const bool fe = camera_model == GSB200_CAMERA_FISHEYE;
+    if (v_viewmats != nullptr) { if (fe) GSB_LAUNCH_PROJ_PBWD(true, true); else GSB_LAUNCH_PROJ_PBWD(true, false); }
+    else { if (fe) GSB_LAUNCH_PROJ_PBWD(false, true); else GSB_LAUNCH_PROJ_PBWD(false, false); }
+#undef GSB_LAUNCH_PROJ_PBWD
+    return check_launch("projection_packed_bwd");
 }
 
 extern "C" int gsb200_compact_count(uint32_t C, uint32_t N, const int32_t *radii, int32_t *block_offsets,

@@ -38,11 +38,10 @@ __device__ __forceinline__ float activate(int act, float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(kThreads)
-fake_quantize_fwd_kernel(int64_t n, float *__restrict__ x, float lo, float hi, float q_step, float qs_norm, int mode, int act,
-                         const float *__restrict__ noise, uint64_t seed, uint64_t offset, float *__restrict__ y) {
-    // 4 consecutive elements per thread (one Philox call yields 4 uniforms)
-    const int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+// 4 consecutive elements starting at `base` (one Philox call yields 4 uniforms)
+__device__ __forceinline__ void fake_quantize_fwd4(int64_t base, int64_t n, float *__restrict__ x, float lo, float hi, float q_step,
+                                                   float qs_norm, int mode, int act, const float *__restrict__ noise, uint64_t seed,
+                                                   uint64_t offset, float *__restrict__ y) {
     if (base >= n) return;
     float u[4] = {0.f, 0.f, 0.f, 0.f};
     if (mode == 0) {
@@ -74,15 +73,53 @@ fake_quantize_fwd_kernel(int64_t n, float *__restrict__ x, float lo, float hi, f
 }
 
 __global__ void __launch_bounds__(kThreads)
-fake_quantize_bwd_kernel(int64_t n, const float *__restrict__ x, const float *__restrict__ y, float lo, float hi, int mode,
-                         int act, const float *__restrict__ v_y, float *__restrict__ v_x) {
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+fake_quantize_fwd_kernel(int64_t n, float *__restrict__ x, float lo, float hi, float q_step, float qs_norm, int mode, int act,
+                         const float *__restrict__ noise, uint64_t seed, uint64_t offset, float *__restrict__ y) {
+    fake_quantize_fwd4(((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4, n, x, lo, hi, q_step, qs_norm, mode, act, noise, seed,
+                       offset, y);
+}
+
+__device__ __forceinline__ void fake_quantize_bwd1(int64_t i, int64_t n, const float *__restrict__ x, const float *__restrict__ y,
+                                                   float lo, float hi, int mode, int act, const float *__restrict__ v_y,
+                                                   float *__restrict__ v_x) {
     if (i >= n) return;
     float g = v_y[i];
     if (act == 1) g *= y[i];
     else if (act == 2) { const float s = y[i]; g *= s * (1.f - s); }
     if (mode == 0) { const float v = x[i]; g = (v >= lo && v <= hi) ? g : 0.f; }  // clamp gate; round mode is a pure STE
     v_x[i] = g;
+}
+
+__global__ void __launch_bounds__(kThreads)
+fake_quantize_bwd_kernel(int64_t n, const float *__restrict__ x, const float *__restrict__ y, float lo, float hi, int mode,
+                         int act, const float *__restrict__ v_y, float *__restrict__ v_x) {
+    fake_quantize_bwd1((int64_t)blockIdx.x * kThreads + threadIdx.x, n, x, y, lo, hi, mode, act, v_y, v_x);
+}
+
+// ---- all attributes of a step in ONE launch per direction (the policy quantises 4-7 tensors per step; one launch each
+// costs more host time than device time at 1 M Gaussians) -- same per-element arithmetic as the single-tensor kernels
+struct FqTable {
+    gsb200_fq_tensor t[GSB200_FQ_MAX_TENSORS];
+    float q_step[GSB200_FQ_MAX_TENSORS], qs_norm[GSB200_FQ_MAX_TENSORS];
+    uint32_t block_end[GSB200_FQ_MAX_TENSORS];  // exclusive prefix of blocks, per tensor
+    uint32_t n;
+};
+
+__global__ void __launch_bounds__(kThreads) fake_quantize_multi_fwd_kernel(const __grid_constant__ FqTable T) {
+    uint32_t ti = 0;
+    while (ti + 1 < T.n && blockIdx.x >= T.block_end[ti]) ++ti;
+    const gsb200_fq_tensor &h = T.t[ti];
+    const uint32_t blk = blockIdx.x - (ti == 0 ? 0u : T.block_end[ti - 1]);
+    fake_quantize_fwd4(((int64_t)blk * kThreads + threadIdx.x) * 4, h.n, h.x, h.lo, h.hi, T.q_step[ti], T.qs_norm[ti], h.mode, h.act,
+                       h.noise, h.seed, h.offset, h.y);
+}
+
+__global__ void __launch_bounds__(kThreads) fake_quantize_multi_bwd_kernel(const __grid_constant__ FqTable T) {
+    uint32_t ti = 0;
+    while (ti + 1 < T.n && blockIdx.x >= T.block_end[ti]) ++ti;
+    const gsb200_fq_tensor &h = T.t[ti];
+    const uint32_t blk = blockIdx.x - (ti == 0 ? 0u : T.block_end[ti - 1]);
+    fake_quantize_bwd1((int64_t)blk * kThreads + threadIdx.x, h.n, h.x, h.y, h.lo, h.hi, h.mode, h.act, h.v_y, h.v_x);
 }
 
 // ---------------------------------------------------------------- factorized entropy model
@@ -257,6 +294,48 @@ extern "C" int gsb200_fake_quantize_fwd(int64_t n, float *x, float lo, float hi,
     fake_quantize_fwd_kernel<<<(unsigned)((nthreads + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         n, x, lo, hi, q_step, qs_norm, mode, act, noise, seed, offset, y);
     return check_launch("fake_quantize_fwd");
+}
+
+static int fq_table(const char *who, uint32_t n_tensors, const gsb200_fq_tensor *tensors, bool backward, FqTable &T, uint64_t &blocks) {
+    if (n_tensors > GSB200_FQ_MAX_TENSORS) return failf(2, "%s: at most %d tensors per call", who, GSB200_FQ_MAX_TENSORS);
+    if (n_tensors > 0 && tensors == nullptr) return failf(2, "%s: null table", who);
+    blocks = 0;
+    for (uint32_t i = 0; i < n_tensors; ++i) {
+        const gsb200_fq_tensor &h = tensors[i];
+        if (h.n <= 0) continue;
+        if (h.mode != 0 && h.mode != 1) return failf(2, "%s: mode must be 0 (noise) or 1 (round)", who);
+        if (h.act < 0 || h.act > 2) return failf(2, "%s: act must be 0, 1 or 2", who);
+        if (h.x == nullptr || h.y == nullptr || (backward && (h.v_y == nullptr || h.v_x == nullptr)))
+            return failf(2, "%s: null pointer in the tensor table", who);
+        const double levels = (double)((1ull << h.bitwidth) - 1ull);
+        T.q_step[T.n] = (float)(((double)h.hi - (double)h.lo) / levels);
+        T.qs_norm[T.n] = (float)(1.0 / levels);
+        const uint64_t units = backward ? (uint64_t)h.n : (uint64_t)(h.n + 3) / 4;
+        blocks += (units + kThreads - 1) / kThreads;
+        if (blocks > 0x7fffffffull) return failf(2, "%s: too many elements for one launch", who);
+        T.t[T.n] = h;
+        T.block_end[T.n] = (uint32_t)blocks;
+        ++T.n;
+    }
+    return 0;
+}
+
+extern "C" int gsb200_fake_quantize_multi_fwd(uint32_t n_tensors, const gsb200_fq_tensor *tensors, gsb200_stream_t stream) {
+    FqTable T{};
+    uint64_t blocks = 0;
+    if (int e = fq_table("gsb200_fake_quantize_multi_fwd", n_tensors, tensors, false, T, blocks)) return e;
+    if (T.n == 0) return 0;
+    fake_quantize_multi_fwd_kernel<<<(uint32_t)blocks, kThreads, 0, (cudaStream_t)stream>>>(T);
+    return check_launch("fake_quantize_multi_fwd");
+}
+
+extern "C" int gsb200_fake_quantize_multi_bwd(uint32_t n_tensors, const gsb200_fq_tensor *tensors, gsb200_stream_t stream) {
+    FqTable T{};
+    uint64_t blocks = 0;
+    if (int e = fq_table("gsb200_fake_quantize_multi_bwd", n_tensors, tensors, true, T, blocks)) return e;
+    if (T.n == 0) return 0;
+    fake_quantize_multi_bwd_kernel<<<(uint32_t)blocks, kThreads, 0, (cudaStream_t)stream>>>(T);
+    return check_launch("fake_quantize_multi_bwd");
 }
 
 extern "C" int gsb200_fake_quantize_bwd(int64_t n, const float *x, const float *y, float lo, float hi, int mode, int act,

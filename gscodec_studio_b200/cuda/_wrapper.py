@@ -480,8 +480,10 @@ class _FullyFusedProjection(torch.autograd.Function):
 
 
 class _FullyFusedProjectionPacked(torch.autograd.Function):
-    """COO variant.  Internally: dense projection (packed radius rule) -> stream compaction; the
-    backward scatters the packed gradients to the dense layout and reuses the dense kernel."""
+    """COO variant, memory proportional to nnz (reference: fully_fused_projection_packed_fwd.cu:200-247, two passes):
+    pass 1 projects and counts the visible pairs per (camera, 256-Gaussian block), the host reads nnz (the reference
+    synchronises at the same point), pass 2 projects again and writes the rows in (camera, Gaussian) order.  The backward
+    consumes the packed gradient rows directly; nothing of size C * N is allocated in either direction."""
 
     @staticmethod
     def forward(ctx, means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
@@ -489,16 +491,15 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         means, covars, quats, scales, viewmats, Ks = map(_f32, (means, covars, quats, scales, viewmats, Ks))
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
-        radii_d, means2d_d, depths_d, conics_d, comps_d = _projection_fwd(
-            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
-            calc_compensations, camera_model, True)
-        nb = (C * N + 2047) // 2048
-        block_offsets = torch.empty(nb + 1, dtype=torch.int32, device=dev)
+        n_blocks = C * ((N + 255) // 256)
+        block_offsets = torch.empty(n_blocks + 1 + (n_blocks + 2047) // 2048 + 3, dtype=torch.int32, device=dev)
         nnz_host = ctypes.c_int64(0)
+        geom = (C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), width, height, eps2d,
+                near_plane, far_plane, radius_clip, _CAMERA_MODELS[camera_model])
         with torch.cuda.device(dev):
-            call("gsb200_compact_count", C, N, ptr(radii_d), ptr(block_offsets), ctypes.byref(nnz_host), stream_ptr(dev))
+            call("gsb200_projection_packed_count", *geom, ptr(block_offsets), ctypes.byref(nnz_host), stream_ptr(dev))
         nnz = int(nnz_host.value)
-        indptr = torch.empty(C + 1, dtype=torch.int32, device=dev)
+        indptr = torch.zeros(C + 1, dtype=torch.int32, device=dev)
         camera_ids = torch.empty(nnz, dtype=torch.int64, device=dev)
         gaussian_ids = torch.empty(nnz, dtype=torch.int64, device=dev)
         radii = torch.empty(nnz, dtype=torch.int32, device=dev)
@@ -507,39 +508,35 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         conics = torch.empty((nnz, 3), dtype=torch.float32, device=dev)
         comps = torch.empty(nnz, dtype=torch.float32, device=dev) if calc_compensations else None
         with torch.cuda.device(dev):
-            call("gsb200_compact_fill", C, N, ptr(radii_d), ptr(means2d_d), ptr(depths_d), ptr(conics_d), ptr(comps_d),
-                 ptr(block_offsets), ptr(indptr), ptr(camera_ids), ptr(gaussian_ids), ptr(radii), ptr(means2d),
-                 ptr(depths), ptr(conics), ptr(comps), stream_ptr(dev))
-        ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, camera_ids, gaussian_ids, radii_d, conics_d,
-                              comps_d)
+            call("gsb200_projection_packed_fill", *geom, ptr(block_offsets), ptr(indptr), ptr(camera_ids), ptr(gaussian_ids),
+                 ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), stream_ptr(dev))
+        ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, gaussian_ids, block_offsets, conics, comps)
         ctx.dims = (width, height, eps2d, camera_model, sparse_grad)
         ctx.mark_non_differentiable(camera_ids, gaussian_ids, radii)
         return camera_ids, gaussian_ids, radii, means2d, depths, conics, comps
 
     @staticmethod
     def backward(ctx, v_camera_ids, v_gaussian_ids, v_radii, v_means2d, v_depths, v_conics, v_comps):
-        (means, covars, quats, scales, viewmats, Ks, camera_ids, gaussian_ids, radii_d, conics_d,
-         comps_d) = ctx.saved_tensors
+        means, covars, quats, scales, viewmats, Ks, gaussian_ids, block_offsets, conics, comps = ctx.saved_tensors
         width, height, eps2d, camera_model, sparse_grad = ctx.dims
         C, N = viewmats.shape[0], means.shape[0]
         dev = means.device
-        nnz = camera_ids.numel()
-        if comps_d is None:
+        nnz = gaussian_ids.numel()
+        if comps is None:
             v_comps = None
         elif v_comps is None:
             v_comps = torch.zeros(nnz, dtype=torch.float32, device=dev)
-        d_means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
-        d_depths = torch.empty((C, N), dtype=torch.float32, device=dev)
-        d_conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
-        d_comps = torch.empty((C, N), dtype=torch.float32, device=dev) if comps_d is not None else None
+        v_means = torch.empty_like(means)
+        v_covars = torch.empty_like(covars) if covars is not None else None
+        v_quats = torch.empty_like(quats) if covars is None else None
+        v_scales = torch.empty_like(scales) if covars is None else None
+        v_viewmats = torch.empty_like(viewmats) if ctx.needs_input_grad[4] else None
         with torch.cuda.device(dev):
-            call("gsb200_scatter_rows", C, N, nnz, ptr(camera_ids), ptr(gaussian_ids), ptr(_f32(v_means2d.contiguous())),
-                 ptr(_f32(v_depths.contiguous())), ptr(_f32(v_conics.contiguous())),
-                 ptr(None if v_comps is None else _f32(v_comps.contiguous())), ptr(d_means2d), ptr(d_depths),
-                 ptr(d_conics), ptr(d_comps), stream_ptr(dev))
-        v_means, v_covars, v_quats, v_scales, v_viewmats = _projection_bwd(
-            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, camera_model, radii_d, conics_d, comps_d,
-            d_means2d, d_depths, d_conics, d_comps, ctx.needs_input_grad[4])
+            call("gsb200_projection_packed_bwd", C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks),
+                 width, height, eps2d, _CAMERA_MODELS[camera_model], ptr(block_offsets), ptr(gaussian_ids), ptr(conics),
+                 ptr(comps), ptr(_f32(v_means2d.contiguous())), ptr(_f32(v_depths.contiguous())),
+                 ptr(_f32(v_conics.contiguous())), ptr(None if v_comps is None else _f32(v_comps.contiguous())),
+                 ptr(v_means), ptr(v_covars), ptr(v_quats), ptr(v_scales), ptr(v_viewmats), stream_ptr(dev))
 
         def out(t, need):
             if t is None or not need:

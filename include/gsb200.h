@@ -67,6 +67,41 @@ int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means, const floa
                           float *v_covars, float *v_quats, float *v_scales, float *v_viewmats,
                           gsb200_stream_t stream);
 
+/* Packed (COO) projection, replaces _C.fully_fused_projection_packed_fwd / _bwd (bindings.h:253-309,
+ * fully_fused_projection_packed_fwd.cu:200-247, _packed_bwd.cu:201-283) with memory proportional to nnz -- nothing of size
+ * C*N is allocated.  Two passes, as in the reference: _count projects every (camera, Gaussian) pair and only counts the
+ * visible ones per (camera, 256-Gaussian block), leaves the exclusive scan of those counts in block_offsets
+ * (i32 [C * ceil(N/256) + 1 + ceil(C * ceil(N/256) / 2048) + 3], the total at index C * ceil(N/256)) and returns nnz to
+ * the host (synchronises `stream`); _fill projects again and writes the rows in (camera, Gaussian) order: indptr i32 [C+1],
+ * camera_ids / gaussian_ids i64 [nnz], radii i32 [nnz], means2d [nnz,2], depths [nnz], conics [nnz,3], compensations
+ * [nnz] or NULL.  The packed radius rule (fully_fused_projection_packed_fwd.cu:183-186) applies.
+ * _bwd: conics / compensations / v_* are the packed rows; gradients come back dense ([N,3], [N,6] | [N,4] + [N,3], [C,4,4])
+ * summed over cameras by the thread that owns the Gaussian -- no atomics, no dense scatter of the incoming gradients. */
+int gsb200_projection_packed_count(uint32_t C, uint32_t N, const float *means, const float *covars,
+                                   const float *quats, const float *scales, const float *viewmats,
+                                   const float *Ks, uint32_t image_width, uint32_t image_height,
+                                   float eps2d, float near_plane, float far_plane, float radius_clip,
+                                   int camera_model, int32_t *block_offsets, int64_t *nnz_host,
+                                   gsb200_stream_t stream);
+int gsb200_projection_packed_fill(uint32_t C, uint32_t N, const float *means, const float *covars,
+                                  const float *quats, const float *scales, const float *viewmats,
+                                  const float *Ks, uint32_t image_width, uint32_t image_height,
+                                  float eps2d, float near_plane, float far_plane, float radius_clip,
+                                  int camera_model, const int32_t *block_offsets, int32_t *indptr,
+                                  int64_t *camera_ids, int64_t *gaussian_ids, int32_t *radii,
+                                  float *means2d, float *depths, float *conics, float *compensations,
+                                  gsb200_stream_t stream);
+int gsb200_projection_packed_bwd(uint32_t C, uint32_t N, const float *means, const float *covars,
+                                 const float *quats, const float *scales, const float *viewmats,
+                                 const float *Ks, uint32_t image_width, uint32_t image_height,
+                                 float eps2d, int camera_model, const int32_t *block_offsets,
+                                 const int64_t *gaussian_ids, const float *conics,
+                                 const float *compensations, const float *v_means2d,
+                                 const float *v_depths, const float *v_conics,
+                                 const float *v_compensations, float *v_means, float *v_covars,
+                                 float *v_quats, float *v_scales, float *v_viewmats,
+                                 gsb200_stream_t stream);
+
 /* packed (COO) projection: replaces _C.fully_fused_projection_packed_fwd
  * (bindings.h:253-276, fully_fused_projection_packed_fwd.cu:22-249).  Two calls:
  *   1. gsb200_compact_count: from dense radii [C,N] count visible pairs; writes block_offsets
@@ -296,6 +331,23 @@ int gsb200_fake_quantize_fwd(int64_t n, float *x, float lo, float hi, int bitwid
 /* v_x = v_y * act'(y) * (mode==0 ? [lo<=x<=hi] : 1) */
 int gsb200_fake_quantize_bwd(int64_t n, const float *x, const float *y, float lo, float hi, int mode,
                              int act, const float *v_y, float *v_x, gsb200_stream_t stream);
+/* All attributes of one simulate_compression() call in ONE launch per direction (same arithmetic per element as the
+ * single-tensor calls above).  fwd reads x / noise (or Philox(seed, offset)), writes y (and, in round mode, the clamped x);
+ * bwd reads x, y, v_y and writes v_x.  Unused pointers of a direction may be NULL. */
+#define GSB200_FQ_MAX_TENSORS 8
+typedef struct {
+    int64_t n; /* elements */
+    float *x;
+    float *y;
+    const float *noise;
+    const float *v_y;
+    float *v_x;
+    uint64_t seed, offset;
+    float lo, hi;
+    int bitwidth, mode, act;
+} gsb200_fq_tensor;
+int gsb200_fake_quantize_multi_fwd(uint32_t n_tensors, const gsb200_fq_tensor *tensors, gsb200_stream_t stream);
+int gsb200_fake_quantize_multi_bwd(uint32_t n_tensors, const gsb200_fq_tensor *tensors, gsb200_stream_t stream);
 
 /* factorized-prior entropy model, replaces Entropy_factorized_optimized_refactor.forward
  * (compression_simulation/entropy_model.py:201-254) incl. its channel-scrambled weight tiling.

@@ -147,6 +147,9 @@ def test_compression_simulation_host_logic_with_stubbed_kernels(monkeypatch):
             return x.abs() * self.w
 
     monkeypatch.setattr(S, "fake_quantize_ste", fake_fq)
+    monkeypatch.setattr(S, "fake_quantize_ste_multi", lambda items: [
+        fake_fq(it["input"], it["lower_bd"], it["upper_bd"], it["bitwidth"], noise=it.get("noise"), activation=it.get("activation"))
+        for it in items])
     monkeypatch.setattr(S, "Entropy_factorized_optimized_refactor", StubModel)
     monkeypatch.setattr(S, "Entropy_gaussian", StubModel)
     g = torch.Generator().manual_seed(0)

@@ -721,9 +721,10 @@ def test_empty_and_degenerate_inputs():
     assert_render_close(ra, ra_o)
 
 
-@pytest.mark.parametrize("tile_size", [8, 16])
+@pytest.mark.parametrize("tile_size", [8, 16, 24, 32])
 def test_per_view_colors_sh_and_tile_sizes(tile_size):
-    """colors given per camera ([C,N,D] and [C,N,K,3]) and a non-default tile size."""
+    """colors given per camera ([C,N,D] and [C,N,K,3]) and non-default tile sizes, up to the 32 x 32 = 1024-thread
+    tiles the reference's launch (rasterize_to_pixels_fwd.cu:228) allows."""
     means, quats, scales, opac, colors, viewmats, Ks, W, H = _scene(C=2, width=200, height=136)
     sel = slice(0, None, 5)
     means, quats, scales, opac, colors = [t[sel].contiguous() for t in (means, quats, scales, opac, colors)]

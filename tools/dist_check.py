@@ -60,6 +60,28 @@ def main():
         ok = ok and rel < 2e-3
         if rank == 0:
             print(f"grad {name}: rel err {rel:.2e}")
+    # SH degree 3 with the trainers' two coefficient tensors handed over as the pair (sh0, shN): published side by side
+    # in the peer buffer (no concatenation), gradients returned per tensor
+    g2 = torch.Generator(device="cpu").manual_seed(7)
+    sh0_all = ((colors - 0.5) / 0.2820947917738781)[:, None, :].contiguous()
+    shN_all = (torch.randn(means.shape[0], 15, 3, generator=g2) * 0.1).to(dev)
+    full_sh = [padded_full(means, float("nan")), padded_full(quats, 0.0), padded_full(scales, 0.0), padded_full(opac, 0.0),
+               padded_full(torch.cat([sh0_all, shN_all], 1), 0.0)]
+    rc_f, _, _ = gs.rasterization(*full_sh, vm, K, W, H, sh_degree=3, packed=False)
+    (rc_f * w).sum().backward()
+    sh = [t[rank::world].clone().contiguous().requires_grad_(True) for t in (means, quats, scales, opac, sh0_all, shN_all)]
+    rc_d, _, _ = gs.rasterization(sh[0], sh[1], sh[2], sh[3], (sh[4], sh[5]), vm, K, W, H, sh_degree=3, packed=False, distributed=True)
+    (rc_d * w).sum().backward()
+    err_sh = (rc_d - rc_f).abs().max().item()
+    ok = ok and err_sh < 2e-4
+    tot = full_sh[4].grad.clone()
+    dist.all_reduce(tot)
+    exp = tot[lo:lo + counts[rank]]
+    for name, got, want in (("sh0", sh[4].grad, exp[:, :1]), ("shN", sh[5].grad, exp[:, 1:])):
+        rel = (got - want).abs().max().item() / max(want.abs().max().item(), 1e-12)
+        ok = ok and rel < 2e-3
+        if rank == 0:
+            print(f"grad {name} (pair, SH deg 3): rel err {rel:.2e}; image max abs err {err_sh:.2e}")
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

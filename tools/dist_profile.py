@@ -13,6 +13,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import gscodec_studio_b200 as gs  # noqa: E402
 from gscodec_studio_b200.compression_simulation import CompressionSimulation  # noqa: E402
+from gscodec_studio_b200.losses import photometric_loss  # noqa: E402
 
 
 def main():
@@ -29,11 +30,11 @@ def main():
         for p in params.values():
             p.grad = None
         new, _ = sim.simulate_compression(params, 100, fuse_activations=True)
-        colors = torch.cat([new["sh0"], new["shN"]], 1)
+        colors = (new["sh0"], new["shN"])
         rc, _, _ = gs.rasterization(new["means"], new["quats"], new["scales_act"], new["opacities_act"], colors, viewmat, K,
                                     bench.W_IMG, bench.H_IMG, sh_degree=3, packed=False, near_plane=0.01, far_plane=100.0,
                                     radius_clip=3.0, distributed=world > 1)
-        (rc - target).abs().mean().backward()
+        photometric_loss(rc, target, ssim_lambda=0.0).backward()
 
     for _ in range(5):
         step()
