@@ -36,12 +36,18 @@ def _deps_mtime() -> float:
 
 
 EXTRA_FLAGS = [f for f in os.environ.get("GSB200_NVCC_EXTRA", "").split() if f]
+# quant.cu is compiled WITHOUT --use_fast_math: its fused exp / sigmoid must return torch.exp / torch.sigmoid's bits (libdevice
+# expf, IEEE division), so that the activated scales / opacities -- hence conics, tile lists and every alpha >= 1/255
+# decision -- equal the reference trainer's from the RAW parameters; the entropy-model kernels in the same file spell their
+# fast intrinsics out (__expf) and are unaffected
+NO_FAST_MATH = {"quant.cu"}
 
 
 def _compile(src: str) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     log = obj + ".log"
-    cmd = [_nvcc(), *NVCC_FLAGS, *EXTRA_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    flags = [f for f in NVCC_FLAGS if not (src in NO_FAST_MATH and f == "--use_fast_math")]
+    cmd = [_nvcc(), *flags, *EXTRA_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
     with open(log, "w") as fh:
         rc = subprocess.call(cmd, stdout=fh, stderr=subprocess.STDOUT)
     if rc != 0:

@@ -49,6 +49,7 @@ class PeerWorkspace:
          [ geometry block     cap_block x GEO_WIDTH ]    this rank's published geometry rows (packed [n_block, w])
          [ gradient staging   world x cap_block x row_floats ]   slot [p] is written by rank p (push)
          [ row flags          world x cap_block (int32) ]
+         [ geometry-gradient staging   world x cap_block x GEO_WIDTH ]   slot [p] is written by rank p (push)
     Every rank uses the same capacities, so a region sits at the same offset in every peer's buffer."""
 
     def __init__(self, device: torch.device, row_floats: int, cap_block: int):
@@ -60,7 +61,8 @@ class PeerWorkspace:
         n_geo = cap_block * GEO_WIDTH
         n_stage = self.world * cap_block * row_floats
         n_flags = self.world * cap_block
-        self.buf = symm_mem.empty(n_coeff + n_geo + n_stage + n_flags, dtype=torch.float32, device=device)
+        n_gstage = self.world * cap_block * GEO_WIDTH  # geometry-gradient staging: slot [p] is written by rank p
+        self.buf = symm_mem.empty(n_coeff + n_geo + n_stage + n_flags + n_gstage, dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(ptrs) == self.world and all(p % 16 == 0 for p in ptrs), ptrs
@@ -68,7 +70,10 @@ class PeerWorkspace:
         self.coeff = self.buf[:o_geo].view(cap_block, row_floats)
         self.geo = self.buf[o_geo:o_stage]
         self.staging = self.buf[o_stage:o_flags]
-        self.flags = self.buf[o_flags:].view(torch.int32)
+        o_gstage = o_flags + n_flags
+        self.flags = self.buf[o_flags:o_gstage].view(torch.int32)
+        self.geo_staging = self.buf[o_gstage:]
+        self._gstage_tab = _ptr_table(ptrs, 4 * o_gstage)
         self._coeff_tab = _ptr_table(ptrs, 0)
         self._geo_tab = _ptr_table(ptrs, 4 * o_geo)
         self._stage_tab = _ptr_table(ptrs, 4 * o_stage)
@@ -110,6 +115,7 @@ class PeerWorkspace:
     geo_table = property(lambda self: self._geo_tab[1])
     stage_table = property(lambda self: self._stage_tab[1])
     flag_table = property(lambda self: self._flag_tab[1])
+    geo_stage_table = property(lambda self: self._gstage_tab[1])
 
 
 def workspace(device: torch.device, row_floats: int, n_block: int) -> PeerWorkspace:
@@ -201,33 +207,58 @@ class _ShViewSharded(torch.autograd.Function):
         return None, v_means, v_campos, v_first, v_rest, None, None, None
 
 
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+def _u32_array(values):
+    arr = (ctypes.c_uint32 * len(values))(*values)
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
 class _GatherGeometry(torch.autograd.Function):
-    """Gathered geometry [world * n_block, w] from the published blocks (pull kernel); the backward is the NCCL
-    reduce-scatter of the (dense) geometry gradients to their owners."""
+    """The attribute tensors of the gathered set ([world * n_block, w_k] each) straight from the published blocks (one
+    pull kernel, no gathered [N, w] intermediate and no column-split copies).  Backward: every rank pushes each owner's
+    gradient rows into that owner's staging slot over NVLink, one barrier, every owner sums its slots in rank order."""
 
     @staticmethod
     def forward(ctx, ws, n_block, *geo_parts):
-        w = sum(t.shape[1] for t in geo_parts)
+        widths = [t.shape[1] for t in geo_parts]
         dev = geo_parts[0].device
-        out = torch.empty((ws.world * n_block, w), dtype=torch.float32, device=dev)
+        outs = [torch.empty((ws.world * n_block, w), dtype=torch.float32, device=dev) for w in widths]
+        keep_w, w_ptr = _u32_array(widths)
+        keep_o, o_ptr = _ptr_array(outs)
         with torch.cuda.device(dev):
-            call("gsb200_shard_gather_rows", ws.world, n_block * w, ws.geo_table, ptr(out), stream_ptr(dev))
+            call("gsb200_shard_gather_geo", ws.world, n_block, len(widths), w_ptr, ws.geo_table, o_ptr, stream_ptr(dev))
         ws.readers = True
-        ctx.n_block, ctx.n_local, ctx.widths = n_block, geo_parts[0].shape[0], [t.shape[1] for t in geo_parts]
-        return out
+        ctx.ws, ctx.n_block, ctx.n_local, ctx.widths, ctx.dev = ws, n_block, geo_parts[0].shape[0], widths, dev
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, v_out):
-        v_out = v_out.contiguous()
-        recv = torch.empty((ctx.n_block, v_out.shape[1]), dtype=v_out.dtype, device=v_out.device)
-        dist.reduce_scatter_tensor(recv, v_out, op=dist.ReduceOp.SUM)
-        return (None, None) + tuple(torch.split(recv[: ctx.n_local], ctx.widths, dim=1))
+    def backward(ctx, *v_outs):
+        ws, n_block, widths, dev = ctx.ws, ctx.n_block, ctx.widths, ctx.dev
+        grads = [None if g is None else g.contiguous() for g in v_outs]
+        outs = [torch.empty((ctx.n_local, w), dtype=torch.float32, device=dev) if ctx.needs_input_grad[2 + k] else None
+                for k, w in enumerate(widths)]
+        keep_w, w_ptr = _u32_array(widths)
+        keep_g, g_ptr = _ptr_array(grads)
+        keep_o, o_ptr = _ptr_array(outs)
+        with torch.cuda.device(dev):
+            call("gsb200_shard_push_geo", ws.world, n_block, ws.rank, GEO_WIDTH, len(widths), w_ptr, g_ptr, ws.geo_stage_table,
+                 stream_ptr(dev))
+            ws.barrier()  # every rank's rows have landed in every owner's staging
+            call("gsb200_shard_reduce_geo", ws.world, n_block, ctx.n_local, GEO_WIDTH, len(widths), w_ptr, ptr(ws.geo_staging),
+                 o_ptr, stream_ptr(dev))
+            # the staging area is next written in the next step's backward, after that step's publish barrier
+        return (None, None) + tuple(outs)
 
 
 def publish_and_gather_geometry(geo_parts: Sequence[Tensor], pad_row: Tensor, coeffs_local: Tensor, n_block: int):
     """Start of a distributed render: publish this rank's geometry rows and SH rows (one barrier), pull everybody's
-    geometry.  Returns (gathered geometry [world * n_block, w] -- differentiable w.r.t. geo_parts --, version token to
-    hand to view_colors_from_sh_sharded).  n_block must be a multiple of 4 and >= every rank's row count."""
+    geometry.  Returns (tuple of the gathered attribute tensors [world * n_block, w_k] -- differentiable w.r.t. geo_parts
+    --, version token to hand to view_colors_from_sh_sharded).  n_block must be a multiple of 4 and >= every rank's row
+    count."""
     assert n_block % 4 == 0, n_block
     pair = isinstance(coeffs_local, (tuple, list))
     dev = coeffs_local[0].device if pair else coeffs_local.device

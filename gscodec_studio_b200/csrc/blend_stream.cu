@@ -25,7 +25,7 @@ namespace gsb200 {
 
 constexpr int kStageRecs = 64;  // records per pipeline stage
 #ifndef GSB_STREAM_STAGES
-#define GSB_STREAM_STAGES 4
+#define GSB_STREAM_STAGES 6
 #endif
 constexpr int kStages = GSB_STREAM_STAGES;
 #ifndef GSB_SFWD_BLOCKS
@@ -150,6 +150,7 @@ struct StreamShared {
     int done;        // consumer warps that need no more records (forward)
     int last_stage;  // last stage in which any pixel of the tile took a contribution (forward)
     int emitted;     // records the producer emitted (forward)
+    int finished;    // warps that have left their loop (forward): the last one publishes the tile's record count
 };
 
 // pixel pair p of warp w: block b = w * NP + p at (b & 1, b >> 1) * 8; lane -> column lane & 7, rows lane >> 3 and + 4
@@ -214,6 +215,7 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
         S.done = 0;
         S.last_stage = -1;
         S.emitted = 0;
+        S.finished = 0;
         fence_barrier_init();
     }
     __syncthreads();
@@ -437,10 +439,17 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
             }
         }
     }
-    __syncthreads();
-    // the backward needs the stream up to the last stage that contributed to any pixel
-    if (tid == 0 && tile_counts != nullptr)
-        tile_counts[ct] = min(S.emitted, (S.last_stage + 1) * kStageRecs);
+    // the backward needs the stream up to the last stage that contributed to any pixel.  No block barrier here: warps leave
+    // as they finish and the LAST one to arrive (it sees every other warp's S.emitted / S.last_stage update) writes the count
+    __syncwarp();
+    if (lane == 0 && tile_counts != nullptr) {
+        __threadfence_block();
+        if (atomicAdd(&S.finished, 1) == (int)NCONS) {
+            __threadfence_block();
+            const int emitted = *reinterpret_cast<volatile int *>(&S.emitted), last = *reinterpret_cast<volatile int *>(&S.last_stage);
+            tile_counts[ct] = min(emitted, (last + 1) * kStageRecs);
+        }
+    }
 }
 
 // --------------------------------------------------------------------------------------------- backward
@@ -494,7 +503,7 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
     // ---------------------------------------------------------------------- consumer warps
     float px[NP];
     float2 npy[NP], T[NP], Tfin[NP], v_a[NP], bg_dot[NP];
-    float2 buffer[NP][CDIM], v_c[NP][CDIM];
+    float2 Bsum[NP], v_c[NP][CDIM];
     int32_t bin0[NP], bin1[NP];
     int32_t warp_bin = -1;
 #pragma unroll
@@ -509,9 +518,9 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
         T[p] = Tfin[p];
         v_a[p] = make_float2(in0 ? v_render_alphas[pix0] : 0.f, in1 ? v_render_alphas[pix1] : 0.f);
         bg_dot[p] = make_float2(0.f, 0.f);
+        Bsum[p] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < CDIM; ++k) {
-            buffer[p][k] = make_float2(0.f, 0.f);
             v_c[p][k] = make_float2(in0 ? v_render_colors[pix0 * CDIM + k] : 0.f, in1 ? v_render_colors[pix1 * CDIM + k] : 0.f);
             if (bg) bg_dot[p] = __ffma2_rn(bc(bg[k]), v_c[p][k], bg_dot[p]);
         }
@@ -580,15 +589,18 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                         float2 fac = __fmul2_rn(alpha, Tn);
                         fac.x = valid0 ? fac.x : 0.f;
                         fac.y = valid1 ? fac.y : 0.f;
-                        float2 v_alpha = make_float2(0.f, 0.f);
+                        // sum_k (c_k T - buffer_k ra) v_k  =  T * A - ra * B  with A = sum_k c_k v_k and B = sum_k buffer_k v_k;
+                        // buffer_k only ever enters through B, and buffer_k += c_k fac means B += fac * A: one running
+                        // scalar per pixel instead of CDIM accumulated colours (rasterize_to_pixels_bwd.cu:211-216)
+                        float2 A2 = __fmul2_rn(bc(cs[0]), v_c[p][0]);
+#pragma unroll
+                        for (int k = 1; k < CDIM; ++k) A2 = __ffma2_rn(bc(cs[k]), v_c[p][k], A2);
+                        float2 v_alpha = __ffma2_rn(Tn, A2, __fmul2_rn(nra, Bsum[p]));
+                        Bsum[p] = __ffma2_rn(fac, A2, Bsum[p]);
 #pragma unroll
                         for (int k = 0; k < CDIM; ++k) {
                             const float2 gk = __fmul2_rn(fac, v_c[p][k]);
                             acc<NP == 1>(vals[k], gk.x + gk.y);
-                            const float2 nbr = __fmul2_rn(buffer[p][k], nra);  // -(buffer * ra)
-                            const float2 diff = __ffma2_rn(bc(cs[k]), Tn, nbr);
-                            v_alpha = k == 0 ? __fmul2_rn(diff, v_c[p][k]) : __ffma2_rn(diff, v_c[p][k], v_alpha);
-                            buffer[p][k] = __ffma2_rn(bc(cs[k]), fac, buffer[p][k]);
                         }
                         v_alpha = __ffma2_rn(__fmul2_rn(Tfin[p], ra), v_a[p], v_alpha);
                         if (bg) v_alpha = __ffma2_rn(__fmul2_rn(Tfin[p], nra), bg_dot[p], v_alpha);

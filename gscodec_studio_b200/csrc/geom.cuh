@@ -58,6 +58,27 @@ __device__ __forceinline__ Sym3 covar_to_cam(const float *R /*3x4 rows*/, const 
     return O;
 }
 
+// Same product keeping all nine entries: (R Sigma) R^T is symmetric in exact arithmetic but NOT bit for bit -- entry (i, j)
+// is sum_k A(i,k) R(j,k) and (j, i) is sum_k A(j,k) R(i,k).  The reference's glm products carry the full matrix into the
+// projection (transform.cuh:40-49, type_mat3x3.inl:529-541), so the forward does too: conics then match the reference's
+// in every bit, which keeps the alpha >= 1/255 / transmittance decisions of the blend identical from the RAW parameters.
+__device__ __forceinline__ Mat3 covar_to_cam_full(const float *R /*3x4 rows*/, const Sym3 &S) {
+    float A[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float r0 = R[i * 4 + 0], r1 = R[i * 4 + 1], r2 = R[i * 4 + 2];
+        A[i][0] = r0 * S.xx + r1 * S.xy + r2 * S.xz;
+        A[i][1] = r0 * S.xy + r1 * S.yy + r2 * S.yz;
+        A[i][2] = r0 * S.xz + r1 * S.yz + r2 * S.zz;
+    }
+    Mat3 O;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) O.m[i][j] = A[i][0] * R[j * 4 + 0] + A[i][1] * R[j * 4 + 1] + A[i][2] * R[j * 4 + 2];
+    return O;
+}
+
 // Forward-mode dual number over (x, y, z): used to differentiate the fisheye projection exactly as written
 // (the reference hand-expands the same derivatives, proj.cuh:244-362).
 struct Dual3 {
@@ -158,6 +179,20 @@ __device__ __forceinline__ void project_covar(const CamProj &P, const Sym3 &S, f
     c00 = B00 * P.J[0][0] + B01 * P.J[0][1] + B02 * P.J[0][2];
     c01 = B00 * P.J[1][0] + B01 * P.J[1][1] + B02 * P.J[1][2];
     c11 = B10 * P.J[1][0] + B11 * P.J[1][1] + B12 * P.J[1][2];
+}
+
+// cov2d = (J Sigma_c) J^T with the full Sigma_c, all four entries (type_mat3x2.inl:451-486): c01 = (row 0, col 1),
+// c10 = (row 1, col 0)
+__device__ __forceinline__ void project_covar_full(const CamProj &P, const Mat3 &C, float &c00, float &c01, float &c10, float &c11) {
+    float T[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) T[r][j] = P.J[r][0] * C.m[0][j] + P.J[r][1] * C.m[1][j] + P.J[r][2] * C.m[2][j];
+    c00 = T[0][0] * P.J[0][0] + T[0][1] * P.J[0][1] + T[0][2] * P.J[0][2];
+    c10 = T[1][0] * P.J[0][0] + T[1][1] * P.J[0][1] + T[1][2] * P.J[0][2];
+    c01 = T[0][0] * P.J[1][0] + T[0][1] * P.J[1][1] + T[0][2] * P.J[1][2];
+    c11 = T[1][0] * P.J[1][0] + T[1][1] * P.J[1][1] + T[1][2] * P.J[1][2];
 }
 
 }  // namespace gsb200

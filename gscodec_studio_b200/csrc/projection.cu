@@ -77,13 +77,14 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                                                   __ldg(scales + (size_t)g * 3 + 2));
                     }
                 }
-                Sym3 Sc = covar_to_cam(R, S);
+                const Mat3 Sc = covar_to_cam_full(R, S);
                 CamProj P = project_point(model, mx, my, mz, s_k[ci][0], s_k[ci][1], s_k[ci][2], s_k[ci][3], W, H);
-                float c00, c01, c11;
-                project_covar(P, Sc, c00, c01, c11);
-                float det_orig = c00 * c11 - c01 * c01;
+                float c00, c01, c10, c11;
+                project_covar_full(P, Sc, c00, c01, c10, c11);
+                // utils.cuh:32-40 and :8-21 with glm's [column][row] indexing: M[0][1] is (row 1, col 0)
+                float det_orig = c00 * c11 - c10 * c01;
                 c00 += eps2d; c11 += eps2d;
-                float det = c00 * c11 - c01 * c01;
+                float det = c00 * c11 - c10 * c01;
                 float compensation = sqrtf(fmaxf(0.f, det_orig / det));
                 if (det > 0.f) {
                     float inv_det = 1.f / det;
@@ -101,7 +102,7 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                     if (ok) {
                         rad = (int32_t)radius;
                         o_mx = P.mx; o_my = P.my; o_d = mz;
-                        o_a = c11 * inv_det; o_b = -c01 * inv_det; o_c = c00 * inv_det;
+                        o_a = c11 * inv_det; o_b = -c10 * inv_det; o_c = c00 * inv_det;
                         o_comp = compensation;
                     }
                 }

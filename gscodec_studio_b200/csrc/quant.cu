@@ -32,9 +32,11 @@ __device__ __forceinline__ float u01_centered(uint32_t r) {  // uniform in (-0.5
     return ((float)(r >> 8) + 0.5f) * (1.f / 16777216.f) - 0.5f;
 }
 
+// the activations the trainer applies next (examples/simple_trainer.py:758-776), with torch.exp / torch.sigmoid's exact
+// arithmetic -- libdevice expf and an IEEE division; this file is built without --use_fast_math (see _build.py)
 __device__ __forceinline__ float activate(int act, float v) {
-    if (act == 1) return __expf(v);
-    if (act == 2) return 1.f / (1.f + __expf(-v));
+    if (act == 1) return expf(v);
+    if (act == 2) return 1.f / (1.f + expf(-v));
     return v;
 }
 

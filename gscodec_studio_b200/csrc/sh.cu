@@ -534,6 +534,67 @@ shard_gather_rows_kernel(uint64_t block_vec4, const BlockShards blocks, float *_
         if (i0 + u * kThreads < block_vec4) stg4(dst + (i0 + u * kThreads) * 4, v[u]);
 }
 
+
+// ---- geometry exchange over peer memory: gather-and-split forward, push + owner-side reduce backward ------------------------
+// The published geometry block of every rank is [n_block, w] (means | quats | scales | opacity, or means | covars |
+// opacity).  The forward pulls all blocks and writes the attribute tensors of the gathered set directly (no gathered
+// [N, w] intermediate, no column-split copies); the backward pushes each owner's rows of the attribute gradients into that
+// owner's staging slot [source rank][row][w] (posted NVLink stores, 4-byte coalesced), and after a barrier every owner sums
+// its world slots in rank order -- replaces torch.cat + ncclReduceScatter on a padded [N, w] tensor.
+struct GeoParts {
+    float *ptr[4];
+    uint32_t width[4], col0[4];  // part k holds columns [col0, col0 + width)
+    uint32_t n_parts, w;
+};
+struct PeerRows {
+    float *base[kMaxShards];
+};
+
+__device__ __forceinline__ void geo_locate(const GeoParts &P, uint32_t col, uint32_t &part, uint32_t &c) {
+    part = 0;
+#pragma unroll
+    for (uint32_t k = 1; k < 4; ++k)
+        if (k < P.n_parts && col >= P.col0[k]) part = k;
+    c = col - P.col0[part];
+}
+
+__global__ void __launch_bounds__(kThreads)
+shard_gather_geo_kernel(uint32_t n_block, const BlockShards blocks, const __grid_constant__ GeoParts out) {
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;  // element of the peer's [n_block, w] block
+    if (i >= (uint64_t)n_block * out.w) return;
+    const uint32_t p = blockIdx.y, row = (uint32_t)(i / out.w), col = (uint32_t)(i % out.w);
+    uint32_t part, c;
+    geo_locate(out, col, part, c);
+    out.ptr[part][((size_t)p * n_block + row) * out.width[part] + c] = __ldg(blocks.base[p] + i);
+}
+
+__global__ void __launch_bounds__(kThreads)
+shard_push_geo_kernel(uint32_t n_block, uint32_t rank, uint32_t stage_width, const __grid_constant__ GeoParts grads,
+                      const PeerRows peers) {
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (uint64_t)n_block * grads.w) return;
+    const uint32_t p = blockIdx.y, row = (uint32_t)(i / grads.w), col = (uint32_t)(i % grads.w);
+    uint32_t part, c;
+    geo_locate(grads, col, part, c);
+    const float *src = grads.ptr[part];
+    const float v = src ? src[((size_t)p * n_block + row) * grads.width[part] + c] : 0.f;
+    // owner p's staging: [world][cap rows][stage_width]; this rank writes slot `rank`
+    peers.base[p][((size_t)rank * n_block + row) * stage_width + col] = v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+shard_reduce_geo_kernel(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t stage_width, const float *__restrict__ staging,
+                        const __grid_constant__ GeoParts out) {
+    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= (uint64_t)n_rows * out.w) return;
+    const uint32_t row = (uint32_t)(i / out.w), col = (uint32_t)(i % out.w);
+    float acc = 0.f;
+    for (uint32_t p = 0; p < world; ++p) acc += staging[((size_t)p * n_block + row) * stage_width + col];
+    uint32_t part, c;
+    geo_locate(out, col, part, c);
+    if (out.ptr[part]) out.ptr[part][(size_t)row * out.width[part] + c] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Split-coefficient form of the fused view-colour stage.  The trainers keep the DC band and the higher bands as
 // two parameters, sh0 [N,1,3] and shN [N,K-1,3], and concatenate them every step only to hand one [N,K,3] tensor
@@ -927,6 +988,72 @@ extern "C" int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, c
     const dim3 grid((uint32_t)((block_vec4 + kThreads * 4 - 1) / (kThreads * 4)), world);
     shard_gather_rows_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(block_vec4, sh, out);
     return check_launch("shard_gather_rows");
+}
+
+
+static int geo_parts(const char *who, uint32_t n_parts, float *const *ptrs, const uint32_t *widths, bool need_ptrs, GeoParts &P) {
+    if (n_parts == 0 || n_parts > 4) return failf(2, "%s: 1..4 attribute tensors", who);
+    P = GeoParts{};
+    P.n_parts = n_parts;
+    uint32_t col = 0;
+    for (uint32_t k = 0; k < n_parts; ++k) {
+        if (widths[k] == 0) return failf(2, "%s: zero-width attribute", who);
+        if (need_ptrs && ptrs[k] == nullptr) return failf(2, "%s: null attribute pointer", who);
+        P.ptr[k] = ptrs[k];
+        P.width[k] = widths[k];
+        P.col0[k] = col;
+        col += widths[k];
+    }
+    P.w = col;
+    return 0;
+}
+
+extern "C" int gsb200_shard_gather_geo(uint32_t world, uint32_t n_block, uint32_t n_parts, const uint32_t *widths,
+                                       const float *const *blocks, float *const *outs, gsb200_stream_t stream) {
+    if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "gsb200_shard_gather_geo: world must be in [1, %d]", kMaxShards);
+    GeoParts P;
+    if (int e = geo_parts("gsb200_shard_gather_geo", n_parts, outs, widths, true, P)) return e;
+    if (n_block == 0) return 0;
+    BlockShards sh{};
+    for (uint32_t r = 0; r < world; ++r) {
+        sh.base[r] = blocks[r];
+        if (sh.base[r] == nullptr) return fail(2, "gsb200_shard_gather_geo: null block pointer");
+    }
+    const dim3 grid((uint32_t)(((uint64_t)n_block * P.w + kThreads - 1) / kThreads), world);
+    shard_gather_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, sh, P);
+    return check_launch("shard_gather_geo");
+}
+
+extern "C" int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t rank, uint32_t stage_width, uint32_t n_parts,
+                                     const uint32_t *widths, float *const *grads, float *const *peer_staging,
+                                     gsb200_stream_t stream) {
+    if (world == 0 || world > (uint32_t)kMaxShards || rank >= world)
+        return failf(2, "gsb200_shard_push_geo: world must be in [1, %d] and rank < world", kMaxShards);
+    GeoParts P;
+    if (int e = geo_parts("gsb200_shard_push_geo", n_parts, grads, widths, false, P)) return e;
+    if (P.w > stage_width) return fail(2, "gsb200_shard_push_geo: row wider than the staging rows");
+    if (n_block == 0) return 0;
+    PeerRows peers{};
+    for (uint32_t r = 0; r < world; ++r) {
+        peers.base[r] = peer_staging[r];
+        if (peers.base[r] == nullptr) return fail(2, "gsb200_shard_push_geo: null staging pointer");
+    }
+    const dim3 grid((uint32_t)(((uint64_t)n_block * P.w + kThreads - 1) / kThreads), world);
+    shard_push_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, rank, stage_width, P, peers);
+    return check_launch("shard_push_geo");
+}
+
+extern "C" int gsb200_shard_reduce_geo(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t stage_width, uint32_t n_parts,
+                                       const uint32_t *widths, const float *staging, float *const *outs, gsb200_stream_t stream) {
+    if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "gsb200_shard_reduce_geo: world must be in [1, %d]", kMaxShards);
+    if (n_rows > n_block) return fail(2, "gsb200_shard_reduce_geo: n_rows > n_block");
+    GeoParts P;
+    if (int e = geo_parts("gsb200_shard_reduce_geo", n_parts, outs, widths, false, P)) return e;
+    if (P.w > stage_width || staging == nullptr) return fail(2, "gsb200_shard_reduce_geo: bad staging");
+    if (n_rows == 0) return 0;
+    shard_reduce_geo_kernel<<<(uint32_t)(((uint64_t)n_rows * P.w + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        world, n_block, n_rows, stage_width, staging, P);
+    return check_launch("shard_reduce_geo");
 }
 
 // ---- split-coefficient entry points (sh0 [N,1,3] + shN [N,K-1,3] in place of one [N,K,3] tensor) -------------

@@ -179,13 +179,12 @@ def rasterization(
                                            n_block))
         colors_local = colors
         if pull_colors:
-            gathered_geo, published = _peer.publish_and_gather_geometry(geo_parts, pad_row, colors_local, n_block)
+            geo, published = _peer.publish_and_gather_geometry(geo_parts, pad_row, colors_local, n_block)
             pending_colors = None
         else:
             pending_geo = start_gather(torch.cat(geo_parts, dim=1), counts, keep_padding=True, pad_row=pad_row)
             pending_colors = start_gather(colors, counts, keep_padding=True)
-            gathered_geo = pending_geo.finish()
-        geo = torch.split(gathered_geo, widths, dim=1)
+            geo = torch.split(pending_geo.finish(), widths, dim=1)
         means = geo[0]
         if covars is None:
             quats, scales = geo[1], geo[2]

@@ -205,6 +205,23 @@ int gsb200_shard_reduce_rows_split(uint32_t world, uint32_t n_block, uint32_t n_
  * pointers).  Replaces the all-gather of all_gather_tensor_list (distributed.py:102-167) for that tensor. */
 int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float *const *blocks, float *out,
                              gsb200_stream_t stream);
+/* Geometry exchange without the gathered [N, w] intermediate.  A rank's published geometry block is [n_block, w] with the
+ * attribute tensors side by side (means | quats | scales | opacity: widths {3,4,3,1}; or means | covars | opacity).
+ *   _gather_geo : pulls every peer's block and writes the n_parts attribute tensors of the gathered set,
+ *                 outs[k] [world * n_block, widths[k]] (rank r's rows at r * n_block) -- HOST arrays of device pointers.
+ *   _push_geo   : backward, sender side: grads[k] [world * n_block, widths[k]] (NULL = zero gradient); the rows of owner p
+ *                 are stored into p's staging array peer_staging[p] [world, n_block, stage_width] at slot `rank`.
+ *   _reduce_geo : backward, owner side (after a cross-rank barrier): sums the world slots of the local staging array in
+ *                 rank order (reproducible) into outs[k] [n_rows, widths[k]] (NULL = not wanted).
+ * Replaces the reduce-scatter of all_gather_tensor_list's backward (gsplat/distributed.py:102-167) for the geometry. */
+int gsb200_shard_gather_geo(uint32_t world, uint32_t n_block, uint32_t n_parts, const uint32_t *widths,
+                            const float *const *blocks, float *const *outs, gsb200_stream_t stream);
+int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t rank, uint32_t stage_width,
+                          uint32_t n_parts, const uint32_t *widths, float *const *grads,
+                          float *const *peer_staging, gsb200_stream_t stream);
+int gsb200_shard_reduce_geo(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t stage_width,
+                            uint32_t n_parts, const uint32_t *widths, const float *staging,
+                            float *const *outs, gsb200_stream_t stream);
 
 /* ---------------------------------------------------------------- stage 2: tile intersection
  * replaces _C.isect_tiles + _C.isect_offset_encode (bindings.h:147-166, isect_tiles.cu:16-389).  Results are

@@ -278,3 +278,26 @@ def test_policy_tables_and_checkpoint_keys_match_the_reference_fixture():
     assert stg2.entropy_model_option["scales"] and stg2.entropy_model_option["colors"]
     with pytest.raises(KeyError):
         S.CompressionSimulation(entropy_model_enable=True, entropy_steps={"scales": 1}, device="cpu")
+
+
+def test_gsplat_import_shim():
+    """integration/gsplat: `import gsplat` resolves the hot path to this package (the reference's trainers import it
+    unchanged); names outside the hot path raise an ImportError that says so (or come from GSPLAT_REFERENCE_PATH)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import gsplat, gscodec_studio_b200 as g\n"
+        "assert gsplat.rasterization is g.rasterization and gsplat.isect_tiles is g.isect_tiles\n"
+        "from gsplat.rendering import rasterization\n"
+        "from gsplat.compression_simulation import CompressionSimulation, STGCompressionSimulation\n"
+        "from gsplat.compression_simulation.ops import fake_quantize_ste\n"
+        "from gsplat.cuda._wrapper import spherical_harmonics, fully_fused_projection\n"
+        "from gsplat.distributed import cli\n"
+        "from gsplat.relocation import compute_relocation\n"
+        "try:\n    gsplat.rasterization_2dgs\n    raise SystemExit('2DGS must not resolve')\nexcept ImportError as e:\n    assert 'outside' in str(e)\n"
+        "print('shim ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "integration"), ROOT]))
+    env.pop("GSPLAT_REFERENCE_PATH", None)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert out.returncode == 0 and "shim ok" in out.stdout, out.stderr[-2000:]
