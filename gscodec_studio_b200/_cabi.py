@@ -50,8 +50,8 @@ SIGNATURES = {
     "gsb200_sh_view_bwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_shard_reduce_rows": [_U, _U, _U, _U, _P, _P, _P, _P],
     "gsb200_shard_gather_geo": [_U, _U, _U, _P, _P, _P, _P],
-    "gsb200_shard_push_geo": [_U, _U, _U, _U, _U, _P, _P, _P, _P],
-    "gsb200_shard_reduce_geo": [_U, _U, _U, _U, _U, _P, _P, _P, _P],
+    "gsb200_shard_push_geo": [_U, _U, _U, c_uint64, _U, _P, _P, _P, _P],
+    "gsb200_shard_reduce_geo": [_U, _U, _U, c_uint64, _U, _P, _P, _P, _P],
     "gsb200_shard_reduce_rows_split": [_U, _U, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_shard_gather_rows": [_U, c_uint64, _P, _P, _P],
     "gsb200_isect_plan": [_U, _U, _U, _U, _P, _P],

@@ -245,10 +245,11 @@ class _GatherGeometry(torch.autograd.Function):
         keep_g, g_ptr = _ptr_array(grads)
         keep_o, o_ptr = _ptr_array(outs)
         with torch.cuda.device(dev):
-            call("gsb200_shard_push_geo", ws.world, n_block, ws.rank, GEO_WIDTH, len(widths), w_ptr, g_ptr, ws.geo_stage_table,
+            slot = ws.cap_block * GEO_WIDTH  # floats per staging slot (one dense [n_block * w] block each)
+            call("gsb200_shard_push_geo", ws.world, n_block, ws.rank, slot, len(widths), w_ptr, g_ptr, ws.geo_stage_table,
                  stream_ptr(dev))
             ws.barrier()  # every rank's rows have landed in every owner's staging
-            call("gsb200_shard_reduce_geo", ws.world, n_block, ctx.n_local, GEO_WIDTH, len(widths), w_ptr, ptr(ws.geo_staging),
+            call("gsb200_shard_reduce_geo", ws.world, n_block, ctx.n_local, slot, len(widths), w_ptr, ptr(ws.geo_staging),
                  o_ptr, stream_ptr(dev))
             # the staging area is next written in the next step's backward, after that step's publish barrier
         return (None, None) + tuple(outs)

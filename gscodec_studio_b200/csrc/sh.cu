@@ -558,41 +558,85 @@ __device__ __forceinline__ void geo_locate(const GeoParts &P, uint32_t col, uint
     c = col - P.col0[part];
 }
 
+// All three kernels move 16-byte vectors of the dense [rows, w] block / staging layout (the remote side of every access is
+// a coalesced 128-bit load or store, several in flight per thread -- NVLink latency is ~1.8 k cycles) and scatter / gather
+// the 1..4 floats of a vector to / from the attribute tensors locally.
+constexpr int kGeoUnroll = 4;
+
+__device__ __forceinline__ void geo_store4(const GeoParts &P, size_t row_base, uint64_t e0, uint64_t n_elems, float4 v) {
+    uint32_t row = (uint32_t)(e0 / P.w), col = (uint32_t)(e0 % P.w);
+    const float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (e0 + u < n_elems) {
+            uint32_t part, c;
+            geo_locate(P, col, part, c);
+            if (P.ptr[part]) P.ptr[part][(row_base + row) * P.width[part] + c] = vals[u];
+        }
+        if (++col == P.w) { col = 0; ++row; }
+    }
+}
+
+__device__ __forceinline__ float4 geo_load4(const GeoParts &P, size_t row_base, uint64_t e0, uint64_t n_elems) {
+    uint32_t row = (uint32_t)(e0 / P.w), col = (uint32_t)(e0 % P.w);
+    float vals[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (e0 + u < n_elems) {
+            uint32_t part, c;
+            geo_locate(P, col, part, c);
+            if (P.ptr[part]) vals[u] = P.ptr[part][(row_base + row) * P.width[part] + c];
+        }
+        if (++col == P.w) { col = 0; ++row; }
+    }
+    return make_float4(vals[0], vals[1], vals[2], vals[3]);
+}
+
+// gather: peer p's block [n_block * w] (float4 loads over NVLink) -> rows p * n_block.. of the attribute tensors
 __global__ void __launch_bounds__(kThreads)
 shard_gather_geo_kernel(uint32_t n_block, const BlockShards blocks, const __grid_constant__ GeoParts out) {
-    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;  // element of the peer's [n_block, w] block
-    if (i >= (uint64_t)n_block * out.w) return;
-    const uint32_t p = blockIdx.y, row = (uint32_t)(i / out.w), col = (uint32_t)(i % out.w);
-    uint32_t part, c;
-    geo_locate(out, col, part, c);
-    out.ptr[part][((size_t)p * n_block + row) * out.width[part] + c] = __ldg(blocks.base[p] + i);
+    const uint32_t p = blockIdx.y;
+    const uint64_t n_elems = (uint64_t)n_block * out.w, n_vec = (n_elems + 3) / 4;  // (blocks are padded to 16 bytes)
+    const uint64_t i0 = (uint64_t)blockIdx.x * kThreads * kGeoUnroll + threadIdx.x;
+    float4 v[kGeoUnroll];
+#pragma unroll
+    for (int u = 0; u < kGeoUnroll; ++u)
+        if (i0 + (uint64_t)u * kThreads < n_vec) v[u] = ldg4(blocks.base[p] + (i0 + (uint64_t)u * kThreads) * 4);
+#pragma unroll
+    for (int u = 0; u < kGeoUnroll; ++u) {
+        const uint64_t i = i0 + (uint64_t)u * kThreads;
+        if (i < n_vec) geo_store4(out, (size_t)p * n_block, i * 4, n_elems, v[u]);
+    }
 }
 
+// push: rows p * n_block.. of the gradient tensors -> owner p's staging slot `rank` (dense [n_block * w], float4 stores)
 __global__ void __launch_bounds__(kThreads)
-shard_push_geo_kernel(uint32_t n_block, uint32_t rank, uint32_t stage_width, const __grid_constant__ GeoParts grads,
+shard_push_geo_kernel(uint32_t n_block, uint32_t rank, uint64_t slot_floats, const __grid_constant__ GeoParts grads,
                       const PeerRows peers) {
-    const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= (uint64_t)n_block * grads.w) return;
-    const uint32_t p = blockIdx.y, row = (uint32_t)(i / grads.w), col = (uint32_t)(i % grads.w);
-    uint32_t part, c;
-    geo_locate(grads, col, part, c);
-    const float *src = grads.ptr[part];
-    const float v = src ? src[((size_t)p * n_block + row) * grads.width[part] + c] : 0.f;
-    // owner p's staging: [world][cap rows][stage_width]; this rank writes slot `rank`
-    peers.base[p][((size_t)rank * n_block + row) * stage_width + col] = v;
+    const uint32_t p = blockIdx.y;
+    const uint64_t n_elems = (uint64_t)n_block * grads.w, n_vec = (n_elems + 3) / 4;
+    const uint64_t i0 = (uint64_t)blockIdx.x * kThreads * kGeoUnroll + threadIdx.x;
+    float *dst = peers.base[p] + (size_t)rank * slot_floats;
+#pragma unroll
+    for (int u = 0; u < kGeoUnroll; ++u) {
+        const uint64_t i = i0 + (uint64_t)u * kThreads;
+        if (i < n_vec) stg4(dst + i * 4, geo_load4(grads, (size_t)p * n_block, i * 4, n_elems));
+    }
 }
 
+// owner-side reduce: sum of the world slots of the local staging array, in rank order -> the local gradient tensors
 __global__ void __launch_bounds__(kThreads)
-shard_reduce_geo_kernel(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t stage_width, const float *__restrict__ staging,
+shard_reduce_geo_kernel(uint32_t world, uint32_t n_rows, uint64_t slot_floats, const float *__restrict__ staging,
                         const __grid_constant__ GeoParts out) {
+    const uint64_t n_elems = (uint64_t)n_rows * out.w, n_vec = (n_elems + 3) / 4;
     const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= (uint64_t)n_rows * out.w) return;
-    const uint32_t row = (uint32_t)(i / out.w), col = (uint32_t)(i % out.w);
-    float acc = 0.f;
-    for (uint32_t p = 0; p < world; ++p) acc += staging[((size_t)p * n_block + row) * stage_width + col];
-    uint32_t part, c;
-    geo_locate(out, col, part, c);
-    if (out.ptr[part]) out.ptr[part][(size_t)row * out.width[part] + c] = acc;
+    if (i >= n_vec) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t p = 0; p < world; ++p) {
+        const float4 v = ldg4(staging + (size_t)p * slot_floats + i * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    geo_store4(out, 0, i * 4, n_elems, acc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1017,42 +1061,50 @@ extern "C" int gsb200_shard_gather_geo(uint32_t world, uint32_t n_block, uint32_
     BlockShards sh{};
     for (uint32_t r = 0; r < world; ++r) {
         sh.base[r] = blocks[r];
-        if (sh.base[r] == nullptr) return fail(2, "gsb200_shard_gather_geo: null block pointer");
+        if (sh.base[r] == nullptr || (reinterpret_cast<uintptr_t>(sh.base[r]) & 15) != 0)
+            return fail(2, "gsb200_shard_gather_geo: block pointers must be non-null and 16-byte aligned");
     }
-    const dim3 grid((uint32_t)(((uint64_t)n_block * P.w + kThreads - 1) / kThreads), world);
+    const uint64_t n_vec = ((uint64_t)n_block * P.w + 3) / 4;
+    const dim3 grid((uint32_t)((n_vec + kThreads * kGeoUnroll - 1) / (kThreads * kGeoUnroll)), world);
     shard_gather_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, sh, P);
     return check_launch("shard_gather_geo");
 }
 
-extern "C" int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t rank, uint32_t stage_width, uint32_t n_parts,
+extern "C" int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t rank, uint64_t slot_floats, uint32_t n_parts,
                                      const uint32_t *widths, float *const *grads, float *const *peer_staging,
                                      gsb200_stream_t stream) {
     if (world == 0 || world > (uint32_t)kMaxShards || rank >= world)
         return failf(2, "gsb200_shard_push_geo: world must be in [1, %d] and rank < world", kMaxShards);
     GeoParts P;
     if (int e = geo_parts("gsb200_shard_push_geo", n_parts, grads, widths, false, P)) return e;
-    if (P.w > stage_width) return fail(2, "gsb200_shard_push_geo: row wider than the staging rows");
+    if ((uint64_t)n_block * P.w > slot_floats || slot_floats % 4 != 0)
+        return fail(2, "gsb200_shard_push_geo: staging slot too small or not a multiple of 4 floats");
     if (n_block == 0) return 0;
     PeerRows peers{};
     for (uint32_t r = 0; r < world; ++r) {
         peers.base[r] = peer_staging[r];
-        if (peers.base[r] == nullptr) return fail(2, "gsb200_shard_push_geo: null staging pointer");
+        if (peers.base[r] == nullptr || (reinterpret_cast<uintptr_t>(peers.base[r]) & 15) != 0)
+            return fail(2, "gsb200_shard_push_geo: staging pointers must be non-null and 16-byte aligned");
     }
-    const dim3 grid((uint32_t)(((uint64_t)n_block * P.w + kThreads - 1) / kThreads), world);
-    shard_push_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, rank, stage_width, P, peers);
+    const uint64_t n_vec = ((uint64_t)n_block * P.w + 3) / 4;
+    const dim3 grid((uint32_t)((n_vec + kThreads * kGeoUnroll - 1) / (kThreads * kGeoUnroll)), world);
+    shard_push_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, rank, slot_floats, P, peers);
     return check_launch("shard_push_geo");
 }
 
-extern "C" int gsb200_shard_reduce_geo(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t stage_width, uint32_t n_parts,
+extern "C" int gsb200_shard_reduce_geo(uint32_t world, uint32_t n_block, uint32_t n_rows, uint64_t slot_floats, uint32_t n_parts,
                                        const uint32_t *widths, const float *staging, float *const *outs, gsb200_stream_t stream) {
     if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "gsb200_shard_reduce_geo: world must be in [1, %d]", kMaxShards);
     if (n_rows > n_block) return fail(2, "gsb200_shard_reduce_geo: n_rows > n_block");
     GeoParts P;
     if (int e = geo_parts("gsb200_shard_reduce_geo", n_parts, outs, widths, false, P)) return e;
-    if (P.w > stage_width || staging == nullptr) return fail(2, "gsb200_shard_reduce_geo: bad staging");
+    if ((uint64_t)n_block * P.w > slot_floats || slot_floats % 4 != 0 || staging == nullptr ||
+        (reinterpret_cast<uintptr_t>(staging) & 15) != 0)
+        return fail(2, "gsb200_shard_reduce_geo: bad staging");
     if (n_rows == 0) return 0;
-    shard_reduce_geo_kernel<<<(uint32_t)(((uint64_t)n_rows * P.w + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        world, n_block, n_rows, stage_width, staging, P);
+    const uint64_t n_vec = ((uint64_t)n_rows * P.w + 3) / 4;
+    shard_reduce_geo_kernel<<<(uint32_t)((n_vec + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        world, n_rows, slot_floats, staging, P);
     return check_launch("shard_reduce_geo");
 }
 

@@ -210,16 +210,17 @@ int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float 
  *   _gather_geo : pulls every peer's block and writes the n_parts attribute tensors of the gathered set,
  *                 outs[k] [world * n_block, widths[k]] (rank r's rows at r * n_block) -- HOST arrays of device pointers.
  *   _push_geo   : backward, sender side: grads[k] [world * n_block, widths[k]] (NULL = zero gradient); the rows of owner p
- *                 are stored into p's staging array peer_staging[p] [world, n_block, stage_width] at slot `rank`.
+ *                 are stored, as one dense [n_block * w] block, into p's staging array peer_staging[p]
+ *                 [world, slot_floats] at slot `rank` (slot_floats >= n_block * w, a multiple of 4).
  *   _reduce_geo : backward, owner side (after a cross-rank barrier): sums the world slots of the local staging array in
  *                 rank order (reproducible) into outs[k] [n_rows, widths[k]] (NULL = not wanted).
  * Replaces the reduce-scatter of all_gather_tensor_list's backward (gsplat/distributed.py:102-167) for the geometry. */
 int gsb200_shard_gather_geo(uint32_t world, uint32_t n_block, uint32_t n_parts, const uint32_t *widths,
                             const float *const *blocks, float *const *outs, gsb200_stream_t stream);
-int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t rank, uint32_t stage_width,
+int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t rank, uint64_t slot_floats,
                           uint32_t n_parts, const uint32_t *widths, float *const *grads,
                           float *const *peer_staging, gsb200_stream_t stream);
-int gsb200_shard_reduce_geo(uint32_t world, uint32_t n_block, uint32_t n_rows, uint32_t stage_width,
+int gsb200_shard_reduce_geo(uint32_t world, uint32_t n_block, uint32_t n_rows, uint64_t slot_floats,
                             uint32_t n_parts, const uint32_t *widths, const float *staging,
                             float *const *outs, gsb200_stream_t stream);
 

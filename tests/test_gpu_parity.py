@@ -927,7 +927,8 @@ def test_headline_m2_step_from_raw_parameters_matches_reference_cuda():
     """One M2 step (1 006 065 Gaussians, 1920x1080, SH degree 3, 8-bit noise fake-quant with injected noise) from the RAW
     trainer parameters, ours against the unmodified reference CUDA kernels driven through the reference's op sequence
     (oracle/ref_pipeline.py): radii / isect_ids / flatten_ids / isect_offsets / tiles_per_gauss EQUAL, RGB and alpha
-    <= 1e-4, gradients of means / scales / quats / opacities / sh0 / shN <= 1e-3 (max-normalised and per element)."""
+    <= 1e-4 on every pixel, gradients of means / scales / quats / opacities / sh0 / shN <= 1e-3 (max-normalised, and per
+    element with rtol = 1e-3, atol = 1e-3 * median |ref| for all but <= 5e-5 of the entries)."""
     from oracle import ref_pipeline as RP
 
     ref = RP.load_ref()
@@ -958,13 +959,11 @@ def test_headline_m2_step_from_raw_parameters_matches_reference_cuda():
     assert torch.equal(meta["isect_ids"], out["isect_ids"]) and torch.equal(meta["flatten_ids"], out["flatten_ids"])
     assert torch.equal(meta["isect_offsets"], out["isect_offsets"])
     assert meta["isect_ids"].numel() > 3_500_000
-    # Same tile lists, same depth order.  The conics of the two projections agree to ~1e-7 but not in every last bit
-    # (symmetric-matrix products here, full glm products there), so a handful of borderline (pixel, Gaussian) pairs --
-    # alpha within an ulp of 1/255 -- fall on the other side of the reference's own discontinuity: RGB / alpha
-    # <= 1e-4 on all but <= 5e-5 of the pixels, those bounded by one pair's weight (see assert_render_close); fed
-    # with IDENTICAL stage-1 outputs the two blends are bit-identical (test_full_size_properties_1080p_1m).
-    assert_render_close(rc, out["render_colors"])
-    assert_render_close(ra, out["render_alphas"])
+    # Same tile lists, same depth order, and -- since the projection forward keeps the reference's full (non-symmetrised)
+    # covariance products and the fused exp / sigmoid are torch's -- the same conics and opacities bit for bit, so every
+    # alpha >= 1/255 / transmittance decision of the blend is the reference's: RGB and alpha within 1e-4 on EVERY pixel
+    # (measured: 0 pixels beyond 1e-4, max 2.4e-7; only the SH evaluation differs in its last bits).
+    assert rel_err(rc, out["render_colors"]) < 1e-4 and rel_err(ra, out["render_alphas"]) < 1e-4
     frac = ((rc - out["render_colors"]).abs().amax(-1) > 1e-4 * out["render_colors"].abs().max()).float().mean().item()
     print(f"headline from raw parameters: {frac:.2e} of the pixels differ by more than 1e-4 (max rel "
           f"{rel_err(rc, out['render_colors']):.2e})")
@@ -978,5 +977,5 @@ def test_headline_m2_step_from_raw_parameters_matches_reference_cuda():
         floor, _ = elementwise_fail_fraction(again[k].grad, theirs[k].grad)
         print(f"grad {k}: {frac:.2e} of the entries outside rtol=1e-3 + atol={atol:.1e} (reference vs itself: {floor:.2e}); "
               f"max-normalised error {rel_err(ours[k].grad, theirs[k].grad):.2e}")
-        # per element: all but a vanishing fraction (heavily cancelling sums, owners of a flipped borderline pair)
-        assert frac <= max(5e-4, 3 * floor), k
+        # per element: all but a vanishing fraction, at the level of the reference's own run-to-run noise (float atomics)
+        assert frac <= max(5e-5, 3 * floor), k

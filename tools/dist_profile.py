@@ -48,7 +48,7 @@ def main():
         evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
         evs.sort(key=lambda e: e.time_range.start)
         # keep the middle step: split at the first fake-quant kernel of each step
-        starts = [i for i, e in enumerate(evs) if "fake_quantize_fwd" in e.name]
+        starts = [i for i, e in enumerate(evs) if "fake_quantize" in e.name and "fwd" in e.name]
         per_step = len(starts) // 3
         lo, hi = starts[per_step], starts[2 * per_step]
         t0 = evs[lo].time_range.start
