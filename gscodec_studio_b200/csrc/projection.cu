@@ -64,7 +64,9 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
             float mz = R[8] * px + R[9] * py + R[10] * pz + R[11];
             int32_t rad = 0;
             float o_mx = 0.f, o_my = 0.f, o_d = 0.f, o_a = 0.f, o_b = 0.f, o_c = 0.f, o_comp = 0.f;
-            if (g < N && !(mz < near_plane || mz > far_plane)) {
+            // (written so that a NaN depth -- the inert padding splats of ragged distributed shards -- is culled for every
+            // camera model; equivalent to the reference's `z < near || z > far` test for every other value)
+            if (g < N && mz >= near_plane && mz <= far_plane) {
                 if (!have_S) {
                     have_S = true;
                     if (covars != nullptr) {

@@ -606,7 +606,9 @@ def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, til
     call("gsb200_isect_plan", C, n_elems, tile_width, tile_height, ctypes.byref(n_scratch), ctypes.byref(total_at))
     tile_cursor = torch.empty(int(n_scratch.value), dtype=torch.int32, device=dev)
     total_index = int(total_at.value)
-    key = (dev.index, C, n_elems, tile_width, tile_height, tile_size)
+    # one rolling capacity per configuration (NOT per element count: in packed mode nnz changes every step, and every
+    # densification changes N -- the previous step's count is still the right guess)
+    key = (dev.index, C, tile_width, tile_height, tile_size, bool(packed))
     capacity = _isect_capacity.get(key)
 
     def prepare(n_host_ref):
