@@ -289,6 +289,240 @@ tile_sort_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, i
     }
 }
 
+// ---- default short-segment sort: per-tile depth buckets + rank by counting ------------------------------------------------
+// The bitonic network above spends ~860 lane-instructions per key.  A tile's keys are (depth bits, flatten id) with depths
+// spread between the tile's own nearest and farthest Gaussian, so a linear map of the depth onto ~n/4 buckets (monotone in
+// the depth, hence in the key) leaves a handful of keys per bucket: histogram -> scan -> scatter in shared memory, then
+// every key counts the smaller keys of its own bucket.  Order = bucket major, exact 64-bit key inside a bucket = the same
+// ascending key order as a full sort.  A segment whose fullest bucket exceeds kBucketBail (all depths equal, one outlier
+// stretching the range) falls back to the bitonic network; segments of <= 64 keys are sorted by one warp in registers.
+constexpr uint32_t kBucketMax = kSortSmall / 4;
+constexpr uint32_t kBucketBail = 160;
+
+__device__ __forceinline__ uint32_t depth_bucket(uint64_t key, float d_min, float scale, uint32_t n_buckets) {
+    const float f = __fmul_rn(__fsub_rn(__uint_as_float((uint32_t)(key >> 32)), d_min), scale);
+    return min((uint32_t)f, n_buckets - 1u);  // f >= 0; float -> uint conversion saturates
+}
+
+__device__ __forceinline__ void write_sorted(int64_t hi, int64_t pos, uint64_t key, int64_t *__restrict__ isect_ids,
+                                             int32_t *__restrict__ flatten_ids) {
+    // low word: sign-extending OR like the reference's (int64)(int32)depth cast (isect_tiles.cu:88)
+    isect_ids[pos] = hi | (int64_t)(int32_t)(uint32_t)(key >> 32);
+    flatten_ids[pos] = (int32_t)(uint32_t)(key & 0xffffffffu);
+}
+
+__global__ void __launch_bounds__(kThreads)
+tile_sort_bucket_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, int64_t n_isects_or_capacity,
+                        const int32_t *__restrict__ total_dev, const int32_t *__restrict__ offsets,
+                        const uint64_t *__restrict__ bucket, int64_t *__restrict__ isect_ids,
+                        int32_t *__restrict__ flatten_ids) {
+    constexpr uint32_t KPT = kSortSmall / kThreads, NW = kThreads / 32;
+    __shared__ uint64_t s_keys[kSortSmall];
+    __shared__ uint32_t s_base[kBucketMax + 1];
+    __shared__ uint32_t s_min[NW], s_max[NW], s_sum[NW], s_full[NW];
+    const int64_t n_isects = total_dev ? (int64_t)*total_dev : n_isects_or_capacity;
+    const int64_t capacity = n_isects_or_capacity;
+    const uint32_t ct = blockIdx.x;
+    const int64_t start = offsets[ct];
+    const int64_t end = (ct + 1 == n_tiles_total) ? n_isects : (int64_t)offsets[ct + 1];
+    const uint32_t n = (uint32_t)(end - start);
+    if (end <= start || n > kSortSmall || end > capacity) return;  // longer segments belong to tile_sort_kernel<true>
+    const uint64_t cam = ct / n_tiles, tile = ct % n_tiles;
+    const int64_t hi = (int64_t)((cam << (32 + tile_bits)) | (tile << 32));
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (n <= 64) {
+        if (warp == 0) {
+            uint64_t x0 = lane < n ? bucket[start + lane] : kInf, x1 = 32 + lane < n ? bucket[start + 32 + lane] : kInf;
+            warp_sort64(x0, x1, lane);
+            if (lane < n) write_sorted(hi, start + lane, x0, isect_ids, flatten_ids);
+            if (32 + lane < n) write_sorted(hi, start + 32 + lane, x1, isect_ids, flatten_ids);
+        }
+        return;
+    }
+    uint32_t n_buckets = 16;
+    while (n_buckets * 4 < n) n_buckets <<= 1;  // <= kBucketMax
+    uint64_t key[KPT];
+    uint32_t d_lo = 0xffffffffu, d_hi = 0;  // positive floats order like their bit patterns
+#pragma unroll
+    for (uint32_t k = 0; k < KPT; ++k) {
+        const uint32_t i = threadIdx.x + k * kThreads;
+        key[k] = i < n ? bucket[start + i] : kInf;
+        if (i < n) {
+            d_lo = min(d_lo, (uint32_t)(key[k] >> 32));
+            d_hi = max(d_hi, (uint32_t)(key[k] >> 32));
+        }
+    }
+    d_lo = __reduce_min_sync(0xffffffffu, d_lo);
+    d_hi = __reduce_max_sync(0xffffffffu, d_hi);
+    if (lane == 0) s_min[warp] = d_lo, s_max[warp] = d_hi;
+    for (uint32_t t = threadIdx.x; t <= n_buckets; t += kThreads) s_base[t] = 0;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t w = 0; w < NW; ++w) d_lo = min(d_lo, s_min[w]), d_hi = max(d_hi, s_max[w]);
+    const float d_min = __uint_as_float(d_lo);
+    float scale = d_hi > d_lo ? __fdiv_rn((float)n_buckets, __fsub_rn(__uint_as_float(d_hi), d_min)) : 0.f;
+    if (!(scale <= 3.0e38f)) scale = 0.f;  // inf / nan: one bucket, the bail-out below sorts it
+    uint32_t where[KPT];  // bucket << 16 | arrival slot inside the bucket
+#pragma unroll
+    for (uint32_t k = 0; k < KPT; ++k) {
+        if (threadIdx.x + k * kThreads < n) {
+            const uint32_t b = depth_bucket(key[k], d_min, scale, n_buckets);
+            where[k] = b << 16 | atomicAdd(&s_base[b], 1u);
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the bucket counts (n_buckets <= 2 * kThreads) and the fullest bucket
+        const uint32_t per = n_buckets > kThreads ? 2u : 1u, i0 = threadIdx.x * per;
+        const uint32_t c0 = i0 < n_buckets ? s_base[i0] : 0u, c1 = per == 2 && i0 + 1 < n_buckets ? s_base[i0 + 1] : 0u;
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        const uint32_t full = __reduce_max_sync(0xffffffffu, max(c0, c1));
+        if (lane == 31) s_sum[warp] = incl;
+        if (lane == 0) s_full[warp] = full;
+        __syncthreads();
+        uint32_t before = 0, fullest = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < NW; ++w) before += w < warp ? s_sum[w] : 0u, fullest = max(fullest, s_full[w]);
+        const uint32_t excl = before + incl - c0 - c1;
+        if (i0 < n_buckets) s_base[i0] = excl;
+        if (per == 2 && i0 + 1 < n_buckets) s_base[i0 + 1] = excl + c0;
+        if (threadIdx.x == 0) s_base[n_buckets] = n;
+        if (fullest > kBucketBail) {  // block-uniform
+            const uint32_t n_pad = (n + 63u) & ~63u;
+#pragma unroll
+            for (uint32_t k = 0; k < KPT; ++k)
+                if (threadIdx.x + k * kThreads < n_pad) s_keys[threadIdx.x + k * kThreads] = key[k];
+            __syncthreads();
+            block_sort_padded(s_keys, n_pad);
+            for (uint32_t t = threadIdx.x; t < n; t += kThreads) write_sorted(hi, start + t, s_keys[t], isect_ids, flatten_ids);
+            return;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < KPT; ++k)
+        if (threadIdx.x + k * kThreads < n) s_keys[s_base[where[k] >> 16] + (where[k] & 0xffffu)] = key[k];
+    __syncthreads();
+    // consecutive lanes take consecutive bucket-ordered slots: neighbours share a bucket, its keys are broadcast reads
+#pragma unroll 2
+    for (uint32_t k = 0; k < KPT; ++k) {
+        const uint32_t i = threadIdx.x + k * kThreads;
+        if (i >= n) break;
+        const uint64_t mine = s_keys[i];
+        const uint32_t b = depth_bucket(mine, d_min, scale, n_buckets);
+        const uint32_t lo = s_base[b], up = s_base[b + 1];
+        uint32_t rank = lo;
+        for (uint32_t j = lo; j < up; ++j) rank += s_keys[j] < mine ? 1u : 0u;
+        write_sorted(hi, start + rank, mine, isect_ids, flatten_ids);
+    }
+}
+
+// Long segments (> kSortSmall keys), same scheme with 1024 threads walking the work list of replica_cursor_kernel.  The
+// keys are not held in registers: the three passes (depth range, histogram, scatter) re-read them from the L2-resident
+// bucket array, and the scatter takes its slot from a running per-bucket cursor, which leaves s_base[b] = end of bucket b.
+constexpr uint32_t kBucketMaxLarge = 4096;
+constexpr size_t kBucketLargeSmem = kSortLarge * sizeof(uint64_t) + (kBucketMaxLarge + 1) * sizeof(uint32_t);
+
+__global__ void __launch_bounds__(1024)
+tile_sort_bucket_large_kernel(uint32_t n_tiles_total, uint32_t n_tiles, uint32_t tile_bits, int64_t n_isects_or_capacity,
+                              const int32_t *__restrict__ total_dev, const int32_t *__restrict__ offsets,
+                              const int32_t *__restrict__ large_list, uint64_t *__restrict__ bucket,
+                              int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+    constexpr uint32_t NT = 1024, NW = NT / 32;
+    extern __shared__ uint64_t s_dyn[];
+    uint64_t *s_keys = s_dyn;
+    uint32_t *s_base = reinterpret_cast<uint32_t *>(s_dyn + kSortLarge);
+    __shared__ uint32_t s_min[NW], s_max[NW], s_sum[NW], s_full[NW];
+    const int64_t n_isects = total_dev ? (int64_t)*total_dev : n_isects_or_capacity;
+    const int64_t capacity = n_isects_or_capacity;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_work = (uint32_t)large_list[0];
+    for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const uint32_t ct = (uint32_t)large_list[1 + w];
+        const int64_t start = offsets[ct];
+        const int64_t end = (ct + 1 == n_tiles_total) ? n_isects : (int64_t)offsets[ct + 1];
+        const uint32_t n = (uint32_t)(end - start);
+        if (end <= start || end > capacity) continue;
+        const uint64_t cam = ct / n_tiles, tile = ct % n_tiles;
+        const int64_t hi = (int64_t)((cam << (32 + tile_bits)) | (tile << 32));
+        uint64_t *seg = bucket + start;
+        if (n > kSortLarge) {  // in place in global memory
+            __syncthreads();
+            block_sort_global(seg, n);
+            for (uint32_t t = threadIdx.x; t < n; t += NT) write_sorted(hi, start + t, seg[t], isect_ids, flatten_ids);
+            continue;
+        }
+        uint32_t n_buckets = NT;
+        while (n_buckets * 4 < n) n_buckets <<= 1;  // <= kBucketMaxLarge
+        uint32_t d_lo = 0xffffffffu, d_hi = 0;
+        for (uint32_t i = threadIdx.x; i < n; i += NT) {
+            const uint32_t d = (uint32_t)(seg[i] >> 32);
+            d_lo = min(d_lo, d), d_hi = max(d_hi, d);
+        }
+        d_lo = __reduce_min_sync(0xffffffffu, d_lo);
+        d_hi = __reduce_max_sync(0xffffffffu, d_hi);
+        if (lane == 0) s_min[warp] = d_lo, s_max[warp] = d_hi;
+        for (uint32_t t = threadIdx.x; t <= n_buckets; t += NT) s_base[t] = 0;
+        __syncthreads();
+#pragma unroll
+        for (uint32_t q = 0; q < NW; ++q) d_lo = min(d_lo, s_min[q]), d_hi = max(d_hi, s_max[q]);
+        const float d_min = __uint_as_float(d_lo);
+        float scale = d_hi > d_lo ? __fdiv_rn((float)n_buckets, __fsub_rn(__uint_as_float(d_hi), d_min)) : 0.f;
+        if (!(scale <= 3.0e38f)) scale = 0.f;
+        for (uint32_t i = threadIdx.x; i < n; i += NT) atomicAdd(&s_base[depth_bucket(seg[i], d_min, scale, n_buckets)], 1u);
+        __syncthreads();
+        const uint32_t per = n_buckets / NT, i0 = threadIdx.x * per;  // 1, 2 or 4 counters per thread
+        uint32_t c[4] = {0, 0, 0, 0}, mine = 0, full = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q)
+            if (q < per) c[q] = s_base[i0 + q], mine += c[q], full = max(full, c[q]);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        full = __reduce_max_sync(0xffffffffu, full);
+        if (lane == 31) s_sum[warp] = incl;
+        if (lane == 0) s_full[warp] = full;
+        __syncthreads();
+        uint32_t run = incl - mine, fullest = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < NW; ++q) run += q < warp ? s_sum[q] : 0u, fullest = max(fullest, s_full[q]);
+        if (fullest > kBucketBail) {  // block-uniform: the bitonic network on the whole segment
+            const uint32_t n_pad = (n + 63u) & ~63u;
+            for (uint32_t t = threadIdx.x; t < n_pad; t += NT) s_keys[t] = t < n ? seg[t] : kInf;
+            __syncthreads();
+            block_sort_padded(s_keys, n_pad);
+            for (uint32_t t = threadIdx.x; t < n; t += NT) write_sorted(hi, start + t, s_keys[t], isect_ids, flatten_ids);
+            __syncthreads();
+            continue;
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q)
+            if (q < per) s_base[i0 + q] = run, run += c[q];  // running cursor, starts at the bucket's first slot
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += NT) {
+            const uint64_t key = seg[i];
+            s_keys[atomicAdd(&s_base[depth_bucket(key, d_min, scale, n_buckets)], 1u)] = key;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += NT) {
+            const uint64_t key = s_keys[i];
+            const uint32_t b = depth_bucket(key, d_min, scale, n_buckets);
+            const uint32_t lo = b ? s_base[b - 1] : 0u, up = s_base[b];
+            uint32_t rank = lo;
+            for (uint32_t j = lo; j < up; ++j) rank += s_keys[j] < key ? 1u : 0u;
+            write_sorted(hi, start + rank, key, isect_ids, flatten_ids);
+        }
+        __syncthreads();  // shared memory is reused by the next work item
+    }
+}
+
 // ---- EXPERIMENTAL alternative to tile_sort_kernel<false> (opt-in: GSB200_TILE_SORT=radix, not yet run on a GPU) -----------
 // The bitonic network above spends ~860 lane-instructions per key (64-bit compare-exchange, 45-66 stages).  Here a CTA
 // sorts its segment (<= kSortSmall keys) with a stable LSD radix sort on the depth word -- four 8-bit passes, passes in
@@ -577,11 +811,14 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
                                                                        tile_width, tile_height, T, tile_cursor, scratch, bound);
     if (int e = check_launch("isect_scatter")) return e;
     const int32_t *large_list = tile_cursor + (size_t)GSB200_ISECT_REPLICAS * T;
-    static const bool radix_small = [] {  // experimental, opt-in (see tile_sort_radix_kernel)
+    static const int small_sort = [] {  // 0 depth buckets (default), 1 bitonic network, 2 radix (both opt-in)
         const char *v = getenv("GSB200_TILE_SORT");
-        return v != nullptr && strcmp(v, "radix") == 0;
+        return v == nullptr ? 0 : strcmp(v, "bitonic") == 0 ? 1 : strcmp(v, "radix") == 0 ? 2 : 0;
     }();
-    if (radix_small)
+    if (small_sort == 0)
+        tile_sort_bucket_kernel<<<T, kThreads, 0, s>>>(T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, scratch,
+                                                        isect_ids, flatten_ids);
+    else if (small_sort == 2)
         tile_sort_radix_kernel<<<T, kThreads, 0, s>>>(T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, scratch,
                                                        isect_ids, flatten_ids);
     else
@@ -592,11 +829,17 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
     if (!attr_set) {
         GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(kSortLarge * sizeof(uint64_t))));
+        GSB_CUDA_OK(cudaFuncSetAttribute(tile_sort_bucket_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kBucketLargeSmem));
         attr_set = true;
     }
     const uint32_t large_grid = min(T, 2u * 148u);
-    tile_sort_kernel<true><<<large_grid, 1024, kSortLarge * sizeof(uint64_t), s>>>(
-        T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, large_list, scratch, isect_ids, flatten_ids);
+    if (small_sort == 0)
+        tile_sort_bucket_large_kernel<<<large_grid, 1024, kBucketLargeSmem, s>>>(
+            T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, large_list, scratch, isect_ids, flatten_ids);
+    else
+        tile_sort_kernel<true><<<large_grid, 1024, kSortLarge * sizeof(uint64_t), s>>>(
+            T, n_tiles, bit_width(n_tiles), bound, total_dev, isect_offsets, large_list, scratch, isect_ids, flatten_ids);
     return check_launch("tile_sort_large");
 }
 
