@@ -578,94 +578,123 @@ def isect_tiles(
 def _isect_tiles_with_offsets(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, packed=False,
                               n_cameras=None, camera_ids=None, gaussian_ids=None):
     """isect_tiles that also returns isect_offsets (a by-product of the per-tile design)."""
-    if packed:
-        nnz = means2d.size(0)
-        assert means2d.shape == (nnz, 2), means2d.size()
-        assert radii.shape == (nnz,), radii.size()
-        assert depths.shape == (nnz,), depths.size()
-        assert camera_ids is not None, "camera_ids is required if packed is True"
-        assert gaussian_ids is not None, "gaussian_ids is required if packed is True"
-        assert n_cameras is not None, "n_cameras is required if packed is True"
-        camera_ids = camera_ids.contiguous()
-        C, n_elems, per_cam = n_cameras, nnz, 0
-    else:
-        C, N, _ = means2d.shape
-        assert means2d.shape == (C, N, 2), means2d.size()
-        assert radii.shape == (C, N), radii.size()
-        assert depths.shape == (C, N), depths.size()
-        camera_ids = None
-        n_elems, per_cam = C * N, N
-    dev = means2d.device
-    means2d, depths = _f32(means2d.detach()), _f32(depths.detach())
-    radii = radii.contiguous()
-    assert radii.dtype == torch.int32, radii.dtype
-    T = C * tile_width * tile_height
-    tiles_per_gauss = torch.empty(radii.shape, dtype=torch.int32, device=dev)
-    isect_offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
-    n_scratch, total_at = ctypes.c_int64(0), ctypes.c_int64(0)
-    call("gsb200_isect_plan", C, n_elems, tile_width, tile_height, ctypes.byref(n_scratch), ctypes.byref(total_at))
-    tile_cursor = torch.empty(int(n_scratch.value), dtype=torch.int32, device=dev)
-    total_index = int(total_at.value)
-    # one rolling capacity per configuration (NOT per element count: in packed mode nnz changes every step, and every
-    # densification changes N -- the previous step's count is still the right guess)
-    key = (dev.index, C, tile_width, tile_height, tile_size, bool(packed))
-    capacity = _isect_capacity.get(key)
+    return _isect_tiles_begin(means2d, radii, depths, tile_size, tile_width, tile_height, sort, packed, n_cameras,
+                              camera_ids, gaussian_ids).finish()
 
-    def prepare(n_host_ref):
-        call("gsb200_isect_prepare", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths), tile_size,
-             tile_width, tile_height, ptr(tiles_per_gauss), ptr(isect_offsets), ptr(tile_cursor), n_host_ref,
-             stream_ptr(dev))
 
-    def fill(n_arg, isect_ids, flatten_ids, scratch):
-        call("gsb200_isect_fill", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths), tile_size,
-             tile_width, tile_height, n_arg, ptr(isect_offsets), ptr(tile_cursor), ptr(scratch), ptr(isect_ids),
-             ptr(flatten_ids), stream_ptr(dev))
+class _IsectPending:
+    """Tile intersection in two halves: the constructor enqueues every kernel of the stage it can (all of them once
+    a previous call has given a capacity to size the buffers with), `finish()` waits for the intersection count and
+    returns (tiles_per_gauss, isect_ids, flatten_ids, isect_offsets).  Work enqueued between the two -- rasterization()
+    puts the colour stage there -- keeps the device busy while the host waits, and is already behind the host when it
+    resumes."""
 
-    if not sort:
-        # emission order (reference: sort=False): exact path + a scan over tiles_per_gauss
-        with torch.cuda.device(dev):
-            n_host = ctypes.c_int64(0)
-            prepare(ctypes.byref(n_host))
-            n_isects = int(n_host.value)
-            isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
-            flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
-            cum = torch.empty(max(n_elems, 1) + n_elems // 2048 + 3, dtype=torch.int32, device=dev)
-            call("gsb200_isect_emit_unsorted", C, n_elems, per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths),
-                 tile_size, tile_width, tile_height, ptr(tiles_per_gauss), ptr(cum), ptr(isect_ids), ptr(flatten_ids),
-                 stream_ptr(dev))
-        return tiles_per_gauss, isect_ids, flatten_ids, isect_offsets
-
-    with torch.cuda.device(dev):
-        if capacity is not None and T > 0 and n_elems > 0:
+    @torch.no_grad()
+    def __init__(self, means2d, radii, depths, tile_size, tile_width, tile_height, sort, packed, n_cameras, camera_ids,
+                 gaussian_ids):
+        if packed:
+            nnz = means2d.size(0)
+            assert means2d.shape == (nnz, 2), means2d.size()
+            assert radii.shape == (nnz,), radii.size()
+            assert depths.shape == (nnz,), depths.size()
+            assert camera_ids is not None, "camera_ids is required if packed is True"
+            assert gaussian_ids is not None, "gaussian_ids is required if packed is True"
+            assert n_cameras is not None, "n_cameras is required if packed is True"
+            camera_ids = camera_ids.contiguous()
+            C, n_elems, per_cam = n_cameras, nnz, 0
+        else:
+            C, N, _ = means2d.shape
+            assert means2d.shape == (C, N, 2), means2d.size()
+            assert radii.shape == (C, N), radii.size()
+            assert depths.shape == (C, N), depths.size()
+            camera_ids = None
+            n_elems, per_cam = C * N, N
+        dev = means2d.device
+        means2d, depths = _f32(means2d.detach()), _f32(depths.detach())
+        radii = radii.contiguous()
+        assert radii.dtype == torch.int32, radii.dtype
+        self.dev, self.sort, self.C, self.n_elems, self.per_cam = dev, sort, C, n_elems, per_cam
+        self.geom = (tile_size, tile_width, tile_height)
+        self.inputs = (camera_ids, means2d, radii, depths)
+        T = C * tile_width * tile_height
+        self.tiles_per_gauss = torch.empty(radii.shape, dtype=torch.int32, device=dev)
+        self.isect_offsets = torch.empty((C, tile_height, tile_width), dtype=torch.int32, device=dev)
+        n_scratch, total_at = ctypes.c_int64(0), ctypes.c_int64(0)
+        call("gsb200_isect_plan", C, n_elems, tile_width, tile_height, ctypes.byref(n_scratch), ctypes.byref(total_at))
+        self.tile_cursor = torch.empty(int(n_scratch.value), dtype=torch.int32, device=dev)
+        total_index = int(total_at.value)
+        # one rolling capacity per configuration (NOT per element count: in packed mode nnz changes every step, and
+        # every densification changes N -- the previous step's count is still the right guess)
+        self.key = (dev.index, C, tile_width, tile_height, tile_size, bool(packed))
+        self.capacity = _isect_capacity.get(self.key) if sort and T > 0 and n_elems > 0 else None
+        self.event = None
+        if self.capacity is not None:
             # Speculative sizing: the intersection count of the previous call (+25 %) sizes the buffers, every
             # kernel of the stage is enqueued, and only then does the host wait -- for an event recorded right
             # after the count reached pinned memory, i.e. while scatter + sort are still running.  The GPU is
             # never idle, unlike with the reference's mid-stage `.item()` (isect_tiles.cu:200).
-            isect_ids = torch.empty(capacity, dtype=torch.int64, device=dev)
-            flatten_ids = torch.empty(capacity, dtype=torch.int32, device=dev)
-            scratch = torch.empty(capacity, dtype=torch.int64, device=dev)
-            prepare(None)
-            pinned = _pinned_counter(dev)
-            pinned.copy_(tile_cursor[total_index:total_index + 1], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            fill(-capacity, isect_ids, flatten_ids, scratch)
-            ev.synchronize()
-            n_isects = int(pinned.item())
-            if n_isects <= capacity:
-                if n_isects < capacity // 2:  # shrink only on a big drop: a stable size keeps the allocator's blocks
-                    _isect_capacity[key] = _round_capacity(n_isects)
-                return tiles_per_gauss, isect_ids[:n_isects], flatten_ids[:n_isects], isect_offsets
+            with torch.cuda.device(dev):
+                self.isect_ids = torch.empty(self.capacity, dtype=torch.int64, device=dev)
+                self.flatten_ids = torch.empty(self.capacity, dtype=torch.int32, device=dev)
+                scratch = torch.empty(self.capacity, dtype=torch.int64, device=dev)
+                self._prepare(None)
+                self.pinned = _pinned_counter(dev)
+                self.pinned.copy_(self.tile_cursor[total_index:total_index + 1], non_blocking=True)
+                self.event = torch.cuda.Event()
+                self.event.record()
+                self._fill(-self.capacity, self.isect_ids, self.flatten_ids, scratch)
+
+    def _prepare(self, n_host_ref):
+        camera_ids, means2d, radii, depths = self.inputs
+        tile_size, tile_width, tile_height = self.geom
+        call("gsb200_isect_prepare", self.C, self.n_elems, self.per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths),
+             tile_size, tile_width, tile_height, ptr(self.tiles_per_gauss), ptr(self.isect_offsets), ptr(self.tile_cursor),
+             n_host_ref, stream_ptr(self.dev))
+
+    def _fill(self, n_arg, isect_ids, flatten_ids, scratch):
+        camera_ids, means2d, radii, depths = self.inputs
+        tile_size, tile_width, tile_height = self.geom
+        call("gsb200_isect_fill", self.C, self.n_elems, self.per_cam, ptr(camera_ids), ptr(means2d), ptr(radii), ptr(depths),
+             tile_size, tile_width, tile_height, n_arg, ptr(self.isect_offsets), ptr(self.tile_cursor), ptr(scratch),
+             ptr(isect_ids), ptr(flatten_ids), stream_ptr(self.dev))
+
+    @torch.no_grad()
+    def finish(self):
+        dev, n_elems = self.dev, self.n_elems
+        camera_ids, means2d, radii, depths = self.inputs
+        tile_size, tile_width, tile_height = self.geom
+        if self.event is not None:
+            self.event.synchronize()
+            n_isects = int(self.pinned.item())
+            if n_isects <= self.capacity:
+                if n_isects < self.capacity // 2:  # shrink only on a big drop: a stable size keeps the allocator's blocks
+                    _isect_capacity[self.key] = _round_capacity(n_isects)
+                return self.tiles_per_gauss, self.isect_ids[:n_isects], self.flatten_ids[:n_isects], self.isect_offsets
             # overflow (scene grew by more than 25 % in one step): fall through to the exact path
-        n_host = ctypes.c_int64(0)
-        prepare(ctypes.byref(n_host))
-        n_isects = int(n_host.value)
-        _isect_capacity[key] = _round_capacity(n_isects)
-        isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
-        flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
-        scratch = torch.empty(max(n_isects, 1), dtype=torch.int64, device=dev)
-        fill(n_isects, isect_ids, flatten_ids, scratch)
-    return tiles_per_gauss, isect_ids, flatten_ids, isect_offsets
+        with torch.cuda.device(dev):
+            n_host = ctypes.c_int64(0)
+            self._prepare(ctypes.byref(n_host))
+            n_isects = int(n_host.value)
+            isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
+            flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
+            if not self.sort:
+                # emission order (reference: sort=False): exact path + a scan over tiles_per_gauss
+                cum = torch.empty(max(n_elems, 1) + n_elems // 2048 + 3, dtype=torch.int32, device=dev)
+                call("gsb200_isect_emit_unsorted", self.C, n_elems, self.per_cam, ptr(camera_ids), ptr(means2d), ptr(radii),
+                     ptr(depths), tile_size, tile_width, tile_height, ptr(self.tiles_per_gauss), ptr(cum), ptr(isect_ids),
+                     ptr(flatten_ids), stream_ptr(dev))
+                return self.tiles_per_gauss, isect_ids, flatten_ids, self.isect_offsets
+            if self.C * tile_width * tile_height > 0 and n_elems > 0:
+                _isect_capacity[self.key] = _round_capacity(n_isects)
+            scratch = torch.empty(max(n_isects, 1), dtype=torch.int64, device=dev)
+            self._fill(n_isects, isect_ids, flatten_ids, scratch)
+        return self.tiles_per_gauss, isect_ids, flatten_ids, self.isect_offsets
+
+
+def _isect_tiles_begin(means2d, radii, depths, tile_size, tile_width, tile_height, sort=True, packed=False,
+                       n_cameras=None, camera_ids=None, gaussian_ids=None) -> _IsectPending:
+    return _IsectPending(means2d, radii, depths, tile_size, tile_width, tile_height, sort, packed, n_cameras, camera_ids,
+                         gaussian_ids)
 
 
 def _round_capacity(n: int) -> int:

@@ -20,6 +20,7 @@ from torch import Tensor
 from typing_extensions import Literal
 
 from .cuda._wrapper import (
+    _isect_tiles_begin,
     _isect_tiles_with_offsets,
     fully_fused_projection,
     rasterize_to_pixels,
@@ -220,7 +221,7 @@ def rasterization(
     # distributed mode, the colour all-gather keeps overlapping with it.
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
-    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = _isect_tiles_with_offsets(
+    isect_pending = _isect_tiles_begin(
         means2d, radii, depths, tile_size, tile_width, tile_height,
         packed=packed, n_cameras=C, camera_ids=camera_ids, gaussian_ids=gaussian_ids,
     )
@@ -250,6 +251,10 @@ def rasterization(
             dirs = means[None, :, :] - campos[:, None, :]  # [C, N, 3]
             masks = radii > 0
             colors = torch.clamp_min(spherical_harmonics(sh_degree, dirs, colors, masks=masks) + 0.5, 0.0)
+
+    # the host waits for the intersection count only now: the colour kernels above are already enqueued behind the
+    # scatter + sort, so the device has work for the whole wait and for the launch of the blend that follows
+    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_pending.finish()
 
     if render_mode in ["RGB+D", "RGB+ED"]:
         colors = torch.cat((colors, depths[..., None]), dim=-1)

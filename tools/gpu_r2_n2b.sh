@@ -1,0 +1,17 @@
+#!/bin/bash
+# 2-GPU visit: timeline of one distributed step + bench at N=2
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+P=gpurun_out/r2n2c
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 300 $TR --master-port 29512 tools/dist_profile.py > ${P}_dist_profile.log 2>&1; grep -E "step span" ${P}_dist_profile.log
+timeout 300 $TR --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 > ${P}_bench.json 2> ${P}_bench.err; python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2n2c_bench.json') if l.startswith('{')][-1])
+print('N=2', d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'])
+PY
+timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra-legs > ${P}_bench_n1.json 2> ${P}_bench_n1.err; python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r2n2c_bench_n1.json') if l.startswith('{')][-1])
+print('N=1', d['value'], d['ms_per_step'], d['e2e']['value'])
+PY
