@@ -334,12 +334,21 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _cabi.enable_stage_timing(True)
+    # inside the timed region only the two blend calls (the roofline's kernels) carry CUDA events; the full per-stage
+    # table comes from a separate, shorter pass: two events around each of the ~25 C-ABI calls of a step cost ~0.2 ms
+    # of host time per step, which showed up as launch gaps in the headline measurement
+    blend_calls = ("gsb200_rasterize_fwd", "gsb200_rasterize_bwd")
+    _cabi.enable_stage_timing(True, only=blend_calls)
     ms, loss = timed(args.steps, e2e=False)
-    stage_ms = _cabi.stage_timing_ms()  # per C-ABI entry point, averaged per call
+    blend_ms = _cabi.stage_timing_ms()
     _cabi.enable_stage_timing(False)
     launches = _cabi.launch_count() - launches0
     ms_e2e, _ = timed(args.steps, e2e=True)
+    _cabi.enable_stage_timing(True)
+    timed(max(3, min(args.steps, 10)), e2e=False)
+    stage_ms = _cabi.stage_timing_ms()  # per C-ABI entry point, averaged per call
+    _cabi.enable_stage_timing(False)
+    stage_ms.update(blend_ms)  # the roofline uses the blend times of the timed region itself
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- checker / context legs, outside the headline's timed region (rank 0 of a 1-GPU run, M2 only) ----------------
@@ -410,8 +419,8 @@ def run_ours(args):
                 "kernel": "blend fwd + bwd (gsb200_rasterize_fwd/_bwd)", "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes": {"fwd": bytes_fwd, "bwd": bytes_bwd},
                 "launch_ms": {"fwd": round(t_fwd, 4), "bwd": round(t_bwd, 4)},
-                "note": "blend is FP32-issue bound, see DESIGN.md; stage_ms holds every stage; `value` is measured with "
-                        "per-call CUDA-event stage timing switched on (the pessimistic one), `e2e` without",
+                "note": "blend is FP32-issue bound, see DESIGN.md; launch_ms is measured inside the timed region of `value`, "
+                        "the other entries of stage_ms in a separate pass of the same step",
             },
             "stage_ms": {k.replace("gsb200_", ""): round(v, 4) for k, v in sorted(stage_ms.items())},
             "loss": float(loss.item()) if torch.is_tensor(loss) else loss,

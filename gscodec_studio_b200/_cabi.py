@@ -49,6 +49,9 @@ SIGNATURES = {
     "gsb200_sh_view_fwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _P, _P, _P, _P],
     "gsb200_sh_view_bwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_shard_reduce_rows": [_U, _U, _U, _U, _P, _P, _P, _P],
+    "gsb200_camera_positions": [_U, _P, _P, _P],
+    "gsb200_shard_publish": [_U, _U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _P, _P],
+    "gsb200_peer_barrier": [_U, _U, _P, _U, _P],
     "gsb200_shard_gather_geo": [_U, _U, _U, _P, _P, _P, _P],
     "gsb200_shard_push_geo": [_U, _U, _U, c_uint64, _U, _P, _P, _P, _P],
     "gsb200_shard_reduce_geo": [_U, _U, _U, c_uint64, _U, _P, _P, _P, _P],
@@ -57,6 +60,7 @@ SIGNATURES = {
     "gsb200_isect_plan": [_U, _U, _U, _U, _P, _P],
     "gsb200_isect_prepare": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_fill": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _L, _P, _P, _P, _P, _P, _P],
+    "gsb200_isect_count_async": [_P, c_int64, _P, _P],
     "gsb200_isect_emit_unsorted": [_U, _U, _U, _P, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P],
     "gsb200_isect_offset_encode": [_L, _P, _U, _U, _U, _P, _P],
     "gsb200_blend_stream_record": [_U, _U],
@@ -141,8 +145,38 @@ def launch_count() -> int:
     return int(load_library().gsb200_launch_count())
 
 
+def _device_index(device) -> int:
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    idx = torch.device(device).index
+    return torch.cuda.current_device() if idx is None else idx
+
+
 def stream_ptr(device=None) -> c_void_p:
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """Raw cudaStream_t of torch's current stream on `device` (the raw query: building a torch.cuda.Stream object per
+    C-ABI call cost ~9 us of host time, 150 us per training step)."""
+    return c_void_p(torch._C._cuda_getCurrentRawStream(_device_index(device)))
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """`with torch.cuda.device(device)` that costs nothing when `device` already is the current device (the usual
+    case: one process per GPU) -- the torch context manager is ~5 us per use, a dozen uses per step."""
+    if _device_index(device) == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
 
 
 def ptr(t: Optional[torch.Tensor]) -> c_void_p:
@@ -170,11 +204,15 @@ def aligned(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 _stage_events = None  # name -> list of (start, end) CUDA events, when stage timing is on
 
 
-def enable_stage_timing(on: bool) -> None:
-    """Record a CUDA-event pair around every C-ABI call (on the stream the kernels are launched on).
-    Used by bench.py to attribute device time to stages inside the timed region."""
-    global _stage_events
+_stage_only = None  # None = every entry point, else the set of names to time
+
+
+def enable_stage_timing(on: bool, only=None) -> None:
+    """Record a CUDA-event pair around every C-ABI call -- or only the entry points named in `only` -- on the stream
+    the kernels are launched on.  Used by bench.py to attribute device time to stages inside the timed region."""
+    global _stage_events, _stage_only
     _stage_events = {} if on else None
+    _stage_only = None if only is None else frozenset(only)
 
 
 def stage_timing_ms() -> dict:
@@ -196,7 +234,7 @@ def call(name: str, *args) -> None:
             rc = getattr(lib, name)(*args)
         finally:
             torch.cuda.nvtx.range_pop()
-    elif _stage_events is not None:
+    elif _stage_events is not None and (_stage_only is None or name in _stage_only):
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         rc = getattr(lib, name)(*args)

@@ -27,7 +27,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
-from ._cabi import call, ptr, stream_ptr
+from ._cabi import call, device_guard, ptr, stream_ptr
 
 MAX_SHARDS = 16  # GSB200_MAX_SHARDS in include/gsb200.h
 
@@ -62,7 +62,8 @@ class PeerWorkspace:
         n_stage = self.world * cap_block * row_floats
         n_flags = self.world * cap_block
         n_gstage = self.world * cap_block * GEO_WIDTH  # geometry-gradient staging: slot [p] is written by rank p
-        self.buf = symm_mem.empty(n_coeff + n_geo + n_stage + n_flags + n_gstage, dtype=torch.float32, device=device)
+        n_pads = 4 * MAX_SHARDS  # signal pad of the barrier kernel (uint32 words; the first MAX_SHARDS are used)
+        self.buf = symm_mem.empty(n_coeff + n_geo + n_stage + n_flags + n_gstage + n_pads, dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         assert len(ptrs) == self.world and all(p % 16 == 0 for p in ptrs), ptrs
@@ -72,7 +73,12 @@ class PeerWorkspace:
         self.staging = self.buf[o_stage:o_flags]
         o_gstage = o_flags + n_flags
         self.flags = self.buf[o_flags:o_gstage].view(torch.int32)
-        self.geo_staging = self.buf[o_gstage:]
+        o_pads = o_gstage + n_gstage
+        self.geo_staging = self.buf[o_gstage:o_pads]
+        self.buf[o_pads:].zero_()
+        self._pad_tab = _ptr_table(ptrs, 4 * o_pads)
+        self.epoch = 0
+        self.hdl.barrier(channel=0)  # every pad is zero before the first signal can arrive
         self._gstage_tab = _ptr_table(ptrs, 4 * o_gstage)
         self._coeff_tab = _ptr_table(ptrs, 0)
         self._geo_tab = _ptr_table(ptrs, 4 * o_geo)
@@ -82,8 +88,11 @@ class PeerWorkspace:
         self.readers = False  # a pull kernel was launched since the last barrier: peers may still be reading
 
     def barrier(self) -> None:
-        """Stream-ordered barrier over all ranks (a small kernel on the current stream; the host does not block)."""
-        self.hdl.barrier(channel=0)
+        """Stream-ordered barrier over all ranks (a small kernel on the current stream; the host does not block).
+        Our own signal-pad kernel: the symmetric-memory handle's barrier costs ~150 us of HOST time per call, four
+        calls per step -- enough to let the host fall behind the device."""
+        self.epoch = (self.epoch + 1) & 0xFFFFFFFF
+        call("gsb200_peer_barrier", self.world, self.rank, self._pad_tab[1], self.epoch, stream_ptr(self.buf.device))
         self.readers = False
 
     def publish(self, coeff_rows: Tensor, geo_parts: Optional[Sequence[Tensor]] = None, pad_row: Optional[Tensor] = None,
@@ -92,21 +101,25 @@ class PeerWorkspace:
         both blocks).  Returns the version number of what is now published."""
         if self.readers:
             self.barrier()
-        if isinstance(coeff_rows, (tuple, list)):  # the trainers' (sh0 [n,1,3], shN [n,K-1,3]): written side by side,
-            sh0, shN = coeff_rows                  # the [n,K,3] concatenation never exists outside this buffer
-            n = sh0.shape[0]
-            rows = self.coeff[:n].view(n, self.row_floats // 3, 3)
-            rows[:, :1].copy_(sh0)
-            rows[:, 1:].copy_(shN)
-        else:
-            n = coeff_rows.shape[0]
-            self.coeff[:n].copy_(coeff_rows.reshape(n, self.row_floats))
+        # one launch writes both blocks: the trainers' (sh0 [n,1,3], shN [n,K-1,3]) land side by side, the [n,K,3]
+        # concatenation never exists outside this buffer
+        first, rest = coeff_rows if isinstance(coeff_rows, (tuple, list)) else (coeff_rows, None)
+        first = first.detach().float().contiguous()
+        rest = None if rest is None else rest.detach().float().contiguous()
+        n = first.shape[0]
+        first_floats = first.numel() // max(n, 1)
+        assert n <= self.cap_block and first_floats + (0 if rest is None else rest.numel() // max(n, 1)) == self.row_floats
+        n_parts, w_ptr, p_ptr, keep = 0, None, None, None
         if geo_parts is not None:
-            w = sum(t.shape[1] for t in geo_parts)
-            block = self.geo[: n_block * w].view(n_block, w)
-            torch.cat(list(geo_parts), dim=1, out=block[:n])
-            if n < n_block:
-                block[n:] = pad_row  # inert splats
+            parts = [t.detach().float().contiguous() for t in geo_parts]
+            widths = [t.shape[1] for t in parts]
+            assert sum(widths) <= GEO_WIDTH and n_block <= self.cap_block and all(t.shape[0] == n for t in parts)
+            keep = (parts, _u32_array(widths), _ptr_array(parts))
+            n_parts, w_ptr, p_ptr = len(parts), keep[1][1], keep[2][1]
+            pad_row = None if pad_row is None else pad_row.detach().float().contiguous()
+        call("gsb200_shard_publish", n, n_block if geo_parts is not None else n, n_parts, w_ptr, p_ptr,
+             ptr(pad_row) if geo_parts is not None else None, ptr(self.geo), ptr(first), ptr(rest), first_floats,
+             self.row_floats, ptr(self.coeff), stream_ptr(self.buf.device))
         self.barrier()
         self.version += 1
         return self.version
@@ -165,7 +178,7 @@ class _ShViewSharded(torch.autograd.Function):
         K = coeffs_local.shape[1] + (coeffs_rest.shape[1] if coeffs_rest is not None else 0)
         ws = workspace(means.device, K * 3, n_block)
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
-        with torch.cuda.device(means.device):
+        with device_guard(means.device):
             if published is None or published != ws.version:
                 ws.publish(coeffs_local if coeffs_rest is None else (coeffs_local, coeffs_rest))
             # local copy of every pulled row: the backward needs the same rows again (d colour / d direction)
@@ -189,7 +202,7 @@ class _ShViewSharded(torch.autograd.Function):
         v_colors = v_colors.contiguous()
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_sh_view_bwd_sharded", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ws.coeff_table, ws.world, n_block,
                  ws.rank, ptr(row_cache), ptr(radii), ptr(v_colors), ws.stage_table, ws.flag_table, ptr(v_means), ptr(v_campos),
                  stream_ptr(dev))
@@ -229,7 +242,7 @@ class _GatherGeometry(torch.autograd.Function):
         outs = [torch.empty((ws.world * n_block, w), dtype=torch.float32, device=dev) for w in widths]
         keep_w, w_ptr = _u32_array(widths)
         keep_o, o_ptr = _ptr_array(outs)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_shard_gather_geo", ws.world, n_block, len(widths), w_ptr, ws.geo_table, o_ptr, stream_ptr(dev))
         ws.readers = True
         ctx.ws, ctx.n_block, ctx.n_local, ctx.widths, ctx.dev = ws, n_block, geo_parts[0].shape[0], widths, dev
@@ -244,7 +257,7 @@ class _GatherGeometry(torch.autograd.Function):
         keep_w, w_ptr = _u32_array(widths)
         keep_g, g_ptr = _ptr_array(grads)
         keep_o, o_ptr = _ptr_array(outs)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             slot = ws.cap_block * GEO_WIDTH  # floats per staging slot (one dense [n_block * w] block each)
             call("gsb200_shard_push_geo", ws.world, n_block, ws.rank, slot, len(widths), w_ptr, g_ptr, ws.geo_stage_table,
                  stream_ptr(dev))
@@ -267,7 +280,7 @@ def publish_and_gather_geometry(geo_parts: Sequence[Tensor], pad_row: Tensor, co
     ws = workspace(dev, K * 3, n_block)
     parts = [t.detach().float() for t in geo_parts]
     rows = tuple(t.detach().float() for t in coeffs_local) if pair else coeffs_local.detach().float()
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         version = ws.publish(rows, parts, pad_row, n_block)
     return _GatherGeometry.apply(ws, n_block, *[t.float() for t in geo_parts]), version
 

@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as nnf
 from torch import Tensor
 
-from .._cabi import aligned, call, ptr, stream_ptr
+from .._cabi import aligned, call, device_guard, ptr, stream_ptr
 
 
 class _EntropyBits(torch.autograd.Function):
@@ -33,7 +33,7 @@ class _EntropyBits(torch.autograd.Function):
         params = aligned(params.to(torch.float32))
         N, ch = x.shape
         bits = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             call("gsb200_entropy_fwd", N, ch, n_hidden, ptr(x), float(q), ptr(params), float(bound), ptr(bits),
                  stream_ptr(x.device))
         ctx.save_for_backward(x, params)
@@ -48,7 +48,7 @@ class _EntropyBits(torch.autograd.Function):
         v_bits = aligned(v_bits.contiguous())
         v_x = torch.empty_like(x)
         v_params = torch.zeros_like(params)
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             call("gsb200_entropy_bwd", N, ch, n_hidden, ptr(x), q, ptr(params), bound, ptr(v_bits), ptr(v_x),
                  ptr(v_params), stream_ptr(x.device))
         return v_x, v_params, None, None, None, None

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from .._cabi import call, ptr, stream_ptr
+from .._cabi import call, device_guard, ptr, stream_ptr
 
 
 class _GridEncode(torch.autograd.Function):
@@ -31,7 +31,7 @@ class _GridEncode(torch.autograd.Function):
         offs = (ctypes.c_int32 * (L + 1))(*[int(o) for o in offsets])
         ress = (ctypes.c_int32 * L)(*[int(r) for r in resolutions])
         out = torch.empty((N, L * F), dtype=torch.float32, device=inputs.device)
-        with torch.cuda.device(inputs.device):
+        with device_guard(inputs.device):
             call("gsb200_grid_encode_fwd", N, D, F, L, ctypes.cast(offs, ctypes.c_void_p), ctypes.cast(ress, ctypes.c_void_p),
                  int(ste_binary), ptr(inputs), ptr(params), ptr(out), stream_ptr(inputs.device))
         ctx.save_for_backward(inputs, params)
@@ -49,7 +49,7 @@ class _GridEncode(torch.autograd.Function):
         v_out = v_out.float().contiguous()
         v_params = torch.empty_like(params)
         v_inputs = torch.empty_like(inputs) if ctx.needs_input_grad[0] else None
-        with torch.cuda.device(inputs.device):
+        with device_guard(inputs.device):
             call("gsb200_grid_encode_bwd", N, D, F, L, ctypes.cast(offs, ctypes.c_void_p), ctypes.cast(ress, ctypes.c_void_p),
                  int(ste_binary), ptr(inputs), ptr(params), ptr(v_out), ptr(v_params), ptr(v_inputs), stream_ptr(inputs.device))
         return v_inputs, v_params, None, None, None

@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import torch
 from torch import Tensor
 
-from .._cabi import aligned, call, ptr, stream_ptr
+from .._cabi import aligned, call, device_guard, ptr, stream_ptr
 
 _ACT = {None: 0, "none": 0, "exp": 1, "sigmoid": 2}
 _MODE = {"noise": 0, "round": 1}
@@ -59,7 +59,7 @@ class _FakeQuantize(torch.autograd.Function):
         if noise is not None:
             noise = aligned(noise.to(torch.float32))
             assert noise.numel() == x.numel(), "noise must have as many elements as the input"
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             call("gsb200_fake_quantize_fwd", xin.numel(), ptr(xin), float(lo), float(hi), int(bitwidth), mode, act,
                  ptr(noise), seed, offset, ptr(y), stream_ptr(x.device))
         # round mode wrote the clamped values through `x` (like the reference's input.clamp_ inside
@@ -76,7 +76,7 @@ class _FakeQuantize(torch.autograd.Function):
             return v_y, None, None, None, None, None, None  # pure straight-through (ops.py:73-75)
         v_y = aligned(v_y.contiguous())
         v_x = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with device_guard(x.device):
             call("gsb200_fake_quantize_bwd", x.numel(), ptr(x), ptr(y), lo, hi, mode, act, ptr(v_y), ptr(v_x),
                  stream_ptr(x.device))
         return v_x.view_as(v_y), None, None, None, None, None, None
@@ -120,7 +120,7 @@ class _FakeQuantizeMulti(torch.autograd.Function):
             outs.append(y)
         import ctypes as _ct
 
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_fake_quantize_multi_fwd", len(xs), _ct.cast(table, _ct.c_void_p), stream_ptr(dev))
         ctx.save_for_backward(*ins, *outs)
         ctx.cfgs = [(float(lo), float(hi), int(bits), mode, act) for (lo, hi, bits, mode, act, _n) in cfgs]
@@ -152,7 +152,7 @@ class _FakeQuantizeMulti(torch.autograd.Function):
             grads.append(v_x.view_as(v_y))
             m += 1
         if m:
-            with torch.cuda.device(dev):
+            with device_guard(dev):
                 call("gsb200_fake_quantize_multi_bwd", m, _ct.cast(table, _ct.c_void_p), stream_ptr(dev))
         return (None, *grads)
 

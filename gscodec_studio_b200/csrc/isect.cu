@@ -792,6 +792,14 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
     return 0;
 }
 
+extern "C" int gsb200_isect_count_async(const int32_t *tile_cursor, int64_t total_index, int32_t *count_pinned,
+                                        gsb200_stream_t stream) {
+    if (tile_cursor == nullptr || count_pinned == nullptr || total_index < 0) return fail(2, "gsb200_isect_count_async: bad argument");
+    GSB_CUDA_OK(cudaMemcpyAsync(count_pinned, tile_cursor + total_index, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera, const int64_t *camera_ids,
                                  const float *means2d, const int32_t *radii, const float *depths, uint32_t tile_size,
                                  uint32_t tile_width, uint32_t tile_height, int64_t n_isects, const int32_t *isect_offsets,

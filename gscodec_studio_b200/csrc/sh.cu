@@ -624,6 +624,73 @@ shard_push_geo_kernel(uint32_t n_block, uint32_t rank, uint64_t slot_floats, con
     }
 }
 
+// publish: this rank's attribute tensors -> its geometry block [n_block, w] (rows >= n_local get the inert pad row) and its
+// coefficient tensor(s) -> its coefficient block [n_local, row_floats] (the trainers' sh0 [n,1,3] next to shN [n,K-1,3]),
+// one launch, every store a coalesced 16-byte vector (replaces two strided torch copies + torch.cat: 110 -> ~40 us at
+// 500 k rows).  Blocks [0, n_geo_blocks) handle the geometry vectors, the rest the coefficient vectors.
+__global__ void __launch_bounds__(kThreads)
+shard_publish_kernel(uint32_t n_local, uint32_t n_block, uint32_t n_geo_blocks, const __grid_constant__ GeoParts parts,
+                     const float *__restrict__ pad_row, float *__restrict__ geo_block, const float *__restrict__ first,
+                     const float *__restrict__ rest, uint32_t first_floats, uint32_t row_floats, float *__restrict__ coeff_block) {
+    if (blockIdx.x < n_geo_blocks) {
+        const uint64_t n_elems = (uint64_t)n_block * parts.w, n_own = (uint64_t)n_local * parts.w;
+        const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+        if (i * 4 >= n_elems) return;
+        float4 v = geo_load4(parts, 0, i * 4, n_own);
+        if (i * 4 + 4 > n_own) {  // inert rows behind the local ones
+            float vals[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t e = i * 4 + u;
+                if (e >= n_own && e < n_elems) vals[u] = pad_row ? pad_row[e % parts.w] : 0.f;
+            }
+            v = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        }
+        stg4(geo_block + i * 4, v);
+        return;
+    }
+    if (first == nullptr) return;
+    const uint32_t vec_per_row = row_floats / 4, rest_floats = row_floats - first_floats;
+    const uint64_t i = (uint64_t)(blockIdx.x - n_geo_blocks) * kThreads + threadIdx.x;
+    if (i >= (uint64_t)n_local * vec_per_row) return;
+    const uint64_t row = i / vec_per_row;
+    const uint32_t e0 = (uint32_t)(i % vec_per_row) * 4;
+    float vals[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t e = e0 + u;
+        vals[u] = e < first_floats ? __ldg(first + row * first_floats + e) : __ldg(rest + row * rest_floats + (e - first_floats));
+    }
+    stg4(coeff_block + i * 4, make_float4(vals[0], vals[1], vals[2], vals[3]));
+}
+
+// Stream-ordered barrier over the ranks of one node: every rank owns a signal pad (kMaxShards words, in the symmetric
+// allocation); thread p stores this barrier's epoch into peer p's pad (release, system scope, after a system fence that
+// orders the stream's earlier writes) and spins until peer p's epoch has arrived in the own pad (acquire).  Epochs only
+// grow, so nothing is ever reset.  A peer that does not arrive within ~20 s traps the context instead of hanging the GPU.
+struct PeerPads {
+    uint32_t *base[kMaxShards];
+};
+__global__ void peer_barrier_kernel(uint32_t rank, uint32_t epoch, const PeerPads pads) {
+    const uint32_t p = threadIdx.x;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pads.base[p] + rank), "r"(epoch) : "memory");
+    const uint32_t *mine = pads.base[rank] + p;
+    uint64_t t0 = 0;
+    for (uint32_t polls = 0;; ++polls) {
+        uint32_t seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        if ((int32_t)(seen - epoch) >= 0) break;
+        if ((polls & 1023u) == 1023u) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
+    }
+    __threadfence_system();
+}
+
 // owner-side reduce: sum of the world slots of the local staging array, in rank order -> the local gradient tensors
 __global__ void __launch_bounds__(kThreads)
 shard_reduce_geo_kernel(uint32_t world, uint32_t n_rows, uint64_t slot_floats, const float *__restrict__ staging,
@@ -1068,6 +1135,68 @@ extern "C" int gsb200_shard_gather_geo(uint32_t world, uint32_t n_block, uint32_
     const dim3 grid((uint32_t)((n_vec + kThreads * kGeoUnroll - 1) / (kThreads * kGeoUnroll)), world);
     shard_gather_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, sh, P);
     return check_launch("shard_gather_geo");
+}
+
+// camera centres of rigid world-to-camera matrices: -R^T t (one thread per camera; replaces a batched matmul + negate,
+// two launches and ~55 us of host time per step for a few dozen flops)
+__global__ void camera_positions_kernel(uint32_t C, const float *__restrict__ viewmats, float *__restrict__ campos) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float *V = viewmats + (size_t)c * 16;
+    const float tx = V[3], ty = V[7], tz = V[11];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        campos[c * 3 + j] = -__fadd_rn(__fadd_rn(__fmul_rn(V[j], tx), __fmul_rn(V[4 + j], ty)), __fmul_rn(V[8 + j], tz));
+}
+
+extern "C" int gsb200_camera_positions(uint32_t C, const float *viewmats, float *campos, gsb200_stream_t stream) {
+    if (C == 0) return 0;
+    if (viewmats == nullptr || campos == nullptr) return fail(2, "gsb200_camera_positions: null pointer");
+    camera_positions_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, viewmats, campos);
+    return check_launch("camera_positions");
+}
+
+extern "C" int gsb200_shard_publish(uint32_t n_local, uint32_t n_block, uint32_t n_parts, const uint32_t *widths,
+                                    float *const *parts, const float *pad_row, float *geo_block, const float *first,
+                                    const float *rest, uint32_t first_floats, uint32_t row_floats, float *coeff_block,
+                                    gsb200_stream_t stream) {
+    if (n_local > n_block) return fail(2, "gsb200_shard_publish: n_local > n_block");
+    GeoParts P{};
+    uint32_t n_geo_blocks = 0;
+    if (n_parts != 0) {
+        if (int e = geo_parts("gsb200_shard_publish", n_parts, parts, widths, true, P)) return e;
+        if (geo_block == nullptr || (reinterpret_cast<uintptr_t>(geo_block) & 15) != 0)
+            return fail(2, "gsb200_shard_publish: geo_block must be non-null and 16-byte aligned");
+        n_geo_blocks = (uint32_t)((((uint64_t)n_block * P.w + 3) / 4 + kThreads - 1) / kThreads);
+    }
+    uint64_t n_coeff_blocks = 0;
+    if (first != nullptr && n_local != 0) {
+        if (row_floats == 0 || row_floats % 4 != 0 || first_floats == 0 || first_floats > row_floats ||
+            (first_floats < row_floats && rest == nullptr))
+            return fail(2, "gsb200_shard_publish: row_floats must be a positive multiple of 4 covered by first (+ rest)");
+        if (coeff_block == nullptr || (reinterpret_cast<uintptr_t>(coeff_block) & 15) != 0)
+            return fail(2, "gsb200_shard_publish: coeff_block must be non-null and 16-byte aligned");
+        n_coeff_blocks = ((uint64_t)n_local * (row_floats / 4) + kThreads - 1) / kThreads;
+    }
+    const uint64_t grid = n_geo_blocks + n_coeff_blocks;
+    if (grid == 0) return 0;
+    if (grid > 0x7fffffffull) return fail(2, "gsb200_shard_publish: too many rows for one launch");
+    shard_publish_kernel<<<(uint32_t)grid, kThreads, 0, (cudaStream_t)stream>>>(
+        n_local, n_block, n_geo_blocks, P, pad_row, geo_block, n_coeff_blocks ? first : nullptr, rest, first_floats, row_floats,
+        coeff_block);
+    return check_launch("shard_publish");
+}
+
+extern "C" int gsb200_peer_barrier(uint32_t world, uint32_t rank, uint32_t *const *pads, uint32_t epoch, gsb200_stream_t stream) {
+    if (world == 0 || world > (uint32_t)kMaxShards || rank >= world)
+        return failf(2, "gsb200_peer_barrier: world must be in [1, %d] and rank < world", kMaxShards);
+    PeerPads P{};
+    for (uint32_t r = 0; r < world; ++r) {
+        P.base[r] = pads[r];
+        if (P.base[r] == nullptr) return fail(2, "gsb200_peer_barrier: null signal pad");
+    }
+    peer_barrier_kernel<<<1, world, 0, (cudaStream_t)stream>>>(rank, epoch, P);
+    return check_launch("peer_barrier");
 }
 
 extern "C" int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t rank, uint64_t slot_floats, uint32_t n_parts,

@@ -24,7 +24,7 @@ from torch import Tensor
 from typing_extensions import Literal
 
 from .. import _cabi
-from .._cabi import aligned, call, ptr, stream_ptr
+from .._cabi import aligned, call, device_guard, ptr, stream_ptr
 
 _CAMERA_MODELS = {"pinhole": 0, "ortho": 1, "fisheye": 2}
 _SUPPORTED_CHANNELS = (1, 2, 3, 4, 5, 8, 9, 16, 17, 32, 33)
@@ -69,7 +69,7 @@ def selective_adam_update(
         raise RuntimeError("selective_adam_update: param_grad must be a float32 CUDA tensor")
     vis = tiles_touched.contiguous()
     vis = vis.view(torch.uint8) if vis.dtype == torch.bool else (vis != 0).view(torch.uint8)
-    with torch.cuda.device(param.device):
+    with device_guard(param.device):
         call("gsb200_selective_adam_update", ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(vis), float(lr),
              float(b1), float(b2), float(eps), N, M, stream_ptr(param.device))
 
@@ -102,7 +102,7 @@ class _SphericalHarmonics(torch.autograd.Function):
         K = coeffs.shape[-2]
         masks_u8 = None if masks is None else masks.to(torch.uint8).contiguous()
         colors = torch.empty(dirs.shape, dtype=torch.float32, device=dirs.device)
-        with torch.cuda.device(dirs.device):
+        with device_guard(dirs.device):
             call("gsb200_sh_fwd", n, K, sh_degree, ptr(dirs), ptr(coeffs), ptr(masks_u8), ptr(colors),
                  stream_ptr(dirs.device))
         ctx.save_for_backward(dirs, coeffs, masks_u8)
@@ -118,7 +118,7 @@ class _SphericalHarmonics(torch.autograd.Function):
         v_colors = _f32(v_colors.contiguous())
         v_coeffs = torch.empty_like(coeffs)
         v_dirs = torch.empty_like(dirs) if compute_v_dirs else None
-        with torch.cuda.device(dirs.device):
+        with device_guard(dirs.device):
             call("gsb200_sh_bwd", n, ctx.num_bases, ctx.sh_degree, ptr(dirs), ptr(coeffs), ptr(masks_u8),
                  ptr(v_colors), ptr(v_coeffs), ptr(v_dirs), stream_ptr(dirs.device))
         return None, v_dirs, v_coeffs, None
@@ -143,7 +143,7 @@ class _ShView(torch.autograd.Function):
         means, campos, coeffs = _f32(means), _f32(campos), _f32(coeffs)
         C, N, K = campos.shape[0], means.shape[0], coeffs.shape[1]
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
-        with torch.cuda.device(means.device):
+        with device_guard(means.device):
             call("gsb200_sh_view_fwd", C, N, K, sh_degree, ptr(means), ptr(campos), ptr(coeffs), ptr(radii), ptr(colors),
                  stream_ptr(means.device))
         ctx.save_for_backward(means, campos, coeffs, radii)
@@ -158,7 +158,7 @@ class _ShView(torch.autograd.Function):
         v_coeffs = torch.empty_like(coeffs)
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
-        with torch.cuda.device(means.device):
+        with device_guard(means.device):
             call("gsb200_sh_view_bwd", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ptr(coeffs), ptr(radii),
                  ptr(v_colors), ptr(v_coeffs), ptr(v_means), ptr(v_campos), stream_ptr(means.device))
         return None, v_means, v_campos, v_coeffs, None
@@ -189,7 +189,7 @@ class _ShViewSplit(torch.autograd.Function):
         means, campos, sh0, shN = _f32(means), _f32(campos), _f32(sh0), _f32(shN)
         C, N, K = campos.shape[0], means.shape[0], 1 + shN.shape[1]
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
-        with torch.cuda.device(means.device):
+        with device_guard(means.device):
             call("gsb200_sh_view_split_fwd", C, N, K, sh_degree, ptr(means), ptr(campos), ptr(sh0), ptr(shN), ptr(radii),
                  ptr(colors), stream_ptr(means.device))
         ctx.save_for_backward(means, campos, sh0, shN, radii)
@@ -205,7 +205,7 @@ class _ShViewSplit(torch.autograd.Function):
         v_shN = torch.empty_like(shN)
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
-        with torch.cuda.device(means.device):
+        with device_guard(means.device):
             call("gsb200_sh_view_split_bwd", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ptr(sh0), ptr(shN), ptr(radii),
                  ptr(v_colors), ptr(v_sh0), ptr(v_shN), ptr(v_means), ptr(v_campos), stream_ptr(means.device))
         return None, v_means, v_campos, v_sh0, v_shN, None
@@ -237,7 +237,7 @@ class _QuatScaleToCovarPreci(torch.autograd.Function):
         shape = (N, 6) if triu else (N, 3, 3)
         covars = torch.empty(shape, dtype=torch.float32, device=dev) if compute_covar else None
         precis = torch.empty(shape, dtype=torch.float32, device=dev) if compute_preci else None
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_quat_scale_to_covar_preci_fwd", N, ptr(quats), ptr(scales), int(triu), ptr(covars), ptr(precis),
                  stream_ptr(dev))
         ctx.save_for_backward(quats, scales)
@@ -251,7 +251,7 @@ class _QuatScaleToCovarPreci(torch.autograd.Function):
         v_covars = _f32(_dense(v_covars)) if compute_covar and v_covars is not None else None
         v_precis = _f32(_dense(v_precis)) if compute_preci and v_precis is not None else None
         v_quats, v_scales = torch.empty_like(quats), torch.empty_like(scales)
-        with torch.cuda.device(quats.device):
+        with device_guard(quats.device):
             call("gsb200_quat_scale_to_covar_preci_bwd", quats.shape[0], ptr(quats), ptr(scales), int(triu), ptr(v_covars),
                  ptr(v_precis), ptr(v_quats), ptr(v_scales), stream_ptr(quats.device))
         return v_quats, v_scales, None, None, None
@@ -295,7 +295,7 @@ class _Proj(torch.autograd.Function):
         C, N, dev = means.shape[0], means.shape[1], means.device
         means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
         covars2d = torch.empty((C, N, 2, 2), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_proj_fwd", C, N, ptr(means), ptr(covars), ptr(Ks), width, height, _CAMERA_MODELS[camera_model],
                  ptr(means2d), ptr(covars2d), stream_ptr(dev))
         ctx.save_for_backward(means, covars, Ks)
@@ -309,7 +309,7 @@ class _Proj(torch.autograd.Function):
         C, N, dev = means.shape[0], means.shape[1], means.device
         v_means2d, v_covars2d = _f32(v_means2d.contiguous()), _f32(v_covars2d.contiguous())
         v_means, v_covars = torch.empty_like(means), torch.empty_like(covars)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_proj_bwd", C, N, ptr(means), ptr(covars), ptr(Ks), width, height, _CAMERA_MODELS[camera_model],
                  ptr(v_means2d), ptr(v_covars2d), ptr(v_means), ptr(v_covars), stream_ptr(dev))
         return v_means, v_covars, None, None, None, None
@@ -336,7 +336,7 @@ class _WorldToCam(torch.autograd.Function):
         C, N, dev = viewmats.shape[0], means.shape[0], means.device
         means_c = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
         covars_c = torch.empty((C, N, 3, 3), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_world_to_cam_fwd", C, N, ptr(means), ptr(covars), ptr(viewmats), ptr(means_c), ptr(covars_c),
                  stream_ptr(dev))
         ctx.save_for_backward(means, covars, viewmats)
@@ -350,7 +350,7 @@ class _WorldToCam(torch.autograd.Function):
         v_means = torch.empty_like(means) if ctx.needs_input_grad[0] else None
         v_covars = torch.empty_like(covars) if ctx.needs_input_grad[1] else None
         v_viewmats = torch.empty_like(viewmats) if ctx.needs_input_grad[2] else None
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_world_to_cam_bwd", C, N, ptr(means), ptr(covars), ptr(viewmats), ptr(v_means_c), ptr(v_covars_c),
                  ptr(v_means), ptr(v_covars), ptr(v_viewmats), stream_ptr(dev))
         return v_means, v_covars, v_viewmats
@@ -419,7 +419,7 @@ def _projection_fwd(means, covars, quats, scales, viewmats, Ks, width, height, e
     depths = torch.empty((C, N), dtype=torch.float32, device=dev)
     conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
     comps = torch.empty((C, N), dtype=torch.float32, device=dev) if calc_compensations else None
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         call("gsb200_projection_fwd", C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks),
              width, height, eps2d, near_plane, far_plane, radius_clip, _CAMERA_MODELS[camera_model], int(packed_rule),
              ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), stream_ptr(dev))
@@ -435,7 +435,7 @@ def _projection_bwd(means, covars, quats, scales, viewmats, Ks, width, height, e
     v_quats = torch.empty_like(quats) if covars is None else None
     v_scales = torch.empty_like(scales) if covars is None else None
     v_viewmats = torch.empty_like(viewmats) if viewmats_requires_grad else None
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         call("gsb200_projection_bwd", C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks),
              width, height, eps2d, _CAMERA_MODELS[camera_model], ptr(radii), ptr(conics), ptr(comps),
              ptr(_f32(v_means2d.contiguous())), ptr(_f32(v_depths.contiguous())), ptr(_f32(v_conics.contiguous())),
@@ -496,7 +496,7 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         nnz_host = ctypes.c_int64(0)
         geom = (C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks), width, height, eps2d,
                 near_plane, far_plane, radius_clip, _CAMERA_MODELS[camera_model])
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_projection_packed_count", *geom, ptr(block_offsets), ctypes.byref(nnz_host), stream_ptr(dev))
         nnz = int(nnz_host.value)
         indptr = torch.zeros(C + 1, dtype=torch.int32, device=dev)
@@ -507,7 +507,7 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         depths = torch.empty(nnz, dtype=torch.float32, device=dev)
         conics = torch.empty((nnz, 3), dtype=torch.float32, device=dev)
         comps = torch.empty(nnz, dtype=torch.float32, device=dev) if calc_compensations else None
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_projection_packed_fill", *geom, ptr(block_offsets), ptr(indptr), ptr(camera_ids), ptr(gaussian_ids),
                  ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps), stream_ptr(dev))
         ctx.save_for_backward(means, covars, quats, scales, viewmats, Ks, gaussian_ids, block_offsets, conics, comps)
@@ -531,7 +531,7 @@ class _FullyFusedProjectionPacked(torch.autograd.Function):
         v_quats = torch.empty_like(quats) if covars is None else None
         v_scales = torch.empty_like(scales) if covars is None else None
         v_viewmats = torch.empty_like(viewmats) if ctx.needs_input_grad[4] else None
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_projection_packed_bwd", C, N, ptr(means), ptr(covars), ptr(quats), ptr(scales), ptr(viewmats), ptr(Ks),
                  width, height, eps2d, _CAMERA_MODELS[camera_model], ptr(block_offsets), ptr(gaussian_ids), ptr(conics),
                  ptr(comps), ptr(_f32(v_means2d.contiguous())), ptr(_f32(v_depths.contiguous())),
@@ -633,15 +633,17 @@ class _IsectPending:
             # kernel of the stage is enqueued, and only then does the host wait -- for an event recorded right
             # after the count reached pinned memory, i.e. while scatter + sort are still running.  The GPU is
             # never idle, unlike with the reference's mid-stage `.item()` (isect_tiles.cu:200).
-            with torch.cuda.device(dev):
+            with device_guard(dev):
                 self.isect_ids = torch.empty(self.capacity, dtype=torch.int64, device=dev)
                 self.flatten_ids = torch.empty(self.capacity, dtype=torch.int32, device=dev)
                 scratch = torch.empty(self.capacity, dtype=torch.int64, device=dev)
                 self._prepare(None)
+                # the count travels to a pinned word the host polls: no event object, no driver call in the wait
                 self.pinned = _pinned_counter(dev)
-                self.pinned.copy_(self.tile_cursor[total_index:total_index + 1], non_blocking=True)
-                self.event = torch.cuda.Event()
-                self.event.record()
+                self.pinned[1][0] = -1
+                call("gsb200_isect_count_async", ptr(self.tile_cursor), total_index, ctypes.c_void_p(self.pinned[0].data_ptr()),
+                     stream_ptr(dev))
+                self.event = True
                 self._fill(-self.capacity, self.isect_ids, self.flatten_ids, scratch)
 
     def _prepare(self, n_host_ref):
@@ -664,14 +666,13 @@ class _IsectPending:
         camera_ids, means2d, radii, depths = self.inputs
         tile_size, tile_width, tile_height = self.geom
         if self.event is not None:
-            self.event.synchronize()
-            n_isects = int(self.pinned.item())
+            n_isects = _wait_counter(self.pinned[1], dev)
             if n_isects <= self.capacity:
                 if n_isects < self.capacity // 2:  # shrink only on a big drop: a stable size keeps the allocator's blocks
                     _isect_capacity[self.key] = _round_capacity(n_isects)
                 return self.tiles_per_gauss, self.isect_ids[:n_isects], self.flatten_ids[:n_isects], self.isect_offsets
             # overflow (scene grew by more than 25 % in one step): fall through to the exact path
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             n_host = ctypes.c_int64(0)
             self._prepare(ctypes.byref(n_host))
             n_isects = int(n_host.value)
@@ -706,12 +707,35 @@ _isect_capacity = {}  # (device, C, n_elems, tile grid) -> speculative buffer ca
 _pinned = {}
 
 
-def _pinned_counter(dev) -> Tensor:
+def _pinned_counter(dev):
+    """(pinned int32 tensor, numpy view of it) -- one per device."""
     buf = _pinned.get(dev.index)
     if buf is None:
-        buf = torch.zeros(1, dtype=torch.int32).pin_memory()
-        _pinned[dev.index] = buf
+        t = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _pinned[dev.index] = buf = (t, t.numpy())
     return buf
+
+
+def _wait_counter(view, dev) -> int:
+    """Spin until the device has written the (non-negative) count; falls back to a stream synchronisation -- which also
+    surfaces a failed kernel -- if nothing arrives for a second."""
+    import time
+
+    polls, t0 = 0, None
+    while True:
+        v = int(view[0])
+        if v >= 0:
+            return v
+        polls += 1
+        if polls & 0xFFF == 0:
+            now = time.monotonic()
+            t0 = t0 or now
+            if now - t0 > 1.0:
+                torch.cuda.current_stream(dev).synchronize()
+                v = int(view[0])
+                if v < 0:
+                    raise RuntimeError("gscodec_studio_b200: the intersection count never reached the host")
+                return v
 
 
 @torch.no_grad()
@@ -721,7 +745,7 @@ def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile
     assert isect_ids.dtype == torch.int64, isect_ids.dtype
     dev = isect_ids.device
     offsets = torch.empty((n_cameras, tile_height, tile_width), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         call("gsb200_isect_offset_encode", isect_ids.numel(), ptr(isect_ids), n_cameras, tile_width, tile_height,
              ptr(offsets), stream_ptr(dev))
     return offsets
@@ -839,7 +863,7 @@ def rasterize_to_indices_in_range(
     geom = (rs, re, C, N, n_isects, ptr(means2d), ptr(conics), ptr(opacities), image_width, image_height, tile_size,
             tile_width, tile_height, ptr(isect_offsets), ptr(flatten_ids), ptr(transmittances))
     chunk_cnts = torch.empty((C, image_height, image_width), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         call("gsb200_indices_in_range_count", *geom, ptr(chunk_cnts), stream_ptr(dev))
         ends = torch.cumsum(chunk_cnts.view(-1), 0, dtype=torch.int64)
         n_elems = int(ends[-1].item()) if ends.numel() else 0  # the host needs the size here, as in the reference
@@ -877,7 +901,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         if rec and any(ctx.needs_input_grad[:5]):
             blend_stream = torch.empty(max(flatten_ids.numel(), 1) * rec, dtype=torch.float32, device=dev)
             tile_counts = torch.empty(max(C * th * tw, 1), dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_rasterize_fwd", C, M, flatten_ids.numel(), D, ptr(means2d), ptr(conics), ptr(colors),
                  ptr(opacities), ptr(backgrounds), ptr(masks_u8), width, height, tile_size, tw, th, ptr(isect_offsets),
                  ptr(flatten_ids), ptr(render_colors), ptr(render_alphas), ptr(last_ids), ptr(tile_order),
@@ -904,7 +928,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         v_colors = torch.empty_like(colors)
         v_opacities = torch.empty_like(opacities)
         v_abs = torch.empty_like(means2d) if absgrad else None
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             rec = int(_cabi.load_library().gsb200_grad_record(D))
             scratch = torch.empty(max(M, 1) * rec, dtype=torch.float32, device=dev)
             call("gsb200_rasterize_bwd", C, M, flatten_ids.numel(), D, ptr(means2d), ptr(conics), ptr(colors),

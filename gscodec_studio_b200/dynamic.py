@@ -8,7 +8,7 @@ from typing import Tuple
 import torch
 from torch import Tensor
 
-from ._cabi import aligned, call, ptr, stream_ptr
+from ._cabi import aligned, call, device_guard, ptr, stream_ptr
 
 
 def stg_temporal_transform(
@@ -49,7 +49,7 @@ class _StgTemporal(torch.autograd.Function):
         N, dev = means.shape[0], means.device
         means_t, quats_t, scales_o = torch.empty_like(means), torch.empty_like(quats), torch.empty_like(scales)
         opac_o, trbf = torch.empty_like(opacities), torch.empty_like(opacities)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_stg_temporal_fwd", N, timestamp, ptr(means), ptr(quats), ptr(scales), ptr(opacities), ptr(trbf_center),
                  ptr(trbf_scale), ptr(motion), ptr(omega), ptr(means_t), ptr(quats_t), ptr(scales_o), ptr(opac_o), ptr(trbf),
                  stream_ptr(dev))
@@ -67,7 +67,7 @@ class _StgTemporal(torch.autograd.Function):
         v_opac_raw, v_center, v_tscale = torch.empty_like(opacities), torch.empty_like(trbf_center), torch.empty_like(trbf_scale)
         v_motion = torch.empty((N, 9), dtype=torch.float32, device=dev)
         v_omega = torch.empty_like(omega)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_stg_temporal_bwd", N, ctx.timestamp, ptr(quats), ptr(scales), ptr(opacities), ptr(trbf_center),
                  ptr(trbf_scale), ptr(omega), ptr(v_means_t), ptr(v_quats_t), ptr(v_scales), ptr(v_opacities), ptr(v_means),
                  ptr(v_quats), ptr(v_scales_raw), ptr(v_opac_raw), ptr(v_center), ptr(v_tscale), ptr(v_motion), ptr(v_omega),

@@ -23,7 +23,7 @@ import torch
 from torch import Tensor
 
 from . import _cabi
-from ._cabi import call, ptr, stream_ptr
+from ._cabi import call, device_guard, ptr, stream_ptr
 
 
 def _check(img: Tensor, name: str) -> Tensor:
@@ -52,7 +52,7 @@ class _Photometric(torch.autograd.Function):
         work = torch.empty(int(lib.gsb200_photometric_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
         out = torch.empty((), dtype=torch.float32, device=dev)
         stats = torch.empty(2, dtype=torch.float32, device=dev)  # L1 mean, SSIM mean (for logging)
-        with torch.cuda.device(dev):
+        with device_guard(dev):
             call("gsb200_photometric_loss_fwd", B, H, W, CH, ptr(img1), ptr(img2), float(coef_l1), float(coef_ssim), float(bias),
                  int(valid), ptr(None if maps is None else maps[0]), ptr(None if maps is None else maps[1]),
                  ptr(None if maps is None else maps[2]), ptr(work), ptr(out), ptr(stats), stream_ptr(dev))
@@ -72,7 +72,7 @@ class _Photometric(torch.autograd.Function):
         B, H, W, CH = img1.shape
         v_loss = v_loss.to(torch.float32).contiguous()
         v_img1 = torch.empty_like(img1)
-        with torch.cuda.device(img1.device):
+        with device_guard(img1.device):
             m = (None, None, None) if maps is None else (maps[0], maps[1], maps[2])
             call("gsb200_photometric_loss_bwd", B, H, W, CH, ptr(img1), ptr(img2), coef_l1, coef_ssim, int(valid), ptr(m[0]),
                  ptr(m[1]), ptr(m[2]), ptr(v_loss), ptr(v_img1), stream_ptr(img1.device))

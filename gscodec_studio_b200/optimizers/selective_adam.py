@@ -16,7 +16,7 @@ import math
 import torch
 
 from .. import _cabi
-from .._cabi import call, ptr, stream_ptr
+from .._cabi import call, device_guard, ptr, stream_ptr
 from ..cuda._wrapper import selective_adam_update
 
 
@@ -97,7 +97,7 @@ class GroupedAdam(torch.optim.Adam):
                 rows.append(_cabi.AdamTensor(
                     ptr(param), ptr(grad), ptr(state["exp_avg"]), ptr(state["exp_avg_sq"]), param.numel(),
                     lr / (1.0 - beta1 ** t), beta1, beta2, eps, 1.0 / math.sqrt(1.0 - beta2 ** t), 1.0 - beta1, 1.0 - beta2))
-        with torch.cuda.device(device) if device is not None else _null():
+        with device_guard(device) if device is not None else _null():
             for i in range(0, len(rows), _cabi.ADAM_MAX_TENSORS):
                 part = rows[i:i + _cabi.ADAM_MAX_TENSORS]
                 table = (_cabi.AdamTensor * len(part))(*part)

@@ -4,7 +4,7 @@ from typing import Tuple
 import torch
 from torch import Tensor
 
-from ._cabi import call, ptr, stream_ptr
+from ._cabi import call, device_guard, ptr, stream_ptr
 
 
 def compute_relocation(opacities: Tensor, scales: Tensor, ratios: Tensor, binoms: Tensor) -> Tuple[Tensor, Tensor]:
@@ -22,7 +22,7 @@ def compute_relocation(opacities: Tensor, scales: Tensor, ratios: Tensor, binoms
     ratios.clamp_(min=1, max=n_max)
     opac_c, scales_c, binoms_c, ratios_i = opacities.contiguous(), scales.contiguous(), binoms.contiguous(), ratios.int().contiguous()
     out_opacities, out_scales = torch.empty_like(opac_c), torch.empty_like(scales_c)
-    with torch.cuda.device(opacities.device):
+    with device_guard(opacities.device):
         call("gsb200_compute_relocation", n_gauss, ptr(opac_c), ptr(scales_c), ptr(ratios_i), ptr(binoms_c), n_max,
              ptr(out_opacities), ptr(out_scales), stream_ptr(opacities.device))
     return out_opacities, out_scales

@@ -33,6 +33,14 @@ from .cuda._wrapper import (
 
 def _camera_positions(viewmats: Tensor) -> Tensor:
     """World-space camera centres [C,3] of world-to-camera matrices [C,4,4]."""
+    if viewmats.is_cuda and viewmats.dtype == torch.float32 and not (viewmats.requires_grad and torch.is_grad_enabled()):
+        from ._cabi import call, device_guard, ptr, stream_ptr
+
+        vm = viewmats.contiguous()
+        campos = torch.empty((vm.shape[0], 3), dtype=torch.float32, device=vm.device)
+        with device_guard(vm.device):
+            call("gsb200_camera_positions", vm.shape[0], ptr(vm), ptr(campos), stream_ptr(vm.device))
+        return campos
     R = viewmats[:, :3, :3]
     t = viewmats[:, :3, 3]
     # rigid transform: inverse(viewmat)[:3,3] = -R^T t ; differentiable w.r.t. viewmats

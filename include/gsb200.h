@@ -215,6 +215,25 @@ int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float 
  *   _reduce_geo : backward, owner side (after a cross-rank barrier): sums the world slots of the local staging array in
  *                 rank order (reproducible) into outs[k] [n_rows, widths[k]] (NULL = not wanted).
  * Replaces the reduce-scatter of all_gather_tensor_list's backward (gsplat/distributed.py:102-167) for the geometry. */
+/* Camera centres campos [C,3] = -R^T t of rigid world-to-camera matrices viewmats [C,4,4] (row major): the
+ * `torch.inverse(viewmats)[:, :3, 3]` of the reference's colour stage (rendering.py:370) for rigid matrices. */
+int gsb200_camera_positions(uint32_t C, const float *viewmats, float *campos, gsb200_stream_t stream);
+/* Start of a distributed step, one launch: this rank's attribute tensors parts[k] [n_local, widths[k]] are written side by
+ * side into its published geometry block geo_block [n_block, w] (rows >= n_local = pad_row [w], an inert splat; NULL = 0),
+ * and its coefficient rows -- `first` [n_local, first_floats] next to `rest` [n_local, row_floats - first_floats] (NULL when
+ * first covers the row): the trainers' sh0 / shN -- into coeff_block [n_local, row_floats].  n_parts = 0 skips the
+ * geometry, first = NULL the coefficients.  Replaces the torch.cat / copies in front of the reference's all-gather
+ * (rendering.py:282-294). */
+int gsb200_shard_publish(uint32_t n_local, uint32_t n_block, uint32_t n_parts, const uint32_t *widths,
+                         float *const *parts, const float *pad_row, float *geo_block, const float *first,
+                         const float *rest, uint32_t first_floats, uint32_t row_floats, float *coeff_block,
+                         gsb200_stream_t stream);
+/* Stream-ordered barrier over the `world` ranks of one node.  pads[r]: rank r's signal pad (GSB200_MAX_SHARDS zero-
+ * initialised uint32 words in peer-mapped memory; a HOST array of device pointers); every rank passes the same, strictly
+ * increasing `epoch` for the same barrier.  The host does not block; kernels enqueued after it see every peer's writes
+ * made before its call.  Stands in for the implicit synchronisation of the reference's NCCL collectives
+ * (gsplat/distributed.py:90-215). */
+int gsb200_peer_barrier(uint32_t world, uint32_t rank, uint32_t *const *pads, uint32_t epoch, gsb200_stream_t stream);
 int gsb200_shard_gather_geo(uint32_t world, uint32_t n_block, uint32_t n_parts, const uint32_t *widths,
                             const float *const *blocks, float *const *outs, gsb200_stream_t stream);
 int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t rank, uint64_t slot_floats,
@@ -251,6 +270,10 @@ int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera
                          const float *depths, uint32_t tile_size, uint32_t tile_width,
                          uint32_t tile_height, int32_t *tiles_per_gauss, int32_t *isect_offsets,
                          int32_t *tile_cursor, int64_t *n_isects_host, gsb200_stream_t stream);
+/* Capacity mode helper: asynchronous 4-byte copy of the intersection count left by gsb200_isect_prepare at
+ * tile_cursor[total_index] (gsb200_isect_plan) into PINNED host memory; the host polls the word or waits on an event. */
+int gsb200_isect_count_async(const int32_t *tile_cursor, int64_t total_index, int32_t *count_pinned,
+                             gsb200_stream_t stream);
 int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_per_camera,
                       const int64_t *camera_ids, const float *means2d, const int32_t *radii,
                       const float *depths, uint32_t tile_size, uint32_t tile_width,

@@ -70,6 +70,23 @@ def main():
                 d = e.time_range.end - e.time_range.start
                 if d >= 15:
                     print(f"{s0 / 1e3:8.3f} ms  {d:7.1f} us  {e.name[:100]}")
+    # host profile of 20 further steps (rank 0): which Python functions own the host time of a distributed step
+    import cProfile
+    import pstats
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(20):
+        step()
+    pr.disable()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("---- cProfile, 20 steps, by own time")
+        pstats.Stats(pr).sort_stats("tottime").print_stats(30)
+        print("---- cProfile, 20 steps, cumulative")
+        pstats.Stats(pr).sort_stats("cumulative").print_stats(50)
     dist.destroy_process_group()
 
 

@@ -4,6 +4,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 P=gpurun_out/r2n2c
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+timeout 200 $TR --master-port 29511 tools/dist_check.py > ${P}_dist_check.log 2>&1; tail -12 ${P}_dist_check.log | grep -v "^\*\|OMP"
+timeout 300 python -m pytest tests -m gpu -q -x -p no:cacheprovider -k "dist or peer or shard" > ${P}_pytest.log 2>&1; tail -2 ${P}_pytest.log
 timeout 300 $TR --master-port 29512 tools/dist_profile.py > ${P}_dist_profile.log 2>&1; grep -E "step span" ${P}_dist_profile.log
 timeout 300 $TR --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 > ${P}_bench.json 2> ${P}_bench.err; python - <<'PY'
 import json
