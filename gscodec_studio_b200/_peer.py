@@ -40,6 +40,7 @@ def _ptr_table(ptrs: Sequence[int], byte_offset: int):
     return arr, ctypes.cast(arr, ctypes.c_void_p)
 
 
+GEOMETRY_ONLY_ROW = 4  # row width of the workspace that only carries geometry
 GEO_WIDTH = 12  # floats reserved per row of the geometry block (means 3 + quats 4 + scales 3 + opacity 1, or covars)
 
 
@@ -104,11 +105,15 @@ class PeerWorkspace:
         # one launch writes both blocks: the trainers' (sh0 [n,1,3], shN [n,K-1,3]) land side by side, the [n,K,3]
         # concatenation never exists outside this buffer
         first, rest = coeff_rows if isinstance(coeff_rows, (tuple, list)) else (coeff_rows, None)
-        first = first.detach().float().contiguous()
-        rest = None if rest is None else rest.detach().float().contiguous()
-        n = first.shape[0]
-        first_floats = first.numel() // max(n, 1)
-        assert n <= self.cap_block and first_floats + (0 if rest is None else rest.numel() // max(n, 1)) == self.row_floats
+        if first is None:  # geometry only (the owner-side colour exchange keeps the coefficients at home)
+            n, first_floats = geo_parts[0].shape[0], 0
+        else:
+            first = first.detach().float().contiguous()
+            rest = None if rest is None else rest.detach().float().contiguous()
+            n = first.shape[0]
+            first_floats = first.numel() // max(n, 1)
+            assert first_floats + (0 if rest is None else rest.numel() // max(n, 1)) == self.row_floats
+        assert n <= self.cap_block
         n_parts, w_ptr, p_ptr, keep = 0, None, None, None
         if geo_parts is not None:
             parts = [t.detach().float().contiguous() for t in geo_parts]
@@ -268,18 +273,21 @@ class _GatherGeometry(torch.autograd.Function):
         return (None, None) + tuple(outs)
 
 
-def publish_and_gather_geometry(geo_parts: Sequence[Tensor], pad_row: Tensor, coeffs_local: Tensor, n_block: int):
+def publish_and_gather_geometry(geo_parts: Sequence[Tensor], pad_row: Tensor, coeffs_local: Optional[Tensor], n_block: int):
     """Start of a distributed render: publish this rank's geometry rows and SH rows (one barrier), pull everybody's
     geometry.  Returns (tuple of the gathered attribute tensors [world * n_block, w_k] -- differentiable w.r.t. geo_parts
     --, version token to hand to view_colors_from_sh_sharded).  n_block must be a multiple of 4 and >= every rank's row
     count."""
     assert n_block % 4 == 0, n_block
     pair = isinstance(coeffs_local, (tuple, list))
-    dev = coeffs_local[0].device if pair else coeffs_local.device
-    K = coeffs_local[0].shape[1] + coeffs_local[1].shape[1] if pair else coeffs_local.shape[1]
-    ws = workspace(dev, K * 3, n_block)
+    dev = geo_parts[0].device
+    if coeffs_local is None:  # coefficients stay with their owner (view_colors_owner): geometry-only workspace
+        ws, rows = workspace(dev, GEOMETRY_ONLY_ROW, n_block), None
+    else:
+        K = coeffs_local[0].shape[1] + coeffs_local[1].shape[1] if pair else coeffs_local.shape[1]
+        ws = workspace(dev, K * 3, n_block)
+        rows = tuple(t.detach().float() for t in coeffs_local) if pair else coeffs_local.detach().float()
     parts = [t.detach().float() for t in geo_parts]
-    rows = tuple(t.detach().float() for t in coeffs_local) if pair else coeffs_local.detach().float()
     with device_guard(dev):
         version = ws.publish(rows, parts, pad_row, n_block)
     return _GatherGeometry.apply(ws, n_block, *[t.float() for t in geo_parts]), version
@@ -298,3 +306,152 @@ def view_colors_from_sh_sharded(sh_degree: int, means: Tensor, campos: Tensor, c
     assert (sh_degree + 1) ** 2 <= first.shape[1] + (rest.shape[1] if rest is not None else 0)
     return _ShViewSharded.apply(sh_degree, means.float().contiguous(), campos.float().contiguous(), first.float().contiguous(),
                                 None if rest is None else rest.float().contiguous(), radii.contiguous(), n_block, published)
+
+
+# ---- owner-side colour exchange ---------------------------------------------------------------------------------------------
+MAX_VIEWS = 64  # GSB200_MAX_VIEWS in include/gsb200.h
+_colour_workspaces: Dict[Tuple[int, int], "ColourExchange"] = {}
+
+
+class ColourExchange:
+    """Symmetric allocation of the owner-side colour exchange for C cameras per rank:
+         [ colours   C x world x cap_block x 3 ]   this rank's colour tensor [C, world * n_block, 3]; owner p writes rows
+                                                   p * n_block.. of every camera
+         [ masks     V x cap_block (int32) ]       view v's radii of THIS rank's rows, pushed by the viewer of v
+         [ v_colors  V x cap_block x 3 ]           view v's colour gradients of this rank's rows, pushed in the backward
+         [ campos    V x 4 ]                       every view's camera centre
+         [ pads ]                                  signal pad of the barrier kernel
+    V = world x C views, view v belongs to rank v // C."""
+
+    def __init__(self, device: torch.device, n_cameras: int, cap_block: int):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.C, self.cap_block, self.V = n_cameras, cap_block, self.world * n_cameras
+        n_col = n_cameras * self.world * cap_block * 3
+        n_mask = self.V * cap_block
+        n_vcol = self.V * cap_block * 3
+        n_cam = self.V * 4
+        n_pads = 4 * MAX_SHARDS
+        self.buf = symm_mem.empty(n_col + n_mask + n_vcol + n_cam + n_pads, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(self.ptrs) == self.world and all(p % 16 == 0 for p in self.ptrs), self.ptrs
+        o_mask, o_vcol = n_col, n_col + n_mask
+        o_cam, o_pads = o_vcol + n_vcol, o_vcol + n_vcol + n_cam
+        self.buf.zero_()  # colours of never-visible pairs are never written: keep them finite
+        self.colours = self.buf[:o_mask]
+        self.masks = self.buf[o_mask:o_vcol].view(torch.int32)
+        self.vcol = self.buf[o_vcol:o_cam]
+        self.campos = self.buf[o_cam:o_pads]
+        self._mask_tab = _ptr_table(self.ptrs, 4 * o_mask)
+        self._vcol_tab = _ptr_table(self.ptrs, 4 * o_vcol)
+        self._cam_tab = _ptr_table(self.ptrs, 4 * o_cam)
+        self._pad_tab = _ptr_table(self.ptrs, 4 * o_pads)
+        self._colour_tabs: Dict[int, tuple] = {}
+        self.epoch = 0
+        self.hdl.barrier(channel=0)  # every pad is zero before the first signal can arrive
+
+    def barrier(self) -> None:
+        self.epoch = (self.epoch + 1) & 0xFFFFFFFF
+        call("gsb200_peer_barrier", self.world, self.rank, self._pad_tab[1], self.epoch, stream_ptr(self.buf.device))
+
+    def colour_table(self, n_block: int):
+        """view v = (rank q, camera c) -> address of THIS rank's [n_block, 3] rows inside q's colour tensor."""
+        tab = self._colour_tabs.get(n_block)
+        if tab is None:
+            n_total = self.world * n_block
+            addrs = [self.ptrs[v // self.C] + 4 * ((v % self.C) * n_total + self.rank * n_block) * 3 for v in range(self.V)]
+            arr = (ctypes.c_void_p * self.V)(*addrs)
+            self._colour_tabs[n_block] = tab = (arr, ctypes.cast(arr, ctypes.c_void_p))
+        return tab[1]
+
+
+def colour_workspace(device: torch.device, n_cameras: int, n_block: int) -> ColourExchange:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), n_cameras)
+    ws = _colour_workspaces.get(key)
+    if ws is None or ws.cap_block < n_block or ws.world != dist.get_world_size():
+        if ws is not None:
+            ws.barrier()
+            _colour_workspaces.pop(key)
+            del ws
+        cap = (int(n_block * 1.1) + 64 + 3) // 4 * 4
+        _colour_workspaces[key] = ws = ColourExchange(device, n_cameras, cap)
+    return ws
+
+
+def owner_exchange_available(device: torch.device, n_cameras: int, n_block: int) -> bool:
+    """The owner-side colour exchange needs what available() needs, at most MAX_VIEWS views in the job, and the same number
+    of cameras on every rank (the caller's contract).  GSB200_SH_EXCHANGE=pull keeps the coefficient-pull path."""
+    if os.environ.get("GSB200_SH_EXCHANGE", "owner") == "pull":
+        return False
+    if not available(device, GEOMETRY_ONLY_ROW, n_block) or dist.get_world_size() * n_cameras > MAX_VIEWS:
+        return False
+    try:
+        colour_workspace(device, n_cameras, n_block)
+    except Exception as e:  # pragma: no cover - same failure on every rank
+        warnings.warn(f"owner-side colour exchange unavailable ({type(e).__name__}: {e}); pulling coefficient rows instead")
+        return False
+    return True
+
+
+class _ShOwnerExchange(torch.autograd.Function):
+    """View colours [C, world * n_block, 3] of the gathered set, evaluated by the owners of the coefficients.
+    forward : push this rank's radii + camera centres to every owner | barrier | evaluate the own rows for all V views,
+              storing the colours into the viewers' tensors over NVLink | barrier
+    backward: push v_colors rows to their owners | barrier | owner-side SH backward -> gradients of the LOCAL sh0, shN and
+              means (no coefficient or coefficient-gradient row ever crosses the link)."""
+
+    @staticmethod
+    def forward(ctx, sh_degree, means_local, campos, sh0, shN, radii, n_block):
+        dev = means_local.device
+        C, n_total = radii.shape
+        ws = colour_workspace(dev, C, n_block)
+        assert n_total == ws.world * n_block and campos.shape == (C, 3), (radii.shape, campos.shape, n_block)
+        K = 1 + shN.shape[1]
+        n_local = means_local.shape[0]
+        with device_guard(dev):
+            call("gsb200_shard_push_rows", ws.world, n_block, 1, C, ws.rank * C, n_block, ptr(radii), ws._mask_tab[1],
+                 ptr(campos), 3, ws._cam_tab[1], stream_ptr(dev))
+            ws.barrier()  # every viewer's masks and camera centres have landed
+            # private copies: the staging is overwritten by the next forward, the backward of THIS one may come later
+            masks = ws.masks[: ws.V * n_block].clone()
+            campos_all = ws.campos[: ws.V * 3].clone()
+            call("gsb200_sh_owner_fwd", ws.V, n_local, n_block, K, sh_degree, ptr(means_local), ptr(campos_all), ptr(sh0),
+                 ptr(shN), ptr(masks), ws.colour_table(n_block), stream_ptr(dev))
+            ws.barrier()  # every owner's colours have landed
+        ctx.save_for_backward(means_local, sh0, shN, masks, campos_all)
+        ctx.cfg = (sh_degree, n_block, C, K)
+        colours = ws.colours[: C * n_total * 3].view(C, n_total, 3)
+        return colours
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        means_local, sh0, shN, masks, campos_all = ctx.saved_tensors
+        sh_degree, n_block, C, K = ctx.cfg
+        dev = means_local.device
+        ws = colour_workspace(dev, C, n_block)
+        n_local = means_local.shape[0]
+        v_colors = v_colors.contiguous()
+        v_sh0 = torch.empty((n_local, 1, 3), dtype=torch.float32, device=dev)
+        v_shN = torch.empty((n_local, K - 1, 3), dtype=torch.float32, device=dev)
+        v_means = torch.empty_like(means_local) if ctx.needs_input_grad[1] else None
+        with device_guard(dev):
+            call("gsb200_shard_push_rows", ws.world, n_block, 3, C, ws.rank * C, n_block * 3, ptr(v_colors), ws._vcol_tab[1],
+                 None, 0, None, stream_ptr(dev))
+            ws.barrier()  # every viewer's colour gradients have landed
+            call("gsb200_sh_owner_bwd", ws.V, n_local, n_block, K, sh_degree, ptr(means_local), ptr(campos_all), ptr(sh0), ptr(shN),
+                 ptr(masks), ptr(ws.vcol), ptr(v_sh0), ptr(v_shN), ptr(v_means), stream_ptr(dev))
+        return None, v_means, None, v_sh0, v_shN, None, None
+
+
+def view_colors_owner(sh_degree: int, means_local: Tensor, campos: Tensor, sh_pair, radii: Tensor, n_block: int) -> Tensor:
+    """Distributed colour stage, owner-side form: `means_local` [n_local,3], `sh_pair` = (sh0 [n_local,1,3],
+    shN [n_local,K-1,3]) are THIS rank's shard, `campos` [C,3] and `radii` [C, world * n_block] this rank's views of the
+    gathered set.  Returns the colours [C, world * n_block, 3] (rows of invisible pairs hold stale finite values; the blend
+    never reads them).  Differentiable w.r.t. means_local, sh0, shN; not w.r.t. campos (use the pull path for that)."""
+    sh0, shN = sh_pair
+    assert sh0.dim() == 3 and sh0.shape[1:] == (1, 3) and shN.dim() == 3 and shN.shape[2] == 3, (sh0.shape, shN.shape)
+    assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1]
+    return _ShOwnerExchange.apply(sh_degree, means_local.float().contiguous(), campos.detach().float().contiguous(),
+                                  sh0.float().contiguous(), shN.float().contiguous(), radii.contiguous(), n_block)

@@ -716,16 +716,48 @@ shard_reduce_geo_kernel(uint32_t world, uint32_t n_rows, uint64_t slot_floats, c
 // are staged in shared memory and written with coalesced 16-byte stores, exactly once.
 constexpr int kSplitThreads = 128;
 
-template <int DEG>
+// Where a (view, Gaussian) pair's visibility, camera centre, colour and colour gradient live.  LocalViews: the viewer
+// evaluates its own views over all N Gaussians (single GPU, or gathered coefficients).  PeerViews: the OWNER of a shard
+// evaluates its rows for every view of the job -- masks and colour gradients were pushed into local staging by the
+// viewers, the colours are stored straight into the viewers' colour tensors over NVLink (12 bytes per visible pair
+// instead of the 16x3-float coefficient row travelling the other way).
+struct LocalViews {
+    const float *campos;
+    const int32_t *radii;
+    float *colors;
+    const float *v_colors;
+    uint32_t N;
+    static constexpr bool kWriteInvisible = true;  // the local colour tensor is torch.empty: invisible rows are zeroed
+    __device__ __forceinline__ bool visible(uint32_t c, uint32_t g) const { return radii[(size_t)c * N + g] > 0; }
+    __device__ __forceinline__ const float *cam(uint32_t c) const { return campos + c * 3; }
+    __device__ __forceinline__ float *color(uint32_t c, uint32_t g) const { return colors + ((size_t)c * N + g) * 3; }
+    __device__ __forceinline__ const float *v_color(uint32_t c, uint32_t g) const { return v_colors + ((size_t)c * N + g) * 3; }
+};
+constexpr int kMaxViews = GSB200_MAX_VIEWS;
+struct PeerViews {
+    const float *campos;       // local [V,3]: every view's camera centre (pushed by the viewers)
+    const int32_t *masks;      // local [V, n_block]: radii of this owner's rows in view v (pushed by the viewers)
+    const float *v_colors;     // local [V, n_block, 3]: colour gradients of this owner's rows (pushed by the viewers)
+    float *colors[kMaxViews];  // view v: this owner's [n_block, 3] slice of the viewer's colour tensor (peer memory)
+    uint32_t n_block;
+    static constexpr bool kWriteInvisible = false;  // nothing travels for an invisible pair (the blend never reads it)
+    __device__ __forceinline__ bool visible(uint32_t c, uint32_t g) const { return masks[(size_t)c * n_block + g] > 0; }
+    __device__ __forceinline__ const float *cam(uint32_t c) const { return campos + c * 3; }
+    __device__ __forceinline__ float *color(uint32_t c, uint32_t g) const { return colors[c] + (size_t)g * 3; }
+    __device__ __forceinline__ const float *v_color(uint32_t c, uint32_t g) const {
+        return v_colors + ((size_t)c * n_block + g) * 3;
+    }
+};
+
+template <int DEG, typename VIEWS>
 __global__ void __launch_bounds__(kSplitThreads)
-sh_view_split_fwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__restrict__ means, const float *__restrict__ campos,
-                         const float *__restrict__ sh0, const float *__restrict__ shN, const int32_t *__restrict__ radii,
-                         float *__restrict__ colors) {
+sh_view_split_fwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__restrict__ means, const float *__restrict__ sh0,
+                         const float *__restrict__ shN, const __grid_constant__ VIEWS views) {
     constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
     const uint32_t g = blockIdx.x * kSplitThreads + threadIdx.x;
     if (g >= N) return;
     bool any = false;
-    for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
+    for (uint32_t c = 0; c < C; ++c) any |= views.visible(c, g);
     float cf[nb * 3];
     float mx = 0.f, my = 0.f, mz = 0.f;
     if (any) {
@@ -738,10 +770,11 @@ sh_view_split_fwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
         mx = means[(size_t)g * 3]; my = means[(size_t)g * 3 + 1]; mz = means[(size_t)g * 3 + 2];
     }
     for (uint32_t c = 0; c < C; ++c) {
-        const size_t idx = (size_t)c * N + g;
         float r = 0.f, gg = 0.f, b = 0.f;
-        if (radii[idx] > 0) {
-            float x = mx - campos[c * 3], y = my - campos[c * 3 + 1], z = mz - campos[c * 3 + 2];
+        const bool vis = any && views.visible(c, g);
+        if (vis) {
+            const float *cam = views.cam(c);
+            float x = mx - cam[0], y = my - cam[1], z = mz - cam[2];
             if (DEG > 0) {
                 const float inorm = rsqrtf(x * x + y * y + z * z);
                 x *= inorm; y *= inorm; z *= inorm;
@@ -751,16 +784,18 @@ sh_view_split_fwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
             });
             r = fmaxf(r + 0.5f, 0.f); gg = fmaxf(gg + 0.5f, 0.f); b = fmaxf(b + 0.5f, 0.f);
         }
-        colors[idx * 3] = r; colors[idx * 3 + 1] = gg; colors[idx * 3 + 2] = b;
+        if (vis || VIEWS::kWriteInvisible) {
+            float *col = views.color(c, g);
+            col[0] = r; col[1] = gg; col[2] = b;
+        }
     }
 }
 
-template <int DEG>
+template <int DEG, typename VIEWS>
 __global__ void __launch_bounds__(kSplitThreads)
-sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__restrict__ means, const float *__restrict__ campos,
-                         const float *__restrict__ sh0, const float *__restrict__ shN, const int32_t *__restrict__ radii,
-                         const float *__restrict__ v_colors, float *__restrict__ v_sh0, float *__restrict__ v_shN,
-                         float *__restrict__ v_means, float *__restrict__ v_campos) {
+sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__restrict__ means, const float *__restrict__ sh0,
+                         const float *__restrict__ shN, const __grid_constant__ VIEWS views, float *__restrict__ v_sh0,
+                         float *__restrict__ v_shN, float *__restrict__ v_means, float *__restrict__ v_campos) {
     extern __shared__ float s_slab[];  // [kSplitThreads][RF | 1]: the block's v_shN rows
     __shared__ float s_red[kSplitThreads / 32][3];
     constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
@@ -773,7 +808,7 @@ sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
     float vmx = 0.f, vmy = 0.f, vmz = 0.f;
     bool any = false;
     if (g < N)
-        for (uint32_t c = 0; c < C; ++c) any |= radii[(size_t)c * N + g] > 0;
+        for (uint32_t c = 0; c < C; ++c) any |= views.visible(c, g);
     float cf[nb * 3];
     float mx = 0.f, my = 0.f, mz = 0.f;
     if (any) {
@@ -787,9 +822,9 @@ sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
     }
     for (uint32_t c = 0; c < C; ++c) {
         float dxv = 0.f, dyv = 0.f, dzv = 0.f;
-        if (any && radii[(size_t)c * N + g] > 0) {
-            const size_t idx = (size_t)c * N + g;
-            float x = mx - campos[c * 3], y = my - campos[c * 3 + 1], z = mz - campos[c * 3 + 2];
+        if (any && views.visible(c, g)) {
+            const float *cam = views.cam(c), *vcol = views.v_color(c, g);
+            float x = mx - cam[0], y = my - cam[1], z = mz - cam[2];
             float inorm = 1.f;
             if (DEG > 0) {
                 inorm = rsqrtf(x * x + y * y + z * z);
@@ -799,9 +834,9 @@ sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
             sh_terms(DEG, x, y, z, [&](int k, float Y, float, float, float) {
                 r += Y * cf[k * 3]; gg += Y * cf[k * 3 + 1]; b += Y * cf[k * 3 + 2];
             });
-            const float vr = (r + 0.5f >= 0.f) ? v_colors[idx * 3] : 0.f;
-            const float vg = (gg + 0.5f >= 0.f) ? v_colors[idx * 3 + 1] : 0.f;
-            const float vb = (b + 0.5f >= 0.f) ? v_colors[idx * 3 + 2] : 0.f;
+            const float vr = (r + 0.5f >= 0.f) ? vcol[0] : 0.f;
+            const float vg = (gg + 0.5f >= 0.f) ? vcol[1] : 0.f;
+            const float vb = (b + 0.5f >= 0.f) ? vcol[2] : 0.f;
             float gx = 0.f, gy = 0.f, gz = 0.f;
             sh_terms(DEG, x, y, z, [&](int k, float Y, float dx, float dy, float dz) {
                 vc[k * 3] += Y * vr; vc[k * 3 + 1] += Y * vg; vc[k * 3 + 2] += Y * vb;
@@ -864,6 +899,30 @@ sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
         const uint32_t r = i / RF, cc = i - r * RF;
         dst[i] = cc < nact ? s_slab[r * stride + cc] : 0.f;
     }
+}
+
+
+// viewer -> owners: slot c of src ([n_slots][world * n_block, width]; rows p * n_block.. belong to owner p) is stored as one
+// dense [n_block * width] block into owner p's staging at slot (slot0 + c), 16-byte vectors over NVLink; block (0, p, c)
+// also delivers the slot's `extra_w` extra floats (the view's camera centre) to owner p.
+__global__ void __launch_bounds__(kThreads)
+shard_push_rows_kernel(uint32_t n_block, uint32_t width, uint32_t slot0, uint64_t slot_floats, const float *__restrict__ src,
+                       uint64_t src_slot_floats, const PeerRows peers, const float *__restrict__ extra_src, uint32_t extra_w,
+                       const PeerRows peer_extra) {
+    const uint32_t p = blockIdx.y, c = blockIdx.z;
+    const uint64_t n_vec = (uint64_t)n_block * width / 4;
+    const float *from = src + (size_t)c * src_slot_floats + (size_t)p * n_block * width;
+    float *dst = peers.base[p] + (size_t)(slot0 + c) * slot_floats;
+    const uint64_t i0 = (uint64_t)blockIdx.x * kThreads * kGeoUnroll + threadIdx.x;
+    float4 v[kGeoUnroll];
+#pragma unroll
+    for (int u = 0; u < kGeoUnroll; ++u)
+        if (i0 + (uint64_t)u * kThreads < n_vec) v[u] = ldg4(from + (i0 + (uint64_t)u * kThreads) * 4);
+#pragma unroll
+    for (int u = 0; u < kGeoUnroll; ++u)
+        if (i0 + (uint64_t)u * kThreads < n_vec) stg4(dst + (i0 + (uint64_t)u * kThreads) * 4, v[u]);
+    if (blockIdx.x == 0 && extra_src != nullptr && threadIdx.x < extra_w)
+        peer_extra.base[p][(size_t)(slot0 + c) * extra_w + threadIdx.x] = extra_src[(size_t)c * extra_w + threadIdx.x];
 }
 
 }  // namespace gsb200
@@ -1245,20 +1304,44 @@ static int check_split_args(const char *who, uint32_t K, uint32_t degree, const 
     return 0;
 }
 
+template <typename VIEWS>
+static void launch_split_fwd(cudaStream_t s, uint32_t degree, uint32_t C, uint32_t N, uint32_t K, const float *means, const float *sh0,
+                             const float *shN, const VIEWS &views) {
+    const uint32_t grid = cdiv(N, kSplitThreads), RF = (K - 1) * 3;
+    switch (degree) {
+        case 0: sh_view_split_fwd_kernel<0, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
+        case 1: sh_view_split_fwd_kernel<1, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
+        case 2: sh_view_split_fwd_kernel<2, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
+        case 3: sh_view_split_fwd_kernel<3, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
+        default: sh_view_split_fwd_kernel<4, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
+    }
+}
+
+template <typename VIEWS>
+static void launch_split_bwd(cudaStream_t s, uint32_t degree, uint32_t C, uint32_t N, uint32_t K, const float *means, const float *sh0,
+                             const float *shN, const VIEWS &views, float *v_sh0, float *v_shN, float *v_means, float *v_campos) {
+    const uint32_t grid = cdiv(N, kSplitThreads), RF = (K - 1) * 3;
+    const size_t smem = sizeof(float) * kSplitThreads * (RF | 1u);
+#define GSB_SPLIT_BWD(D)                                                                                                      \
+    sh_view_split_bwd_kernel<D, VIEWS><<<grid, kSplitThreads, smem, s>>>(C, N, RF, means, sh0, shN, views, v_sh0, v_shN, v_means, \
+                                                                         v_campos)
+    switch (degree) {
+        case 0: GSB_SPLIT_BWD(0); break;
+        case 1: GSB_SPLIT_BWD(1); break;
+        case 2: GSB_SPLIT_BWD(2); break;
+        case 3: GSB_SPLIT_BWD(3); break;
+        default: GSB_SPLIT_BWD(4); break;
+    }
+#undef GSB_SPLIT_BWD
+}
+
 extern "C" int gsb200_sh_view_split_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means, const float *campos,
                                         const float *sh0, const float *shN, const int32_t *radii, float *colors,
                                         gsb200_stream_t stream) {
     if (int rc = check_split_args("gsb200_sh_view_split_fwd", K, degree, sh0, shN)) return rc;
     if (C == 0 || N == 0) return 0;
-    cudaStream_t s = (cudaStream_t)stream;
-    const uint32_t grid = cdiv(N, kSplitThreads), RF = (K - 1) * 3;
-    switch (degree) {
-        case 0: sh_view_split_fwd_kernel<0><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
-        case 1: sh_view_split_fwd_kernel<1><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
-        case 2: sh_view_split_fwd_kernel<2><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
-        case 3: sh_view_split_fwd_kernel<3><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
-        default: sh_view_split_fwd_kernel<4><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, campos, sh0, shN, radii, colors); break;
-    }
+    const LocalViews views{campos, radii, colors, nullptr, N};
+    launch_split_fwd((cudaStream_t)stream, degree, C, N, K, means, sh0, shN, views);
     return check_launch("sh_view_split_fwd");
 }
 
@@ -1272,18 +1355,81 @@ extern "C" int gsb200_sh_view_split_bwd(uint32_t C, uint32_t N, uint32_t K, uint
     if ((reinterpret_cast<uintptr_t>(v_shN) & 15) != 0) return failf(2, "%s: v_shN must be 16-byte aligned", who);
     cudaStream_t s = (cudaStream_t)stream;
     if (v_campos != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_campos, 0, sizeof(float) * 3 * C, s));
-    const uint32_t grid = cdiv(N, kSplitThreads), RF = (K - 1) * 3;
-    const size_t smem = sizeof(float) * kSplitThreads * (RF | 1u);
-#define GSB_SPLIT_BWD(D)                                                                                                   \
-    sh_view_split_bwd_kernel<D><<<grid, kSplitThreads, smem, s>>>(C, N, RF, means, campos, sh0, shN, radii, v_colors, v_sh0, \
-                                                                  v_shN, v_means, v_campos)
-    switch (degree) {
-        case 0: GSB_SPLIT_BWD(0); break;
-        case 1: GSB_SPLIT_BWD(1); break;
-        case 2: GSB_SPLIT_BWD(2); break;
-        case 3: GSB_SPLIT_BWD(3); break;
-        default: GSB_SPLIT_BWD(4); break;
-    }
-#undef GSB_SPLIT_BWD
+    const LocalViews views{campos, radii, nullptr, v_colors, N};
+    launch_split_bwd(s, degree, C, N, K, means, sh0, shN, views, v_sh0, v_shN, v_means, v_campos);
     return check_launch("sh_view_split_bwd");
+}
+
+static int make_peer_views(const char *who, uint32_t V, uint32_t n_local, uint32_t n_block, const float *campos, const int32_t *masks,
+                           const float *v_colors, float *const *view_colors, PeerViews &views) {
+    if (V == 0 || V > (uint32_t)kMaxViews) return failf(2, "%s: 1..%d views", who, kMaxViews);
+    if (n_local > n_block) return failf(2, "%s: n_local > n_block", who);
+    if (campos == nullptr || masks == nullptr) return failf(2, "%s: null campos / masks", who);
+    views = PeerViews{};
+    views.campos = campos;
+    views.masks = masks;
+    views.v_colors = v_colors;
+    views.n_block = n_block;
+    for (uint32_t v = 0; v < V; ++v) views.colors[v] = view_colors ? view_colors[v] : nullptr;
+    return 0;
+}
+
+extern "C" int gsb200_sh_owner_fwd(uint32_t V, uint32_t n_local, uint32_t n_block, uint32_t K, uint32_t degree, const float *means,
+                                   const float *campos, const float *sh0, const float *shN, const int32_t *masks,
+                                   float *const *view_colors, gsb200_stream_t stream) {
+    const char *who = "gsb200_sh_owner_fwd";
+    if (int rc = check_split_args(who, K, degree, sh0, shN)) return rc;
+    PeerViews views;
+    if (int rc = make_peer_views(who, V, n_local, n_block, campos, masks, nullptr, view_colors, views)) return rc;
+    if (view_colors == nullptr) return failf(2, "%s: null colour table", who);
+    for (uint32_t v = 0; v < V; ++v)
+        if (views.colors[v] == nullptr) return failf(2, "%s: null colour pointer", who);
+    if (n_local == 0) return 0;
+    launch_split_fwd((cudaStream_t)stream, degree, V, n_local, K, means, sh0, shN, views);
+    return check_launch("sh_owner_fwd");
+}
+
+extern "C" int gsb200_sh_owner_bwd(uint32_t V, uint32_t n_local, uint32_t n_block, uint32_t K, uint32_t degree, const float *means,
+                                   const float *campos, const float *sh0, const float *shN, const int32_t *masks,
+                                   const float *v_colors, float *v_sh0, float *v_shN, float *v_means, gsb200_stream_t stream) {
+    const char *who = "gsb200_sh_owner_bwd";
+    if (int rc = check_split_args(who, K, degree, sh0, shN)) return rc;
+    PeerViews views;
+    if (int rc = make_peer_views(who, V, n_local, n_block, campos, masks, v_colors, nullptr, views)) return rc;
+    if (v_colors == nullptr) return failf(2, "%s: null v_colors", who);
+    if (n_local == 0) return 0;
+    if (v_sh0 == nullptr || (K > 1 && v_shN == nullptr)) return failf(2, "%s: null gradient pointer", who);
+    if ((reinterpret_cast<uintptr_t>(v_shN) & 15) != 0) return failf(2, "%s: v_shN must be 16-byte aligned", who);
+    launch_split_bwd((cudaStream_t)stream, degree, V, n_local, K, means, sh0, shN, views, v_sh0, v_shN, v_means, nullptr);
+    return check_launch("sh_owner_bwd");
+}
+
+extern "C" int gsb200_shard_push_rows(uint32_t world, uint32_t n_block, uint32_t width, uint32_t n_slots, uint32_t slot0,
+                                      uint64_t slot_floats, const float *src, float *const *peer_staging, const float *extra_src,
+                                      uint32_t extra_w, float *const *peer_extra, gsb200_stream_t stream) {
+    const char *who = "gsb200_shard_push_rows";
+    if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "%s: world must be in [1, %d]", who, kMaxShards);
+    if (n_block % 4 != 0 || width == 0) return failf(2, "%s: n_block must be a multiple of 4 and width > 0", who);
+    if ((uint64_t)n_block * width > slot_floats || slot_floats % 4 != 0) return failf(2, "%s: staging slot too small or unaligned", who);
+    if (n_slots == 0 || n_slots > 65535u) return failf(2, "%s: 1..65535 slots per call", who);
+    if (extra_src != nullptr && (extra_w == 0 || extra_w > (uint32_t)kThreads || peer_extra == nullptr))
+        return failf(2, "%s: bad extra payload", who);
+    if (n_block == 0) return 0;
+    if (src == nullptr || (reinterpret_cast<uintptr_t>(src) & 15) != 0) return failf(2, "%s: src must be non-null and 16-byte aligned", who);
+    PeerRows peers{}, extras{};
+    for (uint32_t r = 0; r < world; ++r) {
+        peers.base[r] = peer_staging[r];
+        if (peers.base[r] == nullptr || (reinterpret_cast<uintptr_t>(peers.base[r]) & 15) != 0)
+            return failf(2, "%s: staging pointers must be non-null and 16-byte aligned", who);
+        if (extra_src != nullptr) {
+            extras.base[r] = peer_extra[r];
+            if (extras.base[r] == nullptr) return failf(2, "%s: null extra pointer", who);
+        }
+    }
+    const uint64_t n_vec = (uint64_t)n_block * width / 4;
+    const dim3 grid((uint32_t)((n_vec + kThreads * kGeoUnroll - 1) / (kThreads * kGeoUnroll)), world, n_slots);
+    shard_push_rows_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, width, slot0, slot_floats, src,
+                                                                        (uint64_t)world * n_block * width, peers, extra_src, extra_w,
+                                                                        extras);
+    return check_launch("shard_push_rows");
 }

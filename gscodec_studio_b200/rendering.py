@@ -177,17 +177,28 @@ def rasterization(
         from . import _peer
 
         n_block = (max(counts) + 3) // 4 * 4
-        if sh_pair_dist is not None:
+        means_local = means
+        # Preferred colour path: the coefficients never move.  Every rank evaluates ITS rows for all views of the job and
+        # stores the colours into the viewers' tensors; the backward sends colour gradients home (_peer.view_colors_owner)
+        owner_colors = (sh_pair_dist is not None and sh_degree is not None and not packed
+                        and sh_pair_dist[1].shape[1] <= SH_SPLIT_MAX_REST
+                        and not (viewmats.requires_grad and torch.is_grad_enabled())
+                        and _peer.owner_exchange_available(device, C, n_block))
+        if sh_pair_dist is not None and not owner_colors:
             k_all = 1 + sh_pair_dist[1].shape[1]
             if _peer.available(device, k_all * 3, n_block):
                 colors = sh_pair_dist  # published side by side, gradients come back per parameter
             else:
                 colors = torch.cat(sh_pair_dist, dim=1)
-        pull_colors = (sh_degree is not None and not packed and (isinstance(colors, tuple) or colors.dim() == 3)
+        pull_colors = (not owner_colors and sh_degree is not None and not packed
+                       and (isinstance(colors, tuple) or colors.dim() == 3)
                        and _peer.available(device, (1 + colors[1].shape[1] if isinstance(colors, tuple) else colors.shape[1]) * 3,
                                            n_block))
         colors_local = colors
-        if pull_colors:
+        if owner_colors:
+            geo, published = _peer.publish_and_gather_geometry(geo_parts, pad_row, None, n_block)
+            pending_colors = None
+        elif pull_colors:
             geo, published = _peer.publish_and_gather_geometry(geo_parts, pad_row, colors_local, n_block)
             pending_colors = None
         else:
@@ -203,7 +214,7 @@ def rasterization(
         colors = None
         N = means.shape[0]
     else:
-        pending_colors, pull_colors = None, False
+        pending_colors, pull_colors, owner_colors = None, False, False
 
     proj_results = fully_fused_projection(
         means, covars, quats, scales, viewmats, Ks, width, height,
@@ -245,6 +256,8 @@ def rasterization(
         campos = _camera_positions(viewmats) if rigid_viewmats else torch.inverse(viewmats)[:, :3, 3]
         if sh_pair is not None:
             colors = view_colors_from_sh_split(sh_degree, means, campos, sh_pair[0], sh_pair[1], radii)
+        elif owner_colors:
+            colors = _peer.view_colors_owner(sh_degree, means_local, campos, sh_pair_dist, radii, n_block)
         elif pull_colors:
             colors = _peer.view_colors_from_sh_sharded(sh_degree, means, campos, colors_local, radii, n_block, published)
         elif not packed and colors.dim() == 3:

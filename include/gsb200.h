@@ -183,6 +183,7 @@ int gsb200_sh_view_split_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree
  *   out[i] = sum over source ranks p (in rank order) of staging[p][i] where flags[p][i] != 0,  i < n_rows.
  * The caller orders the phases across ranks (publish -> barrier -> pull; push -> barrier -> reduce -> barrier). */
 #define GSB200_MAX_SHARDS 16
+#define GSB200_MAX_VIEWS 64 /* views of the whole job (ranks x cameras per rank) in the owner-side colour exchange */
 int gsb200_sh_view_fwd_sharded(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
                                const float *campos, const float *const *shard_coeffs, uint32_t world,
                                uint32_t n_block, const int32_t *radii, float *colors, float *row_cache,
@@ -215,6 +216,33 @@ int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float 
  *   _reduce_geo : backward, owner side (after a cross-rank barrier): sums the world slots of the local staging array in
  *                 rank order (reproducible) into outs[k] [n_rows, widths[k]] (NULL = not wanted).
  * Replaces the reduce-scatter of all_gather_tensor_list's backward (gsplat/distributed.py:102-167) for the geometry. */
+/* Owner-side colour exchange (view-parallel rendering, coefficients sharded by owner).  Instead of pulling the
+ * 16x3-float coefficient rows of visible Gaussians to the viewer, the OWNER of a shard evaluates its rows for every view
+ * of the job and only colours (forward) and colour gradients (backward) -- 12 bytes per visible (view, Gaussian) pair --
+ * cross NVLink; the coefficient gradients never leave their owner.  V = ranks x cameras per rank views, view v belongs to
+ * rank v / C.  All staging arrays live in peer-mapped memory; barriers between the steps are the caller's
+ * (gsb200_peer_barrier).
+ *   _shard_push_rows : viewer side.  src [n_slots][world * n_block, width] (a rank's radii [C, N] as bit patterns, or its
+ *                      v_colors [C, N, 3]); the rows of owner p travel as one dense block into peer_staging[p] at slot
+ *                      (slot0 + c), slot_floats apart; extra_src [n_slots, extra_w] (camera centres; NULL = none) goes to
+ *                      peer_extra[p] + (slot0 + c) * extra_w.  HOST arrays of device pointers.
+ *   _sh_owner_fwd    : owner side, after a barrier.  means [n_local,3], sh0 [n_local,1,3], shN [n_local,K-1,3] local;
+ *                      campos [V,3], masks [V, n_block] (> 0 = visible) local staging; view_colors[v] = address of this
+ *                      owner's [n_block,3] slice inside view v's colour tensor (HOST array of V device pointers).
+ *                      Invisible pairs are not written.
+ *   _sh_owner_bwd    : owner side, after the viewers pushed v_colors [V, n_block, 3] and a barrier.  Overwrites v_sh0,
+ *                      v_shN (dense, 16-byte aligned) and v_means [n_local,3] (NULL = not wanted), summing the views in
+ *                      order (reproducible).  Camera-centre gradients are not produced on this path.
+ * Replaces the coefficient all-to-all of the reference's distributed mode (rendering.py:397-478). */
+int gsb200_shard_push_rows(uint32_t world, uint32_t n_block, uint32_t width, uint32_t n_slots, uint32_t slot0,
+                           uint64_t slot_floats, const float *src, float *const *peer_staging, const float *extra_src,
+                           uint32_t extra_w, float *const *peer_extra, gsb200_stream_t stream);
+int gsb200_sh_owner_fwd(uint32_t V, uint32_t n_local, uint32_t n_block, uint32_t K, uint32_t degree, const float *means,
+                        const float *campos, const float *sh0, const float *shN, const int32_t *masks,
+                        float *const *view_colors, gsb200_stream_t stream);
+int gsb200_sh_owner_bwd(uint32_t V, uint32_t n_local, uint32_t n_block, uint32_t K, uint32_t degree, const float *means,
+                        const float *campos, const float *sh0, const float *shN, const int32_t *masks,
+                        const float *v_colors, float *v_sh0, float *v_shN, float *v_means, gsb200_stream_t stream);
 /* Camera centres campos [C,3] = -R^T t of rigid world-to-camera matrices viewmats [C,4,4] (row major): the
  * `torch.inverse(viewmats)[:, :3, 3]` of the reference's colour stage (rendering.py:370) for rigid matrices. */
 int gsb200_camera_positions(uint32_t C, const float *viewmats, float *campos, gsb200_stream_t stream);
