@@ -550,53 +550,28 @@ struct PeerRows {
     float *base[kMaxShards];
 };
 
-__device__ __forceinline__ void geo_locate(const GeoParts &P, uint32_t col, uint32_t &part, uint32_t &c) {
+// Block / staging-slot layout: the parts one after the other, part k = its [n_block, width_k] rows, dense, at float offset
+// n_block * col0_k (a multiple of 4: n_block is).  Every kernel moves 16-byte vectors that are contiguous on BOTH sides
+// (several in flight per thread -- NVLink latency is ~1.8 k cycles); nothing is scattered element-wise.
+constexpr int kGeoUnroll = 4;
+
+__device__ __forceinline__ void geo_vec_locate(const GeoParts &P, uint32_t n_block, uint64_t e0, uint32_t &part, uint64_t &e) {
     part = 0;
 #pragma unroll
     for (uint32_t k = 1; k < 4; ++k)
-        if (k < P.n_parts && col >= P.col0[k]) part = k;
-    c = col - P.col0[part];
+        if (k < P.n_parts && e0 >= (uint64_t)n_block * P.col0[k]) part = k;
+    e = e0 - (uint64_t)n_block * P.col0[part];
 }
 
-// All three kernels move 16-byte vectors of the dense [rows, w] block / staging layout (the remote side of every access is
-// a coalesced 128-bit load or store, several in flight per thread -- NVLink latency is ~1.8 k cycles) and scatter / gather
-// the 1..4 floats of a vector to / from the attribute tensors locally.
-constexpr int kGeoUnroll = 4;
-
-__device__ __forceinline__ void geo_store4(const GeoParts &P, size_t row_base, uint64_t e0, uint64_t n_elems, float4 v) {
-    uint32_t row = (uint32_t)(e0 / P.w), col = (uint32_t)(e0 % P.w);
-    const float vals[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        if (e0 + u < n_elems) {
-            uint32_t part, c;
-            geo_locate(P, col, part, c);
-            if (P.ptr[part]) P.ptr[part][(row_base + row) * P.width[part] + c] = vals[u];
-        }
-        if (++col == P.w) { col = 0; ++row; }
-    }
+__device__ __forceinline__ float4 load4_maybe(const float *p, bool vec) {
+    return vec ? ldg4(p) : make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
-__device__ __forceinline__ float4 geo_load4(const GeoParts &P, size_t row_base, uint64_t e0, uint64_t n_elems) {
-    uint32_t row = (uint32_t)(e0 / P.w), col = (uint32_t)(e0 % P.w);
-    float vals[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        if (e0 + u < n_elems) {
-            uint32_t part, c;
-            geo_locate(P, col, part, c);
-            if (P.ptr[part]) vals[u] = P.ptr[part][(row_base + row) * P.width[part] + c];
-        }
-        if (++col == P.w) { col = 0; ++row; }
-    }
-    return make_float4(vals[0], vals[1], vals[2], vals[3]);
-}
-
-// gather: peer p's block [n_block * w] (float4 loads over NVLink) -> rows p * n_block.. of the attribute tensors
+// gather: peer p's block (float4 loads over NVLink) -> rows p * n_block.. of the attribute tensors
 __global__ void __launch_bounds__(kThreads)
 shard_gather_geo_kernel(uint32_t n_block, const BlockShards blocks, const __grid_constant__ GeoParts out) {
     const uint32_t p = blockIdx.y;
-    const uint64_t n_elems = (uint64_t)n_block * out.w, n_vec = (n_elems + 3) / 4;  // (blocks are padded to 16 bytes)
+    const uint64_t n_vec = (uint64_t)n_block * out.w / 4;
     const uint64_t i0 = (uint64_t)blockIdx.x * kThreads * kGeoUnroll + threadIdx.x;
     float4 v[kGeoUnroll];
 #pragma unroll
@@ -605,48 +580,60 @@ shard_gather_geo_kernel(uint32_t n_block, const BlockShards blocks, const __grid
 #pragma unroll
     for (int u = 0; u < kGeoUnroll; ++u) {
         const uint64_t i = i0 + (uint64_t)u * kThreads;
-        if (i < n_vec) geo_store4(out, (size_t)p * n_block, i * 4, n_elems, v[u]);
+        if (i >= n_vec) continue;
+        uint32_t part;
+        uint64_t e;
+        geo_vec_locate(out, n_block, i * 4, part, e);
+        stg4(out.ptr[part] + (size_t)p * n_block * out.width[part] + e, v[u]);
     }
 }
 
-// push: rows p * n_block.. of the gradient tensors -> owner p's staging slot `rank` (dense [n_block * w], float4 stores)
+// push: rows p * n_block.. of the gradient tensors -> owner p's staging slot `rank` (float4 stores over NVLink)
 __global__ void __launch_bounds__(kThreads)
-shard_push_geo_kernel(uint32_t n_block, uint32_t rank, uint64_t slot_floats, const __grid_constant__ GeoParts grads,
+shard_push_geo_kernel(uint32_t n_block, uint32_t rank, uint64_t slot_floats, bool vec, const __grid_constant__ GeoParts grads,
                       const PeerRows peers) {
     const uint32_t p = blockIdx.y;
-    const uint64_t n_elems = (uint64_t)n_block * grads.w, n_vec = (n_elems + 3) / 4;
+    const uint64_t n_vec = (uint64_t)n_block * grads.w / 4;
     const uint64_t i0 = (uint64_t)blockIdx.x * kThreads * kGeoUnroll + threadIdx.x;
     float *dst = peers.base[p] + (size_t)rank * slot_floats;
+    float4 v[kGeoUnroll];
 #pragma unroll
     for (int u = 0; u < kGeoUnroll; ++u) {
         const uint64_t i = i0 + (uint64_t)u * kThreads;
-        if (i < n_vec) stg4(dst + i * 4, geo_load4(grads, (size_t)p * n_block, i * 4, n_elems));
+        if (i >= n_vec) continue;
+        uint32_t part;
+        uint64_t e;
+        geo_vec_locate(grads, n_block, i * 4, part, e);
+        v[u] = grads.ptr[part] ? load4_maybe(grads.ptr[part] + (size_t)p * n_block * grads.width[part] + e, vec)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int u = 0; u < kGeoUnroll; ++u)
+        if (i0 + (uint64_t)u * kThreads < n_vec) stg4(dst + (i0 + (uint64_t)u * kThreads) * 4, v[u]);
 }
 
-// publish: this rank's attribute tensors -> its geometry block [n_block, w] (rows >= n_local get the inert pad row) and its
-// coefficient tensor(s) -> its coefficient block [n_local, row_floats] (the trainers' sh0 [n,1,3] next to shN [n,K-1,3]),
-// one launch, every store a coalesced 16-byte vector (replaces two strided torch copies + torch.cat: 110 -> ~40 us at
-// 500 k rows).  Blocks [0, n_geo_blocks) handle the geometry vectors, the rest the coefficient vectors.
+// publish: this rank's attribute tensors -> its geometry block (rows >= n_local of every part get the inert pad row) and
+// its coefficient tensor(s) -> its coefficient block [n_local, row_floats] (the trainers' sh0 [n,1,3] next to shN
+// [n,K-1,3]), one launch, every store a coalesced 16-byte vector (replaces two strided torch copies + torch.cat).
+// Blocks [0, n_geo_blocks) handle the geometry vectors, the rest the coefficient vectors.
 __global__ void __launch_bounds__(kThreads)
 shard_publish_kernel(uint32_t n_local, uint32_t n_block, uint32_t n_geo_blocks, const __grid_constant__ GeoParts parts,
                      const float *__restrict__ pad_row, float *__restrict__ geo_block, const float *__restrict__ first,
                      const float *__restrict__ rest, uint32_t first_floats, uint32_t row_floats, float *__restrict__ coeff_block) {
     if (blockIdx.x < n_geo_blocks) {
-        const uint64_t n_elems = (uint64_t)n_block * parts.w, n_own = (uint64_t)n_local * parts.w;
         const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-        if (i * 4 >= n_elems) return;
-        float4 v = geo_load4(parts, 0, i * 4, n_own);
-        if (i * 4 + 4 > n_own) {  // inert rows behind the local ones
-            float vals[4] = {v.x, v.y, v.z, v.w};
+        if (i >= (uint64_t)n_block * parts.w / 4) return;
+        uint32_t part;
+        uint64_t e;
+        geo_vec_locate(parts, n_block, i * 4, part, e);
+        const uint32_t wk = parts.width[part];
+        const uint64_t n_own = (uint64_t)n_local * wk;
+        const float *src = parts.ptr[part];
+        float vals[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint64_t e = i * 4 + u;
-                if (e >= n_own && e < n_elems) vals[u] = pad_row ? pad_row[e % parts.w] : 0.f;
-            }
-            v = make_float4(vals[0], vals[1], vals[2], vals[3]);
-        }
-        stg4(geo_block + i * 4, v);
+        for (int u = 0; u < 4; ++u)
+            vals[u] = e + u < n_own ? __ldg(src + e + u) : (pad_row ? pad_row[parts.col0[part] + (uint32_t)((e + u) % wk)] : 0.f);
+        stg4(geo_block + i * 4, make_float4(vals[0], vals[1], vals[2], vals[3]));
         return;
     }
     if (first == nullptr) return;
@@ -693,17 +680,27 @@ __global__ void peer_barrier_kernel(uint32_t rank, uint32_t epoch, const PeerPad
 
 // owner-side reduce: sum of the world slots of the local staging array, in rank order -> the local gradient tensors
 __global__ void __launch_bounds__(kThreads)
-shard_reduce_geo_kernel(uint32_t world, uint32_t n_rows, uint64_t slot_floats, const float *__restrict__ staging,
+shard_reduce_geo_kernel(uint32_t world, uint32_t n_block, uint32_t n_rows, uint64_t slot_floats, const float *__restrict__ staging,
                         const __grid_constant__ GeoParts out) {
-    const uint64_t n_elems = (uint64_t)n_rows * out.w, n_vec = (n_elems + 3) / 4;
     const uint64_t i = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= n_vec) return;
+    if (i >= (uint64_t)n_block * out.w / 4) return;
+    uint32_t part;
+    uint64_t e;
+    geo_vec_locate(out, n_block, i * 4, part, e);
+    const uint64_t n_own = (uint64_t)n_rows * out.width[part];
+    if (out.ptr[part] == nullptr || e >= n_own) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t p = 0; p < world; ++p) {
         const float4 v = ldg4(staging + (size_t)p * slot_floats + i * 4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    geo_store4(out, 0, i * 4, n_elems, acc);
+    float *dst = out.ptr[part] + e;
+    if (e + 4 <= n_own) {
+        stg4(dst, acc);
+    } else {
+        const float vals[4] = {acc.x, acc.y, acc.z, acc.w};
+        for (uint32_t u = 0; e + u < n_own; ++u) dst[u] = vals[u];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1183,14 +1180,17 @@ extern "C" int gsb200_shard_gather_geo(uint32_t world, uint32_t n_block, uint32_
     if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "gsb200_shard_gather_geo: world must be in [1, %d]", kMaxShards);
     GeoParts P;
     if (int e = geo_parts("gsb200_shard_gather_geo", n_parts, outs, widths, true, P)) return e;
+    if (n_block % 4 != 0) return fail(2, "gsb200_shard_gather_geo: n_block must be a multiple of 4");
     if (n_block == 0) return 0;
+    for (uint32_t k = 0; k < n_parts; ++k)
+        if ((reinterpret_cast<uintptr_t>(outs[k]) & 15) != 0) return fail(2, "gsb200_shard_gather_geo: outputs must be 16-byte aligned");
     BlockShards sh{};
     for (uint32_t r = 0; r < world; ++r) {
         sh.base[r] = blocks[r];
         if (sh.base[r] == nullptr || (reinterpret_cast<uintptr_t>(sh.base[r]) & 15) != 0)
             return fail(2, "gsb200_shard_gather_geo: block pointers must be non-null and 16-byte aligned");
     }
-    const uint64_t n_vec = ((uint64_t)n_block * P.w + 3) / 4;
+    const uint64_t n_vec = (uint64_t)n_block * P.w / 4;
     const dim3 grid((uint32_t)((n_vec + kThreads * kGeoUnroll - 1) / (kThreads * kGeoUnroll)), world);
     shard_gather_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, sh, P);
     return check_launch("shard_gather_geo");
@@ -1226,7 +1226,8 @@ extern "C" int gsb200_shard_publish(uint32_t n_local, uint32_t n_block, uint32_t
         if (int e = geo_parts("gsb200_shard_publish", n_parts, parts, widths, true, P)) return e;
         if (geo_block == nullptr || (reinterpret_cast<uintptr_t>(geo_block) & 15) != 0)
             return fail(2, "gsb200_shard_publish: geo_block must be non-null and 16-byte aligned");
-        n_geo_blocks = (uint32_t)((((uint64_t)n_block * P.w + 3) / 4 + kThreads - 1) / kThreads);
+        if (n_block % 4 != 0) return fail(2, "gsb200_shard_publish: n_block must be a multiple of 4");
+        n_geo_blocks = (uint32_t)(((uint64_t)n_block * P.w / 4 + kThreads - 1) / kThreads);
     }
     uint64_t n_coeff_blocks = 0;
     if (first != nullptr && n_local != 0) {
@@ -1267,16 +1268,19 @@ extern "C" int gsb200_shard_push_geo(uint32_t world, uint32_t n_block, uint32_t 
     if (int e = geo_parts("gsb200_shard_push_geo", n_parts, grads, widths, false, P)) return e;
     if ((uint64_t)n_block * P.w > slot_floats || slot_floats % 4 != 0)
         return fail(2, "gsb200_shard_push_geo: staging slot too small or not a multiple of 4 floats");
+    if (n_block % 4 != 0) return fail(2, "gsb200_shard_push_geo: n_block must be a multiple of 4");
     if (n_block == 0) return 0;
+    bool vec = true;  // 16-byte loads of the gradient tensors only if every one of them is aligned
+    for (uint32_t k = 0; k < n_parts; ++k) vec = vec && (reinterpret_cast<uintptr_t>(grads[k]) & 15) == 0;
     PeerRows peers{};
     for (uint32_t r = 0; r < world; ++r) {
         peers.base[r] = peer_staging[r];
         if (peers.base[r] == nullptr || (reinterpret_cast<uintptr_t>(peers.base[r]) & 15) != 0)
             return fail(2, "gsb200_shard_push_geo: staging pointers must be non-null and 16-byte aligned");
     }
-    const uint64_t n_vec = ((uint64_t)n_block * P.w + 3) / 4;
+    const uint64_t n_vec = (uint64_t)n_block * P.w / 4;
     const dim3 grid((uint32_t)((n_vec + kThreads * kGeoUnroll - 1) / (kThreads * kGeoUnroll)), world);
-    shard_push_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, rank, slot_floats, P, peers);
+    shard_push_geo_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(n_block, rank, slot_floats, vec, P, peers);
     return check_launch("shard_push_geo");
 }
 
@@ -1289,10 +1293,13 @@ extern "C" int gsb200_shard_reduce_geo(uint32_t world, uint32_t n_block, uint32_
     if ((uint64_t)n_block * P.w > slot_floats || slot_floats % 4 != 0 || staging == nullptr ||
         (reinterpret_cast<uintptr_t>(staging) & 15) != 0)
         return fail(2, "gsb200_shard_reduce_geo: bad staging");
+    if (n_block % 4 != 0) return fail(2, "gsb200_shard_reduce_geo: n_block must be a multiple of 4");
     if (n_rows == 0) return 0;
-    const uint64_t n_vec = ((uint64_t)n_rows * P.w + 3) / 4;
+    for (uint32_t k = 0; k < n_parts; ++k)
+        if ((reinterpret_cast<uintptr_t>(outs[k]) & 15) != 0) return fail(2, "gsb200_shard_reduce_geo: outputs must be 16-byte aligned");
+    const uint64_t n_vec = (uint64_t)n_block * P.w / 4;
     shard_reduce_geo_kernel<<<(uint32_t)((n_vec + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
-        world, n_rows, slot_floats, staging, P);
+        world, n_block, n_rows, slot_floats, staging, P);
     return check_launch("shard_reduce_geo");
 }
 

@@ -206,8 +206,10 @@ int gsb200_shard_reduce_rows_split(uint32_t world, uint32_t n_block, uint32_t n_
  * pointers).  Replaces the all-gather of all_gather_tensor_list (distributed.py:102-167) for that tensor. */
 int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float *const *blocks, float *out,
                              gsb200_stream_t stream);
-/* Geometry exchange without the gathered [N, w] intermediate.  A rank's published geometry block is [n_block, w] with the
- * attribute tensors side by side (means | quats | scales | opacity: widths {3,4,3,1}; or means | covars | opacity).
+/* Geometry exchange without the gathered [N, w] intermediate.  A rank's published geometry block holds the attribute
+ * tensors one after the other (means [n_block,3] | quats [n_block,4] | scales [n_block,3] | opacity [n_block,1]: widths
+ * {3,4,3,1}; or means | covars | opacity), n_block a multiple of 4, so that every transfer is a run of 16-byte vectors that
+ * is contiguous on both sides; the staging slots of the backward use the same layout.
  *   _gather_geo : pulls every peer's block and writes the n_parts attribute tensors of the gathered set,
  *                 outs[k] [world * n_block, widths[k]] (rank r's rows at r * n_block) -- HOST arrays of device pointers.
  *   _push_geo   : backward, sender side: grads[k] [world * n_block, widths[k]] (NULL = zero gradient); the rows of owner p
@@ -247,7 +249,8 @@ int gsb200_sh_owner_bwd(uint32_t V, uint32_t n_local, uint32_t n_block, uint32_t
  * `torch.inverse(viewmats)[:, :3, 3]` of the reference's colour stage (rendering.py:370) for rigid matrices. */
 int gsb200_camera_positions(uint32_t C, const float *viewmats, float *campos, gsb200_stream_t stream);
 /* Start of a distributed step, one launch: this rank's attribute tensors parts[k] [n_local, widths[k]] are written side by
- * side into its published geometry block geo_block [n_block, w] (rows >= n_local = pad_row [w], an inert splat; NULL = 0),
+ * side into its published geometry block geo_block (n_block * w floats: part k's [n_block, widths[k]] rows, dense, one part
+ * after the other; n_block a multiple of 4; rows >= n_local = the matching columns of pad_row [w], an inert splat; NULL = 0),
  * and its coefficient rows -- `first` [n_local, first_floats] next to `rest` [n_local, row_floats - first_floats] (NULL when
  * first covers the row): the trainers' sh0 / shN -- into coeff_block [n_local, row_floats].  n_parts = 0 skips the
  * geometry, first = NULL the coefficients.  Replaces the torch.cat / copies in front of the reference's all-gather
