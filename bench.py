@@ -210,11 +210,13 @@ def run_ours(args):
         for t in m1_attrs:
             t.requires_grad_(True)
 
-    def step_m1(viewmat, K, target):
+    def step_m1(viewmat, K, target, before_target=None):
         for t in m1_attrs:
             t.grad = None
         rc, ra, meta = gs.rasterization(*m1_attrs, viewmat, K, W_IMG, H_IMG, packed=args.packed, near_plane=0.01,
                                         far_plane=100.0, radius_clip=3.0, distributed=world > 1)
+        if before_target is not None:
+            before_target()
         loss = rc.sum()
         loss.backward()
         state["meta"] = meta
@@ -240,7 +242,7 @@ def run_ours(args):
         the_sim = get_sim(entropy)
         the_step = 20_000 if entropy else 100
 
-        def step(viewmat, K, target):
+        def step(viewmat, K, target, before_target=None):
             for p in params.values():
                 p.grad = None
             new, bits = the_sim.simulate_compression(params, the_step, fuse_activations=fuse_act)
@@ -250,6 +252,8 @@ def run_ours(args):
             rc, ra, meta = gs.rasterization(new["means"], new["quats"], scales, opac, colors, viewmat, K, W_IMG, H_IMG,
                                             sh_degree=3, packed=False, near_plane=0.01, far_plane=100.0, radius_clip=3.0,
                                             distributed=world > 1)
+            if before_target is not None:
+                before_target()  # e2e: the stream waits for the target image's upload only here, where it is first read
             loss = (rc - target).abs().mean() if torch_loss else photometric_loss(rc, target, ssim_lambda=0.0)
             for b in bits.values():
                 if b is not None:
@@ -284,13 +288,18 @@ def run_ours(args):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         main = torch.cuda.current_stream(dev)
         ready = [torch.cuda.Event(), torch.cuda.Event()]
+        ready_cam = [torch.cuda.Event(), torch.cuda.Event()]
         free = [torch.cuda.Event(), torch.cuda.Event()]
 
         def issue_copy(k):
+            # camera first (two tiny tensors, needed by the projection), then the target image (25 MB, first read by the
+            # loss): the step starts as soon as the camera is there
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(free[k])
-                for h, d in zip(host_in, dev_bufs[k]):
+                for h, d in zip(host_in[:-1], dev_bufs[k][:-1]):
                     d.copy_(h, non_blocking=True)
+                ready_cam[k].record(copy_stream)
+                dev_bufs[k][-1].copy_(host_in[-1], non_blocking=True)
                 ready[k].record(copy_stream)
 
         t0.record()
@@ -304,8 +313,8 @@ def run_ours(args):
                 k = i % 2
                 if i + 1 < n_steps:
                     issue_copy((i + 1) % 2)
-                main.wait_event(ready[k])
-                loss_t = step(*dev_bufs[k])
+                main.wait_event(ready_cam[k])
+                loss_t = step(*dev_bufs[k], before_target=lambda k=k: main.wait_event(ready[k]))
                 free[k].record(main)
                 # device -> host read of EVERY step's result: an asynchronous 4-byte copy into pinned memory that the
                 # host consumes one step later (the way a trainer's logger reads its loss), so the read does not
@@ -503,7 +512,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--scene-grid", dest="scene_grid", type=int, default=3)

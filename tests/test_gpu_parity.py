@@ -266,6 +266,41 @@ def test_isect_empty_and_oversized_tile():
     assert torch.equal(ids.cpu(), o[1]) and torch.equal(fl.cpu(), o[2])
 
 
+@pytest.mark.parametrize("n", [64, 65, 200, 1500, 2048, 2049, 5000, 12288, 14000])
+@pytest.mark.parametrize("depth_mode", ["uniform", "equal", "outlier", "bimodal", "tiny_range", "few_values"])
+def test_isect_depth_bucket_sort_edge_cases(n, depth_mode):
+    """The per-tile depth-bucket sort (csrc/isect.cu) on depth distributions that stress its bucket map: all keys in one
+    bucket (equal depths / one outlier stretching the range -> bail-out to the bitonic network), clustered depths, a
+    range so small that the bucket scale overflows, heavy ties -- for segment lengths around every kernel boundary
+    (one-warp sort <= 64, short-segment kernel <= 2048, long-segment kernel <= 12288, in-place global sort beyond).
+    Order must equal the reference's stable sort on (tile | depth bits): the oracle's."""
+    g = torch.Generator().manual_seed(n * 7 + len(depth_mode))
+    m2d = (torch.rand(1, n, 2, generator=g) * 10 + 3)          # all inside tile (0, 0) of a 2 x 2 grid
+    m2d[0, : n // 7] += 16.0                                     # ... a few in the neighbouring tiles as well
+    radii = torch.ones(1, n, dtype=torch.int32)
+    if depth_mode == "uniform":
+        dep = torch.rand(1, n, generator=g) * 20 + 0.5
+    elif depth_mode == "equal":
+        dep = torch.full((1, n), 3.25)
+    elif depth_mode == "outlier":
+        dep = torch.rand(1, n, generator=g) * 1e-3 + 2.0
+        dep[0, n // 2] = 9.0e4
+    elif depth_mode == "bimodal":
+        dep = torch.where(torch.rand(1, n, generator=g) < 0.5, torch.rand(1, n, generator=g) * 0.01 + 1.0,
+                          torch.rand(1, n, generator=g) * 0.01 + 50.0)
+    elif depth_mode == "tiny_range":
+        base = torch.tensor(1.0e-38)
+        dep = base + torch.randint(0, 3, (1, n), generator=g).float() * 1.0e-45  # denormal spacing: scale overflows
+    else:
+        dep = torch.randint(1, 5, (1, n), generator=g).float()
+    tpg, ids, fl, offs = _isect_tiles_with_offsets(m2d.to(DEV), radii.to(DEV), dep.to(DEV), 16, 2, 2)
+    o = O.isect_tiles(m2d, radii, dep, 16, 2, 2, 1)
+    assert torch.equal(tpg.cpu(), o[0])
+    assert torch.equal(ids.cpu(), o[1])
+    assert torch.equal(fl.cpu(), o[2])
+    assert torch.equal(offs.cpu(), O.isect_offset_encode(o[1], 1, 2, 2))
+
+
 # ------------------------------------------------------------------------------------- blend
 def _blend_inputs(C=3, channels=3, width=None, height=None, scene_grid=1):
     means, quats, scales, opac, colors, viewmats, Ks, W, H = _scene(C, scene_grid, width, height)
