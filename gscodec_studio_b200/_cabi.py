@@ -49,6 +49,9 @@ SIGNATURES = {
     "gsb200_sh_view_fwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _P, _P, _P, _P],
     "gsb200_sh_view_bwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_shard_reduce_rows": [_U, _U, _U, _U, _P, _P, _P, _P],
+    "gsb200_projection_owner_fwd": [_U, _U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _F, _F, _F, c_int, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_projection_owner_bwd": [_U, _U, _U, _P, _P, _P, _P, _P, _U, _U, _F, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_peer_push_small": [_U, _U, _U, _U, _P, _P, _P],
     "gsb200_shard_push_rows": [_U, _U, _U, _U, _U, c_uint64, _P, _P, _P, _U, _P, _P],
     "gsb200_sh_owner_fwd": [_U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_owner_bwd": [_U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -455,3 +455,204 @@ def view_colors_owner(sh_degree: int, means_local: Tensor, campos: Tensor, sh_pa
     assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1]
     return _ShOwnerExchange.apply(sh_degree, means_local.float().contiguous(), campos.detach().float().contiguous(),
                                   sh0.float().contiguous(), shN.float().contiguous(), radii.contiguous(), n_block)
+
+
+# ---- owner-side projection + colour exchange ("owner render") ---------------------------------------------------------------
+_render_workspaces: Dict[Tuple[int, int], "RenderExchange"] = {}
+_VIEW_ARRAYS = (("radii", 1), ("means2d", 2), ("depths", 1), ("conics", 3), ("opacities", 1), ("colours", 3))
+_STAGE_ARRAYS = (("v_means2d", 2), ("v_conics", 3), ("v_opacities", 1), ("v_colours", 3), ("v_depths", 1))
+
+
+class RenderExchange:
+    """Symmetric allocation of the owner-side render exchange for C cameras per rank (V = world x C views):
+         viewer side, written by the owners : radii | means2d | depths | conics | opacities | colours, each
+                                              [C, world * n_block, w] -- the tensors this rank's tile intersection and
+                                              blend read; owner p writes rows p * n_block.. of every camera
+         owner side, written by the viewers : v_means2d | v_conics | v_opacities | v_colours | v_depths, each
+                                              [V, n_block, w] -- gradients of THIS rank's rows in every view
+         cameras                            : viewmats [V, 16], Ks [V, 9] of every view
+         pads                               : signal pad of the barrier kernel"""
+
+    def __init__(self, device: torch.device, n_cameras: int, cap_block: int):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.C, self.cap_block, self.V = n_cameras, cap_block, self.world * n_cameras
+        off, self.off = 0, {}
+        for name, w in _VIEW_ARRAYS:
+            self.off[name] = off
+            off += n_cameras * self.world * cap_block * w
+        for name, w in _STAGE_ARRAYS:
+            self.off[name] = off
+            off += self.V * cap_block * w
+        for name, w in (("viewmats", 16), ("Ks", 9)):
+            self.off[name] = off
+            off += (self.V * w + 3) // 4 * 4
+        self.off["pads"] = off
+        off += 4 * MAX_SHARDS
+        self.buf = symm_mem.empty(off, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(self.ptrs) == self.world and all(p % 16 == 0 for p in self.ptrs), self.ptrs
+        self.buf.zero_()  # rows of never-visible pairs are never written: keep them finite
+        self.tabs = {name: _ptr_table(self.ptrs, 4 * self.off[name]) for name in self.off}
+        self._view_tabs: Dict[int, dict] = {}
+        self.epoch = 0
+        self.hdl.barrier(channel=0)  # every pad is zero before the first signal can arrive
+
+    def barrier(self) -> None:
+        self.epoch = (self.epoch + 1) & 0xFFFFFFFF
+        call("gsb200_peer_barrier", self.world, self.rank, self.tabs["pads"][1], self.epoch, stream_ptr(self.buf.device))
+
+    def region(self, name: str, n_floats: int) -> Tensor:
+        return self.buf[self.off[name]: self.off[name] + n_floats]
+
+    def view_tables(self, n_block: int) -> dict:
+        """array name -> HOST table: view v = (rank q, camera c) -> address of THIS rank's n_block rows in q's array."""
+        tabs = self._view_tabs.get(n_block)
+        if tabs is None:
+            n_total, tabs = self.world * n_block, {}
+            for name, w in _VIEW_ARRAYS:
+                addrs = [self.ptrs[v // self.C] + 4 * (self.off[name] + ((v % self.C) * n_total + self.rank * n_block) * w)
+                         for v in range(self.V)]
+                arr = (ctypes.c_void_p * self.V)(*addrs)
+                tabs[name] = (arr, ctypes.cast(arr, ctypes.c_void_p))
+            self._view_tabs[n_block] = tabs
+        return tabs
+
+
+def render_workspace(device: torch.device, n_cameras: int, n_block: int) -> RenderExchange:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), n_cameras)
+    ws = _render_workspaces.get(key)
+    if ws is None or ws.cap_block < n_block or ws.world != dist.get_world_size():
+        if ws is not None:
+            ws.barrier()
+            _render_workspaces.pop(key)
+            del ws
+        cap = (int(n_block * 1.1) + 64 + 3) // 4 * 4
+        _render_workspaces[key] = ws = RenderExchange(device, n_cameras, cap)
+    return ws
+
+
+def owner_render_available(device: torch.device, n_cameras: int, n_block: int) -> bool:
+    """Owner-side projection + colours: NCCL job on CUDA with peer mappings, <= MAX_SHARDS ranks, <= MAX_VIEWS views, the
+    same number of cameras on every rank (the caller's contract).  GSB200_DIST_RENDER=gather keeps the gather path."""
+    global _unavailable
+    if _unavailable is not None or os.environ.get("GSB200_DIST_RENDER", "owner") != "owner":
+        return False
+    if os.environ.get("GSB200_PEER_EXCHANGE", "1") == "0":
+        return False
+    if device.type != "cuda" or dist.get_backend() != "nccl":
+        return False
+    if dist.get_world_size() > MAX_SHARDS or dist.get_world_size() * n_cameras > MAX_VIEWS:
+        return False
+    try:
+        render_workspace(device, n_cameras, n_block)
+    except Exception as e:  # no P2P mapping on this machine: every rank fails alike
+        _unavailable = f"{type(e).__name__}: {e}"
+        warnings.warn(f"peer-memory exchange unavailable ({_unavailable}); using NCCL collectives")
+        return False
+    return True
+
+
+class _OwnerRenderInputs(torch.autograd.Function):
+    """Stage 1 + colour stage of a distributed render, computed by the OWNERS of the Gaussians:
+    forward : exchange the cameras | barrier | every rank projects its rows and evaluates their SH colours for all V views,
+              storing radius / 2-D mean / depth / conic / opacity / colour of the visible pairs into the viewers' tensors
+              over NVLink | barrier
+    backward: the viewers push the blend's gradients of those tensors to the owners | barrier | owner-side projection and
+              SH backward -> gradients of the LOCAL means, quats, scales, opacities, sh0, shN.
+    No attribute, coefficient or attribute-gradient row crosses the link; what crosses is ~12 bytes per (view, Gaussian)
+    forward and 36 bytes backward, instead of 44 + 44 bytes per Gaussian plus the SH rows."""
+
+    @staticmethod
+    def forward(ctx, cfg, means, quats, scales, opacities, sh0, shN, viewmats, Ks):
+        (sh_degree, n_block, W, H, eps2d, near, far, radius_clip, model) = cfg
+        dev = means.device
+        C = viewmats.shape[0]
+        ws = render_workspace(dev, C, n_block)
+        V, n_local, n_total = ws.V, means.shape[0], ws.world * n_block
+        K = 1 + shN.shape[1]
+        s = stream_ptr(dev)
+        with device_guard(dev):
+            call("gsb200_peer_push_small", ws.world, ws.rank * C, C, 16, ptr(viewmats), ws.tabs["viewmats"][1], s)
+            call("gsb200_peer_push_small", ws.world, ws.rank * C, C, 9, ptr(Ks), ws.tabs["Ks"][1], s)
+            ws.barrier()  # every rank's cameras have landed
+            vm_all = ws.region("viewmats", V * 16).clone()  # private copies: the backward of THIS step may come after the
+            ks_all = ws.region("Ks", V * 9).clone()         # next forward has overwritten the staging
+            radii_loc = torch.empty((V, n_block), dtype=torch.int32, device=dev)
+            conics_loc = torch.empty((V, n_block, 3), dtype=torch.float32, device=dev)
+            tabs = ws.view_tables(n_block)
+            call("gsb200_projection_owner_fwd", V, n_local, n_block, ptr(means), ptr(quats), ptr(scales), ptr(opacities),
+                 ptr(vm_all), ptr(ks_all), W, H, eps2d, near, far, radius_clip, model, ptr(radii_loc), ptr(conics_loc),
+                 tabs["radii"][1], tabs["means2d"][1], tabs["depths"][1], tabs["conics"][1], tabs["opacities"][1], s)
+            campos_all = torch.empty((V, 3), dtype=torch.float32, device=dev)
+            call("gsb200_camera_positions", V, ptr(vm_all), ptr(campos_all), s)
+            call("gsb200_sh_owner_fwd", V, n_local, n_block, K, sh_degree, ptr(means), ptr(campos_all), ptr(sh0), ptr(shN),
+                 ptr(radii_loc), tabs["colours"][1], s)
+            ws.barrier()  # every owner's rows have landed
+        ctx.save_for_backward(means, quats, scales, sh0, shN, vm_all, ks_all, campos_all, radii_loc, conics_loc)
+        ctx.cfg = cfg
+        ctx.C = C
+        radii = ws.region("radii", C * n_total).view(torch.int32).view(C, n_total)
+        ctx.mark_non_differentiable(radii)
+        return (radii, ws.region("means2d", C * n_total * 2).view(C, n_total, 2), ws.region("depths", C * n_total).view(C, n_total),
+                ws.region("conics", C * n_total * 3).view(C, n_total, 3), ws.region("opacities", C * n_total).view(C, n_total),
+                ws.region("colours", C * n_total * 3).view(C, n_total, 3))
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_means2d, v_depths, v_conics, v_opacities, v_colours):
+        means, quats, scales, sh0, shN, vm_all, ks_all, campos_all, radii_loc, conics_loc = ctx.saved_tensors
+        (sh_degree, n_block, W, H, eps2d, near, far, radius_clip, model) = ctx.cfg
+        dev, C = means.device, ctx.C
+        ws = render_workspace(dev, C, n_block)
+        V, n_local, n_total = ws.V, means.shape[0], ws.world * n_block
+        K = 1 + shN.shape[1]
+        s = stream_ptr(dev)
+
+        def dense(t, w):
+            return torch.zeros((C, n_total, w), dtype=torch.float32, device=dev) if t is None else t.contiguous()
+
+        v_sh0 = torch.empty((n_local, 1, 3), dtype=torch.float32, device=dev)
+        v_shN = torch.empty((n_local, K - 1, 3), dtype=torch.float32, device=dev)
+        v_means = torch.empty_like(means)
+        v_means_sh = torch.empty_like(means)
+        v_quats, v_scales = torch.empty_like(quats), torch.empty_like(scales)
+        with device_guard(dev):
+            for name, w, t in (("v_means2d", 2, v_means2d), ("v_conics", 3, v_conics), ("v_opacities", 1, v_opacities),
+                               ("v_colours", 3, v_colours), ("v_depths", 1, v_depths)):
+                if name == "v_depths" and t is None:
+                    continue
+                call("gsb200_shard_push_rows", ws.world, n_block, w, C, ws.rank * C, n_block * w, ptr(dense(t, w)),
+                     ws.tabs[name][1], None, 0, None, s)
+            ws.barrier()  # every viewer's gradients have landed
+            call("gsb200_projection_owner_bwd", V, n_local, n_block, ptr(means), ptr(quats), ptr(scales), ptr(vm_all), ptr(ks_all),
+                 W, H, eps2d, model, ptr(radii_loc), ptr(conics_loc), ptr(ws.region("v_means2d", V * n_block * 2)),
+                 None if v_depths is None else ptr(ws.region("v_depths", V * n_block)),
+                 ptr(ws.region("v_conics", V * n_block * 3)), ptr(v_means), ptr(v_quats), ptr(v_scales), s)
+            call("gsb200_sh_owner_bwd", V, n_local, n_block, K, sh_degree, ptr(means), ptr(campos_all), ptr(sh0), ptr(shN),
+                 ptr(radii_loc), ptr(ws.region("v_colours", V * n_block * 3)), ptr(v_sh0), ptr(v_shN), ptr(v_means_sh), s)
+            v_means += v_means_sh
+            # opacity: the viewers' rows are zero for invisible pairs, so the plain sum over the views is the gradient
+            v_opac = ws.region("v_opacities", V * n_block).view(V, n_block)[:, :n_local].sum(0)
+        return None, v_means, v_quats, v_scales, v_opac, v_sh0, v_shN, None, None
+
+
+def owner_render_inputs(sh_degree: int, means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, sh_pair, viewmats: Tensor,
+                        Ks: Tensor, width: int, height: int, n_block: int, eps2d: float, near_plane: float, far_plane: float,
+                        radius_clip: float, camera_model: int):
+    """-> (radii [C,N], means2d [C,N,2], depths [C,N], conics [C,N,3], opacities [C,N], colours [C,N,3]) of the gathered set
+    (N = world * n_block, rank r's rows at r * n_block) for THIS rank's cameras, computed by the owners of the rows.  Inputs
+    are this rank's shard ([n_local, ...]) and cameras.  Rows of invisible pairs hold radius 0 and stale finite values
+    elsewhere (the tile intersection and the blend never read them).  Differentiable w.r.t. the shard, not the cameras."""
+    sh0, shN = sh_pair
+    assert sh0.dim() == 3 and sh0.shape[1:] == (1, 3) and shN.dim() == 3 and shN.shape[2] == 3, (sh0.shape, shN.shape)
+    assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1]
+    cfg = (int(sh_degree), int(n_block), int(width), int(height), float(eps2d), float(near_plane), float(far_plane),
+           float(radius_clip), int(camera_model))
+
+    def f(t):
+        return t.float().contiguous()
+
+    return _OwnerRenderInputs.apply(cfg, f(means), f(quats), f(scales), f(opacities), f(sh0), f(shN), f(viewmats.detach()),
+                                    f(Ks.detach()))

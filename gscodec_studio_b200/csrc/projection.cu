@@ -27,6 +27,15 @@ constexpr int kMaxSmemCams = 64;  // cameras cached in shared memory per pass
 //   1  only counts the visible Gaussians of every (camera, block) -> pk_counts[c * n_blocks + block]
 //   2  recomputes the projection and writes row pk_counts[c * n_blocks + block] (now the exclusive scan) + rank inside
 //      the block; rows therefore come out in (camera, Gaussian) lexicographic order, like the reference's
+// owner mode (MODE 3, multi-GPU): where view v's rows of THIS rank live inside the viewer's tensors (peer memory)
+struct ProjOwnerOut {
+    int32_t *radii[GSB200_MAX_VIEWS];
+    float *means2d[GSB200_MAX_VIEWS];
+    float *depths[GSB200_MAX_VIEWS];
+    float *conics[GSB200_MAX_VIEWS];
+    float *opacities[GSB200_MAX_VIEWS];
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
@@ -35,7 +44,8 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                       float eps2d, float near_plane, float far_plane, float radius_clip, int model,
                       int packed_rule, int32_t *__restrict__ radii, float *__restrict__ means2d,
                       float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ comps,
-                      int32_t *__restrict__ pk_counts, int64_t *__restrict__ pk_camera_ids, int64_t *__restrict__ pk_gaussian_ids) {
+                      int32_t *__restrict__ pk_counts, int64_t *__restrict__ pk_camera_ids, int64_t *__restrict__ pk_gaussian_ids,
+                      uint32_t ldN, const float *__restrict__ opacities, const __grid_constant__ ProjOwnerOut peer) {
     __shared__ float s_vm[kMaxSmemCams][12];
     __shared__ float s_k[kMaxSmemCams][4];
     __shared__ int s_wcnt[kThreads / 32];
@@ -56,9 +66,10 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
         }
         __syncthreads();
         if (MODE == 0 && g >= N) continue;  // (the packed passes meet block barriers inside the camera loop)
+        if (MODE == 3 && g >= ldN) continue;  // owner mode: the padding rows [N, ldN) of the block publish radius 0
         for (uint32_t ci = 0; ci < nc; ++ci) {
             const float *R = s_vm[ci];
-            const size_t idx = (size_t)(c0 + ci) * N + g;
+            const size_t idx = (size_t)(c0 + ci) * (MODE == 3 ? ldN : N) + g;
             float mx = R[0] * px + R[1] * py + R[2] * pz + R[3];
             float my = R[4] * px + R[5] * py + R[6] * pz + R[7];
             float mz = R[8] * px + R[9] * py + R[10] * pz + R[11];
@@ -115,6 +126,21 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                 depths[idx] = o_d;
                 conics[idx * 3] = o_a; conics[idx * 3 + 1] = o_b; conics[idx * 3 + 2] = o_c;
                 if (comps != nullptr) comps[idx] = o_comp;
+            } else if (MODE == 3) {
+                // owner mode: view c0 + ci belongs to another rank.  Its radius always travels (the viewer's tile
+                // intersection reads every row), everything else only for a visible pair; a local copy of radius and conic
+                // stays here for the backward.
+                const uint32_t v = c0 + ci;
+                radii[idx] = rad;
+                peer.radii[v][g] = rad;
+                if (rad > 0) {
+                    conics[idx * 3] = o_a; conics[idx * 3 + 1] = o_b; conics[idx * 3 + 2] = o_c;
+                    *reinterpret_cast<float2 *>(peer.means2d[v] + (size_t)g * 2) = make_float2(o_mx, o_my);
+                    peer.depths[v][g] = o_d;
+                    float *pc = peer.conics[v] + (size_t)g * 3;
+                    pc[0] = o_a; pc[1] = o_b; pc[2] = o_c;
+                    peer.opacities[v][g] = __ldg(opacities + g);
+                }
             } else if (MODE == 1) {
                 const int cnt = __syncthreads_count(rad > 0);
                 if (threadIdx.x == 0) pk_counts[(size_t)(c0 + ci) * gridDim.x + blockIdx.x] = cnt;
@@ -156,7 +182,7 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                       const float *__restrict__ v_depths, const float *__restrict__ v_conics,
                       const float *__restrict__ v_comps, float *__restrict__ v_means, float *__restrict__ v_covars,
                       float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_viewmats,
-                      const int32_t *__restrict__ pk_offsets, const int64_t *__restrict__ pk_gaussian_ids) {
+                      const int32_t *__restrict__ pk_offsets, const int64_t *__restrict__ pk_gaussian_ids, uint32_t ldN) {
     __shared__ float s_vm[kMaxSmemCams][12];
     __shared__ float s_k[kMaxSmemCams][4];
     __shared__ float s_red[kThreads / 32][12];
@@ -186,7 +212,7 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
         __syncthreads();
         for (uint32_t ci = 0; ci < nc; ++ci) {
             const float *R = s_vm[ci];
-            size_t idx = (size_t)(c0 + ci) * N + g;
+            size_t idx = (size_t)(c0 + ci) * ldN + g;  // ldN = N, or the block stride of the owner-side staging
             float vR[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
             float vt[3] = {0.f, 0.f, 0.f};
             bool active;
@@ -309,7 +335,7 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                 } else {
                     vmc[0] = fx * vm0; vmc[1] = fy * vm1; vmc[2] = 0.f;
                 }
-                vmc[2] += v_depths[idx];
+                if (v_depths != nullptr) vmc[2] += v_depths[idx];
                 // world -> camera VJPs (transform.cuh:20-71)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) vmean[j] += R[j] * vmc[0] + R[4 + j] * vmc[1] + R[8 + j] * vmc[2];
@@ -510,7 +536,8 @@ extern "C" int gsb200_projection_fwd(uint32_t C, uint32_t N, const float *means,
         return fail(2, "gsb200_projection_fwd: covars or (quats, scales) should be provided");
     projection_fwd_kernel<0><<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip,
-        camera_model, packed_radius_rule, radii, means2d, depths, conics, compensations, nullptr, nullptr, nullptr);
+        camera_model, packed_radius_rule, radii, means2d, depths, conics, compensations, nullptr, nullptr, nullptr, N, nullptr,
+        ProjOwnerOut{});
     return check_launch("projection_fwd");
 }
 
@@ -529,7 +556,7 @@ extern "C" int gsb200_projection_packed_count(uint32_t C, uint32_t N, const floa
     const uint32_t nb = cdiv(N, kThreads), n = C * nb;
     projection_fwd_kernel<1><<<nb, kThreads, 0, s>>>(C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d,
                                                      near_plane, far_plane, radius_clip, camera_model, 1, nullptr, nullptr, nullptr,
-                                                     nullptr, nullptr, block_offsets, nullptr, nullptr);
+                                                     nullptr, nullptr, block_offsets, nullptr, nullptr, N, nullptr, ProjOwnerOut{});
     if (int e = check_launch("projection_packed_count")) return e;
     // exclusive scan over (camera, block): block_offsets[0..n) in place, total -> block_offsets[n]; scratch behind it
     int32_t *scratch = block_offsets + n + 1;
@@ -568,7 +595,7 @@ extern "C" int gsb200_projection_packed_fill(uint32_t C, uint32_t N, const float
     projection_fwd_kernel<2><<<nb, kThreads, 0, s>>>(C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d,
                                                      near_plane, far_plane, radius_clip, camera_model, 1, radii, means2d, depths,
                                                      conics, compensations, const_cast<int32_t *>(block_offsets), camera_ids,
-                                                     gaussian_ids);
+                                                     gaussian_ids, N, nullptr, ProjOwnerOut{});
     if (int e = check_launch("projection_packed_fill")) return e;
     packed_indptr_kernel<<<cdiv(C + 1, kThreads), kThreads, 0, s>>>(C, nb, block_offsets, indptr);
     return check_launch("packed_indptr");
@@ -590,7 +617,7 @@ extern "C" int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means,
     projection_bwd_kernel<VG, FE, false><<<grid, kThreads, 0, s>>>(                                                   \
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,     \
         compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats, \
-        nullptr, nullptr)
+        nullptr, nullptr, N)
     const bool fe = camera_model == GSB200_CAMERA_FISHEYE;
     if (v_viewmats != nullptr) { if (fe) GSB_LAUNCH_PROJ_BWD(true, true); else GSB_LAUNCH_PROJ_BWD(true, false); }
     else { if (fe) GSB_LAUNCH_PROJ_BWD(false, true); else GSB_LAUNCH_PROJ_BWD(false, false); }
@@ -617,7 +644,7 @@ extern "C" int gsb200_projection_packed_bwd(uint32_t C, uint32_t N, const float 
     projection_bwd_kernel<VG, FE, true><<<grid, kThreads, 0, s>>>(                                                    \
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, nullptr, conics,   \
         compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats, \
-        block_offsets, gaussian_ids)
+        block_offsets, gaussian_ids, N)
     const bool fe = camera_model == GSB200_CAMERA_FISHEYE;
     if (v_viewmats != nullptr) { if (fe) GSB_LAUNCH_PROJ_PBWD(true, true); else GSB_LAUNCH_PROJ_PBWD(true, false); }
     else { if (fe) GSB_LAUNCH_PROJ_PBWD(false, true); else GSB_LAUNCH_PROJ_PBWD(false, false); }
@@ -671,4 +698,64 @@ extern "C" int gsb200_scatter_rows(uint32_t C, uint32_t N, int64_t nnz, const in
         N, nnz, camera_ids, gaussian_ids, p_v_means2d, p_v_depths, p_v_conics, p_v_compensations, v_means2d, v_depths,
         v_conics, v_compensations);
     return check_launch("scatter_rows");
+}
+
+
+// ---- owner-side projection (view-parallel rendering over NVLink peer memory) ------------------------------------------------
+// Every rank projects ITS rows for all V views of the job (the cameras were exchanged first) and stores the results into the
+// viewers' tensors; the backward runs on the owner as well, on gradients the viewers pushed into local staging [V, n_block, .]
+// -- the Gaussians' attributes and their gradients never cross the link.
+extern "C" int gsb200_projection_owner_fwd(uint32_t V, uint32_t n_local, uint32_t n_block, const float *means, const float *quats,
+                                           const float *scales, const float *opacities, const float *viewmats, const float *Ks,
+                                           uint32_t W, uint32_t H, float eps2d, float near_plane, float far_plane,
+                                           float radius_clip, int camera_model, int32_t *radii_local, float *conics_local,
+                                           int32_t *const *view_radii, float *const *view_means2d, float *const *view_depths,
+                                           float *const *view_conics, float *const *view_opacities, gsb200_stream_t stream) {
+    const char *who = "gsb200_projection_owner_fwd";
+    if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
+        return failf(2, "%s: camera_model must be pinhole, ortho or fisheye", who);
+    if (V == 0 || V > GSB200_MAX_VIEWS) return failf(2, "%s: 1..%d views", who, GSB200_MAX_VIEWS);
+    if (n_local > n_block) return failf(2, "%s: n_local > n_block", who);
+    if (n_block == 0) return 0;
+    if (n_local != 0 && (means == nullptr || quats == nullptr || scales == nullptr || opacities == nullptr))
+        return failf(2, "%s: null attribute pointer", who);
+    if (radii_local == nullptr || conics_local == nullptr || viewmats == nullptr || Ks == nullptr)
+        return failf(2, "%s: null pointer", who);
+    ProjOwnerOut out{};
+    for (uint32_t v = 0; v < V; ++v) {
+        out.radii[v] = view_radii[v]; out.means2d[v] = view_means2d[v]; out.depths[v] = view_depths[v];
+        out.conics[v] = view_conics[v]; out.opacities[v] = view_opacities[v];
+        if (!out.radii[v] || !out.means2d[v] || !out.depths[v] || !out.conics[v] || !out.opacities[v])
+            return failf(2, "%s: null view pointer", who);
+        if ((reinterpret_cast<uintptr_t>(out.means2d[v]) & 7) != 0) return failf(2, "%s: means2d slices must be 8-byte aligned", who);
+    }
+    projection_fwd_kernel<3><<<cdiv(n_block, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        V, n_local, means, nullptr, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip,
+        camera_model, 0, radii_local, nullptr, nullptr, conics_local, nullptr, nullptr, nullptr, nullptr, n_block, opacities, out);
+    return check_launch("projection_owner_fwd");
+}
+
+extern "C" int gsb200_projection_owner_bwd(uint32_t V, uint32_t n_local, uint32_t n_block, const float *means, const float *quats,
+                                           const float *scales, const float *viewmats, const float *Ks, uint32_t W, uint32_t H,
+                                           float eps2d, int camera_model, const int32_t *radii_local, const float *conics_local,
+                                           const float *v_means2d, const float *v_depths, const float *v_conics, float *v_means,
+                                           float *v_quats, float *v_scales, gsb200_stream_t stream) {
+    const char *who = "gsb200_projection_owner_bwd";
+    if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
+        return failf(2, "%s: camera_model must be pinhole, ortho or fisheye", who);
+    if (V == 0 || n_local > n_block) return failf(2, "%s: bad sizes", who);
+    if (n_local == 0) return 0;
+    if (!means || !quats || !scales || !viewmats || !Ks || !radii_local || !conics_local || !v_means2d || !v_conics || !v_means ||
+        !v_quats || !v_scales)
+        return failf(2, "%s: null pointer", who);
+    const dim3 grid(cdiv(n_local, kThreads));
+    cudaStream_t s = (cudaStream_t)stream;
+#define GSB_LAUNCH_OWNER_BWD(FE)                                                                                              \
+    projection_bwd_kernel<false, FE, false><<<grid, kThreads, 0, s>>>(                                                          \
+        V, n_local, means, nullptr, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii_local,         \
+        conics_local, nullptr, v_means2d, v_depths, v_conics, nullptr, v_means, nullptr, v_quats, v_scales, nullptr, nullptr,   \
+        nullptr, n_block)
+    if (camera_model == GSB200_CAMERA_FISHEYE) GSB_LAUNCH_OWNER_BWD(true); else GSB_LAUNCH_OWNER_BWD(false);
+#undef GSB_LAUNCH_OWNER_BWD
+    return check_launch("projection_owner_bwd");
 }

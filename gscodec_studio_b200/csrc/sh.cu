@@ -922,6 +922,12 @@ shard_push_rows_kernel(uint32_t n_block, uint32_t width, uint32_t slot0, uint64_
         peer_extra.base[p][(size_t)(slot0 + c) * extra_w + threadIdx.x] = extra_src[(size_t)c * extra_w + threadIdx.x];
 }
 
+// a few floats per slot (cameras) to every peer: peer p gets src [n_slots, w] at float offset slot0 * w
+__global__ void peer_push_small_kernel(uint32_t n_floats, uint64_t dst_offset, const float *__restrict__ src, const PeerRows peers) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_floats) peers.base[blockIdx.y][dst_offset + i] = src[i];
+}
+
 }  // namespace gsb200
 
 using namespace gsb200;
@@ -1439,4 +1445,21 @@ extern "C" int gsb200_shard_push_rows(uint32_t world, uint32_t n_block, uint32_t
                                                                         (uint64_t)world * n_block * width, peers, extra_src, extra_w,
                                                                         extras);
     return check_launch("shard_push_rows");
+}
+
+extern "C" int gsb200_peer_push_small(uint32_t world, uint32_t slot0, uint32_t n_slots, uint32_t w, const float *src,
+                                      float *const *peer_dst, gsb200_stream_t stream) {
+    const char *who = "gsb200_peer_push_small";
+    if (world == 0 || world > (uint32_t)kMaxShards) return failf(2, "%s: world must be in [1, %d]", who, kMaxShards);
+    if ((uint64_t)n_slots * w > 65536u) return failf(2, "%s: at most 65536 floats", who);
+    if (n_slots == 0 || w == 0) return 0;
+    if (src == nullptr) return failf(2, "%s: null source", who);
+    PeerRows peers{};
+    for (uint32_t r = 0; r < world; ++r) {
+        peers.base[r] = peer_dst[r];
+        if (peers.base[r] == nullptr) return failf(2, "%s: null destination", who);
+    }
+    const uint32_t n = n_slots * w;
+    peer_push_small_kernel<<<dim3(cdiv(n, 128u), world), 128, 0, (cudaStream_t)stream>>>(n, (uint64_t)slot0 * w, src, peers);
+    return check_launch("peer_push_small");
 }

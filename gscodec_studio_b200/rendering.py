@@ -162,6 +162,7 @@ def rasterization(
         from .distributed import gather_counts, start_gather
 
         counts = gather_counts(N, device)
+        dist_world = len(counts)
         # two collectives each way: the geometry attributes travel as ONE [n, 11 | 10] tensor (every collective has
         # a fixed cost), the (large) colour / SH tensor separately -- it is only waited for after projection and
         # tile intersection have been enqueued, so its transfer overlaps with those kernels
@@ -178,9 +179,18 @@ def rasterization(
 
         n_block = (max(counts) + 3) // 4 * 4
         means_local = means
+        # Preferred path ("owner render"): nothing per-Gaussian moves at all.  Every rank projects ITS rows and evaluates
+        # their SH colours for all views of the job and stores the results of the visible pairs into the viewers' tensors;
+        # the backward sends the blend's gradients of those tensors home (_peer.owner_render_inputs).  Needs the trainers'
+        # parameterisation: (quats, scales), the (sh0, shN) pair, classic rasterisation, fixed cameras.
+        owner_render = (sh_pair_dist is not None and sh_degree is not None and not packed and covars is None
+                        and rasterize_mode == "classic" and not sparse_grad
+                        and sh_pair_dist[1].shape[1] <= SH_SPLIT_MAX_REST
+                        and not ((viewmats.requires_grad or Ks.requires_grad) and torch.is_grad_enabled())
+                        and _peer.owner_render_available(device, C, n_block))
         # Preferred colour path: the coefficients never move.  Every rank evaluates ITS rows for all views of the job and
         # stores the colours into the viewers' tensors; the backward sends colour gradients home (_peer.view_colors_owner)
-        owner_colors = (sh_pair_dist is not None and sh_degree is not None and not packed
+        owner_colors = (not owner_render and sh_pair_dist is not None and sh_degree is not None and not packed
                         and sh_pair_dist[1].shape[1] <= SH_SPLIT_MAX_REST
                         and not (viewmats.requires_grad and torch.is_grad_enabled())
                         and _peer.owner_exchange_available(device, C, n_block))
@@ -195,7 +205,9 @@ def rasterization(
                        and _peer.available(device, (1 + colors[1].shape[1] if isinstance(colors, tuple) else colors.shape[1]) * 3,
                                            n_block))
         colors_local = colors
-        if owner_colors:
+        if owner_render:
+            geo, pending_colors = None, None
+        elif owner_colors:
             geo, published = _peer.publish_and_gather_geometry(geo_parts, pad_row, None, n_block)
             pending_colors = None
         elif pull_colors:
@@ -205,23 +217,36 @@ def rasterization(
             pending_geo = start_gather(torch.cat(geo_parts, dim=1), counts, keep_padding=True, pad_row=pad_row)
             pending_colors = start_gather(colors, counts, keep_padding=True)
             geo = torch.split(pending_geo.finish(), widths, dim=1)
-        means = geo[0]
-        if covars is None:
-            quats, scales = geo[1], geo[2]
+        if geo is not None:
+            means = geo[0]
+            if covars is None:
+                quats, scales = geo[1], geo[2]
+            else:
+                covars = geo[1]
+            opacities = geo[-1][:, 0]
+            N = means.shape[0]
         else:
-            covars = geo[1]
-        opacities = geo[-1][:, 0]
+            N = dist_world * n_block
         colors = None
-        N = means.shape[0]
     else:
-        pending_colors, pull_colors, owner_colors = None, False, False
+        pending_colors, pull_colors, owner_colors, owner_render = None, False, False, False
 
-    proj_results = fully_fused_projection(
-        means, covars, quats, scales, viewmats, Ks, width, height,
-        eps2d=eps2d, packed=packed, near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip,
-        sparse_grad=sparse_grad, calc_compensations=(rasterize_mode == "antialiased"), camera_model=camera_model,
-    )
-    if packed:
+    if owner_render:
+        from .cuda._wrapper import _CAMERA_MODELS
+
+        radii, means2d, depths, conics, opacities, owner_colours = _peer.owner_render_inputs(
+            sh_degree, means_local, quats, scales, opacities, sh_pair_dist, viewmats, Ks, width, height, n_block, eps2d,
+            near_plane, far_plane, radius_clip, _CAMERA_MODELS[camera_model])
+        proj_results = (radii, means2d, depths, conics, None)
+    else:
+        proj_results = fully_fused_projection(
+            means, covars, quats, scales, viewmats, Ks, width, height,
+            eps2d=eps2d, packed=packed, near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip,
+            sparse_grad=sparse_grad, calc_compensations=(rasterize_mode == "antialiased"), camera_model=camera_model,
+        )
+    if owner_render:
+        camera_ids, gaussian_ids, compensations = None, None, None  # (opacities is already [C, N])
+    elif packed:
         camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = proj_results
         opacities = opacities[gaussian_ids]  # [nnz]
     else:
@@ -247,7 +272,9 @@ def rasterization(
     if pending_colors is not None:
         colors = pending_colors.finish()
 
-    if sh_degree is None:
+    if owner_render:
+        colors = owner_colours
+    elif sh_degree is None:
         if packed:
             colors = colors[gaussian_ids] if colors.dim() == 2 else colors[camera_ids, gaussian_ids]
         else:

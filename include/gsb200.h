@@ -236,6 +236,29 @@ int gsb200_shard_gather_rows(uint32_t world, uint64_t block_floats, const float 
  *                      v_shN (dense, 16-byte aligned) and v_means [n_local,3] (NULL = not wanted), summing the views in
  *                      order (reproducible).  Camera-centre gradients are not produced on this path.
  * Replaces the coefficient all-to-all of the reference's distributed mode (rendering.py:397-478). */
+/* Owner-side projection, same idea for stage 1 / 4b: every rank projects ITS rows for all V views (the cameras were
+ * exchanged with gsb200_peer_push_small + a barrier) and stores radius (always), 2-D mean, depth, conic and opacity (visible
+ * pairs only) into the viewers' tensors: view_X[v] = address of this owner's n_block rows inside view v's X tensor (HOST
+ * arrays of V device pointers into peer memory).  radii_local [V, n_block] / conics_local [V, n_block, 3] keep what the
+ * owner's backward needs.  _owner_bwd: v_means2d [V, n_block, 2], v_conics [V, n_block, 3], v_depths [V, n_block] (NULL =
+ * none) were pushed by the viewers (gsb200_shard_push_rows); gradients of the local means / quats / scales are written once,
+ * summed over the views in order, no atomics.  (quats, scales) parameterisation, no compensations, no camera gradients --
+ * the caller falls back to the gather path for anything else.  Replaces fully_fused_projection_{fwd,bwd} + the attribute
+ * all-gather / gradient reduce-scatter of the reference's distributed mode (rendering.py:282-294, distributed.py:102-167). */
+int gsb200_projection_owner_fwd(uint32_t V, uint32_t n_local, uint32_t n_block, const float *means, const float *quats,
+                                const float *scales, const float *opacities, const float *viewmats, const float *Ks,
+                                uint32_t W, uint32_t H, float eps2d, float near_plane, float far_plane,
+                                float radius_clip, int camera_model, int32_t *radii_local, float *conics_local,
+                                int32_t *const *view_radii, float *const *view_means2d, float *const *view_depths,
+                                float *const *view_conics, float *const *view_opacities, gsb200_stream_t stream);
+int gsb200_projection_owner_bwd(uint32_t V, uint32_t n_local, uint32_t n_block, const float *means, const float *quats,
+                                const float *scales, const float *viewmats, const float *Ks, uint32_t W, uint32_t H,
+                                float eps2d, int camera_model, const int32_t *radii_local, const float *conics_local,
+                                const float *v_means2d, const float *v_depths, const float *v_conics, float *v_means,
+                                float *v_quats, float *v_scales, gsb200_stream_t stream);
+/* src [n_slots, w] floats (a rank's cameras) -> peer_dst[p] + slot0 * w on every peer p (HOST array of device pointers). */
+int gsb200_peer_push_small(uint32_t world, uint32_t slot0, uint32_t n_slots, uint32_t w, const float *src,
+                           float *const *peer_dst, gsb200_stream_t stream);
 int gsb200_shard_push_rows(uint32_t world, uint32_t n_block, uint32_t width, uint32_t n_slots, uint32_t slot0,
                            uint64_t slot_floats, const float *src, float *const *peer_staging, const float *extra_src,
                            uint32_t extra_w, float *const *peer_extra, gsb200_stream_t stream);

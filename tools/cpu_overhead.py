@@ -16,7 +16,8 @@ from gscodec_studio_b200.compression_simulation import CompressionSimulation  # 
 from gscodec_studio_b200.losses import photometric_loss  # noqa: E402
 
 dev = torch.device("cuda:0")
-raw, viewmat, K, target, n_total = bench.build_workload(0, 1, 3)
+import os as _os
+raw, viewmat, K, target, n_total = bench.build_workload(0, 1, int(_os.environ.get("SCENE_GRID", "3")))
 params = {k: v.to(dev).requires_grad_(True) for k, v in raw.items()}
 viewmat, K, target = viewmat.to(dev), K.to(dev), target.to(dev)
 sim = CompressionSimulation(entropy_model_enable=False, device=dev)
