@@ -77,7 +77,8 @@ def build_workload(rank: int, world: int, scene_grid: int):
         "shN": shN,
     }
     raw = {k: v[rank::world].contiguous() for k, v in raw.items()}
-    target = torch.rand(1, H_IMG, W_IMG, 3, generator=gen)
+    # an 8-bit RGB image, as a dataset stores it (float copy = value / 255)
+    target = torch.randint(0, 256, (1, H_IMG, W_IMG, 3), generator=gen, dtype=torch.uint8).float() / 255.0
     return raw, viewmat, K, target, n_total
 
 
@@ -191,8 +192,12 @@ def run_ours(args):
     raw_cpu, viewmat_cpu, K_cpu, target_cpu, n_total = build_workload(rank, world, args.scene_grid)
     params = {k: v.to(dev).requires_grad_(True) for k, v in raw_cpu.items()}
     # pinned host copies of the per-step inputs (camera + target image) for the end-to-end leg
-    host_in = [t.pin_memory() for t in (viewmat_cpu, K_cpu, target_cpu)]
-    dev_in = [t.to(dev) for t in host_in]
+    # (the target image travels as the 8-bit RGB a dataset stores -- 6.2 MB instead of the 24.9 MB float32 copy the reference
+    # trainer uploads before its own on-device `/ 255` (examples/simple_trainer.py:689) -- and becomes float32 on the device,
+    # inside the timed step)
+    target_u8 = (target_cpu * 255.0).round().to(torch.uint8)
+    host_in = [t.pin_memory() for t in (viewmat_cpu, K_cpu, target_u8)]
+    dev_in = [viewmat_cpu.to(dev), K_cpu.to(dev), target_cpu.to(dev)]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_in)
     sim = CompressionSimulation(entropy_model_enable=args.entropy,
                                 entropy_steps={"means": -1, "scales": 0, "quats": 0, "opacities": -1, "sh0": 0, "shN": -1},
@@ -273,7 +278,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     copy_stream = torch.cuda.Stream(device=dev)
-    dev_bufs = [dev_in, [torch.empty_like(t) for t in dev_in]]
+    dev_bufs = [[torch.empty_like(t, device=dev) for t in host_in] for _ in range(2)]  # camera, K, 8-bit image
+    target_f32 = [torch.empty_like(dev_in[2]) for _ in range(2)]
     host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -292,7 +298,7 @@ def run_ours(args):
         free = [torch.cuda.Event(), torch.cuda.Event()]
 
         def issue_copy(k):
-            # camera first (two tiny tensors, needed by the projection), then the target image (25 MB, first read by the
+            # camera first (two tiny tensors, needed by the projection), then the target image (6 MB, first read by the
             # loss): the step starts as soon as the camera is there
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(free[k])
@@ -314,7 +320,12 @@ def run_ours(args):
                 if i + 1 < n_steps:
                     issue_copy((i + 1) % 2)
                 main.wait_event(ready_cam[k])
-                loss_t = step(*dev_bufs[k], before_target=lambda k=k: main.wait_event(ready[k]))
+
+                def target_ready(k=k):
+                    main.wait_event(ready[k])
+                    torch.mul(dev_bufs[k][2], 1.0 / 255.0, out=target_f32[k])  # 8-bit image -> float32, on the device
+
+                loss_t = step(dev_bufs[k][0], dev_bufs[k][1], target_f32[k], before_target=target_ready)
                 free[k].record(main)
                 # device -> host read of EVERY step's result: an asynchronous 4-byte copy into pinned memory that the
                 # host consumes one step later (the way a trainer's logger reads its loss), so the read does not
@@ -352,6 +363,7 @@ def run_ours(args):
     blend_ms = _cabi.stage_timing_ms()
     _cabi.enable_stage_timing(False)
     launches = _cabi.launch_count() - launches0
+    timed(3, e2e=True)  # warm-up of what only the e2e loop runs (copy stream, 8-bit -> float32 kernel: first use loads a module)
     ms_e2e, _ = timed(args.steps, e2e=True)
     _cabi.enable_stage_timing(True)
     timed(max(3, min(args.steps, 10)), e2e=False)
@@ -414,11 +426,14 @@ def run_ours(args):
                              + (", colors=torch.cat([sh0, shN], 1)" if args.cat_colors else ", colors=(sh0, shN) pair")
                              + (", factorized entropy model on" if args.entropy else "")),
                 "n_isects": n_isects, "l2": "inputs larger than L2 (236 MB of splat attributes + 25 MB image per step)",
-                "parallelism": (f"view-parallel x{world} (rank r renders view 0 yawed by 3r degrees from the attributes of "
-                                f"{world} Gaussian shards: geometry pulled over NVLink, SH rows of visible Gaussians pulled on "
-                                f"demand, gradients pushed / reduce-scattered to the owners)") if world > 1 else "single GPU",
+                "parallelism": (f"view-parallel x{world} (rank r renders view 0 yawed by 3r degrees; the {n_total} Gaussians are "
+                                f"sharded over the {world} ranks, every rank projects and colours ITS shard for all {world} views "
+                                f"and stores the visible pairs' results into the viewers' tensors over NVLink peer memory, the "
+                                f"blend's gradients of those tensors travel back to the owners)") if world > 1 else "single GPU",
             },
-            "e2e": {"value": round(value_e2e, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+            "e2e": {"value": round(value_e2e, 2), "unit": "Mpix/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "inputs": "camera (viewmat, K) + the 1920x1080 target as the 8-bit RGB image a dataset stores, converted to "
+                              "float32 on the device inside the step (the reference trainer uploads the float32 copy, 24.9 MB)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
