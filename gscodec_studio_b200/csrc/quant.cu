@@ -57,20 +57,40 @@ __device__ __forceinline__ void fake_quantize_fwd4(int64_t base, int64_t n, floa
             u[0] = u01_centered(r.x); u[1] = u01_centered(r.y); u[2] = u01_centered(r.z); u[3] = u01_centered(r.w);
         }
     }
+    // whole, 16-byte aligned quads move as one vector each way; the ragged tail and unaligned tensors element-wise
+    const bool vec = base + 4 <= n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    float in[4] = {0.f, 0.f, 0.f, 0.f}, cl4[4], out4[4];
+    if (vec) {
+        const float4 v4 = *reinterpret_cast<const float4 *>(x + base);
+        in[0] = v4.x; in[1] = v4.y; in[2] = v4.z; in[3] = v4.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (base + k < n) in[k] = x[base + k];
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (base + k >= n) break;
-        const float v = x[base + k];
-        const float cl = fminf(fmaxf(v, lo), hi);
+        const float cl = fminf(fmaxf(in[k], lo), hi);
         float out;
         if (mode == 0) {
             out = __fadd_rn(cl, __fmul_rn(u[k], q_step));  // ops.py:44-47 (two roundings, like the torch ops)
         } else {
-            x[base + k] = cl;  // in-place clamp of the parameter, ops.py:63
             const float nrm = __fdiv_rn(cl - lo, hi - lo);
             out = __fadd_rn(__fmul_rn(__fmul_rn(rintf(__fdiv_rn(nrm, qs_norm)), qs_norm), hi - lo), lo);  // ops.py:65-69
         }
-        y[base + k] = activate(act, out);
+        cl4[k] = cl;
+        out4[k] = activate(act, out);
+    }
+    if (vec) {
+        if (mode != 0) *reinterpret_cast<float4 *>(x + base) = make_float4(cl4[0], cl4[1], cl4[2], cl4[3]);  // ops.py:63
+        *reinterpret_cast<float4 *>(y + base) = make_float4(out4[0], out4[1], out4[2], out4[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (base + k >= n) break;
+            if (mode != 0) x[base + k] = cl4[k];  // in-place clamp of the parameter, ops.py:63
+            y[base + k] = out4[k];
+        }
     }
 }
 
@@ -81,21 +101,40 @@ fake_quantize_fwd_kernel(int64_t n, float *__restrict__ x, float lo, float hi, f
                        offset, y);
 }
 
-__device__ __forceinline__ void fake_quantize_bwd1(int64_t i, int64_t n, const float *__restrict__ x, const float *__restrict__ y,
+__device__ __forceinline__ float fake_quantize_bwd_elem(float g, float xv, float yv, float lo, float hi, int mode, int act) {
+    if (act == 1) g *= yv;
+    else if (act == 2) g *= yv * (1.f - yv);
+    if (mode == 0) g = (xv >= lo && xv <= hi) ? g : 0.f;  // clamp gate; round mode is a pure STE
+    return g;
+}
+
+// 4 consecutive elements starting at `base`: one 16-byte vector per array when the quad is whole and aligned
+__device__ __forceinline__ void fake_quantize_bwd4(int64_t base, int64_t n, const float *__restrict__ x, const float *__restrict__ y,
                                                    float lo, float hi, int mode, int act, const float *__restrict__ v_y,
                                                    float *__restrict__ v_x) {
-    if (i >= n) return;
-    float g = v_y[i];
-    if (act == 1) g *= y[i];
-    else if (act == 2) { const float s = y[i]; g *= s * (1.f - s); }
-    if (mode == 0) { const float v = x[i]; g = (v >= lo && v <= hi) ? g : 0.f; }  // clamp gate; round mode is a pure STE
-    v_x[i] = g;
+    if (base >= n) return;
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(v_y) |
+                           reinterpret_cast<uintptr_t>(v_x);
+    if (base + 4 <= n && (bits & 15) == 0) {
+        const float4 g = *reinterpret_cast<const float4 *>(v_y + base);
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv = xv;
+        if (mode == 0) xv = *reinterpret_cast<const float4 *>(x + base);
+        if (act != 0) yv = *reinterpret_cast<const float4 *>(y + base);
+        *reinterpret_cast<float4 *>(v_x + base) =
+            make_float4(fake_quantize_bwd_elem(g.x, xv.x, yv.x, lo, hi, mode, act), fake_quantize_bwd_elem(g.y, xv.y, yv.y, lo, hi, mode, act),
+                        fake_quantize_bwd_elem(g.z, xv.z, yv.z, lo, hi, mode, act), fake_quantize_bwd_elem(g.w, xv.w, yv.w, lo, hi, mode, act));
+        return;
+    }
+    for (int k = 0; k < 4 && base + k < n; ++k) {
+        const int64_t i = base + k;
+        v_x[i] = fake_quantize_bwd_elem(v_y[i], mode == 0 ? x[i] : 0.f, act != 0 ? y[i] : 0.f, lo, hi, mode, act);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads)
 fake_quantize_bwd_kernel(int64_t n, const float *__restrict__ x, const float *__restrict__ y, float lo, float hi, int mode,
                          int act, const float *__restrict__ v_y, float *__restrict__ v_x) {
-    fake_quantize_bwd1((int64_t)blockIdx.x * kThreads + threadIdx.x, n, x, y, lo, hi, mode, act, v_y, v_x);
+    fake_quantize_bwd4(((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4, n, x, y, lo, hi, mode, act, v_y, v_x);
 }
 
 // ---- all attributes of a step in ONE launch per direction (the policy quantises 4-7 tensors per step; one launch each
@@ -121,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) fake_quantize_multi_bwd_kernel(const
     while (ti + 1 < T.n && blockIdx.x >= T.block_end[ti]) ++ti;
     const gsb200_fq_tensor &h = T.t[ti];
     const uint32_t blk = blockIdx.x - (ti == 0 ? 0u : T.block_end[ti - 1]);
-    fake_quantize_bwd1((int64_t)blk * kThreads + threadIdx.x, h.n, h.x, h.y, h.lo, h.hi, h.mode, h.act, h.v_y, h.v_x);
+    fake_quantize_bwd4(((int64_t)blk * kThreads + threadIdx.x) * 4, h.n, h.x, h.y, h.lo, h.hi, h.mode, h.act, h.v_y, h.v_x);
 }
 
 // ---------------------------------------------------------------- factorized entropy model
@@ -312,7 +351,7 @@ static int fq_table(const char *who, uint32_t n_tensors, const gsb200_fq_tensor 
         const double levels = (double)((1ull << h.bitwidth) - 1ull);
         T.q_step[T.n] = (float)(((double)h.hi - (double)h.lo) / levels);
         T.qs_norm[T.n] = (float)(1.0 / levels);
-        const uint64_t units = backward ? (uint64_t)h.n : (uint64_t)(h.n + 3) / 4;
+        const uint64_t units = (uint64_t)(h.n + 3) / 4;  // four elements per thread, both directions
         blocks += (units + kThreads - 1) / kThreads;
         if (blocks > 0x7fffffffull) return failf(2, "%s: too many elements for one launch", who);
         T.t[T.n] = h;
@@ -343,7 +382,7 @@ extern "C" int gsb200_fake_quantize_multi_bwd(uint32_t n_tensors, const gsb200_f
 extern "C" int gsb200_fake_quantize_bwd(int64_t n, const float *x, const float *y, float lo, float hi, int mode, int act,
                                         const float *v_y, float *v_x, gsb200_stream_t stream) {
     if (n == 0) return 0;
-    fake_quantize_bwd_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+    fake_quantize_bwd_kernel<<<(unsigned)(((n + 3) / 4 + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         n, x, y, lo, hi, mode, act, v_y, v_x);
     return check_launch("fake_quantize_bwd");
 }
