@@ -84,6 +84,8 @@ SIGNATURES = {
     "gsb200_fake_quantize_bwd": [_L, _P, _P, _F, _F, _I, _I, _P, _P, _P],
     "gsb200_entropy_fwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P],
     "gsb200_entropy_bwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P, _P, _P],
+    "gsb200_entropy_params_fwd": [_U, _U, _P, _P, _P, _P, _P],
+    "gsb200_entropy_params_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_grid_encode_fwd": [_U, _U, _U, _U, _P, _P, _I, _P, _P, _P, _P],
     "gsb200_grid_encode_bwd": [_U, _U, _U, _U, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "gsb200_selective_adam_update": [_P, _P, _P, _P, _P, _F, _F, _F, _F, _U, _U, _P],

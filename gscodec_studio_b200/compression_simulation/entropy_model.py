@@ -54,6 +54,50 @@ class _EntropyBits(torch.autograd.Function):
         return v_x, v_params, None, None, None, None
 
 
+def _ptr_array(tensors):
+    import ctypes
+
+    arr = (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+class _EntropyParams(torch.autograd.Function):
+    """softplus(matrices) | bias | tanh(factor) of every layer -> the kernels' [channel, PS] table."""
+
+    @staticmethod
+    def forward(ctx, n_hidden: int, channel: int, *raw):
+        nl = n_hidden + 1
+        raw = [t.detach().to(torch.float32).contiguous() for t in raw]
+        mats, bias, fac = raw[:nl], raw[nl:2 * nl], raw[2 * nl:]
+        ps = 9 + (n_hidden - 1) * 15 + 4
+        table = torch.empty((channel, ps), dtype=torch.float32, device=mats[0].device)
+        keep = (_ptr_array(mats), _ptr_array(bias), _ptr_array(fac))
+        with device_guard(table.device):
+            call("gsb200_entropy_params_fwd", channel, n_hidden, keep[0][1], keep[1][1], keep[2][1], ptr(table),
+                 stream_ptr(table.device))
+        ctx.save_for_backward(*mats, *fac)
+        ctx.cfg = (n_hidden, channel)
+        return table
+
+    @staticmethod
+    def backward(ctx, v_table):
+        n_hidden, channel = ctx.cfg
+        nl = n_hidden + 1
+        saved = ctx.saved_tensors
+        mats, fac = list(saved[:nl]), list(saved[nl:])
+        v_table = v_table.contiguous()
+        need = ctx.needs_input_grad[2:]
+        v_m = [torch.empty_like(t) if need[i] else None for i, t in enumerate(mats)]
+        v_b = [torch.empty((channel, t.shape[1], 1), dtype=torch.float32, device=t.device) if need[nl + i] else None
+               for i, t in enumerate(mats)]
+        v_f = [torch.empty_like(t) if need[2 * nl + i] else None for i, t in enumerate(fac)]
+        keep = (_ptr_array(mats), _ptr_array(fac), _ptr_array(v_m), _ptr_array(v_b), _ptr_array(v_f))
+        with device_guard(v_table.device):
+            call("gsb200_entropy_params_bwd", channel, n_hidden, keep[0][1], keep[1][1], ptr(v_table), keep[2][1], keep[3][1],
+                 keep[4][1], stream_ptr(v_table.device))
+        return (None, None, *v_m, *v_b, *v_f)
+
+
 class Entropy_factorized_optimized_refactor(nn.Module):
     def __init__(self, channel=32, init_scale=10, filters=(3, 3, 3), likelihood_bound=1e-6, tail_mass=1e-9,
                  optimize_integer_offset=True, Q=1):
@@ -93,15 +137,14 @@ class Entropy_factorized_optimized_refactor(nn.Module):
         self.likelihood_lower_bound = LowerBound(likelihood_bound)
 
     def _activated_params(self) -> Tensor:
-        """[channel, PS] tensor in the kernel's layout; differentiable w.r.t. the raw parameters."""
-        parts = []
+        """[channel, PS] tensor in the kernel's layout; differentiable w.r.t. the raw parameters.  One launch each way
+        (gsb200_entropy_params_fwd / _bwd) instead of ~35 tiny torch kernels per model and step."""
         nl = len(self.filters) + 1
-        for i in range(nl):
-            parts.append(nnf.softplus(self._matrices[i]).reshape(self.channel, -1))
-            parts.append(self._bias[i].reshape(self.channel, -1))
-            if i < nl - 1:
-                parts.append(torch.tanh(self._factor[i]).reshape(self.channel, -1))
-        return torch.cat(parts, dim=1).contiguous()
+        raw = [self._matrices[i] for i in range(nl)] + [self._bias[i] for i in range(nl)] + \
+              [self._factor[i] for i in range(nl - 1)]
+        if not raw[0].is_cuda:
+            raise RuntimeError("gscodec_studio_b200: the entropy model needs CUDA tensors (no CPU implementation)")
+        return _EntropyParams.apply(nl - 1, self.channel, *raw)
 
     def _q_value(self, Q) -> float:
         if Q is None:

@@ -170,11 +170,13 @@ __global__ void __launch_bounds__(kThreads) fake_quantize_multi_bwd_kernel(const
 //   last         : W[3] (1x3), b[1]
 template <int NH> struct EntropyDims { static constexpr int PS = 9 + (NH - 1) * 15 + 4; };
 
+// (this file is built without --use_fast_math for the torch-exact activations above; the entropy model keeps the fast
+// intrinsics it was validated with -- an IEEE division here is 8 extra instructions, 22 times per element)
 __device__ __forceinline__ float fast_tanh(float v) {
     const float e = __expf(2.f * v);
-    return 1.f - 2.f / (e + 1.f);  // tanh(v); saturates correctly for |v| large
+    return 1.f - __fdividef(2.f, e + 1.f);  // tanh(v); saturates correctly for |v| large (2 / inf = 0)
 }
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
 template <int NH>
 __device__ __forceinline__ float entropy_logit(const float *__restrict__ P, float u, float (*h_pre)[3], float (*h_tanh)[3]) {
@@ -256,6 +258,62 @@ __device__ __forceinline__ float entropy_logit_vjp(const float *__restrict__ P, 
     return vu;
 }
 
+// ---- activated parameter table of the entropy model in ONE launch each way (softplus of the matrices, tanh of the factors,
+// biases as they are: entropy_model.py:216-232; as torch ops that is ~10 tiny kernels forward and ~25 backward per model, three
+// models per step -- 1 ms of host time).  One thread per (channel, table column).
+struct EntropyRaw {
+    const float *matrices[4], *bias[4], *factor[3];
+    float *v_matrices[4], *v_bias[4], *v_factor[3];
+};
+
+// column of the table row -> (layer, kind 0 matrix / 1 bias / 2 factor, element offset inside the channel's block, block size)
+__device__ __forceinline__ void entropy_column(uint32_t NH, uint32_t col, uint32_t &layer, uint32_t &kind, uint32_t &idx, uint32_t &size) {
+    const uint32_t mid_end = 9 + (NH - 1) * 15;
+    if (col < 9) {
+        layer = 0; kind = col / 3; idx = col % 3; size = 3;
+    } else if (col < mid_end) {
+        layer = 1 + (col - 9) / 15;
+        const uint32_t r = (col - 9) % 15;
+        if (r < 9) { kind = 0; idx = r; size = 9; }
+        else if (r < 12) { kind = 1; idx = r - 9; size = 3; }
+        else { kind = 2; idx = r - 12; size = 3; }
+    } else {
+        layer = NH;
+        const uint32_t r = col - mid_end;
+        if (r < 3) { kind = 0; idx = r; size = 3; }
+        else { kind = 1; idx = 0; size = 1; }
+    }
+}
+
+template <bool BWD>
+__global__ void entropy_params_kernel(uint32_t ch, uint32_t NH, uint32_t PS, const __grid_constant__ EntropyRaw R, float *__restrict__ params,
+                                      const float *__restrict__ v_params) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ch * PS) return;
+    const uint32_t c = t / PS, col = t % PS;
+    uint32_t layer, kind, idx, size;
+    entropy_column(NH, col, layer, kind, idx, size);
+    const size_t at = (size_t)c * size + idx;
+    if (!BWD) {
+        float v;
+        if (kind == 0) { const float x = R.matrices[layer][at]; v = x > 20.f ? x : log1pf(expf(x)); }  // F.softplus
+        else if (kind == 1) v = R.bias[layer][at];
+        else v = tanhf(R.factor[layer][at]);
+        params[t] = v;
+    } else {
+        const float g = v_params[t];
+        if (kind == 0) {
+            const float x = R.matrices[layer][at];
+            if (R.v_matrices[layer]) R.v_matrices[layer][at] = x > 20.f ? g : g / (1.f + expf(-x));
+        } else if (kind == 1) {
+            if (R.v_bias[layer]) R.v_bias[layer][at] = g;
+        } else if (R.v_factor[layer]) {
+            const float th = tanhf(R.factor[layer][at]);
+            R.v_factor[layer][at] = g * (1.f - th * th);
+        }
+    }
+}
+
 constexpr int kEntropyThreads = 128;
 
 // grid: (blocks per segment, 32 chunks, ch); element n = j*L + local, local grid-strided inside the segment
@@ -276,6 +334,14 @@ entropy_kernel(int64_t N, uint32_t ch, int64_t L, const float *__restrict__ x, f
 #pragma unroll
         for (int k = 0; k < PS; ++k) vP[k] = 0.f;
     }
+    // forward: a thread evaluates the same tiny network for all its elements -- its parameters live in registers (the
+    // backward already holds PS gradient accumulators there and reads the parameters from shared memory)
+    float rP[BWD ? 1 : PS];
+    if (!BWD) {
+#pragma unroll
+        for (int k = 0; k < PS; ++k) rP[k] = sP[k];
+    }
+    const float *P = BWD ? sP : rP;
     // grid-stride over the segment: a thread owns many elements, so the parameter-gradient reduction
     // below runs once per thread instead of once per element
     for (int64_t local = (int64_t)blockIdx.x * kEntropyThreads + threadIdx.x; local < L;
@@ -284,8 +350,8 @@ entropy_kernel(int64_t N, uint32_t ch, int64_t L, const float *__restrict__ x, f
         if (n >= N) break;
         const float xv = x[n * ch + c];
         const float ul = xv - 0.5f * q, uu = xv + 0.5f * q;
-        const float lower = entropy_logit<NH>(sP, ul, nullptr, nullptr);
-        const float upper = entropy_logit<NH>(sP, uu, nullptr, nullptr);
+        const float lower = entropy_logit<NH>(P, ul, nullptr, nullptr);
+        const float upper = entropy_logit<NH>(P, uu, nullptr, nullptr);
         const float s = lower + upper;
         const float sign = s > 0.f ? -1.f : (s < 0.f ? 1.f : 0.f);
         const float su = sigmoidf_(sign * upper), sl = sigmoidf_(sign * lower);
@@ -419,4 +485,52 @@ extern "C" int gsb200_entropy_bwd(int64_t N, uint32_t ch, uint32_t n_hidden, con
                                   gsb200_stream_t stream) {
     return entropy_launch(true, N, ch, n_hidden, x, q, params, likelihood_bound, nullptr, v_bits, v_x, v_params,
                           (cudaStream_t)stream);
+}
+
+static int entropy_raw(const char *who, uint32_t n_hidden, const float *const *matrices, const float *const *bias,
+                       const float *const *factor, EntropyRaw &R) {
+    if (n_hidden != 2 && n_hidden != 3) return failf(2, "%s: n_hidden must be 2 or 3", who);
+    R = EntropyRaw{};
+    for (uint32_t i = 0; i <= n_hidden; ++i) {
+        if (matrices == nullptr || matrices[i] == nullptr) return failf(2, "%s: null matrix pointer", who);
+        R.matrices[i] = matrices[i];
+        if (bias != nullptr) R.bias[i] = bias[i];
+        if (i < n_hidden) {
+            if (factor == nullptr || factor[i] == nullptr) return failf(2, "%s: null factor pointer", who);
+            R.factor[i] = factor[i];
+        }
+    }
+    return 0;
+}
+
+extern "C" int gsb200_entropy_params_fwd(uint32_t ch, uint32_t n_hidden, const float *const *matrices, const float *const *bias,
+                                         const float *const *factor, float *params, gsb200_stream_t stream) {
+    const char *who = "gsb200_entropy_params_fwd";
+    EntropyRaw R;
+    if (int e = entropy_raw(who, n_hidden, matrices, bias, factor, R)) return e;
+    if (ch == 0) return 0;
+    for (uint32_t i = 0; i <= n_hidden; ++i)
+        if (R.bias[i] == nullptr) return failf(2, "%s: null bias pointer", who);
+    if (params == nullptr) return failf(2, "%s: null output", who);
+    const uint32_t PS = 9 + (n_hidden - 1) * 15 + 4, n = ch * PS;
+    entropy_params_kernel<false><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ch, n_hidden, PS, R, params, nullptr);
+    return check_launch("entropy_params_fwd");
+}
+
+extern "C" int gsb200_entropy_params_bwd(uint32_t ch, uint32_t n_hidden, const float *const *matrices, const float *const *factor,
+                                         const float *v_params, float *const *v_matrices, float *const *v_bias,
+                                         float *const *v_factor, gsb200_stream_t stream) {
+    const char *who = "gsb200_entropy_params_bwd";
+    EntropyRaw R;
+    if (int e = entropy_raw(who, n_hidden, matrices, nullptr, factor, R)) return e;
+    if (ch == 0) return 0;
+    if (v_params == nullptr) return failf(2, "%s: null v_params", who);
+    for (uint32_t i = 0; i <= n_hidden; ++i) {
+        R.v_matrices[i] = v_matrices ? v_matrices[i] : nullptr;
+        R.v_bias[i] = v_bias ? v_bias[i] : nullptr;
+        if (i < n_hidden) R.v_factor[i] = v_factor ? v_factor[i] : nullptr;
+    }
+    const uint32_t PS = 9 + (n_hidden - 1) * 15 + 4, n = ch * PS;
+    entropy_params_kernel<true><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ch, n_hidden, PS, R, nullptr, v_params);
+    return check_launch("entropy_params_bwd");
 }

@@ -458,6 +458,16 @@ int gsb200_entropy_bwd(int64_t N, uint32_t ch, uint32_t n_hidden, const float *x
                        const float *params, float likelihood_bound, const float *v_bits, float *v_x,
                        float *v_params, gsb200_stream_t stream);
 
+/* The activated parameter table `params` [ch, PS] of the two calls above from the module's raw parameters, one launch each
+ * way: matrices[i] [ch, f(i+1), f(i)] -> softplus, bias[i] [ch, f(i+1), 1] as is, factor[i] [ch, f(i+1), 1] -> tanh
+ * (entropy_model.py:216-232), i = 0..n_hidden (no factor for the last layer); HOST arrays of device pointers.  _bwd applies
+ * the chain rule to v_params [ch, PS] and OVERWRITES v_matrices[i] / v_bias[i] / v_factor[i] (NULL = not wanted). */
+int gsb200_entropy_params_fwd(uint32_t ch, uint32_t n_hidden, const float *const *matrices, const float *const *bias,
+                              const float *const *factor, float *params, gsb200_stream_t stream);
+int gsb200_entropy_params_bwd(uint32_t ch, uint32_t n_hidden, const float *const *matrices, const float *const *factor,
+                              const float *v_params, float *const *v_matrices, float *const *v_bias,
+                              float *const *v_factor, gsb200_stream_t stream);
+
 /* ---------------------------------------------------------------- hash-grid encoder -- EXPERIMENTAL
  * Not yet validated on a GPU; the Python layer only reaches it with GSB200_EXPERIMENTAL_HASHGRID=1.
  * replaces _gridencoder.grid_encode_forward / _backward (third_party/gridencoder/src/gridencoder.cu:100-884,
