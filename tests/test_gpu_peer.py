@@ -1,5 +1,5 @@
-"""GPU tests of the multi-GPU exchange kernels (csrc/sh.cu: publish / gather / push / reduce of the geometry, the
-owner-side colour exchange, the signal-pad barrier) driven from ONE process: the `peer` buffers are separate allocations
+"""GPU tests of the multi-GPU exchange kernels (csrc/sh.cu, csrc/projection.cu: owner-side projection and colour
+exchange, publish / gather / push / reduce of the geometry, the signal-pad barrier) driven from ONE process: the `peer` buffers are separate allocations
 on this GPU, so the addressing, the slot layout and the rank-ordered sums are checked bit for bit against torch and the
 single-array kernels.  The real two-process run over NVLink is tools/dist_check.py (gpurun --gpus 2)."""
 import ctypes
@@ -167,6 +167,109 @@ def test_geometry_exchange_single_process(world, covars):
         assert torch.equal(stagings[r][0, :n_block * 3].view(n_block, 3), odd[r * n_block:(r + 1) * n_block])
     with pytest.raises(RuntimeError):
         call("gsb200_shard_gather_geo", world, n_block + 2, len(widths), keep_w[1], table(blocks)[1], table(outs)[1], s)
+
+
+@pytest.mark.parametrize("world,C,model", [(2, 1, "pinhole"), (3, 2, "pinhole"), (2, 2, "fisheye"), (4, 1, "ortho")])
+def test_owner_projection_single_process(world, C, model):
+    """Owner-side stage 1 (every emulated rank projects ITS rows for all V = world x C views into the viewers' tensors, then
+    runs the projection backward on gradients the viewers pushed) against the single-GPU kernels on the concatenated rows:
+    radii equal, visible rows of means2d / depths / conics / opacities bit-equal, invisible rows untouched, the cameras
+    delivered by peer_push_small, gradients of means / quats / scales bit-equal."""
+    import gscodec_studio_b200 as gs
+    from gscodec_studio_b200._helper import load_test_data
+    from gscodec_studio_b200.cuda._wrapper import _CAMERA_MODELS
+
+    means, quats, scales, opac, _colors, viewmats, Ks, W, H = load_test_data(device=DEV, scene_grid=1)
+    g = torch.Generator().manual_seed(3 + world)
+    n_all = 4000
+    pick = torch.randperm(means.shape[0], generator=g)[:n_all].to(DEV)
+    means, quats, scales, opac = means[pick].contiguous(), quats[pick].contiguous(), scales[pick].contiguous(), opac[pick].contiguous()
+    V = world * C
+    vm_all = viewmats[torch.arange(V) % viewmats.shape[0]].clone()
+    vm_all[:, 0, 3] += torch.linspace(-0.2, 0.2, V, device=DEV)  # V distinct cameras
+    ks_all = Ks[torch.arange(V) % Ks.shape[0]].clone().contiguous()
+    vm_all = vm_all.contiguous()
+    counts = [n_all // world - 5 * r for r in range(world)]
+    n_block = (max(counts) + 7) // 4 * 4
+    n_total = world * n_block
+    starts = [sum(counts[:r]) for r in range(world)]
+    shard = lambda t, r: t[starts[r]:starts[r] + counts[r]].contiguous()  # noqa: E731
+    s = stream_ptr(DEV)
+
+    # reference: one local projection over the block-padded concatenation (padding rows: NaN mean -> culled)
+    def padded(t, fill):
+        out = torch.full((n_total,) + tuple(t.shape[1:]), fill, device=DEV)
+        for r in range(world):
+            out[r * n_block:r * n_block + counts[r]] = shard(t, r)
+        return out
+
+    m_ref = padded(means, float("nan")).requires_grad_(True)
+    q_ref = padded(quats, 0.0)
+    q_ref[:, 0] = torch.where(q_ref.abs().sum(1) == 0, torch.ones_like(q_ref[:, 0]), q_ref[:, 0])
+    q_ref.requires_grad_(True)
+    s_ref = padded(scales, 0.0).requires_grad_(True)
+    radii_r, m2d_r, dep_r, con_r, _ = gs.fully_fused_projection(m_ref, None, q_ref, s_ref, vm_all, ks_all, W, H, camera_model=model)
+    w_m2d = torch.randn(V, n_total, 2, generator=g).to(DEV)
+    w_dep = torch.randn(V, n_total, generator=g).to(DEV)
+    w_con = torch.randn(V, n_total, 3, generator=g).to(DEV)
+    ((m2d_r * w_m2d).sum() + (dep_r * w_dep).sum() + (con_r * w_con).sum()).backward()
+
+    # cameras: every rank pushes its C cameras to every peer
+    cam_vm = [torch.full((V, 16), float("nan"), device=DEV) for _ in range(world)]
+    cam_k = [torch.full((V, 9), float("nan"), device=DEV) for _ in range(world)]
+    for q in range(world):
+        call("gsb200_peer_push_small", world, q * C, C, 16, ptr(vm_all[q * C:(q + 1) * C].contiguous()), table(cam_vm)[1], s)
+        call("gsb200_peer_push_small", world, q * C, C, 9, ptr(ks_all[q * C:(q + 1) * C].contiguous()), table(cam_k)[1], s)
+    for r in range(world):
+        assert torch.equal(cam_vm[r].view(V, 4, 4), vm_all) and torch.equal(cam_k[r].view(V, 3, 3), ks_all)
+
+    # viewer-side tensors (rank q: its C cameras over the whole gathered set), owner-side copies
+    v_radii = [torch.full((C, n_total), -9, dtype=torch.int32, device=DEV) for _ in range(world)]
+    v_m2d = [torch.full((C, n_total, 2), float("nan"), device=DEV) for _ in range(world)]
+    v_dep = [torch.full((C, n_total), float("nan"), device=DEV) for _ in range(world)]
+    v_con = [torch.full((C, n_total, 3), float("nan"), device=DEV) for _ in range(world)]
+    v_opa = [torch.full((C, n_total), float("nan"), device=DEV) for _ in range(world)]
+    radii_loc, conics_loc = [], []
+    for r in range(world):
+        tabs = [table([arr[v // C] for v in range(V)], [((v % C) * n_total + r * n_block) * w for v in range(V)])
+                for arr, w in ((v_radii, 1), (v_m2d, 2), (v_dep, 1), (v_con, 3), (v_opa, 1))]
+        rl = torch.full((V, n_block), -5, dtype=torch.int32, device=DEV)
+        cl = torch.full((V, n_block, 3), float("nan"), device=DEV)
+        call("gsb200_projection_owner_fwd", V, counts[r], n_block, ptr(shard(means, r)), ptr(shard(quats, r)), ptr(shard(scales, r)),
+             ptr(shard(opac, r)), ptr(cam_vm[r]), ptr(cam_k[r]), W, H, 0.3, 0.01, 1e10, 0.0, _CAMERA_MODELS[model], ptr(rl), ptr(cl),
+             tabs[0][1], tabs[1][1], tabs[2][1], tabs[3][1], tabs[4][1], s)
+        radii_loc.append(rl)
+        conics_loc.append(cl)
+    opac_full = padded(opac[:, None], 0.0)[:, 0]
+    for q in range(world):
+        rows = slice(q * C, (q + 1) * C)
+        assert torch.equal(v_radii[q], radii_r[rows])
+        vis = radii_r[rows] > 0
+        assert vis.sum() > 100
+        assert torch.equal(v_m2d[q][vis], m2d_r[rows][vis]) and torch.equal(v_dep[q][vis], dep_r[rows][vis])
+        assert torch.equal(v_con[q][vis], con_r[rows][vis])
+        assert torch.equal(v_opa[q][vis], opac_full[None].expand(C, -1)[vis])
+        assert torch.isnan(v_m2d[q][~vis]).all() and torch.isnan(v_con[q][~vis]).all()  # nothing travels for an invisible pair
+    for r in range(world):
+        assert torch.equal(radii_loc[r], radii_r[:, r * n_block:(r + 1) * n_block])
+
+    # backward: every viewer pushes its gradient rows to the owners, the owners run the projection backward
+    st_m2d = [torch.full((V, n_block, 2), float("nan"), device=DEV) for _ in range(world)]
+    st_dep = [torch.full((V, n_block), float("nan"), device=DEV) for _ in range(world)]
+    st_con = [torch.full((V, n_block, 3), float("nan"), device=DEV) for _ in range(world)]
+    for q in range(world):
+        rows = slice(q * C, (q + 1) * C)
+        for src, w, dst in ((w_m2d, 2, st_m2d), (w_dep, 1, st_dep), (w_con, 3, st_con)):
+            call("gsb200_shard_push_rows", world, n_block, w, C, q * C, n_block * w, ptr(src[rows].contiguous()), table(dst)[1],
+                 None, 0, None, s)
+    for r in range(world):
+        n = counts[r]
+        vm_, vq_, vs_ = (torch.full((n, k), float("nan"), device=DEV) for k in (3, 4, 3))
+        call("gsb200_projection_owner_bwd", V, n, n_block, ptr(shard(means, r)), ptr(shard(quats, r)), ptr(shard(scales, r)),
+             ptr(cam_vm[r]), ptr(cam_k[r]), W, H, 0.3, _CAMERA_MODELS[model], ptr(radii_loc[r]), ptr(conics_loc[r]), ptr(st_m2d[r]),
+             ptr(st_dep[r]), ptr(st_con[r]), ptr(vm_), ptr(vq_), ptr(vs_), s)
+        rows = slice(r * n_block, r * n_block + n)
+        assert torch.equal(vm_, m_ref.grad[rows]) and torch.equal(vq_, q_ref.grad[rows]) and torch.equal(vs_, s_ref.grad[rows])
 
 
 def test_peer_barrier_and_camera_positions():
