@@ -43,7 +43,7 @@ METRIC = "Mpix/s fwd+bwd @1M splats 1920x1080 w/ quant-sim"
 # is the record stream the backward consumes) and blend_stream_bwd_kernel<3,1,0> (128.29 + 6.51 MB), from one
 # `ncu --set full` capture of tools/gpu_stage_timing.py at the headline size -- a constant from that capture, not
 # measured in this run (ncu cannot run inside a timed bench); the roofline object names its source
-NCU_DRAM_TRAFFIC_BYTES = int((27.81 + 76.72 + 128.29 + 6.51) * 1e6)
+NCU_DRAM_TRAFFIC_BYTES = int((28.69 + 82.04 + 128.28 + 5.88) * 1e6)  # gpurun_out/r2v22_blend_stream.ncu-rep
 NCU_TRAFFIC_SOURCE = "profiles/r02_blend_stream_ncu.md (ncu --set full, one launch per kernel, headline size)"
 
 
