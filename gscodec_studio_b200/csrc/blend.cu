@@ -367,9 +367,13 @@ int launch_tile_order(uint32_t total_tiles, int64_t n_isects, const int32_t *off
 }
 
 // packed gradient records -> the reference's tensors
-template <int CDIM>
+// MOMENTS: the record holds the moments of w = -v_sigma about the Gaussian's centre (blend_stream_bwd_kernel):
+//   v_conic = -(1/2 Sxx, Sxy, 1/2 Syy),  v_xy = -(a Sx + b Sy, b Sx + c Sy),  v_opacity = S0 / opacity
+// (rasterize_to_pixels_bwd.cu:225-241 summed over the pixels: every term is linear in w)
+template <int CDIM, bool MOMENTS>
 __global__ void __launch_bounds__(kThreads)
-unpack_grads_kernel(uint32_t M, const float *__restrict__ rec, float *__restrict__ v_abs, float *__restrict__ v_means2d,
+unpack_grads_kernel(uint32_t M, const float *__restrict__ rec, const float *__restrict__ conics, const float *__restrict__ opacities,
+                    float *__restrict__ v_abs, float *__restrict__ v_means2d,
                     float *__restrict__ v_conics, float *__restrict__ v_colors, float *__restrict__ v_opac) {
     constexpr uint32_t REC = grad_record(CDIM);
     const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
@@ -382,6 +386,18 @@ unpack_grads_kernel(uint32_t M, const float *__restrict__ rec, float *__restrict
     }
 #pragma unroll
     for (int k = 0; k < CDIM; ++k) v_colors[(size_t)g * CDIM + k] = r[k];
+    if (MOMENTS) {
+        const float sxx = r[CDIM], sxy = r[CDIM + 1], syy = r[CDIM + 2], sx = r[CDIM + 3], sy = r[CDIM + 4], s0 = r[CDIM + 5];
+        const bool touched = sxx != 0.f || sxy != 0.f || syy != 0.f || sx != 0.f || sy != 0.f || s0 != 0.f;
+        float a = 0.f, b = 0.f, c = 0.f, o = 1.f;
+        if (touched) {  // (rows no pixel wrote to stay zero without reading their attributes)
+            a = __ldg(conics + (size_t)g * 3); b = __ldg(conics + (size_t)g * 3 + 1); c = __ldg(conics + (size_t)g * 3 + 2);
+            o = __ldg(opacities + g);
+        }
+        r[CDIM] = -0.5f * sxx; r[CDIM + 1] = -sxy; r[CDIM + 2] = -0.5f * syy;
+        r[CDIM + 3] = -(a * sx + b * sy); r[CDIM + 4] = -(b * sx + c * sy);
+        r[CDIM + 5] = s0 != 0.f ? s0 / o : 0.f;
+    }
     v_conics[(size_t)g * 3] = r[CDIM]; v_conics[(size_t)g * 3 + 1] = r[CDIM + 1]; v_conics[(size_t)g * 3 + 2] = r[CDIM + 2];
     *reinterpret_cast<float2 *>(v_means2d + (size_t)g * 2) = make_float2(r[CDIM + 3], r[CDIM + 4]);
     v_opac[g] = r[CDIM + 5];
@@ -390,9 +406,14 @@ unpack_grads_kernel(uint32_t M, const float *__restrict__ rec, float *__restrict
 
 template <int CDIM>
 static int launch_unpack(uint32_t M, const float *grad_scratch, float *v_abs, float *v_means2d, float *v_conics, float *v_colors,
-                         float *v_opacities, cudaStream_t s) {
-    unpack_grads_kernel<CDIM><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, v_abs, v_means2d, v_conics, v_colors,
-                                                                      v_opacities);
+                         float *v_opacities, cudaStream_t s, bool moments = false, const float *conics = nullptr,
+                         const float *opacities = nullptr) {
+    if (moments)
+        unpack_grads_kernel<CDIM, true><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, conics, opacities, v_abs, v_means2d,
+                                                                                v_conics, v_colors, v_opacities);
+    else
+        unpack_grads_kernel<CDIM, false><<<cdiv(M, kThreads), kThreads, 0, s>>>(M, grad_scratch, nullptr, nullptr, v_abs, v_means2d,
+                                                                                 v_conics, v_colors, v_opacities);
     return check_launch("unpack_grads");
 }
 
@@ -541,7 +562,9 @@ extern "C" int gsb200_rasterize_bwd(uint32_t C, uint32_t M, int64_t n_isects, ui
                                          v_render_alphas, tile_order, blend_stream, tile_counts, grad_scratch,
                                          v_means2d_abs != nullptr, s))
                 return e;
-        GSB_DISPATCH_CDIM(D, (launch_unpack<CD>(M, grad_scratch, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s)));
+        const bool moments = blend_stream_bwd_moments(v_means2d_abs != nullptr);
+        GSB_DISPATCH_CDIM(D, (launch_unpack<CD>(M, grad_scratch, v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities, s, moments,
+                                                conics, opacities)));
     }
     GSB_DISPATCH_CDIM(D, (launch_bwd<CD>(G, M, means2d, conics, colors, opacities, backgrounds, masks, tile_offsets,
                                          flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas, tile_order,

@@ -137,6 +137,9 @@ int launch_tile_order(uint32_t total_tiles, int64_t n_isects, const int32_t *off
 
 // ---- blend_stream.cu entry points (16x16 tiles, <= 4 colour channels) ------------------------------------
 bool blend_stream_supported(uint32_t tile_size, uint32_t cdim, int64_t n_isects);
+// true: the stream backward leaves [rgb | sum w dx^2, sum w dx dy, sum w dy^2, sum w dx, sum w dy | sum w] (w = -v_sigma) in the
+// gradient record instead of [rgb | v_conic | v_xy | v_opacity]; unpack_grads_kernel applies the per-Gaussian linear map
+bool blend_stream_bwd_moments(bool absgrad);
 int blend_stream_fwd(const BlendGeom &G, uint32_t cdim, const float *means2d, const float *conics, const float *colors,
                      const float *opacities, const float *backgrounds, const uint8_t *masks, const int32_t *tile_offsets,
                      const int32_t *flatten_ids, float *render_colors, float *render_alphas, int32_t *last_ids,

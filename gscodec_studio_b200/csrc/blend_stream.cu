@@ -40,6 +40,9 @@ constexpr int kStages = GSB_STREAM_STAGES;
 #ifndef GSB_CONSUMER_SLEEP_NS
 #define GSB_CONSUMER_SLEEP_NS 32
 #endif
+#ifndef GSB_BWD_MOMENTS
+#define GSB_BWD_MOMENTS 1  // backward accumulates moments of -v_sigma (finished per Gaussian in unpack_grads_kernel); 0: round-2 form
+#endif
 constexpr int kRecBytes = 48;
 constexpr uint32_t kEndFlag = 0x100;
 constexpr float kNegLog2e = -1.4426950408889634f;
@@ -608,22 +611,41 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                         float2 nvs = __fmul2_rn(ov, v_alpha);  // -v_sigma
                         nvs.x = gate0 ? nvs.x : 0.f;
                         nvs.y = gate1 ? nvs.y : 0.f;
-                        const float2 hs = __fmul2_rn(nvs, bc(0.5f));
-                        const float2 ga = __fmul2_rn(__fmul2_rn(hs, bc(dx)), bc(dx));
-                        const float2 gb = __fmul2_rn(__fmul2_rn(nvs, bc(dx)), dy);
-                        const float2 gc = __fmul2_rn(__fmul2_rn(hs, dy), dy);
-                        const float2 gx = __fmul2_rn(nvs, __ffma2_rn(bc(B.y), dy, bc(u)));
-                        const float2 gy = __fmul2_rn(nvs, __ffma2_rn(bc(B.z), dy, bc(v)));
-                        acc<NP == 1>(vals[CDIM + 0], -ga.x - ga.y);
-                        acc<NP == 1>(vals[CDIM + 1], -gb.x - gb.y);
-                        acc<NP == 1>(vals[CDIM + 2], -gc.x - gc.y);
-                        acc<NP == 1>(vals[CDIM + 3], -gx.x - gx.y);
-                        acc<NP == 1>(vals[CDIM + 4], -gy.x - gy.y);
-                        const float2 go = __fmul2_rn(vis, v_alpha);
-                        acc<NP == 1>(tail[0], (gate0 ? go.x : 0.f) + (gate1 ? go.y : 0.f));
-                        if (ABS) {
-                            acc<NP == 1>(tail[1], fabsf(gx.x) + fabsf(gx.y));
-                            acc<NP == 1>(tail[2], fabsf(gy.x) + fabsf(gy.y));
+                        if (ABS || !GSB_BWD_MOMENTS) {
+                            const float2 hs = __fmul2_rn(nvs, bc(0.5f));
+                            const float2 ga = __fmul2_rn(__fmul2_rn(hs, bc(dx)), bc(dx));
+                            const float2 gb = __fmul2_rn(__fmul2_rn(nvs, bc(dx)), dy);
+                            const float2 gc = __fmul2_rn(__fmul2_rn(hs, dy), dy);
+                            const float2 gx = __fmul2_rn(nvs, __ffma2_rn(bc(B.y), dy, bc(u)));
+                            const float2 gy = __fmul2_rn(nvs, __ffma2_rn(bc(B.z), dy, bc(v)));
+                            acc<NP == 1>(vals[CDIM + 0], -ga.x - ga.y);
+                            acc<NP == 1>(vals[CDIM + 1], -gb.x - gb.y);
+                            acc<NP == 1>(vals[CDIM + 2], -gc.x - gc.y);
+                            acc<NP == 1>(vals[CDIM + 3], -gx.x - gx.y);
+                            acc<NP == 1>(vals[CDIM + 4], -gy.x - gy.y);
+                            const float2 go = __fmul2_rn(vis, v_alpha);
+                            acc<NP == 1>(tail[0], (gate0 ? go.x : 0.f) + (gate1 ? go.y : 0.f));
+                            if (ABS) {
+                                acc<NP == 1>(tail[1], fabsf(gx.x) + fabsf(gx.y));
+                                acc<NP == 1>(tail[2], fabsf(gy.x) + fabsf(gy.y));
+                            }
+                        } else {
+                            // moment form: every geometric gradient is linear in the five moments of w = -v_sigma about the
+                            // Gaussian's centre, sum w {dx, dy, dx^2, dx dy, dy^2}, and v_opacity = sum w / opacity (w = opacity
+                            // * vis * v_alpha under the same gate).  The record accumulates the moments; the linear map to
+                            // (v_conic, v_xy, v_opacity) runs once per Gaussian in unpack_grads_kernel.  dx is shared by the
+                            // thread's two pixels: 2 packed + 6 scalar operations instead of 12 packed + 6 scalar.
+                            const float n01 = nvs.x + nvs.y;
+                            const float2 nd = __fmul2_rn(nvs, dy);
+                            const float2 ndd = __fmul2_rn(nd, dy);
+                            const float sy = nd.x + nd.y;
+                            const float sx = dx * n01;
+                            acc<NP == 1>(vals[CDIM + 0], dx * sx);
+                            acc<NP == 1>(vals[CDIM + 1], dx * sy);
+                            acc<NP == 1>(vals[CDIM + 2], ndd.x + ndd.y);
+                            acc<NP == 1>(vals[CDIM + 3], sx);
+                            acc<NP == 1>(vals[CDIM + 4], sy);
+                            acc<NP == 1>(tail[0], n01);
                         }
                     }
                     if (!any_valid) continue;
@@ -675,6 +697,8 @@ static int stream_np() {
     }();
     return np;
 }
+
+bool blend_stream_bwd_moments(bool absgrad) { return GSB_BWD_MOMENTS && !absgrad; }
 
 bool blend_stream_supported(uint32_t tile_size, uint32_t cdim, int64_t n_isects) {
     return tile_size == 16 && cdim >= 1 && cdim <= 4 && n_isects < (int64_t(1) << 28);
