@@ -239,7 +239,7 @@ def run_ours(args):
     if args.entropy:
         sims[True] = sim
 
-    def make_step(cat_colors, torch_loss, fuse_act, entropy):
+    def make_step(cat_colors, torch_loss, fuse_act, entropy, on_load=False):
         """One training step of the M2 workload.  The default (False, False, True, args.entropy) uses the package's two
         additive hooks; (True, True, False, .) is the reference trainer's literal call sequence
         (examples/simple_trainer.py:766-778, 948-953): simulate_compression -> exp / sigmoid in torch ->
@@ -250,7 +250,7 @@ def run_ours(args):
         def step(viewmat, K, target, before_target=None):
             for p in params.values():
                 p.grad = None
-            new, bits = the_sim.simulate_compression(params, the_step, fuse_activations=fuse_act)
+            new, bits = the_sim.simulate_compression(params, the_step, fuse_activations=fuse_act, fuse_into_render=on_load)
             scales = new["scales_act"] if "scales_act" in new else torch.exp(new["scales"])
             opac = new["opacities_act"] if "opacities_act" in new else torch.sigmoid(new["opacities"])
             colors = torch.cat([new["sh0"], new["shN"]], 1) if cat_colors else (new["sh0"], new["shN"])
@@ -269,7 +269,9 @@ def run_ours(args):
 
         return step
 
-    default_step = step_m1 if m1_attrs is not None else make_step(args.cat_colors, args.torch_loss, True, args.entropy)
+    # (view-parallel runs keep the one-launch quantiser: the owner-side exchange kernels read materialised attributes)
+    on_load = not args.no_quant_on_load and not args.cat_colors and world == 1
+    default_step = step_m1 if m1_attrs is not None else make_step(args.cat_colors, args.torch_loss, True, args.entropy, on_load)
     step = default_step
 
     def barrier():
@@ -389,7 +391,7 @@ def run_ours(args):
                                         note="the reference trainer's literal call sequence: torch exp/sigmoid, "
                                              "torch.cat([sh0, shN], 1), torch L1 (no additive hooks)")
         if not args.entropy:
-            extra["entropy_on"] = dict(leg(make_step(args.cat_colors, args.torch_loss, True, True)),
+            extra["entropy_on"] = dict(leg(make_step(args.cat_colors, args.torch_loss, True, True, on_load)),
                                        note="same step with the factorized entropy model's rate term on scales / quats / sh0")
         extra["ref_cuda"] = ref_cuda_leg(params, dev_in, k_extra)
 
@@ -421,8 +423,10 @@ def run_ours(args):
                              f"1 view 1920x1080 per GPU, 3 colour channels, packed={args.packed}, loss=sum, no quant-sim"
                              if args.workload == "m1" else
                              f"M2: load_test_data(scene_grid={args.scene_grid}) {n_total} Gaussians, 1 view 1920x1080 per GPU, "
-                             "SH deg 3, 8-bit noise fake-quant (scales,quats,opacities,sh0) fused with exp/sigmoid, "
-                             "packed=False, L1 loss, fwd+bwd to raw params"
+                             "SH deg 3, 8-bit noise fake-quant (scales,quats,opacities,sh0) + exp/sigmoid "
+                             + ("applied inside the projection / colour kernels' attribute loads, " if on_load else
+                                "fused into one launch each way, ")
+                             + "packed=False, L1 loss, fwd+bwd to raw params"
                              + (", colors=torch.cat([sh0, shN], 1)" if args.cat_colors else ", colors=(sh0, shN) pair")
                              + (", factorized entropy model on" if args.entropy else "")),
                 "n_isects": n_isects, "l2": "inputs larger than L2 (236 MB of splat attributes + 25 MB image per step)",
@@ -538,6 +542,9 @@ def main():
                     help="m2: pass torch.cat([sh0, shN], 1) (the reference trainer's call) instead of the (sh0, shN) pair")
     ap.add_argument("--torch-loss", dest="torch_loss", action="store_true",
                     help="m2: L1 loss as the torch chain (rc - target).abs().mean() instead of the fused loss kernel")
+    ap.add_argument("--no-quant-on-load", dest="no_quant_on_load", action="store_true",
+                    help="m2: fake-quantise in separate kernels (one launch each way) instead of inside the projection / colour "
+                         "kernels' attribute loads")
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--no-extra-legs", dest="no_extra_legs", action="store_true",
                     help="skip the api_literal / entropy_on / ref_cuda context legs (profiling runs)")

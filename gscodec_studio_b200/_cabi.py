@@ -37,6 +37,9 @@ SIGNATURES = {
                                       _P, _P],
     "gsb200_projection_packed_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _U, _U, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                      _P, _P, _P],
+    "gsb200_projection_quant_fwd": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_projection_quant_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                    _P, _P, _P, _P, _P],
     "gsb200_compact_count": [_U, _U, _P, _P, _P, _P],
     "gsb200_compact_fill": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_scatter_rows": [_U, _U, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -46,6 +49,8 @@ SIGNATURES = {
     "gsb200_sh_view_bwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_view_split_fwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_view_split_bwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_sh_view_split_quant_fwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
+    "gsb200_sh_view_split_quant_bwd": [_U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_sh_view_fwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _P, _P, _P, _P],
     "gsb200_sh_view_bwd_sharded": [_U, _U, _U, _U, _P, _P, _P, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_shard_reduce_rows": [_U, _U, _U, _U, _P, _P, _P, _P],
@@ -117,6 +122,12 @@ class FqTensor(ctypes.Structure):
     _fields_ = [("n", c_int64), ("x", c_void_p), ("y", c_void_p), ("noise", c_void_p), ("v_y", c_void_p), ("v_x", c_void_p),
                 ("seed", c_uint64), ("offset", c_uint64), ("lo", c_float), ("hi", c_float), ("bitwidth", c_int), ("mode", c_int),
                 ("act", c_int)]
+
+
+class QuantLoadDesc(ctypes.Structure):
+    """struct gsb200_quant_load (include/gsb200.h): one attribute fake-quantised where a kernel loads it."""
+    _fields_ = [("noise", c_void_p), ("seed", c_uint64), ("offset", c_uint64), ("lo", c_float), ("hi", c_float),
+                ("bitwidth", ctypes.c_int32), ("act", ctypes.c_int32)]
 
 
 FQ_MAX_TENSORS = 8  # GSB200_FQ_MAX_TENSORS

@@ -6,6 +6,10 @@ Additive keyword arguments (ignored by reference callers):
               default: drawn in-kernel with Philox from torch's CUDA generator state (seed, offset)
   activation  None | "exp" | "sigmoid": fuse the activation the trainer applies next
               (examples/simple_trainer.py:758-776) into the same pass.
+
+`QuantOnLoad` (additive) is the tagged, lazy form of a noise-mode result: `rasterization()` recognises it and applies the
+quantisation inside the projection / colour kernels, where the raw parameter is loaded; every other consumer sees the
+materialised tensor (same values: the uniforms come from the same Philox counters or the same injected noise).
 """
 from __future__ import annotations
 
@@ -40,7 +44,8 @@ def _philox_args(device, n: int) -> tuple:
 
 class _FakeQuantize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x: Tensor, lo: float, hi: float, bitwidth: int, mode: int, act: int, noise: Optional[Tensor]):
+    def forward(ctx, x: Tensor, lo: float, hi: float, bitwidth: int, mode: int, act: int, noise: Optional[Tensor],
+                philox: Optional[tuple] = None):
         if not x.is_cuda:
             raise RuntimeError("gscodec_studio_b200: fake_quantize needs a CUDA tensor (no CPU implementation)")
         if x.dtype != torch.float32:
@@ -55,7 +60,7 @@ class _FakeQuantize(torch.autograd.Function):
         y = torch.empty_like(xin)
         seed, offset = (0, 0)
         if mode == 0 and noise is None:
-            seed, offset = _philox_args(x.device, x.numel())
+            seed, offset = philox if philox is not None else _philox_args(x.device, x.numel())
         if noise is not None:
             noise = aligned(noise.to(torch.float32))
             assert noise.numel() == x.numel(), "noise must have as many elements as the input"
@@ -73,13 +78,13 @@ class _FakeQuantize(torch.autograd.Function):
         x, y = ctx.saved_tensors
         lo, hi, mode, act = ctx.cfg
         if mode == 1 and act == 0:
-            return v_y, None, None, None, None, None, None  # pure straight-through (ops.py:73-75)
+            return v_y, None, None, None, None, None, None, None  # pure straight-through (ops.py:73-75)
         v_y = aligned(v_y.contiguous())
         v_x = torch.empty_like(x)
         with device_guard(x.device):
             call("gsb200_fake_quantize_bwd", x.numel(), ptr(x), ptr(y), lo, hi, mode, act, ptr(v_y), ptr(v_x),
                  stream_ptr(x.device))
-        return v_x.view_as(v_y), None, None, None, None, None, None
+        return v_x.view_as(v_y), None, None, None, None, None, None, None
 
 
 class _FakeQuantizeMulti(torch.autograd.Function):
@@ -181,12 +186,154 @@ def fake_quantize_ste_multi(items) -> list:
     return out
 
 
+class QuantOnLoad:
+    """Noise-mode ``fake_quantize_ste(raw, lo, hi, bitwidth)["output_value"]`` that has not been computed yet.
+
+    The fusion hook of SURVEY.md section 8b: ``simulate_compression(..., fuse_into_render=True)`` returns these for the
+    attributes it only fake-quantises; ``torch.exp`` / ``torch.sigmoid`` of one is again lazy (the activation is recorded);
+    ``rasterization()`` hands raw parameter + descriptor to kernels that quantise on load (gsb200_projection_quant_*,
+    gsb200_sh_view_split_quant_*).  Anything else -- any other torch function, attribute, arithmetic, indexing -- works on
+    the materialised tensor, computed once by the stand-alone kernel with the SAME uniforms, so both views agree bit for bit.
+    """
+
+    __slots__ = ("raw", "lo", "hi", "bitwidth", "noise", "seed", "offset", "act", "_value", "_family")
+
+    def __init__(self, raw: Tensor, lower_bd: float, upper_bd: float, bitwidth: int = 8, noise: Optional[Tensor] = None,
+                 activation: Optional[str] = None, philox: Optional[tuple] = None):
+        if raw.dtype != torch.float32:
+            raise RuntimeError(f"gscodec_studio_b200: expected float32 tensor, got {raw.dtype}")
+        self.raw = raw  # (a CPU tensor is refused where a kernel would touch it: there is no CPU implementation)
+        self.lo, self.hi, self.bitwidth = float(lower_bd), float(upper_bd), int(bitwidth)
+        self.act = None if activation in (None, "none") else activation
+        if self.act not in (None, "exp", "sigmoid"):
+            raise ValueError(f"unknown activation {activation!r}")
+        self.noise, self.seed, self.offset = None, 0, 0
+        if noise is not None:
+            assert noise.numel() == raw.numel(), "noise must have as many elements as the input"
+            self.noise = aligned(noise.to(torch.float32))
+        else:
+            self.seed, self.offset = philox if philox is not None else _philox_args(raw.device, raw.numel())
+        self._value = None
+        self._family = {}  # activation -> lazy sibling (shares the draw)
+
+    # ---- what rasterization() needs
+    @property
+    def q_step(self) -> float:
+        return (self.hi - self.lo) / (2 ** self.bitwidth - 1)
+
+    def descriptor(self):
+        """ctypes struct gsb200_quant_load for one kernel call (the caller keeps `self` alive for the noise pointer)."""
+        from .._cabi import QuantLoadDesc
+
+        d = QuantLoadDesc()
+        d.noise = self.noise.data_ptr() if self.noise is not None else None
+        d.seed, d.offset, d.lo, d.hi, d.bitwidth, d.act = self.seed, self.offset, self.lo, self.hi, self.bitwidth, _ACT[self.act]
+        return d
+
+    def raw_tensor(self) -> Tensor:
+        """The raw parameter as the kernels read it (contiguous, 16-byte aligned; autograd-connected to `raw`)."""
+        return aligned(self.raw)
+
+    def materialize(self) -> Tensor:
+        if self._value is None:
+            philox = None if self.noise is not None else (self.seed, self.offset)
+            self._value = _FakeQuantize.apply(self.raw, self.lo, self.hi, self.bitwidth, 0, _ACT[self.act], self.noise, philox)
+        return self._value
+
+    def _activated(self, act: str):
+        if self.act is not None:  # an activation of an activation: no longer an attribute load
+            return getattr(torch, act)(self.materialize())
+        sib = self._family.get(act)
+        if sib is None:
+            sib = QuantOnLoad.__new__(QuantOnLoad)
+            sib.raw, sib.lo, sib.hi, sib.bitwidth = self.raw, self.lo, self.hi, self.bitwidth
+            sib.noise, sib.seed, sib.offset, sib.act, sib._value, sib._family = self.noise, self.seed, self.offset, act, None, {}
+            self._family[act] = sib
+        return sib
+
+    def exp(self):
+        return self._activated("exp")
+
+    def sigmoid(self):
+        return self._activated("sigmoid")
+
+    # ---- tensor-likeness without computing anything
+    shape = property(lambda self: self.raw.shape)
+    device = property(lambda self: self.raw.device)
+    dtype = property(lambda self: self.raw.dtype)
+    requires_grad = property(lambda self: self.raw.requires_grad)
+    is_cuda = property(lambda self: self.raw.is_cuda)
+    ndim = property(lambda self: self.raw.ndim)
+
+    def dim(self):
+        return self.raw.dim()
+
+    def size(self, *a):
+        return self.raw.size(*a)
+
+    def numel(self):
+        return self.raw.numel()
+
+    def __len__(self):
+        return len(self.raw)
+
+    # ---- everything else: the materialised tensor
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func in (torch.exp, torch.sigmoid) and len(args) == 1 and not kwargs and isinstance(args[0], cls):
+            return args[0]._activated(func.__name__)
+
+        def solid(v):
+            if isinstance(v, cls):
+                return v.materialize()
+            if isinstance(v, (list, tuple)):
+                return type(v)(solid(e) for e in v)
+            return v
+
+        return func(*solid(args), **{k: solid(v) for k, v in kwargs.items()})
+
+    def __getattr__(self, name):  # only reached for names not defined above
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __neg__(self):
+        return -self.materialize()
+
+    def __repr__(self):
+        return (f"QuantOnLoad(shape={tuple(self.raw.shape)}, bounds=({self.lo}, {self.hi}), bitwidth={self.bitwidth}, "
+                f"activation={self.act}, materialised={self._value is not None})")
+
+
+def _binary(name):
+    def op(self, other):
+        other = other.materialize() if isinstance(other, QuantOnLoad) else other
+        return getattr(self.materialize(), name)(other)
+
+    op.__name__ = name
+    return op
+
+
+for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__rtruediv__", "__pow__",
+           "__matmul__", "__lt__", "__le__", "__gt__", "__ge__"):
+    setattr(QuantOnLoad, _n, _binary(_n))
+
+
+def solid(value):
+    """The tensor behind `value` (a Tensor, or a QuantOnLoad that gets materialised); None stays None."""
+    return value.materialize() if isinstance(value, QuantOnLoad) else value
+
+
 class STE(torch.autograd.Function):
     """Round-mode straight-through estimator with the reference's signature (ops.py:57-75)."""
 
     @staticmethod
     def forward(ctx, input, bitdepth=8, min=-1, max=1):
-        return _FakeQuantize.apply(input, min, max, bitdepth, 1, 0, None)
+        return _FakeQuantize.apply(input, min, max, bitdepth, 1, 0, None, None)
 
     @staticmethod
     def backward(ctx, grad_output):  # pragma: no cover - apply() of the inner Function records the graph
@@ -199,7 +346,7 @@ def fake_quantize_ste(input: Tensor, lower_bd: float, upper_bd: float, bitwidth:
     q_step = (upper_bd - lower_bd) / (2**bitwidth - 1)
     if q_type not in _MODE:
         raise NotImplementedError(f"q_type {q_type!r} is not supported")
-    out = _FakeQuantize.apply(input, lower_bd, upper_bd, bitwidth, _MODE[q_type], _ACT[activation], noise)
+    out = _FakeQuantize.apply(input, lower_bd, upper_bd, bitwidth, _MODE[q_type], _ACT[activation], noise, None)
     return {"output_value": out, "q_step": q_step}
 
 
@@ -210,5 +357,5 @@ def fake_quantize(input: Tensor, lower_bd: float, upper_bd: float, bitwidth: int
     if q_type != "round":
         raise NotImplementedError
     with torch.no_grad():
-        fq = _FakeQuantize.apply(input.detach().clone(), lower_bd, upper_bd, bitwidth, 1, 0, None)
+        fq = _FakeQuantize.apply(input.detach().clone(), lower_bd, upper_bd, bitwidth, 1, 0, None, None)
     return {"output_value": (fq - input).detach() + input, "q_step": q_step}

@@ -15,6 +15,11 @@ kernel (``ops.fake_quantize_ste``, ``entropy_model``).  Observable behaviour kep
 Additive: ``fuse_activations=True`` makes scales / opacities come back already passed through
 exp / sigmoid under the keys "scales_act" / "opacities_act" (one pass instead of three); callers
 that do not ask for it see the reference's dictionary.
+Additive: ``fuse_into_render=True`` (SURVEY.md section 8b's fusion hook) hands back every attribute that is only
+fake-quantised in "noise" mode (no rate term this step) as a lazy ``ops.QuantOnLoad`` under the reference's key: no
+kernel runs here, ``torch.exp`` / ``torch.sigmoid`` of it stay lazy, and ``rasterization()`` applies quantisation and
+activation inside the projection / colour kernels where the raw parameter is loaded.  Any other consumer of the value
+gets the materialised tensor (identical values).
 """
 from __future__ import annotations
 
@@ -25,7 +30,7 @@ import torch
 from torch import Tensor
 
 from .entropy_model import Entropy_factorized_optimized_refactor, Entropy_gaussian
-from .ops import fake_quantize_ste, fake_quantize_ste_multi
+from .ops import QuantOnLoad, fake_quantize_ste, fake_quantize_ste_multi
 
 
 @dataclass(frozen=True)
@@ -174,7 +179,7 @@ class _SimulationBase:
                 esti_bits = self.entropy_models[name](flat, fq["q_step"])
         return value, esti_bits
 
-    def _simulate(self, splats: Dict[str, Tensor], step: int, q_type, noise, fuse_activations):
+    def _simulate(self, splats: Dict[str, Tensor], step: int, q_type, noise, fuse_activations, fuse_into_render=False):
         new_splats, esti_bits_dict = {}, {}
         choose_idx, pos = None, None
         if (self.entropy_model_enable and getattr(self, "entropy_model_type", "factorized_model") == "gaussian_model"
@@ -186,13 +191,23 @@ class _SimulationBase:
         plans = {name: self._plan_attr(name, splats[name], step, q_type, None if noise is None else noise.get(name),
                                        fuse_activations)
                  for name in splats.keys() if self.policy[name].bounds is not None and self.simulation_option[name]}
-        if len(plans) > 1:
-            fqs = dict(zip(plans, fake_quantize_ste_multi([pl[0] for pl in plans.values()])))
+        lazy = {}
+        if fuse_into_render and q_type in (None, "noise"):
+            # quantise on load: nothing is computed here for attributes without a rate term this step
+            for name, (item, want_entropy, _act) in plans.items():
+                if not want_entropy and splats[name].is_cuda and splats[name].dtype == torch.float32:
+                    lazy[name] = QuantOnLoad(splats[name], item["lower_bd"], item["upper_bd"], item["bitwidth"], item["noise"])
+        eager = {name: pl for name, pl in plans.items() if name not in lazy}
+        if len(eager) > 1:
+            fqs = dict(zip(eager, fake_quantize_ste_multi([pl[0] for pl in eager.values()])))
         else:
-            fqs = {name: fake_quantize_ste(**pl[0]) for name, pl in plans.items()}
+            fqs = {name: fake_quantize_ste(**pl[0]) for name, pl in eager.items()}
         for name in splats.keys():
             esti_bits_dict[name] = None
-            if name in plans:
+            if name in lazy:
+                act = _FUSED_ACT.get(name) if fuse_activations else None
+                new_splats[name + "_act" if act is not None else name] = lazy[name] if act is None else lazy[name]._activated(act)
+            elif name in plans:
                 _item, want_entropy, act = plans[name]
                 value, bits = self._finish_attr(name, fqs[name], want_entropy, choose_idx, pos)
                 new_splats[name + "_act" if act is not None else name] = value
@@ -227,9 +242,9 @@ class CompressionSimulation(_SimulationBase):
         self._setup_mask(ada_mask_opt, ada_mask_step, ada_mask_strategy, device, kwargs)
 
     def simulate_compression(self, splats: Dict[str, Tensor], step: int, noise: Optional[Dict[str, Tensor]] = None,
-                             fuse_activations: bool = False):
+                             fuse_activations: bool = False, fuse_into_render: bool = False):
         """-> (new_splats, esti_bits_dict).  `noise` (optional, per attribute) replaces the in-kernel draw."""
-        return self._simulate(splats, step, None, noise, fuse_activations)
+        return self._simulate(splats, step, None, noise, fuse_activations, fuse_into_render)
 
     def shN_gradient_threshold(self, param: torch.nn.Parameter, step: int) -> None:
         """Zero the gradients of all-zero shN rows whose gradient norm is small (simulation.py:326-349)."""
@@ -258,8 +273,8 @@ class STGCompressionSimulation(_SimulationBase):
         self._setup_mask(ada_mask_opt, ada_mask_step, "learnable", device, kwargs)
 
     def simulate_compression(self, splats: Dict[str, Tensor], step: int, noise: Optional[Dict[str, Tensor]] = None,
-                             fuse_activations: bool = False):
+                             fuse_activations: bool = False, fuse_into_render: bool = False):
         q_type = self.quantization_sim_type
         if q_type is None:
             raise NotImplementedError("quantization_sim_type must be 'round' or 'noise'")
-        return self._simulate(splats, step, q_type, noise, fuse_activations=False)
+        return self._simulate(splats, step, q_type, noise, fuse_activations=False, fuse_into_render=fuse_into_render)

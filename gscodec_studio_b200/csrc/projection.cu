@@ -16,6 +16,7 @@
 //   * v_viewmats is block-reduced in shared memory, one atomic set per block and camera.
 #include "common.cuh"
 #include "geom.cuh"
+#include "quant_load.cuh"
 #include "scan.cuh"
 
 namespace gsb200 {
@@ -36,6 +37,17 @@ struct ProjOwnerOut {
     float *opacities[GSB200_MAX_VIEWS];
 };
 
+// MODE 4 (quantise on load): MODE 0 whose quats / scales / opacities are the trainer's RAW parameters -- the noise-mode fake
+// quantisation of compression_simulation and the exp / sigmoid that follow it are applied where the values are read
+// (quant_load.cuh); the activated opacities [N] (a blend input) are written once per Gaussian.
+struct ProjQuant {
+    QuantLoad quats, scales, opac;
+    const float *opac_raw;    // [N] raw (logit) opacities, or NULL
+    float *opac_act;          // fwd out / bwd in: sigmoid(fake-quantised opacity) [N]
+    const float *v_opac_act;  // bwd in: gradient of opac_act [N]
+    float *v_opac_raw;        // bwd out [N]
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
@@ -45,13 +57,20 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                       int packed_rule, int32_t *__restrict__ radii, float *__restrict__ means2d,
                       float *__restrict__ depths, float *__restrict__ conics, float *__restrict__ comps,
                       int32_t *__restrict__ pk_counts, int64_t *__restrict__ pk_camera_ids, int64_t *__restrict__ pk_gaussian_ids,
-                      uint32_t ldN, const float *__restrict__ opacities, const __grid_constant__ ProjOwnerOut peer) {
+                      uint32_t ldN, const float *__restrict__ opacities, const __grid_constant__ ProjOwnerOut peer,
+                      const __grid_constant__ ProjQuant Q) {
     __shared__ float s_vm[kMaxSmemCams][12];
     __shared__ float s_k[kMaxSmemCams][4];
     __shared__ int s_wcnt[kThreads / 32];
     const uint32_t g = blockIdx.x * kThreads + threadIdx.x;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (g < N) { px = __ldg(means + (size_t)g * 3); py = __ldg(means + (size_t)g * 3 + 1); pz = __ldg(means + (size_t)g * 3 + 2); }
+    if (MODE == 4 && g < N && Q.opac_raw != nullptr) {
+        const float raw[1] = {__ldg(Q.opac_raw + g)};
+        float act[1];
+        quant_load<1>(Q.opac, (int64_t)g, raw, act);
+        Q.opac_act[g] = act[0];
+    }
     // the world-space covariance is built lazily, the first time a camera keeps this Gaussian after the
     // near/far test -- for most Gaussians of a large scene that never happens and quats/scales are never read
     Sym3 S = {0, 0, 0, 0, 0, 0};
@@ -65,7 +84,7 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
             s_k[i][0] = K[0]; s_k[i][1] = K[4]; s_k[i][2] = K[2]; s_k[i][3] = K[5];
         }
         __syncthreads();
-        if (MODE == 0 && g >= N) continue;  // (the packed passes meet block barriers inside the camera loop)
+        if ((MODE == 0 || MODE == 4) && g >= N) continue;  // (the packed passes meet block barriers inside the camera loop)
         if (MODE == 3 && g >= ldN) continue;  // owner mode: the padding rows [N, ldN) of the block publish radius 0
         for (uint32_t ci = 0; ci < nc; ++ci) {
             const float *R = s_vm[ci];
@@ -85,9 +104,15 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                         S.xx = c[0]; S.xy = c[1]; S.xz = c[2]; S.yy = c[3]; S.yz = c[4]; S.zz = c[5];
                     } else {
                         const float4 q = ldg4(quats + (size_t)g * 4);
-                        const Mat3 Rq = quat_to_rot(q.x, q.y, q.z, q.w, nullptr);
-                        S = covar_from_quat_scale(Rq, __ldg(scales + (size_t)g * 3), __ldg(scales + (size_t)g * 3 + 1),
-                                                  __ldg(scales + (size_t)g * 3 + 2));
+                        float qv[4] = {q.x, q.y, q.z, q.w};
+                        float sv[3] = {__ldg(scales + (size_t)g * 3), __ldg(scales + (size_t)g * 3 + 1), __ldg(scales + (size_t)g * 3 + 2)};
+                        if (MODE == 4) {
+                            const float qr[4] = {qv[0], qv[1], qv[2], qv[3]}, sr[3] = {sv[0], sv[1], sv[2]};
+                            quant_load<4>(Q.quats, (int64_t)g * 4, qr, qv);
+                            quant_load<3>(Q.scales, (int64_t)g * 3, sr, sv);
+                        }
+                        const Mat3 Rq = quat_to_rot(qv[0], qv[1], qv[2], qv[3], nullptr);
+                        S = covar_from_quat_scale(Rq, sv[0], sv[1], sv[2]);
                     }
                 }
                 const Mat3 Sc = covar_to_cam_full(R, S);
@@ -120,7 +145,7 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                     }
                 }
             }
-            if (MODE == 0) {
+            if (MODE == 0 || MODE == 4) {
                 radii[idx] = rad;
                 *reinterpret_cast<float2 *>(means2d + idx * 2) = make_float2(o_mx, o_my);
                 depths[idx] = o_d;
@@ -172,7 +197,8 @@ projection_fwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
 // PACKED: radii / conics / comps / v_* are [nnz, ...] rows in (camera, Gaussian) order and `pk_offsets` / `pk_gaussian_ids`
 // (the forward's per-(camera, block) row offsets and the rows' Gaussian indices) tell every block which of its threads
 // own a row for the current camera: same ownership as the dense form -- no atomics, no dense scatter of the gradients.
-template <bool VIEWGRAD, bool FISHEYE, bool PACKED>
+// QUANT: quats / scales (/ opacities) are the RAW parameters of a MODE 4 forward; the gradients are those of the raw parameters
+template <bool VIEWGRAD, bool FISHEYE, bool PACKED, bool QUANT = false>
 __global__ void __launch_bounds__(kThreads, FISHEYE ? 1 : 3)
 projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, const float *__restrict__ covars,
                       const float *__restrict__ quats, const float *__restrict__ scales,
@@ -182,7 +208,8 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                       const float *__restrict__ v_depths, const float *__restrict__ v_conics,
                       const float *__restrict__ v_comps, float *__restrict__ v_means, float *__restrict__ v_covars,
                       float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_viewmats,
-                      const int32_t *__restrict__ pk_offsets, const int64_t *__restrict__ pk_gaussian_ids, uint32_t ldN) {
+                      const int32_t *__restrict__ pk_offsets, const int64_t *__restrict__ pk_gaussian_ids, uint32_t ldN,
+                      const __grid_constant__ ProjQuant Q) {
     __shared__ float s_vm[kMaxSmemCams][12];
     __shared__ float s_k[kMaxSmemCams][4];
     __shared__ float s_red[kThreads / 32][12];
@@ -241,6 +268,14 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
                     } else {
                         q = ldg4(quats + (size_t)g * 4);
                         sx = __ldg(scales + (size_t)g * 3); sy = __ldg(scales + (size_t)g * 3 + 1); sz = __ldg(scales + (size_t)g * 3 + 2);
+                        if (QUANT) {  // the values the forward saw (same uniforms: counter-based RNG)
+                            const float qr[4] = {q.x, q.y, q.z, q.w}, sr[3] = {sx, sy, sz};
+                            float qv[4], sv[3];
+                            quant_load<4>(Q.quats, (int64_t)g * 4, qr, qv);
+                            quant_load<3>(Q.scales, (int64_t)g * 3, sr, sv);
+                            q = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                            sx = sv[0]; sy = sv[1]; sz = sv[2];
+                        }
                         Rq = quat_to_rot(q.x, q.y, q.z, q.w, &inv_norm);
                         S = covar_from_quat_scale(Rq, sx, sy, sz);
                     }
@@ -390,6 +425,9 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
         }
     }
     if (g >= N) return;
+    if (QUANT && Q.v_opac_raw != nullptr)  // sigmoid'(.) and the clamp gate of the opacity (the blend's gradient arrives summed over cameras)
+        Q.v_opac_raw[g] = Q.opac.on ? quant_grad(Q.opac, __ldg(Q.v_opac_act + g), __ldg(Q.opac_raw + g), __ldg(Q.opac_act + g))
+                                    : __ldg(Q.v_opac_act + g);
     if (!have_S) {  // invisible everywhere: all gradients are zero
         v_means[(size_t)g * 3] = 0.f; v_means[(size_t)g * 3 + 1] = 0.f; v_means[(size_t)g * 3 + 2] = 0.f;
         if (covars != nullptr) {
@@ -431,8 +469,21 @@ projection_bwd_kernel(uint32_t C, uint32_t N, const float *__restrict__ means, c
         float vz = 2.f * (x * (vRq[2][0] + vRq[0][2]) + y * (vRq[2][1] + vRq[1][2]) - 2.f * z * (vRq[0][0] + vRq[1][1]) +
                           w * (vRq[1][0] - vRq[0][1]));
         float dotp = vw * w + vx * x + vy * y + vz * z;
-        stg4(v_quats + (size_t)g * 4, make_float4((vw - dotp * w) * inv_norm, (vx - dotp * x) * inv_norm,
-                                                   (vy - dotp * y) * inv_norm, (vz - dotp * z) * inv_norm));
+        float4 vq = make_float4((vw - dotp * w) * inv_norm, (vx - dotp * x) * inv_norm, (vy - dotp * y) * inv_norm,
+                                (vz - dotp * z) * inv_norm);
+        if (QUANT) {  // back to the raw parameters: clamp gates, exp'(.) = the activated scale itself
+            if (Q.quats.on) {
+                const float4 qr = ldg4(quats + (size_t)g * 4);
+                vq.x = quant_grad(Q.quats, vq.x, qr.x, q.x); vq.y = quant_grad(Q.quats, vq.y, qr.y, q.y);
+                vq.z = quant_grad(Q.quats, vq.z, qr.z, q.z); vq.w = quant_grad(Q.quats, vq.w, qr.w, q.w);
+            }
+            if (Q.scales.on) {
+                vsx = quant_grad(Q.scales, vsx, __ldg(scales + (size_t)g * 3), sx);
+                vsy = quant_grad(Q.scales, vsy, __ldg(scales + (size_t)g * 3 + 1), sy);
+                vsz = quant_grad(Q.scales, vsz, __ldg(scales + (size_t)g * 3 + 2), sz);
+            }
+        }
+        stg4(v_quats + (size_t)g * 4, vq);
         v_scales[(size_t)g * 3] = vsx; v_scales[(size_t)g * 3 + 1] = vsy; v_scales[(size_t)g * 3 + 2] = vsz;
     }
 }
@@ -537,8 +588,78 @@ extern "C" int gsb200_projection_fwd(uint32_t C, uint32_t N, const float *means,
     projection_fwd_kernel<0><<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip,
         camera_model, packed_radius_rule, radii, means2d, depths, conics, compensations, nullptr, nullptr, nullptr, N, nullptr,
-        ProjOwnerOut{});
+        ProjOwnerOut{}, ProjQuant{});
     return check_launch("projection_fwd");
+}
+
+// ---- quantise on load: the dense projection on the trainer's RAW parameters (gsplat/compression_simulation fused into the
+// attribute load).  q_* == NULL: that attribute is read as it is.  opacities_raw / opacities_act may both be NULL.
+static int make_proj_quant(const char *who, const gsb200_quant_load *q_quats, const gsb200_quant_load *q_scales,
+                           const gsb200_quant_load *q_opac, ProjQuant &Q) {
+    Q = ProjQuant{};
+    if (int e = make_quant_load(who, q_quats, Q.quats)) return e;
+    if (int e = make_quant_load(who, q_scales, Q.scales)) return e;
+    if (int e = make_quant_load(who, q_opac, Q.opac)) return e;
+    if (Q.quats.on && Q.quats.act != 0) return failf(2, "%s: quats take no activation", who);
+    return 0;
+}
+
+extern "C" int gsb200_projection_quant_fwd(uint32_t C, uint32_t N, const float *means, const float *quats, const float *scales,
+                                           const float *opacities_raw, const gsb200_quant_load *q_quats,
+                                           const gsb200_quant_load *q_scales, const gsb200_quant_load *q_opacities,
+                                           const float *viewmats, const float *Ks, uint32_t W, uint32_t H, float eps2d,
+                                           float near_plane, float far_plane, float radius_clip, int camera_model, int32_t *radii,
+                                           float *means2d, float *depths, float *conics, float *compensations,
+                                           float *opacities_act, gsb200_stream_t stream) {
+    const char *who = "gsb200_projection_quant_fwd";
+    if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
+        return failf(2, "%s: camera_model must be pinhole, ortho or fisheye", who);
+    ProjQuant Q;
+    if (int e = make_proj_quant(who, q_quats, q_scales, q_opacities, Q)) return e;
+    if (C == 0 || N == 0) return 0;
+    if (quats == nullptr || scales == nullptr) return failf(2, "%s: quats and scales are required", who);
+    if ((opacities_raw == nullptr) != (opacities_act == nullptr)) return failf(2, "%s: opacities_raw and opacities_act go together", who);
+    Q.opac_raw = opacities_raw;
+    Q.opac_act = opacities_act;
+    projection_fwd_kernel<4><<<cdiv(N, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+        C, N, means, nullptr, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip,
+        camera_model, 0, radii, means2d, depths, conics, compensations, nullptr, nullptr, nullptr, N, nullptr, ProjOwnerOut{}, Q);
+    return check_launch("projection_quant_fwd");
+}
+
+extern "C" int gsb200_projection_quant_bwd(uint32_t C, uint32_t N, const float *means, const float *quats, const float *scales,
+                                           const float *opacities_raw, const gsb200_quant_load *q_quats,
+                                           const gsb200_quant_load *q_scales, const gsb200_quant_load *q_opacities,
+                                           const float *viewmats, const float *Ks, uint32_t W, uint32_t H, float eps2d,
+                                           int camera_model, const int32_t *radii, const float *conics, const float *compensations,
+                                           const float *v_means2d, const float *v_depths, const float *v_conics,
+                                           const float *v_compensations, const float *opacities_act, const float *v_opacities_act,
+                                           float *v_means, float *v_quats, float *v_scales, float *v_opacities_raw,
+                                           gsb200_stream_t stream) {
+    const char *who = "gsb200_projection_quant_bwd";
+    if (camera_model < GSB200_CAMERA_PINHOLE || camera_model > GSB200_CAMERA_FISHEYE)
+        return failf(2, "%s: camera_model must be pinhole, ortho or fisheye", who);
+    ProjQuant Q;
+    if (int e = make_proj_quant(who, q_quats, q_scales, q_opacities, Q)) return e;
+    if (C == 0 || N == 0) return 0;
+    if (!means || !quats || !scales || !radii || !conics || !v_means2d || !v_conics || !v_means || !v_quats || !v_scales)
+        return failf(2, "%s: null pointer", who);
+    if (v_opacities_raw != nullptr && (v_opacities_act == nullptr || (Q.opac.on && (opacities_raw == nullptr || opacities_act == nullptr))))
+        return failf(2, "%s: the opacity gradient needs opacities_raw, opacities_act and v_opacities_act", who);
+    Q.opac_raw = opacities_raw;
+    Q.opac_act = const_cast<float *>(opacities_act);
+    Q.v_opac_act = v_opacities_act;
+    Q.v_opac_raw = v_opacities_raw;
+    const dim3 grid(cdiv(N, kThreads));
+    cudaStream_t s = (cudaStream_t)stream;
+#define GSB_LAUNCH_PROJ_QBWD(FE)                                                                                       \
+    projection_bwd_kernel<false, FE, false, true><<<grid, kThreads, 0, s>>>(                                            \
+        C, N, means, nullptr, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,      \
+        compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, nullptr, v_quats, v_scales, nullptr,    \
+        nullptr, nullptr, N, Q)
+    if (camera_model == GSB200_CAMERA_FISHEYE) GSB_LAUNCH_PROJ_QBWD(true); else GSB_LAUNCH_PROJ_QBWD(false);
+#undef GSB_LAUNCH_PROJ_QBWD
+    return check_launch("projection_quant_bwd");
 }
 
 // ---- packed (COO) projection: two passes, nothing of size C * N ------------------------------------------------------------
@@ -556,7 +677,7 @@ extern "C" int gsb200_projection_packed_count(uint32_t C, uint32_t N, const floa
     const uint32_t nb = cdiv(N, kThreads), n = C * nb;
     projection_fwd_kernel<1><<<nb, kThreads, 0, s>>>(C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d,
                                                      near_plane, far_plane, radius_clip, camera_model, 1, nullptr, nullptr, nullptr,
-                                                     nullptr, nullptr, block_offsets, nullptr, nullptr, N, nullptr, ProjOwnerOut{});
+                                                     nullptr, nullptr, block_offsets, nullptr, nullptr, N, nullptr, ProjOwnerOut{}, ProjQuant{});
     if (int e = check_launch("projection_packed_count")) return e;
     // exclusive scan over (camera, block): block_offsets[0..n) in place, total -> block_offsets[n]; scratch behind it
     int32_t *scratch = block_offsets + n + 1;
@@ -595,7 +716,7 @@ extern "C" int gsb200_projection_packed_fill(uint32_t C, uint32_t N, const float
     projection_fwd_kernel<2><<<nb, kThreads, 0, s>>>(C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d,
                                                      near_plane, far_plane, radius_clip, camera_model, 1, radii, means2d, depths,
                                                      conics, compensations, const_cast<int32_t *>(block_offsets), camera_ids,
-                                                     gaussian_ids, N, nullptr, ProjOwnerOut{});
+                                                     gaussian_ids, N, nullptr, ProjOwnerOut{}, ProjQuant{});
     if (int e = check_launch("projection_packed_fill")) return e;
     packed_indptr_kernel<<<cdiv(C + 1, kThreads), kThreads, 0, s>>>(C, nb, block_offsets, indptr);
     return check_launch("packed_indptr");
@@ -617,7 +738,7 @@ extern "C" int gsb200_projection_bwd(uint32_t C, uint32_t N, const float *means,
     projection_bwd_kernel<VG, FE, false><<<grid, kThreads, 0, s>>>(                                                   \
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii, conics,     \
         compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats, \
-        nullptr, nullptr, N)
+        nullptr, nullptr, N, ProjQuant{})
     const bool fe = camera_model == GSB200_CAMERA_FISHEYE;
     if (v_viewmats != nullptr) { if (fe) GSB_LAUNCH_PROJ_BWD(true, true); else GSB_LAUNCH_PROJ_BWD(true, false); }
     else { if (fe) GSB_LAUNCH_PROJ_BWD(false, true); else GSB_LAUNCH_PROJ_BWD(false, false); }
@@ -644,7 +765,7 @@ extern "C" int gsb200_projection_packed_bwd(uint32_t C, uint32_t N, const float 
     projection_bwd_kernel<VG, FE, true><<<grid, kThreads, 0, s>>>(                                                    \
         C, N, means, covars, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, nullptr, conics,   \
         compensations, v_means2d, v_depths, v_conics, v_compensations, v_means, v_covars, v_quats, v_scales, v_viewmats, \
-        block_offsets, gaussian_ids, N)
+        block_offsets, gaussian_ids, N, ProjQuant{})
     const bool fe = camera_model == GSB200_CAMERA_FISHEYE;
     if (v_viewmats != nullptr) { if (fe) GSB_LAUNCH_PROJ_PBWD(true, true); else GSB_LAUNCH_PROJ_PBWD(true, false); }
     else { if (fe) GSB_LAUNCH_PROJ_PBWD(false, true); else GSB_LAUNCH_PROJ_PBWD(false, false); }
@@ -731,7 +852,7 @@ extern "C" int gsb200_projection_owner_fwd(uint32_t V, uint32_t n_local, uint32_
     }
     projection_fwd_kernel<3><<<cdiv(n_block, kThreads), kThreads, 0, (cudaStream_t)stream>>>(
         V, n_local, means, nullptr, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, near_plane, far_plane, radius_clip,
-        camera_model, 0, radii_local, nullptr, nullptr, conics_local, nullptr, nullptr, nullptr, nullptr, n_block, opacities, out);
+        camera_model, 0, radii_local, nullptr, nullptr, conics_local, nullptr, nullptr, nullptr, nullptr, n_block, opacities, out, ProjQuant{});
     return check_launch("projection_owner_fwd");
 }
 
@@ -754,7 +875,7 @@ extern "C" int gsb200_projection_owner_bwd(uint32_t V, uint32_t n_local, uint32_
     projection_bwd_kernel<false, FE, false><<<grid, kThreads, 0, s>>>(                                                          \
         V, n_local, means, nullptr, quats, scales, viewmats, Ks, (float)W, (float)H, eps2d, camera_model, radii_local,         \
         conics_local, nullptr, v_means2d, v_depths, v_conics, nullptr, v_means, nullptr, v_quats, v_scales, nullptr, nullptr,   \
-        nullptr, n_block)
+        nullptr, n_block, ProjQuant{})
     if (camera_model == GSB200_CAMERA_FISHEYE) GSB_LAUNCH_OWNER_BWD(true); else GSB_LAUNCH_OWNER_BWD(false);
 #undef GSB_LAUNCH_OWNER_BWD
     return check_launch("projection_owner_bwd");

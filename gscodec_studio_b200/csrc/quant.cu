@@ -13,24 +13,9 @@
 // element (n, c) is evaluated with parameter set p = (32*c + n / (Npad/32)) mod ch for BOTH the
 // lower and the upper logit; blocks are laid out so p is block-uniform.
 #include "common.cuh"
+#include "quant_load.cuh"  // Philox4x32-10 and u01_centered, shared with the quantise-on-load kernels
 
 namespace gsb200 {
-
-// ---------------------------------------------------------------- Philox4x32-10 (counter RNG)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += W0; key.y += W1;
-    }
-    return ctr;
-}
-__device__ __forceinline__ float u01_centered(uint32_t r) {  // uniform in (-0.5, 0.5)
-    return ((float)(r >> 8) + 0.5f) * (1.f / 16777216.f) - 0.5f;
-}
 
 // the activations the trainer applies next (examples/simple_trainer.py:758-776), with torch.exp / torch.sigmoid's exact
 // arithmetic -- libdevice expf and an IEEE division; this file is built without --use_fast_math (see _build.py)

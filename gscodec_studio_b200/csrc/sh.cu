@@ -10,6 +10,7 @@
 // read, and the backward writes each v_coeffs row exactly once (zeros included) so no separate
 // memset pass over the [n,K,3] gradient is needed.
 #include "common.cuh"
+#include "quant_load.cuh"
 
 namespace gsb200 {
 
@@ -749,7 +750,7 @@ struct PeerViews {
 template <int DEG, typename VIEWS>
 __global__ void __launch_bounds__(kSplitThreads)
 sh_view_split_fwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__restrict__ means, const float *__restrict__ sh0,
-                         const float *__restrict__ shN, const __grid_constant__ VIEWS views) {
+                         const float *__restrict__ shN, const __grid_constant__ VIEWS views, const __grid_constant__ QuantLoad q0) {
     constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
     const uint32_t g = blockIdx.x * kSplitThreads + threadIdx.x;
     if (g >= N) return;
@@ -759,6 +760,12 @@ sh_view_split_fwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
     float mx = 0.f, my = 0.f, mz = 0.f;
     if (any) {
         cf[0] = __ldg(sh0 + (size_t)g * 3); cf[1] = __ldg(sh0 + (size_t)g * 3 + 1); cf[2] = __ldg(sh0 + (size_t)g * 3 + 2);
+        if (q0.on) {  // sh0 is the RAW parameter: fake-quantise it here (quant_load.cuh)
+            const float raw[3] = {cf[0], cf[1], cf[2]};
+            float qv[3];
+            quant_load<3>(q0, (int64_t)g * 3, raw, qv);
+            cf[0] = qv[0]; cf[1] = qv[1]; cf[2] = qv[2];
+        }
         if (DEG > 0) {
             const float *row = shN + (size_t)g * RF;
 #pragma unroll
@@ -792,7 +799,8 @@ template <int DEG, typename VIEWS>
 __global__ void __launch_bounds__(kSplitThreads)
 sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__restrict__ means, const float *__restrict__ sh0,
                          const float *__restrict__ shN, const __grid_constant__ VIEWS views, float *__restrict__ v_sh0,
-                         float *__restrict__ v_shN, float *__restrict__ v_means, float *__restrict__ v_campos) {
+                         float *__restrict__ v_shN, float *__restrict__ v_means, float *__restrict__ v_campos,
+                         const __grid_constant__ QuantLoad q0) {
     extern __shared__ float s_slab[];  // [kSplitThreads][RF | 1]: the block's v_shN rows
     __shared__ float s_red[kSplitThreads / 32][3];
     constexpr uint32_t nb = (DEG + 1) * (DEG + 1);
@@ -810,6 +818,12 @@ sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
     float mx = 0.f, my = 0.f, mz = 0.f;
     if (any) {
         cf[0] = __ldg(sh0 + (size_t)g * 3); cf[1] = __ldg(sh0 + (size_t)g * 3 + 1); cf[2] = __ldg(sh0 + (size_t)g * 3 + 2);
+        if (q0.on) {  // sh0 is the RAW parameter: fake-quantise it here (quant_load.cuh)
+            const float raw[3] = {cf[0], cf[1], cf[2]};
+            float qv[3];
+            quant_load<3>(q0, (int64_t)g * 3, raw, qv);
+            cf[0] = qv[0]; cf[1] = qv[1]; cf[2] = qv[2];
+        }
         if (DEG > 0) {
             const float *row = shN + (size_t)g * RF;
 #pragma unroll
@@ -859,6 +873,10 @@ sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
         }
     }
     if (g < N) {
+        if (q0.on && any) {  // gradient to the RAW sh0: the clamp gate of the noise-mode fake quantisation (ops.py:44-47)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) vc[k] = quant_grad(q0, vc[k], __ldg(sh0 + (size_t)g * 3 + k), 0.f);
+        }
         v_sh0[(size_t)g * 3] = vc[0]; v_sh0[(size_t)g * 3 + 1] = vc[1]; v_sh0[(size_t)g * 3 + 2] = vc[2];
         if (v_means != nullptr) {
             v_means[(size_t)g * 3] = vmx; v_means[(size_t)g * 3 + 1] = vmy; v_means[(size_t)g * 3 + 2] = vmz;
@@ -1319,25 +1337,26 @@ static int check_split_args(const char *who, uint32_t K, uint32_t degree, const 
 
 template <typename VIEWS>
 static void launch_split_fwd(cudaStream_t s, uint32_t degree, uint32_t C, uint32_t N, uint32_t K, const float *means, const float *sh0,
-                             const float *shN, const VIEWS &views) {
+                             const float *shN, const VIEWS &views, const QuantLoad &q0 = QuantLoad{nullptr, 0, 0, 0.f, 0.f, 0.f, 0, 0}) {
     const uint32_t grid = cdiv(N, kSplitThreads), RF = (K - 1) * 3;
     switch (degree) {
-        case 0: sh_view_split_fwd_kernel<0, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
-        case 1: sh_view_split_fwd_kernel<1, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
-        case 2: sh_view_split_fwd_kernel<2, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
-        case 3: sh_view_split_fwd_kernel<3, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
-        default: sh_view_split_fwd_kernel<4, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views); break;
+        case 0: sh_view_split_fwd_kernel<0, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views, q0); break;
+        case 1: sh_view_split_fwd_kernel<1, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views, q0); break;
+        case 2: sh_view_split_fwd_kernel<2, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views, q0); break;
+        case 3: sh_view_split_fwd_kernel<3, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views, q0); break;
+        default: sh_view_split_fwd_kernel<4, VIEWS><<<grid, kSplitThreads, 0, s>>>(C, N, RF, means, sh0, shN, views, q0); break;
     }
 }
 
 template <typename VIEWS>
 static void launch_split_bwd(cudaStream_t s, uint32_t degree, uint32_t C, uint32_t N, uint32_t K, const float *means, const float *sh0,
-                             const float *shN, const VIEWS &views, float *v_sh0, float *v_shN, float *v_means, float *v_campos) {
+                             const float *shN, const VIEWS &views, float *v_sh0, float *v_shN, float *v_means, float *v_campos,
+                             const QuantLoad &q0 = QuantLoad{nullptr, 0, 0, 0.f, 0.f, 0.f, 0, 0}) {
     const uint32_t grid = cdiv(N, kSplitThreads), RF = (K - 1) * 3;
     const size_t smem = sizeof(float) * kSplitThreads * (RF | 1u);
 #define GSB_SPLIT_BWD(D)                                                                                                      \
     sh_view_split_bwd_kernel<D, VIEWS><<<grid, kSplitThreads, smem, s>>>(C, N, RF, means, sh0, shN, views, v_sh0, v_shN, v_means, \
-                                                                         v_campos)
+                                                                         v_campos, q0)
     switch (degree) {
         case 0: GSB_SPLIT_BWD(0); break;
         case 1: GSB_SPLIT_BWD(1); break;
@@ -1371,6 +1390,41 @@ extern "C" int gsb200_sh_view_split_bwd(uint32_t C, uint32_t N, uint32_t K, uint
     const LocalViews views{campos, radii, nullptr, v_colors, N};
     launch_split_bwd(s, degree, C, N, K, means, sh0, shN, views, v_sh0, v_shN, v_means, v_campos);
     return check_launch("sh_view_split_bwd");
+}
+
+// ---- the same two calls with sh0 fake-quantised where it is loaded (noise mode; quant_load.cuh): `sh0` is the RAW
+// parameter, v_sh0 its gradient (clamp gate applied).  q_sh0 == NULL: identical to the calls above.
+extern "C" int gsb200_sh_view_split_quant_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                                              const float *campos, const float *sh0, const gsb200_quant_load *q_sh0, const float *shN,
+                                              const int32_t *radii, float *colors, gsb200_stream_t stream) {
+    const char *who = "gsb200_sh_view_split_quant_fwd";
+    if (int rc = check_split_args(who, K, degree, sh0, shN)) return rc;
+    QuantLoad q0;
+    if (int rc = make_quant_load(who, q_sh0, q0)) return rc;
+    if (q0.on && q0.act != 0) return failf(2, "%s: sh0 takes no activation", who);
+    if (C == 0 || N == 0) return 0;
+    const LocalViews views{campos, radii, colors, nullptr, N};
+    launch_split_fwd((cudaStream_t)stream, degree, C, N, K, means, sh0, shN, views, q0);
+    return check_launch("sh_view_split_quant_fwd");
+}
+
+extern "C" int gsb200_sh_view_split_quant_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                                              const float *campos, const float *sh0, const gsb200_quant_load *q_sh0, const float *shN,
+                                              const int32_t *radii, const float *v_colors, float *v_sh0, float *v_shN,
+                                              float *v_means, float *v_campos, gsb200_stream_t stream) {
+    const char *who = "gsb200_sh_view_split_quant_bwd";
+    if (int rc = check_split_args(who, K, degree, sh0, shN)) return rc;
+    QuantLoad q0;
+    if (int rc = make_quant_load(who, q_sh0, q0)) return rc;
+    if (q0.on && q0.act != 0) return failf(2, "%s: sh0 takes no activation", who);
+    if (C == 0 || N == 0) return 0;
+    if (v_sh0 == nullptr || (K > 1 && v_shN == nullptr)) return failf(2, "%s: null gradient pointer", who);
+    if ((reinterpret_cast<uintptr_t>(v_shN) & 15) != 0) return failf(2, "%s: v_shN must be 16-byte aligned", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (v_campos != nullptr) GSB_CUDA_OK(cudaMemsetAsync(v_campos, 0, sizeof(float) * 3 * C, s));
+    const LocalViews views{campos, radii, nullptr, v_colors, N};
+    launch_split_bwd(s, degree, C, N, K, means, sh0, shN, views, v_sh0, v_shN, v_means, v_campos, q0);
+    return check_launch("sh_view_split_quant_bwd");
 }
 
 static int make_peer_views(const char *who, uint32_t V, uint32_t n_local, uint32_t n_block, const float *campos, const int32_t *masks,

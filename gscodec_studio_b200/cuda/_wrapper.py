@@ -179,21 +179,43 @@ def view_colors_from_sh_split(sh_degree: int, means: Tensor, campos: Tensor, sh0
     assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1], shN.shape
     assert shN.shape[1] <= SH_SPLIT_MAX_REST, shN.shape
     assert radii.shape == (C, N), radii.shape
+    from ..compression_simulation.ops import QuantOnLoad
+
+    if isinstance(sh0, QuantOnLoad):
+        # additive: sh0 is still the RAW parameter; its fake quantisation happens where the kernel loads it
+        if sh0.act is not None:
+            sh0 = sh0.materialize()
+        else:
+            return _ShViewSplit.apply(sh_degree, means.contiguous(), campos.contiguous(), sh0.raw_tensor(), shN.contiguous(),
+                                      radii.contiguous(), sh0)
     return _ShViewSplit.apply(sh_degree, means.contiguous(), campos.contiguous(), sh0.contiguous(), shN.contiguous(),
-                              radii.contiguous())
+                              radii.contiguous(), None)
+
+
+def _desc_ptr(desc):
+    """void* of a ctypes gsb200_quant_load (NULL for None)."""
+    return ctypes.c_void_p(0) if desc is None else ctypes.cast(ctypes.pointer(desc), ctypes.c_void_p)
 
 
 class _ShViewSplit(torch.autograd.Function):
+    """`lazy` (a QuantOnLoad or None): sh0 is the raw parameter and is fake-quantised on load."""
+
     @staticmethod
-    def forward(ctx, sh_degree, means, campos, sh0, shN, radii):
+    def forward(ctx, sh_degree, means, campos, sh0, shN, radii, lazy):
         means, campos, sh0, shN = _f32(means), _f32(campos), _f32(sh0), _f32(shN)
         C, N, K = campos.shape[0], means.shape[0], 1 + shN.shape[1]
         colors = torch.empty((C, N, 3), dtype=torch.float32, device=means.device)
         with device_guard(means.device):
-            call("gsb200_sh_view_split_fwd", C, N, K, sh_degree, ptr(means), ptr(campos), ptr(sh0), ptr(shN), ptr(radii),
-                 ptr(colors), stream_ptr(means.device))
+            if lazy is None:
+                call("gsb200_sh_view_split_fwd", C, N, K, sh_degree, ptr(means), ptr(campos), ptr(sh0), ptr(shN), ptr(radii),
+                     ptr(colors), stream_ptr(means.device))
+            else:
+                desc = lazy.descriptor()
+                call("gsb200_sh_view_split_quant_fwd", C, N, K, sh_degree, ptr(means), ptr(campos), ptr(sh0), _desc_ptr(desc),
+                     ptr(shN), ptr(radii), ptr(colors), stream_ptr(means.device))
         ctx.save_for_backward(means, campos, sh0, shN, radii)
         ctx.sh_degree = sh_degree
+        ctx.lazy = lazy
         return colors
 
     @staticmethod
@@ -206,9 +228,15 @@ class _ShViewSplit(torch.autograd.Function):
         v_means = torch.empty_like(means) if ctx.needs_input_grad[1] else None
         v_campos = torch.empty_like(campos) if ctx.needs_input_grad[2] else None
         with device_guard(means.device):
-            call("gsb200_sh_view_split_bwd", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ptr(sh0), ptr(shN), ptr(radii),
-                 ptr(v_colors), ptr(v_sh0), ptr(v_shN), ptr(v_means), ptr(v_campos), stream_ptr(means.device))
-        return None, v_means, v_campos, v_sh0, v_shN, None
+            if ctx.lazy is None:
+                call("gsb200_sh_view_split_bwd", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ptr(sh0), ptr(shN), ptr(radii),
+                     ptr(v_colors), ptr(v_sh0), ptr(v_shN), ptr(v_means), ptr(v_campos), stream_ptr(means.device))
+            else:
+                desc = ctx.lazy.descriptor()
+                call("gsb200_sh_view_split_quant_bwd", C, N, K, ctx.sh_degree, ptr(means), ptr(campos), ptr(sh0),
+                     _desc_ptr(desc), ptr(shN), ptr(radii), ptr(v_colors), ptr(v_sh0), ptr(v_shN), ptr(v_means), ptr(v_campos),
+                     stream_ptr(means.device))
+        return None, v_means, v_campos, v_sh0, v_shN, None, None
 
 
 # --------------------------------------------------------------------------------------
@@ -477,6 +505,99 @@ class _FullyFusedProjection(torch.autograd.Function):
         if not ctx.needs_input_grad[3]:
             v_scales = None
         return (v_means, v_covars, v_quats, v_scales, v_viewmats, None, None, None, None, None, None, None, None, None)
+
+
+def fully_fused_projection_quant(means, quats, scales, opacities, viewmats, Ks, width, height, eps2d=0.3, near_plane=0.01,
+                                 far_plane=1e10, radius_clip=0.0, calc_compensations=False, camera_model="pinhole"):
+    """Additive: the dense `fully_fused_projection` on the trainer's RAW parameters.  `quats` / `scales` / `opacities`
+    are Tensors (read as they are) or QuantOnLoad objects (compression_simulation.ops: raw parameter + noise-mode fake
+    quantisation (+ exp / sigmoid), applied where the kernel loads the value -- no quantised copy is ever written).
+    Returns (radii, means2d, depths, conics, compensations, opacities) with opacities [N] ready for the blend.  Gradients
+    reach the raw parameters; camera gradients are not available in this form."""
+    from ..compression_simulation.ops import QuantOnLoad
+
+    C, N = viewmats.size(0), means.size(0)
+    assert means.size() == (N, 3), means.size()
+    assert viewmats.size() == (C, 4, 4), viewmats.size()
+    assert Ks.size() == (C, 3, 3), Ks.size()
+    assert quats.shape == (N, 4), quats.shape
+    assert scales.shape == (N, 3), scales.shape
+    assert opacities.shape == (N,), opacities.shape
+    if camera_model not in _CAMERA_MODELS:
+        raise ValueError(f"Unsupported camera model: {camera_model}")
+    lazies = []
+    raws = []
+    for v in (quats, scales, opacities):
+        if isinstance(v, QuantOnLoad):
+            lazies.append(v)
+            raws.append(v.raw_tensor())
+        else:
+            lazies.append(None)
+            raws.append(v.contiguous())
+    if lazies[0] is not None and lazies[0].act is not None:  # an activated quaternion is not an attribute load
+        raws[0], lazies[0] = lazies[0].materialize().contiguous(), None
+    opac_plain = lazies[2] is None
+    out = _FullyFusedProjectionQuant.apply(
+        means.contiguous(), raws[0], raws[1], None if opac_plain else raws[2], viewmats.contiguous(), Ks.contiguous(), width,
+        height, eps2d, near_plane, far_plane, radius_clip, calc_compensations, camera_model, lazies[0], lazies[1], lazies[2])
+    radii, means2d, depths, conics, comps, opac_act = out
+    return radii, means2d, depths, conics, comps, (raws[2] if opac_plain else opac_act)
+
+
+class _FullyFusedProjectionQuant(torch.autograd.Function):
+    """gsb200_projection_quant_fwd / _bwd: stage 1 with compression_simulation's fake quantisation fused into the
+    attribute load (reference op chain: ops.py:39-54 per attribute, then exp / sigmoid, then fully_fused_projection)."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, opac_raw, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+                calc_compensations, camera_model, lz_quats, lz_scales, lz_opac):
+        means, quats, scales, opac_raw, viewmats, Ks = map(_f32, (means, quats, scales, opac_raw, viewmats, Ks))
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        radii = torch.empty((C, N), dtype=torch.int32, device=dev)
+        means2d = torch.empty((C, N, 2), dtype=torch.float32, device=dev)
+        depths = torch.empty((C, N), dtype=torch.float32, device=dev)
+        conics = torch.empty((C, N, 3), dtype=torch.float32, device=dev)
+        comps = torch.empty((C, N), dtype=torch.float32, device=dev) if calc_compensations else None
+        opac_act = torch.empty((N,), dtype=torch.float32, device=dev) if opac_raw is not None else None
+        descs = [None if lz is None else lz.descriptor() for lz in (lz_quats, lz_scales, lz_opac)]
+        with device_guard(dev):
+            call("gsb200_projection_quant_fwd", C, N, ptr(means), ptr(quats), ptr(scales), ptr(opac_raw), _desc_ptr(descs[0]),
+                 _desc_ptr(descs[1]), _desc_ptr(descs[2]), ptr(viewmats), ptr(Ks), width, height, eps2d, near_plane, far_plane,
+                 radius_clip, _CAMERA_MODELS[camera_model], ptr(radii), ptr(means2d), ptr(depths), ptr(conics), ptr(comps),
+                 ptr(opac_act), stream_ptr(dev))
+        ctx.save_for_backward(means, quats, scales, opac_raw, viewmats, Ks, radii, conics, comps, opac_act)
+        ctx.dims = (width, height, eps2d, camera_model)
+        ctx.lazies = (lz_quats, lz_scales, lz_opac)
+        ctx.mark_non_differentiable(radii)
+        return radii, means2d, depths, conics, comps, opac_act
+
+    @staticmethod
+    def backward(ctx, v_radii, v_means2d, v_depths, v_conics, v_comps, v_opac_act):
+        means, quats, scales, opac_raw, viewmats, Ks, radii, conics, comps, opac_act = ctx.saved_tensors
+        width, height, eps2d, camera_model = ctx.dims
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+            raise RuntimeError("fully_fused_projection_quant: camera gradients are not available in the quantise-on-load form")
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        if comps is None:
+            v_comps = None
+        elif v_comps is None:
+            v_comps = torch.zeros_like(comps)
+        v_means, v_quats, v_scales = torch.empty_like(means), torch.empty_like(quats), torch.empty_like(scales)
+        want_opac = opac_raw is not None and ctx.needs_input_grad[3] and v_opac_act is not None
+        v_opac_raw = torch.empty_like(opac_raw) if want_opac else None
+        descs = [None if lz is None else lz.descriptor() for lz in ctx.lazies]
+        with device_guard(dev):
+            call("gsb200_projection_quant_bwd", C, N, ptr(means), ptr(quats), ptr(scales), ptr(opac_raw), _desc_ptr(descs[0]),
+                 _desc_ptr(descs[1]), _desc_ptr(descs[2]), ptr(viewmats), ptr(Ks), width, height, eps2d,
+                 _CAMERA_MODELS[camera_model], ptr(radii), ptr(conics), ptr(comps), ptr(_f32(v_means2d.contiguous())),
+                 ptr(_f32(v_depths.contiguous())), ptr(_f32(v_conics.contiguous())),
+                 ptr(None if v_comps is None else _f32(v_comps.contiguous())), ptr(opac_act),
+                 ptr(_f32(v_opac_act.contiguous()) if want_opac else None), ptr(v_means), ptr(v_quats), ptr(v_scales),
+                 ptr(v_opac_raw), stream_ptr(dev))
+        return (v_means if ctx.needs_input_grad[0] else None, v_quats if ctx.needs_input_grad[1] else None,
+                v_scales if ctx.needs_input_grad[2] else None, v_opac_raw) + (None,) * 13
 
 
 class _FullyFusedProjectionPacked(torch.autograd.Function):

@@ -19,10 +19,12 @@ import torch
 from torch import Tensor
 from typing_extensions import Literal
 
+from .compression_simulation.ops import QuantOnLoad, solid
 from .cuda._wrapper import (
     _isect_tiles_begin,
     _isect_tiles_with_offsets,
     fully_fused_projection,
+    fully_fused_projection_quant,
     rasterize_to_pixels,
     spherical_harmonics,
     SH_SPLIT_MAX_REST,
@@ -101,11 +103,24 @@ def rasterization(
     The dense single-process path then reads both arrays in place and writes their gradients directly (no
     [N,K,3] copy forward, no strided gradient copies backward); every other mode concatenates them first, so the
     result is the same as for the concatenated tensor.
+
+    Additive (quantise on load): `quats`, `scales`, `opacities` and `sh0` of the pair may be
+    ``compression_simulation.ops.QuantOnLoad`` objects -- what ``simulate_compression(..., fuse_into_render=True)``
+    returns, possibly passed through ``torch.exp`` / ``torch.sigmoid``.  The dense single-process path then reads the RAW
+    parameters and applies fake quantisation + activation inside the projection / colour kernels; every other mode
+    materialises them first (same values).
     """
     meta: Dict = {}
     N = means.shape[0]
     C = viewmats.shape[0]
     device = means.device
+    # quantise on load is served by the dense single-process kernels with fixed cameras; anything else sees tensors
+    quant_on_load = (not distributed and not packed and covars is None
+                     and not ((viewmats.requires_grad or Ks.requires_grad) and torch.is_grad_enabled()))
+    if not quant_on_load:
+        quats, scales, opacities = solid(quats), solid(scales), solid(opacities)
+    quant_on_load = quant_on_load and any(isinstance(v, QuantOnLoad) for v in (quats, scales, opacities))
+    means = solid(means)
     assert means.shape == (N, 3), means.shape
     if covars is None:
         assert quats.shape == (N, 4), quats.shape
@@ -124,6 +139,9 @@ def rasterization(
     if isinstance(colors, (tuple, list)):
         assert sh_degree is not None and len(colors) == 2, "colors=(sh0, shN) needs sh_degree"
         sh0, shN = colors
+        shN = solid(shN)
+        if isinstance(sh0, QuantOnLoad) and (distributed or packed or shN.shape[1] > SH_SPLIT_MAX_REST or sh0.act is not None):
+            sh0 = sh0.materialize()
         assert sh0.shape == (N, 1, 3), sh0.shape
         assert shN.dim() == 3 and shN.shape[0] == N and shN.shape[2] == 3, shN.shape
         assert (sh_degree + 1) ** 2 <= 1 + shN.shape[1], shN.shape
@@ -134,6 +152,7 @@ def rasterization(
         else:
             colors = torch.cat([sh0, shN], dim=1)
 
+    colors = solid(colors)
     if sh_pair is not None or sh_pair_dist is not None:
         pass
     elif sh_degree is None:
@@ -238,6 +257,11 @@ def rasterization(
             sh_degree, means_local, quats, scales, opacities, sh_pair_dist, viewmats, Ks, width, height, n_block, eps2d,
             near_plane, far_plane, radius_clip, _CAMERA_MODELS[camera_model])
         proj_results = (radii, means2d, depths, conics, None)
+    elif quant_on_load:
+        *proj_results, opacities = fully_fused_projection_quant(
+            means, quats, scales, opacities, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
+            far_plane=far_plane, radius_clip=radius_clip, calc_compensations=(rasterize_mode == "antialiased"),
+            camera_model=camera_model)
     else:
         proj_results = fully_fused_projection(
             means, covars, quats, scales, viewmats, Ks, width, height,

@@ -116,6 +116,42 @@ int gsb200_compact_fill(uint32_t C, uint32_t N, const int32_t *radii, const floa
                         const int32_t *block_offsets, int32_t *indptr, int64_t *camera_ids,
                         int64_t *gaussian_ids, int32_t *p_radii, float *p_means2d, float *p_depths,
                         float *p_conics, float *p_compensations, gsb200_stream_t stream);
+/* ---- quantise on load: compression_simulation fused into the attribute load --------------------------------------------------
+ * The reference fake-quantises every attribute with its own chain of torch ops and hands the quantised copies to
+ * rasterization() (compression_simulation/ops.py:39-54 called from simulation.py:242-316; then torch.exp / torch.sigmoid,
+ * examples/simple_trainer.py:758-776).  These entry points take the trainer's RAW parameters plus one descriptor per quantised
+ * attribute and apply clamp(x, lo, hi) + u * q_step (noise mode; u from Philox (seed, offset) -- one counter per 4 consecutive
+ * elements, exactly gsb200_fake_quantize_fwd's -- or from `noise`) and the activation where the value is loaded; the backward
+ * returns the gradients of the RAW parameters (clamp gate, activation derivative).  No quantised tensor exists in HBM.
+ * A NULL descriptor: that attribute is read as it is.  act: 0 none, 1 exp, 2 sigmoid. */
+typedef struct gsb200_quant_load {
+    const float *noise;  /* explicit U(-.5,.5) draw with the attribute's shape, or NULL */
+    uint64_t seed, offset;
+    float lo, hi;
+    int32_t bitwidth, act;
+} gsb200_quant_load;
+
+/* gsb200_projection_fwd (dense) on raw quats [N,4] / scales [N,3] (+ optionally raw opacities [N] -> opacities_act [N], the
+ * blend's opacity input; both NULL to skip). */
+int gsb200_projection_quant_fwd(uint32_t C, uint32_t N, const float *means, const float *quats, const float *scales,
+                                const float *opacities_raw, const gsb200_quant_load *q_quats,
+                                const gsb200_quant_load *q_scales, const gsb200_quant_load *q_opacities,
+                                const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+                                float eps2d, float near_plane, float far_plane, float radius_clip, int camera_model,
+                                int32_t *radii, float *means2d, float *depths, float *conics, float *compensations,
+                                float *opacities_act, gsb200_stream_t stream);
+/* gsb200_projection_bwd for the call above; v_opacities_act [N] is the gradient of opacities_act (summed over cameras),
+ * v_opacities_raw [N] may be NULL.  No camera gradients in this form. */
+int gsb200_projection_quant_bwd(uint32_t C, uint32_t N, const float *means, const float *quats, const float *scales,
+                                const float *opacities_raw, const gsb200_quant_load *q_quats,
+                                const gsb200_quant_load *q_scales, const gsb200_quant_load *q_opacities,
+                                const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+                                float eps2d, int camera_model, const int32_t *radii, const float *conics,
+                                const float *compensations, const float *v_means2d, const float *v_depths,
+                                const float *v_conics, const float *v_compensations, const float *opacities_act,
+                                const float *v_opacities_act, float *v_means, float *v_quats, float *v_scales,
+                                float *v_opacities_raw, gsb200_stream_t stream);
+
 /* gradient scatter back to the dense layout used by gsb200_projection_bwd:
  * dense v_means2d/v_depths/v_conics/v_compensations [C,N,*] are zero-filled then row r of the packed
  * gradients is written at (camera_ids[r], gaussian_ids[r]).
@@ -164,6 +200,15 @@ int gsb200_sh_view_split_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree
                              const float *campos, const float *sh0, const float *shN, const int32_t *radii,
                              const float *v_colors, float *v_sh0, float *v_shN, float *v_means,
                              float *v_campos, gsb200_stream_t stream);
+
+/* gsb200_sh_view_split_fwd / _bwd with the raw sh0 fake-quantised where it is loaded (q_sh0 NULL: identical to them) */
+int gsb200_sh_view_split_quant_fwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                                   const float *campos, const float *sh0, const gsb200_quant_load *q_sh0, const float *shN,
+                                   const int32_t *radii, float *colors, gsb200_stream_t stream);
+int gsb200_sh_view_split_quant_bwd(uint32_t C, uint32_t N, uint32_t K, uint32_t degree, const float *means,
+                                   const float *campos, const float *sh0, const gsb200_quant_load *q_sh0, const float *shN,
+                                   const int32_t *radii, const float *v_colors, float *v_sh0, float *v_shN, float *v_means,
+                                   float *v_campos, gsb200_stream_t stream);
 
 /* View-parallel multi-GPU form of the same stage.  The reference all-gathers / all-to-alls whole attribute
  * tensors between ranks around these ops (rendering.py:282-294, 397-478; distributed.py:90-215).  Here the SH

@@ -17,7 +17,10 @@
     OP(rasterize_to_indices_in_range)                               /* SURVEY.md section 8(f) rows below */  \
     OP(quat_scale_to_covar_preci_fwd) OP(quat_scale_to_covar_preci_bwd)                                      \
     OP(proj_fwd) OP(proj_bwd) OP(world_to_cam_fwd) OP(world_to_cam_bwd)                                      \
-    OP(compute_relocation)
+    OP(compute_relocation)                                                                                   \
+    OP(fully_fused_projection_fwd_2dgs) OP(fully_fused_projection_bwd_2dgs) /* 2D Gaussian (surfel) family */ \
+    OP(fully_fused_projection_packed_fwd_2dgs) OP(fully_fused_projection_packed_bwd_2dgs)                    \
+    OP(rasterize_to_pixels_fwd_2dgs) OP(rasterize_to_pixels_bwd_2dgs) OP(rasterize_to_indices_in_range_2dgs)
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, mod) {
     namespace ref = gsplat;
