@@ -17,7 +17,14 @@ from .cuda._wrapper import (  # noqa: F401
     spherical_harmonics,
     world_to_cam,
 )
+from .cuda._wrapper_2dgs import (  # noqa: F401
+    accumulate_2dgs,
+    fully_fused_projection_2dgs,
+    rasterize_to_indices_in_range_2dgs,
+    rasterize_to_pixels_2dgs,
+)
 from .rendering import rasterization  # noqa: F401
+from .rendering_2dgs import rasterization_2dgs, rasterization_2dgs_inria_wrapper  # noqa: F401
 from . import distributed  # noqa: F401
 from .version import __version__  # noqa: F401
 
@@ -33,5 +40,11 @@ __all__ = [
     "persp_proj",
     "world_to_cam",
     "rasterize_to_indices_in_range",
+    "rasterization_2dgs",
+    "rasterization_2dgs_inria_wrapper",
+    "fully_fused_projection_2dgs",
+    "rasterize_to_pixels_2dgs",
+    "rasterize_to_indices_in_range_2dgs",
+    "accumulate_2dgs",
     "distributed",
 ]

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libgsb200.so")
-SOURCES = ["abi.cu", "projection.cu", "sh.cu", "isect.cu", "isect_ordered.cu", "blend.cu", "blend_stream.cu", "quant.cu", "optim.cu", "loss.cu", "geom_ops.cu", "dynamic.cu", "indices.cu", "hashgrid.cu"]
+SOURCES = ["abi.cu", "projection.cu", "sh.cu", "isect.cu", "isect_ordered.cu", "blend.cu", "blend_stream.cu", "quant.cu", "optim.cu", "loss.cu", "geom_ops.cu", "dynamic.cu", "indices.cu", "hashgrid.cu", "surfel.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--use_fast_math", "-std=c++17",
     "--extended-lambda", "-Xcompiler", "-fPIC", "-Xptxas", "-v",

@@ -40,6 +40,12 @@ SIGNATURES = {
     "gsb200_projection_quant_fwd": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_projection_quant_bwd": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _U, _U, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                     _P, _P, _P, _P, _P],
+    "gsb200_projection_2dgs_fwd": [_U, _U, _P, _P, _P, _P, _P, _U, _U, _F, _F, _F, _P, _P, _P, _P, _P, _P],
+    "gsb200_projection_2dgs_bwd": [_U, _U] + [_P] * 15,
+    "gsb200_rasterize_2dgs_fwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U] + [_P] * 10,
+    "gsb200_rasterize_2dgs_bwd": [_U, _U, _L, _U, _P, _P, _P, _P, _P, _P, _P, _U, _U, _U, _U, _U] + [_P] * 19,
+    "gsb200_indices_in_range_2dgs_count": [_U, _U, _U, _U, _L, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P],
+    "gsb200_indices_in_range_2dgs_fill": [_U, _U, _U, _U, _L, _P, _P, _P, _U, _U, _U, _U, _U, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_compact_count": [_U, _U, _P, _P, _P, _P],
     "gsb200_compact_fill": [_U, _U, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "gsb200_scatter_rows": [_U, _U, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
@@ -87,6 +93,8 @@ SIGNATURES = {
     "gsb200_fake_quantize_multi_fwd": [_U, _P, _P],
     "gsb200_fake_quantize_multi_bwd": [_U, _P, _P],
     "gsb200_fake_quantize_bwd": [_L, _P, _P, _F, _F, _I, _I, _P, _P, _P],
+    "gsb200_grid_quantize": [_L, _U, _P, _P, _P, _I, _P, _P, _P],
+    "gsb200_grid_dequantize": [_L, _U, _P, _P, _P, _P, _I, _P, _P],
     "gsb200_entropy_fwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P],
     "gsb200_entropy_bwd": [_L, _U, _U, _P, _F, _P, _F, _P, _P, _P, _P],
     "gsb200_entropy_params_fwd": [_U, _U, _P, _P, _P, _P, _P],

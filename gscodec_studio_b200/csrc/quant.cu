@@ -370,9 +370,73 @@ entropy_kernel(int64_t N, uint32_t ch, int64_t L, const float *__restrict__ x, f
     }
 }
 
+// ---------------------------------------------------------------- on-disk quantise-to-grid (PngCompression)
+// gsplat/compression/png_compression.py:166-360: every attribute is normalised per channel to [0, 1] over the whole grid,
+// rounded to `bits` levels (numpy's round-half-even on the float32 product) and stored as 8-bit image planes -- k-bit values
+// left-aligned in the byte (`img << (8 - k)`), 16-bit values as a low and a high plane.  The reference does this with five
+// full-size torch / numpy passes on the host; here it is one pass each way on the device (this file is built without
+// --use_fast_math: the division and the products are the IEEE ones numpy performs).
+__global__ void __launch_bounds__(kThreads)
+grid_quantize_kernel(int64_t n_elems, uint32_t ch, const float *__restrict__ x, const float *__restrict__ mins,
+                     const float *__restrict__ maxs, int bits, uint8_t *__restrict__ lo, uint8_t *__restrict__ hi) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n_elems) return;
+    const uint32_t c = (uint32_t)(i % ch);
+    const float mn = mins[c], mx = maxs[c];
+    const float norm = __fdiv_rn(__fsub_rn(x[i], mn), __fsub_rn(mx, mn));  // (grid - mins) / (maxs - mins)
+    const float levels = (float)((1u << bits) - 1u);
+    const float q = rintf(__fmul_rn(norm, levels));  // np.round: half to even
+    // astype(np.uint8 / np.uint16) of an out-of-range or NaN value (maxs == mins) is unspecified in numpy; saturate
+    const uint32_t v = q >= 0.f ? (q <= levels ? (uint32_t)q : (uint32_t)levels) : 0u;
+    if (bits <= 8) {
+        lo[i] = (uint8_t)(v << (8 - bits));
+    } else {
+        lo[i] = (uint8_t)(v & 0xFFu);
+        hi[i] = (uint8_t)(v >> 8);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+grid_dequantize_kernel(int64_t n_elems, uint32_t ch, const uint8_t *__restrict__ lo, const uint8_t *__restrict__ hi,
+                       const float *__restrict__ mins, const float *__restrict__ maxs, int bits, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n_elems) return;
+    const uint32_t c = (uint32_t)(i % ch);
+    const uint32_t v = bits <= 8 ? ((uint32_t)lo[i] >> (8 - bits)) : (((uint32_t)hi[i] << 8) + (uint32_t)lo[i]);
+    // the reference decodes in float64 (numpy `img / (2**k - 1)`, then a float64 * float32 torch product) and casts at the end
+    const double norm = (double)v / (double)((1u << bits) - 1u);
+    const float span = __fsub_rn(maxs[c], mins[c]);
+    out[i] = (float)(norm * (double)span + (double)mins[c]);
+}
+
 }  // namespace gsb200
 
 using namespace gsb200;
+
+extern "C" int gsb200_grid_quantize(int64_t n_elems, uint32_t ch, const float *x, const float *mins, const float *maxs, int bits,
+                                    uint8_t *lo, uint8_t *hi, gsb200_stream_t stream) {
+    const char *who = "gsb200_grid_quantize";
+    if (bits < 1 || bits > 16) return failf(2, "%s: bits must be in [1, 16]", who);
+    if (ch == 0) return failf(2, "%s: zero channels", who);
+    if (n_elems == 0) return 0;
+    if (!x || !mins || !maxs || !lo || (bits > 8 && !hi)) return failf(2, "%s: null pointer", who);
+    grid_quantize_kernel<<<(unsigned)((n_elems + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(n_elems, ch, x, mins,
+                                                                                                                maxs, bits, lo, hi);
+    return check_launch("grid_quantize");
+}
+
+extern "C" int gsb200_grid_dequantize(int64_t n_elems, uint32_t ch, const uint8_t *lo, const uint8_t *hi, const float *mins,
+                                      const float *maxs, int bits, float *out, gsb200_stream_t stream) {
+    const char *who = "gsb200_grid_dequantize";
+    if (bits < 1 || bits > 16) return failf(2, "%s: bits must be in [1, 16]", who);
+    if (ch == 0) return failf(2, "%s: zero channels", who);
+    if (n_elems == 0) return 0;
+    if (!out || !mins || !maxs || !lo || (bits > 8 && !hi)) return failf(2, "%s: null pointer", who);
+    grid_dequantize_kernel<<<(unsigned)((n_elems + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(n_elems, ch, lo, hi,
+                                                                                                                  mins, maxs, bits, out);
+    return check_launch("grid_dequantize");
+}
+
 
 extern "C" int gsb200_fake_quantize_fwd(int64_t n, float *x, float lo, float hi, int bitwidth, int mode, int act,
                                         const float *noise, uint64_t seed, uint64_t offset, float *y, gsb200_stream_t stream) {

@@ -1063,3 +1063,13 @@ class _RasterizeToPixels(torch.autograd.Function):
         if ctx.needs_input_grad[4]:
             v_backgrounds = (v_render_colors * (1.0 - render_alphas).float()).sum(dim=(1, 2))
         return (v_means2d, v_conics, v_colors, v_opacities, v_backgrounds, None, None, None, None, None, None, None)
+
+
+# the 2D Gaussian (surfel) operators live in their own module; the reference keeps them in _wrapper.py, so callers that
+# import them from here keep working
+from ._wrapper_2dgs import (  # noqa: E402,F401
+    accumulate_2dgs,
+    fully_fused_projection_2dgs,
+    rasterize_to_indices_in_range_2dgs,
+    rasterize_to_pixels_2dgs,
+)

@@ -369,3 +369,7 @@ def rasterization(
             [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1
         )
     return render_colors, render_alphas, meta
+
+
+# (the reference defines these in rendering.py as well)
+from .rendering_2dgs import rasterization_2dgs, rasterization_2dgs_inria_wrapper  # noqa: E402,F401

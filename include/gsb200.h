@@ -116,6 +116,59 @@ int gsb200_compact_fill(uint32_t C, uint32_t N, const int32_t *radii, const floa
                         const int32_t *block_offsets, int32_t *indptr, int64_t *camera_ids,
                         int64_t *gaussian_ids, int32_t *p_radii, float *p_means2d, float *p_depths,
                         float *p_conics, float *p_compensations, gsb200_stream_t stream);
+/* ---- 2D Gaussian (surfel) family ----------------------------------------------------------------------
+ * replaces _C.fully_fused_projection_fwd_2dgs / _bwd_2dgs (bindings.h:311-349; kernels fully_fused_projection_2dgs_{fwd,bwd}.cu,
+ * include/2dgs.cuh).  radii i32 [C,N], means2d [C,N,2], depths [C,N], ray_transforms [C,N,3,3] (rows of K [t_u t_v mean_c]),
+ * normals [C,N,3] (camera space, flipped towards the camera).  Culled entries are zero-filled.  `scales` is [N,3]; only the
+ * first two columns are used and v_scales[:,2] = 0.  No camera gradients (the reference has none either). */
+int gsb200_projection_2dgs_fwd(uint32_t C, uint32_t N, const float *means, const float *quats, const float *scales,
+                               const float *viewmats, const float *Ks, uint32_t image_width, uint32_t image_height,
+                               float near_plane, float far_plane, float radius_clip, int32_t *radii, float *means2d,
+                               float *depths, float *ray_transforms, float *normals, gsb200_stream_t stream);
+int gsb200_projection_2dgs_bwd(uint32_t C, uint32_t N, const float *means, const float *quats, const float *scales,
+                               const float *viewmats, const float *Ks, const int32_t *radii, const float *ray_transforms,
+                               const float *v_means2d, const float *v_depths, const float *v_normals,
+                               const float *v_ray_transforms, float *v_means, float *v_quats, float *v_scales,
+                               gsb200_stream_t stream);
+
+/* replaces _C.rasterize_to_pixels_fwd_2dgs / _bwd_2dgs (bindings.h:351-412; kernels rasterize_to_pixels_2dgs_{fwd,bwd}.cu).
+ * M = C*N or nnz rows; D colour channels in {1,2,3,4,8,16,32}, the LAST channel is read as depth by the distortion and
+ * median-depth outputs.  Outputs: render_colors [C,H,W,D], render_alphas / render_distort / render_median [C,H,W,1],
+ * render_normals [C,H,W,3], last_ids / median_ids i32 [C,H,W].  The backward zero-fills and accumulates the gradient
+ * tensors (v_means2d_abs may be NULL); v_densify [M,2] (may be NULL) = (v_ray_transforms[.,0,2], v_ray_transforms[.,1,2]) *
+ * ray_transforms[.,2,2] from the finished sums. */
+int gsb200_rasterize_2dgs_fwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
+                              const float *ray_transforms, const float *colors, const float *opacities,
+                              const float *normals, const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                              uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                              const int32_t *tile_offsets, const int32_t *flatten_ids, float *render_colors,
+                              float *render_alphas, float *render_normals, float *render_distort, float *render_median,
+                              int32_t *last_ids, int32_t *median_ids, gsb200_stream_t stream);
+int gsb200_rasterize_2dgs_bwd(uint32_t C, uint32_t M, int64_t n_isects, uint32_t D, const float *means2d,
+                              const float *ray_transforms, const float *colors, const float *opacities,
+                              const float *normals, const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                              uint32_t image_height, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                              const int32_t *tile_offsets, const int32_t *flatten_ids, const float *render_colors,
+                              const float *render_alphas, const int32_t *last_ids, const int32_t *median_ids,
+                              const float *v_render_colors, const float *v_render_alphas, const float *v_render_normals,
+                              const float *v_render_distort, const float *v_render_median, float *v_means2d_abs,
+                              float *v_means2d, float *v_ray_transforms, float *v_colors, float *v_opacities,
+                              float *v_normals, float *v_densify, gsb200_stream_t stream);
+
+/* replaces _C.rasterize_to_indices_in_range_2dgs (bindings.h:414-429): the two-call protocol of
+ * gsb200_indices_in_range_count / _fill with the surfel alpha. */
+int gsb200_indices_in_range_2dgs_count(uint32_t range_start, uint32_t range_end, uint32_t C, uint32_t N, int64_t n_isects,
+                                       const float *means2d, const float *ray_transforms, const float *opacities,
+                                       uint32_t image_width, uint32_t image_height, uint32_t tile_size, uint32_t tile_width,
+                                       uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                                       const float *transmittances, int32_t *chunk_cnts, gsb200_stream_t stream);
+int gsb200_indices_in_range_2dgs_fill(uint32_t range_start, uint32_t range_end, uint32_t C, uint32_t N, int64_t n_isects,
+                                      const float *means2d, const float *ray_transforms, const float *opacities,
+                                      uint32_t image_width, uint32_t image_height, uint32_t tile_size, uint32_t tile_width,
+                                      uint32_t tile_height, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                                      const float *transmittances, const int64_t *chunk_starts, int64_t *gaussian_ids,
+                                      int64_t *pixel_ids, gsb200_stream_t stream);
+
 /* ---- quantise on load: compression_simulation fused into the attribute load --------------------------------------------------
  * The reference fake-quantises every attribute with its own chain of torch ops and hands the quantised copies to
  * rasterization() (compression_simulation/ops.py:39-54 called from simulation.py:242-316; then torch.exp / torch.sigmoid,
@@ -488,6 +541,15 @@ typedef struct {
 } gsb200_fq_tensor;
 int gsb200_fake_quantize_multi_fwd(uint32_t n_tensors, const gsb200_fq_tensor *tensors, gsb200_stream_t stream);
 int gsb200_fake_quantize_multi_bwd(uint32_t n_tensors, const gsb200_fq_tensor *tensors, gsb200_stream_t stream);
+
+/* On-disk quantise-to-grid of PngCompression (gsplat/compression/png_compression.py:166-360: _compress_png / _png_kbit /
+ * _png_16bit and their inverses).  x [n_elems] = an attribute viewed as [.., ch]; mins / maxs [ch] are its per-channel extrema.
+ * bits <= 8: lo[i] = round((x - min) / (max - min) * (2^bits - 1)) << (8 - bits); bits in (8, 16]: low / high byte planes.
+ * dequantize mirrors the reference's float64 decode and writes float32. */
+int gsb200_grid_quantize(int64_t n_elems, uint32_t ch, const float *x, const float *mins, const float *maxs, int bits,
+                         uint8_t *lo, uint8_t *hi, gsb200_stream_t stream);
+int gsb200_grid_dequantize(int64_t n_elems, uint32_t ch, const uint8_t *lo, const uint8_t *hi, const float *mins,
+                           const float *maxs, int bits, float *out, gsb200_stream_t stream);
 
 /* factorized-prior entropy model, replaces Entropy_factorized_optimized_refactor.forward
  * (compression_simulation/entropy_model.py:201-254) incl. its channel-scrambled weight tiling.

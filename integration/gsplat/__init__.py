@@ -9,7 +9,7 @@ B200-native hot path without an edit:
     gsplat.compression_simulation (+ .ops / .simulation / .entropy_model / .ada_mask)
     gsplat.optimizers (SelectiveAdam)
 
-Everything else of the reference package (densification strategies, test-time codecs, 2DGS, utilities) is OUTSIDE the
+Everything else of the reference package (densification strategies, test-time codecs) is OUTSIDE the
 hot path and is not re-implemented; when GSPLAT_REFERENCE_PATH points at a checkout of the reference repository those
 sub-packages are served from there (by path, unmodified), otherwise asking for them raises an ImportError that says so.
 """
@@ -27,6 +27,7 @@ _ALIASES = {
     "gsplat.relocation": "gscodec_studio_b200.relocation",
     "gsplat.profile": "gscodec_studio_b200.profile",
     "gsplat._helper": "gscodec_studio_b200._helper",
+    "gsplat.utils": "gscodec_studio_b200.utils",
     "gsplat.cuda": "gscodec_studio_b200.cuda",
     "gsplat.cuda._wrapper": "gscodec_studio_b200.cuda._wrapper",
     "gsplat.optimizers": "gscodec_studio_b200.optimizers",
@@ -51,9 +52,7 @@ if _REF and os.path.isdir(os.path.join(_REF, "gsplat")):
 
 _REFERENCE_ONLY = {
     "DefaultStrategy": "strategy", "MCMCStrategy": "strategy", "Strategy": "strategy", "STG_Strategy": "strategy",
-    "PngCompression": "compression", "rasterization_2dgs": None, "rasterization_inria_wrapper": None,
-    "rasterization_2dgs_inria_wrapper": None, "fully_fused_projection_2dgs": None, "rasterize_to_pixels_2dgs": None,
-    "rasterize_to_indices_in_range_2dgs": None, "accumulate": None, "accumulate_2dgs": None,
+    "PngCompression": "compression", "rasterization_inria_wrapper": None, "accumulate": None,
 }
 if hasattr(_impl.optimizers, "SelectiveAdam"):
     SelectiveAdam = _impl.optimizers.SelectiveAdam

@@ -295,7 +295,11 @@ def test_gsplat_import_shim():
         "from gsplat.cuda._wrapper import spherical_harmonics, fully_fused_projection\n"
         "from gsplat.distributed import cli\n"
         "from gsplat.relocation import compute_relocation\n"
-        "try:\n    gsplat.rasterization_2dgs\n    raise SystemExit('2DGS must not resolve')\nexcept ImportError as e:\n    assert 'outside' in str(e)\n"
+        "assert gsplat.rasterization_2dgs is g.rasterization_2dgs\n"
+        "from gsplat.cuda._wrapper import fully_fused_projection_2dgs, rasterize_to_pixels_2dgs\n"
+        "from gsplat.rendering import rasterization_2dgs\n"
+        "from gsplat.utils import depth_to_normal\n"
+        "try:\n    gsplat.PngCompression\n    raise SystemExit('the codecs must not resolve')\nexcept ImportError as e:\n    assert 'outside' in str(e)\n"
         "print('shim ok')\n")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "integration"), ROOT]))
     env.pop("GSPLAT_REFERENCE_PATH", None)
