@@ -91,6 +91,81 @@ replica_cursor_kernel(uint32_t total_tiles, const int32_t *__restrict__ offsets,
     }
 }
 
+// ---- the three steps above (replica totals -> exclusive scan over the tiles -> replica cursors) in TWO launches ------------
+// One warp per tile, lane = replica: the 32 counters of a tile are one strided warp load, their total one warp reduction,
+// their exclusive prefix one warp scan.  A block covers 32 consecutive tiles.  Kernel 1 leaves the block totals, kernel 2
+// re-derives its own prefix from them (a block reduction over the <= few hundred lower blocks -- no look-back flags, no
+// third kernel), scans its 32 tiles and writes offsets, cursors, the long-tile work list and the grand total.  The five
+// launches this replaces were latency chains on 1 MB of counters: 36 us at 8160 tiles (profiles/r02_isect_bucket_sort_ncu.md).
+static_assert(GSB200_ISECT_REPLICAS == 32, "replica_block_* kernels map one replica to one lane");
+constexpr int kTilesPerBlock = 32;
+
+__global__ void __launch_bounds__(1024)
+replica_block_totals_kernel(uint32_t total_tiles, const int32_t *__restrict__ counts, int32_t *__restrict__ block_totals) {
+    __shared__ int s_tot[kTilesPerBlock];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * kTilesPerBlock + warp;
+    const int c = t < total_tiles ? counts[(size_t)lane * total_tiles + t] : 0;
+    const int tile_total = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) s_tot[warp] = tile_total;
+    __syncthreads();
+    if (warp == 0) {
+        const int b = __reduce_add_sync(0xffffffffu, s_tot[lane]);
+        if (lane == 0) block_totals[blockIdx.x] = b;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+replica_block_cursor_kernel(uint32_t total_tiles, const int32_t *__restrict__ block_totals, int32_t *__restrict__ counts,
+                            int32_t *__restrict__ offsets, int32_t *__restrict__ total_out, uint32_t large_threshold) {
+    __shared__ int s_tot[kTilesPerBlock];
+    __shared__ int s_part[32];
+    __shared__ int s_prefix;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // exclusive prefix of this block: sum of the totals of all lower blocks
+    int part = 0;
+    for (uint32_t j = threadIdx.x; j < blockIdx.x; j += 1024) part += block_totals[j];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) s_part[warp] = part;
+    const uint32_t t = blockIdx.x * kTilesPerBlock + warp;
+    const int c = t < total_tiles ? counts[(size_t)lane * total_tiles + t] : 0;
+    int incl = c;  // inclusive scan over the replicas of this tile
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    const int tile_total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) s_tot[warp] = tile_total;
+    __syncthreads();
+    if (warp == 0) {
+        const int prefix = __reduce_add_sync(0xffffffffu, s_part[lane]);
+        const int v = s_tot[lane];
+        int wi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, wi, o);
+            if ((int)lane >= o) wi += u;
+        }
+        s_tot[lane] = wi - v;  // exclusive prefix of tile `lane` inside the block
+        if (lane == 31) {
+            s_prefix = prefix;
+            if (blockIdx.x == gridDim.x - 1) *total_out = prefix + wi;
+        }
+    }
+    __syncthreads();
+    if (t >= total_tiles) return;
+    const int base = s_prefix + s_tot[warp];
+    counts[(size_t)lane * total_tiles + t] = base + incl - c;  // first slot of replica `lane` inside the tile's segment
+    if (lane == 0) {
+        offsets[t] = base;
+        if ((uint32_t)tile_total > large_threshold) {
+            int32_t *list = counts + (size_t)GSB200_ISECT_REPLICAS * total_tiles;
+            list[1 + atomicAdd(list, 1)] = (int32_t)t;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
 isect_scatter_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids, const float *__restrict__ means2d,
                      const int32_t *__restrict__ radii, const float *__restrict__ depths, float ts, uint32_t tw, uint32_t th,
@@ -715,7 +790,17 @@ static bool use_ordered(uint32_t C, uint32_t n_elems, uint32_t tw, uint32_t th) 
     return on && n_elems > 0 && ordered_plan(C, n_elems, tw, th).ok;
 }
 
-static size_t tilesort_scratch_ints(uint32_t T) { return (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 2 + T / kScanTile + 3; }
+static size_t tilesort_scratch_ints(uint32_t T) {  // counters | work list | total | scan scratch or block totals
+    return (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 2 + max(T / kScanTile + 3, T / 32 + 2);
+}
+// GSB200_ISECT_SCAN=legacy: the five-launch totals / scan / cursor sequence of round 2 (A/B timing)
+static bool fused_replica_scan() {
+    static const bool on = [] {
+        const char *v = getenv("GSB200_ISECT_SCAN");
+        return !(v != nullptr && strcmp(v, "legacy") == 0);
+    }();
+    return on;
+}
 static size_t tilesort_total_index(uint32_t T) { return (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1; }
 
 extern "C" int gsb200_isect_plan(uint32_t C, uint32_t n_elems, uint32_t tile_width, uint32_t tile_height, int64_t *scratch_ints,
@@ -766,25 +851,35 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
                                                                      camera_ids, means2d, radii, (float)tile_size,
                                                                      tile_width, tile_height, T, tiles_per_gauss, tile_cursor);
     if (int e = check_launch("isect_count")) return e;
-    replica_totals_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, tile_cursor, isect_offsets);
-    if (int e = check_launch("replica_totals")) return e;
-    const uint32_t nb = cdiv(T, kScanTile);
-    // scan scratch lives at the end of the caller's tile_cursor buffer (a stream-ordered allocation here would
+    // scratch lives at the end of the caller's tile_cursor buffer (a stream-ordered allocation here would
     // go back to the driver after every host synchronisation -- milliseconds)
     int32_t *scratch = tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 2;
-    int e = exclusive_scan(T, isect_offsets, nullptr, scratch, s);
     int32_t total = 0;
     int32_t *total_dev = tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1;
-    if (e == 0) {
-        replica_cursor_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, isect_offsets, tile_cursor, kSortSmall);
-        e = check_launch("replica_cursor");
-    }
-    if (e == 0) {
-        cudaError_t ce = cudaMemcpyAsync(total_dev, scratch + nb, sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
-        if (ce == cudaSuccess && n_isects_host != nullptr) {
-            ce = cudaMemcpyAsync(&total, scratch + nb, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    int e = 0;
+    if (fused_replica_scan()) {
+        const uint32_t nblk = cdiv(T, kTilesPerBlock);
+        replica_block_totals_kernel<<<nblk, 1024, 0, s>>>(T, tile_cursor, scratch);
+        e = check_launch("replica_block_totals");
+        if (e == 0) {
+            replica_block_cursor_kernel<<<nblk, 1024, 0, s>>>(T, scratch, tile_cursor, isect_offsets, total_dev, kSortSmall);
+            e = check_launch("replica_block_cursor");
         }
+    } else {
+        replica_totals_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, tile_cursor, isect_offsets);
+        if (int e2 = check_launch("replica_totals")) return e2;
+        const uint32_t nb = cdiv(T, kScanTile);
+        e = exclusive_scan(T, isect_offsets, nullptr, scratch, s);
+        if (e == 0) {
+            replica_cursor_kernel<<<cdiv(T, kThreads), kThreads, 0, s>>>(T, isect_offsets, tile_cursor, kSortSmall);
+            e = check_launch("replica_cursor");
+        }
+        if (e == 0 && cudaMemcpyAsync(total_dev, scratch + nb, sizeof(int32_t), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            e = fail(101, "gsb200_isect_prepare: device copy of the intersection count failed");
+    }
+    if (e == 0 && n_isects_host != nullptr) {
+        cudaError_t ce = cudaMemcpyAsync(&total, total_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
         if (ce != cudaSuccess) e = fail(101, cudaGetErrorString(ce));
     }
     if (e) return e;
