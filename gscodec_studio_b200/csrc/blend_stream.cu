@@ -43,6 +43,9 @@ constexpr int kStages = GSB_STREAM_STAGES;
 #ifndef GSB_BWD_MOMENTS
 #define GSB_BWD_MOMENTS 1  // backward accumulates moments of -v_sigma (finished per Gaussian in unpack_grads_kernel); 0: round-2 form
 #endif
+#ifndef GSB_BWD_PIPELINE
+#define GSB_BWD_PIPELINE 0  // retire record i's sums inside the iteration of record i + 1 (see blend_stream_bwd_kernel); measured SLOWER (761 vs 668 us): off
+#endif
 constexpr int kRecBytes = 48;
 constexpr uint32_t kEndFlag = 0x100;
 constexpr float kNegLog2e = -1.4426950408889634f;
@@ -537,6 +540,39 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
     const uint32_t slot8 = spread_slot<8>(lane), slot4 = spread_slot<4>(lane);
     const bool pub8 = (lane & 3) == 0, pub4 = (lane & 7) == 0;
 
+    // Software pipeline over the records (GSB_BWD_PIPELINE): the partial sums of record i are kept in registers and
+    // retired -- warp reduction + REDs -- inside the iteration of record i + 1, right after that record's loads have been
+    // issued: the five dependent shuffle stages (~150 cycles of latency for THIS warp) then overlap with the sigma / exp /
+    // reciprocal chain of the next record instead of preceding it.  A tile's warps walk their records serially, so this
+    // latency is the critical path of the long tiles that finish last (sm__cycles_active was 79 % of elapsed).
+    float pend[NGRP * 8], pend_tail[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NGRP * 8; ++k) pend[k] = 0.f;
+    float *pend_rec = nullptr;  // warp-uniform: record the pending sums belong to (nullptr: nothing pending)
+    auto retire = [&](float *vals, float *tail, float *rec, bool live) {
+#pragma unroll
+        for (int gi = 0; gi < NGRP; ++gi) reduce_spread<8>(vals + gi * 8, lane);
+        float tail_sum;
+        if (ABS) {
+            reduce_spread<4>(tail, lane);
+            tail_sum = tail[0];
+        } else {
+            tail_sum = warp_sum(tail[0]);
+        }
+        // (`live` folds into the lane predicates of the REDs: no branch, so that the compiler can schedule the shuffle
+        // stages between the arithmetic of the record whose loads precede this call)
+#pragma unroll
+        for (int gi = 0; gi < NGRP; ++gi) {
+            const uint32_t off = gi * 8 + slot8;
+            if (live && pub8 && off < (uint32_t)NMAIN) red_add(rec + off, vals[gi * 8]);
+        }
+        if (ABS) {
+            if (live && pub4 && slot4 < 3) red_add(rec + NMAIN + slot4, tail_sum);
+        } else {
+            if (live && lane == 0) red_add(rec + NMAIN, tail_sum);
+        }
+    };
+
     for (uint32_t j = 0; j < nst; ++j) {
         const uint32_t st = nst - 1 - j, slot = j % kStages;
         mbar_wait<GSB_CONSUMER_SLEEP_NS>(a_full + 8 * slot, (j / kStages) & 1);
@@ -557,8 +593,15 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                     const uint32_t wt = __float_as_uint(A.w);
                     const int32_t idx = (int32_t)(wt >> 4);
                     const float opac = A.z;
-                    float vals[NGRP * 8];
-                    float tail[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (GSB_BWD_PIPELINE) {  // (unconditional shuffles, predicated REDs: one basic block with the arithmetic below)
+                        retire(pend, pend_tail, pend_rec, pend_rec != nullptr);
+                        pend_rec = nullptr;
+                    }
+                    // (pipelined: the sums are formed directly in the pending registers the retire above has just consumed)
+                    float vals_local[NGRP * 8], tail_local[4];
+                    float *vals = GSB_BWD_PIPELINE ? pend : vals_local, *tail = GSB_BWD_PIPELINE ? pend_tail : tail_local;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tail[k] = 0.f;
 #pragma unroll
                     for (int k = 0; k < NGRP * 8; ++k) vals[k] = 0.f;
                     bool any_valid = false;
@@ -649,25 +692,11 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                         }
                     }
                     if (!any_valid) continue;
-#pragma unroll
-                    for (int gi = 0; gi < NGRP; ++gi) reduce_spread<8>(vals + gi * 8, lane);
-                    float tail_sum;
-                    if (ABS) {
-                        reduce_spread<4>(tail, lane);
-                        tail_sum = tail[0];
-                    } else {
-                        tail_sum = warp_sum(tail[0]);
-                    }
                     float *rec = grad_rec + (size_t)__float_as_int(B.w) * REC;
-#pragma unroll
-                    for (int gi = 0; gi < NGRP; ++gi) {
-                        const uint32_t off = gi * 8 + slot8;
-                        if (pub8 && off < (uint32_t)NMAIN) red_add(rec + off, vals[gi * 8]);
-                    }
-                    if (ABS) {
-                        if (pub4 && slot4 < 3) red_add(rec + NMAIN + slot4, tail_sum);
+                    if (GSB_BWD_PIPELINE) {
+                        pend_rec = rec;
                     } else {
-                        if (lane == 0) red_add(rec + NMAIN, tail_sum);
+                        retire(vals, tail, rec, true);
                     }
                 }
             }
@@ -683,6 +712,7 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
             }
         }
     }
+    if (GSB_BWD_PIPELINE && pend_rec != nullptr) retire(pend, pend_tail, pend_rec, true);  // the last record of the walk
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -690,6 +720,16 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
 #ifndef GSB_STREAM_NP
 #define GSB_STREAM_NP 1
 #endif
+// Resident CTAs per SM can be capped from the environment (A/B experiments on the long-tile tail): GSB200_SFWD_CTAS /
+// GSB200_SBWD_CTAS = n makes every CTA ask for 1/n of the SM's shared memory as (unused) dynamic shared memory.
+static size_t occupancy_pad(const char *env, size_t static_bytes, int default_ctas = 0) {
+    const char *v = getenv(env);
+    const int n = v != nullptr ? atoi(v) : default_ctas;
+    if (n < 1 || n > 16) return 0;
+    const size_t per_cta = (size_t)(227 * 1024) / (size_t)n - 1024;  // 1 KB per CTA is reserved by the runtime
+    return per_cta > static_bytes ? per_cta - static_bytes : 0;
+}
+
 static int stream_np() {
     static const int np = [] {
         const char *v = getenv("GSB200_STREAM_NP");
@@ -716,10 +756,14 @@ static int fwd_t(const BlendGeom &G, const float *means2d, const float *conics, 
         blend_stream_fwd_kernel<CDIM, 2><<<T, 3 * 32, 0, s>>>(
             G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
             render_colors, render_alphas, last_ids, tile_order, reinterpret_cast<float4 *>(blend_stream), tile_counts);
-    else
-        blend_stream_fwd_kernel<CDIM, 1><<<T, 5 * 32, 0, s>>>(
+    else {
+        const size_t pad = occupancy_pad("GSB200_SFWD_CTAS", sizeof(StreamShared));
+        if (pad > 0)
+            GSB_CUDA_OK(cudaFuncSetAttribute(blend_stream_fwd_kernel<CDIM, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));
+        blend_stream_fwd_kernel<CDIM, 1><<<T, 5 * 32, pad, s>>>(
             G, reinterpret_cast<const float2 *>(means2d), conics, colors, opacities, backgrounds, masks, tile_offsets, flatten_ids,
             render_colors, render_alphas, last_ids, tile_order, reinterpret_cast<float4 *>(blend_stream), tile_counts);
+    }
     return check_launch("blend_stream_fwd");
 }
 
@@ -745,10 +789,18 @@ static int bwd_t(const BlendGeom &G, const float *backgrounds, const uint8_t *ma
                  bool absgrad, cudaStream_t s) {
     const uint32_t T = G.C * G.tw * G.th;
     const float4 *st = reinterpret_cast<const float4 *>(blend_stream);
+    // measured on B200 at the headline size (tools/gpu_r2_visit29.sh): 8 resident CTAs 667 us, 6: 663, 5: 650, 4: 691, 3: 823
+    const size_t pad = occupancy_pad("GSB200_SBWD_CTAS", sizeof(StreamShared), 5);
 #define GSB_BWD_LAUNCH(NPV, ABSV)                                                                                     \
-    blend_stream_bwd_kernel<CDIM, NPV, ABSV><<<T, (4 / NPV) * 32, 0, s>>>(G, backgrounds, masks, tile_offsets, render_alphas, \
-                                                                         last_ids, v_render_colors, v_render_alphas,     \
-                                                                         tile_order, st, tile_counts, grad_scratch)
+    do {                                                                                                              \
+        if (pad > 0)                                                                                                  \
+            GSB_CUDA_OK(cudaFuncSetAttribute(blend_stream_bwd_kernel<CDIM, NPV, ABSV>,                                \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad));                 \
+        blend_stream_bwd_kernel<CDIM, NPV, ABSV><<<T, (4 / NPV) * 32, pad, s>>>(G, backgrounds, masks, tile_offsets,  \
+                                                                             render_alphas, last_ids, v_render_colors, \
+                                                                             v_render_alphas, tile_order, st,         \
+                                                                             tile_counts, grad_scratch);              \
+    } while (0)
     if (stream_np() == 2) {
         if (absgrad) GSB_BWD_LAUNCH(2, true); else GSB_BWD_LAUNCH(2, false);
     } else {
