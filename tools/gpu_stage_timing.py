@@ -80,6 +80,31 @@ def main():
              16, tw, th, ptr(offs), ptr(fl), ptr(rc), ptr(ra), ptr(last), ptr(order), ptr(bstream), ptr(tcnt), stream_ptr(DEV))
 
     res["blend_fwd"] = timeit(fwd)
+    if os.environ.get("TILE_STATS") == "1" and rec:
+        # how uneven is the blend's work?  per tile: intersections, records the backward walks, and -- per 8x8 block (= per
+        # warp) -- the records that hit it: a warp walks its records serially, so the busiest warp of the longest tile is a
+        # lower bound of the kernel time however the other tiles are scheduled
+        torch.cuda.synchronize()
+        T = tw * th
+        ends = torch.cat([offs.view(-1)[1:], torch.tensor([I], device=DEV, dtype=offs.dtype)])
+        n_tile = (ends - offs.view(-1)).long()
+        cnt = tcnt.long()
+        words = bstream[: I * 12].view(-1, 12)[:, 3].contiguous().view(torch.int32)
+        tile_of = torch.repeat_interleave(torch.arange(T, device=DEV), n_tile)
+        pos = torch.arange(I, device=DEV) - offs.view(-1).long()[tile_of]
+        used = pos < cnt[tile_of]
+        hits = torch.zeros(T, 4, dtype=torch.long, device=DEV)
+        for b in range(4):
+            hb = used & (((words >> b) & 1) == 1)
+            hits[:, b] = torch.zeros(T, dtype=torch.long, device=DEV).index_add_(0, tile_of[hb], torch.ones(int(hb.sum()), dtype=torch.long, device=DEV))
+        busiest = hits.max(1).values
+        q = lambda t, p: int(torch.quantile(t.float(), p).item())
+        for name, t in (("intersections / tile", n_tile), ("records walked / tile", cnt), ("hits of the busiest warp / tile", busiest)):
+            print(f"{name:34s} sum {int(t.sum()):9d} mean {t.float().mean().item():8.1f} p50 {q(t, .5):6d} p90 {q(t, .9):6d} "
+                  f"p99 {q(t, .99):6d} max {int(t.max()):6d}")
+        total_hits = int(hits.sum())
+        print(f"warp iterations (block hits) {total_hits}; busiest warp {int(busiest.max())} = "
+              f"{int(busiest.max()) / (total_hits / (148 * 4 * 5)):.2f} x the per-warp-slot average at 5 CTAs/SM")
     v_c = torch.ones(1, Hd, Wd, 3, device=DEV)
     v_a = torch.zeros(1, Hd, Wd, 1, device=DEV)
     scratch = torch.empty(N * 12, device=DEV)
