@@ -305,3 +305,48 @@ def test_gsplat_import_shim():
     env.pop("GSPLAT_REFERENCE_PATH", None)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd="/tmp")
     assert out.returncode == 0 and "shim ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_quant_on_load_host_logic_without_kernels(monkeypatch):
+    """Host side of the quantise-on-load hook on the CPU (kernels stubbed): simulate_compression(fuse_into_render=True) hands
+    back lazy QuantOnLoad objects for the attributes it only fake-quantises, exp / sigmoid of one stay lazy, any other use
+    materialises through the stand-alone kernel with the SAME draw, and attributes with a rate term stay eager."""
+    from gscodec_studio_b200.compression_simulation import ops, simulation as S
+
+    seen = []
+
+    def fake_apply(x, lo, hi, bits, mode, act, noise, philox):  # stands in for _FakeQuantize.apply
+        seen.append((tuple(x.shape), lo, hi, bits, mode, act, noise is not None, philox))
+        y = torch.clamp(x, lo, hi) + (noise if noise is not None else 0.0) * (hi - lo) / (2 ** bits - 1)
+        return torch.exp(y) if act == 1 else torch.sigmoid(y) if act == 2 else y
+
+    monkeypatch.setattr(ops._FakeQuantize, "apply", staticmethod(fake_apply))
+    monkeypatch.setattr(S, "fake_quantize_ste_multi", lambda items: [
+        {"output_value": fake_apply(it["input"], it["lower_bd"], it["upper_bd"], it["bitwidth"], 0, 0, it.get("noise"), None),
+         "q_step": 0.0} for it in items])
+    g = torch.Generator().manual_seed(0)
+    N = 64
+    splats = {"means": torch.randn(N, 3, generator=g), "scales": torch.randn(N, 3, generator=g), "quats": torch.randn(N, 4, generator=g),
+              "opacities": torch.randn(N, generator=g), "sh0": torch.randn(N, 1, 3, generator=g), "shN": torch.randn(N, 15, 3, generator=g)}
+    noise = {k: torch.rand(splats[k].shape, generator=g) - 0.5 for k in ("scales", "quats", "opacities", "sh0")}
+    sim = S.CompressionSimulation(entropy_model_enable=False, device="cpu")
+    # CPU tensors are never made lazy (there is no kernel to consume them): the eager path is taken
+    new, bits = sim.simulate_compression(splats, 100, noise=noise, fuse_into_render=True)
+    assert all(torch.is_tensor(v) for v in new.values()) and all(b is None for b in bits.values())
+
+    # the lazy object itself (construction needs no kernel when the noise is given)
+    lz = ops.QuantOnLoad(splats["scales"], -10, 2, 8, noise["scales"])
+    assert lz.shape == (N, 3) and len(lz) == N and lz.dim() == 2 and not seen[4:]
+    ex = torch.exp(lz)
+    assert isinstance(ex, ops.QuantOnLoad) and ex.act == "exp" and torch.exp(lz) is ex and ex.raw is lz.raw
+    d = ex.descriptor()
+    assert (d.lo, d.hi, d.bitwidth, d.act) == (-10.0, 2.0, 8, 1) and d.noise == lz.noise.data_ptr()
+    n0 = len(seen)
+    a = lz + 1.0                       # arithmetic -> materialised once ...
+    b = torch.cat([lz, lz], dim=1)     # ... and reused by every later consumer
+    assert len(seen) == n0 + 1 and seen[-1][4:7] == (0, 0, True)
+    assert torch.equal(a, lz.materialize() + 1.0) and b.shape == (N, 6)
+    assert torch.allclose(ex.materialize(), torch.exp(lz.materialize()))
+    assert torch.is_tensor(torch.exp(ex)) and ops.solid(lz) is lz.materialize() and ops.solid(None) is None
+    with pytest.raises(ValueError):
+        ops.QuantOnLoad(splats["scales"], -10, 2, 8, noise["scales"], activation="tanh")
