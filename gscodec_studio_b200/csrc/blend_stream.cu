@@ -32,7 +32,10 @@ constexpr int kStages = GSB_STREAM_STAGES;
 #define GSB_SFWD_BLOCKS 6  // minimum resident CTAs per SM the register allocator must allow (forward, NP = 1)
 #endif
 #ifndef GSB_SBWD_BLOCKS
-#define GSB_SBWD_BLOCKS 7  // (backward, NP = 1)
+#define GSB_SBWD_BLOCKS 7  // (backward, NP = 1; the two-record walk, GSB_BWD_PAIR, asks for 5: the launch caps the CTAs at 5 per SM anyway)
+#endif
+#ifndef GSB_SBWD_PAIR_BLOCKS
+#define GSB_SBWD_PAIR_BLOCKS 5
 #endif
 #ifndef GSB_PRODUCER_SLEEP_NS
 #define GSB_PRODUCER_SLEEP_NS 256  // ring full: the consumers need ~10^3 cycles per stage
@@ -45,6 +48,12 @@ constexpr int kStages = GSB_STREAM_STAGES;
 #endif
 #ifndef GSB_BWD_PIPELINE
 #define GSB_BWD_PIPELINE 0  // retire record i's sums inside the iteration of record i + 1 (see blend_stream_bwd_kernel); measured SLOWER (761 vs 668 us): off
+#endif
+#ifndef GSB_FWD_PAIR
+#define GSB_FWD_PAIR 1  // forward consumers walk their records two at a time (NP = 1)
+#endif
+#ifndef GSB_BWD_PAIR
+#define GSB_BWD_PAIR 1  // backward walks a warp's records two at a time (NP = 1): see blend_stream_bwd_kernel
 #endif
 constexpr int kRecBytes = 48;
 constexpr uint32_t kEndFlag = 0x100;
@@ -366,6 +375,61 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
                     const uint32_t e = c0 + lane;
                     const uint32_t word = e < nrec ? lds1u(a_stage + e * kRecBytes + 12) : 0u;
                     unsigned m = __ballot_sync(0xffffffffu, (word & hitsel) != 0);
+#if GSB_FWD_PAIR
+                    // two records per trip (NP = 1): their sigma / exp2 chains are independent, only T, the last-contributor word
+                    // and the colour sums pass from the first to the second -- same per-lane arithmetic in the same order
+                    while (NP == 1 && m) {
+                        const uint32_t t1 = c0 + (uint32_t)__ffs(m) - 1u;
+                        m &= m - 1;
+                        const bool two = m != 0;
+                        const uint32_t t2 = two ? c0 + (uint32_t)__ffs(m) - 1u : t1;
+                        m &= m - 1;
+                        const float4 A1 = lds4(a_stage + t1 * kRecBytes), B1 = lds4(a_stage + t1 * kRecBytes + 16);
+                        const float4 A2 = lds4(a_stage + t2 * kRecBytes), B2 = lds4(a_stage + t2 * kRecBytes + 16);
+                        const float4 C1 = lds4(a_stage + t1 * kRecBytes + 32), C2 = lds4(a_stage + t2 * kRecBytes + 32);
+                        struct F1 {
+                            float2 sigma, alpha;
+                        };
+                        auto phase1 = [&](const float4 &A, const float4 &B) {
+                            F1 q;
+                            const float dx = A.x - px[0];
+                            const float2 dy = __fadd2_rn(bc(A.y), npy[0]);
+                            float2 tt = __fmul2_rn(bc(B.z), dy);
+                            const float u = B.x * dx, v = B.y * dx;
+                            tt = __fmul2_rn(dy, tt);
+                            float2 uu = __ffma2_rn(bc(dx), bc(u), tt);
+                            uu = __fmul2_rn(uu, bc(0.5f));
+                            q.sigma = __ffma2_rn(dy, bc(v), uu);
+                            const float2 ee = __fmul2_rn(q.sigma, bc(kNegLog2e));
+                            const float2 ov = __fmul2_rn(bc(A.z), make_float2(exp2f(ee.x), exp2f(ee.y)));
+                            q.alpha = make_float2(fminf(kAlphaMax, ov.x), fminf(kAlphaMax, ov.y));
+                            return q;
+                        };
+                        const F1 q1 = phase1(A1, B1);
+                        F1 q2 = phase1(A2, B2);
+                        // no second record: alpha = 0 fails the 1/255 test for both pixels, the record is a no-op
+                        q2.alpha.x = two ? q2.alpha.x : 0.f;
+                        q2.alpha.y = two ? q2.alpha.y : 0.f;
+                        auto phase2 = [&](const float4 &A, const float4 &C4, const F1 &q) {
+                            const float cs[4] = {C4.x, C4.y, C4.z, C4.w};
+                            const uint32_t wt = __float_as_uint(A.w);
+                            const float2 next_T = __fmul2_rn(T[0], __ffma2_rn(q.alpha, bc(-1.f), bc(1.f)));
+                            const bool ok0 = !(q.sigma.x < 0.f || q.alpha.x < kAlphaMin), ok1 = !(q.sigma.y < 0.f || q.alpha.y < kAlphaMin);
+                            const bool take0 = ok0 && !(next_T.x <= kTStop), take1 = ok1 && !(next_T.y <= kTStop);
+                            float2 vis = __fmul2_rn(q.alpha, T[0]);
+                            vis.x = take0 ? vis.x : 0.f;
+                            vis.y = take1 ? vis.y : 0.f;
+#pragma unroll
+                            for (int c = 0; c < CDIM; ++c) out[0][c] = __ffma2_rn(bc(cs[c]), vis, out[0][c]);
+                            T[0].x = take0 ? next_T.x : (ok0 ? -fabsf(T[0].x) : T[0].x);
+                            T[0].y = take1 ? next_T.y : (ok1 ? -fabsf(T[0].y) : T[0].y);
+                            cur0[0] = take0 ? wt : cur0[0];
+                            cur1[0] = take1 ? wt : cur1[0];
+                        };
+                        phase2(A1, C1, q1);
+                        phase2(A2, C2, q2);
+                    }
+#endif
                     while (m) {
                         const uint32_t t = c0 + (uint32_t)__ffs(m) - 1u;
                         m &= m - 1;
@@ -462,7 +526,7 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
 // No producer warp here: staging is one bulk copy per stage, so the LAST consumer warp to release a ring slot refills it
 // (a shared-memory counter per slot plays the "empty" barrier) and every warp of the CTA does blend work.
 template <int CDIM, int NP, bool ABS>
-__global__ void __launch_bounds__((4 / NP) * 32, NP == 1 ? GSB_SBWD_BLOCKS : 8)
+__global__ void __launch_bounds__((4 / NP) * 32, NP == 1 ? (GSB_BWD_PAIR ? GSB_SBWD_PAIR_BLOCKS : GSB_SBWD_BLOCKS) : 8)
 blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, const uint8_t *__restrict__ masks,
                         const int32_t *__restrict__ tile_offsets, const float *__restrict__ render_alphas,
                         const int32_t *__restrict__ last_ids, const float *__restrict__ v_render_colors,
@@ -539,6 +603,8 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
     const uint32_t hitsel = ((1u << NP) - 1u) << (warp * NP);
     const uint32_t slot8 = spread_slot<8>(lane), slot4 = spread_slot<4>(lane);
     const bool pub8 = (lane & 3) == 0, pub4 = (lane & 7) == 0;
+    const uint32_t slot16 = spread_slot<16>(lane);
+    const bool pub16 = (lane & 1) == 0;
 
     // Software pipeline over the records (GSB_BWD_PIPELINE): the partial sums of record i are kept in registers and
     // retired -- warp reduction + REDs -- inside the iteration of record i + 1, right after that record's loads have been
@@ -583,6 +649,156 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                 const int32_t r = nrec - 1 - c0 - (int32_t)lane;  // records back to front
                 const uint32_t word = r >= 0 ? lds1u(a_stage + (uint32_t)r * kRecBytes + 12) : 0u;
                 unsigned m = __ballot_sync(0xffffffffu, (word & hitsel) != 0 && (int32_t)(word >> 4) <= warp_bin);
+#if GSB_BWD_PAIR
+                // Two records per trip (NP = 1).  A warp's iteration is one long dependent chain -- record loads, sigma,
+                // exp2, the reciprocal, v_alpha, five shuffle levels -- and with 5 resident CTAs a scheduler has ~4.4 warps
+                // to hide it behind (issue slots 68 % busy, stalls 'wait' + 'short scoreboard' 2.9 of 6.4 cycles per
+                // instruction, profiles/r02b_blend_stream_ncu.md).  Everything of two consecutive records is independent
+                // except the running T and B (one multiply / one FMA per record each), so the two are evaluated as ONE
+                // basic block: the arithmetic of both interleaves, and their 2 x 9 sums go through one 16-value + one 2-value
+                // halving butterfly (21 shuffles instead of 28).  Per-lane arithmetic of a record is unchanged.
+                while (NP == 1 && m) {
+                    const uint32_t base_t = (uint32_t)(nrec - 1 - c0);
+                    const uint32_t t1 = base_t - ((uint32_t)__ffs(m) - 1u);
+                    m &= m - 1;
+                    const bool two = m != 0;
+                    const uint32_t t2 = two ? base_t - ((uint32_t)__ffs(m) - 1u) : t1;
+                    m &= m - 1;
+                    const float4 A1 = lds4(a_stage + t1 * kRecBytes), B1 = lds4(a_stage + t1 * kRecBytes + 16);
+                    const float4 A2 = lds4(a_stage + t2 * kRecBytes), B2 = lds4(a_stage + t2 * kRecBytes + 16);
+                    const float4 C1 = lds4(a_stage + t1 * kRecBytes + 32), C2 = lds4(a_stage + t2 * kRecBytes + 32);
+                    struct P1 {
+                        float dx, u, v;
+                        float2 dy, vis, ov, alpha;
+                        bool valid0, valid1;
+                    };
+                    auto phase1 = [&](const float4 &A, const float4 &B, bool live) {
+                        P1 q;
+                        const int32_t idx = (int32_t)(__float_as_uint(A.w) >> 4);
+                        q.dx = A.x - px[0];
+                        q.dy = __fadd2_rn(bc(A.y), npy[0]);
+                        float2 tt = __fmul2_rn(bc(B.z), q.dy);
+                        q.u = B.x * q.dx;
+                        q.v = B.y * q.dx;
+                        tt = __fmul2_rn(q.dy, tt);
+                        float2 uu = __ffma2_rn(bc(q.dx), bc(q.u), tt);
+                        uu = __fmul2_rn(uu, bc(0.5f));
+                        const float2 sigma = __ffma2_rn(q.dy, bc(q.v), uu);
+                        const float2 ee = __fmul2_rn(sigma, bc(kNegLog2e));
+                        q.vis = make_float2(exp2f(ee.x), exp2f(ee.y));
+                        q.ov = __fmul2_rn(bc(A.z), q.vis);
+                        q.alpha = make_float2(fminf(kAlphaMax, q.ov.x), fminf(kAlphaMax, q.ov.y));
+                        q.valid0 = live && idx <= bin0[0] && !(sigma.x < 0.f || q.alpha.x < kAlphaMin);
+                        q.valid1 = live && idx <= bin1[0] && !(sigma.y < 0.f || q.alpha.y < kAlphaMin);
+                        return q;
+                    };
+                    const P1 q1 = phase1(A1, B1, true), q2 = phase1(A2, B2, two);
+                    const bool any1 = __any_sync(0xffffffffu, q1.valid0 || q1.valid1);
+                    const bool any2 = __any_sync(0xffffffffu, q2.valid0 || q2.valid1);
+                    if (!(any1 || any2)) continue;
+                    // per-thread sums of one record (the arithmetic of the single-record loop below); advances T and B
+                    auto phase2 = [&](const float4 &B, const float4 &C4, const P1 &q, float *vals, float *tail) {
+                        const float cs[4] = {C4.x, C4.y, C4.z, C4.w};
+                        const float2 nom = __fadd2_rn(q.alpha, bc(-1.f));
+                        const float2 nra = make_float2(1.f / nom.x, 1.f / nom.y);
+                        const float2 ra = make_float2(-nra.x, -nra.y);
+                        const float2 Tn = __fmul2_rn(T[0], ra);
+                        T[0].x = q.valid0 ? Tn.x : T[0].x;
+                        T[0].y = q.valid1 ? Tn.y : T[0].y;
+                        float2 fac = __fmul2_rn(q.alpha, Tn);
+                        fac.x = q.valid0 ? fac.x : 0.f;
+                        fac.y = q.valid1 ? fac.y : 0.f;
+                        float2 Acv = __fmul2_rn(bc(cs[0]), v_c[0][0]);
+#pragma unroll
+                        for (int k = 1; k < CDIM; ++k) Acv = __ffma2_rn(bc(cs[k]), v_c[0][k], Acv);
+                        float2 v_alpha = __ffma2_rn(Tn, Acv, __fmul2_rn(nra, Bsum[0]));
+                        Bsum[0] = __ffma2_rn(fac, Acv, Bsum[0]);
+#pragma unroll
+                        for (int k = 0; k < CDIM; ++k) {
+                            const float2 gk = __fmul2_rn(fac, v_c[0][k]);
+                            vals[k] = gk.x + gk.y;
+                        }
+                        v_alpha = __ffma2_rn(__fmul2_rn(Tfin[0], ra), v_a[0], v_alpha);
+                        if (bg) v_alpha = __ffma2_rn(__fmul2_rn(Tfin[0], nra), bg_dot[0], v_alpha);
+                        const bool gate0 = q.valid0 && q.ov.x <= kAlphaMax, gate1 = q.valid1 && q.ov.y <= kAlphaMax;
+                        float2 nvs = __fmul2_rn(q.ov, v_alpha);  // -v_sigma
+                        nvs.x = gate0 ? nvs.x : 0.f;
+                        nvs.y = gate1 ? nvs.y : 0.f;
+                        if (ABS || !GSB_BWD_MOMENTS) {
+                            const float2 hs = __fmul2_rn(nvs, bc(0.5f));
+                            const float2 ga = __fmul2_rn(__fmul2_rn(hs, bc(q.dx)), bc(q.dx));
+                            const float2 gb = __fmul2_rn(__fmul2_rn(nvs, bc(q.dx)), q.dy);
+                            const float2 gc = __fmul2_rn(__fmul2_rn(hs, q.dy), q.dy);
+                            const float2 gx = __fmul2_rn(nvs, __ffma2_rn(bc(B.y), q.dy, bc(q.u)));
+                            const float2 gy = __fmul2_rn(nvs, __ffma2_rn(bc(B.z), q.dy, bc(q.v)));
+                            vals[CDIM + 0] = -ga.x - ga.y;
+                            vals[CDIM + 1] = -gb.x - gb.y;
+                            vals[CDIM + 2] = -gc.x - gc.y;
+                            vals[CDIM + 3] = -gx.x - gx.y;
+                            vals[CDIM + 4] = -gy.x - gy.y;
+                            const float2 go = __fmul2_rn(q.vis, v_alpha);
+                            tail[0] = (gate0 ? go.x : 0.f) + (gate1 ? go.y : 0.f);
+                            if (ABS) {
+                                tail[1] = fabsf(gx.x) + fabsf(gx.y);
+                                tail[2] = fabsf(gy.x) + fabsf(gy.y);
+                            }
+                        } else {
+                            const float n01 = nvs.x + nvs.y;
+                            const float2 nd = __fmul2_rn(nvs, q.dy);
+                            const float2 ndd = __fmul2_rn(nd, q.dy);
+                            const float sy = nd.x + nd.y;
+                            const float sx = q.dx * n01;
+                            vals[CDIM + 0] = q.dx * sx;
+                            vals[CDIM + 1] = q.dx * sy;
+                            vals[CDIM + 2] = ndd.x + ndd.y;
+                            vals[CDIM + 3] = sx;
+                            vals[CDIM + 4] = sy;
+                            tail[0] = n01;
+                        }
+                    };
+                    float red[NGRP][16], tp[8];
+                    {
+                        float va[NGRP * 8], vb[NGRP * 8], ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int k = 0; k < NGRP * 8; ++k) va[k] = vb[k] = 0.f;
+                        phase2(B1, C1, q1, va, ta);  // t1 is further back in the tile's list: it comes first in the walk
+                        phase2(B2, C2, q2, vb, tb);
+#pragma unroll
+                        for (int gi = 0; gi < NGRP; ++gi)
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                red[gi][k] = va[gi * 8 + k];
+                                red[gi][8 + k] = vb[gi * 8 + k];
+                            }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            tp[k] = ABS ? ta[k] : (k == 0 ? ta[0] : (k == 1 ? tb[0] : 0.f));
+                            tp[4 + k] = ABS ? tb[k] : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int gi = 0; gi < NGRP; ++gi) reduce_spread<16>(red[gi], lane);
+                    if (ABS) reduce_spread<8>(tp, lane); else reduce_spread<2>(tp, lane);
+                    float *rec1 = grad_rec + (size_t)__float_as_int(B1.w) * REC, *rec2 = grad_rec + (size_t)__float_as_int(B2.w) * REC;
+                    {
+                        const bool second = slot16 >= 8;
+                        float *rec = second ? rec2 : rec1;
+                        const bool live = (second ? any2 : any1) && pub16;
+#pragma unroll
+                        for (int gi = 0; gi < NGRP; ++gi) {
+                            const uint32_t off = gi * 8 + (slot16 & 7u);
+                            if (live && off < (uint32_t)NMAIN) red_add(rec + off, red[gi][0]);
+                        }
+                    }
+                    if (ABS) {
+                        const bool second = slot8 >= 4;
+                        if ((second ? any2 : any1) && pub8 && (slot8 & 3u) < 3) red_add((second ? rec2 : rec1) + NMAIN + (slot8 & 3u), tp[0]);
+                    } else {
+                        const bool second = (lane & 16u) != 0;
+                        if ((second ? any2 : any1) && (lane & 15u) == 0) red_add((second ? rec2 : rec1) + NMAIN, tp[0]);
+                    }
+                }
+#endif
                 while (m) {
                     const uint32_t t = (uint32_t)(nrec - 1 - c0) - ((uint32_t)__ffs(m) - 1u);
                     m &= m - 1;
