@@ -35,7 +35,7 @@ constexpr int kStages = GSB_STREAM_STAGES;
 #define GSB_SBWD_BLOCKS 7  // (backward, NP = 1; the two-record walk, GSB_BWD_PAIR, asks for 5: the launch caps the CTAs at 5 per SM anyway)
 #endif
 #ifndef GSB_SBWD_PAIR_BLOCKS
-#define GSB_SBWD_PAIR_BLOCKS 5
+#define GSB_SBWD_PAIR_BLOCKS 7  // two-record walk: 68 registers; measured 566 us at 7-8 resident CTAs vs 576 us with 86 registers / 5 CTAs
 #endif
 #ifndef GSB_PRODUCER_SLEEP_NS
 #define GSB_PRODUCER_SLEEP_NS 256  // ring full: the consumers need ~10^3 cycles per stage
@@ -49,8 +49,8 @@ constexpr int kStages = GSB_STREAM_STAGES;
 #ifndef GSB_BWD_PIPELINE
 #define GSB_BWD_PIPELINE 0  // retire record i's sums inside the iteration of record i + 1 (see blend_stream_bwd_kernel); measured SLOWER (761 vs 668 us): off
 #endif
-#ifndef GSB_FWD_PAIR
-#define GSB_FWD_PAIR 1  // forward consumers walk their records two at a time (NP = 1)
+#ifndef GSB_FWD_GROUP
+#define GSB_FWD_GROUP 2  // records a forward consumer warp evaluates per trip (NP = 1); 1: one at a time
 #endif
 #ifndef GSB_BWD_PAIR
 #define GSB_BWD_PAIR 1  // backward walks a warp's records two at a time (NP = 1): see blend_stream_bwd_kernel
@@ -375,48 +375,53 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
                     const uint32_t e = c0 + lane;
                     const uint32_t word = e < nrec ? lds1u(a_stage + e * kRecBytes + 12) : 0u;
                     unsigned m = __ballot_sync(0xffffffffu, (word & hitsel) != 0);
-#if GSB_FWD_PAIR
-                    // two records per trip (NP = 1): their sigma / exp2 chains are independent, only T, the last-contributor word
-                    // and the colour sums pass from the first to the second -- same per-lane arithmetic in the same order
+#if GSB_FWD_GROUP > 1
+                    // GSB_FWD_GROUP records per trip (NP = 1): their sigma / exp2 chains are independent, only T, the
+                    // last-contributor word and the colour sums pass from one record to the next -- same per-lane arithmetic in
+                    // the same order, evaluated as one basic block so that the chains interleave
                     while (NP == 1 && m) {
-                        const uint32_t t1 = c0 + (uint32_t)__ffs(m) - 1u;
-                        m &= m - 1;
-                        const bool two = m != 0;
-                        const uint32_t t2 = two ? c0 + (uint32_t)__ffs(m) - 1u : t1;
-                        m &= m - 1;
-                        const float4 A1 = lds4(a_stage + t1 * kRecBytes), B1 = lds4(a_stage + t1 * kRecBytes + 16);
-                        const float4 A2 = lds4(a_stage + t2 * kRecBytes), B2 = lds4(a_stage + t2 * kRecBytes + 16);
-                        const float4 C1 = lds4(a_stage + t1 * kRecBytes + 32), C2 = lds4(a_stage + t2 * kRecBytes + 32);
-                        struct F1 {
-                            float2 sigma, alpha;
-                        };
-                        auto phase1 = [&](const float4 &A, const float4 &B) {
-                            F1 q;
-                            const float dx = A.x - px[0];
-                            const float2 dy = __fadd2_rn(bc(A.y), npy[0]);
-                            float2 tt = __fmul2_rn(bc(B.z), dy);
-                            const float u = B.x * dx, v = B.y * dx;
+                        constexpr int K = GSB_FWD_GROUP;
+                        uint32_t t[K];
+                        bool have[K];
+#pragma unroll
+                        for (int r = 0; r < K; ++r) {
+                            have[r] = m != 0;
+                            t[r] = have[r] ? c0 + (uint32_t)__ffs(m) - 1u : t[0];
+                            m &= m - 1;
+                        }
+                        float4 A[K], B[K], C4[K];
+#pragma unroll
+                        for (int r = 0; r < K; ++r) {
+                            A[r] = lds4(a_stage + t[r] * kRecBytes);
+                            B[r] = lds4(a_stage + t[r] * kRecBytes + 16);
+                        }
+#pragma unroll
+                        for (int r = 0; r < K; ++r) C4[r] = lds4(a_stage + t[r] * kRecBytes + 32);
+                        float2 sigma[K], alpha[K];
+#pragma unroll
+                        for (int r = 0; r < K; ++r) {
+                            const float dx = A[r].x - px[0];
+                            const float2 dy = __fadd2_rn(bc(A[r].y), npy[0]);
+                            float2 tt = __fmul2_rn(bc(B[r].z), dy);
+                            const float u = B[r].x * dx, v = B[r].y * dx;
                             tt = __fmul2_rn(dy, tt);
                             float2 uu = __ffma2_rn(bc(dx), bc(u), tt);
                             uu = __fmul2_rn(uu, bc(0.5f));
-                            q.sigma = __ffma2_rn(dy, bc(v), uu);
-                            const float2 ee = __fmul2_rn(q.sigma, bc(kNegLog2e));
-                            const float2 ov = __fmul2_rn(bc(A.z), make_float2(exp2f(ee.x), exp2f(ee.y)));
-                            q.alpha = make_float2(fminf(kAlphaMax, ov.x), fminf(kAlphaMax, ov.y));
-                            return q;
-                        };
-                        const F1 q1 = phase1(A1, B1);
-                        F1 q2 = phase1(A2, B2);
-                        // no second record: alpha = 0 fails the 1/255 test for both pixels, the record is a no-op
-                        q2.alpha.x = two ? q2.alpha.x : 0.f;
-                        q2.alpha.y = two ? q2.alpha.y : 0.f;
-                        auto phase2 = [&](const float4 &A, const float4 &C4, const F1 &q) {
-                            const float cs[4] = {C4.x, C4.y, C4.z, C4.w};
-                            const uint32_t wt = __float_as_uint(A.w);
-                            const float2 next_T = __fmul2_rn(T[0], __ffma2_rn(q.alpha, bc(-1.f), bc(1.f)));
-                            const bool ok0 = !(q.sigma.x < 0.f || q.alpha.x < kAlphaMin), ok1 = !(q.sigma.y < 0.f || q.alpha.y < kAlphaMin);
+                            sigma[r] = __ffma2_rn(dy, bc(v), uu);
+                            const float2 ee = __fmul2_rn(sigma[r], bc(kNegLog2e));
+                            const float2 ov = __fmul2_rn(bc(A[r].z), make_float2(exp2f(ee.x), exp2f(ee.y)));
+                            // no such record: alpha = 0 fails the 1/255 test for both pixels, the record is a no-op
+                            alpha[r] = make_float2((r == 0 || have[r]) ? fminf(kAlphaMax, ov.x) : 0.f,
+                                                   (r == 0 || have[r]) ? fminf(kAlphaMax, ov.y) : 0.f);
+                        }
+#pragma unroll
+                        for (int r = 0; r < K; ++r) {
+                            const float cs[4] = {C4[r].x, C4[r].y, C4[r].z, C4[r].w};
+                            const uint32_t wt = __float_as_uint(A[r].w);
+                            const float2 next_T = __fmul2_rn(T[0], __ffma2_rn(alpha[r], bc(-1.f), bc(1.f)));
+                            const bool ok0 = !(sigma[r].x < 0.f || alpha[r].x < kAlphaMin), ok1 = !(sigma[r].y < 0.f || alpha[r].y < kAlphaMin);
                             const bool take0 = ok0 && !(next_T.x <= kTStop), take1 = ok1 && !(next_T.y <= kTStop);
-                            float2 vis = __fmul2_rn(q.alpha, T[0]);
+                            float2 vis = __fmul2_rn(alpha[r], T[0]);
                             vis.x = take0 ? vis.x : 0.f;
                             vis.y = take1 ? vis.y : 0.f;
 #pragma unroll
@@ -425,9 +430,7 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
                             T[0].y = take1 ? next_T.y : (ok1 ? -fabsf(T[0].y) : T[0].y);
                             cur0[0] = take0 ? wt : cur0[0];
                             cur1[0] = take1 ? wt : cur1[0];
-                        };
-                        phase2(A1, C1, q1);
-                        phase2(A2, C2, q2);
+                        }
                     }
 #endif
                     while (m) {
@@ -674,7 +677,8 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                     };
                     auto phase1 = [&](const float4 &A, const float4 &B, bool live) {
                         P1 q;
-                        const int32_t idx = (int32_t)(__float_as_uint(A.w) >> 4);
+                        // (no such record: an index beyond every pixel's last contributor makes both pixels invalid)
+                        const int32_t idx = live ? (int32_t)(__float_as_uint(A.w) >> 4) : INT_MAX;
                         q.dx = A.x - px[0];
                         q.dy = __fadd2_rn(bc(A.y), npy[0]);
                         float2 tt = __fmul2_rn(bc(B.z), q.dy);
@@ -688,8 +692,8 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                         q.vis = make_float2(exp2f(ee.x), exp2f(ee.y));
                         q.ov = __fmul2_rn(bc(A.z), q.vis);
                         q.alpha = make_float2(fminf(kAlphaMax, q.ov.x), fminf(kAlphaMax, q.ov.y));
-                        q.valid0 = live && idx <= bin0[0] && !(sigma.x < 0.f || q.alpha.x < kAlphaMin);
-                        q.valid1 = live && idx <= bin1[0] && !(sigma.y < 0.f || q.alpha.y < kAlphaMin);
+                        q.valid0 = idx <= bin0[0] && !(sigma.x < 0.f || q.alpha.x < kAlphaMin);
+                        q.valid1 = idx <= bin1[0] && !(sigma.y < 0.f || q.alpha.y < kAlphaMin);
                         return q;
                     };
                     const P1 q1 = phase1(A1, B1, true), q2 = phase1(A2, B2, two);
@@ -780,22 +784,20 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                     for (int gi = 0; gi < NGRP; ++gi) reduce_spread<16>(red[gi], lane);
                     if (ABS) reduce_spread<8>(tp, lane); else reduce_spread<2>(tp, lane);
                     float *rec1 = grad_rec + (size_t)__float_as_int(B1.w) * REC, *rec2 = grad_rec + (size_t)__float_as_int(B2.w) * REC;
+                    // (a record none of whose pixels is valid -- or the stand-in for a missing second record -- has all-zero sums:
+                    // adding them is harmless and keeps the publishing lanes free of warp-uniform predicates)
                     {
-                        const bool second = slot16 >= 8;
-                        float *rec = second ? rec2 : rec1;
-                        const bool live = (second ? any2 : any1) && pub16;
+                        float *rec = slot16 >= 8 ? rec2 : rec1;
 #pragma unroll
                         for (int gi = 0; gi < NGRP; ++gi) {
                             const uint32_t off = gi * 8 + (slot16 & 7u);
-                            if (live && off < (uint32_t)NMAIN) red_add(rec + off, red[gi][0]);
+                            if (pub16 && off < (uint32_t)NMAIN) red_add(rec + off, red[gi][0]);
                         }
                     }
                     if (ABS) {
-                        const bool second = slot8 >= 4;
-                        if ((second ? any2 : any1) && pub8 && (slot8 & 3u) < 3) red_add((second ? rec2 : rec1) + NMAIN + (slot8 & 3u), tp[0]);
+                        if (pub8 && (slot8 & 3u) < 3) red_add((slot8 >= 4 ? rec2 : rec1) + NMAIN + (slot8 & 3u), tp[0]);
                     } else {
-                        const bool second = (lane & 16u) != 0;
-                        if ((second ? any2 : any1) && (lane & 15u) == 0) red_add((second ? rec2 : rec1) + NMAIN, tp[0]);
+                        if ((lane & 15u) == 0) red_add(((lane & 16u) ? rec2 : rec1) + NMAIN, tp[0]);
                     }
                 }
 #endif
@@ -1005,8 +1007,10 @@ static int bwd_t(const BlendGeom &G, const float *backgrounds, const uint8_t *ma
                  bool absgrad, cudaStream_t s) {
     const uint32_t T = G.C * G.tw * G.th;
     const float4 *st = reinterpret_cast<const float4 *>(blend_stream);
-    // measured on B200 at the headline size (tools/gpu_r2_visit29.sh): 8 resident CTAs 667 us, 6: 663, 5: 650, 4: 691, 3: 823
-    const size_t pad = occupancy_pad("GSB200_SBWD_CTAS", sizeof(StreamShared), 5);
+    // measured on B200 at the headline size.  One record per trip (tools/gpu_r2_visit29.sh): 8 resident CTAs 667 us, 6: 663,
+    // 5: 650, 4: 691, 3: 823 -- the long tiles' serial chains wanted fewer co-residents.  Two records per trip
+    // (tools/gpu_r2_visit34.sh): 5: 577 us, 6: 568, 8: 566 -- the chains are half as long, no cap
+    const size_t pad = occupancy_pad("GSB200_SBWD_CTAS", sizeof(StreamShared), GSB_BWD_PAIR ? 0 : 5);
 #define GSB_BWD_LAUNCH(NPV, ABSV)                                                                                     \
     do {                                                                                                              \
         if (pad > 0)                                                                                                  \
