@@ -670,12 +670,15 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                     const float4 A1 = lds4(a_stage + t1 * kRecBytes), B1 = lds4(a_stage + t1 * kRecBytes + 16);
                     const float4 A2 = lds4(a_stage + t2 * kRecBytes), B2 = lds4(a_stage + t2 * kRecBytes + 16);
                     const float4 C1 = lds4(a_stage + t1 * kRecBytes + 32), C2 = lds4(a_stage + t2 * kRecBytes + 32);
+                    // Validity is folded into the operands where it is decided: an invalid pixel continues with alpha = 0 -- then
+                    // 1 / (alpha - 1) = -1 exactly, T * 1 = T and fac = 0 * T = 0, i.e. the record is the identity for its T and B
+                    // -- and a pixel outside the gate (invalid, or opacity * vis clamped at 0.999) with opacity * vis = 0, hence
+                    // -v_sigma = 0.  No predicate outlives the vote, no select follows it.
                     struct P1 {
                         float dx, u, v;
-                        float2 dy, vis, ov, alpha;
-                        bool valid0, valid1;
+                        float2 dy, gvis, gov, alpha;
                     };
-                    auto phase1 = [&](const float4 &A, const float4 &B, bool live) {
+                    auto phase1 = [&](const float4 &A, const float4 &B, bool live, bool &any) {
                         P1 q;
                         // (no such record: an index beyond every pixel's last contributor makes both pixels invalid)
                         const int32_t idx = live ? (int32_t)(__float_as_uint(A.w) >> 4) : INT_MAX;
@@ -689,16 +692,20 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                         uu = __fmul2_rn(uu, bc(0.5f));
                         const float2 sigma = __ffma2_rn(q.dy, bc(q.v), uu);
                         const float2 ee = __fmul2_rn(sigma, bc(kNegLog2e));
-                        q.vis = make_float2(exp2f(ee.x), exp2f(ee.y));
-                        q.ov = __fmul2_rn(bc(A.z), q.vis);
-                        q.alpha = make_float2(fminf(kAlphaMax, q.ov.x), fminf(kAlphaMax, q.ov.y));
-                        q.valid0 = idx <= bin0[0] && !(sigma.x < 0.f || q.alpha.x < kAlphaMin);
-                        q.valid1 = idx <= bin1[0] && !(sigma.y < 0.f || q.alpha.y < kAlphaMin);
+                        const float2 vis = make_float2(exp2f(ee.x), exp2f(ee.y));
+                        const float2 ov = __fmul2_rn(bc(A.z), vis);
+                        const float2 alpha = make_float2(fminf(kAlphaMax, ov.x), fminf(kAlphaMax, ov.y));
+                        const bool valid0 = idx <= bin0[0] && sigma.x >= 0.f && alpha.x >= kAlphaMin;
+                        const bool valid1 = idx <= bin1[0] && sigma.y >= 0.f && alpha.y >= kAlphaMin;
+                        any = __any_sync(0xffffffffu, valid0 || valid1);
+                        q.alpha = make_float2(valid0 ? alpha.x : 0.f, valid1 ? alpha.y : 0.f);
+                        const bool gate0 = valid0 && ov.x <= kAlphaMax, gate1 = valid1 && ov.y <= kAlphaMax;
+                        q.gov = make_float2(gate0 ? ov.x : 0.f, gate1 ? ov.y : 0.f);
+                        q.gvis = make_float2(gate0 ? vis.x : 0.f, gate1 ? vis.y : 0.f);  // (ABS / non-moment form only)
                         return q;
                     };
-                    const P1 q1 = phase1(A1, B1, true), q2 = phase1(A2, B2, two);
-                    const bool any1 = __any_sync(0xffffffffu, q1.valid0 || q1.valid1);
-                    const bool any2 = __any_sync(0xffffffffu, q2.valid0 || q2.valid1);
+                    bool any1, any2;
+                    const P1 q1 = phase1(A1, B1, true, any1), q2 = phase1(A2, B2, two, any2);
                     if (!(any1 || any2)) continue;
                     // per-thread sums of one record (the arithmetic of the single-record loop below); advances T and B
                     auto phase2 = [&](const float4 &B, const float4 &C4, const P1 &q, float *vals, float *tail) {
@@ -707,11 +714,8 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                         const float2 nra = make_float2(1.f / nom.x, 1.f / nom.y);
                         const float2 ra = make_float2(-nra.x, -nra.y);
                         const float2 Tn = __fmul2_rn(T[0], ra);
-                        T[0].x = q.valid0 ? Tn.x : T[0].x;
-                        T[0].y = q.valid1 ? Tn.y : T[0].y;
-                        float2 fac = __fmul2_rn(q.alpha, Tn);
-                        fac.x = q.valid0 ? fac.x : 0.f;
-                        fac.y = q.valid1 ? fac.y : 0.f;
+                        T[0] = Tn;
+                        const float2 fac = __fmul2_rn(q.alpha, Tn);
                         float2 Acv = __fmul2_rn(bc(cs[0]), v_c[0][0]);
 #pragma unroll
                         for (int k = 1; k < CDIM; ++k) Acv = __ffma2_rn(bc(cs[k]), v_c[0][k], Acv);
@@ -724,10 +728,7 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                         }
                         v_alpha = __ffma2_rn(__fmul2_rn(Tfin[0], ra), v_a[0], v_alpha);
                         if (bg) v_alpha = __ffma2_rn(__fmul2_rn(Tfin[0], nra), bg_dot[0], v_alpha);
-                        const bool gate0 = q.valid0 && q.ov.x <= kAlphaMax, gate1 = q.valid1 && q.ov.y <= kAlphaMax;
-                        float2 nvs = __fmul2_rn(q.ov, v_alpha);  // -v_sigma
-                        nvs.x = gate0 ? nvs.x : 0.f;
-                        nvs.y = gate1 ? nvs.y : 0.f;
+                        const float2 nvs = __fmul2_rn(q.gov, v_alpha);  // -v_sigma
                         if (ABS || !GSB_BWD_MOMENTS) {
                             const float2 hs = __fmul2_rn(nvs, bc(0.5f));
                             const float2 ga = __fmul2_rn(__fmul2_rn(hs, bc(q.dx)), bc(q.dx));
@@ -740,8 +741,8 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
                             vals[CDIM + 2] = -gc.x - gc.y;
                             vals[CDIM + 3] = -gx.x - gx.y;
                             vals[CDIM + 4] = -gy.x - gy.y;
-                            const float2 go = __fmul2_rn(q.vis, v_alpha);
-                            tail[0] = (gate0 ? go.x : 0.f) + (gate1 ? go.y : 0.f);
+                            const float2 go = __fmul2_rn(q.gvis, v_alpha);
+                            tail[0] = go.x + go.y;
                             if (ABS) {
                                 tail[1] = fabsf(gx.x) + fabsf(gx.y);
                                 tail[2] = fabsf(gy.x) + fabsf(gy.y);
@@ -783,22 +784,17 @@ blend_stream_bwd_kernel(BlendGeom G, const float *__restrict__ backgrounds, cons
 #pragma unroll
                     for (int gi = 0; gi < NGRP; ++gi) reduce_spread<16>(red[gi], lane);
                     if (ABS) reduce_spread<8>(tp, lane); else reduce_spread<2>(tp, lane);
-                    float *rec1 = grad_rec + (size_t)__float_as_int(B1.w) * REC, *rec2 = grad_rec + (size_t)__float_as_int(B2.w) * REC;
                     // (a record none of whose pixels is valid -- or the stand-in for a missing second record -- has all-zero sums:
-                    // adding them is harmless and keeps the publishing lanes free of warp-uniform predicates)
-                    {
-                        float *rec = slot16 >= 8 ? rec2 : rec1;
+                    // adding them is harmless and keeps the publishing lanes free of warp-uniform predicates.)  After the first
+                    // halving step the upper half-warp holds the second record's values in every butterfly: one select of the id
+                    float *rec = grad_rec + (size_t)((lane & 16u) ? __float_as_int(B2.w) : __float_as_int(B1.w)) * REC;
 #pragma unroll
-                        for (int gi = 0; gi < NGRP; ++gi) {
-                            const uint32_t off = gi * 8 + (slot16 & 7u);
-                            if (pub16 && off < (uint32_t)NMAIN) red_add(rec + off, red[gi][0]);
-                        }
-                    }
-                    if (ABS) {
-                        if (pub8 && (slot8 & 3u) < 3) red_add((slot8 >= 4 ? rec2 : rec1) + NMAIN + (slot8 & 3u), tp[0]);
-                    } else {
-                        if ((lane & 15u) == 0) red_add(((lane & 16u) ? rec2 : rec1) + NMAIN, tp[0]);
-                    }
+                    for (int gi = 0; gi < NGRP; ++gi)
+                        red_add_if(rec + gi * 8 + (slot16 & 7u), red[gi][0], pub16 && gi * 8 + (slot16 & 7u) < (uint32_t)NMAIN);
+                    if (ABS)
+                        red_add_if(rec + NMAIN + (slot8 & 3u), tp[0], pub8 && (slot8 & 3u) < 3);
+                    else
+                        red_add_if(rec + NMAIN, tp[0], (lane & 15u) == 0);
                 }
 #endif
                 while (m) {

@@ -68,6 +68,12 @@ __device__ __forceinline__ void red_add(float *addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
+// predicated form: no branch around the reduction (the address is computed by every lane)
+__device__ __forceinline__ void red_add_if(float *addr, float a, bool on) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p red.global.add.f32 [%0], %1;\n}" ::"l"(addr), "f"(a), "r"((uint32_t)on)
+                 : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
