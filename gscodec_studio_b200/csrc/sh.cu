@@ -883,6 +883,17 @@ sh_view_split_bwd_kernel(uint32_t C, uint32_t N, uint32_t RF, const float *__res
         }
     }
     if (RF == 0) return;
+    // a block none of whose Gaussians is visible in any view (71 % of the Gaussians of the headline frame are culled, and
+    // neighbours in memory are neighbours in space): its slab is all zeros -- plain 16-byte stores, no staging
+    if (!__syncthreads_or(any)) {
+        const uint32_t row0z = blockIdx.x * kSplitThreads;
+        const uint32_t totalz = min((uint32_t)kSplitThreads, N - row0z) * RF;
+        float *dstz = v_shN + (size_t)row0z * RF;
+        for (uint32_t v = tid; v < totalz / 4; v += kSplitThreads) stg4(dstz + (size_t)v * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        const uint32_t iz = (totalz / 4) * 4 + tid;
+        if (iz < totalz) dstz[iz] = 0.f;
+        return;
+    }
     const uint32_t stride = RF | 1u;  // odd: the per-thread row writes below are bank-conflict free
     if (DEG > 0) {
 #pragma unroll
