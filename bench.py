@@ -39,12 +39,12 @@ sys.path.insert(0, ROOT)
 W_IMG, H_IMG = 1920, 1080
 SH_C0 = 0.2820947917738781
 METRIC = "Mpix/s fwd+bwd @1M splats 1920x1080 w/ quant-sim"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of blend_stream_fwd_kernel<3,1> (27.81 + 76.72 MB: the write
-# is the record stream the backward consumes) and blend_stream_bwd_kernel<3,1,0> (128.29 + 6.51 MB), from one
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of blend_stream_fwd_kernel<3,1> (28.37 + 81.96 MB: the write
+# is the record stream the backward consumes) and blend_stream_bwd_kernel<3,1,0> (129.08 + 8.42 MB), from one
 # `ncu --set full` capture of tools/gpu_stage_timing.py at the headline size -- a constant from that capture, not
 # measured in this run (ncu cannot run inside a timed bench); the roofline object names its source
-NCU_DRAM_TRAFFIC_BYTES = int((28.69 + 82.04 + 128.28 + 5.88) * 1e6)  # gpurun_out/r2v22_blend_stream.ncu-rep
-NCU_TRAFFIC_SOURCE = "profiles/r02_blend_stream_ncu.md (ncu --set full, one launch per kernel, headline size)"
+NCU_DRAM_TRAFFIC_BYTES = int((28.37 + 81.96 + 129.08 + 8.42) * 1e6)  # gpurun_out/r2v41_blend_stream.ncu-rep
+NCU_TRAFFIC_SOURCE = "profiles/r02c_blend_pair_walk_ncu.md (ncu --set full, one launch per kernel, headline size)"
 
 
 def build_workload(rank: int, world: int, scene_grid: int):

@@ -49,6 +49,30 @@ def _camera_positions(viewmats: Tensor) -> Tensor:
     return -(R.transpose(1, 2) @ t[..., None])[..., 0]
 
 
+_colour_streams: Dict = {}
+
+
+def _colour_stream(device) -> Optional["torch.cuda.Stream"]:
+    """Side stream of the single-GPU colour stage (one per device), or None when disabled (GSB200_COLOR_STREAM=0)
+    or not on a CUDA device.  The colour stage needs the projection's radii and nothing of the tile intersection, and
+    the blend needs both: on its own stream the HBM-bound colour kernel runs while the intersection kernels sit in
+    their atomics -- and, because autograd runs a node's backward on its forward's stream, the colour backward runs
+    beside the projection backward."""
+    import os
+
+    if device.type != "cuda" or os.environ.get("GSB200_COLOR_STREAM", "1") == "0":
+        return None
+    st = _colour_streams.get(device.index)
+    if st is None:
+        st = _colour_streams[device.index] = torch.cuda.Stream(device=device)
+        # the SH parameters' AccumulateGrad nodes live on the main stream and receive their gradient from the side
+        # stream: intended (the engine synchronises the two), so silence torch's once-per-process notice about it
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
+    return st
+
+
 _inert_rows: Dict = {}
 
 
@@ -289,6 +313,16 @@ def rasterization(
     # distributed mode, the colour all-gather keeps overlapping with it.
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
+    # single-GPU SH colours from per-Gaussian coefficients: on a side stream that forks here, after the projection
+    # and BEFORE the intersection kernels are enqueued, and joins the main stream in front of the blend
+    side, fork = None, None
+    if (sh_degree is not None and not owner_render and not packed and pending_colors is None and not owner_colors
+            and not pull_colors and (sh_pair is not None or colors.dim() == 3)):
+        side = _colour_stream(means.device)
+        if side is not None:
+            campos_side = _camera_positions(viewmats) if rigid_viewmats else torch.inverse(viewmats)[:, :3, 3]
+            fork = torch.cuda.Event()
+            fork.record(torch.cuda.current_stream(means.device))
     isect_pending = _isect_tiles_begin(
         means2d, radii, depths, tile_size, tile_width, tile_height,
         packed=packed, n_cameras=C, camera_ids=camera_ids, gaussian_ids=gaussian_ids,
@@ -303,6 +337,15 @@ def rasterization(
             colors = colors[gaussian_ids] if colors.dim() == 2 else colors[camera_ids, gaussian_ids]
         else:
             colors = colors.expand(C, -1, -1) if colors.dim() == 2 else colors
+    elif side is not None:
+        main = torch.cuda.current_stream(means.device)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            if sh_pair is not None:
+                colors = view_colors_from_sh_split(sh_degree, means, campos_side, sh_pair[0], sh_pair[1], radii)
+            else:
+                colors = view_colors_from_sh(sh_degree, means, campos_side, colors, radii)
+        colors.record_stream(main)  # allocated from the side stream's pool, read by the blend on the main stream
     else:
         campos = _camera_positions(viewmats) if rigid_viewmats else torch.inverse(viewmats)[:, :3, 3]
         if sh_pair is not None:
@@ -327,6 +370,8 @@ def rasterization(
     # the host waits for the intersection count only now: the colour kernels above are already enqueued behind the
     # scatter + sort, so the device has work for the whole wait and for the launch of the blend that follows
     tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_pending.finish()
+    if side is not None:
+        torch.cuda.current_stream(means.device).wait_stream(side)
 
     if render_mode in ["RGB+D", "RGB+ED"]:
         colors = torch.cat((colors, depths[..., None]), dim=-1)
