@@ -28,6 +28,15 @@ constexpr int kStageRecs = 64;  // records per pipeline stage
 #define GSB_STREAM_STAGES 6
 #endif
 constexpr int kStages = GSB_STREAM_STAGES;
+// The forward's producer hands records to the consumers in smaller stages than the backward's bulk copies: a consumer can
+// start on a stage only when the producer has completed it, and half of the tiles hold fewer than 128 records
+#ifndef GSB_FWD_STAGE_RECS
+#define GSB_FWD_STAGE_RECS 64
+#endif
+constexpr int kFStageRecs = GSB_FWD_STAGE_RECS;
+constexpr int kFStages = kStages * kStageRecs / kFStageRecs;  // same ring capacity
+constexpr int kMaxStages = kFStages > kStages ? kFStages : kStages;
+static_assert(kFStageRecs >= 32 && kFStageRecs <= 64 && (kStages * kStageRecs) % kFStageRecs == 0, "a chunk of 32 candidates completes at most one stage");
 #ifndef GSB_SFWD_BLOCKS
 #define GSB_SFWD_BLOCKS 6  // minimum resident CTAs per SM the register allocator must allow (forward, NP = 1)
 #endif
@@ -159,9 +168,9 @@ __device__ __forceinline__ uint32_t blocks_hit_mask(float mx, float my, float a,
 
 struct StreamShared {
     float4 rec[kStages * kStageRecs * 3];
-    unsigned long long full[kStages];
-    unsigned long long empty[kStages];
-    int count[kStages];
+    unsigned long long full[kMaxStages];
+    unsigned long long empty[kMaxStages];
+    int count[kMaxStages];
     int done;        // consumer warps that need no more records (forward)
     int last_stage;  // last stage in which any pixel of the tile took a contribution (forward)
     int emitted;     // records the producer emitted (forward)
@@ -223,7 +232,7 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
     const uint32_t a_full = (uint32_t)__cvta_generic_to_shared(S.full), a_empty = (uint32_t)__cvta_generic_to_shared(S.empty);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kFStages; ++s) {
             mbar_init(a_full + 8 * s, 32);      // every producer lane arrives
             mbar_init(a_empty + 8 * s, NCONS);  // lane 0 of every consumer warp arrives
         }
@@ -275,10 +284,10 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
         auto ids = [&](uint32_t at) { return at + lane < n ? __ldg(flatten_ids + range_start + at + lane) : -1; };
 
         uint32_t total = 0;            // records emitted so far
-        uint32_t acquired = kStages;   // stages [0, acquired) may be written (the first ring round is free)
+        uint32_t acquired = kFStages;   // stages [0, acquired) may be written (the first ring round is free)
         auto acquire_to = [&](uint32_t stage) {
             while (acquired <= stage) {
-                mbar_wait<GSB_PRODUCER_SLEEP_NS>(a_empty + 8 * (acquired % kStages), ((acquired / kStages) - 1) & 1);
+                mbar_wait<GSB_PRODUCER_SLEEP_NS>(a_empty + 8 * (acquired % kFStages), ((acquired / kFStages) - 1) & 1);
                 ++acquired;
             }
         };
@@ -298,10 +307,10 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
             const unsigned ballot = __ballot_sync(0xffffffffu, hitmask != 0);
             const uint32_t cnt = __popc(ballot);
             if (cnt) {
-                acquire_to((total + cnt - 1) / kStageRecs);
+                acquire_to((total + cnt - 1) / kFStageRecs);
                 if (hitmask) {
                     const uint32_t pos = total + __popc(ballot & lt_mask);
-                    const uint32_t slot = pos % (kStages * kStageRecs);
+                    const uint32_t slot = pos % (kFStages * kFStageRecs);
                     const float4 q0 = make_float4(cur.xy.x, cur.xy.y, cur.o, __uint_as_float(((base + lane) << 4) | hitmask));
                     const float4 q1 = make_float4(cur.a, cur.b, cur.c, __int_as_float(cur.g));
                     const float4 q2 = make_float4(cur.col[0], cur.col[1], cur.col[2], cur.col[3]);
@@ -316,25 +325,25 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
                         out[2] = q2;
                     }
                 }
-                const uint32_t st_old = total / kStageRecs;
+                const uint32_t st_old = total / kFStageRecs;
                 total += cnt;
-                if (total / kStageRecs != st_old) {  // stage st_old is complete: publish it
-                    if (lane == 0) S.count[st_old % kStages] = kStageRecs;
+                if (total / kFStageRecs != st_old) {  // stage st_old is complete: publish it
+                    if (lane == 0) S.count[st_old % kFStages] = kFStageRecs;
                     __syncwarp();
-                    mbar_arrive(a_full + 8 * (st_old % kStages));
+                    mbar_arrive(a_full + 8 * (st_old % kFStages));
                 }
             }
             cur = nxt;
         }
         // last (possibly empty) stage carries the end flag
-        const uint32_t st_last = total / kStageRecs;
+        const uint32_t st_last = total / kFStageRecs;
         acquire_to(st_last);
         if (lane == 0) {
-            S.count[st_last % kStages] = (int)(total % kStageRecs) | (int)kEndFlag;
+            S.count[st_last % kFStages] = (int)(total % kFStageRecs) | (int)kEndFlag;
             S.emitted = (int)total;
         }
         __syncwarp();
-        mbar_arrive(a_full + 8 * (st_last % kStages));
+        mbar_arrive(a_full + 8 * (st_last % kFStages));
     } else {
         // ------------------------------------------------------------------ consumer warps
         uint32_t pj[NP], pi0[NP];
@@ -362,15 +371,15 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
         int my_last_stage = -1;
 
         for (uint32_t k = 0;; ++k) {
-            const uint32_t slot = k % kStages;
-            mbar_wait<GSB_CONSUMER_SLEEP_NS>(a_full + 8 * slot, (k / kStages) & 1);
+            const uint32_t slot = k % kFStages;
+            mbar_wait<GSB_CONSUMER_SLEEP_NS>(a_full + 8 * slot, (k / kFStages) & 1);
             const int cf = *reinterpret_cast<volatile int *>(&S.count[slot]);
             const uint32_t nrec = (uint32_t)cf & 0xffu;
             if (!warp_done) {
                 uint32_t cur_sig = 0;  // changes iff some pixel of this thread takes a Gaussian of this stage
 #pragma unroll
                 for (uint32_t p = 0; p < NP; ++p) cur_sig += cur0[p] + cur1[p];
-                const uint32_t a_stage = a_rec + slot * (kStageRecs * kRecBytes);
+                const uint32_t a_stage = a_rec + slot * (kFStageRecs * kRecBytes);
                 for (uint32_t c0 = 0; c0 < nrec; c0 += 32) {
                     const uint32_t e = c0 + lane;
                     const uint32_t word = e < nrec ? lds1u(a_stage + e * kRecBytes + 12) : 0u;
@@ -520,7 +529,7 @@ blend_stream_fwd_kernel(BlendGeom G, const float2 *__restrict__ means2d, const f
         if (atomicAdd(&S.finished, 1) == (int)NCONS) {
             __threadfence_block();
             const int emitted = *reinterpret_cast<volatile int *>(&S.emitted), last = *reinterpret_cast<volatile int *>(&S.last_stage);
-            tile_counts[ct] = min(emitted, (last + 1) * kStageRecs);
+            tile_counts[ct] = min(emitted, (last + 1) * kFStageRecs);
         }
     }
 }
