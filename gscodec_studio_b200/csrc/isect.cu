@@ -198,6 +198,108 @@ isect_scatter_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ c
     });
 }
 
+// ---- CTA-private tile histograms (opt-in, where the histogram of ALL tiles fits a CTA's shared memory) ---------------
+// The two kernels above are bound by L2 atomics: one RED per intersection in the count pass and one RETURNING atomic per
+// intersection in the scatter pass (32 + 75 us at the headline size, I = 4 M; 80 MB of traffic would take 12 us).  Here a
+// CTA owns the same Gaussians in BOTH passes and keeps a histogram of all C x tiles counters in shared
+// memory:
+//   count  : shared-memory atomics; the CTA's row is stored to global memory (coalesced) and its NON-ZERO counts are added
+//            to the replica (CTA mod 32) of the global histogram -- the scan kernels downstream are unchanged;
+//   scatter: the CTA reloads its row and claims a contiguous piece of every tile it touches with ONE returning atomic per
+//            (CTA, tile) pair, then hands out the slots of that piece through shared-memory atomics.
+// Global atomics per pass: the number of non-zero (CTA, tile) pairs instead of I.  Which CTA's piece comes first inside a
+// tile is not deterministic, like the slot order before: the per-tile sort that follows orders the unique (depth, id) keys.
+constexpr int kPrivThreads = 512;
+constexpr uint32_t kPrivMaxTiles = 24576;  // 96 KB of counters: two CTAs per SM
+
+// Which Gaussians a CTA owns (the same in both passes): groups of 32 consecutive ones -- the tile walk is warp-cooperative --
+// dealt round-robin to the CTAs and then to their warps.  Contiguous chunks were measured first and were SLOWER than the
+// global-atomic kernels (count 62 -> 128 us): neighbours in memory are neighbours in space, so a few CTAs owned all the
+// large foreground Gaussians.
+#define GSB_PRIVATE_GROUPS(j, n) \
+    for (uint32_t j = blockIdx.x + gridDim.x * (threadIdx.x >> 5); j * 32u < (n); j += gridDim.x * (kPrivThreads / 32))
+
+__global__ void __launch_bounds__(kPrivThreads)
+isect_count_private_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids, const float *__restrict__ means2d,
+                           const int32_t *__restrict__ radii, float ts, uint32_t tw, uint32_t th, uint32_t total_tiles,
+                           int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ tile_counts, int32_t *__restrict__ rows) {
+    extern __shared__ int32_t s_hist[];
+    for (uint32_t t = threadIdx.x; t < total_tiles; t += kPrivThreads) s_hist[t] = 0;
+    __syncthreads();
+    const uint32_t n_tiles = tw * th, end = n;
+    GSB_PRIVATE_GROUPS(j, n) {
+        const uint32_t i = j * 32u + (threadIdx.x & 31u);
+        TileBox b = {0, 0, 0, 0};
+        uint32_t cam = 0;
+        bool has = false;
+        if (i < end) {
+            const int32_t r = radii[i];
+            int32_t tiles = 0;
+            if (r > 0) {
+                const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + i);
+                b = tile_box(m.x, m.y, (float)r, ts, tw, th);
+                tiles = (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0));  // (isect_tiles.cu:73-76)
+                has = b.x1 > b.x0 && b.y1 > b.y0;
+                cam = camera_ids ? (uint32_t)camera_ids[i] : i / per_cam;
+            }
+            tiles_per_gauss[i] = tiles;
+        }
+        for_each_tile_coop(has, b, tw, [&](int src, uint32_t tile, bool on) {
+            const uint32_t c = __shfl_sync(0xffffffffu, cam, src);
+            if (on) atomicAdd(&s_hist[c * n_tiles + tile], 1);
+        });
+    }
+    __syncthreads();
+    int32_t *mine = tile_counts + (size_t)(blockIdx.x % GSB200_ISECT_REPLICAS) * total_tiles;
+    int32_t *row = rows + (size_t)blockIdx.x * total_tiles;
+    for (uint32_t t = threadIdx.x; t < total_tiles; t += kPrivThreads) {
+        const int32_t c = s_hist[t];
+        row[t] = c;
+        if (c != 0) atomicAdd(mine + t, c);
+    }
+}
+
+__global__ void __launch_bounds__(kPrivThreads)
+isect_scatter_private_kernel(uint32_t n, uint32_t per_cam, const int64_t *__restrict__ camera_ids, const float *__restrict__ means2d,
+                             const int32_t *__restrict__ radii, const float *__restrict__ depths, float ts, uint32_t tw, uint32_t th,
+                             uint32_t total_tiles, int32_t *__restrict__ tile_cursor, const int32_t *__restrict__ rows,
+                             uint64_t *__restrict__ bucket, int64_t capacity) {
+    extern __shared__ int32_t s_hist[];  // here: the next free slot of this CTA's piece of every tile
+    int32_t *mine = tile_cursor + (size_t)(blockIdx.x % GSB200_ISECT_REPLICAS) * total_tiles;  // same replica as in the count pass
+    const int32_t *row = rows + (size_t)blockIdx.x * total_tiles;
+    for (uint32_t t = threadIdx.x; t < total_tiles; t += kPrivThreads) {
+        const int32_t c = row[t];
+        s_hist[t] = c != 0 ? atomicAdd(mine + t, c) : 0;
+    }
+    __syncthreads();
+    const uint32_t n_tiles = tw * th, end = n;
+    GSB_PRIVATE_GROUPS(j, n) {
+        const uint32_t i = j * 32u + (threadIdx.x & 31u);
+        TileBox b = {0, 0, 0, 0};
+        uint32_t cam = 0, depth_bits = 0;
+        bool has = false;
+        if (i < end) {
+            const int32_t r = radii[i];
+            if (r > 0) {
+                const float2 m = __ldg(reinterpret_cast<const float2 *>(means2d) + i);
+                b = tile_box(m.x, m.y, (float)r, ts, tw, th);
+                has = b.x1 > b.x0 && b.y1 > b.y0;
+                cam = camera_ids ? (uint32_t)camera_ids[i] : i / per_cam;
+                depth_bits = __float_as_uint(depths[i]);
+            }
+        }
+        for_each_tile_coop(has, b, tw, [&](int src, uint32_t tile, bool on) {
+            const uint32_t c = __shfl_sync(0xffffffffu, cam, src);
+            const uint32_t d = __shfl_sync(0xffffffffu, depth_bits, src);
+            const uint32_t id = __shfl_sync(0xffffffffu, i, src);
+            if (on) {
+                const int32_t slot = atomicAdd(&s_hist[c * n_tiles + tile], 1);
+                if (slot < capacity) bucket[slot] = ((uint64_t)d << 32) | (uint64_t)id;
+            }
+        });
+    }
+}
+
 // ---- per-tile sort: normalized bitonic network, 64-bit unique keys ------------------------------
 // Every comparison moves the smaller key to the lower index, so +inf padding beyond n never moves.
 // Sub-steps whose partner distance is < 64 stay inside aligned 64-element blocks; a warp keeps such a
@@ -802,6 +904,28 @@ static bool fused_replica_scan() {
     return on;
 }
 static size_t tilesort_total_index(uint32_t T) { return (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1; }
+// CTA-private histograms (isect_count_private_kernel) are opt-in, GSB200_ISECT_PRIVATE=1 (read at every call: a test toggles
+// it): bit-exact like the default, but measured no faster at the headline size -- 183 vs 187 us for the stage
+// (profiles/r2v45_timing_priv*.log); with round-robin ownership a CTA touches ~80 % of the 8160 tiles, so the global atomics
+// only halve (1.9 M (CTA, tile) pairs per pass instead of 4 M intersections) and the row store / reload eats the rest
+static uint32_t private_ctas(uint32_t T, uint32_t n_elems) {
+    const char *v = getenv("GSB200_ISECT_PRIVATE");
+    const bool on = v != nullptr && v[0] == '1';
+    if (!on || T > kPrivMaxTiles || n_elems < 8u * kPrivThreads) return 0;
+    return min(2u * 148u, cdiv(n_elems, (uint32_t)kPrivThreads));
+}
+static size_t private_rows_at(uint32_t T) { return (tilesort_scratch_ints(T) + 3) & ~(size_t)3; }
+static int private_smem_ok() {
+    static int state = -1;  // -1: attributes not set yet
+    if (state < 0) {
+        const int bytes = (int)(kPrivMaxTiles * sizeof(int32_t));
+        const bool ok = cudaFuncSetAttribute(isect_count_private_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess &&
+                        cudaFuncSetAttribute(isect_scatter_private_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess;
+        if (!ok) (void)cudaGetLastError();
+        state = ok ? 1 : 0;
+    }
+    return state;
+}
 
 extern "C" int gsb200_isect_plan(uint32_t C, uint32_t n_elems, uint32_t tile_width, uint32_t tile_height, int64_t *scratch_ints,
                                  int64_t *total_index) {
@@ -811,7 +935,8 @@ extern "C" int gsb200_isect_plan(uint32_t C, uint32_t n_elems, uint32_t tile_wid
         *scratch_ints = (int64_t)P.scratch_ints;
         *total_index = (int64_t)P.total_index;
     } else {
-        *scratch_ints = (int64_t)tilesort_scratch_ints(T);
+        // (+ one row of T counters per CTA of the private-histogram passes, behind everything else)
+        *scratch_ints = (int64_t)(private_rows_at(T) + (size_t)private_ctas(T, n_elems) * T);
         *total_index = (int64_t)tilesort_total_index(T);
     }
     return 0;
@@ -847,9 +972,15 @@ extern "C" int gsb200_isect_prepare(uint32_t C, uint32_t n_elems, uint32_t elems
         return 0;
     }
     GSB_CUDA_OK(cudaMemsetAsync(tile_cursor, 0, sizeof(int32_t) * ((size_t)T * GSB200_ISECT_REPLICAS + 1), s));
-    isect_count_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
-                                                                     camera_ids, means2d, radii, (float)tile_size,
-                                                                     tile_width, tile_height, T, tiles_per_gauss, tile_cursor);
+    const uint32_t priv = private_smem_ok() ? private_ctas(T, n_elems) : 0;
+    if (priv)
+        isect_count_private_kernel<<<priv, kPrivThreads, T * sizeof(int32_t), s>>>(
+            n_elems, elems_per_camera ? elems_per_camera : 1, camera_ids, means2d, radii, (float)tile_size, tile_width, tile_height, T,
+            tiles_per_gauss, tile_cursor, tile_cursor + private_rows_at(T));
+    else
+        isect_count_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
+                                                                         camera_ids, means2d, radii, (float)tile_size,
+                                                                         tile_width, tile_height, T, tiles_per_gauss, tile_cursor);
     if (int e = check_launch("isect_count")) return e;
     // scratch lives at the end of the caller's tile_cursor buffer (a stream-ordered allocation here would
     // go back to the driver after every host synchronisation -- milliseconds)
@@ -909,9 +1040,15 @@ extern "C" int gsb200_isect_fill(uint32_t C, uint32_t n_elems, uint32_t elems_pe
         return ordered_fill(C, n_elems, elems_per_camera, camera_ids, means2d, radii, tile_size, tile_width, tile_height, bound,
                             isect_offsets, tile_cursor, isect_ids, flatten_ids, s);
     const int32_t *total_dev = n_isects < 0 ? tile_cursor + (size_t)(GSB200_ISECT_REPLICAS + 1) * T + 1 : nullptr;
-    isect_scatter_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
-                                                                       camera_ids, means2d, radii, depths, (float)tile_size,
-                                                                       tile_width, tile_height, T, tile_cursor, scratch, bound);
+    const uint32_t priv = private_smem_ok() ? private_ctas(T, n_elems) : 0;
+    if (priv)
+        isect_scatter_private_kernel<<<priv, kPrivThreads, T * sizeof(int32_t), s>>>(
+            n_elems, elems_per_camera ? elems_per_camera : 1, camera_ids, means2d, radii, depths, (float)tile_size, tile_width,
+            tile_height, T, tile_cursor, tile_cursor + private_rows_at(T), scratch, bound);
+    else
+        isect_scatter_kernel<<<cdiv(n_elems, kThreads), kThreads, 0, s>>>(n_elems, elems_per_camera ? elems_per_camera : 1,
+                                                                           camera_ids, means2d, radii, depths, (float)tile_size,
+                                                                           tile_width, tile_height, T, tile_cursor, scratch, bound);
     if (int e = check_launch("isect_scatter")) return e;
     const int32_t *large_list = tile_cursor + (size_t)GSB200_ISECT_REPLICAS * T;
     static const int small_sort = [] {  // 0 depth buckets (default), 1 bitonic network, 2 radix (both opt-in)

@@ -247,6 +247,28 @@ def test_isect_scene_bit_exact(packed):
         assert torch.equal(offs, ref.isect_offset_encode(r_ids, 3, tw, th))
 
 
+@pytest.mark.parametrize("packed", [False, True])
+def test_isect_private_histograms_bit_exact(packed, monkeypatch):
+    """The opt-in CTA-private shared-memory histograms of the count / scatter passes (GSB200_ISECT_PRIVATE=1): same
+    tiles_per_gauss, isect_ids, flatten_ids and offsets as the default path, through the exact call and through the
+    speculative-capacity call that follows it."""
+    means, quats, scales, opac, colors, viewmats, Ks, W, H = [t.to(DEV) if torch.is_tensor(t) else t for t in _scene()]
+    tw, th = math.ceil(W / 16), math.ceil(H / 16)
+    if packed:
+        cam, gid, radii, m2d, dep, con, _ = gs.fully_fused_projection(means, None, quats, scales, viewmats, Ks, W, H, packed=True)
+        kw = dict(packed=True, n_cameras=3, camera_ids=cam, gaussian_ids=gid)
+    else:
+        radii, m2d, dep, con, _ = gs.fully_fused_projection(means, None, quats, scales, viewmats, Ks, W, H)
+        kw = {}
+    monkeypatch.setenv("GSB200_ISECT_PRIVATE", "0")
+    want = _isect_tiles_with_offsets(m2d, radii, dep, 16, tw, th, **kw)
+    monkeypatch.setenv("GSB200_ISECT_PRIVATE", "1")
+    for _ in range(2):  # first call sizes the buffers exactly, the second runs in capacity mode
+        got = _isect_tiles_with_offsets(m2d, radii, dep, 16, tw, th, **kw)
+        for a, b in zip(want, got):
+            assert torch.equal(a, b)
+
+
 def test_isect_empty_and_oversized_tile():
     # nothing visible
     m2d = torch.zeros(1, 10, 2, device=DEV)
