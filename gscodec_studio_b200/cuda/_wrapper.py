@@ -824,7 +824,7 @@ def _round_capacity(n: int) -> int:
     return ((int(n * 1.25) + 4096 + (1 << 18) - 1) >> 18) << 18
 
 
-_isect_capacity = {}  # (device, C, n_elems, tile grid) -> speculative buffer capacity for the next call
+_isect_capacity = {}  # (device, C, tile grid, tile size, packed) -> speculative buffer capacity for the next call
 _pinned = {}
 
 
