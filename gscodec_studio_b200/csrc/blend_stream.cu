@@ -44,7 +44,7 @@ static_assert(kFStageRecs >= 32 && kFStageRecs <= 64 && (kStages * kStageRecs) %
 #define GSB_SBWD_BLOCKS 7  // (backward, NP = 1; the two-record walk, GSB_BWD_PAIR, asks for 5: the launch caps the CTAs at 5 per SM anyway)
 #endif
 #ifndef GSB_SBWD_PAIR_BLOCKS
-#define GSB_SBWD_PAIR_BLOCKS 7  // two-record walk: 68 registers; measured 566 us at 7-8 resident CTAs vs 576 us with 86 registers / 5 CTAs
+#define GSB_SBWD_PAIR_BLOCKS 8  // two-record walk, final kernel: 8 CTAs / 62 registers 495 us, 7 / 69: 515-524, 6 / 76: 512 (tools/gpu_r2_visit50.sh); no spills in any instantiation
 #endif
 #ifndef GSB_PRODUCER_SLEEP_NS
 #define GSB_PRODUCER_SLEEP_NS 256  // ring full: the consumers need ~10^3 cycles per stage
