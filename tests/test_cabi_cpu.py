@@ -350,3 +350,43 @@ def test_quant_on_load_host_logic_without_kernels(monkeypatch):
     assert torch.is_tensor(torch.exp(ex)) and ops.solid(lz) is lz.materialize() and ops.solid(None) is None
     with pytest.raises(ValueError):
         ops.QuantOnLoad(splats["scales"], -10, 2, 8, noise["scales"], activation="tanh")
+
+
+def test_isect_plan_is_host_only_and_sizes_the_private_histogram_rows(monkeypatch):
+    """gsb200_isect_plan makes no CUDA call.  With GSB200_ISECT_PRIVATE=1 (CTA-private tile histograms, opt-in) it
+    appends one row of C x tiles counters per CTA behind the default layout; the intersection count stays where it was;
+    configurations whose histogram does not fit a CTA's shared memory, or that are too small, keep the default size."""
+    import ctypes
+
+    from gscodec_studio_b200 import _cabi
+
+    lib = _cabi.load_library()
+
+    def plan(C, n, tw, th):
+        n_scratch, total_at = ctypes.c_int64(0), ctypes.c_int64(0)
+        assert lib.gsb200_isect_plan(C, n, tw, th, ctypes.byref(n_scratch), ctypes.byref(total_at)) == 0
+        return n_scratch.value, total_at.value
+
+    monkeypatch.delenv("GSB200_ISECT", raising=False)
+    monkeypatch.setenv("GSB200_ISECT_PRIVATE", "0")
+    base, total_at = plan(1, 1_000_000, 120, 68)
+    T = 120 * 68
+    assert total_at == 33 * T + 1 and base > 33 * T + 2
+    monkeypatch.delenv("GSB200_ISECT_PRIVATE")
+    assert plan(1, 1_000_000, 120, 68) == (base, total_at)  # opt-in: off by default
+    monkeypatch.setenv("GSB200_ISECT_PRIVATE", "1")
+    big, total_at1 = plan(1, 1_000_000, 120, 68)
+    assert total_at1 == total_at
+    rows = big - ((base + 3) & ~3)
+    assert rows % T == 0 and rows // T == 2 * 148  # two CTAs per SM
+    assert plan(1, 20_000, 120, 68)[0] - ((base + 3) & ~3) == ((20_000 + 511) // 512) * T  # fewer Gaussians, fewer CTAs
+    assert plan(1, 1000, 120, 68)[0] == base  # too small: default kernels
+    assert plan(8, 1_000_000, 120, 68)[0] == plan(8, 1000, 120, 68)[0]  # 65 280 counters do not fit: default kernels
+
+
+def test_colour_stream_is_cuda_only_and_opt_out(monkeypatch):
+    from gscodec_studio_b200 import rendering
+
+    assert rendering._colour_stream(torch.device("cpu")) is None
+    monkeypatch.setenv("GSB200_COLOR_STREAM", "0")
+    assert rendering._colour_stream(torch.device("cuda", 0)) is None  # (no CUDA call is made on this path)
