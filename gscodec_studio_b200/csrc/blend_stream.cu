@@ -28,8 +28,9 @@ constexpr int kStageRecs = 64;  // records per pipeline stage
 #define GSB_STREAM_STAGES 6
 #endif
 constexpr int kStages = GSB_STREAM_STAGES;
-// The forward's producer hands records to the consumers in smaller stages than the backward's bulk copies: a consumer can
-// start on a stage only when the producer has completed it, and half of the tiles hold fewer than 128 records
+// The forward's ring may use smaller stages than the backward's bulk copies (a consumer can start on a stage only when the
+// producer has completed it, and half of the tiles hold fewer than 128 records).  Measured on B200: 64 / 48 / 32 records per
+// stage all 292-296 us -- 64 stays (tools/gpu_r2_visit43.sh)
 #ifndef GSB_FWD_STAGE_RECS
 #define GSB_FWD_STAGE_RECS 64
 #endif
@@ -41,7 +42,7 @@ static_assert(kFStageRecs >= 32 && kFStageRecs <= 64 && (kStages * kStageRecs) %
 #define GSB_SFWD_BLOCKS 6  // minimum resident CTAs per SM the register allocator must allow (forward, NP = 1)
 #endif
 #ifndef GSB_SBWD_BLOCKS
-#define GSB_SBWD_BLOCKS 7  // (backward, NP = 1; the two-record walk, GSB_BWD_PAIR, asks for 5: the launch caps the CTAs at 5 per SM anyway)
+#define GSB_SBWD_BLOCKS 7  // (backward, NP = 1, one record per trip -- GSB_BWD_PAIR = 0; that walk is launched with a 5-CTA cap, see bwd_t)
 #endif
 #ifndef GSB_SBWD_PAIR_BLOCKS
 #define GSB_SBWD_PAIR_BLOCKS 8  // two-record walk, final kernel: 8 CTAs / 62 registers 495 us, 7 / 69: 515-524, 6 / 76: 512 (tools/gpu_r2_visit50.sh); no spills in any instantiation
