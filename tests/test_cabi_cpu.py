@@ -390,3 +390,30 @@ def test_colour_stream_is_cuda_only_and_opt_out(monkeypatch):
     assert rendering._colour_stream(torch.device("cpu")) is None
     monkeypatch.setenv("GSB200_COLOR_STREAM", "0")
     assert rendering._colour_stream(torch.device("cuda", 0)) is None  # (no CUDA call is made on this path)
+
+
+def test_blend_kernels_carry_the_blackwell_instructions_the_design_names():
+    """SASS census of the shipped stream-blend kernels: the backward stages its record stream with
+    the bulk-copy engine (UBLKCP) on mbarriers (SYNCS), both kernels evaluate pixel pairs in packed FP32 (FFMA2 / FMUL2),
+    the two-record walk shows as 4 EX2 per trip in both kernels (two records x two pixels), and the headline (D = 3)
+    kernels do not spill."""
+    import subprocess
+
+    from gscodec_studio_b200 import _cabi
+
+    out = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    funcs = {}
+    for block in out.stdout.split("Function : ")[1:]:
+        funcs[block.split("\n", 1)[0].strip()] = block
+    bwd = [v for k, v in funcs.items() if "blend_stream_bwd_kernelILi3ELi1ELb0" in k]
+    fwd = [v for k, v in funcs.items() if "blend_stream_fwd_kernelILi3ELi1E" in k]
+    assert len(bwd) == 1 and len(fwd) == 1
+    bwd, fwd = bwd[0], fwd[0]
+    assert "UBLKCP" in bwd and "SYNCS" in bwd and "SYNCS" in fwd
+    for sass in (bwd, fwd):
+        assert sass.count("FFMA2") >= 8 and sass.count("FMUL2") >= 8
+    assert bwd.count("MUFU.EX2") == 4 and bwd.count("MUFU.RCP") >= 4 and bwd.count("SHFL.BFLY") >= 21
+    assert fwd.count("MUFU.EX2") == 4
+    assert "STL" not in bwd and "LDL" not in bwd and "STL" not in fwd and "LDL" not in fwd
