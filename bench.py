@@ -454,6 +454,11 @@ def run_ours(args):
                 "kernel": "blend fwd + bwd (gsb200_rasterize_fwd/_bwd)", "peak_source": "measured" if peaks else "fallback",
                 "algorithmic_bytes": {"fwd": bytes_fwd, "bwd": bytes_bwd},
                 "launch_ms": {"fwd": round(t_fwd, 4), "bwd": round(t_bwd, 4)},
+                # pair rate = I x 256 (pixel, Gaussian) pairs of the reference's tile lists per launch / time -- the
+                # figure that explains the distance to the HBM bound (each pair costs ~1 instruction in these kernels)
+                "pair_rate": {"pairs": int(n_isects) * 256, "unit": "Gpairs/s",
+                              "fwd": round(int(n_isects) * 256 / max(float(t_fwd), 1e-9) / 1e6, 1),
+                              "bwd": round(int(n_isects) * 256 / max(float(t_bwd), 1e-9) / 1e6, 1)},
                 "note": "blend is FP32-issue bound, see DESIGN.md; launch_ms is measured inside the timed region of `value`, "
                         "the other entries of stage_ms in a separate pass of the same step",
             },
