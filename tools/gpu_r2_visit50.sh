@@ -1,5 +1,5 @@
 #!/bin/bash
-# backward pair walk at 8 (62 registers) / 7 (69, shipped) / 6 (76) resident CTAs per SM by launch bounds
+# backward pair walk at 8 (62 registers) / 7 (69, the build of the bench records) / 6 (76) resident CTAs per SM by launch bounds; 8 ships
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 P=gpurun_out/r2v50
