@@ -138,3 +138,44 @@ def test_pair_butterfly_publishes_every_value_once_to_the_right_record():
     red2 = _reduce_spread(tail)
     assert red2[0] == tail[:, 0].sum() and red2[16] == tail[:, 1].sum()
     assert _spread_slot(2, 0) == 0 and _spread_slot(2, 16) == 1
+
+
+def _forward_pixel(alphas, sigmas, colours, words, group):
+    """One pixel of the forward consumer loop (blend_stream_fwd_kernel): records taken `group` at a time, a missing record
+    of the last trip standing in with alpha = 0.  T <= 0 marks a finished pixel (-T is its transmittance)."""
+    T, out, cur = F(1), np.zeros(3, F), 0
+    n = len(alphas)
+    for base in range(0, n, group):
+        trip = []
+        for r in range(group):
+            i = base + r
+            have = i < n
+            j = i if have else base  # (the kernel re-reads the trip's first record)
+            al = min(ALPHA_MAX, alphas[j]) if have else F(0)
+            trip.append((sigmas[j], al, colours[j], words[j]))
+        for sigma, al, c, wt in trip:
+            next_T = F(T * F(F(al * F(-1)) + F(1)))
+            ok = not (sigma < 0 or al < ALPHA_MIN)
+            take = ok and not (next_T <= F(1e-4))
+            vis = F(al * T) if take else F(0)
+            out = (c * vis + out).astype(F)
+            T = next_T if take else (-abs(T) if ok else T)
+            cur = wt if take else cur
+    return T, out, cur
+
+
+def test_forward_walk_in_groups_equals_the_record_by_record_walk():
+    rng = np.random.default_rng(3)
+    for trial in range(30):
+        n = int(rng.integers(1, 90))
+        sig = rng.uniform(-0.1, 5.0, n).astype(F)
+        al = (rng.uniform(0, 1, n) * np.exp(-sig)).astype(F) * np.where(rng.uniform(size=n) > 0.8, F(30), F(1)).astype(F)
+        col = rng.uniform(0, 1, (n, 3)).astype(F)
+        words = [(i << 4) | 0xF for i in range(1, n + 1)]  # never 0
+        ref = _forward_pixel(al, sig, col, words, 1)
+        for group in (2, 3, 4):
+            got = _forward_pixel(al, sig, col, words, group)
+            assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and got[2] == ref[2], (trial, group)
+    # a saturating pixel stops taking and keeps its transmittance negated
+    T, out, cur = _forward_pixel(np.full(40, 0.9, F), np.zeros(40, F), np.ones((40, 3), F), list(range(16, 16 * 41, 16)), 2)
+    assert T < 0 and 0 < -T <= 1e-3 and cur == 16 * 4
